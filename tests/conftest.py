@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+def golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+
+
+@pytest.fixture(params=golden_names())
+def golden(request):
+    import numpy as np
+    z = np.load(os.path.join(GOLDEN_DIR, request.param + ".npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    d["kind"] = str(d["kind"])
+    d["ard"] = bool(d["ard"])
+    d["variance"] = float(d["variance"])
+    d["noise"] = float(d["noise"])
+    d["name"] = request.param
+    return d
