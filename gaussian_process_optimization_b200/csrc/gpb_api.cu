@@ -1,0 +1,870 @@
+// extern "C" surface of libgpb200.so (declared in include/gpb200.h) and the resident-model bookkeeping behind it.
+#include <stdarg.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "gpb_common.cuh"
+#include "gpb_kernels.cuh"
+
+namespace gpb {
+
+static thread_local char g_err[1024] = "";
+long long g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- tiny layout kernels ----------------------------------------------------------------------------------------------
+// Y (n x p row-major) -> Yc[p][np] zero padded
+__global__ void pack_cols_kernel(const double *__restrict__ Y, int n, int p, int np, double *__restrict__ Yc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p * np) return;
+  const int pp = e / np, i = e - pp * np;
+  Yc[e] = (i < n) ? Y[(size_t)i * p + pp] : 0.0;
+}
+// Ac[p][np] -> out (n x p row-major)
+__global__ void unpack_cols_kernel(const double *__restrict__ Ac, int n, int p, int np, double *__restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * p) return;
+  const int i = e / p, pp = e - i * p;
+  out[e] = Ac[(size_t)pp * np + i];
+}
+// dst[i][j] = (j <= i) ? src[i][j] : 0      (i, j < n)
+__global__ void tril_copy_kernel(const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n) return;
+  dst[(size_t)i * ldd + j] = (j <= i) ? src[(size_t)i * lds + j] : 0.0;
+}
+// dst[i][j] = src[max(i,j)][min(i,j)]   (full symmetric from the lower triangle; reads of the upper part are transposed)
+__global__ void sym_copy_kernel(const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd, int n) {
+  __shared__ double t[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (bj <= bi) {
+    for (int r = ty; r < 32; r += 8) {
+      const int i = bi * 32 + r, j = bj * 32 + tx;
+      if (i < n && j < n) {
+        const double v = (j <= i) ? src[(size_t)i * lds + j] : src[(size_t)j * lds + i];
+        dst[(size_t)i * ldd + j] = v;
+      }
+    }
+  } else {
+    // upper tile (bi, bj): read the lower tile (bj, bi) and transpose through shared memory
+    for (int r = ty; r < 32; r += 8) {
+      const int i = bj * 32 + r, j = bi * 32 + tx;
+      t[r][tx] = (i < n && j < n) ? src[(size_t)i * lds + j] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      const int i = bi * 32 + r, j = bj * 32 + tx;
+      if (i < n && j < n) dst[(size_t)i * ldd + j] = t[tx][r];
+    }
+  }
+}
+// dL_dK[i][j] = 0.5 (sum_p a_ip a_jp - P Wi[max][min])      exact_gaussian_inference.py:70
+__global__ void dl_dk_kernel(const double *__restrict__ W, int ldw, const double *__restrict__ alpha, int np, int p, int n,
+                             double *__restrict__ dst, int ldd) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= n) return;
+  double aa = 0.0;
+  for (int pp = 0; pp < p; ++pp) aa = fma(alpha[(size_t)pp * np + i], alpha[(size_t)pp * np + j], aa);
+  const double w = (j <= i) ? W[(size_t)i * ldw + j] : W[(size_t)j * ldw + i];
+  dst[(size_t)i * ldd + j] = 0.5 * (aa - (double)p * w);
+}
+// out = sum_e a[e] b[e], single block, fixed order
+__global__ void dot_kernel(const double *__restrict__ a, const double *__restrict__ b, int n, double *out) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) acc = fma(a[i], b[i], acc);
+  acc = block_sum<1024>(acc, scratch);
+  if (threadIdx.x == 0) *out = acc;
+}
+// dst (np x np) = [src (n x n, lower triangle mirrored) 0; 0 I]
+__global__ void pad_sym_kernel(const double *__restrict__ src, int lds, int n, double *__restrict__ dst, int np) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= np) return;
+  double v;
+  if (i < n && j < n)
+    v = (j <= i) ? src[(size_t)i * lds + j] : src[(size_t)j * lds + i];
+  else
+    v = (i == j) ? 1.0 : 0.0;
+  dst[(size_t)i * np + j] = v;
+}
+
+// ---- RAII device temp ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    GPB_CUDA(cudaMalloc(&p, bytes));
+    return 0;
+  }
+  double *d() { return reinterpret_cast<double *>(p); }
+};
+
+static int to_device(DevBuf &buf, const double *src, size_t count, int dev, const double **out, cudaStream_t s) {
+  if (dev) {
+    *out = src;
+    return 0;
+  }
+  GPB_TRY(buf.alloc(count * sizeof(double)));
+  GPB_CUDA(cudaMemcpyAsync(buf.p, src, count * sizeof(double), cudaMemcpyHostToDevice, s));
+  *out = buf.d();
+  return 0;
+}
+
+// lengthscale (nls = d or 1) -> device arrays ls[d], inv_ls[d]
+static int upload_ls(const double *ls, int nls, int d, double *ls_dev, double *inv_ls_dev, cudaStream_t s) {
+  std::vector<double> h(2 * d);
+  for (int q = 0; q < d; ++q) {
+    h[q] = ls[nls == 1 ? 0 : q];
+    h[d + q] = 1.0 / h[q];
+  }
+  GPB_CUDA(cudaMemcpyAsync(ls_dev, h.data(), d * sizeof(double), cudaMemcpyHostToDevice, s));
+  GPB_CUDA(cudaMemcpyAsync(inv_ls_dev, h.data() + d, d * sizeof(double), cudaMemcpyHostToDevice, s));
+  GPB_CUDA(cudaStreamSynchronize(s));  // h goes out of scope
+  return 0;
+}
+
+}  // namespace gpb
+
+using namespace gpb;
+
+// =====================================================================================================================
+// model
+// =====================================================================================================================
+struct gpb_model {
+  int kind = 0, ard = 1, d = 0, p = 1, n_cap = 0, np_cap = 0, cb = 0, nls = 0;
+  int n = 0, np = 0;
+  double variance = 1.0, noise = 1.0, jitter = 0.0;
+  std::vector<double> ls;
+  bool have_data = false, scaled_valid = false, fitted = false, have_wi = false;
+  cudaStream_t stream = 0;
+  void *ws = nullptr;
+  bool own_ws = false;
+  Factor f;
+  // device arrays (carved from ws)
+  double *X = nullptr, *XsT = nullptr, *Yc = nullptr, *alpha = nullptr, *z = nullptr, *ls_dev = nullptr, *inv_ls_dev = nullptr;
+  double *scal = nullptr;  // [0] logdet [1] alpha.Y [2..] kgrad outputs (d + 2)
+  double *gpart = nullptr;
+  // candidate-block buffers
+  double *Xc = nullptr, *XcT = nullptr, *KxT = nullptr, *Vt = nullptr, *Ut = nullptr, *mu = nullptr, *var = nullptr, *dmu = nullptr,
+         *dvar = nullptr, *fbuf = nullptr, *dfbuf = nullptr, *sdbuf = nullptr, *dsbuf = nullptr;
+  double *topv = nullptr;
+  long long *topi = nullptr;
+  double *pinned = nullptr;  // host, 256 doubles
+};
+
+static size_t carve(int n_cap, int d, int p, int cb, gpb_model *m, char *base) {
+  const size_t np = round_up(std::max(n_cap, 1), TILE);
+  const size_t nb = np / TILE;
+  size_t off = 0;
+  auto take = [&](size_t count, double **dst) {
+    if (m && dst) *dst = reinterpret_cast<double *>(base + off);
+    off += align256(count * sizeof(double));
+  };
+  double *fa = nullptr, *fm = nullptr, *fw = nullptr, *fpart = nullptr;
+  take(np * np, &fa);
+  take(np * np, &fm);
+  take(np * np, &fw);
+  take(nb * np, &fpart);
+  take(nb * (nb + 1) / 2 * (size_t)(d + 2), m ? &m->gpart : nullptr);
+  take(np * (size_t)d, m ? &m->X : nullptr);
+  take(np * (size_t)d, m ? &m->XsT : nullptr);
+  take(np * (size_t)p, m ? &m->Yc : nullptr);
+  take(np * (size_t)p, m ? &m->alpha : nullptr);
+  take(np * (size_t)p, m ? &m->z : nullptr);
+  take(d, m ? &m->ls_dev : nullptr);
+  take(d, m ? &m->inv_ls_dev : nullptr);
+  take(d + 16, m ? &m->scal : nullptr);
+  take((size_t)cb * d, m ? &m->Xc : nullptr);
+  take((size_t)cb * d, m ? &m->XcT : nullptr);
+  take((size_t)cb * np, m ? &m->KxT : nullptr);
+  take((size_t)cb * np, m ? &m->Vt : nullptr);
+  take((size_t)cb * np, m ? &m->Ut : nullptr);
+  take((size_t)cb * p, m ? &m->mu : nullptr);
+  take(cb, m ? &m->var : nullptr);
+  take((size_t)cb * d, m ? &m->dmu : nullptr);
+  take((size_t)cb * d, m ? &m->dvar : nullptr);
+  take(cb, m ? &m->fbuf : nullptr);
+  take((size_t)cb * d, m ? &m->dfbuf : nullptr);
+  take(cb, m ? &m->sdbuf : nullptr);
+  take((size_t)cb * d, m ? &m->dsbuf : nullptr);
+  take(64, m ? &m->topv : nullptr);
+  double *ti = nullptr;
+  take(64, &ti);
+  double *finfo = nullptr;
+  take(4, &finfo);
+  if (m) {
+    m->f.A = fa;
+    m->f.Mi = fm;
+    m->f.W = fw;
+    m->f.part = fpart;
+    m->topi = reinterpret_cast<long long *>(ti);
+    m->f.info = reinterpret_cast<int *>(finfo);
+  }
+  return off;
+}
+
+extern "C" {
+
+int gpb_version(void) { return 100; }
+const char *gpb_last_error(void) { return g_err; }
+long long gpb_launch_count(void) { return g_launches; }
+int gpb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+size_t gpb_model_workspace_bytes(int n_cap, int d, int p, int cand_block) {
+  if (n_cap < 1 || d < 1 || p < 1 || cand_block < 1) return 0;
+  return carve(n_cap, d, p, round_up(cand_block, TILE), nullptr, nullptr);
+}
+
+int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap, int cand_block, void *workspace,
+                     size_t workspace_bytes, void *stream) {
+  GPB_REQUIRE(out != nullptr, "model_create: out is NULL");
+  GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "model_create: unknown kernel kind %d", kind);
+  GPB_REQUIRE(d >= 1 && d <= 96, "model_create: input_dim %d out of range [1, 96]", d);
+  GPB_REQUIRE(p >= 1 && p <= 16, "model_create: output_dim %d out of range [1, 16]", p);
+  GPB_REQUIRE(n_cap >= 1 && cand_block >= 1, "model_create: capacities must be positive");
+  GPB_REQUIRE(gpb_device_count() > 0, "model_create: no CUDA device visible -- libgpb200 has no CPU fallback");
+  gpb_model *m = new gpb_model();
+  m->kind = kind;
+  m->ard = ard ? 1 : 0;
+  m->d = d;
+  m->p = p;
+  m->n_cap = n_cap;
+  m->np_cap = round_up(n_cap, TILE);
+  m->cb = round_up(cand_block, TILE);
+  m->nls = ard ? d : 1;
+  m->ls.assign(m->nls, 1.0);
+  m->stream = reinterpret_cast<cudaStream_t>(stream);
+  const size_t need = carve(n_cap, d, p, m->cb, nullptr, nullptr);
+  if (workspace) {
+    if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+      delete m;
+      set_error("model_create: workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, need);
+      return -2;
+    }
+    m->ws = workspace;
+  } else {
+    cudaError_t e = cudaMalloc(&m->ws, need);
+    if (e != cudaSuccess) {
+      delete m;
+      set_error("model_create: cudaMalloc(%zu) -> %s", need, cudaGetErrorString(e));
+      return -1;
+    }
+    m->own_ws = true;
+  }
+  carve(n_cap, d, p, m->cb, m, reinterpret_cast<char *>(m->ws));
+  m->f.stream = m->stream;
+  if (cudaMallocHost(&m->pinned, 256 * sizeof(double)) != cudaSuccess) {
+    if (m->own_ws) cudaFree(m->ws);
+    delete m;
+    set_error("model_create: cudaMallocHost failed");
+    return -1;
+  }
+  *out = m;
+  return 0;
+}
+
+int gpb_model_destroy(gpb_model *m) {
+  if (!m) return 0;
+  cudaStreamSynchronize(m->stream);
+  if (m->own_ws && m->ws) cudaFree(m->ws);
+  if (m->pinned) cudaFreeHost(m->pinned);
+  delete m;
+  return 0;
+}
+
+int gpb_model_set_data(gpb_model *m, int n, const double *X, const double *Y, int dev) {
+  GPB_REQUIRE(m && X && Y, "set_data: NULL argument");
+  GPB_REQUIRE(n >= 1 && n <= m->n_cap, "set_data: n = %d exceeds the model capacity %d", n, m->n_cap);
+  m->n = n;
+  m->np = round_up(n, TILE);
+  m->f.n = n;
+  m->f.np = m->np;
+  const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  GPB_CUDA(cudaMemcpyAsync(m->X, X, (size_t)n * m->d * sizeof(double), kind, m->stream));
+  // Y -> column blocks; stage the row-major copy in z (same size class) first when it comes from the host
+  DevBuf tmp;
+  const double *Yd = nullptr;
+  GPB_TRY(to_device(tmp, Y, (size_t)n * m->p, dev, &Yd, m->stream));
+  pack_cols_kernel<<<(m->p * m->np + 255) / 256, 256, 0, m->stream>>>(Yd, n, m->p, m->np, m->Yc);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  GPB_CUDA(cudaStreamSynchronize(m->stream));
+  m->have_data = true;
+  m->scaled_valid = false;
+  m->fitted = false;
+  m->have_wi = false;
+  return 0;
+}
+
+int gpb_model_set_theta(gpb_model *m, double variance, const double *lengthscale, double noise) {
+  GPB_REQUIRE(m && lengthscale, "set_theta: NULL argument");
+  m->variance = variance;
+  m->noise = noise;
+  for (int q = 0; q < m->nls; ++q) m->ls[q] = lengthscale[q];
+  m->scaled_valid = false;
+  m->fitted = false;
+  m->have_wi = false;
+  return 0;
+}
+
+static int ensure_scaled(gpb_model *m) {
+  if (m->scaled_valid) return 0;
+  GPB_TRY(upload_ls(m->ls.data(), m->nls, m->d, m->ls_dev, m->inv_ls_dev, m->stream));
+  GPB_TRY(launch_scale_transpose(m->X, m->n, m->d, m->ls_dev, m->XsT, m->np, m->stream));
+  m->scaled_valid = true;
+  return 0;
+}
+
+static int ensure_wi(gpb_model *m) {
+  if (m->have_wi) return 0;
+  GPB_TRY(factor_potri(m->f));
+  m->have_wi = true;
+  return 0;
+}
+
+int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out) {
+  GPB_REQUIRE(m && out, "fit: NULL argument");
+  GPB_REQUIRE(m->have_data, "fit: set_data has not been called");
+  GPB_REQUIRE(m->variance > 0 && m->noise >= 0, "fit: variance must be > 0 and noise >= 0");
+  for (int q = 0; q < m->nls; ++q) GPB_REQUIRE(m->ls[q] > 0, "fit: lengthscale[%d] must be > 0", q);
+  m->fitted = false;
+  m->have_wi = false;
+  m->jitter = extra_jitter;
+  GPB_TRY(ensure_scaled(m));
+  const int n = m->n, np = m->np, d = m->d, p = m->p;
+  // Ky = K + (noise + 1e-8 [+ jitter]) I     exact_gaussian_inference.py:55-56
+  GPB_TRY(launch_kmat(m->kind, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->noise + 1e-8 + extra_jitter, 1, m->f.A, np, np,
+                      np, m->stream));
+  GPB_TRY(factor_potrf_inv(m->f));
+  GPB_TRY(factor_solve(m->f, m->Yc, p, m->z, m->alpha));
+  GPB_TRY(factor_logdet(m->f, m->scal + 0));
+  dot_kernel<<<1, 1024, 0, m->stream>>>(m->alpha, m->Yc, p * np, m->scal + 1);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  if (want_grad) {
+    GPB_TRY(ensure_wi(m));
+    GPB_TRY(launch_kgrad(m->kind, 1, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->f.W, np, m->alpha, np, p, m->gpart,
+                         m->scal + 2, m->stream));
+  }
+  GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 4) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  GPB_CUDA(cudaMemcpyAsync(m->pinned + 128, m->f.info, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  GPB_CUDA(cudaStreamSynchronize(m->stream));
+  const int info = *reinterpret_cast<int *>(m->pinned + 128);
+  if (info != 0) {
+    set_error("fit: matrix not positive definite (leading minor %d)", info);
+    return info > n ? n : info;
+  }
+  const double logdet = m->pinned[0], ay = m->pinned[1];
+  out[0] = 0.5 * (-(double)n * p * log(2.0 * M_PI) - (double)p * logdet - ay);  // exact_gaussian_inference.py:62
+  if (want_grad) {
+    const double *g = m->pinned + 2;
+    out[1] = g[0] / m->variance;                          // stationary.py:224
+    if (m->ard) {
+      for (int q = 0; q < d; ++q) out[2 + q] = -g[2 + q] / m->ls[q];   // stationary.py:233,268 in scaled coordinates
+    } else {
+      double sacc = 0.0;
+      for (int q = 0; q < d; ++q) sacc += g[2 + q];
+      out[2] = -sacc / m->ls[0];                         // stationary.py:237-238
+    }
+    out[2 + m->nls] = g[1];                               // exact_gaussian_inference.py:72, gaussian.py:78-79
+  }
+  m->fitted = true;
+  return 0;
+}
+
+int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) {
+  GPB_REQUIRE(m && what && dst, "get: NULL argument");
+  const std::string w(what);
+  const int n = m->n, np = m->np, p = m->p;
+  cudaStream_t s = m->stream;
+  const bool is_mat = (w == "L" || w == "Li" || w == "Wi" || w == "K" || w == "dL_dK");
+  GPB_REQUIRE(is_mat || w == "alpha", "get: unknown quantity '%s'", what);
+  if (w != "K") GPB_REQUIRE(m->fitted, "get: model has not been fitted");
+  const int cols = is_mat ? n : p;
+  GPB_REQUIRE(ld >= cols, "get: ld too small");
+  DevBuf tmp;
+  double *ddst = dst;
+  int ldd = ld;
+  if (!dev) {
+    GPB_TRY(tmp.alloc((size_t)n * cols * sizeof(double)));
+    ddst = tmp.d();
+    ldd = cols;
+  }
+  const dim3 grid((n + 255) / 256, n), gsym((n + 31) / 32, (n + 31) / 32);
+  if (w == "L") {
+    tril_copy_kernel<<<grid, 256, 0, s>>>(m->f.A, np, ddst, ldd, n);
+  } else if (w == "Li") {
+    tril_copy_kernel<<<grid, 256, 0, s>>>(m->f.Mi, np, ddst, ldd, n);
+  } else if (w == "Wi") {
+    GPB_TRY(ensure_wi(m));
+    sym_copy_kernel<<<gsym, dim3(32, 8), 0, s>>>(m->f.W, np, ddst, ldd, n);
+  } else if (w == "dL_dK") {
+    GPB_TRY(ensure_wi(m));
+    dl_dk_kernel<<<grid, 256, 0, s>>>(m->f.W, np, m->alpha, np, p, n, ddst, ldd);
+  } else if (w == "K") {
+    GPB_REQUIRE(m->have_data, "get: no data");
+    GPB_TRY(ensure_scaled(m));
+    GPB_TRY(launch_kmat(m->kind, m->XsT, np, m->XsT, np, m->d, n, n, m->variance, 0.0, 0, ddst, ldd, np, np, s));
+  } else {
+    unpack_cols_kernel<<<(n * p + 255) / 256, 256, 0, s>>>(m->alpha, n, p, np, ddst);
+  }
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  if (!dev) {
+    GPB_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(double), ddst, (size_t)ldd * sizeof(double), (size_t)cols * sizeof(double),
+                               n, cudaMemcpyDeviceToHost, s));
+  }
+  GPB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ---- predictive pipeline over one candidate block -------------------------------------------------------------------
+// level 0: mean only; 1: + variance; 2: + gradients (dmu, dvar)
+static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int level, int include_likelihood) {
+  const int n = m->n, np = m->np, d = m->d, p = m->p;
+  const int cpad = round_up(mcb, TILE);
+  cudaStream_t s = m->stream;
+  GPB_CUDA(cudaMemcpyAsync(m->Xc, Xc, (size_t)mcb * d * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  GPB_TRY(launch_scale_transpose(m->Xc, mcb, d, m->ls_dev, m->XcT, cpad, s));
+  // KxT[c][n] = k(x*_c, x_n)                                        posterior.py:275 (stored transposed)
+  GPB_TRY(launch_kmat(m->kind, m->XcT, cpad, m->XsT, np, d, mcb, n, m->variance, 0.0, 2, m->KxT, np, cpad, np, s));
+  // mu = Kx^T alpha                                                 posterior.py:276
+  GPB_TRY(launch_rowdot(m->KxT, np, mcb, n, m->alpha, np, p, m->mu, s));
+  if (level >= 1) {
+    // Vt = KxT M^T  (== (L^-1 Kx)^T: dtrtrs of posterior.py:293 as a product with the explicit inverse factor)
+    GemmArgs g{m->KxT, np, m->f.Mi, np, m->Vt, np, cpad, np, np, 1.0, 0.0, 0, 0, 2};
+    GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, s));
+    // var = Kdiag - sum(tmp^2) (+ noise)                            posterior.py:294-295, gaussian.py:109
+    GPB_TRY(launch_var_from_vt(m->Vt, np, mcb, n, m->variance + (include_likelihood ? m->noise : 0.0), m->var, s));
+  }
+  if (level >= 2) {
+    GPB_REQUIRE(p == 1, "predictive gradients are implemented for a single output column (got %d)", p);
+    // Ut = Vt M = (Ky^-1 Kx)^T                                      core/gp.py:450-451 (woodbury_inv product as 2nd triangular product)
+    GemmArgs g{m->Vt, np, m->f.Mi, np, m->Ut, np, cpad, np, np, 1.0, 0.0, 0, 2, 0};
+    GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, s));
+    // dmu = gradients_X(alpha^T, X*, X); dvar = gradients_X(-2 Kx^T Wi, X*, X)     core/gp.py:431-434,450-453
+    GPB_TRY(launch_gradx(m->kind, m->XcT, cpad, mcb, m->XsT, np, n, d, m->variance, m->inv_ls_dev, m->alpha, 0, 1.0, 0, m->Ut, np,
+                         -2.0, m->dmu, m->dvar, d, s));
+  }
+  return 0;
+}
+
+static int copy_out(double *dst, const double *src_dev, size_t count, int dev, cudaStream_t s) {
+  if (!dst) return 0;
+  GPB_CUDA(cudaMemcpyAsync(dst, src_dev, count * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+int gpb_model_predict(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *var, int dev) {
+  GPB_REQUIRE(m && Xc, "predict: NULL argument");
+  GPB_REQUIRE(m->fitted, "predict: model has not been fitted");
+  GPB_REQUIRE(mc >= 0, "predict: negative candidate count");
+  for (int c0 = 0; c0 < mc; c0 += m->cb) {
+    const int mcb = std::min(m->cb, mc - c0);
+    GPB_TRY(predict_block(m, Xc + (size_t)c0 * m->d, mcb, dev, var ? 1 : 0, include_likelihood));
+    GPB_TRY(copy_out(mu ? mu + (size_t)c0 * m->p : nullptr, m->mu, (size_t)mcb * m->p, dev, m->stream));
+    GPB_TRY(copy_out(var ? var + c0 : nullptr, m->var, mcb, dev, m->stream));
+    if (!dev) GPB_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  GPB_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *cov, int dev) {
+  GPB_REQUIRE(m && Xc && cov, "predict_full_cov: NULL argument");
+  GPB_REQUIRE(m->fitted, "predict_full_cov: model has not been fitted");
+  GPB_REQUIRE(mc >= 1 && mc <= m->cb, "predict_full_cov: mc = %d exceeds the candidate block %d", mc, m->cb);
+  const int cpad = round_up(mc, TILE), np = m->np;
+  cudaStream_t s = m->stream;
+  GPB_TRY(predict_block(m, Xc, mc, dev, 1, include_likelihood));
+  // cov = Kxx - tmp^T tmp (+ noise I)      posterior.py:281-284, gaussian.py:104-107
+  DevBuf cbuf;
+  GPB_TRY(cbuf.alloc((size_t)cpad * cpad * sizeof(double)));
+  GPB_TRY(launch_kmat(m->kind, m->XcT, cpad, m->XcT, cpad, m->d, mc, mc, m->variance, include_likelihood ? m->noise : 0.0, 1,
+                      cbuf.d(), cpad, cpad, cpad, s));
+  GemmArgs g{m->Vt, np, m->Vt, np, cbuf.d(), cpad, cpad, cpad, np, -1.0, 1.0, 0, 0, 0};
+  GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, s));
+  GPB_TRY(copy_out(mu, m->mu, (size_t)mc * m->p, dev, s));
+  GPB_CUDA(cudaMemcpy2DAsync(cov, (size_t)mc * sizeof(double), cbuf.d(), (size_t)cpad * sizeof(double), (size_t)mc * sizeof(double), mc,
+                             dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int gpb_model_predictive_gradients(gpb_model *m, int mc, const double *Xc, double *dmu, double *dvar, int dev) {
+  GPB_REQUIRE(m && Xc, "predictive_gradients: NULL argument");
+  GPB_REQUIRE(m->fitted, "predictive_gradients: model has not been fitted");
+  for (int c0 = 0; c0 < mc; c0 += m->cb) {
+    const int mcb = std::min(m->cb, mc - c0);
+    GPB_TRY(predict_block(m, Xc + (size_t)c0 * m->d, mcb, dev, 2, 0));
+    GPB_TRY(copy_out(dmu ? dmu + (size_t)c0 * m->d : nullptr, m->dmu, (size_t)mcb * m->d, dev, m->stream));
+    GPB_TRY(copy_out(dvar ? dvar + (size_t)c0 * m->d : nullptr, m->dvar, (size_t)mcb * m->d, dev, m->stream));
+    if (!dev) GPB_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  GPB_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int gpb_model_fmin(gpb_model *m, double *fmin) {
+  GPB_REQUIRE(m && fmin, "fmin: NULL argument");
+  GPB_REQUIRE(m->fitted, "fmin: model has not been fitted");
+  GPB_REQUIRE(m->p == 1, "fmin: single output only");
+  // model.predict(model.X)[0].min()   gpmodel.py:125-129 -- only the mean is used, so the variance solve is skipped
+  double best = INFINITY;
+  for (int c0 = 0; c0 < m->n; c0 += m->cb) {
+    const int mcb = std::min(m->cb, m->n - c0);
+    GPB_TRY(predict_block(m, m->X + (size_t)c0 * m->d, mcb, 1, 0, 1));
+    GPB_TRY(launch_min(m->mu, mcb, m->scal + 0, m->stream));
+    GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    GPB_CUDA(cudaStreamSynchronize(m->stream));
+    best = std::min(best, m->pinned[0]);
+  }
+  *fmin = best;
+  return 0;
+}
+
+int gpb_model_acquisition(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df,
+                          double *mean, double *sd, double *dmdx, double *dsdx, int dev) {
+  GPB_REQUIRE(m && Xc, "acquisition: NULL argument");
+  GPB_REQUIRE(m->fitted, "acquisition: model has not been fitted");
+  GPB_REQUIRE(acq == GPB_ACQ_EI || acq == GPB_ACQ_LCB, "acquisition: unknown type %d", acq);
+  GPB_REQUIRE(m->p == 1, "acquisition: single output only");
+  const bool grad = df || dmdx || dsdx;
+  const int d = m->d;
+  for (int c0 = 0; c0 < mc; c0 += m->cb) {
+    const int mcb = std::min(m->cb, mc - c0);
+    GPB_TRY(predict_block(m, Xc + (size_t)c0 * d, mcb, dev, grad ? 2 : 1, 1));
+    GPB_TRY(launch_acq_epilogue(acq, par, fmin, mcb, d, m->mu, m->var, grad ? m->dmu : nullptr, grad ? m->dvar : nullptr, m->fbuf,
+                                m->dfbuf, nullptr, m->sdbuf, nullptr, m->dsbuf, m->stream));
+    GPB_TRY(copy_out(f ? f + c0 : nullptr, m->fbuf, mcb, dev, m->stream));
+    GPB_TRY(copy_out(mean ? mean + c0 : nullptr, m->mu, mcb, dev, m->stream));
+    GPB_TRY(copy_out(sd ? sd + c0 : nullptr, m->sdbuf, mcb, dev, m->stream));
+    if (grad) {
+      GPB_TRY(copy_out(df ? df + (size_t)c0 * d : nullptr, m->dfbuf, (size_t)mcb * d, dev, m->stream));
+      GPB_TRY(copy_out(dmdx ? dmdx + (size_t)c0 * d : nullptr, m->dmu, (size_t)mcb * d, dev, m->stream));
+      GPB_TRY(copy_out(dsdx ? dsdx + (size_t)c0 * d : nullptr, m->dsbuf, (size_t)mcb * d, dev, m->stream));
+    }
+    if (!dev) GPB_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  GPB_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
+                       long long index_offset, double *vals, long long *idx, double *pts) {
+  GPB_REQUIRE(m && Xc && vals && idx, "acq_topk: NULL argument");
+  GPB_REQUIRE(m->fitted, "acq_topk: model has not been fitted");
+  GPB_REQUIRE(k >= 1 && k <= 64 && k <= mc, "acq_topk: k = %d must be in [1, min(64, mc)]", k);
+  GPB_REQUIRE(m->p == 1, "acq_topk: single output only");
+  const int d = m->d;
+  cudaStream_t s = m->stream;
+  GPB_TRY(launch_topk_init(m->topv, m->topi, k, s));
+  for (int c0 = 0; c0 < mc; c0 += m->cb) {
+    const int mcb = std::min(m->cb, mc - c0);
+    GPB_TRY(predict_block(m, Xc + (size_t)c0 * d, mcb, dev, 1, 1));
+    GPB_TRY(launch_acq_epilogue(acq, par, fmin, mcb, d, m->mu, m->var, nullptr, nullptr, m->fbuf, nullptr, nullptr, nullptr, nullptr,
+                                nullptr, s));
+    GPB_TRY(launch_topk_update(m->fbuf, mcb, index_offset + c0, m->topv, m->topi, k, s));
+    if (!dev) GPB_CUDA(cudaStreamSynchronize(s));  // the host block may be reused by the caller's next copy
+  }
+  GPB_CUDA(cudaMemcpyAsync(m->pinned, m->topv, k * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaMemcpyAsync(m->pinned + 64, m->topi, k * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < k; ++i) {
+    vals[i] = m->pinned[i];
+    idx[i] = reinterpret_cast<long long *>(m->pinned + 64)[i];
+  }
+  if (pts) {
+    for (int i = 0; i < k; ++i) {
+      const long long local = idx[i] - index_offset;
+      GPB_CUDA(cudaMemcpy(pts + (size_t)i * d, Xc + (size_t)local * d, d * sizeof(double),
+                          dev ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+    }
+  }
+  return 0;
+}
+
+// =====================================================================================================================
+// Kern contract (stateless)
+// =====================================================================================================================
+struct KernTmp {
+  DevBuf xa, xb, ls, xat, xbt;
+  const double *Xa = nullptr, *Xb = nullptr;
+  double *XaT = nullptr, *XbT = nullptr, *ls_dev = nullptr, *inv_ls_dev = nullptr;
+  int npa = 0, npb = 0;
+};
+
+static int kern_prepare(KernTmp &t, int d, int n, const double *X, int m, const double *X2, const double *ls, int nls, int dev,
+                        cudaStream_t s) {
+  GPB_REQUIRE(X && ls && d >= 1 && d <= 96 && n >= 1, "kern: bad arguments");
+  GPB_REQUIRE(nls == 1 || nls == d, "kern: lengthscale must have 1 or input_dim entries (got %d)", nls);
+  GPB_REQUIRE(gpb_device_count() > 0, "kern: no CUDA device visible -- libgpb200 has no CPU fallback");
+  t.npa = round_up(n, TILE);
+  GPB_TRY(to_device(t.xa, X, (size_t)n * d, dev, &t.Xa, s));
+  GPB_TRY(t.ls.alloc(2 * d * sizeof(double)));
+  t.ls_dev = t.ls.d();
+  t.inv_ls_dev = t.ls.d() + d;
+  GPB_TRY(upload_ls(ls, nls, d, t.ls_dev, t.inv_ls_dev, s));
+  GPB_TRY(t.xat.alloc((size_t)d * t.npa * sizeof(double)));
+  t.XaT = t.xat.d();
+  GPB_TRY(launch_scale_transpose(t.Xa, n, d, t.ls_dev, t.XaT, t.npa, s));
+  if (X2) {
+    GPB_REQUIRE(m >= 1, "kern: X2 given with m = %d", m);
+    t.npb = round_up(m, TILE);
+    GPB_TRY(to_device(t.xb, X2, (size_t)m * d, dev, &t.Xb, s));
+    GPB_TRY(t.xbt.alloc((size_t)d * t.npb * sizeof(double)));
+    t.XbT = t.xbt.d();
+    GPB_TRY(launch_scale_transpose(t.Xb, m, d, t.ls_dev, t.XbT, t.npb, s));
+  } else {
+    t.npb = t.npa;
+    t.XbT = t.XaT;
+  }
+  return 0;
+}
+
+int gpb_kern_K(int kind, int d, int n, const double *X, int m, const double *X2, double variance, const double *lengthscale,
+               int nls, double *K, int ldk, int dev, void *stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GPB_REQUIRE(K != nullptr, "kern_K: K is NULL");
+  GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "kern_K: unknown kernel kind %d", kind);
+  KernTmp t;
+  GPB_TRY(kern_prepare(t, d, n, X, m, X2, lengthscale, nls, dev, s));
+  const int cols = X2 ? m : n;
+  GPB_REQUIRE(ldk >= cols, "kern_K: ldk too small");
+  DevBuf out;
+  double *Kd = K;
+  int ld = ldk;
+  if (!dev) {
+    GPB_TRY(out.alloc((size_t)n * cols * sizeof(double)));
+    Kd = out.d();
+    ld = cols;
+  }
+  GPB_TRY(launch_kmat(kind, t.XaT, t.npa, t.XbT, t.npb, d, n, cols, variance, 0.0, 0, Kd, ld, t.npa, t.npb, s));
+  if (!dev)
+    GPB_CUDA(cudaMemcpy2DAsync(K, (size_t)ldk * sizeof(double), Kd, (size_t)ld * sizeof(double), (size_t)cols * sizeof(double), n,
+                               cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
+                                   double variance, const double *lengthscale, int nls, double *out, int dev, void *stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GPB_REQUIRE(dL_dK && out, "update_gradients_full: NULL argument");
+  GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "update_gradients_full: unknown kernel kind %d", kind);
+  KernTmp t;
+  GPB_TRY(kern_prepare(t, d, n, X, m, X2, lengthscale, nls, dev, s));
+  const int cols = X2 ? m : n;
+  GPB_REQUIRE(ld >= cols, "update_gradients_full: ld too small");
+  DevBuf gbuf, part, res;
+  const double *G = dL_dK;
+  int ldg = ld;
+  if (!dev) {
+    GPB_TRY(gbuf.alloc((size_t)n * cols * sizeof(double)));
+    GPB_CUDA(cudaMemcpy2DAsync(gbuf.p, (size_t)cols * sizeof(double), dL_dK, (size_t)ld * sizeof(double), (size_t)cols * sizeof(double), n,
+                               cudaMemcpyHostToDevice, s));
+    G = gbuf.d();
+    ldg = cols;
+  }
+  const size_t tiles = (size_t)(t.npa / TILE) * (t.npb / TILE);
+  GPB_TRY(part.alloc(tiles * (d + 2) * sizeof(double)));
+  GPB_TRY(res.alloc((d + 2) * sizeof(double)));
+  GPB_TRY(launch_kgrad(kind, 0, t.XaT, t.npa, t.XbT, t.npb, d, n, cols, variance, G, ldg, nullptr, 0, 1, part.d(), res.d(), s));
+  std::vector<double> h(d + 2);
+  GPB_CUDA(cudaMemcpyAsync(h.data(), res.p, (d + 2) * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  out[0] = h[0] / variance;
+  if (nls == d) {
+    for (int q = 0; q < d; ++q) out[1 + q] = -h[2 + q] / lengthscale[q];  // stationary.py:233,268 (scaled coordinates)
+  } else {
+    double acc = 0.0;
+    for (int q = 0; q < d; ++q) acc += h[2 + q];
+    out[1] = -acc / lengthscale[0];                                       // stationary.py:237-238
+  }
+  return 0;
+}
+
+int gpb_kern_gradients_X(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
+                         double variance, const double *lengthscale, int nls, double *out, int dev, void *stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GPB_REQUIRE(dL_dK && out, "gradients_X: NULL argument");
+  GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "gradients_X: unknown kernel kind %d", kind);
+  KernTmp t;
+  GPB_TRY(kern_prepare(t, d, n, X, m, X2, lengthscale, nls, dev, s));
+  const int cols = X2 ? m : n;
+  GPB_REQUIRE(ld >= cols, "gradients_X: ld too small");
+  DevBuf gbuf, obuf;
+  const double *G = dL_dK;
+  int ldg = ld;
+  if (!dev) {
+    GPB_TRY(gbuf.alloc((size_t)n * cols * sizeof(double)));
+    GPB_CUDA(cudaMemcpy2DAsync(gbuf.p, (size_t)cols * sizeof(double), dL_dK, (size_t)ld * sizeof(double), (size_t)cols * sizeof(double), n,
+                               cudaMemcpyHostToDevice, s));
+    G = gbuf.d();
+    ldg = cols;
+  }
+  double *od = out;
+  if (!dev) {
+    GPB_TRY(obuf.alloc((size_t)n * d * sizeof(double)));
+    od = obuf.d();
+  }
+  GPB_TRY(launch_gradx(kind, t.XaT, t.npa, n, t.XbT, t.npb, cols, d, variance, t.inv_ls_dev, G, ldg, 1.0, X2 ? 0 : 1, nullptr, 0, 0.0,
+                       od, nullptr, d, s));
+  if (!dev) GPB_CUDA(cudaMemcpyAsync(out, od, (size_t)n * d * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// =====================================================================================================================
+// util.linalg
+// =====================================================================================================================
+int gpb_pdinv(int n, const double *A, int lda, double *L, double *Ai, double *Li, double *logdet, int dev, void *stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GPB_REQUIRE(A && n >= 1 && lda >= n, "pdinv: bad arguments");
+  GPB_REQUIRE(gpb_device_count() > 0, "pdinv: no CUDA device visible -- libgpb200 has no CPU fallback");
+  const int np = round_up(n, TILE), nb = np / TILE;
+  DevBuf ain, a, mi, w, part, misc, outb;
+  const double *Ad = A;
+  int ldad = lda;
+  if (!dev) {
+    GPB_TRY(ain.alloc((size_t)n * n * sizeof(double)));
+    GPB_CUDA(cudaMemcpy2DAsync(ain.p, (size_t)n * sizeof(double), A, (size_t)lda * sizeof(double), (size_t)n * sizeof(double), n,
+                               cudaMemcpyHostToDevice, s));
+    Ad = ain.d();
+    ldad = n;
+  }
+  GPB_TRY(a.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(mi.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(w.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(part.alloc((size_t)nb * np * sizeof(double)));
+  GPB_TRY(misc.alloc(64));
+  Factor f;
+  f.n = n;
+  f.np = np;
+  f.A = a.d();
+  f.Mi = mi.d();
+  f.W = w.d();
+  f.part = part.d();
+  f.info = reinterpret_cast<int *>(misc.d() + 1);
+  f.stream = s;
+  pad_sym_kernel<<<dim3((np + 255) / 256, np), 256, 0, s>>>(Ad, ldad, n, f.A, np);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  GPB_TRY(factor_potrf_inv(f));
+  GPB_TRY(factor_logdet(f, misc.d()));
+  double h[2];
+  GPB_CUDA(cudaMemcpyAsync(h, misc.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  const int info = *reinterpret_cast<int *>(&h[1]);
+  if (info != 0) {
+    set_error("pdinv: matrix not positive definite (leading minor %d)", info);
+    return info > n ? n : info;
+  }
+  if (logdet) *logdet = h[0];
+  if (Ai) GPB_TRY(factor_potri(f));
+  if (!dev && (L || Ai || Li)) GPB_TRY(outb.alloc((size_t)n * n * sizeof(double)));
+  const dim3 grid((n + 255) / 256, n), gsym((n + 31) / 32, (n + 31) / 32);
+  for (int which = 0; which < 3; ++which) {
+    double *dst = which == 0 ? L : which == 1 ? Li : Ai;
+    if (!dst) continue;
+    double *dd = dev ? dst : outb.d();
+    if (which == 0)
+      tril_copy_kernel<<<grid, 256, 0, s>>>(f.A, np, dd, n, n);
+    else if (which == 1)
+      tril_copy_kernel<<<grid, 256, 0, s>>>(f.Mi, np, dd, n, n);
+    else
+      sym_copy_kernel<<<gsym, dim3(32, 8), 0, s>>>(f.W, np, dd, n, n);
+    count_launch();
+    GPB_CHECK_LAUNCH();
+    if (!dev) GPB_CUDA(cudaMemcpyAsync(dst, dd, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    GPB_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+
+int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, void *stream) {
+  // (L L^T) X = B as X = M^T (M B) with M = L^-1 rebuilt by the triangular-inverse recursion (factor_trtri).
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GPB_REQUIRE(L && B && n >= 1 && ldl >= n && nrhs >= 1, "potrs: bad arguments");
+  GPB_REQUIRE(gpb_device_count() > 0, "potrs: no CUDA device visible -- libgpb200 has no CPU fallback");
+  const int np = round_up(n, TILE), nb = np / TILE;
+  DevBuf lin, a, mi, w, part, misc, bbuf, yc, zc, xc;
+  const double *Ld = L;
+  int ldd = ldl;
+  if (!dev) {
+    GPB_TRY(lin.alloc((size_t)n * n * sizeof(double)));
+    GPB_CUDA(cudaMemcpy2DAsync(lin.p, (size_t)n * sizeof(double), L, (size_t)ldl * sizeof(double), (size_t)n * sizeof(double), n,
+                               cudaMemcpyHostToDevice, s));
+    Ld = lin.d();
+    ldd = n;
+  }
+  GPB_TRY(a.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(mi.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(w.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(part.alloc((size_t)nb * np * sizeof(double)));
+  GPB_TRY(misc.alloc(64));
+  // A-buffer = [tril(L) 0; 0 I]  (pad_sym mirrors the lower triangle; only the lower part is read afterwards)
+  pad_sym_kernel<<<dim3((np + 255) / 256, np), 256, 0, s>>>(Ld, ldd, n, a.d(), np);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  Factor f;
+  f.n = n;
+  f.np = np;
+  f.A = a.d();
+  f.Mi = mi.d();
+  f.W = w.d();
+  f.part = part.d();
+  f.info = reinterpret_cast<int *>(misc.d() + 1);
+  f.stream = s;
+  GPB_TRY(factor_trtri(f));
+  const double *Bd = nullptr;
+  GPB_TRY(to_device(bbuf, B, (size_t)n * nrhs, dev, &Bd, s));
+  GPB_TRY(yc.alloc((size_t)np * nrhs * sizeof(double)));
+  GPB_TRY(zc.alloc((size_t)np * nrhs * sizeof(double)));
+  GPB_TRY(xc.alloc((size_t)np * nrhs * sizeof(double)));
+  pack_cols_kernel<<<(nrhs * np + 255) / 256, 256, 0, s>>>(Bd, n, nrhs, np, yc.d());
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  GPB_TRY(factor_solve(f, yc.d(), nrhs, zc.d(), xc.d()));
+  double *outd = dev ? B : const_cast<double *>(Bd);
+  unpack_cols_kernel<<<(n * nrhs + 255) / 256, 256, 0, s>>>(xc.d(), n, nrhs, np, outd);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  if (!dev) GPB_CUDA(cudaMemcpyAsync(B, outd, (size_t)n * nrhs * sizeof(double), cudaMemcpyDeviceToHost, s));
+  int info = 0;
+  GPB_CUDA(cudaMemcpyAsync(&info, f.info, sizeof(int), cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  if (info != 0) {
+    set_error("potrs: factor is singular (pivot %d)", info);
+    return info;
+  }
+  return 0;
+}
+
+int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb, double beta,
+              double *C, int ldc, void *stream) {
+  GPB_REQUIRE(A && B && C, "dgemm: NULL argument");
+  GemmArgs g{A, lda, B, ldb, C, ldc, m, n, k, alpha, beta, 0, 0, 0};
+  return gemm_launch(ta ? LAYOUT_COLK : LAYOUT_ROWK, tb ? LAYOUT_COLK : LAYOUT_ROWK, g, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+// Shared definitions for libgpb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gpb200.h"
+
+namespace gpb {
+
+constexpr int TILE = 128;  // everything N x N is padded to a multiple of this; also the Cholesky leaf size
+constexpr double SQRT5 = 2.23606797749978969640917366873128;
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// ---- error plumbing -------------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
+inline void count_launch(int n = 1) { g_launches += n; }
+
+#define GPB_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      gpb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+      return -1;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+#define GPB_CHECK_LAUNCH()                                                                     \
+  do {                                                                                         \
+    cudaError_t e_ = cudaGetLastError();                                                       \
+    if (e_ != cudaSuccess) {                                                                   \
+      gpb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return -1;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+#define GPB_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      gpb::set_error(__VA_ARGS__);        \
+      return -2;                          \
+    }                                     \
+  } while (0)
+
+#define GPB_TRY(call)        \
+  do {                       \
+    int r_ = (call);         \
+    if (r_ != 0) return r_;  \
+  } while (0)
+
+// ---- stationary covariance functions of the scaled squared distance ---------------------------------------------------
+// k(r) and k'(r)/r for r = sqrt(r2).  The reference forms dK_dr * inv_dist (stationary.py:227-230,251-258) with inv_dist := 0
+// where r == 0; k'(r)/r is finite at 0 and is only ever multiplied by (x - x') which vanishes there, so the closed form
+// gives the same sums without the division.
+//   RBF      (rbf.py:50-54):            k = v exp(-r^2/2),                        k'/r = -k
+//   Matern52 (stationary.py:575-579):   k = v (1 + s5 r + 5/3 r^2) exp(-s5 r),    k'/r = -(5/3) v (1 + s5 r) exp(-s5 r)
+template <int KIND>
+__device__ __forceinline__ double cov_k(double r2, double variance) {
+  if (KIND == GPB_KERN_RBF) {
+    return variance * exp(-0.5 * r2);
+  } else {
+    const double r = sqrt(r2);
+    const double s = SQRT5 * r;
+    return variance * (1.0 + s + (5.0 / 3.0) * r2) * exp(-s);
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void cov_k_dk(double r2, double variance, double &k, double &dk_over_r) {
+  if (KIND == GPB_KERN_RBF) {
+    k = variance * exp(-0.5 * r2);
+    dk_over_r = -k;
+  } else {
+    const double r = sqrt(r2);
+    const double s = SQRT5 * r;
+    const double e = variance * exp(-s);
+    k = (1.0 + s + (5.0 / 3.0) * r2) * e;
+    dk_over_r = -(5.0 / 3.0) * (1.0 + s) * e;
+  }
+}
+
+// ---- reductions -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over a block of NT threads (NT multiple of 32, <= 1024); result valid in thread 0.  `scratch` holds >= 32 doubles.
+// Fixed shuffle/tree order -> bitwise reproducible run to run.
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) scratch[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < NT / 32) ? scratch[l] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// ---- factorisation state shared by the linalg drivers ----------------------------------------------------------------
+// All three matrices are Np x Np row-major with leading dimension Np (Np = round_up(N, TILE)); rows/cols >= N are the
+// identity so that padded problems factor to [L 0; 0 I].
+struct Factor {
+  int n = 0;    // logical size
+  int np = 0;   // padded size
+  double *A = nullptr;  // in: Ky (lower read); out: L in the lower triangle (diagonal leaf blocks have a zeroed upper part)
+  double *Mi = nullptr; // out: L^-1 (lower; diagonal leaf blocks explicit zeros above the diagonal)
+  double *W = nullptr;  // scratch during potrf; out of potri: Ky^-1 (lower tiles valid, diagonal tiles full)
+  int *info = nullptr;  // device int: 0 or (1 + index of first non-positive pivot)
+  double *part = nullptr;  // scratch for GEMV partials: (np / TILE) * np doubles
+  cudaStream_t stream = 0;
+};
+
+// gemm engine (gpb_gemm.cu)
+enum { LAYOUT_ROWK = 0, LAYOUT_COLK = 1 };
+struct GemmArgs {
+  const double *A; int lda;
+  const double *B; int ldb;
+  double *C; int ldc;
+  int M, N, K;
+  double alpha, beta;
+  int tri_out;   // 1: only tiles with tile_col <= tile_row are computed
+  int klo_mode;  // 0: 0       1: row0        2: col0
+  int khi_mode;  // 0: K       1: row0 + 128  2: col0 + 128
+};
+int gemm_launch(int layout_a, int layout_b, const GemmArgs &g, cudaStream_t s);
+
+// linalg drivers (gpb_chol.cu)
+int factor_potrf_inv(Factor &f);                 // A -> L, Mi = L^-1, *info
+int factor_trtri(Factor &f);                     // A holds a lower-triangular L (diag blocks clean) -> Mi = L^-1
+int factor_potri(Factor &f);                     // W = Mi^T Mi (lower tiles)
+int factor_solve(Factor &f, const double *Y, int p, double *z, double *alpha);  // alpha = Mi^T (Mi Y);  Y, z, alpha: np x p col-major (p vectors of np)
+int factor_logdet(Factor &f, double *out_dev);   // 2 sum log L_ii, i < n
+int launch_copy2d(double *dst, int ldd, const double *src, int lds, int rows, int cols, cudaStream_t s);
+int launch_symmetrize_lower(double *A, int ld, int n, cudaStream_t s);
+
+}  // namespace gpb

@@ -1,0 +1,205 @@
+// fp64 tensor-core GEMM engine for the blocked Cholesky / inverse / predictive solves (north_star (b), (c)).
+//
+//   C = alpha * op(A) * op(B) + beta * C        (row-major everywhere, M,N multiples of 128, K multiple of 16)
+//
+// Blackwell has no f64 kind for tcgen05/UMMA, so the FP64 tensor path on sm_100a is the warp-level
+// mma.sync.aligned.m8n8k4.f64 (SASS: DMMA.8x8x4).  One CTA owns a 128x128 output tile, 8 warps each own a 64x32 sub-tile
+// (8x4 DMMA accumulators = 64 fp64 registers per lane).  Operand tiles (128 x 16 k) are staged through shared memory with
+// a 3-stage cp.async (LDGSTS) pipeline; row strides are padded (20 / 132 doubles == 4 mod 16) so that every half-warp's
+// 64-bit fragment loads hit 16 distinct bank pairs (conflict free) in both storage orders.
+//
+// Triangular structure is exploited at tile granularity through a per-tile k-range (klo_mode / khi_mode) and through
+// tri_out (only lower tiles are produced): operands that are triangular carry explicit zeros inside their 128x128 diagonal
+// blocks, blocks strictly above the diagonal are never read.
+#include "gpb_common.cuh"
+
+namespace gpb {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 3;
+constexpr int GEMM_THREADS = 256;
+constexpr int LD_ROWK = BK + 4;    // operand stored [row][k]  (k contiguous)
+constexpr int LD_COLK = BM + 4;    // operand stored [k][row]  (row contiguous)
+constexpr int TILE_ROWK = BM * LD_ROWK;  // doubles per stage
+constexpr int TILE_COLK = BK * LD_COLK;
+
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// Stage one 128(row) x 16(k) operand tile.  base points at element (row0, 0) [ROWK] or (0, row0) [COLK] of the operand,
+// kk is the k offset of this tile.
+template <int LAYOUT>
+__device__ __forceinline__ void load_tile(double *s, const double *__restrict__ base, int ld, int kk, int tid) {
+  if (LAYOUT == LAYOUT_ROWK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int chunk = tid + i * GEMM_THREADS;  // 1024 chunks of 2 doubles
+      const int row = chunk >> 3, c = chunk & 7;
+      cp_async16(s + row * LD_ROWK + 2 * c, base + (size_t)row * ld + kk + 2 * c);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int chunk = tid + i * GEMM_THREADS;
+      const int kr = chunk >> 6, c = chunk & 63;
+      cp_async16(s + kr * LD_COLK + 2 * c, base + (size_t)(kk + kr) * ld + 2 * c);
+    }
+  }
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ double frag(const double *s, int row, int k) {
+  return (LAYOUT == LAYOUT_ROWK) ? s[row * LD_ROWK + k] : s[k * LD_COLK + row];
+}
+
+template <int LA, int LB>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int A_TILE = (LA == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
+  constexpr int B_TILE = (LB == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
+  double *sA = smem;
+  double *sB = smem + STAGES * A_TILE;
+
+  // ---- tile coordinates ----
+  int tm, tn;
+  const int t = blockIdx.x;
+  if (p.tri_out) {
+    // t = tm (tm + 1) / 2 + tn, tn <= tm
+    tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
+    while (tm * (tm + 1) / 2 > t) --tm;
+    tn = t - tm * (tm + 1) / 2;
+  } else {
+    const int tiles_n = p.N / BN;
+    tm = t / tiles_n;
+    tn = t - tm * tiles_n;
+  }
+  const int row0 = tm * BM, col0 = tn * BN;
+  int klo = (p.klo_mode == 1) ? row0 : (p.klo_mode == 2) ? col0 : 0;
+  int khi = (p.khi_mode == 1) ? row0 + BM : (p.khi_mode == 2) ? col0 + BN : p.K;
+  if (khi > p.K) khi = p.K;
+  const int ktiles = (khi - klo) / BK;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+
+  const double *Abase = (LA == LAYOUT_ROWK) ? p.A + (size_t)row0 * p.lda : p.A + row0;
+  const double *Bbase = (LB == LAYOUT_ROWK) ? p.B + (size_t)col0 * p.ldb : p.B + col0;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // ---- prologue ----
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < ktiles) {
+      load_tile<LA>(sA + s * A_TILE, Abase, p.lda, klo + s * BK, tid);
+      load_tile<LB>(sB + s * B_TILE, Bbase, p.ldb, klo + s * BK, tid);
+    }
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nt = kt + STAGES - 1;
+      if (nt < ktiles) {
+        const int s = nt % STAGES;
+        load_tile<LA>(sA + s * A_TILE, Abase, p.lda, klo + nt * BK, tid);
+        load_tile<LB>(sB + s * B_TILE, Bbase, p.ldb, klo + nt * BK, tid);
+      }
+      cp_async_commit();
+    }
+    const double *a_s = sA + (kt % STAGES) * A_TILE;
+    const double *b_s = sB + (kt % STAGES) * B_TILE;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ++ks) {
+      const int k0 = ks * 4 + tq;
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = frag<LA>(a_s, wm + i * 8 + g, k0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = frag<LB>(b_s, wn + j * 8 + g, k0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: lane holds (row g, cols 2 tq, 2 tq + 1) of every 8x8 accumulator ----
+  const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + wm + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + wn + j * 8 + 2 * tq;
+      double2 *ptr = reinterpret_cast<double2 *>(p.C + (size_t)row * p.ldc + col);
+      double2 o;
+      o.x = alpha * acc[i][j][0];
+      o.y = alpha * acc[i][j][1];
+      if (beta != 0.0) {
+        const double2 c = *ptr;
+        o.x += beta * c.x;
+        o.y += beta * c.y;
+      }
+      *ptr = o;
+    }
+  }
+}
+
+template <int LA, int LB>
+static int launch_t(const GemmArgs &g, cudaStream_t s) {
+  constexpr int A_TILE = (LA == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
+  constexpr int B_TILE = (LB == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
+  const size_t smem = (size_t)STAGES * (A_TILE + B_TILE) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    GPB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int tm = g.M / BM, tn = g.N / BN;
+  const int tiles = g.tri_out ? tm * (tm + 1) / 2 : tm * tn;
+  if (tiles == 0) return 0;
+  gemm_dmma_kernel<LA, LB><<<tiles, GEMM_THREADS, smem, s>>>(g);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+int gemm_launch(int la, int lb, const GemmArgs &g, cudaStream_t s) {
+  GPB_REQUIRE(g.M % BM == 0 && g.N % BN == 0 && g.K % BK == 0, "gemm: M,N must be multiples of 128 and K of 16 (got %d %d %d)",
+              g.M, g.N, g.K);
+  GPB_REQUIRE((g.lda % 2) == 0 && (g.ldb % 2) == 0 && (g.ldc % 2) == 0, "gemm: leading dimensions must be even");
+  GPB_REQUIRE(!g.tri_out || g.M == g.N, "gemm: tri_out needs a square output");
+  GPB_REQUIRE((((uintptr_t)g.A | (uintptr_t)g.B | (uintptr_t)g.C) & 15) == 0, "gemm: operands must be 16-byte aligned");
+  if (la == LAYOUT_ROWK && lb == LAYOUT_ROWK) return launch_t<LAYOUT_ROWK, LAYOUT_ROWK>(g, s);
+  if (la == LAYOUT_ROWK && lb == LAYOUT_COLK) return launch_t<LAYOUT_ROWK, LAYOUT_COLK>(g, s);
+  if (la == LAYOUT_COLK && lb == LAYOUT_COLK) return launch_t<LAYOUT_COLK, LAYOUT_COLK>(g, s);
+  if (la == LAYOUT_COLK && lb == LAYOUT_ROWK) return launch_t<LAYOUT_COLK, LAYOUT_ROWK>(g, s);
+  set_error("gemm: bad layouts %d %d", la, lb);
+  return -2;
+}
+
+}  // namespace gpb

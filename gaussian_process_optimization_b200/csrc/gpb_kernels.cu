@@ -1,0 +1,366 @@
+// Stationary-kernel construction K(X, X') and the hyper-parameter / input gradient reductions (north_star (a)).
+//
+// Replaces GPy/GPy/kern/src/stationary.py: _unscaled_dist/_scaled_dist (:155-193), K (:107-140), update_gradients_full
+// (:218-238) with _inv_dist (:251-258) and the serial Cython loop lengthscale_grads (stationary_cython.pyx:51-60), and
+// gradients_X (:271-278,354-364 -> stationary_utils.c:1-14); RBF.K_of_r/dK_dr (rbf.py:50-54), Matern52 (:575-579).
+//
+// Layout: inputs are pre-scaled once per parameter write into a dimension-major array XsT[q][i] = X[i][q] / l_q
+// (row stride ldx >= number of points, zero padded), so that a 128-point tile of one dimension is one coalesced 1 KB line
+// and lands in shared memory in the order the register-tiled pair loops read it.  r^2 is the direct sum of squared
+// differences (exactly 0 on the diagonal, never negative) instead of the reference's |x|^2+|y|^2-2xy expansion.
+#include "gpb_common.cuh"
+#include "gpb_kernels.cuh"
+
+namespace gpb {
+
+// XsT[q][i] = X[i][q] / ls[q]  (i < n), 0 for n <= i < ldx.   ls_dev: d doubles (already broadcast for the isotropic case)
+__global__ void scale_transpose_kernel(const double *__restrict__ X, int n, int d, const double *__restrict__ ls, double *__restrict__ XsT,
+                                       int ldx) {
+  const size_t total = (size_t)d * ldx;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int q = (int)(e / ldx), i = (int)(e - (size_t)q * ldx);
+    XsT[e] = (i < n) ? X[(size_t)i * d + q] / ls[q] : 0.0;
+  }
+}
+
+int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, double *XsT, int ldx, cudaStream_t s) {
+  const size_t total = (size_t)d * ldx;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scale_transpose_kernel<<<blocks, 256, 0, s>>>(X, n, d, ls_dev, XsT, ldx);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K tile kernel: one CTA = one 128 x 128 tile, 256 threads, thread (ty, tx) owns rows ty + 16a, cols tx + 16b (a, b < 8):
+// for fixed (a, b) a warp writes two 128-byte row segments (fully coalesced).
+//   mode 0 (rect):  out[i][j] = k(r_ij) for i < n_rows, j < n_cols (nothing else is written)
+//   mode 1 (Ky, padded): out is np x np;  i, j < n: k + (i == j) * diag_add;  otherwise identity
+//   mode 2 (rect, zero padded): out is rows_pad x cols_pad; k inside n_rows x n_cols, 0 outside
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) kmat_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
+                                                   int n_rows, int n_cols, double variance, double diag_add, int mode,
+                                                   double *__restrict__ out, int ldo) {
+  extern __shared__ double sm[];
+  double *xa = sm;             // [d][128]
+  double *xb = sm + d * TILE;  // [d][128]
+  const int row0 = blockIdx.y * TILE, col0 = blockIdx.x * TILE;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int e = tid; e < d * TILE; e += 256) {
+    const int q = e >> 7, i = e & 127;
+    xa[e] = XaT[(size_t)q * lda + row0 + i];
+    xb[e] = XbT[(size_t)q * ldb + col0 + i];
+  }
+  __syncthreads();
+  double r2[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) r2[a][b] = 0.0;
+  for (int q = 0; q < d; ++q) {
+    double va[8], vb[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) va[a] = xa[q * TILE + ty + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) vb[b] = xb[q * TILE + tx + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const double df = va[a] - vb[b];
+        r2[a][b] = fma(df, df, r2[a][b]);
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int i = row0 + ty + 16 * a;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int j = col0 + tx + 16 * b;
+      const bool inside = (i < n_rows) && (j < n_cols);
+      double v;
+      if (inside) {
+        v = cov_k<KIND>(r2[a][b], variance);
+        if (mode == 1 && i == j) v += diag_add;
+      } else {
+        v = (mode == 1 && i == j) ? 1.0 : 0.0;
+      }
+      if (inside || mode != 0) out[(size_t)i * ldo + j] = v;
+    }
+  }
+}
+
+int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
+                double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
+                cudaStream_t s) {
+  const size_t smem = (size_t)2 * d * TILE * sizeof(double);
+  GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large (max 100)", d);
+  dim3 grid(cols_pad / TILE, rows_pad / TILE);
+  if (grid.x == 0 || grid.y == 0) return 0;
+  if (kind == GPB_KERN_RBF) {
+    if (smem > 48 * 1024)
+      GPB_CUDA(cudaFuncSetAttribute(kmat_kernel<GPB_KERN_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kmat_kernel<GPB_KERN_RBF><<<grid, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, diag_add, mode, out, ldo);
+  } else {
+    if (smem > 48 * 1024)
+      GPB_CUDA(cudaFuncSetAttribute(kmat_kernel<GPB_KERN_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kmat_kernel<GPB_KERN_MATERN52><<<grid, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, diag_add, mode, out, ldo);
+  }
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Hyper-parameter gradient reduction.  Per 128x128 tile: recompute r^2, k, k'/r from the X tiles, form G on the fly and
+// accumulate
+//     part[tile][0]     = sum w K_ij G_ij                      (-> d/dvariance after / variance, stationary.py:224)
+//     part[tile][1]     = sum_{i == j} G_ii                    (-> d/dnoise = tr(dL_dK), exact_gaussian_inference.py:72)
+//     part[tile][2 + q] = sum w (k'/r)_ij G_ij (xs_iq - xs_jq)^2   (-> -(.)/l_q, stationary.py:227-235,260-269)
+// FUSED = 1:  G = 0.5 (sum_p alpha_ip alpha_jp - P Wi_ij) (exact_gaussian_inference.py:70) is never materialised; only the
+//             lower tiles of Wi are read (w = 2 off the diagonal tiles, the diagonal tiles are complete).
+// FUSED = 0:  G = dL_dK[i][j] (n_rows x n_cols, any matrix) -- the Kern.update_gradients_full(dL_dK, X, X2) contract.
+// Reductions: fixed-order shuffles -> per-warp shared slots -> per-tile partial -> a second fixed-order kernel; no atomics,
+// so the result is bitwise reproducible (L-BFGS-B trajectories depend on it).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KIND, int FUSED>
+__global__ void __launch_bounds__(256) kgrad_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
+                                                    int n_rows, int n_cols, double variance, const double *__restrict__ G, int ldg,
+                                                    const double *__restrict__ alpha, int ld_alpha, int p_out, int tiles_x,
+                                                    double *__restrict__ part) {
+  extern __shared__ double sm[];
+  double *xa = sm;                   // [d][128]
+  double *xb = sm + d * TILE;        // [d][128]
+  double *wacc = xb + d * TILE;      // [8 warps][d + 2]
+  int tr, tc;
+  if (FUSED) {
+    const int t = blockIdx.x;
+    tr = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+    while (tr * (tr + 1) / 2 > t) --tr;
+    tc = t - tr * (tr + 1) / 2;
+  } else {
+    tr = blockIdx.x / tiles_x;
+    tc = blockIdx.x - tr * tiles_x;
+  }
+  const int row0 = tr * TILE, col0 = tc * TILE;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < d * TILE; e += 256) {
+    const int q = e >> 7, i = e & 127;
+    xa[e] = XaT[(size_t)q * lda + row0 + i];
+    xb[e] = XbT[(size_t)q * ldb + col0 + i];
+  }
+  __syncthreads();
+  double r2[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) r2[a][b] = 0.0;
+  for (int q = 0; q < d; ++q) {
+    double va[8], vb[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) va[a] = xa[q * TILE + ty + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) vb[b] = xb[q * TILE + tx + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const double df = va[a] - vb[b];
+        r2[a][b] = fma(df, df, r2[a][b]);
+      }
+  }
+  // r2[a][b] is overwritten by the pair weight  w * (k'/r) * G
+  const double wt = (FUSED && tr != tc) ? 2.0 : 1.0;
+  double acc_var = 0.0, acc_tr = 0.0;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int i = row0 + ty + 16 * a;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int j = col0 + tx + 16 * b;
+      double wgt = 0.0;
+      if (i < n_rows && j < n_cols) {
+        double g;
+        if (FUSED) {
+          double aa = 0.0;
+          for (int p = 0; p < p_out; ++p) aa = fma(alpha[(size_t)p * ld_alpha + i], alpha[(size_t)p * ld_alpha + j], aa);
+          g = 0.5 * (aa - (double)p_out * G[(size_t)i * ldg + j]);
+          if (i == j) acc_tr += g;
+        } else {
+          g = G[(size_t)i * ldg + j];
+        }
+        double k, dk;
+        cov_k_dk<KIND>(r2[a][b], variance, k, dk);
+        acc_var = fma(wt * k, g, acc_var);
+        wgt = wt * dk * g;
+      }
+      r2[a][b] = wgt;
+    }
+  }
+  acc_var = warp_sum(acc_var);
+  acc_tr = warp_sum(acc_tr);
+  if (lane == 0) {
+    wacc[warp * (d + 2) + 0] = acc_var;
+    wacc[warp * (d + 2) + 1] = acc_tr;
+  }
+  for (int q = 0; q < d; ++q) {
+    double va[8], vb[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) va[a] = xa[q * TILE + ty + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) vb[b] = xb[q * TILE + tx + 16 * b];
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const double df = va[a] - vb[b];
+        acc = fma(r2[a][b], df * df, acc);
+      }
+    acc = warp_sum(acc);
+    if (lane == 0) wacc[warp * (d + 2) + 2 + q] = acc;
+  }
+  __syncthreads();
+  for (int c = tid; c < d + 2; c += 256) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += wacc[w * (d + 2) + c];
+    part[(size_t)blockIdx.x * (d + 2) + c] = s;
+  }
+}
+
+// out[c] = sum_t part[t][c], fixed order (one block per column).
+__global__ void colsum_kernel(const double *__restrict__ part, int ntiles, int ncols, double *__restrict__ out) {
+  __shared__ double scratch[32];
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int t = threadIdx.x; t < ntiles; t += 256) acc += part[(size_t)t * ncols + c];
+  acc = block_sum<256>(acc, scratch);
+  if (threadIdx.x == 0) out[c] = acc;
+}
+
+int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
+                 double variance, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out, double *part,
+                 double *out_dev, cudaStream_t s) {
+  const size_t smem = (size_t)(2 * d * TILE + 8 * (d + 2)) * sizeof(double);
+  GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large (max 96)", d);
+  const int tr = (n_rows + TILE - 1) / TILE, tc = (n_cols + TILE - 1) / TILE;
+  const int tiles = fused ? tr * (tr + 1) / 2 : tr * tc;
+  if (tiles == 0) return 0;
+#define GPB_KGRAD(K_, F_)                                                                                                 \
+  do {                                                                                                                    \
+    if (smem > 48 * 1024)                                                                                                 \
+      GPB_CUDA(cudaFuncSetAttribute(kgrad_kernel<K_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    kgrad_kernel<K_, F_><<<tiles, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, G, ldg, alpha, ld_alpha, \
+                                                  p_out, tc, part);                                                       \
+  } while (0)
+  if (kind == GPB_KERN_RBF) {
+    if (fused) GPB_KGRAD(GPB_KERN_RBF, 1); else GPB_KGRAD(GPB_KERN_RBF, 0);
+  } else {
+    if (fused) GPB_KGRAD(GPB_KERN_MATERN52, 1); else GPB_KGRAD(GPB_KERN_MATERN52, 0);
+  }
+#undef GPB_KGRAD
+  GPB_CHECK_LAUNCH();
+  colsum_kernel<<<d + 2, 256, 0, s>>>(part, tiles, d + 2, out_dev);
+  count_launch(2);
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Input gradients:  out1[c][q] = (s1 / l_q) sum_n (k'/r)_cn g1_cn (xs_cq - xs_nq)       [and the same with g2, s2]
+// with g_cn = G[c * ldg + n] (ldg == 0 broadcasts one row: the dL_dK = alpha^T case of core/gp.py:431-434)
+// (+ G[n * ldg + c] when add_t: the `tmp + tmp.T` of stationary.py:359-361 when X2 is None).
+// One warp per output row c; lanes stride over n (coalesced in the dimension-major layout); per-lane accumulators for all
+// dimensions live in registers (DCAP), then a fixed-order warp reduction.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int KIND, int DCAP, int TWO>
+__global__ void __launch_bounds__(256) gradx_kernel(const double *__restrict__ XcT, int ldc, int n_c, const double *__restrict__ XT, int ldx,
+                                                    int n, int d, double variance, const double *__restrict__ inv_ls,
+                                                    const double *__restrict__ G1, int ldg1, double s1, int add_t,
+                                                    const double *__restrict__ G2, int ldg2, double s2,
+                                                    double *__restrict__ out1, double *__restrict__ out2, int ldo) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= n_c) return;
+  double xc[DCAP], a1[DCAP], a2[TWO ? DCAP : 1];
+#pragma unroll
+  for (int q = 0; q < DCAP; ++q) {
+    xc[q] = (q < d) ? XcT[(size_t)q * ldc + c] : 0.0;
+    a1[q] = 0.0;
+    if (TWO) a2[q] = 0.0;
+  }
+  for (int j = lane; j < n; j += 32) {
+    double df[DCAP];
+    double r2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < DCAP; ++q) {
+      df[q] = (q < d) ? xc[q] - XT[(size_t)q * ldx + j] : 0.0;
+      r2 = fma(df[q], df[q], r2);
+    }
+    double k, dk;
+    cov_k_dk<KIND>(r2, variance, k, dk);
+    double g1 = G1[(size_t)c * ldg1 + j];
+    if (add_t) g1 += G1[(size_t)j * ldg1 + c];
+    const double w1 = dk * g1;
+    double w2 = 0.0;
+    if (TWO) w2 = dk * G2[(size_t)c * ldg2 + j];
+#pragma unroll
+    for (int q = 0; q < DCAP; ++q) {
+      a1[q] = fma(w1, df[q], a1[q]);
+      if (TWO) a2[q] = fma(w2, df[q], a2[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < DCAP; ++q) {
+    if (q < d) {
+      const double v1 = warp_sum(a1[q]);
+      if (lane == 0) out1[(size_t)c * ldo + q] = s1 * inv_ls[q] * v1;
+      if (TWO) {
+        const double v2 = warp_sum(a2[q]);
+        if (lane == 0) out2[(size_t)c * ldo + q] = s2 * inv_ls[q] * v2;
+      }
+    }
+  }
+}
+
+template <int KIND, int DCAP>
+static int launch_gradx_t(const double *XcT, int ldc, int n_c, const double *XT, int ldx, int n, int d, double variance,
+                          const double *inv_ls, const double *G1, int ldg1, double s1, int add_t, const double *G2, int ldg2,
+                          double s2, double *out1, double *out2, int ldo, cudaStream_t s) {
+  const int blocks = (n_c * 32 + 255) / 256;
+  if (G2)
+    gradx_kernel<KIND, DCAP, 1><<<blocks, 256, 0, s>>>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, G2, ldg2, s2, out1, out2, ldo);
+  else
+    gradx_kernel<KIND, DCAP, 0><<<blocks, 256, 0, s>>>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, nullptr, 0, 0.0, out1, nullptr, ldo);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_gradx(int kind, const double *XcT, int ldc, int n_c, const double *XT, int ldx, int n, int d, double variance,
+                 const double *inv_ls, const double *G1, int ldg1, double s1, int add_t, const double *G2, int ldg2, double s2,
+                 double *out1, double *out2, int ldo, cudaStream_t s) {
+  if (n_c == 0) return 0;
+  GPB_REQUIRE(d <= 64, "gradients_X: input dimension %d > 64 not supported", d);
+#define GPB_GX(K_, D_) return launch_gradx_t<K_, D_>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, G2, ldg2, s2, out1, out2, ldo, s)
+  if (kind == GPB_KERN_RBF) {
+    if (d <= 4) GPB_GX(GPB_KERN_RBF, 4);
+    if (d <= 8) GPB_GX(GPB_KERN_RBF, 8);
+    if (d <= 16) GPB_GX(GPB_KERN_RBF, 16);
+    if (d <= 32) GPB_GX(GPB_KERN_RBF, 32);
+    GPB_GX(GPB_KERN_RBF, 64);
+  } else {
+    if (d <= 4) GPB_GX(GPB_KERN_MATERN52, 4);
+    if (d <= 8) GPB_GX(GPB_KERN_MATERN52, 8);
+    if (d <= 16) GPB_GX(GPB_KERN_MATERN52, 16);
+    if (d <= 32) GPB_GX(GPB_KERN_MATERN52, 32);
+    GPB_GX(GPB_KERN_MATERN52, 64);
+  }
+#undef GPB_GX
+}
+
+}  // namespace gpb

@@ -1,0 +1,38 @@
+// Launchers of the covariance / gradient / predictive kernels (gpb_kernels.cu, gpb_predict.cu).
+#pragma once
+#include "gpb_common.cuh"
+
+namespace gpb {
+
+int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, double *XsT, int ldx, cudaStream_t s);
+
+// mode: 0 rect exact, 1 padded Ky (identity outside n x n, diag_add on the diagonal), 2 rect zero padded
+int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
+                double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
+                cudaStream_t s);
+
+// out_dev[0] = sum K.G, out_dev[1] = tr G (fused only), out_dev[2+q] = sum (k'/r) G ds_q^2.
+// part: scratch of tiles * (d + 2) doubles.
+int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
+                 double variance, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out, double *part,
+                 double *out_dev, cudaStream_t s);
+
+int launch_gradx(int kind, const double *XcT, int ldc, int n_c, const double *XT, int ldx, int n, int d, double variance,
+                 const double *inv_ls, const double *G1, int ldg1, double s1, int add_t, const double *G2, int ldg2, double s2,
+                 double *out1, double *out2, int ldo, cudaStream_t s);
+
+// gpb_predict.cu
+// mu[c][p] = sum_n KxT[c][n] alpha_p[n]   (row dot products, one warp per candidate)
+int launch_rowdot(const double *KxT, int ld, int n_c, int n, const double *alpha, int ld_alpha, int p, double *mu, cudaStream_t s);
+// var[c] = base - sum_n Vt[c][n]^2
+int launch_var_from_vt(const double *Vt, int ld, int n_c, int n, double base, double *var, cudaStream_t s);
+// GPModel.predict clip + get_quantiles + EI/LCB (+ gradients) + AcquisitionBase sign
+int launch_acq_epilogue(int acq, double par, double fmin, int n_c, int d, const double *mu, const double *var, const double *dmu,
+                        const double *dvar, double *f, double *df, double *mean_out, double *sd_out, double *dmdx_out,
+                        double *dsdx_out, cudaStream_t s);
+// running top-k of the k smallest f (ties -> lowest index); state on device: vals[k], idx[k]
+int launch_topk_init(double *vals, long long *idx, int k, cudaStream_t s);
+int launch_topk_update(const double *f, int n_c, long long index_base, double *vals, long long *idx, int k, cudaStream_t s);
+int launch_min(const double *v, int n, double *out, cudaStream_t s);
+
+}  // namespace gpb

@@ -1,0 +1,241 @@
+// Small kernels around the predictive GEMMs (north_star (c)): posterior mean, variance from the triangular product,
+// the GPyOpt acquisition epilogue and the anchor-point top-k.
+//
+// Reference path being replaced: PosteriorExact._raw_predict (GPy/.../posterior.py:273-302), GPModel._predict / predict /
+// predict_withGradients (GPyOpt/GPyOpt/models/gpmodel.py:95-142), get_quantiles (GPyOpt/util/general.py:113-128),
+// AcquisitionEI (acquisitions/EI.py:32-51), AcquisitionLCB (LCB.py:31-46), AcquisitionBase sign/cost (base.py:33-50),
+// anchor selection np.argsort(scores)[:k] (optimization/anchor_points_generator.py:58-63).
+#include <float.h>
+
+#include "gpb_common.cuh"
+#include "gpb_kernels.cuh"
+
+namespace gpb {
+
+__global__ void rowdot_kernel(const double *__restrict__ KxT, int ld, int n_c, int n, const double *__restrict__ alpha, int ld_alpha,
+                              int p, double *__restrict__ mu) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= n_c) return;
+  const double *row = KxT + (size_t)c * ld;
+  for (int pp = 0; pp < p; ++pp) {
+    const double *a = alpha + (size_t)pp * ld_alpha;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc = fma(row[j], a[j], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) mu[(size_t)c * p + pp] = acc;
+  }
+}
+
+int launch_rowdot(const double *KxT, int ld, int n_c, int n, const double *alpha, int ld_alpha, int p, double *mu, cudaStream_t s) {
+  if (n_c == 0) return 0;
+  rowdot_kernel<<<(n_c * 32 + 255) / 256, 256, 0, s>>>(KxT, ld, n_c, n, alpha, ld_alpha, p, mu);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void var_from_vt_kernel(const double *__restrict__ Vt, int ld, int n_c, int n, double base, double *__restrict__ var) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= n_c) return;
+  const double *row = Vt + (size_t)c * ld;
+  double acc = 0.0;
+  for (int j = lane; j < n; j += 32) acc = fma(row[j], row[j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) var[c] = base - acc;
+}
+
+int launch_var_from_vt(const double *Vt, int ld, int n_c, int n, double base, double *var, cudaStream_t s) {
+  if (n_c == 0) return 0;
+  var_from_vt_kernel<<<(n_c * 32 + 255) / 256, 256, 0, s>>>(Vt, ld, n_c, n, base, var);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+// One thread per candidate.  var already includes the likelihood variance (GP.predict include_likelihood=True).
+__global__ void acq_epilogue_kernel(int acq, double par, double fmin, int n_c, int d, const double *__restrict__ mu,
+                                    const double *__restrict__ var, const double *__restrict__ dmu, const double *__restrict__ dvar,
+                                    double *__restrict__ f, double *__restrict__ df, double *__restrict__ mean_out,
+                                    double *__restrict__ sd_out, double *__restrict__ dmdx_out, double *__restrict__ dsdx_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_c) return;
+  const double m = mu[c];
+  double v = var[c];
+  v = fmax(v, 1e-10);                       // gpmodel.py:99,137 np.clip(v, 1e-10, inf)
+  double s = sqrt(v);                        // gpmodel.py:112,142
+  const double ds_scale = 1.0 / (2.0 * s);   // gpmodel.py:140 dsdx = dvdx / (2 sqrt(v))
+  double fa, c_m, c_s;                       // dacq = c_s * dsdx + c_m * dmdx
+  if (acq == GPB_ACQ_EI) {
+    if (s < 1e-10) s = 1e-10;                // general.py:121-124 (in place: the floored s is what EI multiplies)
+    const double u = (fmin - m - par) / s;   // general.py:125
+    const double phi = exp(-0.5 * u * u) / sqrt(2.0 * M_PI);
+    const double Phi = 0.5 * erfc(-u / sqrt(2.0));
+    fa = s * (u * Phi + phi);                // EI.py:39
+    c_s = phi;                               // EI.py:50
+    c_m = -Phi;
+  } else {
+    fa = -m + par * s;                       // LCB.py:36
+    c_s = par;                               // LCB.py:45
+    c_m = -1.0;
+  }
+  if (f) f[c] = -fa;                         // base.py:39,50 (cost == 1, indicator == 1)
+  if (mean_out) mean_out[c] = m;
+  if (sd_out) sd_out[c] = s;
+  if (dmu) {
+    for (int q = 0; q < d; ++q) {
+      const double dm = dmu[(size_t)c * d + q];
+      const double ds = dvar[(size_t)c * d + q] * ds_scale;
+      if (df) df[(size_t)c * d + q] = -(c_s * ds + c_m * dm);
+      if (dmdx_out) dmdx_out[(size_t)c * d + q] = dm;
+      if (dsdx_out) dsdx_out[(size_t)c * d + q] = ds;
+    }
+  }
+}
+
+int launch_acq_epilogue(int acq, double par, double fmin, int n_c, int d, const double *mu, const double *var, const double *dmu,
+                        const double *dvar, double *f, double *df, double *mean_out, double *sd_out, double *dmdx_out,
+                        double *dsdx_out, cudaStream_t s) {
+  if (n_c == 0) return 0;
+  acq_epilogue_kernel<<<(n_c + 255) / 256, 256, 0, s>>>(acq, par, fmin, n_c, d, mu, var, dmu, dvar, f, df, mean_out, sd_out,
+                                                        dmdx_out, dsdx_out);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- top-k (k smallest, lexicographic on (value, global index)) -----------------------------------------------------
+__device__ __forceinline__ bool lex_less(double av, long long ai, double bv, long long bi) {
+  return (av < bv) || (av == bv && ai < bi);
+}
+
+__global__ void topk_init_kernel(double *vals, long long *idx, int k) {
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    vals[i] = DBL_MAX;
+    idx[i] = LLONG_MAX;
+  }
+}
+
+int launch_topk_init(double *vals, long long *idx, int k, cudaStream_t s) {
+  topk_init_kernel<<<1, 64, 0, s>>>(vals, idx, k);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+constexpr int TOPK_MAX = 64;
+
+// Single CTA: k selection rounds; each round takes the lexicographic minimum of {f[i]} U {previous state} that is strictly
+// greater than the element selected in the previous round.  Deterministic.
+__global__ void __launch_bounds__(1024) topk_update_kernel(const double *__restrict__ f, int n_c, long long index_base, double *vals,
+                                                           long long *idx, int k) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ double old_v[TOPK_MAX], new_v[TOPK_MAX];
+  __shared__ long long old_i[TOPK_MAX], new_i[TOPK_MAX];
+  __shared__ double last_v;
+  __shared__ long long last_i;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < k) {
+    old_v[tid] = vals[tid];
+    old_i[tid] = idx[tid];
+  }
+  if (tid == 0) {
+    last_v = -DBL_MAX;
+    last_i = -1;
+  }
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    const double lv = last_v;
+    const long long li = last_i;
+    const bool first = (r == 0);
+    double bv = DBL_MAX;
+    long long bi = LLONG_MAX;
+    for (int i = tid; i < n_c; i += 1024) {
+      const double v = f[i];
+      const long long gi = index_base + i;
+      if ((first || lex_less(lv, li, v, gi)) && lex_less(v, gi, bv, bi)) {
+        bv = v;
+        bi = gi;
+      }
+    }
+    if (tid < k) {
+      const double v = old_v[tid];
+      const long long gi = old_i[tid];
+      if ((first || lex_less(lv, li, v, gi)) && lex_less(v, gi, bv, bi)) {
+        bv = v;
+        bi = gi;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (lex_less(ov, oi, bv, bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      sv[warp] = bv;
+      si[warp] = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      bv = sv[lane];
+      bi = si[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (lex_less(ov, oi, bv, bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        new_v[r] = bv;
+        new_i[r] = bi;
+        last_v = bv;
+        last_i = bi;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < k) {
+    vals[tid] = new_v[tid];
+    idx[tid] = new_i[tid];
+  }
+}
+
+int launch_topk_update(const double *f, int n_c, long long index_base, double *vals, long long *idx, int k, cudaStream_t s) {
+  GPB_REQUIRE(k >= 1 && k <= TOPK_MAX, "top-k: k must be in [1, %d]", TOPK_MAX);
+  topk_update_kernel<<<1, 1024, 0, s>>>(f, n_c, index_base, vals, idx, k);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void min_kernel(const double *__restrict__ v, int n, double *out) {
+  __shared__ double sv[32];
+  double m = DBL_MAX;
+  for (int i = threadIdx.x; i < n; i += 1024) m = fmin(m, v[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = sv[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) *out = m;
+  }
+}
+
+int launch_min(const double *v, int n, double *out, cudaStream_t s) {
+  min_kernel<<<1, 1024, 0, s>>>(v, n, out);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace gpb

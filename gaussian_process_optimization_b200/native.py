@@ -1,0 +1,258 @@
+"""Thin Python wrappers over the C ABI (include/gpb200.h): NumPy arrays in/out (host path, copies inside the call) or CUDA
+torch tensors (device path, in place).  No numerics happen here -- every function forwards to libgpb200.so."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import KIND_IDS, ACQ_IDS, as_host, check, dptr, is_torch, ptr
+
+
+def _kind(kind):
+    return kind if isinstance(kind, int) else KIND_IDS[kind]
+
+
+def _ls(lengthscale):
+    return np.ascontiguousarray(np.atleast_1d(np.asarray(lengthscale, dtype=np.float64)))
+
+
+def kern_K(kind, X, X2, variance, lengthscale):
+    """Stationary.K(X, X2) (GPy/GPy/kern/src/stationary.py:107-140)."""
+    lib = _lib.require_gpu()
+    X = as_host(X)
+    n, d = X.shape
+    ls = _ls(lengthscale)
+    if X2 is None:
+        m, X2p = 0, None
+        out = np.empty((n, n))
+    else:
+        X2 = as_host(X2)
+        m, X2p = X2.shape[0], ptr(X2)
+        out = np.empty((n, m))
+    check(lib.gpb_kern_K(_kind(kind), d, n, ptr(X), m, X2p, float(variance), dptr(ls), ls.size, ptr(out), out.shape[1], 0,
+                         _lib.current_stream()), "kern_K")
+    return out
+
+
+def kern_update_gradients_full(kind, dL_dK, X, X2, variance, lengthscale):
+    """Stationary.update_gradients_full (stationary.py:218-238) -> (dvariance, dlengthscale[nls])."""
+    lib = _lib.require_gpu()
+    X = as_host(X)
+    n, d = X.shape
+    ls = _ls(lengthscale)
+    G = as_host(dL_dK)
+    if X2 is None:
+        m, X2p = 0, None
+        assert G.shape == (n, n)
+    else:
+        X2 = as_host(X2)
+        m, X2p = X2.shape[0], ptr(X2)
+        assert G.shape == (n, m)
+    out = np.empty(1 + ls.size)
+    check(lib.gpb_kern_update_gradients_full(_kind(kind), d, n, ptr(X), m, X2p, ptr(G), G.shape[1], float(variance), dptr(ls), ls.size,
+                                             dptr(out), 0, _lib.current_stream()), "update_gradients_full")
+    return out[0], out[1:].copy()
+
+
+def kern_gradients_X(kind, dL_dK, X, X2, variance, lengthscale):
+    """Stationary.gradients_X (stationary.py:271-278,354-364)."""
+    lib = _lib.require_gpu()
+    X = as_host(X)
+    n, d = X.shape
+    ls = _ls(lengthscale)
+    G = as_host(dL_dK)
+    if X2 is None:
+        m, X2p = 0, None
+        assert G.shape == (n, n)
+    else:
+        X2 = as_host(X2)
+        m, X2p = X2.shape[0], ptr(X2)
+        if G.shape == (1, m) and n != 1:  # broadcast row (core/gp.py:431-434 passes alpha^T)
+            G = np.ascontiguousarray(np.broadcast_to(G, (n, m)))
+        assert G.shape == (n, m)
+    out = np.empty((n, d))
+    check(lib.gpb_kern_gradients_X(_kind(kind), d, n, ptr(X), m, X2p, ptr(G), G.shape[1], float(variance), dptr(ls), ls.size, ptr(out),
+                                   0, _lib.current_stream()), "gradients_X")
+    return out
+
+
+def pdinv(A, want=("Ai", "L", "Li", "logdet")):
+    """pdinv without the jitter ladder (GPy/GPy/util/linalg.py:193-214); raises LinAlgError when not PD."""
+    lib = _lib.require_gpu()
+    A = as_host(A)
+    n = A.shape[0]
+    L = np.empty((n, n)) if "L" in want else None
+    Ai = np.empty((n, n)) if "Ai" in want else None
+    Li = np.empty((n, n)) if "Li" in want else None
+    logdet = ctypes.c_double(0.0)
+    rc = lib.gpb_pdinv(n, ptr(A), n, ptr(L), ptr(Ai), ptr(Li), ctypes.byref(logdet), 0, _lib.current_stream())
+    return rc, Ai, L, Li, logdet.value
+
+
+def potrs(L, B):
+    """dpotrs(L, B, lower=1) (linalg.py:116-125)."""
+    lib = _lib.require_gpu()
+    L = as_host(L)
+    Bc = as_host(B).copy()
+    if Bc.ndim == 1:
+        Bc = Bc[:, None]
+    check(lib.gpb_potrs(L.shape[0], ptr(L), L.shape[0], ptr(Bc), Bc.shape[1], 0, _lib.current_stream()), "potrs")
+    return Bc
+
+
+def dgemm(ta, tb, alpha, A, B, beta, C):
+    """Device-only DMMA GEMM on CUDA torch tensors (row-major).  C is updated in place."""
+    lib = _lib.require_gpu()
+    assert is_torch(A) and is_torch(B) and is_torch(C)
+    m, n = C.shape
+    k = A.shape[0] if ta else A.shape[1]
+    check(lib.gpb_dgemm(int(ta), int(tb), m, n, k, float(alpha), ptr(A), A.stride(0), ptr(B), B.stride(0), float(beta), ptr(C),
+                        C.stride(0), _lib.current_stream()), "dgemm")
+    return C
+
+
+def launch_count():
+    return int(_lib.load().gpb_launch_count())
+
+
+class NativeModel(object):
+    """Owner of one `gpb_model` handle: a GPRegression resident on the current CUDA device."""
+
+    def __init__(self, kind, ard, d, p=1, n_cap=1024, cand_block=1024, use_torch_workspace=True):
+        lib = _lib.require_gpu()
+        self._lib = lib
+        self.kind, self.ard, self.d, self.p = _kind(kind), bool(ard), int(d), int(p)
+        self.n_cap, self.cand_block = int(n_cap), int(cand_block)
+        self.nls = self.d if self.ard else 1
+        self.n = 0
+        self._ws = None
+        ws_ptr, ws_bytes = None, 0
+        if use_torch_workspace:
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    ws_bytes = int(lib.gpb_model_workspace_bytes(self.n_cap, self.d, self.p, self.cand_block))
+                    self._ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device="cuda")
+                    base = self._ws.data_ptr()
+                    ws_ptr = ctypes.c_void_p((base + 255) // 256 * 256)
+            except ImportError:
+                pass
+        h = ctypes.c_void_p()
+        check(lib.gpb_model_create(ctypes.byref(h), self.kind, int(self.ard), self.d, self.p, self.n_cap, self.cand_block, ws_ptr,
+                                   ws_bytes, _lib.current_stream()), "model_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gpb_model_destroy(self._h)
+            self._h = None
+            self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- data / parameters -------------------------------------------------------------------------------------------
+    def set_data(self, X, Y):
+        dev = is_torch(X)
+        if not dev:
+            X, Y = as_host(X), as_host(Y)
+        n = X.shape[0]
+        assert X.shape[1] == self.d and Y.shape == (n, self.p)
+        check(self._lib.gpb_model_set_data(self._h, n, ptr(X), ptr(Y), int(dev)), "set_data")
+        self.n = n
+
+    def set_theta(self, variance, lengthscale, noise):
+        ls = _ls(lengthscale)
+        assert ls.size == self.nls
+        check(self._lib.gpb_model_set_theta(self._h, float(variance), dptr(ls), float(noise)), "set_theta")
+
+    def fit(self, want_grad=True, extra_jitter=0.0):
+        """-> (info, log_marginal, grads or None); grads ordered [variance, lengthscale..., noise]."""
+        out = np.zeros(3 + self.nls)
+        rc = self._lib.gpb_model_fit(self._h, int(want_grad), float(extra_jitter), dptr(out))
+        if rc < 0:
+            check(rc, "fit")
+        if rc > 0:
+            return rc, None, None
+        return 0, float(out[0]), (out[1:].copy() if want_grad else None)
+
+    def get(self, what, out=None):
+        n = self.n
+        shape = (n, self.p) if what == "alpha" else (n, n)
+        dev = out is not None and is_torch(out)
+        if out is None:
+            out = np.empty(shape)
+        ld = out.stride(0) if dev else out.shape[1]
+        check(self._lib.gpb_model_get(self._h, what.encode(), ptr(out), int(ld), int(dev)), "get(%s)" % what)
+        return out
+
+    # -- prediction ----------------------------------------------------------------------------------------------------
+    def predict(self, Xc, include_likelihood=True, want_var=True):
+        Xc = as_host(Xc)
+        mc = Xc.shape[0]
+        mu = np.empty((mc, self.p))
+        var = np.empty((mc, 1)) if want_var else None
+        check(self._lib.gpb_model_predict(self._h, mc, ptr(Xc), int(include_likelihood), ptr(mu), ptr(var), 0), "predict")
+        return mu, var
+
+    def predict_full_cov(self, Xc, include_likelihood=True):
+        Xc = as_host(Xc)
+        mc = Xc.shape[0]
+        mu = np.empty((mc, self.p))
+        cov = np.empty((mc, mc))
+        check(self._lib.gpb_model_predict_full_cov(self._h, mc, ptr(Xc), int(include_likelihood), ptr(mu), ptr(cov), 0),
+              "predict_full_cov")
+        return mu, cov
+
+    def predictive_gradients(self, Xc):
+        Xc = as_host(Xc)
+        mc = Xc.shape[0]
+        dmu = np.empty((mc, self.d, 1))
+        dvar = np.empty((mc, self.d))
+        check(self._lib.gpb_model_predictive_gradients(self._h, mc, ptr(Xc), ptr(dmu), ptr(dvar), 0), "predictive_gradients")
+        return dmu, dvar
+
+    def fmin(self):
+        v = ctypes.c_double(0.0)
+        check(self._lib.gpb_model_fmin(self._h, ctypes.byref(v)), "fmin")
+        return v.value
+
+    def acquisition(self, acq, par, fmin, Xc, with_gradients=False, want_moments=False):
+        """-> dict with f (mc,1) [, df (mc,d)] [, m, s (mc,1), dmdx, dsdx (mc,d)]; f = -acq like AcquisitionBase."""
+        dev = is_torch(Xc)
+        if dev:
+            import torch
+            mc = Xc.shape[0]
+            new = lambda *s: torch.empty(*s, dtype=torch.float64, device=Xc.device)  # noqa: E731
+        else:
+            Xc = as_host(Xc)
+            mc = Xc.shape[0]
+            new = lambda *s: np.empty(s)  # noqa: E731
+        r = {"f": new(mc, 1)}
+        if with_gradients:
+            r["df"] = new(mc, self.d)
+        if want_moments:
+            r["m"], r["s"] = new(mc, 1), new(mc, 1)
+            if with_gradients:
+                r["dmdx"], r["dsdx"] = new(mc, self.d), new(mc, self.d)
+        aid = acq if isinstance(acq, int) else ACQ_IDS[acq]
+        check(self._lib.gpb_model_acquisition(self._h, aid, float(par), float(fmin), mc, ptr(Xc), ptr(r["f"]), ptr(r.get("df")),
+                                              ptr(r.get("m")), ptr(r.get("s")), ptr(r.get("dmdx")), ptr(r.get("dsdx")), int(dev)),
+              "acquisition")
+        return r
+
+    def acq_topk(self, acq, par, fmin, Xc, k, index_offset=0):
+        dev = is_torch(Xc)
+        if not dev:
+            Xc = as_host(Xc)
+        mc = Xc.shape[0]
+        vals = np.empty(k)
+        idx = np.empty(k, dtype=np.int64)
+        pts = np.empty((k, self.d))
+        aid = acq if isinstance(acq, int) else ACQ_IDS[acq]
+        check(self._lib.gpb_model_acq_topk(self._h, aid, float(par), float(fmin), mc, ptr(Xc), int(dev), int(k), int(index_offset),
+                                           dptr(vals), idx.ctypes.data_as(_lib.c_ll_p), dptr(pts)), "acq_topk")
+        return vals, idx, pts

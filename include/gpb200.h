@@ -1,0 +1,117 @@
+/* gpb200.h -- C ABI of libgpb200.so: the B200 (sm_100a) exact-GP inner loop.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch / C++ types) and returns an int status:
+ *   0 = OK, <0 = bad argument / CUDA error (message via gpb_last_error()), >0 = LAPACK-style `info`
+ *   (leading minor of that order is not positive definite).
+ * Matrices are fp64, row-major (C-contiguous NumPy layout).  "dev" flags say whether a pointer is a device (1) or host (0)
+ * pointer; host pointers are copied inside the call (the e2e path), device pointers are used in place.
+ *
+ * The reference (GPy 1.9.6 / GPyOpt 1.2.5) has no FFI on this path -- its plug-in boundary is Python duck typing
+ * (SURVEY.md section 8b).  Each function below names the reference Python interface it replaces (file:line relative to
+ * /root/reference); INTEGRATION.md shows the ctypes stub a maintainer would add on the reference side.
+ */
+#ifndef GPB200_H
+#define GPB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_KERN_RBF 0      /* GPy.kern.RBF        GPy/GPy/kern/src/rbf.py:50-54 */
+#define GPB_KERN_MATERN52 1 /* GPy.kern.Matern52   GPy/GPy/kern/src/stationary.py:575-579 */
+#define GPB_ACQ_EI 0        /* GPyOpt AcquisitionEI   GPyOpt/GPyOpt/acquisitions/EI.py:32-51 */
+#define GPB_ACQ_LCB 1       /* GPyOpt AcquisitionLCB  GPyOpt/GPyOpt/acquisitions/LCB.py:31-46 */
+
+typedef struct gpb_model gpb_model; /* opaque: one GPRegression (data, hyper-parameters, posterior) resident on one GPU */
+
+/* ---- library ------------------------------------------------------------------------------------------------------ */
+int gpb_version(void);
+const char *gpb_last_error(void);
+int gpb_device_count(void);
+/* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
+long long gpb_launch_count(void);
+
+/* ---- Kern contract: GPy/GPy/kern/src/kern.py:119-202, stationary.py ------------------------------------------------ */
+/* Stationary.K(X, X2=None)  (stationary.py:107-140, _scaled_dist :176-193, K_of_r rbf.py:50 / stationary.py:575).
+ * X: n x d, X2: m x d or NULL (-> symmetric n x n, diagonal r forced to 0), lengthscale: nls = d (ARD) or 1 host doubles.
+ * K out: n x m (ldk >= m). */
+int gpb_kern_K(int kind, int d, int n, const double *X, int m, const double *X2, double variance,
+               const double *lengthscale, int nls, double *K, int ldk, int dev, void *stream);
+
+/* Stationary.update_gradients_full(dL_dK, X, X2=None)  (stationary.py:218-238, _inv_dist :251-258,
+ * _lengthscale_grads_cython :263-269 -> stationary_cython.pyx:51-60).  dL_dK: n x m.  out (host): [dvariance, dlengthscale[nls]]. */
+int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK,
+                                   int ld, double variance, const double *lengthscale, int nls, double *out, int dev,
+                                   void *stream);
+
+/* Stationary.gradients_X(dL_dK, X, X2=None)  (stationary.py:271-278,354-364 -> stationary_utils.c:1-14 _grad_X).
+ * out: n x d. */
+int gpb_kern_gradients_X(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
+                         double variance, const double *lengthscale, int nls, double *out, int dev, void *stream);
+
+/* ---- util.linalg: GPy/GPy/util/linalg.py -------------------------------------------------------------------------- */
+/* pdinv(A) (linalg.py:193-214) = jitchol's dpotrf (:56-60) + logdet (:208) + dpotri/symmetrify (:210-212).
+ * A: n x n symmetric (lower triangle read).  Outputs (any may be NULL): L n x n lower (upper zeroed), Ai n x n symmetric,
+ * Li n x n lower = L^-1, logdet (host double).  Returns info > 0 if a pivot is not positive (caller runs the jitter ladder,
+ * linalg.py:62-75). */
+int gpb_pdinv(int n, const double *A, int lda, double *L, double *Ai, double *Li, double *logdet, int dev, void *stream);
+/* dpotrs(L, B) (linalg.py:116-125): solve (L L^T) X = B in place, B: n x nrhs row-major. */
+int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, void *stream);
+
+/* ---- GPRegression / ExactGaussianInference / PosteriorExact -------------------------------------------------------- */
+/* Device workspace (bytes) a model of capacity n_cap points in d dims needs; cand_block = max candidates per predict block. */
+size_t gpb_model_workspace_bytes(int n_cap, int d, int p, int cand_block);
+/* GPRegression(X, Y, kernel, noise_var) (GPy/GPy/models/gp_regression.py:29-36, core/gp.py:38-110).
+ * workspace: device memory owned by the caller (e.g. a torch tensor) of >= gpb_model_workspace_bytes, or NULL to let the
+ * library cudaMalloc it.  ard: 1 -> d lengthscales, 0 -> one. */
+int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap, int cand_block, void *workspace,
+                     size_t workspace_bytes, void *stream);
+int gpb_model_destroy(gpb_model *m);
+/* GP.set_XY (core/gp.py:202-238).  X: n x d, Y: n x p. */
+int gpb_model_set_data(gpb_model *m, int n, const double *X, const double *Y, int dev);
+/* parameter write: kern.variance, kern.lengthscale[nls], Gaussian_noise.variance (link order stationary.py:83, gp.py:108-109) */
+int gpb_model_set_theta(gpb_model *m, double variance, const double *lengthscale, double noise);
+/* GP.parameters_changed (core/gp.py:258-271) = ExactGaussianInference.inference (exact_gaussian_inference.py:37-74)
+ * + Gaussian.update_gradients + Stationary.update_gradients_full.
+ * extra_jitter is added to the diagonal on top of noise + 1e-8 (jitchol ladder, linalg.py:62-72).
+ * out (host): [log_marginal, dL/dvariance, dL/dlengthscale[nls], dL/dnoise]  (want_grad = 0 -> only out[0]).
+ * Returns 0 or info > 0 (not positive definite). */
+int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out);
+/* Posterior accessors (posterior.py:79-218): woodbury_chol L (n x n), woodbury_inv (n x n, symmetric), woodbury_vector
+ * alpha (n x p), K (n x n, recomputed), dL_dK (n x n; exact_gaussian_inference.py:70).  dst may be host or device. */
+int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev);
+/* GP.predict(Xnew, full_cov=False, include_likelihood) (core/gp.py:297-354; posterior.py:273-302; gaussian.py:102-110).
+ * mu: mc x p, var: mc (no clipping, like PosteriorExact). */
+int gpb_model_predict(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *var, int dev);
+/* GP.predict(full_cov=True): cov mc x mc (posterior.py:281-284). */
+int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *cov,
+                               int dev);
+/* GP.predictive_gradients(Xnew) (core/gp.py:407-454): dmu mc x d x p, dvar mc x d. */
+int gpb_model_predictive_gradients(gpb_model *m, int mc, const double *Xc, double *dmu, double *dvar, int dev);
+/* GPModel.get_fmin (GPyOpt/GPyOpt/models/gpmodel.py:125-129): min posterior mean over the training inputs (host out). */
+int gpb_model_fmin(gpb_model *m, double *fmin);
+
+/* ---- GPyOpt acquisition: GPModel.predict(_withGradients) + get_quantiles + EI/LCB + AcquisitionBase sign ----------- */
+/* acquisition_function(x) / acquisition_function_withGradients(x) (GPyOpt/GPyOpt/acquisitions/base.py:33-50) for an
+ * unconstrained space and constant cost: f = -acq, df = -dacq.  par = jitter (EI) or exploration_weight (LCB).
+ * Outputs (any may be NULL): f mc, df mc x d, mean mc, sd mc (clipped at 1e-10 like gpmodel.py:99), dmdx mc x d, dsdx mc x d. */
+int gpb_model_acquisition(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df,
+                          double *mean, double *sd, double *dmdx, double *dsdx, int dev);
+/* Score mc candidates and return the k lowest f = -acq (anchor selection, anchor_points_generator.py:58-63, ties -> lowest
+ * index).  idx are candidate indices + index_offset (global ids for a sharded candidate set).  vals/idx/pts are host. */
+int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
+                       long long index_offset, double *vals, long long *idx, double *pts);
+
+/* ---- raw building blocks (tests, benchmarks, roofline measurements) ------------------------------------------------ */
+/* C = alpha * op(A) op(B) + beta * C with the fp64 tensor-core (DMMA) engine; all of m, n multiples of 128, k of 16.
+ * ta = 0: A is m x k row-major; 1: A is stored k x m.  tb = 0: B is stored n x k ("NT"); 1: B is stored k x n.
+ * Device pointers only. */
+int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb,
+              double beta, double *C, int ldc, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPB200_H */

@@ -1,0 +1,294 @@
+"""GPU parity tests through the C ABI (libgpb200.so via gaussian_process_optimization_b200.native).
+
+Every check compares the CUDA path with (i) the golden vectors produced by the reference's own source files
+(tests/golden/*.npz) and (ii) the CPU oracle (oracle/gp_oracle.py) on seeded inputs.
+Tolerances follow BASELINE.json north_star: rtol 1e-9 on K, log-likelihood and predictions, 1e-7 on gradients; quantities
+whose conditioning is cond(Ky) * eps (alpha, Ky^-1 and what is built from them, the noise-free variance near the data) carry
+that factor explicitly -- two LAPACK builds do not agree better than that either.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+native = pytest.importorskip("gaussian_process_optimization_b200.native")
+
+
+def _theta(g):
+    return g["variance"], g["lengthscale"], g["noise"]
+
+
+def _cond_tol(g, base):
+    """base * max(1, cond(Ky) * eps / 1e-12): widen only for the nearly singular exact-evaluation case."""
+    K = g["K"]
+    w = np.linalg.eigvalsh(K + (g["noise"] + 1e-8) * np.eye(K.shape[0]))
+    cond = w[-1] / w[0]
+    return base * max(1.0, cond * 2.2e-16 / 1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DMMA GEMM engine
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 16), (256, 384, 272), (512, 128, 1024)])
+def test_dgemm_layouts(ta, tb, m, n, k):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(m + 7 * n + 13 * k + ta + 2 * tb)
+    A = torch.randn((k, m) if ta else (m, k), generator=g, dtype=torch.float64)
+    B = torch.randn((k, n) if tb else (n, k), generator=g, dtype=torch.float64)
+    C = torch.randn((m, n), generator=g, dtype=torch.float64)
+    ref = 1.5 * ((A.T if ta else A) @ (B if tb else B.T)) - 0.5 * C
+    Cd = C.cuda()
+    native.dgemm(ta, tb, 1.5, A.cuda(), B.cuda(), -0.5, Cd)
+    torch.cuda.synchronize()
+    assert_allclose(Cd.cpu().numpy(), ref.numpy(), rtol=1e-12, atol=1e-11)
+
+
+def test_dgemm_beta_zero_ignores_nan_in_c():
+    import torch
+    A = torch.randn((128, 32), dtype=torch.float64)
+    B = torch.randn((128, 32), dtype=torch.float64)
+    Cd = torch.full((128, 128), float("nan"), dtype=torch.float64, device="cuda")
+    native.dgemm(0, 0, 1.0, A.cuda(), B.cuda(), 0.0, Cd)
+    assert_allclose(Cd.cpu().numpy(), (A @ B.T).numpy(), rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (a) kernels
+# ---------------------------------------------------------------------------------------------------------------------
+def test_kernel_matrix_golden(golden):
+    g = golden
+    v, ls, _ = _theta(g)
+    Ks = native.kern_K(g["kind"], g["X"], None, v, ls)
+    assert_allclose(Ks, g["K"], rtol=1e-9, atol=1e-300)
+    assert np.array_equal(np.diag(Ks), np.full(Ks.shape[0], v))          # r_ii forced to 0 (stationary.py:164)
+    assert_allclose(native.kern_K(g["kind"], g["Xs"], g["X"], v, ls), g["K_cross"], rtol=1e-9)
+
+
+def test_update_gradients_full_golden(golden):
+    g = golden
+    v, ls, _ = _theta(g)
+    dv, dl = native.kern_update_gradients_full(g["kind"], g["G_sq"], g["X"], None, v, ls)
+    assert_allclose(dv, g["ugf_sq_var"].ravel()[0], rtol=1e-7)
+    assert_allclose(dl, g["ugf_sq_len"], rtol=1e-7)
+    dv, dl = native.kern_update_gradients_full(g["kind"], g["G_rect"], g["Xs"], g["X"], v, ls)
+    assert_allclose(dv, g["ugf_rect_var"].ravel()[0], rtol=1e-7)
+    assert_allclose(dl, g["ugf_rect_len"], rtol=1e-7)
+
+
+def test_gradients_X_golden(golden):
+    g = golden
+    v, ls, _ = _theta(g)
+    if not g["ard"]:
+        ls = np.full(g["X"].shape[1], ls[0])    # gradients_X divides by lengthscale**2 per column either way
+    scale = np.abs(g["gX_sq"]).max()
+    assert_allclose(native.kern_gradients_X(g["kind"], g["G_sq"], g["X"], None, v, ls), g["gX_sq"], rtol=1e-7, atol=1e-9 * scale)
+    scale = np.abs(g["gX_rect"]).max()
+    assert_allclose(native.kern_gradients_X(g["kind"], g["G_rect"], g["Xs"], g["X"], v, ls), g["gX_rect"], rtol=1e-7,
+                    atol=1e-9 * scale)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "mat52"])
+def test_kernel_shapes_like_reference_cython_tests(kind):
+    """GPy/GPy/testing/cython_tests.py:39-67 shapes: X 300x10, Z 20x10, random dL_dK, square and rectangular."""
+    rs = np.random.RandomState(5)
+    X, Z = rs.randn(300, 10), rs.randn(20, 10)
+    ls = 0.8 + rs.rand(10)
+    G1, G2 = rs.randn(300, 300), rs.randn(300, 20)
+    assert_allclose(native.kern_K(kind, X, Z, 1.7, ls), O.K(kind, X, Z, 1.7, ls), rtol=1e-9, atol=1e-300)
+    for G, X2 in ((G1, None), (G2, Z)):
+        dv, dl = native.kern_update_gradients_full(kind, G, X, X2, 1.7, ls)
+        rv, rl = O.update_gradients_full(kind, G, X, X2, 1.7, ls)
+        assert_allclose(dv, rv, rtol=1e-7)
+        assert_allclose(dl, rl, rtol=1e-7)
+        ref = O.gradients_X(kind, G, X, X2, 1.7, ls)
+        assert_allclose(native.kern_gradients_X(kind, G, X, X2, 1.7, ls), ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (b) linalg
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 300, 640, 1100])
+def test_pdinv_against_lapack(n):
+    rs = np.random.RandomState(n)
+    B = rs.randn(n, n + 3)
+    A = B @ B.T + 0.5 * n * np.eye(n)
+    rc, Ai, L, Li, logdet = native.pdinv(A)
+    assert rc == 0
+    Lr = np.linalg.cholesky(A)
+    assert_allclose(L, Lr, rtol=1e-10, atol=1e-12 * np.abs(Lr).max())
+    assert_allclose(Li, np.linalg.inv(Lr), rtol=1e-9, atol=1e-12)
+    assert_allclose(Ai, np.linalg.inv(A), rtol=1e-9, atol=1e-12 * np.abs(Ai).max())
+    assert_allclose(logdet, 2 * np.log(np.diag(Lr)).sum(), rtol=1e-12)
+    assert np.array_equal(Ai, Ai.T)
+    assert np.all(np.triu(L, 1) == 0)
+
+
+def test_pdinv_not_pd_reports_info():
+    rs = np.random.RandomState(0)
+    B = rs.randn(300, 300)
+    A = B @ B.T
+    w, V = np.linalg.eigh(A)
+    w[0] = -1.0
+    A = (V * w) @ V.T
+    rc = native.pdinv(A)[0]
+    assert rc > 0
+    with pytest.raises(np.linalg.LinAlgError):
+        native._lib.check(rc, "pdinv")
+
+
+@pytest.mark.parametrize("n,nrhs", [(64, 1), (300, 3)])
+def test_potrs(n, nrhs):
+    rs = np.random.RandomState(n)
+    B = rs.randn(n, n)
+    A = B @ B.T + n * np.eye(n)
+    L = np.linalg.cholesky(A)
+    rhs = rs.randn(n, nrhs)
+    assert_allclose(native.potrs(L, rhs), np.linalg.solve(A, rhs), rtol=1e-9, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (b)+(c) model: inference, gradients, posterior, predictions, acquisitions -- against the reference's own outputs
+# ---------------------------------------------------------------------------------------------------------------------
+def _fitted(g, cand_block=128):
+    v, ls, n = _theta(g)
+    m = native.NativeModel(g["kind"], g["ard"], g["X"].shape[1], 1, n_cap=g["X"].shape[0], cand_block=cand_block)
+    m.set_data(g["X"], g["Y"])
+    m.set_theta(v, ls, n)
+    info, logL, grads = m.fit(True)
+    assert info == 0
+    return m, logL, grads
+
+
+def test_inference_golden(golden):
+    g = golden
+    m, logL, grads = _fitted(g)
+    ct = _cond_tol(g, 1.0)
+    assert_allclose(logL, g["logL"], rtol=1e-9 * ct)
+    assert_allclose(m.get("L"), g["L"], rtol=1e-9, atol=1e-12)
+    assert_allclose(m.get("alpha"), g["alpha"], rtol=1e-9 * ct, atol=1e-9 * ct * np.abs(g["alpha"]).max())
+    Wi = m.get("Wi")
+    assert_allclose(Wi, g["Wi"], rtol=1e-9 * ct, atol=1e-9 * ct * np.abs(g["Wi"]).max())
+    assert_allclose(m.get("dL_dK"), g["dL_dK"], rtol=1e-9 * ct, atol=1e-9 * ct * np.abs(g["dL_dK"]).max())
+    assert_allclose(m.get("K"), g["K"], rtol=1e-9, atol=1e-300)
+    assert_allclose(grads[0], g["grad_var"].ravel()[0], rtol=1e-7 * ct)
+    assert_allclose(grads[1:-1], g["grad_len"], rtol=1e-7 * ct)
+    assert_allclose(grads[-1], g["grad_noise"].ravel()[0], rtol=1e-7 * ct)
+    m.close()
+
+
+def test_predict_and_acquisition_golden(golden):
+    g = golden
+    m, _, _ = _fitted(g)
+    ct = _cond_tol(g, 1.0)
+    Xs = g["Xs"]
+    mu, var = m.predict(Xs)
+    assert_allclose(mu, g["pred_mu"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(var, g["pred_var"], rtol=1e-9 * ct, atol=1e-13 * ct)
+    _, var0 = m.predict(Xs, include_likelihood=False)
+    assert_allclose(var0, g["pred_var_noiseless"], rtol=1e-8 * ct, atol=1e-12 * ct)
+    mu2, cov = m.predict_full_cov(Xs)
+    assert_allclose(mu2, g["pred_mu"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(cov, g["pred_cov"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    dmu, dvar = m.predictive_gradients(Xs)
+    assert_allclose(dmu, g["dmu_dX"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["dmu_dX"]).max())
+    assert_allclose(dvar, g["dv_dX"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["dv_dX"]).max())
+    fmin = m.fmin()
+    assert_allclose(fmin, g["fmin"], rtol=1e-9 * ct)
+    r = m.acquisition("EI", 0.01, fmin, Xs, with_gradients=True, want_moments=True)
+    assert_allclose(r["m"], g["gpm_m"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(r["s"], g["gpm_s"], rtol=1e-9 * ct)
+    assert_allclose(r["dmdx"], g["gpm_dmdx"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["gpm_dmdx"]).max())
+    assert_allclose(r["dsdx"], g["gpm_dsdx"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["gpm_dsdx"]).max())
+    assert_allclose(r["f"], g["ei_g_f"], rtol=1e-8 * ct, atol=1e-14)
+    assert_allclose(r["df"], g["ei_g_df"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["ei_g_df"]).max())
+    r0 = m.acquisition("EI", 0.01, fmin, Xs)
+    assert_allclose(r0["f"], g["ei"], rtol=1e-8 * ct, atol=1e-14)
+    rl = m.acquisition("LCB", 2.0, fmin, Xs, with_gradients=True)
+    assert_allclose(rl["f"], g["lcb_g_f"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(rl["df"], g["lcb_g_df"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["lcb_g_df"]).max())
+    # anchor selection: the k lowest scores, ties -> lowest index
+    k = 5
+    vals, idx, pts = m.acq_topk("EI", 0.01, fmin, Xs, k)
+    order = np.argsort(g["ei"].ravel(), kind="stable")[:k]
+    assert np.array_equal(idx, order)
+    assert_allclose(vals, g["ei"].ravel()[order], rtol=1e-8 * ct, atol=1e-14)
+    assert np.array_equal(pts, Xs[order])
+    m.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# seeded larger cases against the oracle (sizes the oracle finishes in seconds)
+# ---------------------------------------------------------------------------------------------------------------------
+def _synth(N, D, seed=1234):
+    """SURVEY.md 8(d) generator."""
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(0, 1, (N, D))
+    w = rs.randn(D)
+    Y = np.sin(X @ w)[:, None] + 0.05 * rs.randn(N, 1)
+    Y = (Y - Y.mean()) / Y.std()
+    ls = 0.5 + 0.5 * np.arange(D) / D
+    return X, Y, ls
+
+
+@pytest.mark.parametrize("kind,N,D", [("rbf", 1000, 8), ("mat52", 1500, 16), ("rbf", 2048, 3)])
+def test_nll_grad_against_oracle(kind, N, D):
+    X, Y, ls = _synth(N, D)
+    logL, grads, post = O.log_likelihood_and_gradients(kind, X, Y, 1.0, ls, 1e-2, native=True)
+    m = native.NativeModel(kind, True, D, 1, n_cap=N, cand_block=512)
+    m.set_data(X, Y)
+    m.set_theta(1.0, ls, 1e-2)
+    info, l2, g2 = m.fit(True)
+    assert info == 0
+    assert_allclose(l2, logL, rtol=1e-9)
+    assert_allclose(g2, grads, rtol=1e-7)
+    # repeated evaluation is bitwise reproducible (fixed-order reductions; the L-BFGS-B trajectory depends on it)
+    info, l3, g3 = m.fit(True)
+    assert l3 == l2 and np.array_equal(g2, g3)
+    # acquisition over more candidates than one block, with and without gradients
+    st = O.GPState(kind, X, Y, 1.0, ls, 1e-2)
+    Xc = np.random.RandomState(7).uniform(0, 1, (1200, D))
+    fmin = m.fmin()
+    assert_allclose(fmin, st.get_fmin(), rtol=1e-9)
+    f_ref, df_ref = st.acquisition("EI", Xc, with_gradients=True, native=True)
+    r = m.acquisition("EI", 0.01, fmin, Xc, with_gradients=True)
+    assert_allclose(r["f"], f_ref, rtol=1e-7, atol=1e-12)
+    assert_allclose(r["df"], df_ref, rtol=1e-6, atol=1e-9 * np.abs(df_ref).max())
+    f_ref, df_ref = st.acquisition("LCB", Xc, with_gradients=True, native=True)
+    r = m.acquisition("LCB", 2.0, fmin, Xc, with_gradients=True)
+    assert_allclose(r["f"], f_ref, rtol=1e-9, atol=1e-11)
+    assert_allclose(r["df"], df_ref, rtol=1e-7, atol=1e-9 * np.abs(df_ref).max())
+    vals, idx, pts = m.acq_topk("LCB", 2.0, fmin, Xc, 5, index_offset=1000)
+    order = np.argsort(f_ref.ravel(), kind="stable")[:5]
+    assert np.array_equal(idx - 1000, order)
+    m.close()
+
+
+def test_model_grows_like_bo_loop():
+    """set_XY with one more point per step (GPModel.updateModel, gpmodel.py:78-93): N crosses the 128 padding boundary."""
+    X, Y, ls = _synth(140, 2)
+    m = native.NativeModel("mat52", False, 2, 1, n_cap=256, cand_block=128)
+    for n in (3, 5, 127, 128, 129, 140):
+        m.set_data(X[:n], Y[:n])
+        m.set_theta(1.3, [0.7], 1e-3)
+        info, logL, grads = m.fit(True)
+        assert info == 0
+        l_ref, g_ref, _ = O.log_likelihood_and_gradients("mat52", X[:n], Y[:n], 1.3, [0.7], 1e-3, ard=False)
+        assert_allclose(logL, l_ref, rtol=1e-9)
+        assert_allclose(grads, g_ref, rtol=1e-7, atol=1e-9 * np.abs(g_ref).max())
+    m.close()
+
+
+def test_not_positive_definite_returns_info():
+    """Duplicate inputs + zero noise: Ky is singular up to the 1e-8 jitter of exact_gaussian_inference.py:56."""
+    X = np.zeros((200, 2))
+    Y = np.ones((200, 1))
+    m = native.NativeModel("rbf", True, 2, 1, n_cap=200, cand_block=128)
+    m.set_data(X, Y)
+    m.set_theta(1.0, [1.0, 1.0], 0.0)
+    info, _, _ = m.fit(False, extra_jitter=-2e-8)   # net diagonal shift < 0 -> a non-positive pivot must be reported
+    assert info > 0
+    m.close()
