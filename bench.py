@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the exact-GP hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Metric (BASELINE.json): NLL+grad evals/s (N=16384, D=16, RBF-ARD, fp64).  One step = one pass of the hot path
+(K build -> Ky -> Cholesky + inverse -> alpha -> log-likelihood -> all D+2 gradients) over the synthetic data of SURVEY.md 8(d).
+
+  value     evals/s with X, Y resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e       the same through the host-buffer C-ABI call sequence (set_data: H2D of X, Y; set_theta; fit; D2H of D+3 doubles)
+  roofline  the dominant kernel (DMMA GEMM engine): algorithmic N^3 flops per eval / its summed launch time per eval,
+            against a cuBLAS DGEMM 8192^3 rate measured in the same process (MEASURED_PEAKS.json holds no fp64 figure)
+  cpu_baseline  the CPU oracle (oracle/gp_oracle.py, NumPy/SciPy + the reference's own C helper) on the box's host cores
+  aux       EI value+gradient candidates/s (config 4), candidates sharded over the ranks, top-5 all-gathered
+
+Multi-GPU: the N x N factorisation stays on one GPU (north_star) -> NLL evals are independent replicas (weak scaling);
+the acquisition shards its candidate set.  `--impl reference` times the CPU oracle (rank 0 only).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRAIN, DIM = 16384, 16
+KIND = "rbf"
+METRIC = "nll_grad_evals_per_s"
+UNIT = "evals/s"
+WORKLOAD = "GPRegression RBF-ARD N=16384 D=16 fp64 log_likelihood+gradients (SURVEY 8d headline)"
+
+
+def synth(N, D, seed=1234):
+    """SURVEY.md 8(d) generator (NumPy legacy RandomState so CPU and GPU legs share bits)."""
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(0, 1, (N, D))
+    w = rs.randn(D)
+    Y = np.sin(X @ w)[:, None] + 0.05 * rs.randn(N, 1)
+    Y = (Y - Y.mean()) / Y.std()
+    ls = 0.5 + 0.5 * np.arange(D) / D
+    return X, Y, ls
+
+
+def algorithmic_flops(N, D):
+    return float(N) ** 3 + float(N) ** 2 * (6 * D + 62)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle): the only place bench.py executes oracle/
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_eval_time(N, D, kind=KIND):
+    """One oracle NLL+grad evaluation at (N, D); returns (total s, cubic LAPACK part s)."""
+    from oracle import gp_oracle as O
+    X, Y, ls = synth(N, D)
+    t0 = time.perf_counter()
+    Kmat = O.K(kind, X, None, 1.0, ls, True)
+    Ky = Kmat.copy()
+    Ky[np.diag_indices_from(Ky)] += 1e-2 + 1e-8
+    t1 = time.perf_counter()
+    Wi, LW, _, logdet = O.pdinv(Ky, with_Li=True)      # the reference's pdinv includes the unused dtrtri (linalg.py:209)
+    alpha, _ = O.dpotrs(LW, Y, lower=1)
+    t2 = time.perf_counter()
+    dL_dK = 0.5 * (O.tdot(alpha) - Wi)
+    O.update_gradients_full(kind, dL_dK, X, None, 1.0, ls, True, native=O.ref_native() is not None)
+    t3 = time.perf_counter()
+    return t3 - t0, t2 - t1
+
+
+def cpu_baseline(sample_n=4096):
+    import threadpoolctl
+    cores = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1])
+    cpu_eval_time(1024, DIM)  # warm up BLAS threads
+    total, cubic = cpu_eval_time(sample_n, DIM)
+    scale = N_TRAIN / sample_n
+    est = cubic * scale ** 3 + (total - cubic) * scale ** 2
+    from oracle import gp_oracle as O
+    return {"value": 1.0 / est, "unit": UNIT, "cores": int(cores), "kind": "port",
+            "sample": "one oracle eval at N=%d D=%d took %.2f s (LAPACK part %.2f s); extrapolated to N=%d as cubic x%d + "
+                      "quadratic x%d = %.1f s/eval; lengthscale loop = reference C helper %s" %
+                      (sample_n, DIM, total, cubic, N_TRAIN, scale ** 3, scale ** 2, est,
+                       "(oracle/_ref)" if O.ref_native() is not None else "unavailable -> NumPy")}, est
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    # each "step" = one bounded-sample oracle evaluation, reported in the metric's unit through the cubic/quadratic scaling
+    sample_n = 2048
+    ests = []
+    for i in range(args.warmup + args.steps):
+        total, cubic = cpu_eval_time(sample_n, DIM)
+        scale = N_TRAIN / sample_n
+        if i >= args.warmup:
+            ests.append(cubic * scale ** 3 + (total - cubic) * scale ** 2)
+    import threadpoolctl
+    cores = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1])
+    est = float(np.mean(ests))
+    line = {"impl": "reference", "metric": METRIC, "value": 1.0 / est, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference path (the reference package cannot be "
+                       "imported here: paramz is un-vendored); each step is an N=%d evaluation scaled to N=%d" % (sample_n, N_TRAIN)},
+            "cpu_baseline": {"value": 1.0 / est, "unit": UNIT, "cores": int(cores), "kind": "port",
+                             "sample": "N=%d D=%d oracle evals, cubic part x%d + quadratic part x%d" %
+                                       (sample_n, DIM, (N_TRAIN // sample_n) ** 3, (N_TRAIN // sample_n) ** 2)},
+            "e2e": {"value": 1.0 / est, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-ml): runs DURING the timed region
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from gaussian_process_optimization_b200 import native
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    X, Y, ls = synth(N_TRAIN, DIM)
+    model = native.NativeModel(KIND, True, DIM, 1, n_cap=N_TRAIN, cand_block=2048)
+    Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda()
+    model.set_data(Xd, Yd)                 # device-resident inputs for `value`
+
+    def theta(i):                          # every step evaluates a (slightly) different hyper-parameter vector, like L-BFGS-B
+        return 1.0 + 1e-3 * (i % 7), ls * (1.0 + 1e-3 * (i % 5)), 1e-2
+
+    def step_resident(i):
+        v, l, nz = theta(i)
+        model.set_theta(v, l, nz)
+        info, logL, g = model.fit(True)
+        assert info == 0 and np.isfinite(logL) and np.all(np.isfinite(g))
+        return logL
+
+    def step_e2e(i):
+        v, l, nz = theta(i)
+        model.set_data(X, Y)               # host buffers: H2D inside the timed region
+        model.set_theta(v, l, nz)
+        info, logL, g = model.fit(True)    # D2H of the D+3 results inside
+        assert info == 0
+        return logL
+
+    # ---- fp64 peak: cuBLAS DGEMM 8192^3 in this process (burst, best of 5) ----
+    n = 8192
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    B = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    C = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    best = 1e30
+    for i in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(A, B, out=C)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+    peak_tflops = 2.0 * n ** 3 / best / 1e12
+    del A, B, C
+    torch.cuda.empty_cache()
+
+    # ---- warm-up ----
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    step_e2e(0)
+
+    # ---- timed: resident ----
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(100 + i)
+    e1.record()
+    barrier()
+    t_res = e0.elapsed_time(e1) * 1e-3
+    launches = native.launch_count() - launches0
+
+    # ---- timed: e2e ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(200 + i)
+    e1.record()
+    barrier()
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop()
+
+    # ---- roofline leg: per-launch events around the dominant kernel, same steps ----
+    native.profile_gemm(1)
+    for i in range(args.steps):
+        step_resident(100 + i)
+    gemm_ms, gemm_flops_exec, gemm_launches = native.profile_gemm_collect()
+    native.profile_gemm(0)
+
+    if world > 1:
+        tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = float(tt[0]), float(tt[1])
+
+    # ---- aux: EI value+gradient candidates/s over a candidate set sharded across the ranks (config 4) ----
+    aux = None
+    try:
+        aux = bench_acquisition(args, model, rank, world, barrier)
+    except Exception as exc:  # report, never hide
+        aux = {"error": repr(exc)}
+
+    if rank == 0:
+        value = world * args.steps / t_res
+        gemm_s_per_eval = gemm_ms * 1e-3 / args.steps
+        achieved = float(N_TRAIN) ** 3 / gemm_s_per_eval / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu, _ = cpu_baseline() if world == 1 else (None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": "replicas x%d (N x N factorisation stays on one GPU)" % world,
+                       "l2": "inputs larger than L2 (three 2.1 GB fp64 matrices per eval vs 126 MB L2)",
+                       "algorithmic_flops_per_eval": algorithmic_flops(N_TRAIN, DIM),
+                       "algorithmic_tflops": algorithmic_flops(N_TRAIN, DIM) * args.steps / t_res / 1e12},
+            "e2e": {"value": world * args.steps / t_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + (DIM + 2) * 8), "d2h_bytes_per_step": int((DIM + 3) * 8 + 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_dmma_kernel (fp64 DMMA.8x8x4 GEMM engine)", "achieved": achieved,
+                         "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (burst, best of 5); MEASURED_PEAKS.json has no fp64 entry",
+                         "launches_per_eval": gemm_launches / args.steps, "kernel_s_per_eval": gemm_s_per_eval,
+                         "kernel_share_of_step": gemm_s_per_eval / (t_res / args.steps),
+                         "executed_tflops": gemm_flops_exec / (gemm_ms * 1e-3) / 1e12},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if aux is not None:
+            line["aux"] = aux
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_acquisition(args, model, rank, world, barrier):
+    """Config 4: EI value + gradient over a synthetic candidate set, sharded over the ranks; per-shard top-5 all-gathered."""
+    import torch
+    import torch.distributed as dist
+    from gaussian_process_optimization_b200 import native
+    per_rank = 4096
+    chunk = np.random.RandomState(4321).uniform(0, 1, (2 ** 20, DIM))       # chunk c = RandomState(4321 + c)
+    shard = torch.from_numpy(np.ascontiguousarray(chunk[rank * per_rank:(rank + 1) * per_rank])).cuda()
+    model.set_theta(1.0, 0.5 + 0.5 * np.arange(DIM) / DIM, 1e-2)
+    info, _, _ = model.fit(False)
+    assert info == 0
+    fmin = model.fmin()
+    model.acquisition("EI", 0.01, fmin, shard, with_gradients=True)          # warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = model.acquisition("EI", 0.01, fmin, shard, with_gradients=True)
+    vals, idx, pts = model.acq_topk("EI", 0.01, fmin, shard, 5, index_offset=rank * per_rank)
+    if world > 1:
+        mine = torch.from_numpy(np.concatenate([vals, idx.astype(np.float64), pts.ravel()])).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        allv = torch.stack(gathered).cpu().numpy()
+        cand = sorted((allv[g, i], int(allv[g, 5 + i])) for g in range(world) for i in range(5))[:5]
+    else:
+        cand = sorted(zip(vals.tolist(), idx.tolist()))[:5]
+    e1.record()
+    barrier()
+    t = e0.elapsed_time(e1) * 1e-3
+    if world > 1:
+        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+    n_cand = per_rank * world
+    fl = 2.0 * N_TRAIN ** 2 + N_TRAIN * (6 * DIM + 40) + float(N_TRAIN) ** 2 + N_TRAIN * (3 * DIM + 30)  # grad pass + top-k value pass
+    return {"metric": "ei_value_gradient_candidates_per_s", "value": n_cand / t, "unit": "candidates/s",
+            "candidates": n_cand, "per_rank": per_rank, "model_N": N_TRAIN, "D": DIM, "seconds": t,
+            "algorithmic_tflops": fl * n_cand / t / 1e12, "top5_global_idx": [c[1] for c in cand], "scaling": "weak",
+            "note": "each candidate is scored twice inside the timed region: value+gradient pass, then the value-only fused top-5 pass"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpb200", choices=["gpb200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -860,6 +860,9 @@ int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, voi
   return 0;
 }
 
+int gpb_profile_gemm(int enable) { return gemm_profile_enable(enable); }
+int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches) { return gemm_profile_collect(ms, flops, launches); }
+
 int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb, double beta,
               double *C, int ldc, void *stream) {
   GPB_REQUIRE(A && B && C, "dgemm: NULL argument");

@@ -135,6 +135,8 @@ struct GemmArgs {
   int khi_mode;  // 0: K       1: row0 + 128  2: col0 + 128
 };
 int gemm_launch(int layout_a, int layout_b, const GemmArgs &g, cudaStream_t s);
+int gemm_profile_enable(int on);
+int gemm_profile_collect(double *ms, double *flops, long long *launches);
 
 // linalg drivers (gpb_chol.cu)
 int factor_potrf_inv(Factor &f);                 // A -> L, Mi = L^-1, *info

@@ -11,6 +11,8 @@
 // Triangular structure is exploited at tile granularity through a per-tile k-range (klo_mode / khi_mode) and through
 // tri_out (only lower tiles are produced): operands that are triangular carry explicit zeros inside their 128x128 diagonal
 // blocks, blocks strictly above the diagonal are never read.
+#include <vector>
+
 #include "gpb_common.cuh"
 
 namespace gpb {
@@ -169,6 +171,69 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs p) 
   }
 }
 
+// ---- optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream around every GEMM ----
+struct GemmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // pairs (start, stop)
+  size_t used = 0;
+  double flops = 0.0;           // executed tile flops (diagonal tiles counted in full)
+  long long launches = 0;
+};
+static GemmProfile g_prof;
+
+int gemm_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  g_prof.flops = 0.0;
+  g_prof.launches = 0;
+  return 0;
+}
+
+// -> total milliseconds spent in GEMM launches since enable / last collect, executed flops, launch count
+int gemm_profile_collect(double *ms, double *flops, long long *launches) {
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    GPB_CUDA(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float t = 0.f;
+    GPB_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (flops) *flops = g_prof.flops;
+  if (launches) *launches = g_prof.launches;
+  g_prof.used = 0;
+  g_prof.flops = 0.0;
+  g_prof.launches = 0;
+  return 0;
+}
+
+static int prof_event(cudaStream_t s) {
+  if (g_prof.used == g_prof.ev.size()) {
+    cudaEvent_t e;
+    GPB_CUDA(cudaEventCreate(&e));
+    g_prof.ev.push_back(e);
+  }
+  GPB_CUDA(cudaEventRecord(g_prof.ev[g_prof.used++], s));
+  return 0;
+}
+
+static double tile_flops(const GemmArgs &g) {
+  // sum over launched tiles of 2 * 128 * 128 * (khi - klo)
+  const int tm = g.M / BM, tn = g.N / BN;
+  double k_sum = 0.0;
+  for (int i = 0; i < tm; ++i) {
+    const int jmax = g.tri_out ? i + 1 : tn;
+    for (int j = 0; j < jmax; ++j) {
+      const int row0 = i * BM, col0 = j * BN;
+      int klo = (g.klo_mode == 1) ? row0 : (g.klo_mode == 2) ? col0 : 0;
+      int khi = (g.khi_mode == 1) ? row0 + BM : (g.khi_mode == 2) ? col0 + BN : g.K;
+      if (khi > g.K) khi = g.K;
+      k_sum += (khi - klo);
+    }
+  }
+  return 2.0 * BM * BN * k_sum;
+}
+
 template <int LA, int LB>
 static int launch_t(const GemmArgs &g, cudaStream_t s) {
   constexpr int A_TILE = (LA == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
@@ -182,9 +247,15 @@ static int launch_t(const GemmArgs &g, cudaStream_t s) {
   const int tm = g.M / BM, tn = g.N / BN;
   const int tiles = g.tri_out ? tm * (tm + 1) / 2 : tm * tn;
   if (tiles == 0) return 0;
+  if (g_prof.on) GPB_TRY(prof_event(s));
   gemm_dmma_kernel<LA, LB><<<tiles, GEMM_THREADS, smem, s>>>(g);
   count_launch();
   GPB_CHECK_LAUNCH();
+  if (g_prof.on) {
+    GPB_TRY(prof_event(s));
+    g_prof.flops += tile_flops(g);
+    g_prof.launches += 1;
+  }
   return 0;
 }
 

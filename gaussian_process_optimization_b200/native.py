@@ -111,6 +111,17 @@ def dgemm(ta, tb, alpha, A, B, beta, C):
     return C
 
 
+def profile_gemm(enable):
+    check(_lib.load().gpb_profile_gemm(int(enable)), "profile_gemm")
+
+
+def profile_gemm_collect():
+    """-> (milliseconds in GEMM kernels, executed flops, launches) since the last collect."""
+    ms, fl, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_longlong(0)
+    check(_lib.load().gpb_profile_gemm_collect(ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)), "profile_gemm_collect")
+    return ms.value, fl.value, n.value
+
+
 def launch_count():
     return int(_lib.load().gpb_launch_count())
 

@@ -111,6 +111,12 @@ int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, c
 int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb,
               double beta, double *C, int ldc, void *stream);
 
+/* Measurement hook for bench.py's roofline leg: when enabled, every DMMA GEMM launch is bracketed by CUDA events on its
+ * stream.  collect() waits for them and returns the summed kernel time (ms), the executed tile flops and the launch count
+ * since the last collect. */
+int gpb_profile_gemm(int enable);
+int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches);
+
 #ifdef __cplusplus
 }
 #endif
