@@ -861,6 +861,7 @@ int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, voi
 }
 
 int gpb_profile_gemm(int enable) { return gemm_profile_enable(enable); }
+int gpb_gemm_config(int cfg) { return gemm_force_config(cfg); }
 int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches) { return gemm_profile_collect(ms, flops, launches); }
 
 int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb, double beta,

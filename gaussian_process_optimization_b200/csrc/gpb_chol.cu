@@ -29,6 +29,63 @@ namespace gpb {
 constexpr int LEAF_THREADS = 256;
 constexpr int LEAF_LD = TILE + 1;
 
+// The 16 steps j = 16 JB + jt of one column block.  JB is a template parameter so that for every register entry (a, b)
+// the membership test  y > j && (x <= j || y <= x)  collapses at compile time to at most three per-thread booleans
+// (tx > jt, ty <= jt, tx <= ty): the body is straight-line predicated DFMAs, no per-entry index arithmetic or branches.
+template <int MODE, int JB>
+__device__ __forceinline__ void leaf_sweep_block(double (&s)[8][8], double *colbuf, double *piv, int tx, int ty, int tid,
+                                                 int index_base, int *info, bool &failed) {
+  const bool t_le = tx <= ty;  // y <= x inside a diagonal (a == b) register block
+#pragma unroll 1
+  for (int jt = 0; jt < 16; ++jt) {
+    const int j = JB * 16 + jt;
+    double *cb = colbuf + (j & 1) * TILE;
+    if (tx == jt) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) cb[ty + 16 * a] = s[a][JB];
+    }
+    __syncthreads();
+    const double pivot = cb[j];
+    if (!(pivot > 0.0) && !failed) {
+      failed = true;
+      if (tid == 0) atomicCAS(info, 0, index_base + j + 1);
+    }
+    // the epilogue divides by sqrt(piv): Cholesky pivots are L_jj^2, in MODE 1 the diagonal entry is L_jj itself
+    if (tid == 0) piv[j] = MODE ? pivot * pivot : pivot;
+    const double rinv = 1.0 / pivot;
+    const bool y_gt = tx > jt;   // y > j inside column block JB
+    const bool x_le = ty <= jt;  // x <= j inside row block JB
+    double w[8], u[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      if (MODE && a > JB) continue;  // trtri-only: rows below the current block are never touched
+      double c = cb[ty + 16 * a];
+      if (a == JB && ty == jt) c = 1.0;
+      w[a] = c * rinv;
+    }
+#pragma unroll
+    for (int b = JB; b < 8; ++b) u[b] = cb[tx + 16 * b];
+#pragma unroll
+    for (int b = JB; b < 8; ++b) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        bool act;
+        if (a < JB) {
+          act = true;                        // W^T rows: x <= j always
+        } else if (a == JB) {
+          if (MODE) act = x_le;
+          else act = x_le || (b == a && t_le);   // x > j: trailing matrix, needs y <= x (impossible for b > a)
+        } else {
+          if (MODE || b > a) continue;       // x > j: only the lower part of the trailing matrix (Cholesky mode)
+          act = (b < a) || t_le;
+        }
+        if (b == JB) act = act && y_gt;
+        if (act) s[a][b] = fma(-w[a], u[b], s[a][b]);
+      }
+    }
+  }
+}
+
 // MODE 0: Cholesky + inverse (A is overwritten by L).  MODE 1: A already holds a lower-triangular factor L; only W = L^-1
 // is produced (forward elimination on [L | I]: the same sweep restricted to the W^T rows, pivot = L_jj).
 template <int MODE>
@@ -54,49 +111,14 @@ leaf_potrf_inv_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, 
   }
 
   bool failed = false;
-  for (int j = 0; j < TILE; ++j) {
-    double *cb = colbuf + (j & 1) * TILE;
-    const int jb = j >> 4, jt = j & 15;
-    if (tx == jt) {
-#pragma unroll
-      for (int b = 0; b < 8; ++b)
-        if (b == jb) {
-#pragma unroll
-          for (int a = 0; a < 8; ++a) cb[ty + 16 * a] = s[a][b];
-        }
-    }
-    __syncthreads();
-    const double pivot = cb[j];
-    if (!(pivot > 0.0) && !failed) {
-      failed = true;
-      if (tid == 0) atomicCAS(info, 0, index_base + j + 1);
-    }
-    // the epilogue divides by sqrt(piv): Cholesky pivots are L_jj^2, in MODE 1 the diagonal entry is L_jj itself
-    if (tid == 0) piv[j] = MODE ? pivot * pivot : pivot;
-    const double rinv = 1.0 / pivot;
-    double w[8], u[8];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) {
-      const int x = ty + 16 * a;
-      w[a] = (x == j) ? rinv : cb[x] * rinv;
-    }
-#pragma unroll
-    for (int b = 0; b < 8; ++b) u[b] = cb[tx + 16 * b];
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      if (b >= jb) {  // warp-uniform: column blocks entirely <= j are finished
-        const int y = tx + 16 * b;
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          // row block containing some x <= j: W^T rows (any y > j); otherwise only the lower part of the trailing matrix
-          if ((16 * a <= j) || (!MODE && b <= a)) {
-            const int x = ty + 16 * a;
-            if (y > j && (x <= j || (!MODE && y <= x))) s[a][b] = fma(-w[a], u[b], s[a][b]);
-          }
-        }
-      }
-    }
-  }
+  leaf_sweep_block<MODE, 0>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
+  leaf_sweep_block<MODE, 1>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
+  leaf_sweep_block<MODE, 2>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
+  leaf_sweep_block<MODE, 3>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
+  leaf_sweep_block<MODE, 4>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
+  leaf_sweep_block<MODE, 5>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
+  leaf_sweep_block<MODE, 6>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
+  leaf_sweep_block<MODE, 7>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
   __syncthreads();
 
   // ---- epilogue: scale, stage through shared memory, coalesced writes of L (into A) and W = L^-1 (into Mi) ----

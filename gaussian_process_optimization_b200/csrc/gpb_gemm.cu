@@ -3,27 +3,29 @@
 //   C = alpha * op(A) * op(B) + beta * C        (row-major everywhere, M,N multiples of 128, K multiple of 16)
 //
 // Blackwell has no f64 kind for tcgen05/UMMA, so the FP64 tensor path on sm_100a is the warp-level
-// mma.sync.aligned.m8n8k4.f64 (SASS: DMMA.8x8x4).  One CTA owns a 128x128 output tile, 8 warps each own a 64x32 sub-tile
-// (8x4 DMMA accumulators = 64 fp64 registers per lane).  Operand tiles (128 x 16 k) are staged through shared memory with
-// a 3-stage cp.async (LDGSTS) pipeline; row strides are padded (20 / 132 doubles == 4 mod 16) so that every half-warp's
-// 64-bit fragment loads hit 16 distinct bank pairs (conflict free) in both storage orders.
+// mma.sync.aligned.m8n8k4.f64 (SASS: DMMA.8x8x4, 16 issue cycles per sub-partition -> 64 FMA/clk/SM).  Operand tiles
+// (rows x 16 k) are staged through shared memory with a 3-stage cp.async (LDGSTS) pipeline; row strides are padded
+// (20 / rows+4 doubles == 4 mod 16) so that every half-warp's 64-bit fragment loads hit 16 distinct bank pairs (conflict
+// free) in both storage orders.
 //
-// Triangular structure is exploited at tile granularity through a per-tile k-range (klo_mode / khi_mode) and through
-// tri_out (only lower tiles are produced): operands that are triangular carry explicit zeros inside their 128x128 diagonal
-// blocks, blocks strictly above the diagonal are never read.
+// Three tile configurations share one kernel template (picked per launch from the number of output tiles):
+//   BIG    64 x 128 per CTA, 4 warps (each 64 x 32), 2 CTAs resident per SM: while one CTA sits at its per-k-tile barrier
+//          the other keeps the DMMA pipe busy (a single 128x128 CTA per SM left ~10% barrier/ramp bubbles in ncu);
+//   MID    64 x 64, 4 warps (32 x 32)   -- 4x the CTAs of a 128-tile grid for problems that would not fill 148 SMs;
+//   SMALL  32 x 32, 4 warps (16 x 16)   -- 16x the CTAs, for the bottom levels of the recursion (128..512-sized blocks).
+//
+// Triangular structure is exploited at 128-block granularity through a per-tile k-range (klo_mode / khi_mode) and through
+// tri_out (only tiles touching the lower triangle are produced): operands that are triangular carry explicit zeros inside
+// their 128x128 diagonal blocks, blocks strictly above the diagonal are never read.
 #include <vector>
 
 #include "gpb_common.cuh"
 
 namespace gpb {
 
-constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int BK = 16;
 constexpr int STAGES = 3;
-constexpr int GEMM_THREADS = 256;
-constexpr int LD_ROWK = BK + 4;    // operand stored [row][k]  (k contiguous)
-constexpr int LD_COLK = BM + 4;    // operand stored [k][row]  (row contiguous)
-constexpr int TILE_ROWK = BM * LD_ROWK;  // doubles per stage
-constexpr int TILE_COLK = BK * LD_COLK;
+constexpr int LD_ROWK = BK + 4;  // operand stored [row][k]  (k contiguous)
 
 __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gmem_src) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -41,37 +43,48 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Stage one 128(row) x 16(k) operand tile.  base points at element (row0, 0) [ROWK] or (0, row0) [COLK] of the operand,
+// Stage one ROWS(row) x 16(k) operand tile.  base points at element (row0, 0) [ROWK] or (0, row0) [COLK] of the operand,
 // kk is the k offset of this tile.
-template <int LAYOUT>
+template <int LAYOUT, int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile(double *s, const double *__restrict__ base, int ld, int kk, int tid) {
+  constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks
+  static_assert(CHUNKS % THREADS == 0, "tile/threads mismatch");
   if (LAYOUT == LAYOUT_ROWK) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int chunk = tid + i * GEMM_THREADS;  // 1024 chunks of 2 doubles
+    for (int i = 0; i < CHUNKS / THREADS; ++i) {
+      const int chunk = tid + i * THREADS;
       const int row = chunk >> 3, c = chunk & 7;
       cp_async16(s + row * LD_ROWK + 2 * c, base + (size_t)row * ld + kk + 2 * c);
     }
   } else {
+    constexpr int LD = ROWS + 4, CPR = ROWS / 2;  // chunks per k-row
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int chunk = tid + i * GEMM_THREADS;
-      const int kr = chunk >> 6, c = chunk & 63;
-      cp_async16(s + kr * LD_COLK + 2 * c, base + (size_t)(kk + kr) * ld + 2 * c);
+    for (int i = 0; i < CHUNKS / THREADS; ++i) {
+      const int chunk = tid + i * THREADS;
+      const int kr = chunk / CPR, c = chunk - kr * CPR;
+      cp_async16(s + kr * LD + 2 * c, base + (size_t)(kk + kr) * ld + 2 * c);
     }
   }
 }
 
-template <int LAYOUT>
+template <int LAYOUT, int ROWS>
 __device__ __forceinline__ double frag(const double *s, int row, int k) {
-  return (LAYOUT == LAYOUT_ROWK) ? s[row * LD_ROWK + k] : s[k * LD_COLK + row];
+  return (LAYOUT == LAYOUT_ROWK) ? s[row * LD_ROWK + k] : s[k * (ROWS + 4) + row];
 }
 
-template <int LA, int LB>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs p) {
+template <int LAYOUT, int ROWS>
+__host__ __device__ constexpr int tile_doubles() {
+  return (LAYOUT == LAYOUT_ROWK) ? ROWS * LD_ROWK : BK * (ROWS + 4);
+}
+
+template <int LA, int LB, int BM, int BN, int WARPS_M, int WARPS_N, int MIN_BLOCKS>
+__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_kernel(GemmArgs p) {
+  constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;  // warp tile
+  constexpr int MI = WTM / 8, NI = WTN / 8;
+  constexpr int A_TILE = tile_doubles<LA, BM>();
+  constexpr int B_TILE = tile_doubles<LB, BN>();
   extern __shared__ __align__(16) double smem[];
-  constexpr int A_TILE = (LA == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
-  constexpr int B_TILE = (LB == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
   double *sA = smem;
   double *sB = smem + STAGES * A_TILE;
 
@@ -79,42 +92,58 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs p) 
   int tm, tn;
   const int t = blockIdx.x;
   if (p.tri_out) {
-    // t = tm (tm + 1) / 2 + tn, tn <= tm
-    tm = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((tm + 1) * (tm + 2) / 2 <= t) ++tm;
-    while (tm * (tm + 1) / 2 > t) --tm;
-    tn = t - tm * (tm + 1) / 2;
+    // Tiles are enumerated by 128-row "super rows": super row i holds R = 128 / BM tile rows, each with
+    // C_i = (i + 1) * (128 / BN) tile columns (everything left of and including the diagonal 128-block).
+    constexpr int R = 128 / BM, CW = 128 / BN;
+    const int per = R * CW;  // tiles of one 128x128 block
+    // tiles before super row i: per * i (i + 1) / 2
+    const int q = t / per;   // index in units of 128-blocks (lower-triangular enumeration, row-major)
+    int i = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= q) ++i;
+    while (i * (i + 1) / 2 > q) --i;
+    const int rem = t - per * (i * (i + 1) / 2);  // index inside super row i: R rows x (i + 1) * CW cols
+    const int cols = (i + 1) * CW;
+    tm = i * R + rem / cols;
+    tn = rem % cols;
   } else {
-    const int tiles_n = p.N / BN;
-    tm = t / tiles_n;
-    tn = t - tm * tiles_n;
+    // grouped rasterisation: GROUP consecutive tile rows share their B panels while they are L2 resident
+    const int tiles_m = p.M / BM, tiles_n = p.N / BN;
+    constexpr int GROUP = 16;
+    const int in_group = GROUP * tiles_n;
+    const int gid = t / in_group;
+    const int first = gid * GROUP;
+    const int gsz = min(tiles_m - first, GROUP);
+    const int r = t - gid * in_group;
+    tm = first + r % gsz;
+    tn = r / gsz;
   }
   const int row0 = tm * BM, col0 = tn * BN;
-  int klo = (p.klo_mode == 1) ? row0 : (p.klo_mode == 2) ? col0 : 0;
-  int khi = (p.khi_mode == 1) ? row0 + BM : (p.khi_mode == 2) ? col0 + BN : p.K;
+  const int rblk = row0 & ~127, cblk = col0 & ~127;  // enclosing 128-block
+  int klo = (p.klo_mode == 1) ? rblk : (p.klo_mode == 2) ? cblk : 0;
+  int khi = (p.khi_mode == 1) ? rblk + 128 : (p.khi_mode == 2) ? cblk + 128 : p.K;
   if (khi > p.K) khi = p.K;
   const int ktiles = (khi - klo) / BK;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
-  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int wm = (warp / WARPS_N) * WTM, wn = (warp % WARPS_N) * WTN;
 
   const double *Abase = (LA == LAYOUT_ROWK) ? p.A + (size_t)row0 * p.lda : p.A + row0;
   const double *Bbase = (LB == LAYOUT_ROWK) ? p.B + (size_t)col0 * p.ldb : p.B + col0;
 
-  double acc[8][4][2];
+  double acc[MI][NI][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // ---- prologue ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) {
-      load_tile<LA>(sA + s * A_TILE, Abase, p.lda, klo + s * BK, tid);
-      load_tile<LB>(sB + s * B_TILE, Bbase, p.ldb, klo + s * BK, tid);
+      load_tile<LA, BM, THREADS>(sA + s * A_TILE, Abase, p.lda, klo + s * BK, tid);
+      load_tile<LB, BN, THREADS>(sB + s * B_TILE, Bbase, p.ldb, klo + s * BK, tid);
     }
     cp_async_commit();
   }
@@ -126,8 +155,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs p) 
       const int nt = kt + STAGES - 1;
       if (nt < ktiles) {
         const int s = nt % STAGES;
-        load_tile<LA>(sA + s * A_TILE, Abase, p.lda, klo + nt * BK, tid);
-        load_tile<LB>(sB + s * B_TILE, Bbase, p.ldb, klo + nt * BK, tid);
+        load_tile<LA, BM, THREADS>(sA + s * A_TILE, Abase, p.lda, klo + nt * BK, tid);
+        load_tile<LB, BN, THREADS>(sB + s * B_TILE, Bbase, p.ldb, klo + nt * BK, tid);
       }
       cp_async_commit();
     }
@@ -136,15 +165,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs p) 
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
       const int k0 = ks * 4 + tq;
-      double a[8], b[4];
+      double a[MI], b[NI];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = frag<LA>(a_s, wm + i * 8 + g, k0);
+      for (int i = 0; i < MI; ++i) a[i] = frag<LA, BM>(a_s, wm + i * 8 + g, k0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = frag<LB>(b_s, wn + j * 8 + g, k0);
+      for (int j = 0; j < NI; ++j) b[j] = frag<LB, BN>(b_s, wn + j * 8 + g, k0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
   cp_async_wait<0>();
@@ -152,10 +181,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_dmma_kernel(GemmArgs p) 
   // ---- epilogue: lane holds (row g, cols 2 tq, 2 tq + 1) of every 8x8 accumulator ----
   const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < MI; ++i) {
     const int row = row0 + wm + i * 8 + g;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NI; ++j) {
       const int col = col0 + wn + j * 8 + 2 * tq;
       double2 *ptr = reinterpret_cast<double2 *>(p.C + (size_t)row * p.ldc + col);
       double2 o;
@@ -176,16 +205,22 @@ struct GemmProfile {
   bool on = false;
   std::vector<cudaEvent_t> ev;  // pairs (start, stop)
   size_t used = 0;
-  double flops = 0.0;           // executed tile flops (diagonal tiles counted in full)
+  double flops = 0.0;           // executed tile flops (diagonal blocks counted in full)
   long long launches = 0;
 };
 static GemmProfile g_prof;
+static int g_forced_config = 0;  // 0 auto, 1 BIG, 2 MID, 3 SMALL (tuning / tests)
 
 int gemm_profile_enable(int on) {
   g_prof.on = on != 0;
   g_prof.used = 0;
   g_prof.flops = 0.0;
   g_prof.launches = 0;
+  return 0;
+}
+
+int gemm_force_config(int cfg) {
+  g_forced_config = cfg;
   return 0;
 }
 
@@ -217,58 +252,73 @@ static int prof_event(cudaStream_t s) {
   return 0;
 }
 
-static double tile_flops(const GemmArgs &g) {
-  // sum over launched tiles of 2 * 128 * 128 * (khi - klo)
-  const int tm = g.M / BM, tn = g.N / BN;
+static double block_flops(const GemmArgs &g) {
+  // sum over computed 128x128 blocks of 2 * 128 * 128 * (khi - klo)
+  const int tm = g.M / 128, tn = g.N / 128;
   double k_sum = 0.0;
   for (int i = 0; i < tm; ++i) {
     const int jmax = g.tri_out ? i + 1 : tn;
     for (int j = 0; j < jmax; ++j) {
-      const int row0 = i * BM, col0 = j * BN;
+      const int row0 = i * 128, col0 = j * 128;
       int klo = (g.klo_mode == 1) ? row0 : (g.klo_mode == 2) ? col0 : 0;
-      int khi = (g.khi_mode == 1) ? row0 + BM : (g.khi_mode == 2) ? col0 + BN : g.K;
+      int khi = (g.khi_mode == 1) ? row0 + 128 : (g.khi_mode == 2) ? col0 + 128 : g.K;
       if (khi > g.K) khi = g.K;
       k_sum += (khi - klo);
     }
   }
-  return 2.0 * BM * BN * k_sum;
+  return 2.0 * 128 * 128 * k_sum;
 }
 
-template <int LA, int LB>
+template <int LA, int LB, int BM, int BN, int WARPS_M, int WARPS_N, int MIN_BLOCKS>
 static int launch_t(const GemmArgs &g, cudaStream_t s) {
-  constexpr int A_TILE = (LA == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
-  constexpr int B_TILE = (LB == LAYOUT_ROWK) ? TILE_ROWK : TILE_COLK;
+  constexpr int A_TILE = tile_doubles<LA, BM>();
+  constexpr int B_TILE = tile_doubles<LB, BN>();
+  constexpr int THREADS = WARPS_M * WARPS_N * 32;
   const size_t smem = (size_t)STAGES * (A_TILE + B_TILE) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    GPB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int tm = g.M / BM, tn = g.N / BN;
-  const int tiles = g.tri_out ? tm * (tm + 1) / 2 : tm * tn;
+  const int b128m = g.M / 128, b128n = g.N / 128;
+  const int blocks128 = g.tri_out ? b128m * (b128m + 1) / 2 : b128m * b128n;
+  const int tiles = blocks128 * (128 / BM) * (128 / BN);
   if (tiles == 0) return 0;
   if (g_prof.on) GPB_TRY(prof_event(s));
-  gemm_dmma_kernel<LA, LB><<<tiles, GEMM_THREADS, smem, s>>>(g);
+  gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS><<<tiles, THREADS, smem, s>>>(g);
   count_launch();
   GPB_CHECK_LAUNCH();
   if (g_prof.on) {
     GPB_TRY(prof_event(s));
-    g_prof.flops += tile_flops(g);
+    g_prof.flops += block_flops(g);
     g_prof.launches += 1;
   }
   return 0;
 }
 
+template <int LA, int LB>
+static int launch_cfg(const GemmArgs &g, cudaStream_t s) {
+  const int b128m = g.M / 128, b128n = g.N / 128;
+  const int blocks128 = g.tri_out ? b128m * (b128m + 1) / 2 : b128m * b128n;
+  int cfg = g_forced_config;
+  if (cfg == 0) cfg = (blocks128 >= 148) ? 1 : (blocks128 >= 20) ? 2 : 3;
+  if (cfg == 1) return launch_t<LA, LB, 64, 128, 1, 4, 2>(g, s);
+  if (cfg == 2) return launch_t<LA, LB, 64, 64, 2, 2, 3>(g, s);
+  return launch_t<LA, LB, 32, 32, 2, 2, 4>(g, s);
+}
+
 int gemm_launch(int la, int lb, const GemmArgs &g, cudaStream_t s) {
-  GPB_REQUIRE(g.M % BM == 0 && g.N % BN == 0 && g.K % BK == 0, "gemm: M,N must be multiples of 128 and K of 16 (got %d %d %d)",
+  GPB_REQUIRE(g.M % 128 == 0 && g.N % 128 == 0 && g.K % BK == 0, "gemm: M,N must be multiples of 128 and K of 16 (got %d %d %d)",
               g.M, g.N, g.K);
   GPB_REQUIRE((g.lda % 2) == 0 && (g.ldb % 2) == 0 && (g.ldc % 2) == 0, "gemm: leading dimensions must be even");
   GPB_REQUIRE(!g.tri_out || g.M == g.N, "gemm: tri_out needs a square output");
+  GPB_REQUIRE((g.klo_mode == 0 && g.khi_mode == 0) || g.K % 128 == 0, "gemm: triangular k-ranges need K to be a multiple of 128");
   GPB_REQUIRE((((uintptr_t)g.A | (uintptr_t)g.B | (uintptr_t)g.C) & 15) == 0, "gemm: operands must be 16-byte aligned");
-  if (la == LAYOUT_ROWK && lb == LAYOUT_ROWK) return launch_t<LAYOUT_ROWK, LAYOUT_ROWK>(g, s);
-  if (la == LAYOUT_ROWK && lb == LAYOUT_COLK) return launch_t<LAYOUT_ROWK, LAYOUT_COLK>(g, s);
-  if (la == LAYOUT_COLK && lb == LAYOUT_COLK) return launch_t<LAYOUT_COLK, LAYOUT_COLK>(g, s);
-  if (la == LAYOUT_COLK && lb == LAYOUT_ROWK) return launch_t<LAYOUT_COLK, LAYOUT_ROWK>(g, s);
+  if (la == LAYOUT_ROWK && lb == LAYOUT_ROWK) return launch_cfg<LAYOUT_ROWK, LAYOUT_ROWK>(g, s);
+  if (la == LAYOUT_ROWK && lb == LAYOUT_COLK) return launch_cfg<LAYOUT_ROWK, LAYOUT_COLK>(g, s);
+  if (la == LAYOUT_COLK && lb == LAYOUT_COLK) return launch_cfg<LAYOUT_COLK, LAYOUT_COLK>(g, s);
+  if (la == LAYOUT_COLK && lb == LAYOUT_ROWK) return launch_cfg<LAYOUT_COLK, LAYOUT_ROWK>(g, s);
   set_error("gemm: bad layouts %d %d", la, lb);
   return -2;
 }

@@ -111,6 +111,11 @@ def dgemm(ta, tb, alpha, A, B, beta, C):
     return C
 
 
+def gemm_config(cfg):
+    """0 auto, 1 = 64x128, 2 = 64x64, 3 = 32x32 CTA tiles (tuning / tests)."""
+    check(_lib.load().gpb_gemm_config(int(cfg)), "gemm_config")
+
+
 def profile_gemm(enable):
     check(_lib.load().gpb_profile_gemm(int(enable)), "profile_gemm")
 

@@ -115,6 +115,8 @@ int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A
  * stream.  collect() waits for them and returns the summed kernel time (ms), the executed tile flops and the launch count
  * since the last collect. */
 int gpb_profile_gemm(int enable);
+/* Tuning/testing knob: force the GEMM tile configuration (0 auto, 1 = 64x128, 2 = 64x64, 3 = 32x32 CTA tiles). */
+int gpb_gemm_config(int cfg);
 int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches);
 
 #ifdef __cplusplus

@@ -26,6 +26,18 @@ def ev_time(fn, reps=5, warm=2):
 
 
 out = {}
+for n in (128, 256, 512, 1024):
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    B = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    C = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    res = {}
+    for cfg in (1, 2, 3):
+        native.gemm_config(cfg)
+        t = ev_time(lambda: native.dgemm(0, 0, 1.0, A, B, 0.0, C), reps=20, warm=3)
+        res["cfg%d_us" % cfg] = t * 1e6
+    native.gemm_config(0)
+    out["gemm_small_%d" % n] = res
+    print(n, res, flush=True)
 for n in (2048, 4096, 8192):
     A = torch.randn(n, n, dtype=torch.float64, device="cuda")
     B = torch.randn(n, n, dtype=torch.float64, device="cuda")

@@ -32,9 +32,18 @@ def _cond_tol(g, base):
 # ---------------------------------------------------------------------------------------------------------------------
 # DMMA GEMM engine
 # ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def gemm_cfg(request):
+    """Force one GEMM tile configuration (1 = 64x128, 2 = 64x64, 3 = 32x32 CTA tiles; 0 = automatic) for a test."""
+    native.gemm_config(request.param)
+    yield request.param
+    native.gemm_config(0)
+
+
+@pytest.mark.parametrize("gemm_cfg", [0, 1, 2, 3], indirect=True)
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 16), (256, 384, 272), (512, 128, 1024)])
-def test_dgemm_layouts(ta, tb, m, n, k):
+def test_dgemm_layouts(ta, tb, m, n, k, gemm_cfg):
     import torch
     g = torch.Generator(device="cpu").manual_seed(m + 7 * n + 13 * k + ta + 2 * tb)
     A = torch.randn((k, m) if ta else (m, k), generator=g, dtype=torch.float64)
@@ -45,6 +54,21 @@ def test_dgemm_layouts(ta, tb, m, n, k):
     native.dgemm(ta, tb, 1.5, A.cuda(), B.cuda(), -0.5, Cd)
     torch.cuda.synchronize()
     assert_allclose(Cd.cpu().numpy(), ref.numpy(), rtol=1e-12, atol=1e-11)
+
+
+@pytest.mark.parametrize("gemm_cfg", [1, 2, 3], indirect=True)
+def test_pdinv_each_gemm_config(gemm_cfg):
+    """The triangular k-ranges and the lower-tile enumeration of every tile configuration (n = 5 blocks of 128)."""
+    n = 600
+    rs = np.random.RandomState(n)
+    B = rs.randn(n, n + 3)
+    A = B @ B.T + 0.5 * n * np.eye(n)
+    rc, Ai, L, Li, logdet = native.pdinv(A)
+    assert rc == 0
+    Lr = np.linalg.cholesky(A)
+    assert_allclose(L, Lr, rtol=1e-10, atol=1e-12 * np.abs(Lr).max())
+    assert_allclose(Li, np.linalg.inv(Lr), rtol=1e-9, atol=1e-12)
+    assert_allclose(Ai, np.linalg.inv(A), rtol=1e-9, atol=1e-12 * np.abs(Ai).max())
 
 
 def test_dgemm_beta_zero_ignores_nan_in_c():
