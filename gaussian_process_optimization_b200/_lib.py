@@ -34,6 +34,7 @@ SIGNATURES = {
                                      c_int, c_void_p, c_int, c_void_p]),
     "gpb_pdinv": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_double_p, c_int, c_void_p]),
     "gpb_potrs": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "gpb_potri": (c_int, [c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "gpb_model_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int, c_int]),
     "gpb_model_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_size_t,
                                  c_void_p]),

@@ -860,6 +860,63 @@ int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, voi
   return 0;
 }
 
+int gpb_potri(int n, const double *L, int ldl, double *Ai, int ldai, int dev, void *stream) {
+  // A^-1 = L^-T L^-1 from the Cholesky factor: triangular-inverse recursion (dtrtri) + the lower-tile product M^T M
+  // (dlauum), then mirrored like GPy's symmetrify.
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GPB_REQUIRE(L && Ai && n >= 1 && ldl >= n && ldai >= n, "potri: bad arguments");
+  GPB_REQUIRE(gpb_device_count() > 0, "potri: no CUDA device visible -- libgpb200 has no CPU fallback");
+  const int np = round_up(n, TILE);
+  DevBuf lin, a, mi, w, misc, outb;
+  const double *Ld = L;
+  int ldd = ldl;
+  if (!dev) {
+    GPB_TRY(lin.alloc((size_t)n * n * sizeof(double)));
+    GPB_CUDA(cudaMemcpy2DAsync(lin.p, (size_t)n * sizeof(double), L, (size_t)ldl * sizeof(double), (size_t)n * sizeof(double), n,
+                               cudaMemcpyHostToDevice, s));
+    Ld = lin.d();
+    ldd = n;
+  }
+  GPB_TRY(a.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(mi.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(w.alloc((size_t)np * np * sizeof(double)));
+  GPB_TRY(misc.alloc(64));
+  pad_sym_kernel<<<dim3((np + 255) / 256, np), 256, 0, s>>>(Ld, ldd, n, a.d(), np);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  Factor f;
+  f.n = n;
+  f.np = np;
+  f.A = a.d();
+  f.Mi = mi.d();
+  f.W = w.d();
+  f.info = reinterpret_cast<int *>(misc.d() + 1);
+  f.stream = s;
+  GPB_TRY(factor_trtri(f));
+  GPB_TRY(factor_potri(f));
+  double *dd = Ai;
+  int ldo = ldai;
+  if (!dev) {
+    GPB_TRY(outb.alloc((size_t)n * n * sizeof(double)));
+    dd = outb.d();
+    ldo = n;
+  }
+  sym_copy_kernel<<<dim3((n + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, s>>>(f.W, np, dd, ldo, n);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  if (!dev)
+    GPB_CUDA(cudaMemcpy2DAsync(Ai, (size_t)ldai * sizeof(double), dd, (size_t)ldo * sizeof(double), (size_t)n * sizeof(double), n,
+                               cudaMemcpyDeviceToHost, s));
+  int info = 0;
+  GPB_CUDA(cudaMemcpyAsync(&info, f.info, sizeof(int), cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  if (info != 0) {
+    set_error("potri: factor is singular (pivot %d)", info);
+    return info;
+  }
+  return 0;
+}
+
 int gpb_profile_gemm(int enable) { return gemm_profile_enable(enable); }
 int gpb_gemm_config(int cfg) { return gemm_force_config(cfg); }
 int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches) { return gemm_profile_collect(ms, flops, launches); }

@@ -1,0 +1,787 @@
+"""GPyOpt surface for the Bayesian-optimisation step on top of the B200 GP model.
+
+Mirrors (paths relative to /root/reference/GPyOpt/GPyOpt):
+  models/base.py:7-33, models/gpmodel.py:9-177            BOModel, GPModel
+  acquisitions/base.py:6-68, EI.py:7-51, LCB.py:7-46      AcquisitionBase, AcquisitionEI, AcquisitionLCB
+  util/general.py:113-128,203-234                         get_quantiles, normalize
+  optimization/optimizer.py:28-61,130-168                 OptLbfgs, apply_optimizer
+  optimization/anchor_points_generator.py:8-98            ObjectiveAnchorPointsGenerator
+  optimization/acquisition_optimizer.py:16-77             AcquisitionOptimizer
+  experiment_design/random_design.py:7-91                 RandomDesign (np.random consumption order preserved)
+  core/task/space.py, variables.py                        Design_space with continuous / discrete variables
+  core/task/objective.py:24-76                            SingleObjective
+  core/evaluators/sequential.py:7-23                      Sequential
+  core/bo.py:20-260, methods/bayesian_optimization.py:76-202   BO, BayesianOptimization
+Host logic only (bookkeeping, RNG order, L-BFGS-B through SciPy like the reference); every GP quantity comes from the device.
+"""
+import time
+
+import numpy as np
+from scipy.special import erfc
+
+from . import kern as _kern
+from .models import GPRegression
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# errors / general utilities
+# ----------------------------------------------------------------------------------------------------------------------
+class InvalidConfigError(Exception):
+    pass
+
+
+class FullyExploredOptimizationDomainError(Exception):
+    pass
+
+
+def normalize(Y, normalization_type='stats'):
+    """util/general.py:203-234."""
+    Y = np.asarray(Y, dtype=float)
+    if np.max(Y.shape) != Y.size:
+        raise NotImplementedError('Only 1-dimensional arrays are supported.')
+    if normalization_type == 'stats':
+        Y_norm = Y - Y.mean()
+        std = Y.std()
+        if std > 0:
+            Y_norm /= std
+    elif normalization_type == 'maxmin':
+        Y_norm = Y - Y.min()
+        y_range = np.ptp(Y)
+        if y_range > 0:
+            Y_norm /= y_range
+            Y_norm = 2 * (Y_norm - 0.5)
+    else:
+        raise ValueError('Unknown normalization type: {}'.format(normalization_type))
+    return Y_norm
+
+
+def best_value(Y, sign=1):
+    """util/general.py:131-143."""
+    n = Y.shape[0]
+    Y_best = np.ones(n)
+    for i in range(n):
+        Y_best[i] = Y[:(i + 1)].min() if sign == 1 else Y[:(i + 1)].max()
+    return Y_best
+
+
+def get_quantiles(acquisition_par, fmin, m, s):
+    """util/general.py:113-128 -- only used for user-supplied (non-B200) models; the GPModel path fuses this on the device."""
+    if isinstance(s, np.ndarray):
+        s[s < 1e-10] = 1e-10
+    elif s < 1e-10:
+        s = 1e-10
+    u = (fmin - m - acquisition_par) / s
+    phi = np.exp(-0.5 * u ** 2) / np.sqrt(2 * np.pi)
+    Phi = 0.5 * erfc(-u / np.sqrt(2))
+    return (phi, Phi, u)
+
+
+def constant_cost_withGradients(x):
+    """core/task/cost.py:76-80."""
+    return np.ones(x.shape[0])[:, None], np.zeros(x.shape)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# design space
+# ----------------------------------------------------------------------------------------------------------------------
+class _Variable(object):
+    def __init__(self, name, var_type, domain):
+        self.name, self.type, self.domain = name, var_type, domain
+        self.dimensionality = 1
+        self.dimensionality_in_model = 1
+
+    def is_continuous(self):
+        return self.type == 'continuous'
+
+    def is_discrete(self):
+        return self.type == 'discrete'
+
+    def is_bandit(self):
+        return False
+
+    def get_bounds(self):
+        if self.type == 'continuous':
+            return [tuple(self.domain)]
+        return [(min(self.domain), max(self.domain))]
+
+    def round(self, value_array):
+        """variables.py:124-139 (continuous: clamp) and :186-199 (discrete: nearest domain value, first wins)."""
+        v = value_array[0]
+        if self.type == 'continuous':
+            lo, hi = self.domain[0], self.domain[1]
+            if v < lo:
+                v = lo
+            elif v > hi:
+                v = hi
+            return [v]
+        r = self.domain[0]
+        for dv in self.domain:
+            if np.abs(dv - v) < np.abs(r - v):
+                r = dv
+        return [r]
+
+
+class Design_space(object):
+    """core/task/space.py:14-100 for continuous and discrete variables (categorical / bandit arms are out of scope)."""
+
+    supported_types = ['continuous', 'discrete']
+
+    def __init__(self, space, constraints=None, store_noncontinuous=False):
+        self.config_space = space
+        self.space_expanded = []
+        for i, d in enumerate(space):
+            t = d.get('type', 'continuous')
+            if t not in self.supported_types:
+                raise InvalidConfigError("variable type %r is not supported on the B200 path" % t)
+            dim = int(d.get('dimensionality', 1))
+            name = d.get('name', 'var_' + str(i + 1))
+            for j in range(dim):
+                self.space_expanded.append(_Variable(name if dim == 1 else '{}_{}'.format(name, j + 1), t, d['domain']))
+        self.space = self.space_expanded
+        self.config_space_expanded = [{'name': v.name, 'type': v.type, 'domain': v.domain, 'dimensionality': 1}
+                                      for v in self.space_expanded]
+        self.dimensionality = len(self.space_expanded)
+        self.objective_dimensionality = self.dimensionality
+        self.model_dimensionality = self.dimensionality
+        self.model_input_dims = [1] * self.dimensionality
+        if constraints is not None:
+            for c in constraints:
+                if 'constrain' in c:
+                    c['constraint'] = c['constrain']
+        self.constraints = constraints
+
+    def has_constraints(self):
+        return self.constraints is not None
+
+    def has_continuous(self):
+        return any(v.is_continuous() for v in self.space)
+
+    def has_discrete(self):
+        return any(v.is_discrete() for v in self.space)
+
+    def _has_bandit(self):
+        return False
+
+    def get_bounds(self):
+        b = []
+        for v in self.space_expanded:
+            b += v.get_bounds()
+        return b
+
+    def get_continuous_bounds(self):
+        return [tuple(v.domain) for v in self.space if v.type == 'continuous']
+
+    def get_continuous_dims(self):
+        return [i for i, v in enumerate(self.space_expanded) if v.type == 'continuous']
+
+    def get_discrete_dims(self):
+        return [i for i, v in enumerate(self.space_expanded) if v.type == 'discrete']
+
+    def input_dim(self):
+        return self.dimensionality
+
+    def unzip_inputs(self, X):
+        return np.atleast_2d(X)
+
+    def zip_inputs(self, X):
+        return np.atleast_2d(X)
+
+    def indicator_constraints(self, x):
+        """core/task/space.py:303-318 (constraints are python expressions in `x`)."""
+        x = np.atleast_2d(x)
+        I_x = np.ones((x.shape[0], 1))
+        if self.constraints is not None:
+            for d in self.constraints:
+                constraint = eval('lambda x:' + d['constraint'], {'np': np})
+                ind_x = (constraint(x) < 0) * 1
+                I_x *= ind_x.reshape(x.shape[0], 1)
+        return I_x
+
+    def round_optimum(self, x):
+        """core/task/space.py:328-349."""
+        x = np.array(x)
+        if not ((x.ndim == 1) or (x.ndim == 2 and x.shape[0] == 1)):
+            raise ValueError("Unexpected dimentionality of x. Got {}, expected (1, N) or (N,)".format(x.ndim))
+        if x.ndim == 2:
+            x = x[0]
+        x_rounded = []
+        for i, variable in enumerate(self.space_expanded):
+            x_rounded.append(variable.round(x[i:i + 1]))
+        return np.atleast_2d(np.concatenate(x_rounded))
+
+
+def bounds_to_space(bounds):
+    return [{'name': 'var_' + str(k + 1), 'type': 'continuous', 'domain': bounds[k], 'dimensionality': 1}
+            for k in range(len(bounds))]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# experiment design (random): np.random consumption order is part of the trajectory
+# ----------------------------------------------------------------------------------------------------------------------
+def samples_multidimensional_uniform(bounds, points_count):
+    """random_design.py:80-91: ONE np.random.uniform(size=n) call per continuous dimension, in order."""
+    dim = len(bounds)
+    Z_rand = np.zeros(shape=(points_count, dim))
+    for k in range(0, dim):
+        Z_rand[:, k] = np.random.uniform(low=bounds[k][0], high=bounds[k][1], size=points_count)
+    return Z_rand
+
+
+class RandomDesign(object):
+    def __init__(self, space):
+        self.space = space
+
+    def get_samples(self, init_points_count):
+        if self.space.has_constraints():
+            return self.get_samples_with_constraints(init_points_count)
+        return self.get_samples_without_constraints(init_points_count)
+
+    def get_samples_with_constraints(self, init_points_count):
+        samples = np.empty((0, self.space.dimensionality))
+        while samples.shape[0] < init_points_count:
+            domain_samples = self.get_samples_without_constraints(init_points_count)
+            valid_indices = (self.space.indicator_constraints(domain_samples) == 1).flatten()
+            if sum(valid_indices) > 0:
+                samples = np.vstack((samples, domain_samples[valid_indices, :]))
+        return samples[0:init_points_count, :]
+
+    def get_samples_without_constraints(self, init_points_count):
+        samples = np.empty((init_points_count, self.space.dimensionality))
+        for idx, var in enumerate(self.space.space_expanded):          # discrete variables first (random_design.py:43-46)
+            if var.is_discrete():
+                samples[:, idx] = np.atleast_2d(np.random.choice(var.domain, init_points_count)).flatten()
+        if self.space.has_continuous():
+            X_design = samples_multidimensional_uniform(self.space.get_continuous_bounds(), init_points_count)
+            samples[:, self.space.get_continuous_dims()] = X_design
+        return samples
+
+
+def initial_design(design_name, space, init_points_count):
+    if design_name != 'random':
+        raise ValueError("only the 'random' design is provided (latin / sobol need pyDOE / sobol_seq): " + str(design_name))
+    return RandomDesign(space).get_samples(init_points_count)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# objective
+# ----------------------------------------------------------------------------------------------------------------------
+class SingleObjective(object):
+    """core/task/objective.py:24-76 (sequential evaluation)."""
+
+    def __init__(self, func, num_cores=1, objective_name='no_name', batch_type='synchronous', space=None):
+        self.func, self.n_procs, self.num_evaluations, self.space, self.objective_name = func, num_cores, 0, space, objective_name
+
+    def evaluate(self, x):
+        cost_evals = []
+        f_evals = np.empty(shape=[0, 1])
+        for i in range(x.shape[0]):
+            st_time = time.time()
+            rlt = self.func(np.atleast_2d(x[i]))
+            f_evals = np.vstack([f_evals, rlt])
+            cost_evals += [time.time() - st_time]
+        return f_evals, cost_evals
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# models
+# ----------------------------------------------------------------------------------------------------------------------
+class BOModel(object):
+    """models/base.py:7-33."""
+    MCMC_sampler = False
+    analytical_gradient_prediction = False
+
+    def updateModel(self, X_all, Y_all, X_new, Y_new):
+        raise NotImplementedError
+
+    def predict(self, X):
+        raise NotImplementedError
+
+    def predict_withGradients(self, X):
+        return
+
+    def get_fmin(self):
+        raise NotImplementedError
+
+
+class GPModel(BOModel):
+    """models/gpmodel.py:9-177 on the B200 GPRegression."""
+
+    analytical_gradient_prediction = True
+
+    def __init__(self, kernel=None, noise_var=None, exact_feval=False, optimizer='bfgs', max_iters=1000, optimize_restarts=5,
+                 sparse=False, num_inducing=10, verbose=True, ARD=False, Gower=False, space=None):
+        if sparse:
+            raise NotImplementedError("sparse GPs are outside the B200 hot path (exact N x N on one GPU)")
+        if Gower:
+            raise NotImplementedError("the Gower kernel patch is outside the B200 hot path")
+        self.kernel, self.noise_var, self.exact_feval = kernel, noise_var, exact_feval
+        self.optimize_restarts, self.optimizer, self.max_iters, self.verbose = optimize_restarts, optimizer, max_iters, verbose
+        self.sparse, self.num_inducing, self.model, self.ARD = sparse, num_inducing, None, ARD
+        self._fmin = None
+
+    @staticmethod
+    def fromConfig(config):
+        return GPModel(**config)
+
+    def _create_model(self, X, Y):
+        """gpmodel.py:50-76."""
+        self.input_dim = X.shape[1]
+        if self.kernel is None:
+            kern = _kern.Matern52(self.input_dim, variance=1., ARD=self.ARD)
+        else:
+            kern = self.kernel
+            self.kernel = None
+        noise_var = Y.var() * 0.01 if self.noise_var is None else self.noise_var
+        self.model = GPRegression(X, Y, kernel=kern, noise_var=noise_var)
+        if self.exact_feval:
+            self.model.Gaussian_noise.constrain_fixed(1e-6, warning=False)
+        else:
+            self.model.Gaussian_noise.constrain_bounded(1e-9, 1e6, warning=False)
+
+    def updateModel(self, X_all, Y_all, X_new, Y_new):
+        """gpmodel.py:78-93."""
+        self._fmin = None
+        if self.model is None:
+            self._create_model(X_all, Y_all)
+        else:
+            self.model.set_XY(X_all, Y_all)
+        if self.max_iters > 0:
+            if self.optimize_restarts == 1:
+                self.model.optimize(optimizer=self.optimizer, max_iters=self.max_iters, messages=False, ipython_notebook=False)
+            else:
+                self.model.optimize_restarts(num_restarts=self.optimize_restarts, optimizer=self.optimizer,
+                                             max_iters=self.max_iters, verbose=self.verbose)
+        self._fmin = None
+
+    def _nat(self):
+        return self.model.posterior._nat
+
+    def _predict(self, X, full_cov, include_likelihood):
+        if X.ndim == 1:
+            X = X[None, :]
+        m, v = self.model.predict(X, full_cov=full_cov, include_likelihood=include_likelihood)
+        v = np.clip(v, 1e-10, np.inf)
+        return m, v
+
+    def predict(self, X, with_noise=True):
+        """gpmodel.py:102-112 -> (mean, standard deviation)."""
+        m, v = self._predict(X, False, with_noise)
+        return m, np.sqrt(v)
+
+    def predict_covariance(self, X, with_noise=True):
+        _, v = self._predict(X, True, with_noise)
+        return v
+
+    def get_fmin(self):
+        """gpmodel.py:125-129.  The reference recomputes predict(model.X)[0].min() on every acquisition call; the value only
+        changes with the model, so it is computed once per model state (on the device)."""
+        if self._fmin is None or self._fmin[0] is not self.model.posterior:
+            self._fmin = (self.model.posterior, self._nat().fmin())
+        return self._fmin[1]
+
+    def predict_withGradients(self, X):
+        """gpmodel.py:131-142."""
+        if X.ndim == 1:
+            X = X[None, :]
+        r = self._nat().acquisition("LCB", 0.0, 0.0, X, with_gradients=True, want_moments=True)
+        return r["m"], r["s"], r["dmdx"], r["dsdx"]
+
+    def acquisition_native(self, acq, par, X, with_gradients):
+        """Fused device path of AcquisitionEI/LCB._compute_acq(_withGradients): returns (-f) [, (-df)] un-negated, i.e. the
+        acquisition value and its gradient as the reference's _compute_acq* do."""
+        if X.ndim == 1:
+            X = X[None, :]
+        r = self._nat().acquisition(acq, par, self.get_fmin() if acq == "EI" else 0.0, X, with_gradients=with_gradients)
+        if with_gradients:
+            return -r["f"], -r["df"]
+        return -r["f"]
+
+    def copy(self):
+        """gpmodel.py:144-159."""
+        copied_model = GPModel(kernel=self.model.kern.copy(), noise_var=self.noise_var, exact_feval=self.exact_feval,
+                               optimizer=self.optimizer, max_iters=self.max_iters, optimize_restarts=self.optimize_restarts,
+                               verbose=self.verbose, ARD=self.ARD)
+        copied_model._create_model(self.model.X, self.model.Y)
+        copied_model.updateModel(self.model.X, self.model.Y, None, None)
+        return copied_model
+
+    def get_model_parameters(self):
+        return np.atleast_2d(self.model[:])
+
+    def get_model_parameters_names(self):
+        return self.model.parameter_names_flat(include_fixed=True).tolist()
+
+    def get_covariance_between_points(self, x1, x2):
+        return self.model.posterior_covariance_between_points(x1, x2)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# acquisitions
+# ----------------------------------------------------------------------------------------------------------------------
+class AcquisitionBase(object):
+    """acquisitions/base.py:6-68."""
+    analytical_gradient_prediction = False
+
+    def __init__(self, model, space, optimizer, cost_withGradients=None):
+        self.model, self.space, self.optimizer = model, space, optimizer
+        self.analytical_gradient_acq = self.analytical_gradient_prediction and self.model.analytical_gradient_prediction
+        self.cost_withGradients = constant_cost_withGradients if cost_withGradients is None else cost_withGradients
+
+    def acquisition_function(self, x):
+        f_acqu = self._compute_acq(x)
+        cost_x, _ = self.cost_withGradients(x)
+        return -(f_acqu * self.space.indicator_constraints(x)) / cost_x
+
+    def acquisition_function_withGradients(self, x):
+        f_acqu, df_acqu = self._compute_acq_withGradients(x)
+        cost_x, cost_grad_x = self.cost_withGradients(x)
+        f_acq_cost = f_acqu / cost_x
+        df_acq_cost = (df_acqu * cost_x - f_acqu * cost_grad_x) / (cost_x ** 2)
+        ind = self.space.indicator_constraints(x)
+        return -f_acq_cost * ind, -df_acq_cost * ind
+
+    def optimize(self, duplicate_manager=None):
+        if not self.analytical_gradient_acq:
+            out = self.optimizer.optimize(f=self.acquisition_function, duplicate_manager=duplicate_manager)
+        else:
+            out = self.optimizer.optimize(f=self.acquisition_function, f_df=self.acquisition_function_withGradients,
+                                          duplicate_manager=duplicate_manager)
+        return out
+
+    def _compute_acq(self, x):
+        raise NotImplementedError('')
+
+    def _compute_acq_withGradients(self, x):
+        raise NotImplementedError('')
+
+
+class AcquisitionEI(AcquisitionBase):
+    """acquisitions/EI.py:7-51."""
+    analytical_gradient_prediction = True
+
+    def __init__(self, model, space, optimizer=None, cost_withGradients=None, jitter=0.01):
+        self.optimizer = optimizer
+        super(AcquisitionEI, self).__init__(model, space, optimizer, cost_withGradients=cost_withGradients)
+        self.jitter = jitter
+
+    @staticmethod
+    def fromConfig(model, space, optimizer, cost_withGradients, config):
+        return AcquisitionEI(model, space, optimizer, cost_withGradients, jitter=config['jitter'])
+
+    def _compute_acq(self, x):
+        if hasattr(self.model, "acquisition_native"):
+            return self.model.acquisition_native("EI", self.jitter, np.atleast_2d(x), False)
+        m, s = self.model.predict(x)
+        fmin = self.model.get_fmin()
+        phi, Phi, u = get_quantiles(self.jitter, fmin, m, s)
+        return s * (u * Phi + phi)
+
+    def _compute_acq_withGradients(self, x):
+        if hasattr(self.model, "acquisition_native"):
+            return self.model.acquisition_native("EI", self.jitter, np.atleast_2d(x), True)
+        fmin = self.model.get_fmin()
+        m, s, dmdx, dsdx = self.model.predict_withGradients(x)
+        phi, Phi, u = get_quantiles(self.jitter, fmin, m, s)
+        return s * (u * Phi + phi), dsdx * phi - Phi * dmdx
+
+
+class AcquisitionLCB(AcquisitionBase):
+    """acquisitions/LCB.py:7-46."""
+    analytical_gradient_prediction = True
+
+    def __init__(self, model, space, optimizer=None, cost_withGradients=None, exploration_weight=2):
+        self.optimizer = optimizer
+        super(AcquisitionLCB, self).__init__(model, space, optimizer)
+        self.exploration_weight = exploration_weight
+        if cost_withGradients is not None:
+            print('The set cost function is ignored! LCB acquisition does not make sense with cost.')
+
+    def _compute_acq(self, x):
+        if hasattr(self.model, "acquisition_native"):
+            return self.model.acquisition_native("LCB", self.exploration_weight, np.atleast_2d(x), False)
+        m, s = self.model.predict(x)
+        return -m + self.exploration_weight * s
+
+    def _compute_acq_withGradients(self, x):
+        if hasattr(self.model, "acquisition_native"):
+            return self.model.acquisition_native("LCB", self.exploration_weight, np.atleast_2d(x), True)
+        m, s, dmdx, dsdx = self.model.predict_withGradients(x)
+        return -m + self.exploration_weight * s, -dmdx + self.exploration_weight * dsdx
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# acquisition optimiser
+# ----------------------------------------------------------------------------------------------------------------------
+class OptLbfgs(object):
+    """optimization/optimizer.py:28-61."""
+
+    def __init__(self, bounds, maxiter=1000):
+        self.bounds, self.maxiter = bounds, maxiter
+
+    def optimize(self, x0, f=None, df=None, f_df=None):
+        import scipy.optimize
+        if f_df is None and df is not None:
+            f_df = lambda x: (float(f(x)), df(x))  # noqa: E731
+        if f_df is not None:
+            def _f_df(x):
+                # the reference evaluates f(x) AND f_df(x) per step (optimizer.py:46-47); both come from the same device
+                # kernels, so one fused call returns bit-identical values
+                fx, dfx = f_df(x)
+                return fx, dfx[0]
+        if f_df is None and df is None:
+            res = scipy.optimize.fmin_l_bfgs_b(f, x0=x0, bounds=self.bounds, approx_grad=True, maxiter=self.maxiter)
+        else:
+            res = scipy.optimize.fmin_l_bfgs_b(_f_df, x0=x0, bounds=self.bounds, maxiter=self.maxiter)
+        if res[2]['task'] == b'ABNORMAL_TERMINATION_IN_LNSRCH' or res[2]['task'] == 'ABNORMAL_TERMINATION_IN_LNSRCH':
+            result_x = np.atleast_2d(x0)
+            result_fx = np.atleast_2d(f(x0))
+        else:
+            result_x = np.atleast_2d(res[0])
+            result_fx = np.atleast_2d(res[1])
+        return result_x, result_fx
+
+
+def apply_optimizer(optimizer, x0, f=None, df=None, f_df=None, duplicate_manager=None, context_manager=None, space=None):
+    """optimization/optimizer.py:130-168 without context variables."""
+    x0 = np.atleast_2d(x0)
+    optimized_x, _ = optimizer.optimize(x0, f, df, f_df)
+    suggested_x_rounded = space.round_optimum(optimized_x)
+    return suggested_x_rounded, f(suggested_x_rounded)
+
+
+class ObjectiveAnchorPointsGenerator(object):
+    """optimization/anchor_points_generator.py:8-98: 1000 random points, scored in ONE batched call, keep the 5 lowest."""
+
+    def __init__(self, space, design_type, objective, num_samples=1000):
+        self.space, self.design_type, self.objective, self.num_samples = space, design_type, objective, num_samples
+
+    def get_anchor_point_scores(self, X):
+        return self.objective(X).flatten()
+
+    def get(self, num_anchor=5, duplicate_manager=None, unique=False, context_manager=None):
+        X = initial_design(self.design_type, self.space, self.num_samples)
+        X = self.space.unzip_inputs(X)
+        scores = self.get_anchor_point_scores(X)
+        # np.argsort's default introsort is not stable; ties are resolved towards the lowest index here (and in the oracle)
+        return X[np.argsort(scores, kind='stable')[:min(len(scores), num_anchor)], :]
+
+
+class AcquisitionOptimizer(object):
+    """optimization/acquisition_optimizer.py:16-77."""
+
+    def __init__(self, space, optimizer='lbfgs', **kwargs):
+        if optimizer != 'lbfgs':
+            raise NotImplementedError("only 'lbfgs' is provided (DIRECT / CMA need external packages)")
+        self.space, self.optimizer_name, self.kwargs = space, optimizer, kwargs
+        if 'model' in self.kwargs:
+            self.model = self.kwargs['model']
+        self.context_manager = None
+
+    def optimize(self, f=None, df=None, f_df=None, duplicate_manager=None):
+        self.f, self.df, self.f_df = f, df, f_df
+        self.optimizer = OptLbfgs(self.space.get_bounds())
+        anchor_points = ObjectiveAnchorPointsGenerator(self.space, 'random', f).get(duplicate_manager=duplicate_manager)
+        optimized_points = [apply_optimizer(self.optimizer, a, f=f, df=None, f_df=f_df, space=self.space) for a in anchor_points]
+        x_min, fx_min = min(optimized_points, key=lambda t: t[1])
+        return x_min, fx_min
+
+
+class Sequential(object):
+    """core/evaluators/sequential.py:7-23."""
+
+    def __init__(self, acquisition, batch_size=1):
+        self.acquisition, self.batch_size = acquisition, batch_size
+
+    def compute_batch(self, duplicate_manager=None, context_manager=None):
+        x, _ = self.acquisition.optimize(duplicate_manager=duplicate_manager)
+        return x
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BO loop
+# ----------------------------------------------------------------------------------------------------------------------
+class BO(object):
+    """core/bo.py:20-260."""
+
+    def __init__(self, model, space, objective, acquisition, evaluator, X_init, Y_init=None, cost=None, normalize_Y=True,
+                 model_update_interval=1, de_duplication=False):
+        self.model, self.space, self.objective, self.acquisition, self.evaluator = model, space, objective, acquisition, evaluator
+        self.normalize_Y, self.model_update_interval = normalize_Y, model_update_interval
+        self.X, self.Y = X_init, Y_init
+        self.normalization_type = 'stats'
+        self.de_duplication = de_duplication
+        self.model_parameters_iterations = None
+        self.context = None
+        self.num_acquisitions = 0
+
+    def suggest_next_locations(self, context=None, pending_X=None, ignored_X=None):
+        self.model_parameters_iterations = None
+        self.num_acquisitions = 0
+        self.context = context
+        self._update_model(self.normalization_type)
+        return self._compute_next_evaluations()
+
+    def run_optimization(self, max_iter=0, max_time=np.inf, eps=1e-8, context=None, verbosity=False,
+                         save_models_parameters=True, report_file=None, evaluations_file=None, models_file=None):
+        if self.objective is None:
+            raise InvalidConfigError("Cannot run the optimization loop without the objective function")
+        self.verbosity = verbosity
+        self.save_models_parameters = save_models_parameters
+        self.model_parameters_iterations = None
+        self.context = context
+        self.eps = eps
+        if (max_iter is None) and (max_time is None):
+            self.max_iter, self.max_time = 0, np.inf
+        elif (max_iter is None) and (max_time is not None):
+            self.max_iter, self.max_time = np.inf, max_time
+        elif (max_iter is not None) and (max_time is None):
+            self.max_iter, self.max_time = max_iter, np.inf
+        else:
+            self.max_iter, self.max_time = max_iter, max_time
+        if self.X is not None and self.Y is None:
+            self.Y, _ = self.objective.evaluate(self.X)
+        self.time_zero = time.time()
+        self.cum_time = 0
+        self.num_acquisitions = 0
+        self.suggested_sample = self.X
+        self.Y_new = self.Y
+        while self.max_time > self.cum_time:
+            try:
+                self._update_model(self.normalization_type)
+            except np.linalg.LinAlgError:
+                break
+            if (self.num_acquisitions >= self.max_iter
+                    or (len(self.X) > 1 and self._distance_last_evaluations() <= self.eps)):
+                break
+            self.suggested_sample = self._compute_next_evaluations()
+            self.X = np.vstack((self.X, self.suggested_sample))
+            self.evaluate_objective()
+            self.cum_time = time.time() - self.time_zero
+            self.num_acquisitions += 1
+            if verbosity:
+                print("num acquisition: {}, time elapsed: {:.2f}s".format(self.num_acquisitions, self.cum_time))
+        self._compute_results()
+
+    def evaluate_objective(self):
+        self.Y_new, _ = self.objective.evaluate(self.suggested_sample)
+        self.Y = np.vstack((self.Y, self.Y_new))
+
+    def _compute_results(self):
+        self.Y_best = best_value(self.Y)
+        self.x_opt = self.X[np.argmin(self.Y), :]
+        self.fx_opt = np.min(self.Y)
+
+    def _distance_last_evaluations(self):
+        if self.X.shape[0] < 2:
+            return np.inf
+        return np.sqrt(np.sum((self.X[-1, :] - self.X[-2, :]) ** 2))
+
+    def _compute_next_evaluations(self, pending_zipped_X=None, ignored_zipped_X=None):
+        return self.space.zip_inputs(self.evaluator.compute_batch(duplicate_manager=None, context_manager=None))
+
+    def _update_model(self, normalization_type='stats'):
+        if self.num_acquisitions % self.model_update_interval == 0:
+            X_inmodel = self.space.unzip_inputs(self.X)
+            Y_inmodel = normalize(self.Y, normalization_type) if self.normalize_Y else self.Y
+            self.model.updateModel(X_inmodel, Y_inmodel, None, None)
+        self._save_model_parameter_values()
+
+    def _save_model_parameter_values(self):
+        if self.model_parameters_iterations is None:
+            self.model_parameters_iterations = self.model.get_model_parameters()
+        else:
+            self.model_parameters_iterations = np.vstack((self.model_parameters_iterations, self.model.get_model_parameters()))
+
+    def get_evaluations(self):
+        return self.X.copy(), self.Y.copy()
+
+
+class BayesianOptimization(BO):
+    """methods/bayesian_optimization.py:76-202 (GP model, EI / LCB acquisition, L-BFGS-B acquisition optimiser)."""
+
+    def __init__(self, f, domain=None, constraints=None, cost_withGradients=None, model_type='GP', X=None, Y=None,
+                 initial_design_numdata=5, initial_design_type='random', acquisition_type='EI', normalize_Y=True,
+                 exact_feval=False, acquisition_optimizer_type='lbfgs', model_update_interval=1, evaluator_type='sequential',
+                 batch_size=1, num_cores=1, verbosity=False, verbosity_model=False, maximize=False, de_duplication=False, **kwargs):
+        self.modular_optimization = False
+        self.initial_iter = True
+        self.verbosity, self.verbosity_model = verbosity, verbosity_model
+        self.model_update_interval, self.de_duplication, self.kwargs = model_update_interval, de_duplication, kwargs
+        if de_duplication:
+            raise NotImplementedError("de_duplication is host-side set bookkeeping outside the B200 hot path")
+        self.constraints, self.domain = constraints, domain
+        self.space = Design_space(self.domain, self.constraints)
+        self.maximize = maximize
+        self.objective_name = kwargs.get('objective_name', 'no_name')
+        self.batch_size, self.num_cores = batch_size, num_cores
+        if f is not None:
+            self.f = self._sign(f)
+            self.objective = SingleObjective(self.f, self.batch_size, self.objective_name)
+        else:
+            self.f, self.objective = None, None
+        self.cost_withGradients = cost_withGradients
+        self.X, self.Y = X, Y
+        self.initial_design_type, self.initial_design_numdata = initial_design_type, initial_design_numdata
+        self._init_design_chooser()
+        self.model_type, self.exact_feval, self.normalize_Y = model_type, exact_feval, normalize_Y
+        if 'model' in kwargs and isinstance(kwargs['model'], BOModel):
+            self.model = kwargs['model']
+            self.model_type = 'User defined model used.'
+        else:
+            self.model = self._model_chooser()
+        self.acquisition_optimizer_type = acquisition_optimizer_type
+        self.acquisition_optimizer = AcquisitionOptimizer(self.space, self.acquisition_optimizer_type, model=self.model)
+        self.acquisition_type = acquisition_type
+        if 'acquisition' in kwargs and isinstance(kwargs['acquisition'], AcquisitionBase):
+            self.acquisition = kwargs['acquisition']
+            self.acquisition_type = 'User defined acquisition used.'
+        else:
+            self.acquisition = self._acquisition_chooser()
+        self.evaluator_type = evaluator_type
+        self.evaluator = self._evaluator_chooser()
+        super(BayesianOptimization, self).__init__(model=self.model, space=self.space, objective=self.objective,
+                                                   acquisition=self.acquisition, evaluator=self.evaluator, X_init=self.X,
+                                                   Y_init=self.Y, cost=None, normalize_Y=self.normalize_Y,
+                                                   model_update_interval=self.model_update_interval,
+                                                   de_duplication=self.de_duplication)
+
+    def _model_chooser(self):
+        """util/arguments_manager.py:78-110 (defaults: lbfgs, max_iters 1000, 5 restarts, ARD False)."""
+        if self.model_type != 'GP':
+            raise NotImplementedError("model_type %r is outside the B200 hot path" % (self.model_type,))
+        kw = self.kwargs
+        return GPModel(kw.get('kernel', None), kw.get('noise_var', None), self.exact_feval, kw.get('model_optimizer_type', 'lbfgs'),
+                       kw.get('max_iters', 1000), kw.get('optimize_restarts', 5), False, kw.get('num_inducing', 10),
+                       kw.get('verbosity_model', False), kw.get('ARD', False))
+
+    def _acquisition_chooser(self):
+        """util/arguments_manager.py:42-75 (jitter 0.01, weight 2)."""
+        jitter = self.kwargs.get('acquisition_jitter', 0.01)
+        weight = self.kwargs.get('acquisition_weight', 2)
+        if self.acquisition_type is None or self.acquisition_type == 'EI':
+            return AcquisitionEI(self.model, self.space, self.acquisition_optimizer, self.cost_withGradients, jitter)
+        if self.acquisition_type == 'LCB':
+            return AcquisitionLCB(self.model, self.space, self.acquisition_optimizer, self.cost_withGradients, weight)
+        raise Exception('Invalid acquisition selected.')
+
+    def _evaluator_chooser(self):
+        if self.batch_size == 1 or self.evaluator_type == 'sequential':
+            return Sequential(self.acquisition)
+        raise NotImplementedError("batch evaluators are not provided yet (local penalisation is the next row of SURVEY 8f)")
+
+    def _init_design_chooser(self):
+        if self.f is None and (self.X is None or self.Y is None):
+            raise InvalidConfigError("Initial data for both X and Y is required when objective function is not provided")
+        if self.X is None:
+            self.X = initial_design(self.initial_design_type, self.space, self.initial_design_numdata)
+            self.Y, _ = self.objective.evaluate(self.X)
+        elif self.X is not None and self.Y is None:
+            self.Y, _ = self.objective.evaluate(self.X)
+
+    def _sign(self, f):
+        if self.maximize:
+            f_copy = f
+
+            def f(x):
+                return -f_copy(x)
+        return f

@@ -100,6 +100,16 @@ def potrs(L, B):
     return Bc
 
 
+def potri(L):
+    """dpotri(L, lower=1) + symmetrify (linalg.py:127-145)."""
+    lib = _lib.require_gpu()
+    L = as_host(L)
+    n = L.shape[0]
+    Ai = np.empty((n, n))
+    check(lib.gpb_potri(n, ptr(L), n, ptr(Ai), n, 0, _lib.current_stream()), "potri")
+    return Ai
+
+
 def dgemm(ta, tb, alpha, A, B, beta, C):
     """Device-only DMMA GEMM on CUDA torch tensors (row-major).  C is updated in place."""
     lib = _lib.require_gpu()

@@ -59,6 +59,8 @@ int gpb_kern_gradients_X(int kind, int d, int n, const double *X, int m, const d
 int gpb_pdinv(int n, const double *A, int lda, double *L, double *Ai, double *Li, double *logdet, int dev, void *stream);
 /* dpotrs(L, B) (linalg.py:116-125): solve (L L^T) X = B in place, B: n x nrhs row-major. */
 int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, void *stream);
+/* dpotri(L) (linalg.py:127-145): A^-1 from the lower Cholesky factor, symmetrised. */
+int gpb_potri(int n, const double *L, int ldl, double *Ai, int ldai, int dev, void *stream);
 
 /* ---- GPRegression / ExactGaussianInference / PosteriorExact -------------------------------------------------------- */
 /* Device workspace (bytes) a model of capacity n_cap points in d dims needs; cand_block = max candidates per predict block. */
