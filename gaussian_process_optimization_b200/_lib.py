@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libgpb200.so")
 
 KERN_RBF, KERN_MATERN52 = 0, 1
 ACQ_EI, ACQ_LCB = 0, 1
+ERR_CUDA, ERR_ARG, ERR_DOMAIN = -1, -2, -3
 KIND_IDS = {"rbf": KERN_RBF, "RBF": KERN_RBF, "mat52": KERN_MATERN52, "Mat52": KERN_MATERN52, "Matern52": KERN_MATERN52}
 ACQ_IDS = {"EI": ACQ_EI, "LCB": ACQ_LCB}
 
@@ -91,6 +92,8 @@ def check(rc, what=""):
     (GPy/GPy/util/linalg.py:64,75).  rc < 0: usage / CUDA error."""
     if rc == 0:
         return
+    if rc == ERR_DOMAIN:
+        raise np.linalg.LinAlgError("not positive definite, even with jitter. (%s)" % last_error())
     if rc > 0:
         raise np.linalg.LinAlgError("not positive definite, even with jitter." if what == "jitchol" else
                                     "%s: %s" % (what or "gpb", last_error()))

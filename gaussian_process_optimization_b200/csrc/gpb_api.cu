@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -344,8 +345,18 @@ static int ensure_wi(gpb_model *m) {
 int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out) {
   GPB_REQUIRE(m && out, "fit: NULL argument");
   GPB_REQUIRE(m->have_data, "fit: set_data has not been called");
-  GPB_REQUIRE(m->variance > 0 && m->noise >= 0, "fit: variance must be > 0 and noise >= 0");
-  for (int q = 0; q < m->nls; ++q) GPB_REQUIRE(m->ls[q] > 0, "fit: lengthscale[%d] must be > 0", q);
+  // Hyper-parameters outside the domain (an L-BFGS-B line search can push the transformed parameters to 0, inf or NaN):
+  // the reference's NumPy path turns those into NaNs and ends in jitchol's LinAlgError (linalg.py:62-75), which paramz
+  // catches.  Same contract here: GPB_ERR_DOMAIN -> LinAlgError in the Python layer.  variance == 0 is legal (K = 0).
+  {
+    bool ok = std::isfinite(m->variance) && m->variance >= 0 && std::isfinite(m->noise) && m->noise >= 0 &&
+              std::isfinite(extra_jitter);
+    for (int q = 0; q < m->nls; ++q) ok = ok && std::isfinite(m->ls[q]) && m->ls[q] > 0 && std::isfinite(1.0 / m->ls[q]);
+    if (!ok) {
+      set_error("fit: hyper-parameters outside the domain (variance >= 0, lengthscale > 0, noise >= 0, all finite)");
+      return GPB_ERR_DOMAIN;
+    }
+  }
   m->fitted = false;
   m->have_wi = false;
   m->jitter = extra_jitter;

@@ -59,8 +59,14 @@ inline void count_launch(int n = 1) { g_launches += n; }
 // gives the same sums without the division.
 //   RBF      (rbf.py:50-54):            k = v exp(-r^2/2),                        k'/r = -k
 //   Matern52 (stationary.py:575-579):   k = v (1 + s5 r + 5/3 r^2) exp(-s5 r),    k'/r = -(5/3) v (1 + s5 r) exp(-s5 r)
+// r2 can overflow to +inf when an optimiser step drives a lengthscale towards 0; the covariance is exactly 0 there, but
+// (1 + s + ..) * exp(-s) and (k'/r) * dx^2 would evaluate inf * 0.  Clamping r2 keeps every factor finite (NaN stays NaN:
+// the comparison is false for it, and a NaN kernel matrix ends in the jitchol LinAlgError like in the reference).
+__device__ __forceinline__ double clamp_r2(double r2) { return r2 > 1e300 ? 1e300 : r2; }
+
 template <int KIND>
 __device__ __forceinline__ double cov_k(double r2, double variance) {
+  r2 = clamp_r2(r2);
   if (KIND == GPB_KERN_RBF) {
     return variance * exp(-0.5 * r2);
   } else {
@@ -72,6 +78,7 @@ __device__ __forceinline__ double cov_k(double r2, double variance) {
 
 template <int KIND>
 __device__ __forceinline__ void cov_k_dk(double r2, double variance, double &k, double &dk_over_r) {
+  r2 = clamp_r2(r2);
   if (KIND == GPB_KERN_RBF) {
     k = variance * exp(-0.5 * r2);
     dk_over_r = -k;

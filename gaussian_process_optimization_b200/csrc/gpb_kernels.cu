@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(256) kgrad_kernel(const double *__restrict__ X
 #pragma unroll
       for (int b = 0; b < 8; ++b) {
         const double df = va[a] - vb[b];
-        acc = fma(r2[a][b], df * df, acc);
+        const double w = r2[a][b];
+        if (w != 0.0) acc = fma(w, df * df, acc);   // w == 0 with df^2 == inf (lengthscale -> 0) contributes 0, not NaN
       }
     acc = warp_sum(acc);
     if (lane == 0) wacc[warp * (d + 2) + 2 + q] = acc;
@@ -310,8 +311,8 @@ __global__ void __launch_bounds__(256) gradx_kernel(const double *__restrict__ X
     if (TWO) w2 = dk * G2[(size_t)c * ldg2 + j];
 #pragma unroll
     for (int q = 0; q < DCAP; ++q) {
-      a1[q] = fma(w1, df[q], a1[q]);
-      if (TWO) a2[q] = fma(w2, df[q], a2[q]);
+      if (w1 != 0.0) a1[q] = fma(w1, df[q], a1[q]);   // 0 * inf (lengthscale -> 0) contributes 0, not NaN
+      if (TWO && w2 != 0.0) a2[q] = fma(w2, df[q], a2[q]);
     }
   }
 #pragma unroll

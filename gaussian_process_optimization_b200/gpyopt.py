@@ -376,14 +376,14 @@ class GPModel(BOModel):
         """gpmodel.py:125-129.  The reference recomputes predict(model.X)[0].min() on every acquisition call; the value only
         changes with the model, so it is computed once per model state (on the device)."""
         if self._fmin is None or self._fmin[0] is not self.model.posterior:
-            self._fmin = (self.model.posterior, self._nat().fmin())
+            self._fmin = (self.model.posterior, self.model.posterior.fmin())
         return self._fmin[1]
 
     def predict_withGradients(self, X):
         """gpmodel.py:131-142."""
         if X.ndim == 1:
             X = X[None, :]
-        r = self._nat().acquisition("LCB", 0.0, 0.0, X, with_gradients=True, want_moments=True)
+        r = self.model.posterior.acquisition("LCB", 0.0, 0.0, X, with_gradients=True, want_moments=True)
         return r["m"], r["s"], r["dmdx"], r["dsdx"]
 
     def acquisition_native(self, acq, par, X, with_gradients):
@@ -391,7 +391,7 @@ class GPModel(BOModel):
         acquisition value and its gradient as the reference's _compute_acq* do."""
         if X.ndim == 1:
             X = X[None, :]
-        r = self._nat().acquisition(acq, par, self.get_fmin() if acq == "EI" else 0.0, X, with_gradients=with_gradients)
+        r = self.model.posterior.acquisition(acq, par, self.get_fmin() if acq == "EI" else 0.0, X, with_gradients=with_gradients)
         if with_gradients:
             return -r["f"], -r["df"]
         return -r["f"]
@@ -544,7 +544,15 @@ class OptLbfgs(object):
 def apply_optimizer(optimizer, x0, f=None, df=None, f_df=None, duplicate_manager=None, context_manager=None, space=None):
     """optimization/optimizer.py:130-168 without context variables."""
     x0 = np.atleast_2d(x0)
-    optimized_x, _ = optimizer.optimize(x0, f, df, f_df)
+
+    # OptimizationWithContext.f_nc / f_df_nc (optimizer.py:200-232): SciPy hands the objective a 1-D x; the reference always
+    # routes it through these wrappers (a ContextManager exists even without context), so acquisitions only ever see 2-D input
+    def f_nc(x):
+        x = np.atleast_2d(x)
+        return f(x)[0] if x.shape[0] == 1 else f(x)
+
+    f_df_nc = None if f_df is None else (lambda x: f_df(np.atleast_2d(x)))
+    optimized_x, _ = optimizer.optimize(x0, f_nc, df, f_df_nc)
     suggested_x_rounded = space.round_optimum(optimized_x)
     return suggested_x_rounded, f(suggested_x_rounded)
 

@@ -135,6 +135,22 @@ class PosteriorExact(object):
             return self._nat.predict_full_cov(Xnew, include_likelihood=False)
         return self._nat.predict(Xnew, include_likelihood=False)
 
+    # -- what GP / GPModel need beyond the reference's Posterior attributes: the fused device entry points -------------
+    def predictive_gradients(self, Xnew):
+        """core/gp.py:407-454 -> (dmu_dX (M, D, P), dv_dX (M, D))."""
+        return self._nat.predictive_gradients(np.asarray(Xnew, dtype=np.float64))
+
+    def fmin(self):
+        """min of the posterior mean over the training inputs (gpmodel.py:125-129)."""
+        return self._nat.fmin()
+
+    def acquisition(self, acq, par, fmin, X, with_gradients=False, want_moments=False):
+        """GPModel.predict(_withGradients) + get_quantiles + EI / LCB (+ gradients) + AcquisitionBase sign, one device pass."""
+        return self._nat.acquisition(acq, par, fmin, X, with_gradients=with_gradients, want_moments=want_moments)
+
+    def acq_topk(self, acq, par, fmin, X, k, index_offset=0):
+        return self._nat.acq_topk(acq, par, fmin, X, k, index_offset=index_offset)
+
 
 class ExactGaussianInference(object):
     """exact_gaussian_inference.py:11-74.  `inference` returns (PosteriorExact, log_marginal, grad_dict)."""
@@ -304,13 +320,12 @@ class GP(Model):
 
     def predictive_gradients(self, Xnew, kern=None):
         """core/gp.py:407-454 -> (dmu_dX (M, D, P), dv_dX (M, D))."""
-        Xnew = np.asarray(Xnew, dtype=np.float64)
-        return self.posterior._nat.predictive_gradients(Xnew)
+        return self.posterior.predictive_gradients(np.asarray(Xnew, dtype=np.float64))
 
     def posterior_covariance_between_points(self, X1, X2):
         """posterior.py:109-130 through one joint full-covariance prediction."""
         X1, X2 = np.asarray(X1, dtype=np.float64), np.asarray(X2, dtype=np.float64)
-        _, cov = self.posterior._nat.predict_full_cov(np.vstack([X1, X2]), include_likelihood=False)
+        _, cov = self.posterior._raw_predict(self.kern, np.vstack([X1, X2]), self._predictive_variable, full_cov=True)
         return cov[:X1.shape[0], X1.shape[0]:]
 
     def copy(self):

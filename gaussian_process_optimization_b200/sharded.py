@@ -70,9 +70,9 @@ class ShardedAnchorScorer(object):
             s = np.asarray(self.score_fn(X_shard), dtype=np.float64).ravel()
             order = np.argsort(s, kind="stable")[:kk]
             return s[order], order.astype(np.int64) + index_offset, np.asarray(X_shard)[order]
-        nat = self.model._nat() if hasattr(self.model, "_nat") else self.model
-        fmin = self.model.get_fmin() if hasattr(self.model, "get_fmin") else nat.fmin()
-        return nat.acq_topk(self.acq, self.par, fmin if self.acq == "EI" else 0.0, X_shard, kk, index_offset=index_offset)
+        post = self.model.model.posterior if hasattr(self.model, "get_fmin") else self.model   # GPModel or a NativeModel
+        fmin = self.model.get_fmin() if hasattr(self.model, "get_fmin") else post.fmin()
+        return post.acq_topk(self.acq, self.par, fmin if self.acq == "EI" else 0.0, X_shard, kk, index_offset=index_offset)
 
     def topk(self, X_shard, k, index_offset):
         vals, idx, pts = self.local_topk(X_shard, k, index_offset)

@@ -24,6 +24,11 @@ extern "C" {
 #define GPB_ACQ_EI 0        /* GPyOpt AcquisitionEI   GPyOpt/GPyOpt/acquisitions/EI.py:32-51 */
 #define GPB_ACQ_LCB 1       /* GPyOpt AcquisitionLCB  GPyOpt/GPyOpt/acquisitions/LCB.py:31-46 */
 
+#define GPB_ERR_CUDA (-1)   /* CUDA runtime error */
+#define GPB_ERR_ARG (-2)    /* bad argument / wrong call order */
+#define GPB_ERR_DOMAIN (-3) /* hyper-parameter outside its domain (NaN, inf, lengthscale <= 0, ...): the reference ends in
+                               jitchol's LinAlgError for these (GPy/GPy/util/linalg.py:62-75) and so does the Python layer */
+
 typedef struct gpb_model gpb_model; /* opaque: one GPRegression (data, hyper-parameters, posterior) resident on one GPU */
 
 /* ---- library ------------------------------------------------------------------------------------------------------ */

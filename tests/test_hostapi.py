@@ -1,0 +1,318 @@
+"""The GPy / GPyOpt-shaped host API (`from gaussian_process_optimization_b200 import GPy, GPyOpt`).
+
+Two backends run the same test bodies:
+  * "cuda"   (marked gpu): GPRegression / GPModel on libgpb200.so -- the product path;
+  * "oracle" (CPU):        the same host classes on the CPU oracle (tests/oracle_backend.py) -- this validates the host logic
+                           (parameter plumbing, transforms, L-BFGS-B, BO loop) without a GPU and gives the cuda run its
+                           comparison target for optimiser runs and BO trajectories.
+The bodies re-express the reference's own tests for this path: GradientTests (model_tests.py:647-723),
+test_raw_predict (:63-82), test_raw_predict_numerical_stability (:25-61), test_setxy_gp (gp_tests.py:50-60),
+jitchol success / failure (linalg_test.py:7-37), and config 1 of BASELINE.json (BO on Branin).
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from gaussian_process_optimization_b200 import GPy, GPyOpt, _lib
+from oracle import gp_oracle as O
+import oracle_backend as OB
+
+
+def _has_gpu():
+    try:
+        return _lib.load().gpb_device_count() > 0
+    except Exception:
+        return False
+
+
+BACKENDS = [pytest.param("cuda", marks=pytest.mark.gpu), "oracle"]
+
+
+def make_gpr(backend, X, Y, kernel, noise_var=1.):
+    if backend == "cuda":
+        return GPy.models.GPRegression(X, Y, kernel=kernel, noise_var=noise_var)
+    return OB.oracle_gp_regression(X, Y, kernel, noise_var)
+
+
+def make_gpmodel(backend, **kw):
+    return GPyOpt.models.GPModel(**kw) if backend == "cuda" else OB.OracleGPModel(**kw)
+
+
+def branin(X):
+    """GPyOpt/GPyOpt/objective_examples/experiments2d.py:203-216 (sd = 0)."""
+    X = np.atleast_2d(X)
+    x1, x2 = X[:, 0], X[:, 1]
+    b, c, r, s, t = 5.1 / (4 * np.pi ** 2), 5 / np.pi, 6, 10, 1 / (8 * np.pi)
+    return ((x2 - b * x1 ** 2 + c * x1 - r) ** 2 + s * (1 - t) * np.cos(x1) + s).reshape(-1, 1)
+
+
+BRANIN_DOMAIN = [{'name': 'x1', 'type': 'continuous', 'domain': (-5, 10)}, {'name': 'x2', 'type': 'continuous', 'domain': (1, 15)}]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GradientTests.check_model (model_tests.py:647-723): randomize + checkgrad for rbf / matern52, ARD or not, 1-D and 2-D
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("kname,dim,ard", [("RBF", 1, False), ("RBF", 2, False), ("RBF", 2, True), ("Matern52", 1, False),
+                                           ("Matern52", 2, False), ("Matern52", 2, True)])
+def test_gpregression_checkgrad(backend, kname, dim, ard):
+    np.random.seed(11 + dim)
+    if dim == 1:
+        X = np.random.uniform(-3., 3., (20, 1))
+        Y = np.sin(X) + np.random.randn(20, 1) * 0.05
+    else:
+        X = np.random.uniform(-3., 3., (40, 2))
+        Y = np.sin(X[:, 0:1]) * np.sin(X[:, 1:2]) + np.random.randn(40, 1) * 0.05
+    k = getattr(GPy.kern, kname)(dim, ARD=ard)
+    m = make_gpr(backend, X, Y, k)
+    m.randomize()
+    assert m.checkgrad()
+    # parameter order in m[:] (stationary.py:83, core/gp.py:108-109)
+    names = m.parameter_names_flat()
+    assert names[0].endswith("variance") and names[-1].endswith("Gaussian_noise.variance")
+    assert m[:].size == 2 + (dim if ard else 1)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_raw_predict_closed_form(backend):
+    """model_tests.py:63-82: predict_noiseless against the explicit pinv(K + s2 I) formula, 7 decimals."""
+    np.random.seed(12345)
+    N, N_new, D = 20, 50, 1
+    X = np.random.uniform(-3., 3., (N, 1))
+    Y = np.sin(X) + np.random.randn(N, D) * 0.05
+    X_new = np.random.uniform(-3., 3., (N_new, 1))
+    k = GPy.kern.RBF(1)
+    m = make_gpr(backend, X, Y, k)
+    m.randomize()
+    m.likelihood.variance = .5
+    v, ls = float(k.variance.values[0]), k.lengthscale.values
+    Kf = lambda A, B=None: O.K("rbf", A, B, v, ls, False)  # noqa: E731  (closed form on the host, independent of the backend)
+    Kinv = np.linalg.pinv(Kf(X) + np.eye(N) * 0.5)
+    K_hat = Kf(X_new) - Kf(X_new, X).dot(Kinv).dot(Kf(X, X_new))
+    mu_hat = Kf(X_new, X).dot(Kinv).dot(m.Y_normalized)
+    mu, covar = m.predict_noiseless(X_new, full_cov=True)
+    assert mu.shape == (N_new, D) and covar.shape == (N_new, N_new)
+    np.testing.assert_almost_equal(K_hat, covar)
+    np.testing.assert_almost_equal(mu_hat, mu)
+    mu, var = m.predict_noiseless(X_new)
+    assert mu.shape == (N_new, D) and var.shape == (N_new, 1)
+    np.testing.assert_almost_equal(np.diag(K_hat)[:, None], var)
+    np.testing.assert_almost_equal(mu_hat, mu)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_setxy_roundtrip(backend):
+    """gp_tests.py:50-60."""
+    np.random.seed(12345)
+    X = np.random.uniform(-3., 3., (20, 1))
+    Y = np.sin(X) + np.random.randn(20, 1) * 0.05
+    m = make_gpr(backend, X, Y, GPy.kern.RBF(1))
+    mu, var = m.predict(m.X)
+    Xc = m.X.copy()
+    m.set_XY(m.X[:10], m.Y[:10])
+    assert m.checkgrad()
+    m.set_XY(Xc, Y)
+    mu2, var2 = m.predict(m.X)
+    assert_allclose(mu, mu2)
+    assert_allclose(var, var2)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_branin_grid_variance_nonnegative(backend):
+    """model_tests.py:25-61: 5x5 Branin grid, RBF-ARD, noise fixed 1e-5, randomize + optimize, var >= 0 at 1e5 points."""
+    np.random.seed(3)
+    xg1, xg2 = np.linspace(-5, 10, 5), np.linspace(0, 15, 5)
+    X = np.zeros((25, 2))
+    for i, x1 in enumerate(xg1):
+        for j, x2 in enumerate(xg2):
+            X[i + 5 * j, :] = [x1, x2]
+    Y = branin(X)
+    m = make_gpr(backend, X, Y, GPy.kern.RBF(input_dim=2, ARD=True))
+    m.likelihood.variance.fix(1e-5)
+    m.randomize()
+    m.optimize()
+    Xp = np.random.uniform(size=(int(1e5) if backend == "cuda" else 5000, 2))
+    Xp[:, 0] = Xp[:, 0] * 15 - 5
+    Xp[:, 1] = Xp[:, 1] * 15
+    _, var = m.predict(Xp)
+    assert np.all(var >= 0.)
+    assert m.parameter_names_flat().size == 3      # the fixed noise is not an optimiser variable
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPyOpt GPModel / acquisitions through the public classes, against the golden vectors of the reference's own sources
+# ---------------------------------------------------------------------------------------------------------------------
+def _cond_tol(g):
+    K = g["K"]
+    w = np.linalg.eigvalsh(K + (g["noise"] + 1e-8) * np.eye(K.shape[0]))
+    return max(1.0, w[-1] / w[0] * 2.2e-16 / 1e-12)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_public_classes_golden(backend, golden):
+    g = golden
+    D = g["X"].shape[1]
+    ct = _cond_tol(g)
+    K = GPy.kern.RBF if g["kind"] == "rbf" else GPy.kern.Matern52
+    k = K(D, variance=g["variance"], lengthscale=g["lengthscale"], ARD=g["ard"])
+    m = make_gpr(backend, g["X"], g["Y"], k, noise_var=g["noise"])
+    assert_allclose(m.log_likelihood(), g["logL"], rtol=1e-9 * ct)
+    assert_allclose(np.ravel(k.variance.gradient), g["grad_var"].ravel(), rtol=1e-7 * ct)
+    assert_allclose(np.ravel(k.lengthscale.gradient), g["grad_len"].ravel(), rtol=1e-7 * ct)
+    assert_allclose(np.ravel(m.likelihood.variance.gradient), g["grad_noise"].ravel(), rtol=1e-7 * ct)
+    assert_allclose(m.posterior.woodbury_chol, g["L"], rtol=1e-9, atol=1e-12)
+    assert_allclose(m.posterior.woodbury_vector, g["alpha"], rtol=1e-9 * ct, atol=1e-9 * ct * np.abs(g["alpha"]).max())
+    mu, var = m.predict(g["Xs"])
+    assert_allclose(mu, g["pred_mu"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(var, g["pred_var"], rtol=1e-9 * ct, atol=1e-13 * ct)
+    mu, cov = m.predict(g["Xs"], full_cov=True)
+    assert_allclose(cov, g["pred_cov"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    dm, dv = m.predictive_gradients(g["Xs"])
+    assert dm.shape == g["dmu_dX"].shape and dv.shape == g["dv_dX"].shape
+    assert_allclose(dm, g["dmu_dX"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["dmu_dX"]).max())
+    assert_allclose(dv, g["dv_dX"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["dv_dX"]).max())
+    # GPyOpt adaptor + acquisitions (the object layout GPyOpt builds in BayesianOptimization.__init__)
+    gm = make_gpmodel(backend, exact_feval=False, verbose=False)
+    gm.model = m
+    mm, ss = gm.predict(g["Xs"])
+    assert_allclose(mm, g["gpm_m"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(ss, g["gpm_s"], rtol=1e-9 * ct)
+    mm, ss, dmdx, dsdx = gm.predict_withGradients(g["Xs"])
+    assert_allclose(dmdx, g["gpm_dmdx"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["gpm_dmdx"]).max())
+    assert_allclose(dsdx, g["gpm_dsdx"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["gpm_dsdx"]).max())
+    assert_allclose(gm.get_fmin(), g["fmin"], rtol=1e-9 * ct)
+    space = GPyOpt.Design_space([{'name': 'x', 'type': 'continuous', 'domain': (0, 1), 'dimensionality': D}])
+    ei = GPyOpt.acquisitions.AcquisitionEI(gm, space, optimizer=None, jitter=0.01)
+    lcb = GPyOpt.acquisitions.AcquisitionLCB(gm, space, optimizer=None, exploration_weight=2)
+    assert_allclose(ei.acquisition_function(g["Xs"]), g["ei"], rtol=1e-8 * ct, atol=1e-14)
+    f, df = ei.acquisition_function_withGradients(g["Xs"])
+    assert_allclose(f, g["ei_g_f"], rtol=1e-8 * ct, atol=1e-14)
+    assert_allclose(df, g["ei_g_df"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["ei_g_df"]).max())
+    assert_allclose(lcb.acquisition_function(g["Xs"]), g["lcb"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    f, df = lcb.acquisition_function_withGradients(g["Xs"])
+    assert_allclose(df, g["lcb_g_df"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["lcb_g_df"]).max())
+    # one point, as apply_optimizer's wrappers pass it (optimizer.py:200-232)
+    f1 = ei.acquisition_function(g["Xs"][3:4])
+    assert f1.shape == (1, 1)
+    assert_allclose(f1[0, 0], g["ei"][3, 0], rtol=1e-8 * ct, atol=1e-14)
+    m1, s1 = gm.predict(g["Xs"][3])            # GPModel itself accepts 1-D input (gpmodel.py:96-97)
+    assert_allclose(m1[0, 0], g["gpm_m"][3, 0], rtol=1e-9 * ct, atol=1e-11 * ct)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# jitchol ladder (linalg_test.py:7-37) -- CUDA only (the oracle's jitchol is checked in test_oracle_golden.py)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_jitchol_ladder_success_and_failure():
+    np.random.seed(5)
+    A = np.random.randn(20, 100)
+    A = A.dot(A.T)
+    vals, vectors = np.linalg.eigh(A)
+    vals[vals.argmin()] = 0
+    default_jitter = 1e-6 * np.mean(vals)
+    vals[vals.argmin()] = -default_jitter * (10 ** 3.5)
+    A_corrupt = (vectors * vals).dot(vectors.T)
+    L = GPy.util.linalg.jitchol(A_corrupt, maxtries=5)
+    A_new = L.dot(L.T)
+    diff = A_new - A_corrupt
+    assert_allclose(diff, np.eye(20) * np.diag(diff).mean(), atol=1e-11)
+    # the jitter that made it through is the 5th rung: mean(diag) * 1e-6 * 10^4 (linalg.py:66-72)
+    assert_allclose(np.diag(diff).mean(), np.diag(A_corrupt).mean() * 1e-6 * 1e4, rtol=1e-6)
+    with pytest.raises(np.linalg.LinAlgError):
+        GPy.util.linalg.jitchol(A_corrupt, maxtries=4)
+    with pytest.raises(np.linalg.LinAlgError, match="non-positive diagonal"):
+        GPy.util.linalg.jitchol(-np.eye(4))
+    # same ladder in the oracle
+    assert_allclose(O.jitchol(A_corrupt, maxtries=5), L, rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_linalg_surface_against_lapack():
+    rs = np.random.RandomState(9)
+    B = rs.randn(150, 150)
+    A = B @ B.T + 150 * np.eye(150)
+    Ai, L, Li, logdet = GPy.util.linalg.pdinv(A)
+    Ai_r, L_r, Li_r, ld_r = O.pdinv(A)
+    assert_allclose(L, L_r, rtol=1e-11, atol=1e-12)
+    assert_allclose(Li, Li_r, rtol=1e-10, atol=1e-13)
+    assert_allclose(Ai, Ai_r, rtol=1e-10, atol=1e-14)
+    assert_allclose(logdet, ld_r, rtol=1e-13)
+    Y = rs.randn(150, 2)
+    assert_allclose(GPy.util.linalg.dpotrs(L, Y, lower=1)[0], O.dpotrs(L_r, Y, lower=1)[0], rtol=1e-10, atol=1e-14)
+    assert_allclose(GPy.util.linalg.dpotri(L, lower=1)[0], Ai_r, rtol=1e-10, atol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hyper-parameter optimisation and the BO loop: CUDA run vs the identical host logic on the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def _opt_problem():
+    rs = np.random.RandomState(21)
+    X = rs.uniform(0, 1, (120, 3))
+    Y = np.sin(3 * X[:, :1]) + np.cos(2 * X[:, 1:2]) * X[:, 2:3] + 0.05 * rs.randn(120, 1)
+    return X, (Y - Y.mean()) / Y.std()
+
+
+@pytest.mark.parametrize("backend", ["oracle"])
+def test_optimize_restarts_improves_objective(backend):
+    X, Y = _opt_problem()
+    m = make_gpr(backend, X, Y, GPy.kern.Matern52(3, ARD=True), noise_var=0.1)
+    f0 = m.objective_function()
+    np.random.seed(0)
+    m.optimize_restarts(num_restarts=2, optimizer='lbfgs', max_iters=200, verbose=False)
+    assert m.objective_function() < f0 - 10
+    assert len(m.optimization_runs) == 2
+    assert_allclose(m.objective_function(), min(r.f_opt for r in m.optimization_runs), rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_optimize_matches_oracle_run():
+    """GP.optimize (core/gp.py:643-664) from the same start: every L-BFGS-B step sees f, g equal to ~1e-11, so the two runs
+    must end at the same optimum (compared at the optimiser's own tolerance, factr = 1e7 -> ~2e-9 relative in f)."""
+    X, Y = _opt_problem()
+    res = {}
+    for backend in ("cuda", "oracle"):
+        m = make_gpr(backend, X, Y, GPy.kern.Matern52(3, ARD=True), noise_var=0.1)
+        m.optimize(optimizer='lbfgs', max_iters=1000)
+        res[backend] = (m.objective_function(), m[:].copy(), m.optimization_runs[-1].funct_eval)
+    assert_allclose(res["cuda"][0], res["oracle"][0], rtol=1e-8)
+    assert_allclose(res["cuda"][1], res["oracle"][1], rtol=2e-4)
+    assert res["cuda"][2] == res["oracle"][2], "different number of objective evaluations: %r" % (res,)
+
+
+def _run_bo(backend, iters, seed=0, acquisition_type='EI', **kw):
+    np.random.seed(seed)
+    model = make_gpmodel(backend, kernel=GPy.kern.RBF(2), exact_feval=True, verbose=False, optimize_restarts=kw.pop("restarts", 5))
+    bo = GPyOpt.methods.BayesianOptimization(branin, domain=BRANIN_DOMAIN, model=model, acquisition_type=acquisition_type,
+                                             exact_feval=True, initial_design_numdata=5, initial_design_type='random', **kw)
+    bo.run_optimization(max_iter=iters)
+    return bo
+
+
+def test_bo_branin_runs_on_oracle_backend():
+    """Config 1 host logic end to end on CPU: 5 random initial points + 6 EI steps; the RNG order of Appendix C holds."""
+    bo = _run_bo("oracle", 6, restarts=2)
+    assert bo.X.shape == (11, 2) and bo.Y.shape == (11, 1)
+    np.random.seed(0)
+    x1 = np.random.uniform(-5, 10, 5)      # random_design.py:73-77: one uniform(size=n) draw per dimension, in order
+    x2 = np.random.uniform(1, 15, 5)
+    assert_allclose(bo.X[:5], np.c_[x1, x2])
+    assert bo.fx_opt == bo.Y.min() and bo.fx_opt <= bo.Y[:5].min()
+    lo, hi = np.array([-5., 1.]), np.array([10., 15.])
+    assert np.all(bo.X >= lo) and np.all(bo.X <= hi)
+    assert bo.model_parameters_iterations.shape[1] == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("acq", ["EI", "LCB"])
+def test_bo_branin_trajectory_matches_oracle(acq):
+    """BASELINE.json config 1: BO on 2-D Branin, GPRegression RBF, fixed seed -- CUDA numerics vs oracle numerics under the
+    identical host loop.  The evaluated points must coincide step by step."""
+    iters = 12
+    a = _run_bo("cuda", iters, acquisition_type=acq)
+    b = _run_bo("oracle", iters, acquisition_type=acq)
+    assert a.X.shape == b.X.shape == (5 + iters, 2)
+    same = np.all(np.abs(a.X - b.X) <= 1e-5 * (1 + np.abs(b.X)), axis=1)
+    first_bad = int(np.argmin(same)) if not same.all() else len(same)
+    assert same.all(), "trajectories separate at evaluation %d:\ncuda   %r\noracle %r" % (first_bad, a.X[first_bad], b.X[first_bad])
+    assert_allclose(a.Y, b.Y, rtol=1e-4, atol=1e-6)
+    assert np.argmin(a.Y) == np.argmin(b.Y)
