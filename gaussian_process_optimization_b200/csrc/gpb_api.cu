@@ -177,8 +177,8 @@ static size_t carve(int n_cap, int d, int p, int cb, gpb_model *m, char *base) {
   take(np * np, &fa);
   take(np * np, &fm);
   take(np * np, &fw);
-  take(nb * np, &fpart);
-  take(nb * (nb + 1) / 2 * (size_t)(d + 2), m ? &m->gpart : nullptr);
+  take(std::max<size_t>(nb, 128) * np, &fpart);  // GEMV partials: nb * np (factor_solve) or 8 * 16 * np (skinny products)
+  take(kgrad_part_doubles((int)np, (int)np, d, 1), m ? &m->gpart : nullptr);
   take(np * (size_t)d, m ? &m->X : nullptr);
   take(np * (size_t)d, m ? &m->XsT : nullptr);
   take(np * (size_t)p, m ? &m->Yc : nullptr);
@@ -460,7 +460,14 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   GPB_TRY(launch_kmat(m->kind, m->XcT, cpad, m->XsT, np, d, mcb, n, m->variance, 0.0, 2, m->KxT, np, cpad, np, s));
   // mu = Kx^T alpha                                                 posterior.py:276
   GPB_TRY(launch_rowdot(m->KxT, np, mcb, n, m->alpha, np, p, m->mu, s));
-  if (level >= 1) {
+  // A handful of candidates (the M = 1 calls of the L-BFGS-B refinement, optimizer.py:46-51): one bandwidth-bound pass over
+  // the triangle of M per product instead of a 128-row padded GEMM.
+  const bool skinny = mcb <= 8;
+  if (level >= 1 && skinny) {
+    const int c = mcb <= 1 ? 1 : mcb <= 2 ? 2 : mcb <= 4 ? 4 : 8;   // rows mcb .. c of KxT are zero (mode 2 padding)
+    GPB_TRY(factor_skinny_products(m->f, c, m->KxT, np, m->Vt, np, level >= 2 ? m->Ut : nullptr, np, m->f.part));
+    GPB_TRY(launch_var_from_vt(m->Vt, np, mcb, n, m->variance + (include_likelihood ? m->noise : 0.0), m->var, s));
+  } else if (level >= 1) {
     // Vt = KxT M^T  (== (L^-1 Kx)^T: dtrtrs of posterior.py:293 as a product with the explicit inverse factor)
     GemmArgs g{m->KxT, np, m->f.Mi, np, m->Vt, np, cpad, np, np, 1.0, 0.0, 0, 0, 2};
     GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, s));
@@ -470,8 +477,10 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   if (level >= 2) {
     GPB_REQUIRE(p == 1, "predictive gradients are implemented for a single output column (got %d)", p);
     // Ut = Vt M = (Ky^-1 Kx)^T                                      core/gp.py:450-451 (woodbury_inv product as 2nd triangular product)
-    GemmArgs g{m->Vt, np, m->f.Mi, np, m->Ut, np, cpad, np, np, 1.0, 0.0, 0, 2, 0};
-    GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, s));
+    if (!skinny) {
+      GemmArgs g{m->Vt, np, m->f.Mi, np, m->Ut, np, cpad, np, np, 1.0, 0.0, 0, 2, 0};
+      GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, s));
+    }
     // dmu = gradients_X(alpha^T, X*, X); dvar = gradients_X(-2 Kx^T Wi, X*, X)     core/gp.py:431-434,450-453
     GPB_TRY(launch_gradx(m->kind, m->XcT, cpad, mcb, m->XsT, np, n, d, m->variance, m->inv_ls_dev, m->alpha, 0, 1.0, 0, m->Ut, np,
                          -2.0, m->dmu, m->dvar, d, s));
@@ -696,8 +705,7 @@ int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int 
     G = gbuf.d();
     ldg = cols;
   }
-  const size_t tiles = (size_t)(t.npa / TILE) * (t.npb / TILE);
-  GPB_TRY(part.alloc(tiles * (d + 2) * sizeof(double)));
+  GPB_TRY(part.alloc(kgrad_part_doubles(t.npa, t.npb, d, 0) * sizeof(double)));
   GPB_TRY(res.alloc((d + 2) * sizeof(double)));
   GPB_TRY(launch_kgrad(kind, 0, t.XaT, t.npa, t.XbT, t.npb, d, n, cols, variance, G, ldg, nullptr, 0, 1, part.d(), res.d(), s));
   std::vector<double> h(d + 2);

@@ -29,59 +29,112 @@ namespace gpb {
 constexpr int LEAF_THREADS = 256;
 constexpr int LEAF_LD = TILE + 1;
 
-// The 16 steps j = 16 JB + jt of one column block.  JB is a template parameter so that for every register entry (a, b)
-// the membership test  y > j && (x <= j || y <= x)  collapses at compile time to at most three per-thread booleans
-// (tx > jt, ty <= jt, tx <= ty): the body is straight-line predicated DFMAs, no per-entry index arithmetic or branches.
+// One column block b of the rank-1 update of step j = 16 JB + jt.  Called from fully unrolled loops, so `b` and JB are
+// compile-time after unrolling.  The membership test of entry (a, b),
+//     y > j && (x <= j || y <= x)        (x = ty + 16 a, y = tx + 16 b),
+// is folded into the OPERANDS instead of predicating 64 DFMAs: the caller zeroes u for the columns left of j, and passes
+// row factors that are zero where the row is inactive (nw: plain -w; nwd: -w masked by y <= x for the diagonal register
+// blocks; nw_jd / nw_jo: row block JB on / off the diagonal register block).  A zero factor leaves the entry unchanged
+// (s + (-0 * u) == s), so the body is straight-line unconditional DFMAs.
 template <int MODE, int JB>
-__device__ __forceinline__ void leaf_sweep_block(double (&s)[8][8], double *colbuf, double *piv, int tx, int ty, int tid,
-                                                 int index_base, int *info, bool &failed) {
+__device__ __forceinline__ void leaf_update_col(double (&s)[8][8], const double (&nw)[8], const double (&nwd)[8], double nw_jd,
+                                                double nw_jo, double ub, int b) {
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    if (a < JB) {
+      s[a][b] = fma(nw[a], ub, s[a][b]);                     // W^T rows: x <= j always
+    } else if (a == JB) {
+      s[a][b] = fma(b == JB ? nw_jd : nw_jo, ub, s[a][b]);   // rows of the current block
+    } else {
+      if (MODE || b > a) continue;                           // x > j: only the lower part of the trailing matrix
+      s[a][b] = fma(b == a ? nwd[a] : nw[a], ub, s[a][b]);
+    }
+  }
+}
+
+// ---- split-phase CTA barrier (mbarrier): arrive right after publishing a column, wait just before reading the next one ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("{\n.reg .b64 t;\nmbarrier.arrive.shared::cta.b64 t, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nLEAF_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra LEAF_DONE;\nbra LEAF_WAIT;\nLEAF_DONE:\n}" ::"r"(
+          (unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
+// Zero-instruction scheduling fence for one value: everything that consumes v is ordered after this point.
+__device__ __forceinline__ void pin(double &v) { asm volatile("" : "+d"(v)); }
+
+// The 16 steps j = 16 JB + jt of one column block, software pipelined with a split-phase barrier.  Phase j of the mbarrier
+// completes when all 256 threads have passed the point "column j is published".  A step is
+//     wait(phase j) -> load column j (pivot, row factors, column factors) -> reciprocal -> update the register column block
+//     that holds column j + 1 -> its 16 owner threads publish it -> arrive(phase j + 1) -> the bulk of the rank-1 update,
+// so that the publish -> barrier -> load -> reciprocal chain of the next column (~180 cycles, scripts/microbench) runs under
+// the bulk DFMAs of this one instead of after them.  `pin` keeps the compiler from hoisting the bulk above the publish.
+// Two column buffers suffice: a thread overwrites buffer (j + 1) & 1 only after phase j completed, i.e. after every thread
+// has finished its loads of column j - 1 (all loads of a step precede its arrive).
+template <int MODE, int JB>
+__device__ __forceinline__ void leaf_sweep_block(double (&s)[8][8], double *colbuf, double *piv, uint64_t *bar, int tx, int ty,
+                                                 int tid, int &fail_at) {
   const bool t_le = tx <= ty;  // y <= x inside a diagonal (a == b) register block
 #pragma unroll 1
   for (int jt = 0; jt < 16; ++jt) {
     const int j = JB * 16 + jt;
-    double *cb = colbuf + (j & 1) * TILE;
-    if (tx == jt) {
-#pragma unroll
-      for (int a = 0; a < 8; ++a) cb[ty + 16 * a] = s[a][JB];
-    }
-    __syncthreads();
+    const double *cb = colbuf + (j & 1) * TILE;
+    double *nb = colbuf + ((j + 1) & 1) * TILE;
+    mbar_wait(bar, j & 1);
     const double pivot = cb[j];
-    if (!(pivot > 0.0) && !failed) {
-      failed = true;
-      if (tid == 0) atomicCAS(info, 0, index_base + j + 1);
-    }
+    if (!(pivot > 0.0) && fail_at == 0) fail_at = j + 1;
     // the epilogue divides by sqrt(piv): Cholesky pivots are L_jj^2, in MODE 1 the diagonal entry is L_jj itself
     if (tid == 0) piv[j] = MODE ? pivot * pivot : pivot;
-    const double rinv = 1.0 / pivot;
+    const double nrinv = -1.0 / pivot;
     const bool y_gt = tx > jt;   // y > j inside column block JB
     const bool x_le = ty <= jt;  // x <= j inside row block JB
-    double w[8], u[8];
+    double nw[8], nwd[8], u[8];
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
       if (MODE && a > JB) continue;  // trtri-only: rows below the current block are never touched
       double c = cb[ty + 16 * a];
       if (a == JB && ty == jt) c = 1.0;
-      w[a] = c * rinv;
+      nw[a] = c * nrinv;
+      nwd[a] = t_le ? nw[a] : 0.0;
     }
+    const double nw_jo = x_le ? nw[JB] : 0.0;                           // row block JB, columns right of the diagonal block
+    const double nw_jd = (MODE ? x_le : (x_le || t_le)) ? nw[JB] : 0.0;  // row block JB, diagonal register block
 #pragma unroll
     for (int b = JB; b < 8; ++b) u[b] = cb[tx + 16 * b];
+    if (jt < 15) {
+      // column j + 1 lives in column block JB of the threads with tx == jt + 1
+      leaf_update_col<MODE, JB>(s, nw, nwd, nw_jd, nw_jo, y_gt ? u[JB] : 0.0, JB);
+      if (tx == jt + 1) {
 #pragma unroll
-    for (int b = JB; b < 8; ++b) {
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        bool act;
-        if (a < JB) {
-          act = true;                        // W^T rows: x <= j always
-        } else if (a == JB) {
-          if (MODE) act = x_le;
-          else act = x_le || (b == a && t_le);   // x > j: trailing matrix, needs y <= x (impossible for b > a)
-        } else {
-          if (MODE || b > a) continue;       // x > j: only the lower part of the trailing matrix (Cholesky mode)
-          act = (b < a) || t_le;
-        }
-        if (b == JB) act = act && y_gt;
-        if (act) s[a][b] = fma(-w[a], u[b], s[a][b]);
+        for (int a = 0; a < 8; ++a) nb[ty + 16 * a] = s[a][JB];
       }
+      mbar_arrive(bar);
+#pragma unroll
+      for (int b = JB + 1; b < 8; ++b) pin(u[b]);
+#pragma unroll
+      for (int b = JB + 1; b < 8; ++b) leaf_update_col<MODE, JB>(s, nw, nwd, nw_jd, nw_jo, u[b], b);
+    } else {
+      // last column of the block: nothing of block JB is right of it; column j + 1 is the first column of block JB + 1,
+      // owned by the threads with tx == 0
+      constexpr int NB = JB < 7 ? JB + 1 : 7;
+      if (JB < 7) {
+        leaf_update_col<MODE, JB>(s, nw, nwd, nw_jd, nw_jo, u[NB], NB);
+        if (tx == 0) {
+#pragma unroll
+          for (int a = 0; a < 8; ++a) nb[ty + 16 * a] = s[a][NB];
+        }
+      }
+      mbar_arrive(bar);
+#pragma unroll
+      for (int b = JB + 2; b < 8; ++b) pin(u[b]);
+#pragma unroll
+      for (int b = JB + 2; b < 8; ++b) leaf_update_col<MODE, JB>(s, nw, nwd, nw_jd, nw_jo, u[b], b);
     }
   }
 }
@@ -92,12 +145,14 @@ template <int MODE>
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
 leaf_potrf_inv_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, int ldm, int index_base, int *info) {
   extern __shared__ double sm[];
-  double *colbuf = sm;               // 2 x 128
-  double *piv = sm + 2 * TILE;       // 128
-  double *stage = sm + 3 * TILE;     // 128 x 129 (epilogue only)
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm);  // sm[0]; sm[1] pads to 16 bytes
+  double *colbuf = sm + 2;           // 2 x 128
+  double *piv = colbuf + 2 * TILE;   // 128 (after the sweep: 1 / sqrt(pivot))
+  double *stage = piv + TILE;        // 128 x 129 (epilogue only)
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
+  if (tid == 0) mbar_init(bar, LEAF_THREADS);
 
   double s[8][8];
 #pragma unroll
@@ -110,16 +165,22 @@ leaf_potrf_inv_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, 
     }
   }
 
-  bool failed = false;
-  leaf_sweep_block<MODE, 0>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
-  leaf_sweep_block<MODE, 1>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
-  leaf_sweep_block<MODE, 2>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
-  leaf_sweep_block<MODE, 3>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
-  leaf_sweep_block<MODE, 4>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
-  leaf_sweep_block<MODE, 5>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
-  leaf_sweep_block<MODE, 6>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
-  leaf_sweep_block<MODE, 7>(s, colbuf, piv, tx, ty, tid, index_base, info, failed);
-  __syncthreads();
+  if (tx == 0) {
+#pragma unroll
+    for (int a = 0; a < 8; ++a) colbuf[ty + 16 * a] = s[a][0];
+  }
+  __syncthreads();   // mbarrier initialised, column 0 published
+  mbar_arrive(bar);  // phase 0
+  int fail_at = 0;
+  leaf_sweep_block<MODE, 0>(s, colbuf, piv, bar, tx, ty, tid, fail_at);
+  leaf_sweep_block<MODE, 1>(s, colbuf, piv, bar, tx, ty, tid, fail_at);
+  leaf_sweep_block<MODE, 2>(s, colbuf, piv, bar, tx, ty, tid, fail_at);
+  leaf_sweep_block<MODE, 3>(s, colbuf, piv, bar, tx, ty, tid, fail_at);
+  leaf_sweep_block<MODE, 4>(s, colbuf, piv, bar, tx, ty, tid, fail_at);
+  leaf_sweep_block<MODE, 5>(s, colbuf, piv, bar, tx, ty, tid, fail_at);
+  leaf_sweep_block<MODE, 6>(s, colbuf, piv, bar, tx, ty, tid, fail_at);
+  leaf_sweep_block<MODE, 7>(s, colbuf, piv, bar, tx, ty, tid, fail_at);
+  if (tid == 0 && fail_at != 0) atomicCAS(info, 0, index_base + fail_at);  // every thread saw the same pivots
 
   // ---- epilogue: scale, stage through shared memory, coalesced writes of L (into A) and W = L^-1 (into Mi) ----
 #pragma unroll
@@ -127,16 +188,18 @@ leaf_potrf_inv_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, 
 #pragma unroll
     for (int b = 0; b < 8; ++b) stage[(ty + 16 * a) * LEAF_LD + tx + 16 * b] = s[a][b];
   __syncthreads();
+  if (tid < TILE) piv[tid] = 1.0 / sqrt(piv[tid]);   // one reciprocal square root per column instead of two per element
+  __syncthreads();
   for (int e = tid; e < TILE * TILE; e += LEAF_THREADS) {
     const int r = e >> 7, c = e & 127;
     double l, wv;
     if (c < r) {
-      l = stage[r * LEAF_LD + c] / sqrt(piv[c]);
-      wv = stage[c * LEAF_LD + r] / sqrt(piv[r]);
+      l = stage[r * LEAF_LD + c] * piv[c];
+      wv = stage[c * LEAF_LD + r] * piv[r];
     } else if (c == r) {
-      const double d = sqrt(piv[r]);
-      l = d;
-      wv = 1.0 / d;
+      const double d = piv[r];
+      l = 1.0 / d;
+      wv = d;
     } else {
       l = 0.0;
       wv = 0.0;
@@ -147,7 +210,7 @@ leaf_potrf_inv_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, 
 }
 
 static int launch_leaf(Factor &f, int off, int mode) {
-  const size_t smem = (size_t)(3 * TILE + TILE * LEAF_LD) * sizeof(double);
+  const size_t smem = (size_t)(2 + 3 * TILE + TILE * LEAF_LD) * sizeof(double);
   static bool configured = false;
   if (!configured) {
     GPB_CUDA(cudaFuncSetAttribute(leaf_potrf_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -339,6 +402,109 @@ int factor_solve(Factor &f, const double *Y, int p, double *z, double *alpha) {
     GPB_CHECK_LAUNCH();
     count_launch(3);
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Skinny triangular products for a handful of right-hand sides (the M = 1 .. 8 candidate calls that L-BFGS-B makes from
+// every anchor point, optimizer.py:46-51): one pass over M serves all C vectors, so the cost is the HBM read of the
+// triangle (8 N^2 / 2 bytes) instead of a 128-row padded GEMM.
+//   Z[c][i] = sum_{k <= i} M[i][k] B[c][k]          (trmm_lower_skinny:   Vt = KxT M^T, row c = M k*_c)
+//   U[c][j] = sum_{i >= j} M[i][j] Z[c][i]          (trmm_lower_t_skinny: Ut = Vt M,    row c = M^T (M k*_c))
+// Fixed reduction orders -> bitwise reproducible.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) trmm_lower_skinny_kernel(const double *__restrict__ M, int ld, int np,
+                                                                const double *__restrict__ B, int ldb, double *__restrict__ Z,
+                                                                int ldz) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= np) return;
+  const int i = np - 1 - warp;             // long rows first
+  const int kend = (i / TILE + 1) * TILE;  // the diagonal leaf block holds explicit zeros above the diagonal
+  const double *row = M + (size_t)i * ld;
+  double acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.0;
+  int k = lane;
+  for (; k + 96 < kend; k += 128) {
+    const double m0 = row[k], m1 = row[k + 32], m2 = row[k + 64], m3 = row[k + 96];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const double *b = B + (size_t)c * ldb + k;
+      acc[c] = fma(m0, b[0], acc[c]);
+      acc[c] = fma(m1, b[32], acc[c]);
+      acc[c] = fma(m2, b[64], acc[c]);
+      acc[c] = fma(m3, b[96], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const double v = warp_sum(acc[c]);
+    if (lane == 0) Z[(size_t)c * ldz + i] = v;
+  }
+}
+
+constexpr int TRMM_T_SPLITS = 16;
+
+// part[(c * S + s) * np + j] = sum over the 128-row chunks rc >= cb with rc % S == s of sum_i M[i][j] Z[c][i]
+template <int C>
+__global__ void __launch_bounds__(TILE) trmm_lower_t_skinny_partial_kernel(const double *__restrict__ M, int ld,
+                                                                           const double *__restrict__ Z, int ldz,
+                                                                           double *__restrict__ part, int np) {
+  const int cb = blockIdx.x, s = blockIdx.y, nb = np / TILE;
+  const int j = cb * TILE + threadIdx.x;
+  double acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.0;
+  int rc = cb + ((s - cb) % TRMM_T_SPLITS + TRMM_T_SPLITS) % TRMM_T_SPLITS;  // first chunk >= cb congruent to s
+  for (; rc < nb; rc += TRMM_T_SPLITS) {
+    const double *p = M + (size_t)(rc * TILE) * ld + j;
+    const double *zz = Z + rc * TILE;
+#pragma unroll 8
+    for (int i = 0; i < TILE; ++i) {
+      const double m = p[(size_t)i * ld];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fma(m, zz[(size_t)c * ldz + i], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) part[((size_t)c * TRMM_T_SPLITS + s) * np + j] = acc[c];
+}
+
+__global__ void trmm_lower_t_skinny_reduce_kernel(const double *__restrict__ part, int np, int C, double *__restrict__ U, int ldu) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (j >= np || c >= C) return;
+  double acc = 0.0;
+#pragma unroll
+  for (int s = 0; s < TRMM_T_SPLITS; ++s) acc += part[((size_t)c * TRMM_T_SPLITS + s) * np + j];
+  U[(size_t)c * ldu + j] = acc;
+}
+
+// C in {1, 2, 4, 8} right-hand sides stored as rows of B (row stride ldb); rows beyond the caller's count must be readable
+// (zero padded).  want_u = 0: only Z.  part: >= 8 * TRMM_T_SPLITS * np doubles.
+int factor_skinny_products(Factor &f, int c, const double *B, int ldb, double *Z, int ldz, double *U, int ldu, double *part) {
+  GPB_REQUIRE(c == 1 || c == 2 || c == 4 || c == 8, "skinny products: C must be 1, 2, 4 or 8 (got %d)", c);
+  const int np = f.np, nb = np / TILE;
+  const int blocks = (np * 32 + 255) / 256;
+  const dim3 gp(nb, TRMM_T_SPLITS), gr((np + 255) / 256, c);
+#define GPB_SK(C_)                                                                                     \
+  do {                                                                                                 \
+    trmm_lower_skinny_kernel<C_><<<blocks, 256, 0, f.stream>>>(f.Mi, np, np, B, ldb, Z, ldz);           \
+    GPB_CHECK_LAUNCH();                                                                                \
+    count_launch();                                                                                    \
+    if (U) {                                                                                           \
+      trmm_lower_t_skinny_partial_kernel<C_><<<gp, TILE, 0, f.stream>>>(f.Mi, np, Z, ldz, part, np);    \
+      GPB_CHECK_LAUNCH();                                                                              \
+      trmm_lower_t_skinny_reduce_kernel<<<gr, 256, 0, f.stream>>>(part, np, C_, U, ldu);               \
+      GPB_CHECK_LAUNCH();                                                                              \
+      count_launch(2);                                                                                 \
+    }                                                                                                  \
+  } while (0)
+  if (c == 1) GPB_SK(1);
+  else if (c == 2) GPB_SK(2);
+  else if (c == 4) GPB_SK(4);
+  else GPB_SK(8);
+#undef GPB_SK
   return 0;
 }
 

@@ -152,6 +152,8 @@ int factor_trtri(Factor &f);                     // A holds a lower-triangular L
 int factor_potri(Factor &f);                     // W = Mi^T Mi (lower tiles)
 int factor_solve(Factor &f, const double *Y, int p, double *z, double *alpha);  // alpha = Mi^T (Mi Y);  Y, z, alpha: np x p col-major (p vectors of np)
 int factor_logdet(Factor &f, double *out_dev);   // 2 sum log L_ii, i < n
+// Z[c] = Mi B[c], U[c] = Mi^T Z[c] for c in {1,2,4,8} vectors stored as rows (U may be NULL); part: 8 * 16 * np doubles
+int factor_skinny_products(Factor &f, int c, const double *B, int ldb, double *Z, int ldz, double *U, int ldu, double *part);
 int launch_copy2d(double *dst, int ldd, const double *src, int lds, int rows, int cols, cudaStream_t s);
 int launch_symmetrize_lower(double *A, int ld, int n, cudaStream_t s);
 

@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_k
     const int r = t - gid * in_group;
     tm = first + r % gsz;
     tn = r / gsz;
+    // longest k-ranges first: with a triangular k-range the tiles differ in length by up to K / 16 : 1, and a launch that
+    // ends on its longest tiles leaves most SMs idle for a full-length tile (~1 ms at K = 8192)
+    if (p.khi_mode == 2) tn = tiles_n - 1 - tn;   // k <= column block: right-most columns are the longest
+    if (p.khi_mode == 1) tm = tiles_m - 1 - tm;   // k <= row block: bottom rows are the longest
   }
   const int row0 = tm * BM, col0 = tn * BN;
   const int rblk = row0 & ~127, cblk = col0 & ~127;  // enclosing 128-block

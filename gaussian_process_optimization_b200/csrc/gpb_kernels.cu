@@ -5,7 +5,7 @@
 // gradients_X (:271-278,354-364 -> stationary_utils.c:1-14); RBF.K_of_r/dK_dr (rbf.py:50-54), Matern52 (:575-579).
 //
 // Layout: inputs are pre-scaled once per parameter write into a dimension-major array XsT[q][i] = X[i][q] / l_q
-// (row stride ldx >= number of points, zero padded), so that a 128-point tile of one dimension is one coalesced 1 KB line
+// (row stride ldx >= number of points, zero padded), so that a 64-point tile of one dimension is one coalesced 512 B line
 // and lands in shared memory in the order the register-tiled pair loops read it.  r^2 is the direct sum of squared
 // differences (exactly 0 on the diagonal, never negative) instead of the reference's |x|^2+|y|^2-2xy expansion.
 #include "gpb_common.cuh"
@@ -34,51 +34,54 @@ int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K tile kernel: one CTA = one 128 x 128 tile, 256 threads, thread (ty, tx) owns rows ty + 16a, cols tx + 16b (a, b < 8):
-// for fixed (a, b) a warp writes two 128-byte row segments (fully coalesced).
+// K tile kernel: one CTA = one 64 x 64 tile, 256 threads, thread (ty, tx) owns rows ty + 16a, cols tx + 16b (a, b < 4):
+// for fixed (a, b) a warp writes two 128-byte row segments (fully coalesced).  The 4 x 4 register tile keeps the kernel at
+// ~64 registers (4+ CTAs per SM) and its unrolled body inside the instruction cache -- the first version (8 x 8 per thread,
+// 1 CTA per SM) stalled on instruction fetch and exposed latency (ncu: profiles/r1c_kgrad_full.md).
 //   mode 0 (rect):  out[i][j] = k(r_ij) for i < n_rows, j < n_cols (nothing else is written)
 //   mode 1 (Ky, padded): out is np x np;  i, j < n: k + (i == j) * diag_add;  otherwise identity
 //   mode 2 (rect, zero padded): out is rows_pad x cols_pad; k inside n_rows x n_cols, 0 outside
 // ---------------------------------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(256) kmat_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
-                                                   int n_rows, int n_cols, double variance, double diag_add, int mode,
-                                                   double *__restrict__ out, int ldo) {
+__global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
+                                                      int n_rows, int n_cols, double variance, double diag_add, int mode,
+                                                      double *__restrict__ out, int ldo) {
   extern __shared__ double sm[];
-  double *xa = sm;             // [d][128]
-  double *xb = sm + d * TILE;  // [d][128]
-  const int row0 = blockIdx.y * TILE, col0 = blockIdx.x * TILE;
+  double *xa = sm;              // [d][64]
+  double *xb = sm + d * KTILE;  // [d][64]
+  const int row0 = blockIdx.y * KTILE, col0 = blockIdx.x * KTILE;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int e = tid; e < d * TILE; e += 256) {
-    const int q = e >> 7, i = e & 127;
+  for (int e = tid; e < d * KTILE; e += 256) {
+    const int q = e >> 6, i = e & 63;
     xa[e] = XaT[(size_t)q * lda + row0 + i];
     xb[e] = XbT[(size_t)q * ldb + col0 + i];
   }
   __syncthreads();
-  double r2[8][8];
+  double r2[4][4];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) r2[a][b] = 0.0;
+    for (int b = 0; b < 4; ++b) r2[a][b] = 0.0;
+#pragma unroll 2
   for (int q = 0; q < d; ++q) {
-    double va[8], vb[8];
+    double va[4], vb[4];
 #pragma unroll
-    for (int a = 0; a < 8; ++a) va[a] = xa[q * TILE + ty + 16 * a];
+    for (int a = 0; a < 4; ++a) va[a] = xa[q * KTILE + ty + 16 * a];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) vb[b] = xb[q * TILE + tx + 16 * b];
+    for (int b = 0; b < 4; ++b) vb[b] = xb[q * KTILE + tx + 16 * b];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
+      for (int b = 0; b < 4; ++b) {
         const double df = va[a] - vb[b];
         r2[a][b] = fma(df, df, r2[a][b]);
       }
   }
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
+  for (int a = 0; a < 4; ++a) {
     const int i = row0 + ty + 16 * a;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < 4; ++b) {
       const int j = col0 + tx + 16 * b;
       const bool inside = (i < n_rows) && (j < n_cols);
       double v;
@@ -96,9 +99,10 @@ __global__ void __launch_bounds__(256) kmat_kernel(const double *__restrict__ Xa
 int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                 double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
                 cudaStream_t s) {
-  const size_t smem = (size_t)2 * d * TILE * sizeof(double);
-  GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large (max 100)", d);
-  dim3 grid(cols_pad / TILE, rows_pad / TILE);
+  const size_t smem = (size_t)2 * d * KTILE * sizeof(double);
+  GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large", d);
+  GPB_REQUIRE(rows_pad % KTILE == 0 && cols_pad % KTILE == 0, "kmat: padded sizes must be multiples of %d", KTILE);
+  dim3 grid(cols_pad / KTILE, rows_pad / KTILE);
   if (grid.x == 0 || grid.y == 0) return 0;
   if (kind == GPB_KERN_RBF) {
     if (smem > 48 * 1024)
@@ -115,7 +119,7 @@ int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Hyper-parameter gradient reduction.  Per 128x128 tile: recompute r^2, k, k'/r from the X tiles, form G on the fly and
+// Hyper-parameter gradient reduction.  Per 64 x 64 tile: recompute r^2, k, k'/r from the X tiles, form G on the fly and
 // accumulate
 //     part[tile][0]     = sum w K_ij G_ij                      (-> d/dvariance after / variance, stationary.py:224)
 //     part[tile][1]     = sum_{i == j} G_ii                    (-> d/dnoise = tr(dL_dK), exact_gaussian_inference.py:72)
@@ -127,14 +131,14 @@ int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb
 // so the result is bitwise reproducible (L-BFGS-B trajectories depend on it).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int KIND, int FUSED>
-__global__ void __launch_bounds__(256) kgrad_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
-                                                    int n_rows, int n_cols, double variance, const double *__restrict__ G, int ldg,
-                                                    const double *__restrict__ alpha, int ld_alpha, int p_out, int tiles_x,
-                                                    double *__restrict__ part) {
+__global__ void __launch_bounds__(256, 3) kgrad_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
+                                                       int n_rows, int n_cols, double variance, const double *__restrict__ G, int ldg,
+                                                       const double *__restrict__ alpha, int ld_alpha, int p_out, int tiles_x,
+                                                       double *__restrict__ part) {
   extern __shared__ double sm[];
-  double *xa = sm;                   // [d][128]
-  double *xb = sm + d * TILE;        // [d][128]
-  double *wacc = xb + d * TILE;      // [8 warps][d + 2]
+  double *xa = sm;                   // [d][64]
+  double *xb = sm + d * KTILE;       // [d][64]
+  double *wacc = xb + d * KTILE;     // [8 warps][d + 2]
   int tr, tc;
   if (FUSED) {
     const int t = blockIdx.x;
@@ -146,53 +150,74 @@ __global__ void __launch_bounds__(256) kgrad_kernel(const double *__restrict__ X
     tr = blockIdx.x / tiles_x;
     tc = blockIdx.x - tr * tiles_x;
   }
-  const int row0 = tr * TILE, col0 = tc * TILE;
+  const int row0 = tr * KTILE, col0 = tc * KTILE;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, warp = tid >> 5, lane = tid & 31;
-  for (int e = tid; e < d * TILE; e += 256) {
-    const int q = e >> 7, i = e & 127;
+  for (int e = tid; e < d * KTILE; e += 256) {
+    const int q = e >> 6, i = e & 63;
     xa[e] = XaT[(size_t)q * lda + row0 + i];
     xb[e] = XbT[(size_t)q * ldb + col0 + i];
   }
+  // G (or Wi) entries of this thread: issued before the distance loop so that the HBM latency hides behind it
+  double gw[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = row0 + ty + 16 * a;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = col0 + tx + 16 * b;
+      gw[a][b] = (i < n_rows && j < n_cols) ? G[(size_t)i * ldg + j] : 0.0;
+    }
+  }
   __syncthreads();
-  double r2[8][8];
+  double r2[4][4];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) r2[a][b] = 0.0;
+    for (int b = 0; b < 4; ++b) r2[a][b] = 0.0;
+#pragma unroll 2
   for (int q = 0; q < d; ++q) {
-    double va[8], vb[8];
+    double va[4], vb[4];
 #pragma unroll
-    for (int a = 0; a < 8; ++a) va[a] = xa[q * TILE + ty + 16 * a];
+    for (int a = 0; a < 4; ++a) va[a] = xa[q * KTILE + ty + 16 * a];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) vb[b] = xb[q * TILE + tx + 16 * b];
+    for (int b = 0; b < 4; ++b) vb[b] = xb[q * KTILE + tx + 16 * b];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
+      for (int b = 0; b < 4; ++b) {
         const double df = va[a] - vb[b];
         r2[a][b] = fma(df, df, r2[a][b]);
       }
+  }
+  if (FUSED) {
+    // gw <- dL_dK = 0.5 (alpha alpha^T - P Wi)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = row0 + ty + 16 * a;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int j = col0 + tx + 16 * b;
+        if (i < n_rows && j < n_cols) {
+          double aa = 0.0;
+          for (int p = 0; p < p_out; ++p) aa = fma(alpha[(size_t)p * ld_alpha + i], alpha[(size_t)p * ld_alpha + j], aa);
+          gw[a][b] = 0.5 * (aa - (double)p_out * gw[a][b]);
+        }
+      }
+    }
   }
   // r2[a][b] is overwritten by the pair weight  w * (k'/r) * G
   const double wt = (FUSED && tr != tc) ? 2.0 : 1.0;
   double acc_var = 0.0, acc_tr = 0.0;
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
+  for (int a = 0; a < 4; ++a) {
     const int i = row0 + ty + 16 * a;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < 4; ++b) {
       const int j = col0 + tx + 16 * b;
       double wgt = 0.0;
       if (i < n_rows && j < n_cols) {
-        double g;
-        if (FUSED) {
-          double aa = 0.0;
-          for (int p = 0; p < p_out; ++p) aa = fma(alpha[(size_t)p * ld_alpha + i], alpha[(size_t)p * ld_alpha + j], aa);
-          g = 0.5 * (aa - (double)p_out * G[(size_t)i * ldg + j]);
-          if (i == j) acc_tr += g;
-        } else {
-          g = G[(size_t)i * ldg + j];
-        }
+        const double g = gw[a][b];
+        if (FUSED && i == j) acc_tr += g;
         double k, dk;
         cov_k_dk<KIND>(r2[a][b], variance, k, dk);
         acc_var = fma(wt * k, g, acc_var);
@@ -208,20 +233,21 @@ __global__ void __launch_bounds__(256) kgrad_kernel(const double *__restrict__ X
     wacc[warp * (d + 2) + 1] = acc_tr;
   }
   for (int q = 0; q < d; ++q) {
-    double va[8], vb[8];
+    double va[4], vb[4];
 #pragma unroll
-    for (int a = 0; a < 8; ++a) va[a] = xa[q * TILE + ty + 16 * a];
+    for (int a = 0; a < 4; ++a) va[a] = xa[q * KTILE + ty + 16 * a];
 #pragma unroll
-    for (int b = 0; b < 8; ++b) vb[b] = xb[q * TILE + tx + 16 * b];
-    double acc = 0.0;
+    for (int b = 0; b < 4; ++b) vb[b] = xb[q * KTILE + tx + 16 * b];
+    double acc4[4] = {0.0, 0.0, 0.0, 0.0};   // one chain per row block: four independent dependency chains
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
+      for (int b = 0; b < 4; ++b) {
         const double df = va[a] - vb[b];
         const double w = r2[a][b];
-        if (w != 0.0) acc = fma(w, df * df, acc);   // w == 0 with df^2 == inf (lengthscale -> 0) contributes 0, not NaN
+        if (w != 0.0) acc4[a] = fma(w, df * df, acc4[a]);   // w == 0 with df^2 == inf (lengthscale -> 0) contributes 0, not NaN
       }
+    double acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
     acc = warp_sum(acc);
     if (lane == 0) wacc[warp * (d + 2) + 2 + q] = acc;
   }
@@ -247,9 +273,9 @@ __global__ void colsum_kernel(const double *__restrict__ part, int ntiles, int n
 int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                  double variance, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out, double *part,
                  double *out_dev, cudaStream_t s) {
-  const size_t smem = (size_t)(2 * d * TILE + 8 * (d + 2)) * sizeof(double);
-  GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large (max 96)", d);
-  const int tr = (n_rows + TILE - 1) / TILE, tc = (n_cols + TILE - 1) / TILE;
+  const size_t smem = (size_t)(2 * d * KTILE + 8 * (d + 2)) * sizeof(double);
+  GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large", d);
+  const int tr = (n_rows + KTILE - 1) / KTILE, tc = (n_cols + KTILE - 1) / KTILE;
   const int tiles = fused ? tr * (tr + 1) / 2 : tr * tc;
   if (tiles == 0) return 0;
 #define GPB_KGRAD(K_, F_)                                                                                                 \

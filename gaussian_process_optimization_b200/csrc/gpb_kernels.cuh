@@ -4,6 +4,13 @@
 
 namespace gpb {
 
+constexpr int KTILE = 64;  // covariance / gradient-reduction tile edge (kmat_kernel, kgrad_kernel)
+// doubles of scratch launch_kgrad needs for its per-tile partials (padded sizes are multiples of 128)
+inline size_t kgrad_part_doubles(int rows_pad, int cols_pad, int d, int fused) {
+  const size_t tr = rows_pad / KTILE, tc = cols_pad / KTILE;
+  return (fused ? tr * (tr + 1) / 2 : tr * tc) * (size_t)(d + 2);
+}
+
 int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, double *XsT, int ldx, cudaStream_t s);
 
 // mode: 0 rect exact, 1 padded Ky (identity outside n x n, diag_add on the diagonal), 2 rect zero padded

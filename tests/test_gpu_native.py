@@ -316,3 +316,32 @@ def test_not_positive_definite_returns_info():
     info, _, _ = m.fit(False, extra_jitter=-2e-8)   # net diagonal shift < 0 -> a non-positive pivot must be reported
     assert info > 0
     m.close()
+
+
+@pytest.mark.parametrize("kind", ["rbf", "mat52"])
+def test_small_candidate_counts_use_the_skinny_products(kind):
+    """M = 1 .. 8 candidates (the L-BFGS-B refinement calls, optimizer.py:46-51) take the bandwidth-bound triangular
+    matrix-vector path; M = 9 takes the GEMM path.  Both must match the oracle and each other."""
+    N, D = 700, 6
+    X, Y, ls = _synth(N, D)
+    st = O.GPState(kind, X, Y, 1.1, ls, 1e-3)
+    m = native.NativeModel(kind, True, D, 1, n_cap=N, cand_block=256)
+    m.set_data(X, Y)
+    m.set_theta(1.1, ls, 1e-3)
+    info, _, _ = m.fit(False)
+    assert info == 0
+    fmin = m.fmin()
+    Xc = np.random.RandomState(3).uniform(0, 1, (9, D))
+    f9 = m.acquisition("EI", 0.01, fmin, Xc, with_gradients=True, want_moments=True)
+    for mc in (1, 2, 3, 4, 5, 8):
+        f_ref, df_ref = st.acquisition("EI", Xc[:mc], with_gradients=True, native=True)
+        r = m.acquisition("EI", 0.01, fmin, Xc[:mc], with_gradients=True, want_moments=True)
+        assert_allclose(r["f"], f_ref, rtol=1e-7, atol=1e-12)
+        assert_allclose(r["df"], df_ref, rtol=1e-6, atol=1e-9 * np.abs(df_ref).max())
+        for key in ("f", "df", "m", "s", "dmdx", "dsdx"):
+            assert_allclose(r[key], f9[key][:mc], rtol=1e-9, atol=1e-12 * max(1.0, np.abs(f9[key]).max()))
+        mu, var = m.predict(Xc[:mc])
+        mu_r, var_r = O.predict(kind, st.post, X, Xc[:mc], 1.1, ls, 1e-3)
+        assert_allclose(mu, mu_r, rtol=1e-9, atol=1e-11)
+        assert_allclose(var, var_r, rtol=1e-9, atol=1e-12)
+    m.close()
