@@ -52,9 +52,11 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "gpb_model_acq_topk": (c_int, [c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_int, c_int,
                                    ctypes.c_longlong, c_double_p, c_ll_p, c_double_p]),
+    "gpb_set_overlap": (c_int, [c_int]),
     "gpb_profile_gemm": (c_int, [c_int]),
     "gpb_gemm_config": (c_int, [c_int]),
     "gpb_profile_gemm_collect": (c_int, [c_double_p, c_double_p, c_ll_p]),
+    "gpb_profile_gemm_last": (c_int, [c_double_p, c_double_p]),
     "gpb_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.c_double, c_void_p, c_int, c_void_p, c_int, ctypes.c_double,
                           c_void_p, c_int, c_void_p]),
 }

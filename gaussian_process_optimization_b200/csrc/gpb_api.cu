@@ -163,7 +163,10 @@ struct gpb_model {
   double *topv = nullptr;
   long long *topi = nullptr;
   double *pinned = nullptr;  // host, 256 doubles
+  FactorOverlap *ov = nullptr;  // streams / events of the two-stream factorisation schedule
 };
+
+static int g_overlap_min_n = 512;  // 0 disables the two-stream schedule (gpb_set_overlap)
 
 static size_t carve(int n_cap, int d, int p, int cb, gpb_model *m, char *base) {
   const size_t np = round_up(std::max(n_cap, 1), TILE);
@@ -279,6 +282,12 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
     set_error("model_create: cudaMallocHost failed");
     return -1;
   }
+  if (factor_overlap_create(&m->ov) != 0) {
+    if (m->own_ws) cudaFree(m->ws);
+    cudaFreeHost(m->pinned);
+    delete m;
+    return -1;
+  }
   *out = m;
   return 0;
 }
@@ -286,6 +295,7 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
 int gpb_model_destroy(gpb_model *m) {
   if (!m) return 0;
   cudaStreamSynchronize(m->stream);
+  factor_overlap_destroy(m->ov);
   if (m->own_ws && m->ws) cudaFree(m->ws);
   if (m->pinned) cudaFreeHost(m->pinned);
   delete m;
@@ -365,7 +375,23 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
   // Ky = K + (noise + 1e-8 [+ jitter]) I     exact_gaussian_inference.py:55-56
   GPB_TRY(launch_kmat(m->kind, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->noise + 1e-8 + extra_jitter, 1, m->f.A, np, np,
                       np, m->stream));
-  GPB_TRY(factor_potrf_inv(m->f));
+  // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
+  const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / 8) : 0;
+  if (m->ov && fork_min_n > 0 && np >= fork_min_n) {
+    // critical path on the model's high-priority stream, T21 products on its low-priority side streams (gpb_chol.cu)
+    Factor fo = m->f;
+    fo.stream = m->ov->main;
+    fo.ov = m->ov;
+    m->ov->min_n = fork_min_n;
+    GPB_CUDA(cudaEventRecord(m->ov->enter, m->stream));
+    GPB_CUDA(cudaStreamWaitEvent(m->ov->main, m->ov->enter, 0));
+    const int rc = factor_potrf_inv(fo);
+    GPB_CUDA(cudaEventRecord(m->ov->leave, m->ov->main));
+    GPB_CUDA(cudaStreamWaitEvent(m->stream, m->ov->leave, 0));
+    GPB_TRY(rc);
+  } else {
+    GPB_TRY(factor_potrf_inv(m->f));
+  }
   GPB_TRY(factor_solve(m->f, m->Yc, p, m->z, m->alpha));
   GPB_TRY(factor_logdet(m->f, m->scal + 0));
   dot_kernel<<<1, 1024, 0, m->stream>>>(m->alpha, m->Yc, p * np, m->scal + 1);
@@ -936,9 +962,14 @@ int gpb_potri(int n, const double *L, int ldl, double *Ai, int ldai, int dev, vo
   return 0;
 }
 
+int gpb_set_overlap(int min_n) {
+  g_overlap_min_n = min_n < 0 ? 0 : min_n;
+  return 0;
+}
 int gpb_profile_gemm(int enable) { return gemm_profile_enable(enable); }
 int gpb_gemm_config(int cfg) { return gemm_force_config(cfg); }
 int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches) { return gemm_profile_collect(ms, flops, launches); }
+int gpb_profile_gemm_last(double *ms, double *flops) { return gemm_profile_last(ms, flops); }
 
 int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb, double beta,
               double *C, int ldc, void *stream) {

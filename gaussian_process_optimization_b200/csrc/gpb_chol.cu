@@ -281,34 +281,83 @@ int launch_symmetrize_lower(double *A, int ld, int n, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------------------
 // potrf + triangular inverse (recursive)
 // ---------------------------------------------------------------------------------------------------------------------
-static int cholinv(Factor &f, int off, int n) {
+// Two-stream schedule (f.ov != nullptr): the product T21 = L21 M11 only needs L21 and M11, so it is issued on a low-priority
+// side stream (one per recursion depth) right after L21 exists and runs underneath the critical path
+//     A22 -= L21 L21^T  ->  cholinv(A22)
+// whose lower levels (leaves, 32x32-tile GEMMs) leave most of the 148 SMs idle; M21 = -M22 T21 joins the two streams.
+// f.stream must be a high-priority stream so that the small critical-path kernels get the next free SM slots while a long
+// side GEMM is resident.  Buffers: T21 overwrites the S21 scratch, therefore the SYRK reads the copy of L21 in A21.
+static int cholinv(Factor &f, int off, int n, int depth) {
   if (n == TILE) return launch_leaf(f, off, 0);
   const int ld = f.np;
   const int h = ((n / TILE) / 2) * TILE;  // first half (multiple of 128), second half n - h >= h
   const int r = n - h;
-  GPB_TRY(cholinv(f, off, h));
+  GPB_TRY(cholinv(f, off, h, depth + 1));
   double *A21 = f.A + (size_t)(off + h) * ld + off;
   double *A22 = f.A + (size_t)(off + h) * ld + off + h;
   double *M11 = f.Mi + (size_t)off * ld + off;
   double *M21 = f.Mi + (size_t)(off + h) * ld + off;
   double *M22 = f.Mi + (size_t)(off + h) * ld + off + h;
   double *S21 = f.W + (size_t)(off + h) * ld + off;  // scratch with the shape of the (2,1) block
+  const bool fork = f.ov != nullptr && depth < FactorOverlap::MAX_DEPTH && n >= f.ov->min_n;
   GemmArgs g;
   // S21 = A21 * M11^T      (M11 lower: k <= column tile)
   g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 0, 2};
   GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
   GPB_TRY(launch_copy2d(A21, ld, S21, ld, r, h, f.stream));  // A21 <- L21
+  cudaStream_t s5 = f.stream;
+  if (fork) {
+    s5 = f.ov->side[depth];
+    GPB_CUDA(cudaEventRecord(f.ov->fork[depth], f.stream));
+    GPB_CUDA(cudaStreamWaitEvent(s5, f.ov->fork[depth], 0));
+    // T21 = L21 * M11      (M11 lower: k >= column tile)   -- side stream, overwrites S21
+    g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 2, 0};
+    GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, s5));
+    GPB_CUDA(cudaEventRecord(f.ov->join[depth], s5));
+  }
   // A22 -= L21 * L21^T     (lower tiles)
-  g = GemmArgs{S21, ld, S21, ld, A22, ld, r, r, h, -1.0, 1.0, 1, 0, 0};
+  g = GemmArgs{A21, ld, A21, ld, A22, ld, r, r, h, -1.0, 1.0, 1, 0, 0};
   GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
-  GPB_TRY(cholinv(f, off + h, r));
-  // S21 = L21 * M11        (M11 lower: k >= column tile)
-  g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 2, 0};
-  GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, f.stream));
-  // M21 = -M22 * S21       (M22 lower: k <= row tile)
+  GPB_TRY(cholinv(f, off + h, r, depth + 1));
+  if (fork) {
+    GPB_CUDA(cudaStreamWaitEvent(f.stream, f.ov->join[depth], 0));
+  } else {
+    g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 2, 0};
+    GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, f.stream));
+  }
+  // M21 = -M22 * T21       (M22 lower: k <= row tile)
   g = GemmArgs{M22, ld, S21, ld, M21, ld, r, h, r, -1.0, 0.0, 0, 0, 1};
   GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, f.stream));
   return 0;
+}
+
+int factor_overlap_create(FactorOverlap **out) {
+  FactorOverlap *ov = new FactorOverlap();
+  int least = 0, greatest = 0;
+  GPB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  GPB_CUDA(cudaStreamCreateWithPriority(&ov->main, cudaStreamNonBlocking, greatest));
+  for (int d = 0; d < FactorOverlap::MAX_DEPTH; ++d) {
+    GPB_CUDA(cudaStreamCreateWithPriority(&ov->side[d], cudaStreamNonBlocking, least));
+    GPB_CUDA(cudaEventCreateWithFlags(&ov->fork[d], cudaEventDisableTiming));
+    GPB_CUDA(cudaEventCreateWithFlags(&ov->join[d], cudaEventDisableTiming));
+  }
+  GPB_CUDA(cudaEventCreateWithFlags(&ov->enter, cudaEventDisableTiming));
+  GPB_CUDA(cudaEventCreateWithFlags(&ov->leave, cudaEventDisableTiming));
+  *out = ov;
+  return 0;
+}
+
+void factor_overlap_destroy(FactorOverlap *ov) {
+  if (!ov) return;
+  for (int d = 0; d < FactorOverlap::MAX_DEPTH; ++d) {
+    cudaStreamDestroy(ov->side[d]);
+    cudaEventDestroy(ov->fork[d]);
+    cudaEventDestroy(ov->join[d]);
+  }
+  cudaStreamDestroy(ov->main);
+  cudaEventDestroy(ov->enter);
+  cudaEventDestroy(ov->leave);
+  delete ov;
 }
 
 // M = L^-1 for a lower-triangular factor already stored in f.A (dtrtri, linalg.py:217-227): the inverse half of cholinv.
@@ -340,7 +389,7 @@ int factor_trtri(Factor &f) {
 int factor_potrf_inv(Factor &f) {
   GPB_REQUIRE(f.np % TILE == 0 && f.np >= TILE, "factor: padded size must be a multiple of 128");
   GPB_CUDA(cudaMemsetAsync(f.info, 0, sizeof(int), f.stream));
-  return cholinv(f, 0, f.np);
+  return cholinv(f, 0, f.np, 0);
 }
 
 // Ky^-1 = M^T M: W[i][j] = sum_{k >= max(i,j)} M[k][i] M[k][j]; lower tiles only (diagonal tiles complete).

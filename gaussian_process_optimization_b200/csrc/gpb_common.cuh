@@ -118,6 +118,18 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
 // ---- factorisation state shared by the linalg drivers ----------------------------------------------------------------
 // All three matrices are Np x Np row-major with leading dimension Np (Np = round_up(N, TILE)); rows/cols >= N are the
 // identity so that padded problems factor to [L 0; 0 I].
+// Streams and events of the two-stream factorisation schedule (gpb_chol.cu: cholinv).
+struct FactorOverlap {
+  static constexpr int MAX_DEPTH = 10;
+  cudaStream_t main = 0;               // high priority: the critical path of a fit runs here
+  cudaStream_t side[MAX_DEPTH] = {};   // low priority, one per recursion depth
+  cudaEvent_t fork[MAX_DEPTH] = {}, join[MAX_DEPTH] = {};
+  cudaEvent_t enter = nullptr, leave = nullptr;  // hand-over between the caller's stream and `main`
+  int min_n = 512;                     // smallest block size whose T21 product is forked
+};
+int factor_overlap_create(FactorOverlap **out);
+void factor_overlap_destroy(FactorOverlap *ov);
+
 struct Factor {
   int n = 0;    // logical size
   int np = 0;   // padded size
@@ -127,6 +139,7 @@ struct Factor {
   int *info = nullptr;  // device int: 0 or (1 + index of first non-positive pivot)
   double *part = nullptr;  // scratch for GEMV partials: (np / TILE) * np doubles
   cudaStream_t stream = 0;
+  FactorOverlap *ov = nullptr;  // non-null: two-stream schedule (stream must then be ov->main)
 };
 
 // gemm engine (gpb_gemm.cu)
@@ -145,6 +158,7 @@ int gemm_launch(int layout_a, int layout_b, const GemmArgs &g, cudaStream_t s);
 int gemm_profile_enable(int on);
 int gemm_force_config(int cfg);  // 0 auto, 1 BIG (64x128), 2 MID (64x64), 3 SMALL (32x32)
 int gemm_profile_collect(double *ms, double *flops, long long *launches);
+int gemm_profile_last(double *ms, double *flops);
 
 // linalg drivers (gpb_chol.cu)
 int factor_potrf_inv(Factor &f);                 // A -> L, Mi = L^-1, *info

@@ -23,9 +23,7 @@
 
 namespace gpb {
 
-constexpr int BK = 16;
-constexpr int STAGES = 3;
-constexpr int LD_ROWK = BK + 4;  // operand stored [row][k]  (k contiguous)
+constexpr int BK_MIN = 16;  // every k-range is a multiple of this (and of every BK used below)
 
 __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gmem_src) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -45,15 +43,17 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 
 // Stage one ROWS(row) x 16(k) operand tile.  base points at element (row0, 0) [ROWK] or (0, row0) [COLK] of the operand,
 // kk is the k offset of this tile.
-template <int LAYOUT, int ROWS, int THREADS>
+template <int LAYOUT, int ROWS, int THREADS, int BK>
 __device__ __forceinline__ void load_tile(double *s, const double *__restrict__ base, int ld, int kk, int tid) {
   constexpr int CHUNKS = ROWS * BK / 2;  // 16-byte chunks
+  constexpr int LD_ROWK = BK + 4;        // operand stored [row][k]  (k contiguous)
   static_assert(CHUNKS % THREADS == 0, "tile/threads mismatch");
   if (LAYOUT == LAYOUT_ROWK) {
+    constexpr int CPR = BK / 2;  // chunks per row
 #pragma unroll
     for (int i = 0; i < CHUNKS / THREADS; ++i) {
       const int chunk = tid + i * THREADS;
-      const int row = chunk >> 3, c = chunk & 7;
+      const int row = chunk / CPR, c = chunk % CPR;
       cp_async16(s + row * LD_ROWK + 2 * c, base + (size_t)row * ld + kk + 2 * c);
     }
   } else {
@@ -67,23 +67,23 @@ __device__ __forceinline__ void load_tile(double *s, const double *__restrict__ 
   }
 }
 
-template <int LAYOUT, int ROWS>
+template <int LAYOUT, int ROWS, int BK>
 __device__ __forceinline__ double frag(const double *s, int row, int k) {
-  return (LAYOUT == LAYOUT_ROWK) ? s[row * LD_ROWK + k] : s[k * (ROWS + 4) + row];
+  return (LAYOUT == LAYOUT_ROWK) ? s[row * (BK + 4) + k] : s[k * (ROWS + 4) + row];
 }
 
-template <int LAYOUT, int ROWS>
+template <int LAYOUT, int ROWS, int BK>
 __host__ __device__ constexpr int tile_doubles() {
-  return (LAYOUT == LAYOUT_ROWK) ? ROWS * LD_ROWK : BK * (ROWS + 4);
+  return (LAYOUT == LAYOUT_ROWK) ? ROWS * (BK + 4) : BK * (ROWS + 4);
 }
 
-template <int LA, int LB, int BM, int BN, int WARPS_M, int WARPS_N, int MIN_BLOCKS>
+template <int LA, int LB, int BM, int BN, int WARPS_M, int WARPS_N, int MIN_BLOCKS, int BK, int STAGES>
 __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_kernel(GemmArgs p) {
   constexpr int THREADS = WARPS_M * WARPS_N * 32;
   constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;  // warp tile
   constexpr int MI = WTM / 8, NI = WTN / 8;
-  constexpr int A_TILE = tile_doubles<LA, BM>();
-  constexpr int B_TILE = tile_doubles<LB, BN>();
+  constexpr int A_TILE = tile_doubles<LA, BM, BK>();
+  constexpr int B_TILE = tile_doubles<LB, BN, BK>();
   extern __shared__ __align__(16) double smem[];
   double *sA = smem;
   double *sB = smem + STAGES * A_TILE;
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_k
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) {
-      load_tile<LA, BM, THREADS>(sA + s * A_TILE, Abase, p.lda, klo + s * BK, tid);
-      load_tile<LB, BN, THREADS>(sB + s * B_TILE, Bbase, p.ldb, klo + s * BK, tid);
+      load_tile<LA, BM, THREADS, BK>(sA + s * A_TILE, Abase, p.lda, klo + s * BK, tid);
+      load_tile<LB, BN, THREADS, BK>(sB + s * B_TILE, Bbase, p.ldb, klo + s * BK, tid);
     }
     cp_async_commit();
   }
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_k
       const int nt = kt + STAGES - 1;
       if (nt < ktiles) {
         const int s = nt % STAGES;
-        load_tile<LA, BM, THREADS>(sA + s * A_TILE, Abase, p.lda, klo + nt * BK, tid);
-        load_tile<LB, BN, THREADS>(sB + s * B_TILE, Bbase, p.ldb, klo + nt * BK, tid);
+        load_tile<LA, BM, THREADS, BK>(sA + s * A_TILE, Abase, p.lda, klo + nt * BK, tid);
+        load_tile<LB, BN, THREADS, BK>(sB + s * B_TILE, Bbase, p.ldb, klo + nt * BK, tid);
       }
       cp_async_commit();
     }
@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_k
       const int k0 = ks * 4 + tq;
       double a[MI], b[NI];
 #pragma unroll
-      for (int i = 0; i < MI; ++i) a[i] = frag<LA, BM>(a_s, wm + i * 8 + g, k0);
+      for (int i = 0; i < MI; ++i) a[i] = frag<LA, BM, BK>(a_s, wm + i * 8 + g, k0);
 #pragma unroll
-      for (int j = 0; j < NI; ++j) b[j] = frag<LB, BN>(b_s, wn + j * 8 + g, k0);
+      for (int j = 0; j < NI; ++j) b[j] = frag<LB, BN, BK>(b_s, wn + j * 8 + g, k0);
 #pragma unroll
       for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -246,6 +246,23 @@ int gemm_profile_collect(double *ms, double *flops, long long *launches) {
   return 0;
 }
 
+// -> milliseconds and executed flops of the LAST GEMM launch recorded since enable / collect (in an NLL+grad evaluation that
+// is Ky^-1 = M^T M, the largest single launch); call before gemm_profile_collect.
+static double g_last_flops = 0.0;
+int gemm_profile_last(double *ms, double *flops) {
+  if (g_prof.used < 2) {
+    if (ms) *ms = 0.0;
+    if (flops) *flops = 0.0;
+    return 0;
+  }
+  GPB_CUDA(cudaEventSynchronize(g_prof.ev[g_prof.used - 1]));
+  float t = 0.f;
+  GPB_CUDA(cudaEventElapsedTime(&t, g_prof.ev[g_prof.used - 2], g_prof.ev[g_prof.used - 1]));
+  if (ms) *ms = t;
+  if (flops) *flops = g_last_flops;
+  return 0;
+}
+
 static int prof_event(cudaStream_t s) {
   if (g_prof.used == g_prof.ev.size()) {
     cudaEvent_t e;
@@ -273,15 +290,15 @@ static double block_flops(const GemmArgs &g) {
   return 2.0 * 128 * 128 * k_sum;
 }
 
-template <int LA, int LB, int BM, int BN, int WARPS_M, int WARPS_N, int MIN_BLOCKS>
+template <int LA, int LB, int BM, int BN, int WARPS_M, int WARPS_N, int MIN_BLOCKS, int BK, int STAGES>
 static int launch_t(const GemmArgs &g, cudaStream_t s) {
-  constexpr int A_TILE = tile_doubles<LA, BM>();
-  constexpr int B_TILE = tile_doubles<LB, BN>();
+  constexpr int A_TILE = tile_doubles<LA, BM, BK>();
+  constexpr int B_TILE = tile_doubles<LB, BN, BK>();
   constexpr int THREADS = WARPS_M * WARPS_N * 32;
   const size_t smem = (size_t)STAGES * (A_TILE + B_TILE) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    GPB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS>,
+    GPB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS, BK, STAGES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
@@ -290,12 +307,13 @@ static int launch_t(const GemmArgs &g, cudaStream_t s) {
   const int tiles = blocks128 * (128 / BM) * (128 / BN);
   if (tiles == 0) return 0;
   if (g_prof.on) GPB_TRY(prof_event(s));
-  gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS><<<tiles, THREADS, smem, s>>>(g);
+  gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS, BK, STAGES><<<tiles, THREADS, smem, s>>>(g);
   count_launch();
   GPB_CHECK_LAUNCH();
   if (g_prof.on) {
     GPB_TRY(prof_event(s));
-    g_prof.flops += block_flops(g);
+    g_last_flops = block_flops(g);
+    g_prof.flops += g_last_flops;
     g_prof.launches += 1;
   }
   return 0;
@@ -307,13 +325,18 @@ static int launch_cfg(const GemmArgs &g, cudaStream_t s) {
   const int blocks128 = g.tri_out ? b128m * (b128m + 1) / 2 : b128m * b128n;
   int cfg = g_forced_config;
   if (cfg == 0) cfg = (blocks128 >= 148) ? 1 : (blocks128 >= 20) ? 2 : 3;
-  if (cfg == 1) return launch_t<LA, LB, 64, 128, 1, 4, 2>(g, s);
-  if (cfg == 2) return launch_t<LA, LB, 64, 64, 2, 2, 3>(g, s);
-  return launch_t<LA, LB, 32, 32, 2, 2, 4>(g, s);
+  // both operands k-contiguous: BK = 32 with two stages halves the per-k-tile barriers (+1.8% at 8192^3); the strided
+  // layouts are faster with BK = 16 and three stages (scripts/gemm_sweep.py)
+  if (cfg == 1 && LA == LAYOUT_ROWK && LB == LAYOUT_ROWK && g.K % 32 == 0 && g_forced_config == 0)
+    return launch_t<LA, LB, 64, 128, 1, 4, 2, 32, 2>(g, s);
+  if (cfg == 1) return launch_t<LA, LB, 64, 128, 1, 4, 2, 16, 3>(g, s);
+  if (cfg == 2) return launch_t<LA, LB, 64, 64, 2, 2, 3, 16, 3>(g, s);
+  if (cfg == 4 && g.K % 32 == 0) return launch_t<LA, LB, 64, 128, 1, 4, 2, 32, 2>(g, s);   // 64x128, BK = 32, two stages
+  return launch_t<LA, LB, 32, 32, 2, 2, 4, 16, 3>(g, s);
 }
 
 int gemm_launch(int la, int lb, const GemmArgs &g, cudaStream_t s) {
-  GPB_REQUIRE(g.M % 128 == 0 && g.N % 128 == 0 && g.K % BK == 0, "gemm: M,N must be multiples of 128 and K of 16 (got %d %d %d)",
+  GPB_REQUIRE(g.M % 128 == 0 && g.N % 128 == 0 && g.K % BK_MIN == 0, "gemm: M,N must be multiples of 128 and K of 16 (got %d %d %d)",
               g.M, g.N, g.K);
   GPB_REQUIRE((g.lda % 2) == 0 && (g.ldb % 2) == 0 && (g.ldc % 2) == 0, "gemm: leading dimensions must be even");
   GPB_REQUIRE(!g.tri_out || g.M == g.N, "gemm: tri_out needs a square output");

@@ -126,6 +126,11 @@ def gemm_config(cfg):
     check(_lib.load().gpb_gemm_config(int(cfg)), "gemm_config")
 
 
+def set_overlap(min_n):
+    """Two-stream factorisation schedule: fork the T21 products of blocks with >= min_n rows (0 = single stream)."""
+    check(_lib.load().gpb_set_overlap(int(min_n)), "set_overlap")
+
+
 def profile_gemm(enable):
     check(_lib.load().gpb_profile_gemm(int(enable)), "profile_gemm")
 
@@ -135,6 +140,13 @@ def profile_gemm_collect():
     ms, fl, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_longlong(0)
     check(_lib.load().gpb_profile_gemm_collect(ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(n)), "profile_gemm_collect")
     return ms.value, fl.value, n.value
+
+
+def profile_gemm_last():
+    """-> (milliseconds, executed flops) of the last recorded GEMM launch (call before profile_gemm_collect)."""
+    ms, fl = ctypes.c_double(0), ctypes.c_double(0)
+    check(_lib.load().gpb_profile_gemm_last(ctypes.byref(ms), ctypes.byref(fl)), "profile_gemm_last")
+    return ms.value, fl.value
 
 
 def launch_count():

@@ -118,6 +118,10 @@ int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, c
 int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb,
               double beta, double *C, int ldc, void *stream);
 
+/* Two-stream factorisation schedule of gpb_model_fit: blocks of at least min_n rows fork their T21 = L21 M11 product onto a
+ * low-priority side stream underneath the critical path (default 512; 0 = single stream, used when timing kernels one by one). */
+int gpb_set_overlap(int min_n);
+
 /* Measurement hook for bench.py's roofline leg: when enabled, every DMMA GEMM launch is bracketed by CUDA events on its
  * stream.  collect() waits for them and returns the summed kernel time (ms), the executed tile flops and the launch count
  * since the last collect. */
@@ -125,6 +129,8 @@ int gpb_profile_gemm(int enable);
 /* Tuning/testing knob: force the GEMM tile configuration (0 auto, 1 = 64x128, 2 = 64x64, 3 = 32x32 CTA tiles). */
 int gpb_gemm_config(int cfg);
 int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches);
+/* Duration (ms) and executed flops of the last recorded GEMM launch (call before collect). */
+int gpb_profile_gemm_last(double *ms, double *flops);
 
 #ifdef __cplusplus
 }
