@@ -1,0 +1,137 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle needs minutes at N = 16384).
+
+Headline configuration: N = 16384, D = 16, synthetic data of SURVEY.md 8(d).  Checked on the device (cuBLAS fp64 products
+via torch are the independent reference for the residuals):
+  factorisation   L L^T = Ky,  M L = I,  Ky^-1 Ky = I,  Ky alpha = Y,  log-likelihood recomputed from L and alpha
+  gradients       central finite differences of the log-likelihood in every parameter class (variance, lengthscale, noise)
+  prediction      at training inputs  mu = Y - s alpha  and  var = s - s^2 (Ky^-1)_ii  with s = noise + 1e-8 (closed forms)
+  acquisition     top-k == stable argsort of the scores; sharded ranges merged == unsharded; bitwise repeatability
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+pytestmark = pytest.mark.gpu
+
+native = pytest.importorskip("gaussian_process_optimization_b200.native")
+from gaussian_process_optimization_b200 import sharded  # noqa: E402
+
+N, D = 16384, 16
+
+
+def _synth(n, d, seed=1234):
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(0, 1, (n, d))
+    w = rs.randn(d)
+    Y = np.sin(X @ w)[:, None] + 0.05 * rs.randn(n, 1)
+    Y = (Y - Y.mean()) / Y.std()
+    return X, Y, 0.5 + 0.5 * np.arange(d) / d
+
+
+@pytest.fixture(scope="module")
+def fitted():
+    import torch
+    X, Y, ls = _synth(N, D)
+    m = native.NativeModel("mat52", True, D, 1, n_cap=N, cand_block=2048)
+    m.set_data(X, Y)
+    theta = (1.3, ls, 1e-2)
+    m.set_theta(*theta)
+    info, logL, g = m.fit(True)
+    assert info == 0
+    yield m, X, Y, theta, logL, g, torch
+    m.close()
+
+
+def test_factorisation_residuals(fitted):
+    m, X, Y, (v, ls, noise), logL, g, torch = fitted
+    dev = torch.device("cuda")
+    new = lambda: torch.empty((N, N), dtype=torch.float64, device=dev)  # noqa: E731
+    K = m.get("K", out=new())
+    Ky = K + (noise + 1e-8) * torch.eye(N, dtype=torch.float64, device=dev)
+    del K
+    L = m.get("L", out=new())
+    R = L @ L.T
+    R -= Ky
+    assert float(R.abs().max()) <= 1e-12 * float(Ky.abs().max()) * N ** 0.5
+    Li = m.get("Li", out=R)
+    P = Li @ L
+    P -= torch.eye(N, dtype=torch.float64, device=dev)
+    assert float(P.abs().max()) <= 1e-9
+    del P, Li, R
+    Wi = m.get("Wi", out=new())
+    assert float((Wi - Wi.T).abs().max()) == 0.0          # symmetrified like linalg.py:144
+    Q = Wi @ Ky
+    Q -= torch.eye(N, dtype=torch.float64, device=dev)
+    assert float(Q.abs().max()) <= 1e-8
+    del Q
+    alpha = torch.from_numpy(m.get("alpha")).to(dev)
+    Yd = torch.from_numpy(Y).to(dev)
+    assert float((Ky @ alpha - Yd).abs().max()) <= 1e-9
+    logdet = 2.0 * float(torch.log(torch.diagonal(L)).sum())
+    ll = 0.5 * (-N * np.log(2 * np.pi) - logdet - float((alpha * Yd).sum()))
+    assert_allclose(logL, ll, rtol=1e-12)
+    # dL/dnoise = tr(dL_dK) = 0.5 (alpha^T alpha - tr(Ky^-1))      exact_gaussian_inference.py:70-72
+    assert_allclose(g[-1], 0.5 * (float((alpha * alpha).sum()) - float(torch.diagonal(Wi).sum())), rtol=1e-10)
+    # closed forms at the training inputs
+    s = noise + 1e-8
+    idx = np.arange(0, N, 37)[:300]
+    mu, var = m.predict(X[idx], include_likelihood=False)
+    a_np = alpha.cpu().numpy()
+    assert_allclose(mu, Y[idx] - s * a_np[idx], rtol=1e-9, atol=1e-10)
+    wii = torch.diagonal(Wi).cpu().numpy()[idx]
+    assert_allclose(var.ravel(), s - s * s * wii, rtol=1e-6, atol=1e-11)
+
+
+def test_gradients_against_finite_differences(fitted):
+    m, X, Y, (v, ls, noise), logL, g, torch = fitted
+
+    def ll(v_, ls_, nz_):
+        m.set_theta(v_, ls_, nz_)
+        info, val, _ = m.fit(False)
+        assert info == 0
+        return val
+
+    h = 1e-5
+    fd_v = (ll(v * (1 + h), ls, noise) - ll(v * (1 - h), ls, noise)) / (2 * v * h)
+    assert_allclose(g[0], fd_v, rtol=1e-5, atol=1e-4)
+    fd_n = (ll(v, ls, noise * (1 + h)) - ll(v, ls, noise * (1 - h))) / (2 * noise * h)
+    assert_allclose(g[-1], fd_n, rtol=1e-5, atol=1e-4)
+    for q in (0, D - 1):
+        lp, lm = ls.copy(), ls.copy()
+        lp[q] *= 1 + h
+        lm[q] *= 1 - h
+        fd_l = (ll(v, lp, noise) - ll(v, lm, noise)) / (2 * ls[q] * h)
+        assert_allclose(g[1 + q], fd_l, rtol=1e-5, atol=1e-4)
+    # restore the fitted state for the tests below and check bitwise repeatability of the whole evaluation
+    m.set_theta(v, ls, noise)
+    info, logL2, g2 = m.fit(True)
+    assert info == 0 and logL2 == logL and np.array_equal(g, g2)
+
+
+def test_acquisition_topk_properties(fitted):
+    m, X, Y, theta, logL, g, torch = fitted
+    fmin = m.fmin()
+    assert_allclose(fmin, (Y - (theta[2] + 1e-8) * m.get("alpha")).min(), rtol=1e-9)     # min of the closed-form mean
+    Xc = np.random.RandomState(4321).uniform(0, 1, (2 ** 14, D))
+    f = m.acquisition("EI", 0.01, fmin, Xc)["f"].ravel()
+    assert np.all(f <= 0.0) and np.all(np.isfinite(f))
+    vals, idx, pts = m.acq_topk("EI", 0.01, fmin, Xc, 5)
+    order = np.argsort(f, kind="stable")[:5]
+    assert np.array_equal(idx, order) and np.array_equal(vals, f[order]) and np.array_equal(pts, Xc[order])
+    # sharding the candidate set and merging the per-shard top-5 gives the same anchors (world sizes 2, 4, 8)
+    for world in (2, 4, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = sharded.divide_candidates(Xc.shape[0], r, world)
+            parts.append(m.acq_topk("EI", 0.01, fmin, Xc[lo:hi], 5, index_offset=lo))
+        mv, mi, mp = sharded.merge_topk(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]),
+                                        np.concatenate([p[2] for p in parts]), 5)
+        assert np.array_equal(mi, order) and np.array_equal(mv, f[order]) and np.array_equal(mp, Xc[order])
+    # value + gradient pass returns the same values as the value-only pass, and the gradient matches a finite difference
+    r = m.acquisition("EI", 0.01, fmin, Xc[:64], with_gradients=True)
+    assert_allclose(r["f"].ravel(), f[:64], rtol=1e-12, atol=1e-300)
+    c = int(np.argmin(f[:64]))
+    e = np.zeros(D)
+    e[3] = 1e-6
+    fd = (m.acquisition("EI", 0.01, fmin, (Xc[c] + e)[None])["f"][0, 0] - m.acquisition("EI", 0.01, fmin, (Xc[c] - e)[None])["f"][0, 0]) / 2e-6
+    assert_allclose(r["df"][c, 3], fd, rtol=1e-4, atol=1e-9)
