@@ -38,11 +38,13 @@ GPy = _NS(
 GPyOpt = _NS(
     methods=_NS(BayesianOptimization=_g.BayesianOptimization),
     models=_NS(GPModel=_g.GPModel, BOModel=_g.BOModel, base=_NS(BOModel=_g.BOModel), gpmodel=_NS(GPModel=_g.GPModel)),
-    acquisitions=_NS(AcquisitionBase=_g.AcquisitionBase, AcquisitionEI=_g.AcquisitionEI, AcquisitionLCB=_g.AcquisitionLCB),
+    acquisitions=_NS(AcquisitionBase=_g.AcquisitionBase, AcquisitionEI=_g.AcquisitionEI, AcquisitionLCB=_g.AcquisitionLCB,
+                     AcquisitionLP=_g.AcquisitionLP),
     optimization=_NS(AcquisitionOptimizer=_g.AcquisitionOptimizer, OptLbfgs=_g.OptLbfgs, apply_optimizer=_g.apply_optimizer,
                      ObjectiveAnchorPointsGenerator=_g.ObjectiveAnchorPointsGenerator,
                      ShardedAnchorScorer=_s.ShardedAnchorScorer),
-    core=_NS(BO=_g.BO, evaluators=_NS(Sequential=_g.Sequential),
+    core=_NS(BO=_g.BO, evaluators=_NS(Sequential=_g.Sequential, LocalPenalization=_g.LocalPenalization,
+                                      batch_local_penalization=_NS(LocalPenalization=_g.LocalPenalization, estimate_L=_g.estimate_L)),
              task=_NS(space=_NS(Design_space=_g.Design_space, bounds_to_space=_g.bounds_to_space),
                       objective=_NS(SingleObjective=_g.SingleObjective), SingleObjective=_g.SingleObjective),
              errors=_NS(InvalidConfigError=_g.InvalidConfigError)),

@@ -50,6 +50,9 @@ SIGNATURES = {
     "gpb_model_fmin": (c_int, [c_void_p, c_double_p]),
     "gpb_model_acquisition": (c_int, [c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
+    "gpb_model_set_penalizers": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gpb_model_acquisition_lp": (c_int, [c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_int]),
     "gpb_model_acq_topk": (c_int, [c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_int, c_int,
                                    ctypes.c_longlong, c_double_p, c_ll_p, c_double_p]),
     "gpb_set_overlap": (c_int, [c_int]),

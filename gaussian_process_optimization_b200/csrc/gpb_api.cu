@@ -164,6 +164,9 @@ struct gpb_model {
   long long *topi = nullptr;
   double *pinned = nullptr;  // host, 256 doubles
   FactorOverlap *ov = nullptr;  // streams / events of the two-stream factorisation schedule
+  // local-penalisation state (AcquisitionLP.update_batches): batch points and hammer-function parameters on the device
+  double *lp_buf = nullptr;     // [Xb (nb x d) | r (nb) | s (nb)], own allocation of lp_cap rows
+  int lp_cap = 0, lp_nb = 0, lp_transform = 0;
 };
 
 static int g_overlap_min_n = 512;  // 0 disables the two-stream schedule (gpb_set_overlap)
@@ -296,6 +299,7 @@ int gpb_model_destroy(gpb_model *m) {
   if (!m) return 0;
   cudaStreamSynchronize(m->stream);
   factor_overlap_destroy(m->ov);
+  if (m->lp_buf) cudaFree(m->lp_buf);
   if (m->own_ws && m->ws) cudaFree(m->ws);
   if (m->pinned) cudaFreeHost(m->pinned);
   delete m;
@@ -475,7 +479,7 @@ int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) 
 }
 
 // ---- predictive pipeline over one candidate block -------------------------------------------------------------------
-// level 0: mean only; 1: + variance; 2: + gradients (dmu, dvar)
+// level 0: mean only; 1: + variance; 2: + gradients (dmu, dvar); 3: mean and its gradient only (estimate_L)
 static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int level, int include_likelihood) {
   const int n = m->n, np = m->np, d = m->d, p = m->p;
   const int cpad = round_up(mcb, TILE);
@@ -489,6 +493,12 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   // A handful of candidates (the M = 1 calls of the L-BFGS-B refinement, optimizer.py:46-51): one bandwidth-bound pass over
   // the triangle of M per product instead of a 128-row padded GEMM.
   const bool skinny = mcb <= 8;
+  if (level == 3) {
+    GPB_REQUIRE(p == 1, "predictive gradients are implemented for a single output column (got %d)", p);
+    GPB_TRY(launch_gradx(m->kind, m->XcT, cpad, mcb, m->XsT, np, n, d, m->variance, m->inv_ls_dev, m->alpha, 0, 1.0, 0, nullptr, 0,
+                         0.0, m->dmu, nullptr, d, s));
+    return 0;
+  }
   if (level >= 1 && skinny) {
     const int c = mcb <= 1 ? 1 : mcb <= 2 ? 2 : mcb <= 4 ? 4 : 8;   // rows mcb .. c of KxT are zero (mode 2 padding)
     GPB_TRY(factor_skinny_products(m->f, c, m->KxT, np, m->Vt, np, level >= 2 ? m->Ut : nullptr, np, m->f.part));
@@ -561,7 +571,7 @@ int gpb_model_predictive_gradients(gpb_model *m, int mc, const double *Xc, doubl
   GPB_REQUIRE(m->fitted, "predictive_gradients: model has not been fitted");
   for (int c0 = 0; c0 < mc; c0 += m->cb) {
     const int mcb = std::min(m->cb, mc - c0);
-    GPB_TRY(predict_block(m, Xc + (size_t)c0 * m->d, mcb, dev, 2, 0));
+    GPB_TRY(predict_block(m, Xc + (size_t)c0 * m->d, mcb, dev, dvar ? 2 : 3, 0));
     GPB_TRY(copy_out(dmu ? dmu + (size_t)c0 * m->d : nullptr, m->dmu, (size_t)mcb * m->d, dev, m->stream));
     GPB_TRY(copy_out(dvar ? dvar + (size_t)c0 * m->d : nullptr, m->dvar, (size_t)mcb * m->d, dev, m->stream));
     if (!dev) GPB_CUDA(cudaStreamSynchronize(m->stream));
@@ -609,6 +619,52 @@ int gpb_model_acquisition(gpb_model *m, int acq, double par, double fmin, int mc
       GPB_TRY(copy_out(dmdx ? dmdx + (size_t)c0 * d : nullptr, m->dmu, (size_t)mcb * d, dev, m->stream));
       GPB_TRY(copy_out(dsdx ? dsdx + (size_t)c0 * d : nullptr, m->dsbuf, (size_t)mcb * d, dev, m->stream));
     }
+    if (!dev) GPB_CUDA(cudaStreamSynchronize(m->stream));
+  }
+  GPB_CUDA(cudaStreamSynchronize(m->stream));
+  return 0;
+}
+
+int gpb_model_set_penalizers(gpb_model *m, int transform, int nb, const double *Xb, const double *r, const double *s) {
+  GPB_REQUIRE(m, "set_penalizers: NULL model");
+  GPB_REQUIRE(transform == 0 || transform == 1, "set_penalizers: transform must be 0 (none) or 1 (softplus)");
+  GPB_REQUIRE(nb >= 0 && (nb == 0 || (Xb && r && s)), "set_penalizers: bad arguments");
+  m->lp_transform = transform;
+  m->lp_nb = nb;
+  if (nb == 0) return 0;
+  const int d = m->d;
+  if (nb > m->lp_cap) {
+    if (m->lp_buf) GPB_CUDA(cudaFree(m->lp_buf));
+    m->lp_buf = nullptr;
+    m->lp_cap = std::max(64, 2 * nb);
+    GPB_CUDA(cudaMalloc(&m->lp_buf, (size_t)m->lp_cap * (d + 2) * sizeof(double)));
+  }
+  cudaStream_t st = m->stream;
+  GPB_CUDA(cudaMemcpyAsync(m->lp_buf, Xb, (size_t)nb * d * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPB_CUDA(cudaMemcpyAsync(m->lp_buf + (size_t)m->lp_cap * d, r, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPB_CUDA(cudaMemcpyAsync(m->lp_buf + (size_t)m->lp_cap * (d + 1), s, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+  GPB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df, int dev) {
+  GPB_REQUIRE(m && Xc && f, "acquisition_lp: NULL argument");
+  GPB_REQUIRE(m->fitted, "acquisition_lp: model has not been fitted");
+  GPB_REQUIRE(acq == GPB_ACQ_EI || acq == GPB_ACQ_LCB, "acquisition_lp: unknown type %d", acq);
+  GPB_REQUIRE(m->p == 1, "acquisition_lp: single output only");
+  const int d = m->d;
+  const bool grad = df != nullptr;
+  const double *Xb = m->lp_buf, *r = m->lp_buf + (size_t)m->lp_cap * d, *s = m->lp_buf + (size_t)m->lp_cap * (d + 1);
+  for (int c0 = 0; c0 < mc; c0 += m->cb) {
+    const int mcb = std::min(m->cb, mc - c0);
+    GPB_TRY(predict_block(m, Xc + (size_t)c0 * d, mcb, dev, grad ? 2 : 1, 1));
+    GPB_TRY(launch_acq_epilogue(acq, par, fmin, mcb, d, m->mu, m->var, grad ? m->dmu : nullptr, grad ? m->dvar : nullptr, m->fbuf,
+                                m->dfbuf, nullptr, nullptr, nullptr, nullptr, m->stream));
+    // fbuf / dfbuf hold -acq / -dacq; the LP epilogue rewrites them in place-compatible buffers (sdbuf, dsbuf are free here)
+    GPB_TRY(launch_lp_epilogue(mcb, d, m->lp_nb, m->Xc, Xb, r, s, m->lp_transform, m->fbuf, grad ? m->dfbuf : nullptr, m->sdbuf,
+                               grad ? m->dsbuf : nullptr, m->stream));
+    GPB_TRY(copy_out(f + c0, m->sdbuf, mcb, dev, m->stream));
+    if (grad) GPB_TRY(copy_out(df + (size_t)c0 * d, m->dsbuf, (size_t)mcb * d, dev, m->stream));
     if (!dev) GPB_CUDA(cudaStreamSynchronize(m->stream));
   }
   GPB_CUDA(cudaStreamSynchronize(m->stream));

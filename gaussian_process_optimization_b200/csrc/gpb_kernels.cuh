@@ -37,6 +37,9 @@ int launch_var_from_vt(const double *Vt, int ld, int n_c, int n, double base, do
 int launch_acq_epilogue(int acq, double par, double fmin, int n_c, int d, const double *mu, const double *var, const double *dmu,
                         const double *dvar, double *f, double *df, double *mean_out, double *sd_out, double *dmdx_out,
                         double *dsdx_out, cudaStream_t s);
+// AcquisitionLP (LP.py:70-132): log transform + hammer-function penalisers around nb batch points, value and gradient
+int launch_lp_epilogue(int n_c, int d, int nb, const double *Xc, const double *Xb, const double *r, const double *s, int transform,
+                       const double *F, const double *dF, double *f_out, double *df_out, cudaStream_t st);
 // running top-k of the k smallest f (ties -> lowest index); state on device: vals[k], idx[k]
 int launch_topk_init(double *vals, long long *idx, int k, cudaStream_t s);
 int launch_topk_update(const double *f, int n_c, long long index_base, double *vals, long long *idx, int k, cudaStream_t s);

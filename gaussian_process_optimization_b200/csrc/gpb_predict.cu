@@ -103,6 +103,66 @@ int launch_acq_epilogue(int acq, double par, double fmin, int n_c, int d, const 
   return 0;
 }
 
+// ---- local penalisation (GPyOpt/GPyOpt/acquisitions/LP.py) -------------------------------------------------------------
+// log Phi(z) without underflow: erfcx(x) = exp(x^2) erfc(x) keeps the left tail exact (scipy's norm.logcdf = log_ndtr).
+__device__ __forceinline__ double log_ndtr(double z) {
+  const double t = z * 0.70710678118654752440;
+  if (z < 0.0) return log(0.5 * erfcx(-t)) - t * t;
+  return log1p(-0.5 * erfc(t));
+}
+
+// One thread per candidate.  In: F = -acq and dF = -dacq as AcquisitionBase returns them (base.py:33-50).  Out:
+//   f  = -T(acq) - sum_b log Phi((|x - x_b| - r_b) / s_b)                       LP.py:70-89 (_penalized_acquisition)
+//   df = scale * dF - sum_b d_b   (d_b a scalar broadcast over the dimensions, exactly like LP.py:91-104,121-128)
+// with T = log(acq + 1e-50), scale = 1 / acq (transform 'none') or T = log softplus(acq), scale = 1 / (softplus(acq) (1 + e^-acq))
+// ('softplus', the default for LCB: LP.py:31-34).
+__global__ void lp_epilogue_kernel(int n_c, int d, int nb, const double *__restrict__ Xc, const double *__restrict__ Xb,
+                                   const double *__restrict__ r, const double *__restrict__ s, int transform,
+                                   const double *__restrict__ F, const double *__restrict__ dF, double *__restrict__ f_out,
+                                   double *__restrict__ df_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_c) return;
+  const double acqv = -F[c];
+  double t, scale;
+  if (transform == 1) {
+    const double sp = log1p(exp(acqv));
+    t = (acqv >= 40.0) ? log(acqv) : log(sp);
+    scale = 1.0 / (sp * (1.0 + exp(-acqv)));
+  } else {
+    t = log(acqv + 1e-50);
+    scale = 1.0 / acqv;
+  }
+  double hsum = 0.0, dsum = 0.0;
+  for (int b = 0; b < nb; ++b) {
+    double n2 = 0.0;
+    for (int q = 0; q < d; ++q) {
+      const double df = Xc[(size_t)c * d + q] - Xb[(size_t)b * d + q];
+      n2 = fma(df, df, n2);
+    }
+    const double nm = sqrt(n2);
+    const double z = (nm - r[b]) / s[b];
+    hsum += log_ndtr(z);
+    if (df_out) {
+      const double hf = 0.5 * erfc(-z * 0.70710678118654752440);
+      double dd = 1.0 / (s[b] * 2.50662827463100050242 * hf) * exp(-0.5 * z * z) / nm;
+      if (hf < 1e-50) dd = 0.0;
+      dsum += dd;
+    }
+  }
+  f_out[c] = -t - hsum;
+  if (df_out)
+    for (int q = 0; q < d; ++q) df_out[(size_t)c * d + q] = scale * dF[(size_t)c * d + q] - dsum;
+}
+
+int launch_lp_epilogue(int n_c, int d, int nb, const double *Xc, const double *Xb, const double *r, const double *s, int transform,
+                       const double *F, const double *dF, double *f_out, double *df_out, cudaStream_t st) {
+  if (n_c == 0) return 0;
+  lp_epilogue_kernel<<<(n_c + 127) / 128, 128, 0, st>>>(n_c, d, nb, Xc, Xb, r, s, transform, F, dF, f_out, df_out);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
 // ---- top-k (k smallest, lexicographic on (value, global index)) -----------------------------------------------------
 __device__ __forceinline__ bool lex_less(double av, long long ai, double bv, long long bi) {
   return (av < bv) || (av == bv && ai < bi);

@@ -11,6 +11,8 @@ Mirrors (paths relative to /root/reference/GPyOpt/GPyOpt):
   core/task/space.py, variables.py                        Design_space with continuous / discrete variables
   core/task/objective.py:24-76                            SingleObjective
   core/evaluators/sequential.py:7-23                      Sequential
+  acquisitions/LP.py:10-140                               AcquisitionLP (local penalisation)
+  core/evaluators/batch_local_penalization.py:9-70        LocalPenalization, estimate_L
   core/bo.py:20-260, methods/bayesian_optimization.py:76-202   BO, BayesianOptimization
 Host logic only (bookkeeping, RNG order, L-BFGS-B through SciPy like the reference); every GP quantity comes from the device.
 """
@@ -509,6 +511,140 @@ class AcquisitionLCB(AcquisitionBase):
         return -m + self.exploration_weight * s, -dmdx + self.exploration_weight * dsdx
 
 
+class AcquisitionLP(AcquisitionBase):
+    """acquisitions/LP.py:10-140: local-penalisation wrapper used by the batch evaluator.  The penalised acquisition lives in
+    log space: f(x) = -T(acq(x)) - sum_b log Phi((|x - x_b| - r_b) / s_b), T = log(. + 1e-50) or log softplus(.).
+
+    With the B200 GPModel and an EI / LCB base acquisition (constant cost, no constraints) value and gradient come from one
+    device pass (gpb_model_acquisition_lp); any other combination runs the reference's NumPy formulas on whatever the wrapped
+    acquisition returns."""
+    analytical_gradient_prediction = True
+
+    def __init__(self, model, space, optimizer, acquisition, transform='none'):
+        super(AcquisitionLP, self).__init__(model, space, optimizer)
+        self.acq = acquisition
+        self.transform = transform.lower()
+        if isinstance(acquisition, AcquisitionLCB) and self.transform == 'none':
+            self.transform = 'softplus'
+        self.X_batch = None
+        self.r_x0 = None
+        self.s_x0 = None
+        self._pushed_to = None
+
+    # -- device path -----------------------------------------------------------------------------------------------------
+    def _native_kind(self):
+        if not (isinstance(self.model, GPModel) and self.model.model is not None
+                and hasattr(self.model.model.posterior, "acquisition_lp")):
+            return None
+        if self.transform not in ('none', 'softplus') or self.space.has_constraints():
+            return None
+        if getattr(self.acq, "cost_withGradients", None) is not constant_cost_withGradients:
+            return None
+        if type(self.acq) is AcquisitionEI:
+            return "EI", self.acq.jitter
+        if type(self.acq) is AcquisitionLCB:
+            return "LCB", self.acq.exploration_weight
+        return None
+
+    def _push(self, post):
+        """Upload the batch points / hammer parameters when they or the resident model changed."""
+        key = (id(getattr(post, "_nat", post)), id(self.X_batch), self.transform)
+        if self._pushed_to != key:
+            post.set_penalizers(self.transform, self.X_batch, self.r_x0, self.s_x0)
+            self._pushed_to = key
+
+    def _native_call(self, x, with_gradients):
+        kind, par = self._native_kind()
+        post = self.model.model.posterior
+        self._push(post)
+        fmin = self.model.get_fmin() if kind == "EI" else 0.0
+        return post.acquisition_lp(kind, par, fmin, np.atleast_2d(x), with_gradients=with_gradients)
+
+    # -- reference logic -------------------------------------------------------------------------------------------------
+    def update_batches(self, X_batch, L, Min):
+        """LP.py:40-47."""
+        self.X_batch = X_batch
+        self._pushed_to = None
+        if X_batch is not None:
+            self.r_x0, self.s_x0 = self._hammer_function_precompute(X_batch, L, Min, self.model)
+
+    def _hammer_function_precompute(self, x0, L, Min, model):
+        """LP.py:49-62 (note: the reference takes the square root of the predicted standard deviation once more)."""
+        if x0 is None:
+            return None, None
+        if len(x0.shape) == 1:
+            x0 = x0[None, :]
+        m, sd = model.predict(x0)
+        pred = sd.copy()
+        pred[pred < 1e-16] = 1e-16
+        s = np.sqrt(pred)
+        r_x0 = (m - Min) / L
+        s_x0 = s / L
+        return r_x0.flatten(), s_x0.flatten()
+
+    def _hammer_function(self, x, x0, r_x0, s_x0):
+        """LP.py:64-68."""
+        from scipy.stats import norm
+        return norm.logcdf((np.sqrt((np.square(np.atleast_2d(x)[:, None, :] - np.atleast_2d(x0)[None, :, :])).sum(-1)) - r_x0) / s_x0)
+
+    def _penalized_acquisition(self, x, model, X_batch, r_x0, s_x0):
+        """LP.py:70-89."""
+        fval = -self.acq.acquisition_function(x)[:, 0]
+        if self.transform == 'softplus':
+            fval_org = fval.copy()
+            fval[fval_org >= 40.] = np.log(fval_org[fval_org >= 40.])
+            fval[fval_org < 40.] = np.log(np.log1p(np.exp(fval_org[fval_org < 40.])))
+        elif self.transform == 'none':
+            fval = np.log(fval + 1e-50)
+        fval = -fval
+        if X_batch is not None:
+            h_vals = self._hammer_function(x, X_batch, r_x0, s_x0)
+            fval += -h_vals.sum(axis=-1)
+        return fval
+
+    def _d_hammer_function(self, x, X_batch, r_x0, s_x0):
+        """LP.py:91-104 (the sum over the batch is returned as one scalar per point, broadcast over the dimensions)."""
+        from scipy.stats import norm
+        dx = np.atleast_2d(x)[:, None, :] - np.atleast_2d(X_batch)[None, :, :]
+        nm = np.sqrt((np.square(dx)).sum(-1))
+        z = (nm - r_x0) / s_x0
+        h_func = norm.cdf(z)
+        d = 1. / (s_x0 * np.sqrt(2 * np.pi) * h_func) * np.exp(-np.square(z) / 2) / nm
+        d[h_func < 1e-50] = 0.
+        d = d[:, :, None]
+        return d.sum(axis=1)
+
+    def acquisition_function(self, x):
+        """LP.py:106-111."""
+        if self._native_kind() is not None:
+            return self._native_call(x, False)
+        return self._penalized_acquisition(x, self.model, self.X_batch, self.r_x0, self.s_x0)
+
+    def d_acquisition_function(self, x):
+        """LP.py:113-132."""
+        if self._native_kind() is not None:
+            return self._native_call(x, True)[1]
+        x = np.atleast_2d(x)
+        if self.transform == 'softplus':
+            fval = -self.acq.acquisition_function(x)[:, 0]
+            scale = 1. / (np.log1p(np.exp(fval)) * (1. + np.exp(-fval)))
+        elif self.transform == 'none':
+            fval = -self.acq.acquisition_function(x)[:, 0]
+            scale = 1. / fval
+        else:
+            scale = 1.
+        _, grad_acq_x = self.acq.acquisition_function_withGradients(x)
+        if self.X_batch is None:
+            return scale * grad_acq_x
+        return scale * grad_acq_x - self._d_hammer_function(x, self.X_batch, self.r_x0, self.s_x0)
+
+    def acquisition_function_withGradients(self, x):
+        """LP.py:134-140."""
+        if self._native_kind() is not None:
+            return self._native_call(x, True)
+        return self.acquisition_function(x), self.d_acquisition_function(x)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # acquisition optimiser
 # ----------------------------------------------------------------------------------------------------------------------
@@ -603,6 +739,58 @@ class Sequential(object):
     def compute_batch(self, duplicate_manager=None, context_manager=None):
         x, _ = self.acquisition.optimize(duplicate_manager=duplicate_manager)
         return x
+
+
+def estimate_L(model, bounds, storehistory=True):
+    """core/evaluators/batch_local_penalization.py:50-70: Lipschitz constant = max over the domain of |d mu / dx|.
+    500 uniform samples (one np.random.uniform call per dimension, util/general.py:63-73) + the training inputs are scored
+    in one batched call, then bounded L-BFGS-B (maxiter 200, finite-difference gradient like the reference) from the best."""
+    import scipy.optimize
+
+    def df(x, model, x0):
+        x = np.atleast_2d(x)
+        try:
+            dmdx, _ = model.predictive_gradients(x, want_var=False)   # the reference computes and discards the variance part
+        except TypeError:
+            dmdx, _ = model.predictive_gradients(x)
+        res = np.sqrt((dmdx * dmdx).sum(1))
+        return -res
+
+    samples = samples_multidimensional_uniform(bounds, 500)
+    samples = np.vstack([samples, model.X])
+    pred_samples = df(samples, model, 0)
+    x0 = samples[np.argmin(pred_samples)]
+    res = scipy.optimize.minimize(lambda x, *a: float(df(x, *a)[0, 0]), x0, method='L-BFGS-B', bounds=bounds, args=(model, x0),
+                                  options={'maxiter': 200})
+    minusL = float(np.atleast_2d(res.fun)[0][0])
+    L = -minusL
+    if L < 1e-7:
+        L = 10  # to avoid problems in cases in which the model is flat
+    return L
+
+
+class LocalPenalization(object):
+    """core/evaluators/batch_local_penalization.py:9-48: batch = first point from the plain acquisition, the others from the
+    acquisition penalised around the points already in the batch."""
+
+    def __init__(self, acquisition, batch_size):
+        self.acquisition, self.batch_size = acquisition, batch_size
+
+    def compute_batch(self, duplicate_manager=None, context_manager=None):
+        assert isinstance(self.acquisition, AcquisitionLP)
+        self.acquisition.update_batches(None, None, None)
+        X_batch = self.acquisition.optimize()[0]
+        k = 1
+        if self.batch_size > 1:
+            L = estimate_L(self.acquisition.model.model, self.acquisition.space.get_bounds())
+            Min = self.acquisition.model.model.Y.min()
+        while k < self.batch_size:
+            self.acquisition.update_batches(X_batch, L, Min)
+            new_sample = self.acquisition.optimize()[0]
+            X_batch = np.vstack((X_batch, new_sample))
+            k += 1
+        self.acquisition.update_batches(None, None, None)
+        return X_batch
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -773,9 +961,18 @@ class BayesianOptimization(BO):
         raise Exception('Invalid acquisition selected.')
 
     def _evaluator_chooser(self):
+        """util/arguments_manager.py:17-38."""
         if self.batch_size == 1 or self.evaluator_type == 'sequential':
             return Sequential(self.acquisition)
-        raise NotImplementedError("batch evaluators are not provided yet (local penalisation is the next row of SURVEY 8f)")
+        if self.evaluator_type == 'local_penalization':
+            if self.model_type not in ['GP', 'User defined model used.']:
+                raise InvalidConfigError('local_penalization evaluator can only be used with GP models')
+            acq = self.acquisition
+            if not isinstance(acq, AcquisitionLP):
+                acq = AcquisitionLP(self.model, self.space, self.acquisition_optimizer, self.acquisition,
+                                    self.kwargs.get('acquisition_transformation', 'none'))
+            return LocalPenalization(acq, self.batch_size)
+        raise NotImplementedError("evaluator_type %r is outside the B200 hot path (random / Thompson batches)" % (self.evaluator_type,))
 
     def _init_design_chooser(self):
         if self.f is None and (self.X is None or self.Y is None):

@@ -136,9 +136,17 @@ class PosteriorExact(object):
         return self._nat.predict(Xnew, include_likelihood=False)
 
     # -- what GP / GPModel need beyond the reference's Posterior attributes: the fused device entry points -------------
-    def predictive_gradients(self, Xnew):
-        """core/gp.py:407-454 -> (dmu_dX (M, D, P), dv_dX (M, D))."""
-        return self._nat.predictive_gradients(np.asarray(Xnew, dtype=np.float64))
+    def predictive_gradients(self, Xnew, want_var=True):
+        """core/gp.py:407-454 -> (dmu_dX (M, D, P), dv_dX (M, D) or None)."""
+        return self._nat.predictive_gradients(np.asarray(Xnew, dtype=np.float64), want_var=want_var)
+
+    def set_penalizers(self, transform, Xb, r, s):
+        """AcquisitionLP.update_batches (LP.py:40-62): upload the batch points and hammer-function parameters."""
+        self._nat.set_penalizers(transform, Xb, r, s)
+
+    def acquisition_lp(self, acq, par, fmin, X, with_gradients=False):
+        """AcquisitionLP.acquisition_function(_withGradients) (LP.py:70-140) in one device pass."""
+        return self._nat.acquisition_lp(acq, par, fmin, X, with_gradients=with_gradients)
 
     def fmin(self):
         """min of the posterior mean over the training inputs (gpmodel.py:125-129)."""
@@ -318,9 +326,12 @@ class GP(Model):
     def predict_noiseless(self, Xnew, full_cov=False, Y_metadata=None, kern=None):
         return self.predict(Xnew, full_cov, Y_metadata, kern, None, False)
 
-    def predictive_gradients(self, Xnew, kern=None):
-        """core/gp.py:407-454 -> (dmu_dX (M, D, P), dv_dX (M, D))."""
-        return self.posterior.predictive_gradients(np.asarray(Xnew, dtype=np.float64))
+    def predictive_gradients(self, Xnew, kern=None, want_var=True):
+        """core/gp.py:407-454 -> (dmu_dX (M, D, P), dv_dX (M, D)).  want_var=False (not in the reference) skips the variance
+        gradient for callers that discard it (estimate_L, batch_local_penalization.py:56-58) and returns None in its place."""
+        if want_var:
+            return self.posterior.predictive_gradients(np.asarray(Xnew, dtype=np.float64))
+        return self.posterior.predictive_gradients(np.asarray(Xnew, dtype=np.float64), want_var=False)
 
     def posterior_covariance_between_points(self, X1, X2):
         """posterior.py:109-130 through one joint full-covariance prediction."""

@@ -245,11 +245,11 @@ class NativeModel(object):
               "predict_full_cov")
         return mu, cov
 
-    def predictive_gradients(self, Xc):
+    def predictive_gradients(self, Xc, want_var=True):
         Xc = as_host(Xc)
         mc = Xc.shape[0]
         dmu = np.empty((mc, self.d, 1))
-        dvar = np.empty((mc, self.d))
+        dvar = np.empty((mc, self.d)) if want_var else None
         check(self._lib.gpb_model_predictive_gradients(self._h, mc, ptr(Xc), ptr(dmu), ptr(dvar), 0), "predictive_gradients")
         return dmu, dvar
 
@@ -281,6 +281,26 @@ class NativeModel(object):
                                               ptr(r.get("m")), ptr(r.get("s")), ptr(r.get("dmdx")), ptr(r.get("dsdx")), int(dev)),
               "acquisition")
         return r
+
+    def set_penalizers(self, transform, Xb, r, s):
+        """AcquisitionLP.update_batches (LP.py:40-62); Xb None clears the penalisers (the log transform stays)."""
+        t = {"none": 0, "softplus": 1}[transform] if isinstance(transform, str) else int(transform)
+        if Xb is None:
+            check(self._lib.gpb_model_set_penalizers(self._h, t, 0, None, None, None), "set_penalizers")
+            return
+        Xb, r, s = as_host(Xb), as_host(r).ravel(), as_host(s).ravel()
+        assert Xb.shape == (r.size, self.d) and s.size == r.size
+        check(self._lib.gpb_model_set_penalizers(self._h, t, r.size, ptr(Xb), ptr(r), ptr(s)), "set_penalizers")
+
+    def acquisition_lp(self, acq, par, fmin, Xc, with_gradients=False):
+        """AcquisitionLP.acquisition_function(_withGradients) (LP.py:70-140) -> f (mc,) [, df (mc, d)]."""
+        Xc = as_host(Xc)
+        mc = Xc.shape[0]
+        f = np.empty(mc)
+        df = np.empty((mc, self.d)) if with_gradients else None
+        aid = acq if isinstance(acq, int) else ACQ_IDS[acq]
+        check(self._lib.gpb_model_acquisition_lp(self._h, aid, float(par), float(fmin), mc, ptr(Xc), ptr(f), ptr(df), 0), "acquisition_lp")
+        return (f, df) if with_gradients else f
 
     def acq_topk(self, acq, par, fmin, Xc, k, index_offset=0):
         dev = is_torch(Xc)

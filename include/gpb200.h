@@ -95,7 +95,8 @@ int gpb_model_predict(gpb_model *m, int mc, const double *Xc, int include_likeli
 /* GP.predict(full_cov=True): cov mc x mc (posterior.py:281-284). */
 int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *cov,
                                int dev);
-/* GP.predictive_gradients(Xnew) (core/gp.py:407-454): dmu mc x d x p, dvar mc x d. */
+/* GP.predictive_gradients(Xnew) (core/gp.py:407-454): dmu mc x d x p, dvar mc x d.  dvar = NULL skips the variance part
+ * (estimate_L only uses the mean gradient, GPyOpt/GPyOpt/core/evaluators/batch_local_penalization.py:56-58). */
 int gpb_model_predictive_gradients(gpb_model *m, int mc, const double *Xc, double *dmu, double *dvar, int dev);
 /* GPModel.get_fmin (GPyOpt/GPyOpt/models/gpmodel.py:125-129): min posterior mean over the training inputs (host out). */
 int gpb_model_fmin(gpb_model *m, double *fmin);
@@ -106,6 +107,13 @@ int gpb_model_fmin(gpb_model *m, double *fmin);
  * Outputs (any may be NULL): f mc, df mc x d, mean mc, sd mc (clipped at 1e-10 like gpmodel.py:99), dmdx mc x d, dsdx mc x d. */
 int gpb_model_acquisition(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df,
                           double *mean, double *sd, double *dmdx, double *dsdx, int dev);
+/* AcquisitionLP.update_batches (GPyOpt/GPyOpt/acquisitions/LP.py:40-62): nb batch points Xb (nb x d) with their hammer-function
+ * parameters r_x0, s_x0 (host arrays, copied to the device once); transform 0 = 'none', 1 = 'softplus'.  nb = 0 clears. */
+int gpb_model_set_penalizers(gpb_model *m, int transform, int nb, const double *Xb, const double *r, const double *s);
+/* AcquisitionLP.acquisition_function / acquisition_function_withGradients (LP.py:70-140): the log-transformed acquisition
+ * penalised by the hammer functions set above.  f: mc, df: mc x d or NULL. */
+int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df,
+                             int dev);
 /* Score mc candidates and return the k lowest f = -acq (anchor selection, anchor_points_generator.py:58-63, ties -> lowest
  * index).  idx are candidate indices + index_offset (global ids for a sharded candidate set).  vals/idx/pts are host. */
 int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,

@@ -90,6 +90,18 @@ def run_case(ns, name, kind, ard, N, D, M, noise, seed):
     out["lcb"] = np.array(lcb.acquisition_function(Xs))
     f, df = lcb.acquisition_function_withGradients(Xs)
     out["lcb_g_f"], out["lcb_g_df"] = np.array(f), np.array(df)
+    # (f) local penalisation (GPyOpt/acquisitions/LP.py): batch of 3 points, L and Min as LocalPenalization would pass them
+    Xb, L_lip, Min = Xs[:3].copy(), 2.5, float(Y.min())
+    out["lp_Xb"], out["lp_L"], out["lp_Min"] = Xb, L_lip, Min
+    for tag, base in (("ei", ei), ("lcb", lcb)):
+        lp = ns.AcquisitionLP(gm, sp, None, base)       # LCB switches itself to the softplus transform (LP.py:31-32)
+        lp.update_batches(Xb, L_lip, Min)
+        out["lp_%s_r" % tag], out["lp_%s_s" % tag] = np.array(lp.r_x0), np.array(lp.s_x0)
+        out["lp_%s_f" % tag] = np.array(lp.acquisition_function(Xs[3:]))
+        # the reference's gradient broadcasting only works for one point at a time (LP.py:129-132)
+        out["lp_%s_df" % tag] = np.vstack([lp.acquisition_function_withGradients(Xs[i:i + 1])[1] for i in range(3, Xs.shape[0])])
+        lp.update_batches(None, None, None)
+        out["lp_%s_f_nobatch" % tag] = np.array(lp.acquisition_function(Xs[3:]))
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     return out
 

@@ -12,7 +12,7 @@ GPy/__init__.py trips over NumPy-2 / Python-3.12 removals.  The *numerical* modu
   * and then import the reference's own source files for everything that does arithmetic:
       GPy/util/linalg.py, GPy/util/diag.py, GPy/kern/src/{kern,kernel_slice_operations,stationary,rbf}.py,
       GPy/inference/latent_function_inference/{exact_gaussian_inference,posterior}.py, GPy/likelihoods/gaussian.py,
-      GPy/core/gp.py, GPy/models/gp_regression.py, GPyOpt/util/general.py, GPyOpt/acquisitions/{base,EI,LCB}.py,
+      GPy/core/gp.py, GPy/models/gp_regression.py, GPyOpt/util/general.py, GPyOpt/acquisitions/{base,EI,LCB,LP}.py,
       GPyOpt/models/gpmodel.py.
 The Cython stand-ins call the reference's own C file (GPy/GPy/kern/src/stationary_utils.c) compiled into
 oracle/_ref/libstationary_utils_ref.so by oracle/Makefile, or restate the 10-line .pyx loops in NumPy.
@@ -303,6 +303,12 @@ def load():
     ns.acq_base = importlib.import_module("GPyOpt.acquisitions.base")
     ns.EI = importlib.import_module("GPyOpt.acquisitions.EI")
     ns.LCB = importlib.import_module("GPyOpt.acquisitions.LCB")
+
+    class AcquisitionLCB_MCMC(ns.LCB.AcquisitionLCB):   # only referenced in an isinstance test of LP.py:33
+        pass
+    _mod("GPyOpt.acquisitions.LCB_mcmc", AcquisitionLCB_MCMC=AcquisitionLCB_MCMC)
+    ns.LP = importlib.import_module("GPyOpt.acquisitions.LP")
+    ns.AcquisitionLP = ns.LP.AcquisitionLP
 
     ns.RBF = ns.rbf.RBF
     ns.Matern52 = ns.stationary.Matern52

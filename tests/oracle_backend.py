@@ -30,7 +30,7 @@ class OraclePosterior(object):
         return O.raw_predict(self.kind, self.post, self.X, np.asarray(Xnew, dtype=np.float64), self.variance, self.lengthscale,
                              self.ard, full_cov)
 
-    def predictive_gradients(self, Xnew):
+    def predictive_gradients(self, Xnew, want_var=True):
         return O.predictive_gradients(self.kind, self.post, self.X, Xnew, self.variance, self.lengthscale, self.ard)
 
     def fmin(self):

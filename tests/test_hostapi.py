@@ -191,6 +191,25 @@ def test_public_classes_golden(backend, golden):
     assert_allclose(lcb.acquisition_function(g["Xs"]), g["lcb"], rtol=1e-9 * ct, atol=1e-11 * ct)
     f, df = lcb.acquisition_function_withGradients(g["Xs"])
     assert_allclose(df, g["lcb_g_df"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["lcb_g_df"]).max())
+    # local penalisation around a batch of three points (acquisitions/LP.py), reference vectors from the reference's own LP.py
+    for tag, base in (("ei", ei), ("lcb", lcb)):
+        lp = GPyOpt.acquisitions.AcquisitionLP(gm, space, None, base)
+        assert lp.transform == ("none" if tag == "ei" else "softplus")
+        assert (lp._native_kind() is not None) == (backend == "cuda")
+        lp.update_batches(g["lp_Xb"], float(g["lp_L"]), float(g["lp_Min"]))
+        assert_allclose(lp.r_x0, g["lp_%s_r" % tag], rtol=1e-9 * ct, atol=1e-11 * ct)
+        assert_allclose(lp.s_x0, g["lp_%s_s" % tag], rtol=1e-9 * ct)
+        Xq = g["Xs"][3:]
+        f_ref, df_ref = g["lp_%s_f" % tag], g["lp_%s_df" % tag]
+        assert_allclose(lp.acquisition_function(Xq), f_ref, rtol=1e-7 * ct, atol=1e-7 * ct)
+        got = np.vstack([lp.acquisition_function_withGradients(Xq[i:i + 1])[1] for i in range(Xq.shape[0])])
+        assert_allclose(got, df_ref, rtol=1e-6 * ct, atol=1e-8 * ct * np.abs(df_ref).max())
+        if backend == "cuda":     # the device path also takes many points at once
+            fb, dfb = lp.acquisition_function_withGradients(Xq)
+            assert_allclose(fb, f_ref, rtol=1e-7 * ct, atol=1e-7 * ct)
+            assert_allclose(dfb, df_ref, rtol=1e-6 * ct, atol=1e-8 * ct * np.abs(df_ref).max())
+        lp.update_batches(None, None, None)
+        assert_allclose(lp.acquisition_function(Xq), g["lp_%s_f_nobatch" % tag], rtol=1e-7 * ct, atol=1e-7 * ct)
     # one point, as apply_optimizer's wrappers pass it (optimizer.py:200-232)
     f1 = ei.acquisition_function(g["Xs"][3:4])
     assert f1.shape == (1, 1)
@@ -286,6 +305,39 @@ def _run_bo(backend, iters, seed=0, acquisition_type='EI', **kw):
                                              exact_feval=True, initial_design_numdata=5, initial_design_type='random', **kw)
     bo.run_optimization(max_iter=iters)
     return bo
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_bo_local_penalization_batch(backend):
+    """Batch BO with evaluator_type='local_penalization' (core/evaluators/batch_local_penalization.py): every iteration
+    proposes batch_size points, the first from the plain log-acquisition, the others from the penalised one."""
+    np.random.seed(4)
+    model = make_gpmodel(backend, kernel=GPy.kern.Matern52(2), exact_feval=True, verbose=False, optimize_restarts=1)
+    bo = GPyOpt.methods.BayesianOptimization(branin, domain=BRANIN_DOMAIN, model=model, acquisition_type='EI', exact_feval=True,
+                                             initial_design_numdata=6, evaluator_type='local_penalization', batch_size=3)
+    assert isinstance(bo.evaluator, GPyOpt.core.evaluators.LocalPenalization)
+    bo.run_optimization(max_iter=3)
+    assert bo.X.shape == (6 + 3 * 3, 2) and bo.Y.shape == (15, 1)
+    for it in range(3):                       # the points of one batch are kept apart by the penalisers
+        B = bo.X[6 + 3 * it: 9 + 3 * it]
+        dist = np.sqrt(((B[:, None, :] - B[None, :, :]) ** 2).sum(-1))[np.triu_indices(3, 1)]
+        assert np.all(dist > 1e-3)
+    assert bo.fx_opt <= bo.Y[:6].min()
+
+
+@pytest.mark.gpu
+def test_bo_local_penalization_matches_oracle():
+    np.random.seed(4)
+    res = {}
+    for backend in ("cuda", "oracle"):
+        np.random.seed(4)
+        model = make_gpmodel(backend, kernel=GPy.kern.Matern52(2), exact_feval=True, verbose=False, optimize_restarts=1)
+        bo = GPyOpt.methods.BayesianOptimization(branin, domain=BRANIN_DOMAIN, model=model, acquisition_type='EI', exact_feval=True,
+                                                 initial_design_numdata=6, evaluator_type='local_penalization', batch_size=3)
+        bo.run_optimization(max_iter=2)
+        res[backend] = bo.X.copy()
+    assert res["cuda"].shape == res["oracle"].shape == (12, 2)
+    assert_allclose(res["cuda"], res["oracle"], rtol=1e-4, atol=1e-4)
 
 
 def test_bo_branin_runs_on_oracle_backend():
