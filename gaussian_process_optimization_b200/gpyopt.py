@@ -311,7 +311,7 @@ class GPModel(BOModel):
     analytical_gradient_prediction = True
 
     def __init__(self, kernel=None, noise_var=None, exact_feval=False, optimizer='bfgs', max_iters=1000, optimize_restarts=5,
-                 sparse=False, num_inducing=10, verbose=True, ARD=False, Gower=False, space=None):
+                 sparse=False, num_inducing=10, verbose=True, ARD=False, Gower=False, space=None, distributed_restarts=False):
         if sparse:
             raise NotImplementedError("sparse GPs are outside the B200 hot path (exact N x N on one GPU)")
         if Gower:
@@ -320,6 +320,8 @@ class GPModel(BOModel):
         self.optimize_restarts, self.optimizer, self.max_iters, self.verbose = optimize_restarts, optimizer, max_iters, verbose
         self.sparse, self.num_inducing, self.model, self.ARD = sparse, num_inducing, None, ARD
         self._fmin = None
+        # one optimize_restarts restart per torch.distributed rank (every rank must hold the same data and RNG state)
+        self.distributed_restarts = distributed_restarts
 
     @staticmethod
     def fromConfig(config):
@@ -352,7 +354,8 @@ class GPModel(BOModel):
                 self.model.optimize(optimizer=self.optimizer, max_iters=self.max_iters, messages=False, ipython_notebook=False)
             else:
                 self.model.optimize_restarts(num_restarts=self.optimize_restarts, optimizer=self.optimizer,
-                                             max_iters=self.max_iters, verbose=self.verbose)
+                                             max_iters=self.max_iters, verbose=self.verbose,
+                                             **({"distributed": True} if self.distributed_restarts else {}))
         self._fmin = None
 
     def _nat(self):

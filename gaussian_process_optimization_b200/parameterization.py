@@ -427,7 +427,52 @@ class Model(Parameterized):
         self.optimization_runs.append(run)
         return run
 
-    def optimize_restarts(self, num_restarts=10, robust=False, verbose=True, parallel=False, num_processes=None, **kwargs):
+    def _optimize_restarts_distributed(self, num_restarts, robust, verbose, group, **kwargs):
+        """One restart per rank: the restarts are independent once their starting points are drawn, so rank r
+        runs restarts r, r + world, ... and ONE all-reduce of (f_opt, x_opt) per restart row makes every rank adopt the same
+        best run.  Every rank must hold the same model and the same np.random state: the starts are drawn exactly as the
+        sequential loop draws them (one normal(size=n_free) vector per restart i > 0, GPy/GPy/core/__init__.py:19-43), which
+        keeps the global RNG stream -- and therefore the BO trajectory -- identical to the sequential run."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = self._size_transformed()
+        starts = [self.optimizer_array.copy()] + [np.random.normal(size=n) for _ in range(1, num_restarts)]
+        table = np.full((num_restarts, 3 + n), np.inf)        # f_opt, funct_eval, ok flag, x_opt
+        for i in range(rank, num_restarts, world):
+            try:
+                self.optimizer_array = starts[i]
+                run = self.optimize(start=starts[i], **kwargs)
+                table[i, 0], table[i, 1], table[i, 2], table[i, 3:] = run.f_opt, run.funct_eval, 1.0, run.x_opt
+                self.optimization_runs.pop()                  # re-appended below in restart order on every rank
+            except Exception as e:
+                if not robust:
+                    raise e
+                print("Warning - optimization restart {0}/{1} failed".format(i + 1, num_restarts))
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(table).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)  # every row was written by exactly one rank, +inf elsewhere
+        table = t.cpu().numpy()
+        done = [i for i in range(num_restarts) if np.isfinite(table[i, 2])]
+        for i in done:
+            self.optimization_runs.append(ObjectiveRun(table[i, 3:].copy(), float(table[i, 0]), int(table[i, 1]), "distributed"))
+            if verbose:
+                print("Optimization restart {0}/{1}, f = {2}".format(i + 1, num_restarts, table[i, 0]))
+        return done, table
+
+    def optimize_restarts(self, num_restarts=10, robust=False, verbose=True, parallel=False, num_processes=None, distributed=False,
+                          group=None, **kwargs):
+        if distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                initial_parameters = self.optimizer_array.copy()
+                done, table = self._optimize_restarts_distributed(num_restarts, robust, verbose, group, **kwargs)
+                if done:
+                    best = done[int(np.argmin([table[i, 0] for i in done]))]
+                    self.optimizer_array = table[best, 3:]
+                else:
+                    self.optimizer_array = initial_parameters
+                return self.optimization_runs
         initial_length = len(self.optimization_runs)
         initial_parameters = self.optimizer_array.copy()
         for i in range(num_restarts):

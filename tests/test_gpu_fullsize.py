@@ -135,3 +135,29 @@ def test_acquisition_topk_properties(fitted):
     e[3] = 1e-6
     fd = (m.acquisition("EI", 0.01, fmin, (Xc[c] + e)[None])["f"][0, 0] - m.acquisition("EI", 0.01, fmin, (Xc[c] - e)[None])["f"][0, 0]) / 2e-6
     assert_allclose(r["df"][c, 3], fd, rtol=1e-4, atol=1e-9)
+
+
+def test_n32768_d20_end_state_of_config5():
+    """BASELINE.json config 5 grows the model to N = 32768 (D = 20): three 8.6 GB matrices resident on one GPU.  Checked through
+    the closed forms at the training inputs (no second N x N copy needed) and one finite difference."""
+    n, d = 32768, 20
+    X, Y, ls = _synth(n, d, seed=20)
+    m = native.NativeModel("mat52", True, d, 1, n_cap=n, cand_block=1024)
+    m.set_data(X, Y)
+    v, noise = 1.1, 1e-2
+    m.set_theta(v, ls, noise)
+    info, logL, g = m.fit(True)
+    assert info == 0 and np.isfinite(logL) and np.all(np.isfinite(g))
+    s = noise + 1e-8
+    alpha = m.get("alpha")
+    idx = np.arange(0, n, 113)[:256]
+    mu, var = m.predict(X[idx], include_likelihood=False)
+    assert_allclose(mu, Y[idx] - s * alpha[idx], rtol=1e-9, atol=1e-10)
+    assert np.all(var > 0) and np.all(var < s)                      # var = s - s^2 (Ky^-1)_ii, and (Ky^-1)_ii > 0
+    h = 1e-5
+    m.set_theta(v, ls, noise * (1 + h))
+    _, lp, _ = m.fit(False)
+    m.set_theta(v, ls, noise * (1 - h))
+    _, lm, _ = m.fit(False)
+    assert_allclose(g[-1], (lp - lm) / (2 * noise * h), rtol=1e-5, atol=1e-4)
+    m.close()

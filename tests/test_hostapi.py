@@ -368,3 +368,38 @@ def test_bo_branin_trajectory_matches_oracle(acq):
     assert same.all(), "trajectories separate at evaluation %d:\ncuda   %r\noracle %r" % (first_bad, a.X[first_bad], b.X[first_bad])
     assert_allclose(a.Y, b.Y, rtol=1e-4, atol=1e-6)
     assert np.argmin(a.Y) == np.argmin(b.Y)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# optimize_restarts with one restart per rank (gloo, world size 2, oracle backend on CPU): same runs, same optimum
+# ---------------------------------------------------------------------------------------------------------------------
+def _restart_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, Y = _opt_problem()
+    m = make_gpr("oracle", X, Y, GPy.kern.Matern52(3, ARD=True), noise_var=0.1)
+    np.random.seed(0)
+    m.optimize_restarts(num_restarts=3, optimizer='lbfgs', max_iters=100, verbose=False, distributed=True)
+    np.savez(out % rank, x=m.optimizer_array, f=[r.f_opt for r in m.optimization_runs], theta=m[:], rng=np.random.uniform())
+    dist.destroy_process_group()
+
+
+def test_distributed_restarts_match_sequential(tmp_path):
+    import os
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r%d.npz")
+    mp.spawn(_restart_worker, args=(2, 29700 + (os.getpid() % 2000), out), nprocs=2, join=True)
+    X, Y = _opt_problem()
+    m = make_gpr("oracle", X, Y, GPy.kern.Matern52(3, ARD=True), noise_var=0.1)
+    np.random.seed(0)
+    m.optimize_restarts(num_restarts=3, optimizer='lbfgs', max_iters=100, verbose=False)
+    rng_after = np.random.uniform()
+    for r in range(2):
+        z = np.load(out % r)
+        assert_allclose(z["f"], [run.f_opt for run in m.optimization_runs], rtol=1e-12)
+        assert_allclose(z["x"], m.optimizer_array, rtol=1e-12)
+        assert_allclose(z["theta"], m[:], rtol=1e-12)
+        assert z["rng"] == rng_after            # the global NumPy stream advanced exactly as in the sequential run
