@@ -56,6 +56,8 @@ SIGNATURES = {
     "gpb_model_acq_topk": (c_int, [c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_int, c_int,
                                    ctypes.c_longlong, c_double_p, c_ll_p, c_double_p]),
     "gpb_set_overlap": (c_int, [c_int]),
+    "gpb_model_acq_topk_full": (c_int, [c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_int, c_int,
+                                        ctypes.c_longlong, c_double_p, c_ll_p, c_double_p, c_void_p, c_void_p]),
     "gpb_profile_gemm": (c_int, [c_int]),
     "gpb_gemm_config": (c_int, [c_int]),
     "gpb_profile_gemm_collect": (c_int, [c_double_p, c_double_p, c_ll_p]),

@@ -671,21 +671,24 @@ int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int
   return 0;
 }
 
-int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
-                       long long index_offset, double *vals, long long *idx, double *pts) {
+int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
+                            long long index_offset, double *vals, long long *idx, double *pts, double *f, double *df) {
   GPB_REQUIRE(m && Xc && vals && idx, "acq_topk: NULL argument");
   GPB_REQUIRE(m->fitted, "acq_topk: model has not been fitted");
   GPB_REQUIRE(k >= 1 && k <= 64 && k <= mc, "acq_topk: k = %d must be in [1, min(64, mc)]", k);
   GPB_REQUIRE(m->p == 1, "acq_topk: single output only");
   const int d = m->d;
+  const bool grad = df != nullptr;
   cudaStream_t s = m->stream;
   GPB_TRY(launch_topk_init(m->topv, m->topi, k, s));
   for (int c0 = 0; c0 < mc; c0 += m->cb) {
     const int mcb = std::min(m->cb, mc - c0);
-    GPB_TRY(predict_block(m, Xc + (size_t)c0 * d, mcb, dev, 1, 1));
-    GPB_TRY(launch_acq_epilogue(acq, par, fmin, mcb, d, m->mu, m->var, nullptr, nullptr, m->fbuf, nullptr, nullptr, nullptr, nullptr,
-                                nullptr, s));
+    GPB_TRY(predict_block(m, Xc + (size_t)c0 * d, mcb, dev, grad ? 2 : 1, 1));
+    GPB_TRY(launch_acq_epilogue(acq, par, fmin, mcb, d, m->mu, m->var, grad ? m->dmu : nullptr, grad ? m->dvar : nullptr, m->fbuf,
+                                grad ? m->dfbuf : nullptr, nullptr, nullptr, nullptr, nullptr, s));
     GPB_TRY(launch_topk_update(m->fbuf, mcb, index_offset + c0, m->topv, m->topi, k, s));
+    GPB_TRY(copy_out(f ? f + c0 : nullptr, m->fbuf, mcb, dev, s));
+    if (grad) GPB_TRY(copy_out(df + (size_t)c0 * d, m->dfbuf, (size_t)mcb * d, dev, s));
     if (!dev) GPB_CUDA(cudaStreamSynchronize(s));  // the host block may be reused by the caller's next copy
   }
   GPB_CUDA(cudaMemcpyAsync(m->pinned, m->topv, k * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -703,6 +706,11 @@ int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, c
     }
   }
   return 0;
+}
+
+int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
+                       long long index_offset, double *vals, long long *idx, double *pts) {
+  return gpb_model_acq_topk_full(m, acq, par, fmin, mc, Xc, dev, k, index_offset, vals, idx, pts, nullptr, nullptr);
 }
 
 // =====================================================================================================================

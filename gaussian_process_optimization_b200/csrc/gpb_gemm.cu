@@ -223,8 +223,13 @@ int gemm_profile_enable(int on) {
   return 0;
 }
 
+static int g_big_config = 9;     // configuration of launches with >= 20 output blocks of 128x128 (100 + cfg selects it)
+
 int gemm_force_config(int cfg) {
-  g_forced_config = cfg;
+  if (cfg >= 100)
+    g_big_config = cfg - 100;
+  else
+    g_forced_config = cfg;
   return 0;
 }
 
@@ -324,7 +329,12 @@ static int launch_cfg(const GemmArgs &g, cudaStream_t s) {
   const int b128m = g.M / 128, b128n = g.N / 128;
   const int blocks128 = g.tri_out ? b128m * (b128m + 1) / 2 : b128m * b128n;
   int cfg = g_forced_config;
-  if (cfg == 0) cfg = (blocks128 >= 148) ? 1 : (blocks128 >= 20) ? 2 : 3;
+  // 64x64 tiles with four CTAs (16 warps) per SM and a two-stage pipeline beat the 64x128 / two-CTA configuration in every
+  // storage order (scripts/gemm_sweep.py: 35.4 / 34.9 / 35.0 vs 34.6 / 34.1 / 34.4 TFLOP/s at 8192^3; cuBLAS 36.2): with the
+  // DMMA issue slot held 16 cycles per instruction, more resident warps hide the fragment-load latency better than bigger
+  // register tiles do
+  if (cfg == 0) cfg = (blocks128 >= 20) ? g_big_config : 3;
+  if (cfg == 1 && g_forced_config == 0 && blocks128 < 148) cfg = 2;   // the 64x128 policy of the first version, kept selectable
   // both operands k-contiguous: BK = 32 with two stages halves the per-k-tile barriers (+1.8% at 8192^3); the strided
   // layouts are faster with BK = 16 and three stages (scripts/gemm_sweep.py)
   if (cfg == 1 && LA == LAYOUT_ROWK && LB == LAYOUT_ROWK && g.K % 32 == 0 && g_forced_config == 0)
@@ -332,6 +342,8 @@ static int launch_cfg(const GemmArgs &g, cudaStream_t s) {
   if (cfg == 1) return launch_t<LA, LB, 64, 128, 1, 4, 2, 16, 3>(g, s);
   if (cfg == 2) return launch_t<LA, LB, 64, 64, 2, 2, 3, 16, 3>(g, s);
   if (cfg == 4 && g.K % 32 == 0) return launch_t<LA, LB, 64, 128, 1, 4, 2, 32, 2>(g, s);   // 64x128, BK = 32, two stages
+  if (cfg == 9) return launch_t<LA, LB, 64, 64, 2, 2, 4, 16, 2>(g, s);                      // experimental: 64x64, 4 CTAs / SM, two stages
+  if (cfg == 11) return launch_t<LA, LB, 64, 64, 2, 2, 5, 16, 2>(g, s);                     // experimental: 5 CTAs / SM (<= 102 registers)
   return launch_t<LA, LB, 32, 32, 2, 2, 4, 16, 3>(g, s);
 }
 

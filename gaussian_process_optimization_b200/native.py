@@ -302,6 +302,24 @@ class NativeModel(object):
         check(self._lib.gpb_model_acquisition_lp(self._h, aid, float(par), float(fmin), mc, ptr(Xc), ptr(f), ptr(df), 0), "acquisition_lp")
         return (f, df) if with_gradients else f
 
+    def acq_topk_full(self, acq, par, fmin, Xc, k, index_offset=0, with_gradients=True):
+        """One pass: every candidate's f [and df] plus the k best -> (vals, idx, pts, f, df)."""
+        dev = is_torch(Xc)
+        if dev:
+            import torch
+            new = lambda *s: torch.empty(*s, dtype=torch.float64, device=Xc.device)  # noqa: E731
+        else:
+            Xc = as_host(Xc)
+            new = lambda *s: np.empty(s)  # noqa: E731
+        mc = Xc.shape[0]
+        f = new(mc, 1)
+        df = new(mc, self.d) if with_gradients else None
+        vals, idx, pts = np.empty(k), np.empty(k, dtype=np.int64), np.empty((k, self.d))
+        aid = acq if isinstance(acq, int) else ACQ_IDS[acq]
+        check(self._lib.gpb_model_acq_topk_full(self._h, aid, float(par), float(fmin), mc, ptr(Xc), int(dev), int(k), int(index_offset),
+                                                dptr(vals), idx.ctypes.data_as(_lib.c_ll_p), dptr(pts), ptr(f), ptr(df)), "acq_topk_full")
+        return vals, idx, pts, f, df
+
     def acq_topk(self, acq, par, fmin, Xc, k, index_offset=0):
         dev = is_torch(Xc)
         if not dev:

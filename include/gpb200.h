@@ -119,6 +119,11 @@ int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int
 int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
                        long long index_offset, double *vals, long long *idx, double *pts);
 
+/* The same in ONE pass that also returns every candidate's f = -acq (mc; NULL to skip) and df = -dacq (mc x d; NULL to skip the
+ * gradient solves): "score a candidate list with gradients and keep the k best" (run.py:1240-1253 at scale, BASELINE config 4). */
+int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
+                            long long index_offset, double *vals, long long *idx, double *pts, double *f, double *df);
+
 /* ---- raw building blocks (tests, benchmarks, roofline measurements) ------------------------------------------------ */
 /* C = alpha * op(A) op(B) + beta * C with the fp64 tensor-core (DMMA) engine; all of m, n multiples of 128, k of 16.
  * ta = 0: A is m x k row-major; 1: A is stored k x m.  tb = 0: B is stored n x k ("NT"); 1: B is stored k x n.
@@ -134,7 +139,9 @@ int gpb_set_overlap(int min_n);
  * stream.  collect() waits for them and returns the summed kernel time (ms), the executed tile flops and the launch count
  * since the last collect. */
 int gpb_profile_gemm(int enable);
-/* Tuning/testing knob: force the GEMM tile configuration (0 auto, 1 = 64x128, 2 = 64x64, 3 = 32x32 CTA tiles). */
+/* Tuning/testing knob: force the GEMM tile configuration (0 auto, 1 = 64x128 two CTAs/SM, 2 = 64x64 three CTAs/SM, 3 = 32x32,
+ * 4 = 64x128 BK 32, 9 = 64x64 four CTAs/SM two stages, 11 = five CTAs/SM); 100 + cfg only selects the configuration of the
+ * large launches (>= 20 output blocks of 128x128) and leaves the small ones automatic. */
 int gpb_gemm_config(int cfg);
 int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches);
 /* Duration (ms) and executed flops of the last recorded GEMM launch (call before collect). */

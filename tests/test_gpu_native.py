@@ -345,3 +345,21 @@ def test_small_candidate_counts_use_the_skinny_products(kind):
         assert_allclose(mu, mu_r, rtol=1e-9, atol=1e-11)
         assert_allclose(var, var_r, rtol=1e-9, atol=1e-12)
     m.close()
+
+
+def test_acq_topk_full_single_pass():
+    """Values, gradients and the k best from ONE pass equal the separate calls."""
+    N, D = 900, 5
+    X, Y, ls = _synth(N, D)
+    m = native.NativeModel("mat52", True, D, 1, n_cap=N, cand_block=256)
+    m.set_data(X, Y)
+    m.set_theta(1.0, ls, 1e-3)
+    assert m.fit(False)[0] == 0
+    fmin = m.fmin()
+    Xc = np.random.RandomState(8).uniform(0, 1, (700, D))
+    ref = m.acquisition("EI", 0.01, fmin, Xc, with_gradients=True)
+    v0, i0, p0 = m.acq_topk("EI", 0.01, fmin, Xc, 5, index_offset=100)
+    vals, idx, pts, f, df = m.acq_topk_full("EI", 0.01, fmin, Xc, 5, index_offset=100)
+    assert np.array_equal(f, ref["f"]) and np.array_equal(df, ref["df"])
+    assert np.array_equal(idx, i0) and np.array_equal(vals, v0) and np.array_equal(pts, p0)
+    m.close()
