@@ -144,6 +144,7 @@ using namespace gpb;
 // model
 // =====================================================================================================================
 struct gpb_model {
+  int device = 0;  // the CUDA device the model was created on; every call must be made with that device current
   int kind = 0, ard = 1, d = 0, p = 1, n_cap = 0, np_cap = 0, cb = 0, nls = 0;
   int n = 0, np = 0;
   double variance = 1.0, noise = 1.0, jitter = 0.0;
@@ -168,6 +169,14 @@ struct gpb_model {
   double *lp_buf = nullptr;     // [Xb (nb x d) | r (nb) | s (nb)], own allocation of lp_cap rows
   int lp_cap = 0, lp_nb = 0, lp_transform = 0;
 };
+
+// A model's buffers, streams and events belong to one device: refuse calls made while another device is current.
+static int check_device(const gpb_model *m, const char *what) {
+  int dev = -1;
+  GPB_CUDA(cudaGetDevice(&dev));
+  GPB_REQUIRE(dev == m->device, "%s: the model lives on CUDA device %d but device %d is current", what, m->device, dev);
+  return 0;
+}
 
 static int g_overlap_min_n = 512;  // 0 disables the two-stream schedule (gpb_set_overlap)
 
@@ -260,6 +269,11 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
   m->nls = ard ? d : 1;
   m->ls.assign(m->nls, 1.0);
   m->stream = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaGetDevice(&m->device) != cudaSuccess) {
+    delete m;
+    set_error("model_create: cudaGetDevice failed");
+    return -1;
+  }
   const size_t need = carve(n_cap, d, p, m->cb, nullptr, nullptr);
   if (workspace) {
     if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
@@ -308,6 +322,7 @@ int gpb_model_destroy(gpb_model *m) {
 
 int gpb_model_set_data(gpb_model *m, int n, const double *X, const double *Y, int dev) {
   GPB_REQUIRE(m && X && Y, "set_data: NULL argument");
+  GPB_TRY(check_device(m, "set_data"));
   GPB_REQUIRE(n >= 1 && n <= m->n_cap, "set_data: n = %d exceeds the model capacity %d", n, m->n_cap);
   m->n = n;
   m->np = round_up(n, TILE);
@@ -358,6 +373,7 @@ static int ensure_wi(gpb_model *m) {
 
 int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out) {
   GPB_REQUIRE(m && out, "fit: NULL argument");
+  GPB_TRY(check_device(m, "fit"));
   GPB_REQUIRE(m->have_data, "fit: set_data has not been called");
   // Hyper-parameters outside the domain (an L-BFGS-B line search can push the transformed parameters to 0, inf or NaN):
   // the reference's NumPy path turns those into NaNs and ends in jitchol's LinAlgError (linalg.py:62-75), which paramz
@@ -377,7 +393,7 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
   GPB_TRY(ensure_scaled(m));
   const int n = m->n, np = m->np, d = m->d, p = m->p;
   // Ky = K + (noise + 1e-8 [+ jitter]) I     exact_gaussian_inference.py:55-56
-  GPB_TRY(launch_kmat(m->kind, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->noise + 1e-8 + extra_jitter, 1, m->f.A, np, np,
+  GPB_TRY(launch_kmat(m->kind, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np,
                       np, m->stream));
   // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
   const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / 8) : 0;
@@ -434,6 +450,7 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
 
 int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) {
   GPB_REQUIRE(m && what && dst, "get: NULL argument");
+  GPB_TRY(check_device(m, "get"));
   const std::string w(what);
   const int n = m->n, np = m->np, p = m->p;
   cudaStream_t s = m->stream;
@@ -532,6 +549,7 @@ static int copy_out(double *dst, const double *src_dev, size_t count, int dev, c
 
 int gpb_model_predict(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *var, int dev) {
   GPB_REQUIRE(m && Xc, "predict: NULL argument");
+  GPB_TRY(check_device(m, "predict"));
   GPB_REQUIRE(m->fitted, "predict: model has not been fitted");
   GPB_REQUIRE(mc >= 0, "predict: negative candidate count");
   for (int c0 = 0; c0 < mc; c0 += m->cb) {
@@ -547,6 +565,7 @@ int gpb_model_predict(gpb_model *m, int mc, const double *Xc, int include_likeli
 
 int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *cov, int dev) {
   GPB_REQUIRE(m && Xc && cov, "predict_full_cov: NULL argument");
+  GPB_TRY(check_device(m, "predict_full_cov"));
   GPB_REQUIRE(m->fitted, "predict_full_cov: model has not been fitted");
   GPB_REQUIRE(mc >= 1 && mc <= m->cb, "predict_full_cov: mc = %d exceeds the candidate block %d", mc, m->cb);
   const int cpad = round_up(mc, TILE), np = m->np;
@@ -568,6 +587,7 @@ int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int inclu
 
 int gpb_model_predictive_gradients(gpb_model *m, int mc, const double *Xc, double *dmu, double *dvar, int dev) {
   GPB_REQUIRE(m && Xc, "predictive_gradients: NULL argument");
+  GPB_TRY(check_device(m, "predictive_gradients"));
   GPB_REQUIRE(m->fitted, "predictive_gradients: model has not been fitted");
   for (int c0 = 0; c0 < mc; c0 += m->cb) {
     const int mcb = std::min(m->cb, mc - c0);
@@ -582,6 +602,7 @@ int gpb_model_predictive_gradients(gpb_model *m, int mc, const double *Xc, doubl
 
 int gpb_model_fmin(gpb_model *m, double *fmin) {
   GPB_REQUIRE(m && fmin, "fmin: NULL argument");
+  GPB_TRY(check_device(m, "fmin"));
   GPB_REQUIRE(m->fitted, "fmin: model has not been fitted");
   GPB_REQUIRE(m->p == 1, "fmin: single output only");
   // model.predict(model.X)[0].min()   gpmodel.py:125-129 -- only the mean is used, so the variance solve is skipped
@@ -601,6 +622,7 @@ int gpb_model_fmin(gpb_model *m, double *fmin) {
 int gpb_model_acquisition(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df,
                           double *mean, double *sd, double *dmdx, double *dsdx, int dev) {
   GPB_REQUIRE(m && Xc, "acquisition: NULL argument");
+  GPB_TRY(check_device(m, "acquisition"));
   GPB_REQUIRE(m->fitted, "acquisition: model has not been fitted");
   GPB_REQUIRE(acq == GPB_ACQ_EI || acq == GPB_ACQ_LCB, "acquisition: unknown type %d", acq);
   GPB_REQUIRE(m->p == 1, "acquisition: single output only");
@@ -627,6 +649,7 @@ int gpb_model_acquisition(gpb_model *m, int acq, double par, double fmin, int mc
 
 int gpb_model_set_penalizers(gpb_model *m, int transform, int nb, const double *Xb, const double *r, const double *s) {
   GPB_REQUIRE(m, "set_penalizers: NULL model");
+  GPB_TRY(check_device(m, "set_penalizers"));
   GPB_REQUIRE(transform == 0 || transform == 1, "set_penalizers: transform must be 0 (none) or 1 (softplus)");
   GPB_REQUIRE(nb >= 0 && (nb == 0 || (Xb && r && s)), "set_penalizers: bad arguments");
   m->lp_transform = transform;
@@ -649,6 +672,7 @@ int gpb_model_set_penalizers(gpb_model *m, int transform, int nb, const double *
 
 int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df, int dev) {
   GPB_REQUIRE(m && Xc && f, "acquisition_lp: NULL argument");
+  GPB_TRY(check_device(m, "acquisition_lp"));
   GPB_REQUIRE(m->fitted, "acquisition_lp: model has not been fitted");
   GPB_REQUIRE(acq == GPB_ACQ_EI || acq == GPB_ACQ_LCB, "acquisition_lp: unknown type %d", acq);
   GPB_REQUIRE(m->p == 1, "acquisition_lp: single output only");
@@ -674,6 +698,7 @@ int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int
 int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
                             long long index_offset, double *vals, long long *idx, double *pts, double *f, double *df) {
   GPB_REQUIRE(m && Xc && vals && idx, "acq_topk: NULL argument");
+  GPB_TRY(check_device(m, "acq_topk_full"));
   GPB_REQUIRE(m->fitted, "acq_topk: model has not been fitted");
   GPB_REQUIRE(k >= 1 && k <= 64 && k <= mc, "acq_topk: k = %d must be in [1, min(64, mc)]", k);
   GPB_REQUIRE(m->p == 1, "acq_topk: single output only");

@@ -211,11 +211,10 @@ leaf_potrf_inv_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, 
 
 static int launch_leaf(Factor &f, int off, int mode) {
   const size_t smem = (size_t)(2 + 3 * TILE + TILE * LEAF_LD) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (needs_func_config(configured)) {
     GPB_CUDA(cudaFuncSetAttribute(leaf_potrf_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GPB_CUDA(cudaFuncSetAttribute(leaf_potrf_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   double *a = f.A + (size_t)off * f.np + off;
   double *m = f.Mi + (size_t)off * f.np + off;

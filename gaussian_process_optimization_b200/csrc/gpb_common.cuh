@@ -53,6 +53,16 @@ inline void count_launch(int n = 1) { g_launches += n; }
     if (r_ != 0) return r_;  \
   } while (0)
 
+// Opt-in dynamic shared memory must be configured once per kernel AND per device (function attributes are per context):
+// `done` is a per-call-site bit mask over device ordinals.
+inline bool needs_func_config(unsigned long long &done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done & (1ull << dev)) return false;
+  done |= (1ull << dev);
+  return true;
+}
+
 // ---- stationary covariance functions of the scaled squared distance ---------------------------------------------------
 // k(r) and k'(r)/r for r = sqrt(r2).  The reference forms dK_dr * inv_dist (stationary.py:227-230,251-258) with inv_dist := 0
 // where r == 0; k'(r)/r is finite at 0 and is only ever multiplied by (x - x') which vanishes there, so the closed form

@@ -301,11 +301,10 @@ static int launch_t(const GemmArgs &g, cudaStream_t s) {
   constexpr int B_TILE = tile_doubles<LB, BN, BK>();
   constexpr int THREADS = WARPS_M * WARPS_N * 32;
   const size_t smem = (size_t)STAGES * (A_TILE + B_TILE) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (needs_func_config(configured)) {
     GPB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS, BK, STAGES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const int b128m = g.M / 128, b128n = g.N / 128;
   const int blocks128 = g.tri_out ? b128m * (b128m + 1) / 2 : b128m * b128n;

@@ -41,6 +41,7 @@ int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, 
 //   mode 0 (rect):  out[i][j] = k(r_ij) for i < n_rows, j < n_cols (nothing else is written)
 //   mode 1 (Ky, padded): out is np x np;  i, j < n: k + (i == j) * diag_add;  otherwise identity
 //   mode 2 (rect, zero padded): out is rows_pad x cols_pad; k inside n_rows x n_cols, 0 outside
+//   mode 3 = mode 1 restricted to the 128-blocks on and below the diagonal (input of the factorisation)
 // ---------------------------------------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
@@ -50,6 +51,12 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__
   double *xa = sm;              // [d][64]
   double *xb = sm + d * KTILE;  // [d][64]
   const int row0 = blockIdx.y * KTILE, col0 = blockIdx.x * KTILE;
+  if (mode == 3) {
+    // Ky for the factorisation: nothing reads the 128-blocks strictly above the diagonal (gpb_chol.cu only touches lower
+    // blocks and complete diagonal blocks), so half of the exp() work and of the HBM writes is skipped
+    if ((col0 >> 7) > (row0 >> 7)) return;
+    mode = 1;
+  }
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   for (int e = tid; e < d * KTILE; e += 256) {
     const int q = e >> 6, i = e & 63;

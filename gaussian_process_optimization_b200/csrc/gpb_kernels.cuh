@@ -13,7 +13,8 @@ inline size_t kgrad_part_doubles(int rows_pad, int cols_pad, int d, int fused) {
 
 int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, double *XsT, int ldx, cudaStream_t s);
 
-// mode: 0 rect exact, 1 padded Ky (identity outside n x n, diag_add on the diagonal), 2 rect zero padded
+// mode: 0 rect exact, 1 padded Ky (identity outside n x n, diag_add on the diagonal), 2 rect zero padded,
+//       3 = 1 but only the 128-blocks on / below the diagonal (what the factorisation reads)
 int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                 double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
                 cudaStream_t s);

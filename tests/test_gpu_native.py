@@ -363,3 +363,32 @@ def test_acq_topk_full_single_pass():
     assert np.array_equal(f, ref["f"]) and np.array_equal(df, ref["df"])
     assert np.array_equal(idx, i0) and np.array_equal(vals, v0) and np.array_equal(pts, p0)
     m.close()
+
+
+@pytest.mark.parametrize("kind,N,D,noise", [("rbf", 1500, 4, 1e-6), ("mat52", 2500, 6, 1e-6), ("rbf", 1200, 2, 1e-4)])
+def test_ill_conditioned_exact_feval_models(kind, N, D, noise):
+    """The exact_feval regime of GPyOpt (noise fixed at 1e-6, gpmodel.py:72-73) with smooth kernels: cond(Ky) is 1e8 .. 1e12.
+    Two LAPACK builds only agree to cond * eps there; the explicit-inverse factorisation must not lose more than that."""
+    X, Y, ls = _synth(N, D, seed=77)
+    ls = ls * 0.6
+    st = O.GPState(kind, X, Y, 1.0, ls, noise)
+    w = np.linalg.eigvalsh(st.post.K + (noise + 1e-8) * np.eye(N))
+    cond = w[-1] / w[0]
+    tol = max(1.0, cond * 2.2e-16 / 1e-12)
+    m = native.NativeModel(kind, True, D, 1, n_cap=N, cand_block=512)
+    m.set_data(X, Y)
+    m.set_theta(1.0, ls, noise)
+    info, logL, g = m.fit(True)
+    assert info == 0
+    l_ref, g_ref, _ = O.log_likelihood_and_gradients(kind, X, Y, 1.0, ls, noise)
+    assert_allclose(logL, l_ref, rtol=1e-9 * tol)
+    assert_allclose(g, g_ref, rtol=1e-7 * tol, atol=1e-7 * tol * np.abs(g_ref).max())
+    Xc = np.random.RandomState(2).uniform(0, 1, (300, D))
+    mu, var = m.predict(Xc)
+    mu_r, var_r = O.predict(kind, st.post, X, Xc, 1.0, ls, noise)
+    assert_allclose(mu, mu_r, rtol=1e-9 * tol, atol=1e-10 * tol)
+    assert_allclose(var, var_r, rtol=1e-9 * tol, atol=1e-12 * tol)
+    assert np.all(var >= noise * 0.5)          # never below the noise floor by more than rounding
+    print("cond(Ky) = %.2e, |dlogL|/|logL| = %.2e, max |dmu| = %.2e, max |dvar| = %.2e" %
+          (cond, abs(logL - l_ref) / abs(l_ref), np.abs(mu - mu_r).max(), np.abs(var - var_r).max()))
+    m.close()
