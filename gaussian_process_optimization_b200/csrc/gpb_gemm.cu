@@ -341,8 +341,7 @@ static int launch_cfg(const GemmArgs &g, cudaStream_t s) {
   if (cfg == 1) return launch_t<LA, LB, 64, 128, 1, 4, 2, 16, 3>(g, s);
   if (cfg == 2) return launch_t<LA, LB, 64, 64, 2, 2, 3, 16, 3>(g, s);
   if (cfg == 4 && g.K % 32 == 0) return launch_t<LA, LB, 64, 128, 1, 4, 2, 32, 2>(g, s);   // 64x128, BK = 32, two stages
-  if (cfg == 9) return launch_t<LA, LB, 64, 64, 2, 2, 4, 16, 2>(g, s);                      // experimental: 64x64, 4 CTAs / SM, two stages
-  if (cfg == 11) return launch_t<LA, LB, 64, 64, 2, 2, 5, 16, 2>(g, s);                     // experimental: 5 CTAs / SM (<= 102 registers)
+  if (cfg == 9) return launch_t<LA, LB, 64, 64, 2, 2, 4, 16, 2>(g, s);                      // 64x64, 4 CTAs / SM, two stages
   return launch_t<LA, LB, 32, 32, 2, 2, 4, 16, 3>(g, s);
 }
 

@@ -140,7 +140,7 @@ int gpb_set_overlap(int min_n);
  * since the last collect. */
 int gpb_profile_gemm(int enable);
 /* Tuning/testing knob: force the GEMM tile configuration (0 auto, 1 = 64x128 two CTAs/SM, 2 = 64x64 three CTAs/SM, 3 = 32x32,
- * 4 = 64x128 BK 32, 9 = 64x64 four CTAs/SM two stages, 11 = five CTAs/SM); 100 + cfg only selects the configuration of the
+ * 4 = 64x128 BK 32, 9 = 64x64 four CTAs/SM two stages); 100 + cfg only selects the configuration of the
  * large launches (>= 20 output blocks of 128x128) and leaves the small ones automatic. */
 int gpb_gemm_config(int cfg);
 int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches);
