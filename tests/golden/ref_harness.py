@@ -138,11 +138,61 @@ def _pkg(name, path):
 _loaded = None
 
 
-def load():
-    """Install the stand-ins, import the reference's numerical modules, return a namespace of them."""
-    global _loaded
+class _IdList(list):
+    """paramz keeps parameters in an ArrayList whose `in` tests identity (GP.set_XY asks `self.X in self.parameters`)."""
+
+    def __contains__(self, item):
+        return any(item is e for e in self)
+
+
+def _full_paramz():
+    """The repo's own restatement of paramz (gaussian_process_optimization_b200/parameterization.py: transforms, observer
+    pattern, optimize / optimize_restarts / randomize) as the stand-in, so that the reference's GPModel.updateModel and BO
+    loop can run end to end.  Host logic only -- it does no GP arithmetic."""
+    sys.path.insert(0, _REPO)
+    from gaussian_process_optimization_b200 import parameterization as P
+
+    class FullParameterized(P.Parameterized):
+        def __init__(self, name=None, *a, **kw):
+            super(FullParameterized, self).__init__(name, *a, **kw)
+            self.parameters = _IdList()
+
+        def unlink_parameter(self, param):
+            self.parameters = _IdList(p for p in self.parameters if p is not param)
+            param._parent = None
+
+        # paramz Parameterized forwards constrain_* to every parameter below it (gpmodel.py:72-76 calls them on Gaussian_noise)
+        def constrain_fixed(self, value=None, warning=True):
+            for p in self.flattened_parameters():
+                p.constrain_fixed(value, warning)
+        fix = constrain_fixed
+
+        def constrain_bounded(self, lower, upper, warning=True):
+            for p in self.flattened_parameters():
+                p.constrain_bounded(lower, upper, warning)
+
+        def constrain_positive(self, warning=True):
+            for p in self.flattened_parameters():
+                p.constrain_positive(warning)
+
+    class FullModel(P.Model, FullParameterized):
+        def __init__(self, name):
+            P.Model.__init__(self, name)
+            self.parameters = _IdList()
+
+    return P.Param, FullParameterized, FullModel, P.Logexp
+
+
+def load(full_paramz=False):
+    """Install the stand-ins, import the reference's numerical modules, return a namespace of them.
+    full_paramz=True swaps the minimal Param/Parameterized stand-ins for the repo's paramz restatement (needed to run
+    optimize_restarts and the BO loop; tests/golden/ref_bo_harness.py)."""
+    global _loaded, Param, Parameterized, Logexp
     if _loaded is not None:
         return _loaded
+    ModelBase = None
+    if full_paramz:
+        Param, Parameterized, ModelBase, Logexp = _full_paramz()
     if not available():
         raise RuntimeError("reference tree not present at %s" % REF)
     warnings.filterwarnings("ignore", category=SyntaxWarning)
@@ -233,7 +283,12 @@ def load():
     sys.modules["GPy.kern.src"].grid_kerns = gk
 
     class LatentFunctionInference(object):
-        pass
+        # GPy/inference/latent_function_inference/__init__.py:36-46 (hooks called by GP.optimize, no-ops for exact inference)
+        def on_optimization_start(self):
+            pass
+
+        def on_optimization_end(self):
+            pass
     lfi.LatentFunctionInference = LatentFunctionInference
 
     # --- the reference's own numerical modules ---------------------------------------------------------------------
@@ -268,8 +323,11 @@ def load():
     kern_pkg.RBF = ns.rbf.RBF
     kern_pkg.Matern52 = ns.stationary.Matern52
 
-    class Model(Parameterized):
-        pass
+    if ModelBase is not None:
+        Model = ModelBase
+    else:
+        class Model(Parameterized):
+            pass
     core.model = _mod("GPy.core.model", Model=Model)
     core.Model = Model
 
