@@ -69,9 +69,10 @@ inline bool needs_func_config(unsigned long long &done) {
 // gives the same sums without the division.
 //   RBF      (rbf.py:50-54):            k = v exp(-r^2/2),                        k'/r = -k
 //   Matern52 (stationary.py:575-579):   k = v (1 + s5 r + 5/3 r^2) exp(-s5 r),    k'/r = -(5/3) v (1 + s5 r) exp(-s5 r)
-// r2 can overflow to +inf when an optimiser step drives a lengthscale towards 0; the covariance is exactly 0 there, but
-// (1 + s + ..) * exp(-s) and (k'/r) * dx^2 would evaluate inf * 0.  Clamping r2 keeps every factor finite (NaN stays NaN:
-// the comparison is false for it, and a NaN kernel matrix ends in the jitchol LinAlgError like in the reference).
+// r2 can reach 1e300+ when an optimiser step drives a lengthscale towards 0 (scaled coordinates are clamped at 1e150 in
+// scale_transpose_kernel); the covariance is exactly 0 there, but (1 + s + ..) * exp(-s) would evaluate inf * 0.  Clamping r2
+// keeps every factor finite (NaN stays NaN: the comparison is false for it, and a NaN kernel matrix ends in the jitchol
+// LinAlgError like in the reference).
 __device__ __forceinline__ double clamp_r2(double r2) { return r2 > 1e300 ? 1e300 : r2; }
 
 template <int KIND>

@@ -19,7 +19,12 @@ __global__ void scale_transpose_kernel(const double *__restrict__ X, int n, int 
   const size_t total = (size_t)d * ldx;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int q = (int)(e / ldx), i = (int)(e - (size_t)q * ldx);
-    XsT[e] = (i < n) ? X[(size_t)i * d + q] / ls[q] : 0.0;
+    // |x / l| is clamped at 1e150: when an optimiser step drives a lengthscale towards 0 the scaled coordinates would overflow
+    // to inf and produce inf - inf = NaN distances and 0 * inf = NaN gradient terms; clamped, coincident points keep r = 0,
+    // distinct ones get r^2 ~ 1e300 -> k = 0 exactly, and every product below stays finite (no guards in the inner loops)
+    double v = (i < n) ? X[(size_t)i * d + q] / ls[q] : 0.0;
+    v = v > 1e150 ? 1e150 : (v < -1e150 ? -1e150 : v);
+    XsT[e] = v;
   }
 }
 
@@ -251,8 +256,7 @@ __global__ void __launch_bounds__(256, 3) kgrad_kernel(const double *__restrict_
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const double df = va[a] - vb[b];
-        const double w = r2[a][b];
-        if (w != 0.0) acc4[a] = fma(w, df * df, acc4[a]);   // w == 0 with df^2 == inf (lengthscale -> 0) contributes 0, not NaN
+        acc4[a] = fma(r2[a][b], df * df, acc4[a]);
       }
     double acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
     acc = warp_sum(acc);
@@ -344,8 +348,8 @@ __global__ void __launch_bounds__(256) gradx_kernel(const double *__restrict__ X
     if (TWO) w2 = dk * G2[(size_t)c * ldg2 + j];
 #pragma unroll
     for (int q = 0; q < DCAP; ++q) {
-      if (w1 != 0.0) a1[q] = fma(w1, df[q], a1[q]);   // 0 * inf (lengthscale -> 0) contributes 0, not NaN
-      if (TWO && w2 != 0.0) a2[q] = fma(w2, df[q], a2[q]);
+      a1[q] = fma(w1, df[q], a1[q]);
+      if (TWO) a2[q] = fma(w2, df[q], a2[q]);
     }
   }
 #pragma unroll
