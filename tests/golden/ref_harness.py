@@ -357,6 +357,7 @@ def load(full_paramz=False):
     importlib.import_module("GPyOpt.models.base")
     ns.gpmodel = importlib.import_module("GPyOpt.models.gpmodel")
     sys.modules["GPyOpt.models"].GPModel = ns.gpmodel.GPModel
+    sys.modules["GPyOpt.models"].GPModel_MCMC = ns.gpmodel.GPModel_MCMC   # isinstance test in core/bo.py:99
     ns.cost = importlib.import_module("GPyOpt.core.task.cost")
     ns.acq_base = importlib.import_module("GPyOpt.acquisitions.base")
     ns.EI = importlib.import_module("GPyOpt.acquisitions.EI")
