@@ -18,6 +18,7 @@ ACQ_IDS = {"EI": ACQ_EI, "LCB": ACQ_LCB}
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_ll_p = ctypes.POINTER(ctypes.c_longlong)
+c_int_p = ctypes.POINTER(ctypes.c_int)
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
 
@@ -31,6 +32,11 @@ SIGNATURES = {
                            c_int, c_void_p]),
     "gpb_kern_update_gradients_full": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.c_double,
                                                c_double_p, c_int, c_double_p, c_int, c_void_p]),
+    "gpb_kern_K_gower": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, ctypes.c_double, c_int_p, c_double_p, c_void_p,
+                                 c_int, c_int, c_void_p]),
+    "gpb_kern_update_gradients_full_gower": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.c_double,
+                                                     c_double_p, c_int, c_int_p, c_double_p, c_double_p, c_int, c_void_p]),
+    "gpb_model_set_gower": (c_int, [c_void_p, c_int, c_int_p, c_double_p]),
     "gpb_kern_gradients_X": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, ctypes.c_double, c_double_p,
                                      c_int, c_void_p, c_int, c_void_p]),
     "gpb_pdinv": (c_int, [c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_double_p, c_int, c_void_p]),

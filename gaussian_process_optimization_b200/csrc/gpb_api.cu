@@ -166,6 +166,11 @@ struct gpb_model {
   double *pinned = nullptr;  // host, 256 doubles
   FactorOverlap *ov = nullptr;  // streams / events of the two-stream factorisation schedule
   // local-penalisation state (AcquisitionLP.update_batches): batch points and hammer-function parameters on the device
+  // Gower mixed-variable kernel patch (stationary.py:116-135): per-dimension flags / inverse ranges and the coordinate copies
+  // scaled for it (K uses them; every gradient keeps the Euclidean XsT / XcT, like the reference)
+  bool gower = false;
+  std::vector<double> g_flag, g_inv;   // host: 1.0 = discrete; 1 / range (continuous) or 1 (discrete)
+  double *XgT = nullptr, *XcgT = nullptr, *gflag_dev = nullptr, *ginv_dev = nullptr;
   double *lp_buf = nullptr;     // [Xb (nb x d) | r (nb) | s (nb)], own allocation of lp_cap rows
   int lp_cap = 0, lp_nb = 0, lp_transform = 0;
 };
@@ -201,6 +206,10 @@ static size_t carve(int n_cap, int d, int p, int cb, gpb_model *m, char *base) {
   take(np * (size_t)p, m ? &m->z : nullptr);
   take(d, m ? &m->ls_dev : nullptr);
   take(d, m ? &m->inv_ls_dev : nullptr);
+  take(np * (size_t)d, m ? &m->XgT : nullptr);
+  take((size_t)cb * d, m ? &m->XcgT : nullptr);
+  take(d, m ? &m->gflag_dev : nullptr);
+  take(d, m ? &m->ginv_dev : nullptr);
   take(d + 16, m ? &m->scal : nullptr);
   take((size_t)cb * d, m ? &m->Xc : nullptr);
   take((size_t)cb * d, m ? &m->XcT : nullptr);
@@ -345,6 +354,35 @@ int gpb_model_set_data(gpb_model *m, int n, const double *X, const double *Y, in
   return 0;
 }
 
+int gpb_model_set_gower(gpb_model *m, int enable, const int *discrete, const double *ranges) {
+  GPB_REQUIRE(m, "set_gower: NULL model");
+  GPB_TRY(check_device(m, "set_gower"));
+  m->scaled_valid = false;
+  m->fitted = false;
+  m->have_wi = false;
+  if (!enable) {
+    m->gower = false;
+    return 0;
+  }
+  GPB_REQUIRE(discrete && ranges, "set_gower: NULL argument");
+  const int d = m->d;
+  m->g_flag.assign(d, 0.0);
+  m->g_inv.assign(d, 1.0);
+  for (int q = 0; q < d; ++q) {
+    if (discrete[q]) {
+      m->g_flag[q] = 1.0;
+    } else {
+      GPB_REQUIRE(ranges[q] > 0 && std::isfinite(ranges[q]), "set_gower: range of continuous dimension %d must be positive", q);
+      m->g_inv[q] = ranges[q];   // scale_transpose divides by its scale vector
+    }
+  }
+  GPB_CUDA(cudaMemcpyAsync(m->gflag_dev, m->g_flag.data(), d * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  GPB_CUDA(cudaMemcpyAsync(m->ginv_dev, m->g_inv.data(), d * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+  GPB_CUDA(cudaStreamSynchronize(m->stream));
+  m->gower = true;
+  return 0;
+}
+
 int gpb_model_set_theta(gpb_model *m, double variance, const double *lengthscale, double noise) {
   GPB_REQUIRE(m && lengthscale, "set_theta: NULL argument");
   m->variance = variance;
@@ -360,8 +398,19 @@ static int ensure_scaled(gpb_model *m) {
   if (m->scaled_valid) return 0;
   GPB_TRY(upload_ls(m->ls.data(), m->nls, m->d, m->ls_dev, m->inv_ls_dev, m->stream));
   GPB_TRY(launch_scale_transpose(m->X, m->n, m->d, m->ls_dev, m->XsT, m->np, m->stream));
+  if (m->gower) GPB_TRY(launch_scale_transpose(m->X, m->n, m->d, m->ginv_dev, m->XgT, m->np, m->stream, 1));
   m->scaled_valid = true;
   return 0;
+}
+
+// Coordinates, flags and variance factor the covariance kernel reads: Euclidean scaled (default) or the Gower set.
+struct KCoords {
+  const double *XT, *gflag;
+  double var;
+};
+static KCoords train_coords(const gpb_model *m) {
+  if (!m->gower) return {m->XsT, nullptr, m->variance};
+  return {m->XgT, m->gflag_dev, std::pow(m->variance, m->d)};
 }
 
 static int ensure_wi(gpb_model *m) {
@@ -393,8 +442,9 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
   GPB_TRY(ensure_scaled(m));
   const int n = m->n, np = m->np, d = m->d, p = m->p;
   // Ky = K + (noise + 1e-8 [+ jitter]) I     exact_gaussian_inference.py:55-56
-  GPB_TRY(launch_kmat(m->kind, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np,
-                      np, m->stream));
+  const KCoords kc = train_coords(m);
+  GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, d, n, n, kc.var, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np, np,
+                      m->stream, kc.gflag));
   // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
   const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / 8) : 0;
   if (m->ov && fork_min_n > 0 && np >= fork_min_n) {
@@ -421,6 +471,10 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
     GPB_TRY(ensure_wi(m));
     GPB_TRY(launch_kgrad(m->kind, 1, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->f.W, np, m->alpha, np, p, m->gpart,
                          m->scal + 2, m->stream));
+    // Gower patch: only the variance term sees the patched K (stationary.py:224); it overwrites kgrad's Euclidean one
+    if (m->gower)
+      GPB_TRY(launch_kvar_gower(m->kind, 1, kc.XT, np, kc.XT, np, d, n, n, kc.var, kc.gflag, m->f.W, np, m->alpha, np, p, m->gpart,
+                                m->scal + 2, m->stream));
   }
   GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 4) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   GPB_CUDA(cudaMemcpyAsync(m->pinned + 128, m->f.info, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -481,7 +535,8 @@ int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) 
   } else if (w == "K") {
     GPB_REQUIRE(m->have_data, "get: no data");
     GPB_TRY(ensure_scaled(m));
-    GPB_TRY(launch_kmat(m->kind, m->XsT, np, m->XsT, np, m->d, n, n, m->variance, 0.0, 0, ddst, ldd, np, np, s));
+    const KCoords kc = train_coords(m);
+    GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, m->d, n, n, kc.var, 0.0, 0, ddst, ldd, np, np, s, kc.gflag));
   } else {
     unpack_cols_kernel<<<(n * p + 255) / 256, 256, 0, s>>>(m->alpha, n, p, np, ddst);
   }
@@ -504,7 +559,13 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   GPB_CUDA(cudaMemcpyAsync(m->Xc, Xc, (size_t)mcb * d * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
   GPB_TRY(launch_scale_transpose(m->Xc, mcb, d, m->ls_dev, m->XcT, cpad, s));
   // KxT[c][n] = k(x*_c, x_n)                                        posterior.py:275 (stored transposed)
-  GPB_TRY(launch_kmat(m->kind, m->XcT, cpad, m->XsT, np, d, mcb, n, m->variance, 0.0, 2, m->KxT, np, cpad, np, s));
+  const KCoords kc = train_coords(m);
+  const double *XcK = m->XcT;
+  if (m->gower) {
+    GPB_TRY(launch_scale_transpose(m->Xc, mcb, d, m->ginv_dev, m->XcgT, cpad, s, 1));
+    XcK = m->XcgT;
+  }
+  GPB_TRY(launch_kmat(m->kind, XcK, cpad, kc.XT, np, d, mcb, n, kc.var, 0.0, 2, m->KxT, np, cpad, np, s, kc.gflag));
   // mu = Kx^T alpha                                                 posterior.py:276
   GPB_TRY(launch_rowdot(m->KxT, np, mcb, n, m->alpha, np, p, m->mu, s));
   // A handful of candidates (the M = 1 calls of the L-BFGS-B refinement, optimizer.py:46-51): one bandwidth-bound pass over
@@ -574,8 +635,10 @@ int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int inclu
   // cov = Kxx - tmp^T tmp (+ noise I)      posterior.py:281-284, gaussian.py:104-107
   DevBuf cbuf;
   GPB_TRY(cbuf.alloc((size_t)cpad * cpad * sizeof(double)));
-  GPB_TRY(launch_kmat(m->kind, m->XcT, cpad, m->XcT, cpad, m->d, mc, mc, m->variance, include_likelihood ? m->noise : 0.0, 1,
-                      cbuf.d(), cpad, cpad, cpad, s));
+  const KCoords kc = train_coords(m);
+  const double *XcK = m->gower ? m->XcgT : m->XcT;
+  GPB_TRY(launch_kmat(m->kind, XcK, cpad, XcK, cpad, m->d, mc, mc, kc.var, include_likelihood ? m->noise : 0.0, 1, cbuf.d(), cpad,
+                      cpad, cpad, s, kc.gflag));
   GemmArgs g{m->Vt, np, m->Vt, np, cbuf.d(), cpad, cpad, cpad, np, -1.0, 1.0, 0, 0, 0};
   GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, s));
   GPB_TRY(copy_out(mu, m->mu, (size_t)mc * m->p, dev, s));
@@ -798,6 +861,106 @@ int gpb_kern_K(int kind, int d, int n, const double *X, int m, const double *X2,
     GPB_CUDA(cudaMemcpy2DAsync(K, (size_t)ldk * sizeof(double), Kd, (size_t)ld * sizeof(double), (size_t)cols * sizeof(double), n,
                                cudaMemcpyDeviceToHost, s));
   GPB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// Gower coordinates for the stateless Kern calls: XaT / XbT = x / range (continuous) or x (discrete), flags on the device
+struct GowerTmp {
+  DevBuf xa, xb, xat, xbt, par;
+  double *XaT = nullptr, *XbT = nullptr, *gflag = nullptr;
+  int npa = 0, npb = 0;
+};
+
+static int gower_prepare(GowerTmp &t, int d, int n, const double *X, int m, const double *X2, const int *discrete, const double *ranges,
+                         int dev, cudaStream_t s) {
+  GPB_REQUIRE(X && discrete && ranges && d >= 1 && d <= 96 && n >= 1, "kern (Gower): bad arguments");
+  GPB_REQUIRE(gpb_device_count() > 0, "kern: no CUDA device visible -- libgpb200 has no CPU fallback");
+  std::vector<double> h(2 * d);
+  for (int q = 0; q < d; ++q) {
+    h[q] = discrete[q] ? 1.0 : 0.0;
+    h[d + q] = discrete[q] ? 1.0 : ranges[q];
+    GPB_REQUIRE(h[d + q] > 0, "kern (Gower): range of continuous dimension %d must be positive", q);
+  }
+  GPB_TRY(t.par.alloc(2 * d * sizeof(double)));
+  GPB_CUDA(cudaMemcpyAsync(t.par.p, h.data(), 2 * d * sizeof(double), cudaMemcpyHostToDevice, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  t.gflag = t.par.d();
+  const double *scale = t.par.d() + d, *Xa = nullptr, *Xb = nullptr;
+  t.npa = round_up(n, TILE);
+  GPB_TRY(to_device(t.xa, X, (size_t)n * d, dev, &Xa, s));
+  GPB_TRY(t.xat.alloc((size_t)d * t.npa * sizeof(double)));
+  t.XaT = t.xat.d();
+  GPB_TRY(launch_scale_transpose(Xa, n, d, scale, t.XaT, t.npa, s, 1));
+  if (X2) {
+    GPB_REQUIRE(m >= 1, "kern: X2 given with m = %d", m);
+    t.npb = round_up(m, TILE);
+    GPB_TRY(to_device(t.xb, X2, (size_t)m * d, dev, &Xb, s));
+    GPB_TRY(t.xbt.alloc((size_t)d * t.npb * sizeof(double)));
+    t.XbT = t.xbt.d();
+    GPB_TRY(launch_scale_transpose(Xb, m, d, scale, t.XbT, t.npb, s, 1));
+  } else {
+    t.npb = t.npa;
+    t.XbT = t.XaT;
+  }
+  return 0;
+}
+
+int gpb_kern_K_gower(int kind, int d, int n, const double *X, int m, const double *X2, double variance, const int *discrete,
+                     const double *ranges, double *K, int ldk, int dev, void *stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GPB_REQUIRE(K != nullptr, "kern_K: K is NULL");
+  GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "kern_K: unknown kernel kind %d", kind);
+  GowerTmp t;
+  GPB_TRY(gower_prepare(t, d, n, X, m, X2, discrete, ranges, dev, s));
+  const int cols = X2 ? m : n;
+  GPB_REQUIRE(ldk >= cols, "kern_K: ldk too small");
+  DevBuf out;
+  double *Kd = K;
+  int ld = ldk;
+  if (!dev) {
+    GPB_TRY(out.alloc((size_t)n * cols * sizeof(double)));
+    Kd = out.d();
+    ld = cols;
+  }
+  GPB_TRY(launch_kmat(kind, t.XaT, t.npa, t.XbT, t.npb, d, n, cols, std::pow(variance, d), 0.0, 0, Kd, ld, t.npa, t.npb, s, t.gflag));
+  if (!dev)
+    GPB_CUDA(cudaMemcpy2DAsync(K, (size_t)ldk * sizeof(double), Kd, (size_t)ld * sizeof(double), (size_t)cols * sizeof(double), n,
+                               cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
+                                   double variance, const double *lengthscale, int nls, double *out, int dev, void *stream);
+
+int gpb_kern_update_gradients_full_gower(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
+                                         double variance, const double *lengthscale, int nls, const int *discrete,
+                                         const double *ranges, double *out, int dev, void *stream) {
+  // lengthscale terms: the reference keeps the Euclidean distance under the patch (stationary.py:227-238)
+  GPB_TRY(gpb_kern_update_gradients_full(kind, d, n, X, m, X2, dL_dK, ld, variance, lengthscale, nls, out, dev, stream));
+  // variance term: sum(K_gower * dL_dK) / variance (stationary.py:224 with the patched K)
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  GowerTmp t;
+  GPB_TRY(gower_prepare(t, d, n, X, m, X2, discrete, ranges, dev, s));
+  const int cols = X2 ? m : n;
+  DevBuf gbuf, part, res;
+  const double *G = dL_dK;
+  int ldg = ld;
+  if (!dev) {
+    GPB_TRY(gbuf.alloc((size_t)n * cols * sizeof(double)));
+    GPB_CUDA(cudaMemcpy2DAsync(gbuf.p, (size_t)cols * sizeof(double), dL_dK, (size_t)ld * sizeof(double), (size_t)cols * sizeof(double), n,
+                               cudaMemcpyHostToDevice, s));
+    G = gbuf.d();
+    ldg = cols;
+  }
+  GPB_TRY(part.alloc(kgrad_part_doubles(t.npa, t.npb, d, 0) * sizeof(double)));
+  GPB_TRY(res.alloc(sizeof(double)));
+  GPB_TRY(launch_kvar_gower(kind, 0, t.XaT, t.npa, t.XbT, t.npb, d, n, cols, std::pow(variance, d), t.gflag, G, ldg, nullptr, 0, 1,
+                            part.d(), res.d(), s));
+  double h = 0.0;
+  GPB_CUDA(cudaMemcpyAsync(&h, res.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+  GPB_CUDA(cudaStreamSynchronize(s));
+  out[0] = h / variance;
   return 0;
 }
 

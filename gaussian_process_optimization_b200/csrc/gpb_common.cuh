@@ -102,6 +102,24 @@ __device__ __forceinline__ void cov_k_dk(double r2, double variance, double &k, 
   }
 }
 
+// ---- Gower product kernel (stationary.py:116-135): accumulate over dimensions, then evaluate once ---------------------------
+// RBF:      s += r^2                       value = vpow exp(-s / 2)
+// Matern52: s += r, p *= 1 + s5 r + 5/3 r^2  value = vpow p exp(-s5 s)
+template <int KIND>
+__device__ __forceinline__ void gower_accumulate(double r, double &s, double &p) {
+  if (KIND == GPB_KERN_RBF) {
+    s = fma(r, r, s);
+  } else {
+    s += r;
+    p *= fma(r, fma(5.0 / 3.0, r, SQRT5), 1.0);
+  }
+}
+template <int KIND>
+__device__ __forceinline__ double gower_value(double s, double p, double vpow) {
+  if (KIND == GPB_KERN_RBF) return vpow * exp(-0.5 * s);
+  return vpow * p * exp(-SQRT5 * s);
+}
+
 // ---- reductions -----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -28,7 +28,7 @@ __global__ void scale_transpose_kernel(const double *__restrict__ X, int n, int 
   }
 }
 
-int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, double *XsT, int ldx, cudaStream_t s) {
+int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, double *XsT, int ldx, cudaStream_t s, int /*tag*/) {
   const size_t total = (size_t)d * ldx;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -48,10 +48,15 @@ int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, 
 //   mode 2 (rect, zero padded): out is rows_pad x cols_pad; k inside n_rows x n_cols, 0 outside
 //   mode 3 = mode 1 restricted to the 128-blocks on and below the diagonal (input of the factorisation)
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KIND>
+// GOWER = 1: the reference's local "Gower" patch (stationary.py:116-135) -- a product of one-dimensional kernels,
+// r_q = |dx_q| / range_q on continuous dimensions (XaT / XbT then hold x_q / range_q) and r_q = [x_q != x'_q] on discrete ones
+// (gflag[q] != 0; coordinates unscaled).  Every factor carries the variance: `variance` is then variance^d (vpow).
+//   Matern52: prod_q (1 + s5 r_q + 5/3 r_q^2) * exp(-s5 sum_q r_q)        RBF: exp(-1/2 sum_q r_q^2)
+// -- one exp per pair instead of d.
+template <int KIND, int GOWER>
 __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
                                                       int n_rows, int n_cols, double variance, double diag_add, int mode,
-                                                      double *__restrict__ out, int ldo) {
+                                                      double *__restrict__ out, int ldo, const double *__restrict__ gflag) {
   extern __shared__ double sm[];
   double *xa = sm;              // [d][64]
   double *xb = sm + d * KTILE;  // [d][64]
@@ -69,11 +74,14 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__
     xb[e] = XbT[(size_t)q * ldb + col0 + i];
   }
   __syncthreads();
-  double r2[4][4];
+  double r2[4][4], pr[GOWER ? 4 : 1][GOWER ? 4 : 1];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) r2[a][b] = 0.0;
+    for (int b = 0; b < 4; ++b) {
+      r2[a][b] = 0.0;
+      if (GOWER) pr[a][b] = 1.0;
+    }
 #pragma unroll 2
   for (int q = 0; q < d; ++q) {
     double va[4], vb[4];
@@ -81,12 +89,18 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__
     for (int a = 0; a < 4; ++a) va[a] = xa[q * KTILE + ty + 16 * a];
 #pragma unroll
     for (int b = 0; b < 4; ++b) vb[b] = xb[q * KTILE + tx + 16 * b];
+    const bool disc = GOWER ? (gflag[q] != 0.0) : false;
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const double df = va[a] - vb[b];
-        r2[a][b] = fma(df, df, r2[a][b]);
+        if (!GOWER) {
+          r2[a][b] = fma(df, df, r2[a][b]);
+        } else {
+          const double r = disc ? (df != 0.0 ? 1.0 : 0.0) : fabs(df);
+          gower_accumulate<KIND>(r, r2[a][b], pr[a][b]);
+        }
       }
   }
 #pragma unroll
@@ -98,7 +112,7 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__
       const bool inside = (i < n_rows) && (j < n_cols);
       double v;
       if (inside) {
-        v = cov_k<KIND>(r2[a][b], variance);
+        v = GOWER ? gower_value<KIND>(r2[a][b], pr[GOWER ? a : 0][GOWER ? b : 0], variance) : cov_k<KIND>(r2[a][b], variance);
         if (mode == 1 && i == j) v += diag_add;
       } else {
         v = (mode == 1 && i == j) ? 1.0 : 0.0;
@@ -110,21 +124,25 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__
 
 int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                 double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
-                cudaStream_t s) {
+                cudaStream_t s, const double *gflag) {
   const size_t smem = (size_t)2 * d * KTILE * sizeof(double);
   GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large", d);
   GPB_REQUIRE(rows_pad % KTILE == 0 && cols_pad % KTILE == 0, "kmat: padded sizes must be multiples of %d", KTILE);
   dim3 grid(cols_pad / KTILE, rows_pad / KTILE);
   if (grid.x == 0 || grid.y == 0) return 0;
+#define GPB_KMAT(K_, G_)                                                                                                  \
+  do {                                                                                                                    \
+    if (smem > 48 * 1024)                                                                                                 \
+      GPB_CUDA(cudaFuncSetAttribute(kmat_kernel<K_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    kmat_kernel<K_, G_><<<grid, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, diag_add, mode, out, ldo, \
+                                                gflag);                                                                   \
+  } while (0)
   if (kind == GPB_KERN_RBF) {
-    if (smem > 48 * 1024)
-      GPB_CUDA(cudaFuncSetAttribute(kmat_kernel<GPB_KERN_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kmat_kernel<GPB_KERN_RBF><<<grid, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, diag_add, mode, out, ldo);
+    if (gflag) GPB_KMAT(GPB_KERN_RBF, 1); else GPB_KMAT(GPB_KERN_RBF, 0);
   } else {
-    if (smem > 48 * 1024)
-      GPB_CUDA(cudaFuncSetAttribute(kmat_kernel<GPB_KERN_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kmat_kernel<GPB_KERN_MATERN52><<<grid, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, diag_add, mode, out, ldo);
+    if (gflag) GPB_KMAT(GPB_KERN_MATERN52, 1); else GPB_KMAT(GPB_KERN_MATERN52, 0);
   }
+#undef GPB_KMAT
   count_launch();
   GPB_CHECK_LAUNCH();
   return 0;
@@ -279,6 +297,112 @@ __global__ void colsum_kernel(const double *__restrict__ part, int ntiles, int n
   for (int t = threadIdx.x; t < ntiles; t += 256) acc += part[(size_t)t * ncols + c];
   acc = block_sum<256>(acc, scratch);
   if (threadIdx.x == 0) out[c] = acc;
+}
+
+// Gower variant of the variance-gradient term only:  part[tile] = sum w K_gower,ij G_ij  (stationary.py:224 with the patched K;
+// the lengthscale terms keep the Euclidean distance in the reference, so kgrad_kernel still produces them).
+template <int KIND, int FUSED>
+__global__ void __launch_bounds__(256, 3) kvar_gower_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb,
+                                                            int d, int n_rows, int n_cols, double vpow, const double *__restrict__ gflag,
+                                                            const double *__restrict__ G, int ldg, const double *__restrict__ alpha,
+                                                            int ld_alpha, int p_out, int tiles_x, double *__restrict__ part) {
+  extern __shared__ double sm[];
+  double *xa = sm, *xb = sm + d * KTILE, *wacc = xb + d * KTILE;
+  int tr, tc;
+  if (FUSED) {
+    const int t = blockIdx.x;
+    tr = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+    while (tr * (tr + 1) / 2 > t) --tr;
+    tc = t - tr * (tr + 1) / 2;
+  } else {
+    tr = blockIdx.x / tiles_x;
+    tc = blockIdx.x - tr * tiles_x;
+  }
+  const int row0 = tr * KTILE, col0 = tc * KTILE;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < d * KTILE; e += 256) {
+    const int q = e >> 6, i = e & 63;
+    xa[e] = XaT[(size_t)q * lda + row0 + i];
+    xb[e] = XbT[(size_t)q * ldb + col0 + i];
+  }
+  __syncthreads();
+  double sacc[4][4], pr[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      sacc[a][b] = 0.0;
+      pr[a][b] = 1.0;
+    }
+  for (int q = 0; q < d; ++q) {
+    const bool disc = gflag[q] != 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double df = xa[q * KTILE + ty + 16 * a] - xb[q * KTILE + tx + 16 * b];
+        const double r = disc ? (df != 0.0 ? 1.0 : 0.0) : fabs(df);
+        gower_accumulate<KIND>(r, sacc[a][b], pr[a][b]);
+      }
+  }
+  const double wt = (FUSED && tr != tc) ? 2.0 : 1.0;
+  double acc = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = row0 + ty + 16 * a;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = col0 + tx + 16 * b;
+      if (i < n_rows && j < n_cols) {
+        double g = G[(size_t)i * ldg + j];
+        if (FUSED) {
+          double aa = 0.0;
+          for (int p = 0; p < p_out; ++p) aa = fma(alpha[(size_t)p * ld_alpha + i], alpha[(size_t)p * ld_alpha + j], aa);
+          g = 0.5 * (aa - (double)p_out * g);
+        }
+        acc = fma(wt * gower_value<KIND>(sacc[a][b], pr[a][b], vpow), g, acc);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) wacc[warp] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += wacc[w];
+    part[blockIdx.x] = s;
+  }
+}
+
+// out_dev[0] = sum K_gower . G  (part: scratch of `tiles` doubles)
+int launch_kvar_gower(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
+                      double vpow, const double *gflag, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out,
+                      double *part, double *out_dev, cudaStream_t s) {
+  const size_t smem = (size_t)(2 * d * KTILE + 8) * sizeof(double);
+  GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large", d);
+  const int tr = (n_rows + KTILE - 1) / KTILE, tc = (n_cols + KTILE - 1) / KTILE;
+  const int tiles = fused ? tr * (tr + 1) / 2 : tr * tc;
+  if (tiles == 0) return 0;
+#define GPB_KV(K_, F_)                                                                                                     \
+  do {                                                                                                                     \
+    if (smem > 48 * 1024)                                                                                                  \
+      GPB_CUDA(cudaFuncSetAttribute(kvar_gower_kernel<K_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    kvar_gower_kernel<K_, F_><<<tiles, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, vpow, gflag, G, ldg, alpha,    \
+                                                       ld_alpha, p_out, tc, part);                                          \
+  } while (0)
+  if (kind == GPB_KERN_RBF) {
+    if (fused) GPB_KV(GPB_KERN_RBF, 1); else GPB_KV(GPB_KERN_RBF, 0);
+  } else {
+    if (fused) GPB_KV(GPB_KERN_MATERN52, 1); else GPB_KV(GPB_KERN_MATERN52, 0);
+  }
+#undef GPB_KV
+  GPB_CHECK_LAUNCH();
+  colsum_kernel<<<1, 256, 0, s>>>(part, tiles, 1, out_dev);
+  count_launch(2);
+  GPB_CHECK_LAUNCH();
+  return 0;
 }
 
 int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,

@@ -11,13 +11,20 @@ inline size_t kgrad_part_doubles(int rows_pad, int cols_pad, int d, int fused) {
   return (fused ? tr * (tr + 1) / 2 : tr * tc) * (size_t)(d + 2);
 }
 
-int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, double *XsT, int ldx, cudaStream_t s);
+// XsT[q][i] = X[i][q] / scale[q] (zero padded to ldx); tag is informational (0 lengthscales, 1 Gower ranges)
+int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, double *XsT, int ldx, cudaStream_t s, int tag = 0);
 
 // mode: 0 rect exact, 1 padded Ky (identity outside n x n, diag_add on the diagonal), 2 rect zero padded,
 //       3 = 1 but only the 128-blocks on / below the diagonal (what the factorisation reads)
+// gflag != NULL: the Gower product kernel (coordinates pre-divided by the ranges on continuous dimensions, gflag[q] != 0 marks
+// a discrete dimension, `variance` is variance^d)
 int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                 double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
-                cudaStream_t s);
+                cudaStream_t s, const double *gflag = nullptr);
+// out_dev[0] = sum K_gower . G  (variance-gradient term under the Gower patch); part: tiles doubles
+int launch_kvar_gower(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
+                      double vpow, const double *gflag, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out,
+                      double *part, double *out_dev, cudaStream_t s);
 
 // out_dev[0] = sum K.G, out_dev[1] = tr G (fused only), out_dev[2+q] = sum (k'/r) G ds_q^2.
 // part: scratch of tiles * (d + 2) doubles.

@@ -78,6 +78,25 @@ def get_quantiles(acquisition_par, fmin, m, s):
     return (phi, Phi, u)
 
 
+class DuplicateManager(object):
+    """util/duplicate_manager.py:7-41: the set of configurations already evaluated / pending / black-listed."""
+
+    def __init__(self, space, zipped_X, pending_zipped_X=None, ignored_zipped_X=None):
+        self.space = space
+        self.unique_points = set()
+        self.unique_points.update(tuple(x.flatten()) for x in zipped_X)
+        if np.any(pending_zipped_X):
+            self.unique_points.update(tuple(x.flatten()) for x in pending_zipped_X)
+        if np.any(ignored_zipped_X):
+            self.unique_points.update(tuple(x.flatten()) for x in ignored_zipped_X)
+
+    def is_zipped_x_duplicate(self, zipped_x):
+        return tuple(zipped_x.flatten()) in self.unique_points
+
+    def is_unzipped_x_duplicate(self, unzipped_x):
+        return self.is_zipped_x_duplicate(self.space.zip_inputs(np.atleast_2d(unzipped_x)))
+
+
 def constant_cost_withGradients(x):
     """core/task/cost.py:76-80."""
     return np.ones(x.shape[0])[:, None], np.zeros(x.shape)
@@ -169,6 +188,11 @@ class Design_space(object):
         for v in self.space_expanded:
             b += v.get_bounds()
         return b
+
+    def lengthscales(self):
+        """core/task/space.py:351-362 (local patch of the reference): the domain width of every continuous variable, in order --
+        the per-dimension scales of the Gower kernel."""
+        return [v.domain[-1] - v.domain[0] for v in self.space if v.type == 'continuous']
 
     def get_continuous_bounds(self):
         return [tuple(v.domain) for v in self.space if v.type == 'continuous']
@@ -314,8 +338,7 @@ class GPModel(BOModel):
                  sparse=False, num_inducing=10, verbose=True, ARD=False, Gower=False, space=None, distributed_restarts=False):
         if sparse:
             raise NotImplementedError("sparse GPs are outside the B200 hot path (exact N x N on one GPU)")
-        if Gower:
-            raise NotImplementedError("the Gower kernel patch is outside the B200 hot path")
+        self.Gower, self.space = Gower, space
         self.kernel, self.noise_var, self.exact_feval = kernel, noise_var, exact_feval
         self.optimize_restarts, self.optimizer, self.max_iters, self.verbose = optimize_restarts, optimizer, max_iters, verbose
         self.sparse, self.num_inducing, self.model, self.ARD = sparse, num_inducing, None, ARD
@@ -331,7 +354,7 @@ class GPModel(BOModel):
         """gpmodel.py:50-76."""
         self.input_dim = X.shape[1]
         if self.kernel is None:
-            kern = _kern.Matern52(self.input_dim, variance=1., ARD=self.ARD)
+            kern = _kern.Matern52(self.input_dim, variance=1., ARD=self.ARD, Gower=self.Gower, space=self.space)
         else:
             kern = self.kernel
             self.kernel = None
@@ -683,6 +706,8 @@ class OptLbfgs(object):
 def apply_optimizer(optimizer, x0, f=None, df=None, f_df=None, duplicate_manager=None, context_manager=None, space=None):
     """optimization/optimizer.py:130-168 without context variables."""
     x0 = np.atleast_2d(x0)
+    if duplicate_manager and duplicate_manager.is_unzipped_x_duplicate(x0):
+        raise ValueError("The starting point of the optimizer cannot be a duplicate.")
 
     # OptimizationWithContext.f_nc / f_df_nc (optimizer.py:200-232): SciPy hands the objective a 1-D x; the reference always
     # routes it through these wrappers (a ContextManager exists even without context), so acquisitions only ever see 2-D input
@@ -693,6 +718,8 @@ def apply_optimizer(optimizer, x0, f=None, df=None, f_df=None, duplicate_manager
     f_df_nc = None if f_df is None else (lambda x: f_df(np.atleast_2d(x)))
     optimized_x, _ = optimizer.optimize(x0, f_nc, df, f_df_nc)
     suggested_x_rounded = space.round_optimum(optimized_x)
+    if duplicate_manager and duplicate_manager.is_unzipped_x_duplicate(suggested_x_rounded):
+        return x0, np.atleast_2d(f(x0))            # optimizer.py:163-164: fall back to the (non-duplicate) anchor
     return suggested_x_rounded, f(suggested_x_rounded)
 
 
@@ -707,7 +734,17 @@ class ObjectiveAnchorPointsGenerator(object):
 
     def get(self, num_anchor=5, duplicate_manager=None, unique=False, context_manager=None):
         X = initial_design(self.design_type, self.space, self.num_samples)
+        if unique:
+            X = np.vstack(sorted(list({tuple(x) for x in X})))
         X = self.space.unzip_inputs(X)
+        if duplicate_manager:                                          # anchor_points_generator.py:44-58
+            keep = [i for i, x in enumerate(X) if not duplicate_manager.is_unzipped_x_duplicate(x)]
+            if not keep:
+                raise FullyExploredOptimizationDomainError("No anchor points could be generated ({} used samples, {} requested "
+                                                           "anchor points).".format(self.num_samples, num_anchor))
+            if len(keep) < num_anchor:
+                print("Warning: expecting {} anchor points, only {} available.".format(num_anchor, len(keep)))
+            X = X[keep, :]
         scores = self.get_anchor_point_scores(X)
         # np.argsort's default introsort is not stable; ties are resolved towards the lowest index here (and in the oracle)
         return X[np.argsort(scores, kind='stable')[:min(len(scores), num_anchor)], :]
@@ -728,7 +765,8 @@ class AcquisitionOptimizer(object):
         self.f, self.df, self.f_df = f, df, f_df
         self.optimizer = OptLbfgs(self.space.get_bounds())
         anchor_points = ObjectiveAnchorPointsGenerator(self.space, 'random', f).get(duplicate_manager=duplicate_manager)
-        optimized_points = [apply_optimizer(self.optimizer, a, f=f, df=None, f_df=f_df, space=self.space) for a in anchor_points]
+        optimized_points = [apply_optimizer(self.optimizer, a, f=f, df=None, f_df=f_df, duplicate_manager=duplicate_manager,
+                                            space=self.space) for a in anchor_points]
         x_min, fx_min = min(optimized_points, key=lambda t: t[1])
         return x_min, fx_min
 
@@ -818,7 +856,7 @@ class BO(object):
         self.num_acquisitions = 0
         self.context = context
         self._update_model(self.normalization_type)
-        return self._compute_next_evaluations()
+        return self._compute_next_evaluations(pending_zipped_X=pending_X, ignored_zipped_X=ignored_X)
 
     def run_optimization(self, max_iter=0, max_time=np.inf, eps=1e-8, context=None, verbosity=False,
                          save_models_parameters=True, report_file=None, evaluations_file=None, models_file=None):
@@ -876,7 +914,12 @@ class BO(object):
         return np.sqrt(np.sum((self.X[-1, :] - self.X[-2, :]) ** 2))
 
     def _compute_next_evaluations(self, pending_zipped_X=None, ignored_zipped_X=None):
-        return self.space.zip_inputs(self.evaluator.compute_batch(duplicate_manager=None, context_manager=None))
+        """core/bo.py:216-234."""
+        duplicate_manager = None
+        if self.de_duplication:
+            duplicate_manager = DuplicateManager(space=self.space, zipped_X=self.X, pending_zipped_X=pending_zipped_X,
+                                                 ignored_zipped_X=ignored_zipped_X)
+        return self.space.zip_inputs(self.evaluator.compute_batch(duplicate_manager=duplicate_manager, context_manager=None))
 
     def _update_model(self, normalization_type='stats'):
         if self.num_acquisitions % self.model_update_interval == 0:
@@ -906,8 +949,6 @@ class BayesianOptimization(BO):
         self.initial_iter = True
         self.verbosity, self.verbosity_model = verbosity, verbosity_model
         self.model_update_interval, self.de_duplication, self.kwargs = model_update_interval, de_duplication, kwargs
-        if de_duplication:
-            raise NotImplementedError("de_duplication is host-side set bookkeeping outside the B200 hot path")
         self.constraints, self.domain = constraints, domain
         self.space = Design_space(self.domain, self.constraints)
         self.maximize = maximize
@@ -949,9 +990,10 @@ class BayesianOptimization(BO):
         if self.model_type != 'GP':
             raise NotImplementedError("model_type %r is outside the B200 hot path" % (self.model_type,))
         kw = self.kwargs
+        Gower = kw.get('Gower', False)
         return GPModel(kw.get('kernel', None), kw.get('noise_var', None), self.exact_feval, kw.get('model_optimizer_type', 'lbfgs'),
                        kw.get('max_iters', 1000), kw.get('optimize_restarts', 5), False, kw.get('num_inducing', 10),
-                       kw.get('verbosity_model', False), kw.get('ARD', False))
+                       kw.get('verbosity_model', False), kw.get('ARD', False), Gower, self.space if Gower is True else None)
 
     def _acquisition_chooser(self):
         """util/arguments_manager.py:42-75 (jitter 0.01, weight 2)."""

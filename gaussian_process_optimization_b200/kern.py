@@ -58,8 +58,9 @@ class Stationary(Kern):
 
     def __init__(self, input_dim, variance, lengthscale, ARD, active_dims, name, useGPU=False, Gower=False, space=None):
         super(Stationary, self).__init__(input_dim, active_dims, name, useGPU=useGPU)
-        if Gower:
-            raise NotImplementedError("the Gower mixed-variable branch (stationary.py:116-135) is outside the B200 hot path")
+        # the reference's local mixed-variable patch (stationary.py:61-65,116-135): active when Gower and a design space are given
+        self.Gower = bool(Gower)
+        self.space = space
         self.ARD = bool(ARD)
         if not ARD:
             if lengthscale is None:
@@ -80,12 +81,22 @@ class Stationary(Kern):
         assert self.variance.size == 1
         self.link_parameters(self.variance, self.lengthscale)   # link order = order in m[:] (stationary.py:83)
 
+    def gower_config(self):
+        """(continuous dims, discrete dims, ranges of the continuous dims) when the Gower branch of K is active
+        (stationary.py:116-119: `self.Gower and self.space is not None`), else None."""
+        if not (self.Gower and self.space is not None):
+            return None
+        return (list(self.space.get_continuous_dims()), list(self.space.get_discrete_dims()), list(self.space.lengthscales()))
+
     # -- Kern contract ---------------------------------------------------------------------------------------------------
     def K(self, X, X2=None):
-        """stationary.py:107-140."""
+        """stationary.py:107-140 (Gower branch :116-135)."""
         X = np.asarray(X, dtype=np.float64)
         X2 = None if X2 is None else np.asarray(X2, dtype=np.float64)
         self._check(X, X2)
+        gw = self.gower_config()
+        if gw is not None:
+            return native.kern_K_gower(self._kind, X, X2, float(self.variance.values[0]), gw)
         return native.kern_K(self._kind, X, X2, float(self.variance.values[0]), self.lengthscale.values)
 
     def Kdiag(self, X):
@@ -99,8 +110,13 @@ class Stationary(Kern):
         X = np.asarray(X, dtype=np.float64)
         X2 = None if X2 is None else np.asarray(X2, dtype=np.float64)
         self._check(X, X2)
-        dv, dl = native.kern_update_gradients_full(self._kind, np.asarray(dL_dK, dtype=np.float64), X, X2,
-                                                   float(self.variance.values[0]), self.lengthscale.values)
+        gw = self.gower_config()
+        if gw is not None:   # the patched K only enters the variance term; lengthscale terms stay Euclidean (stationary.py:224-238)
+            dv, dl = native.kern_update_gradients_full_gower(self._kind, np.asarray(dL_dK, dtype=np.float64), X, X2,
+                                                             float(self.variance.values[0]), self.lengthscale.values, gw)
+        else:
+            dv, dl = native.kern_update_gradients_full(self._kind, np.asarray(dL_dK, dtype=np.float64), X, X2,
+                                                       float(self.variance.values[0]), self.lengthscale.values)
         self.variance.gradient = dv
         self.lengthscale.gradient = dl if self.ARD else dl[0]
 
@@ -130,8 +146,9 @@ class Stationary(Kern):
         return self.variance.values * np.ones(self.input_dim) / self.lengthscale.values ** 2
 
     def copy(self):
+        kw = {"Gower": self.Gower, "space": self.space} if self.Gower else {}
         c = self.__class__(self.input_dim, variance=float(self.variance.values[0]), lengthscale=self.lengthscale.values.copy(),
-                           ARD=self.ARD, name=self.name)
+                           ARD=self.ARD, name=self.name, **kw)
         for src, dst in ((self.variance, c.variance), (self.lengthscale, c.lengthscale)):
             dst._constraint, dst._fixed = src._constraint, src._fixed
         return c

@@ -201,6 +201,11 @@ class ExactGaussianInference(object):
             nat.set_data(X, Y)
             self._data_id, self._data_dirty = data_id, False
             self._data_refs = (X, Y)   # keep the arrays alive so that id() stays unique
+        gw = kern.gower_config()
+        gw_key = None if gw is None else tuple(map(tuple, gw))
+        if getattr(self, "_gower_key", "unset") != (id(nat), gw_key):
+            nat.set_gower(gw)
+            self._gower_key = (id(nat), gw_key)
         nat.set_theta(float(kern.variance.values[0]), kern.lengthscale.values, noise)
         # jitchol (linalg.py:56-75): try as is; on failure raise if the diagonal is not positive, else the jitter ladder
         info, logL, grads = nat.fit(True)

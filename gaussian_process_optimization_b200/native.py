@@ -54,6 +54,54 @@ def kern_update_gradients_full(kind, dL_dK, X, X2, variance, lengthscale):
     return out[0], out[1:].copy()
 
 
+def _gower_args(gower, d):
+    """gower = (continuous dims, discrete dims, ranges of the continuous dims in that order) -> (int flags[d], ranges[d])."""
+    cont, disc, ranges = gower
+    flags = np.zeros(d, dtype=np.int32)
+    rng = np.ones(d)
+    flags[list(disc)] = 1
+    for i, q in enumerate(cont):
+        rng[q] = float(ranges[i])
+    assert len(cont) + len(disc) == d, "every input dimension must be continuous or discrete"
+    return flags, rng
+
+
+def kern_K_gower(kind, X, X2, variance, gower):
+    """Stationary.K under the Gower patch (stationary.py:116-135)."""
+    lib = _lib.require_gpu()
+    X = as_host(X)
+    n, d = X.shape
+    flags, rng = _gower_args(gower, d)
+    if X2 is None:
+        m, X2p, out = 0, None, np.empty((n, n))
+    else:
+        X2 = as_host(X2)
+        m, X2p, out = X2.shape[0], ptr(X2), np.empty((n, X2.shape[0]))
+    check(lib.gpb_kern_K_gower(_kind(kind), d, n, ptr(X), m, X2p, float(variance), flags.ctypes.data_as(_lib.c_int_p), dptr(rng),
+                               ptr(out), out.shape[1], 0, _lib.current_stream()), "kern_K_gower")
+    return out
+
+
+def kern_update_gradients_full_gower(kind, dL_dK, X, X2, variance, lengthscale, gower):
+    """Stationary.update_gradients_full under the Gower patch: patched K in the variance term only (stationary.py:224)."""
+    lib = _lib.require_gpu()
+    X = as_host(X)
+    n, d = X.shape
+    ls = _ls(lengthscale)
+    G = as_host(dL_dK)
+    flags, rng = _gower_args(gower, d)
+    if X2 is None:
+        m, X2p = 0, None
+    else:
+        X2 = as_host(X2)
+        m, X2p = X2.shape[0], ptr(X2)
+    out = np.empty(1 + ls.size)
+    check(lib.gpb_kern_update_gradients_full_gower(_kind(kind), d, n, ptr(X), m, X2p, ptr(G), G.shape[1], float(variance), dptr(ls),
+                                                   ls.size, flags.ctypes.data_as(_lib.c_int_p), dptr(rng), dptr(out), 0,
+                                                   _lib.current_stream()), "update_gradients_full_gower")
+    return out[0], out[1:].copy()
+
+
 def kern_gradients_X(kind, dL_dK, X, X2, variance, lengthscale):
     """Stationary.gradients_X (stationary.py:271-278,354-364)."""
     lib = _lib.require_gpu()
@@ -202,6 +250,14 @@ class NativeModel(object):
         check(self._lib.gpb_model_set_data(self._h, n, ptr(X), ptr(Y), int(dev)), "set_data")
         self.n = n
 
+    def set_gower(self, gower):
+        """Matern52(Gower=True, space=...): gower = (continuous dims, discrete dims, ranges) or None to switch it off."""
+        if gower is None:
+            check(self._lib.gpb_model_set_gower(self._h, 0, None, None), "set_gower")
+            return
+        flags, rng = _gower_args(gower, self.d)
+        check(self._lib.gpb_model_set_gower(self._h, 1, flags.ctypes.data_as(_lib.c_int_p), dptr(rng)), "set_gower")
+
     def set_theta(self, variance, lengthscale, noise):
         ls = _ls(lengthscale)
         assert ls.size == self.nls
@@ -288,7 +344,7 @@ class NativeModel(object):
         if Xb is None:
             check(self._lib.gpb_model_set_penalizers(self._h, t, 0, None, None, None), "set_penalizers")
             return
-        Xb, r, s = as_host(Xb), as_host(r).ravel(), as_host(s).ravel()
+        Xb, r, s = np.atleast_2d(as_host(Xb)), as_host(r).ravel(), as_host(s).ravel()   # run.py:1240-1253 passes one 1-D point
         assert Xb.shape == (r.size, self.d) and s.size == r.size
         check(self._lib.gpb_model_set_penalizers(self._h, t, r.size, ptr(Xb), ptr(r), ptr(s)), "set_penalizers")
 

@@ -51,6 +51,17 @@ int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int 
                                    int ld, double variance, const double *lengthscale, int nls, double *out, int dev,
                                    void *stream);
 
+/* The reference's local "Gower" mixed-variable patch of Stationary.K (GPy/GPy/kern/src/stationary.py:61-65,116-135; enabled by
+ * run.py:1207-1224 through GPyOpt/GPyOpt/models/gpmodel.py:58): K = prod_q k1d(r_q), r_q = |dx_q| / ranges[q] on continuous
+ * dimensions and r_q = [x_q != x'_q] where discrete[q] != 0; the kernel's lengthscale is ignored by K.  The gradient methods
+ * were NOT patched: update_gradients_full only swaps K in the variance term (:224), lengthscale and input gradients keep the
+ * Euclidean distance -- reproduced as it is. */
+int gpb_kern_K_gower(int kind, int d, int n, const double *X, int m, const double *X2, double variance, const int *discrete,
+                     const double *ranges, double *K, int ldk, int dev, void *stream);
+int gpb_kern_update_gradients_full_gower(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK,
+                                         int ld, double variance, const double *lengthscale, int nls, const int *discrete,
+                                         const double *ranges, double *out, int dev, void *stream);
+
 /* Stationary.gradients_X(dL_dK, X, X2=None)  (stationary.py:271-278,354-364 -> stationary_utils.c:1-14 _grad_X).
  * out: n x d. */
 int gpb_kern_gradients_X(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
@@ -78,6 +89,10 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
 int gpb_model_destroy(gpb_model *m);
 /* GP.set_XY (core/gp.py:202-238).  X: n x d, Y: n x p. */
 int gpb_model_set_data(gpb_model *m, int n, const double *X, const double *Y, int dev);
+/* Matern52(..., Gower=True, space=...) (stationary.py:61-65): switch the model's covariance to the Gower product kernel.
+ * discrete[d]: 1 for discrete dimensions; ranges[d]: domain width of the continuous ones (Design_space.lengthscales(),
+ * GPyOpt/GPyOpt/core/task/space.py:351-362).  enable = 0 restores the stationary kernel. */
+int gpb_model_set_gower(gpb_model *m, int enable, const int *discrete, const double *ranges);
 /* parameter write: kern.variance, kern.lengthscale[nls], Gaussian_noise.variance (link order stationary.py:83, gp.py:108-109) */
 int gpb_model_set_theta(gpb_model *m, double variance, const double *lengthscale, double noise);
 /* GP.parameters_changed (core/gp.py:258-271) = ExactGaussianInference.inference (exact_gaussian_inference.py:37-74)

@@ -178,8 +178,32 @@ def dK_dr(kind, r, variance):
     raise ValueError(kind)
 
 
-def K(kind, X, X2, variance, lengthscale, ard=True):
-    """stationary.py:107-140 (non-Gower branch :137-139)"""
+def K_gower(kind, X, X2, variance, gower):
+    """stationary.py:116-135, the local "Gower" patch of the reference: a product of one-dimensional kernels, r = |dx| / range
+    on the continuous dimensions (space.lengthscales(), GPyOpt core/task/space.py:351-362) and r = [x != x'] on the discrete
+    ones.  Every factor carries the variance; the kernel's own lengthscale parameter is ignored.
+    gower = (continuous dims, discrete dims, ranges of the continuous dims in that order)."""
+    const_dims, disc_dims, ranges = gower
+    if X2 is None:
+        X2 = X
+    numDims = X.shape[1]
+    K_1D = [None for _ in range(numDims)]
+    for index, const_dim in enumerate(const_dims):
+        r = abs(X[:, np.newaxis, const_dim] - X2[np.newaxis, :, const_dim]) / ranges[index]
+        K_1D[const_dim] = K_of_r(kind, r, variance)
+    for disc_dim in disc_dims:
+        r = (X[:, np.newaxis, disc_dim] != X2[np.newaxis, :, disc_dim]).astype(int)
+        K_1D[disc_dim] = K_of_r(kind, r, variance)
+    kernel = K_1D[0]
+    for dim in range(numDims - 1):
+        kernel = kernel * K_1D[dim + 1]
+    return kernel
+
+
+def K(kind, X, X2, variance, lengthscale, ard=True, gower=None):
+    """stationary.py:107-140 (Gower branch :116-135 when gower is given, else :137-139)"""
+    if gower is not None:
+        return K_gower(kind, X, X2, variance, gower)
     return K_of_r(kind, scaled_dist(X, X2, lengthscale, ard), variance)
 
 
@@ -221,10 +245,11 @@ def lengthscale_grads_native(tmp, X, X2, lengthscale):
     return -grads / ls ** 3
 
 
-def update_gradients_full(kind, dL_dK, X, X2, variance, lengthscale, ard=True, native=False):
-    """stationary.py:218-238 -> (d/dvariance, d/dlengthscale)."""
+def update_gradients_full(kind, dL_dK, X, X2, variance, lengthscale, ard=True, native=False, gower=None):
+    """stationary.py:218-238 -> (d/dvariance, d/dlengthscale).  With the Gower patch only self.K changes (:224); the
+    lengthscale part keeps using the Euclidean scaled distance (:227-238), exactly as the reference does."""
     ls = _ls(lengthscale)
-    dvar = np.sum(K(kind, X, X2, variance, ls, ard) * dL_dK) / variance
+    dvar = np.sum(K(kind, X, X2, variance, ls, ard, gower) * dL_dK) / variance
     r = scaled_dist(X, X2, ls, ard)
     dL_dr = dK_dr(kind, r, variance) * dL_dK
     if ard:
@@ -286,9 +311,9 @@ class Posterior(object):
         return self._woodbury_inv
 
 
-def exact_inference(kind, X, Y, variance, lengthscale, noise, ard=True, with_Li=False):
+def exact_inference(kind, X, Y, variance, lengthscale, noise, ard=True, with_Li=False, gower=None):
     """exact_gaussian_inference.py:37-74 -> (Posterior, log_marginal, {'dL_dK','dL_dthetaL','dL_dm'})."""
-    Kmat = K(kind, X, None, variance, lengthscale, ard)
+    Kmat = K(kind, X, None, variance, lengthscale, ard, gower)
     Ky = Kmat.copy()
     Ky[np.diag_indices_from(Ky)] += noise + 1e-8                      # :55-56
     Wi, LW, LWi, W_logdet = pdinv(Ky, with_Li=with_Li)               # :58
@@ -299,24 +324,24 @@ def exact_inference(kind, X, Y, variance, lengthscale, noise, ard=True, with_Li=
     return Posterior(LW, alpha, Kmat, Wi), log_marginal, {'dL_dK': dL_dK, 'dL_dthetaL': dL_dthetaL, 'dL_dm': alpha}
 
 
-def log_likelihood_and_gradients(kind, X, Y, variance, lengthscale, noise, ard=True, native=False):
+def log_likelihood_and_gradients(kind, X, Y, variance, lengthscale, noise, ard=True, native=False, gower=None):
     """GP.parameters_changed (core/gp.py:258-271): inference, then likelihood + kernel gradient updates.
 
     Returns (logL, grads) with grads ordered like m[:] = [kern.variance, kern.lengthscale..., Gaussian_noise.variance]
     (link order: stationary.py:83, core/gp.py:108-109)."""
-    post, logL, gd = exact_inference(kind, X, Y, variance, lengthscale, noise, ard)
-    dvar, dlen = update_gradients_full(kind, gd['dL_dK'], X, None, variance, lengthscale, ard, native=native)
+    post, logL, gd = exact_inference(kind, X, Y, variance, lengthscale, noise, ard, gower=gower)
+    dvar, dlen = update_gradients_full(kind, gd['dL_dK'], X, None, variance, lengthscale, ard, native=native, gower=gower)
     return logL, np.concatenate([[dvar], dlen, [gd['dL_dthetaL']]]), post
 
 
-def raw_predict(kind, post, X, Xnew, variance, lengthscale, ard=True, full_cov=False):
+def raw_predict(kind, post, X, Xnew, variance, lengthscale, ard=True, full_cov=False, gower=None):
     """posterior.py:273-302 (PosteriorExact._raw_predict); no clipping here."""
-    Kx = K(kind, X, Xnew, variance, lengthscale, ard)
+    Kx = K(kind, X, Xnew, variance, lengthscale, ard, gower)
     mu = np.dot(Kx.T, post.woodbury_vector)
     if mu.ndim == 1:
         mu = mu.reshape(-1, 1)
     if full_cov:
-        Kxx = K(kind, Xnew, None, variance, lengthscale, ard)
+        Kxx = K(kind, Xnew, None, variance, lengthscale, ard, gower)
         tmp = dtrtrs(post.woodbury_chol, Kx)[0]
         var = Kxx - tdot(tmp.T)
     else:
@@ -326,9 +351,9 @@ def raw_predict(kind, post, X, Xnew, variance, lengthscale, ard=True, full_cov=F
     return mu, var
 
 
-def predict(kind, post, X, Xnew, variance, lengthscale, noise, ard=True, full_cov=False, include_likelihood=True):
+def predict(kind, post, X, Xnew, variance, lengthscale, noise, ard=True, full_cov=False, include_likelihood=True, gower=None):
     """core/gp.py:297-354 (+ gaussian.py:102-110 predictive_values)."""
-    mu, var = raw_predict(kind, post, X, Xnew, variance, lengthscale, ard, full_cov)
+    mu, var = raw_predict(kind, post, X, Xnew, variance, lengthscale, ard, full_cov, gower)
     if include_likelihood:
         if full_cov:
             var = var + np.eye(var.shape[0]) * noise
@@ -337,7 +362,7 @@ def predict(kind, post, X, Xnew, variance, lengthscale, noise, ard=True, full_co
     return mu, var
 
 
-def predictive_gradients(kind, post, X, Xnew, variance, lengthscale, ard=True, native=False):
+def predictive_gradients(kind, post, X, Xnew, variance, lengthscale, ard=True, native=False, gower=None):
     """core/gp.py:407-454 -> (dmu_dX (M,D,P), dv_dX (M,D))."""
     P = post.woodbury_vector.shape[1]
     mean_jac = np.empty((Xnew.shape[0], Xnew.shape[1], P))
@@ -345,7 +370,7 @@ def predictive_gradients(kind, post, X, Xnew, variance, lengthscale, ard=True, n
         mean_jac[:, :, i] = gradients_X(kind, post.woodbury_vector[:, i:i + 1].T, Xnew, X, variance, lengthscale, ard,
                                         native=native)
     dv_dX = gradients_X_diag(Xnew)
-    alpha = -2. * np.dot(K(kind, Xnew, X, variance, lengthscale, ard), post.woodbury_inv)
+    alpha = -2. * np.dot(K(kind, Xnew, X, variance, lengthscale, ard, gower), post.woodbury_inv)
     dv_dX = dv_dX + gradients_X(kind, alpha, Xnew, X, variance, lengthscale, ard, native=native)
     return mean_jac, dv_dX
 
@@ -353,27 +378,27 @@ def predictive_gradients(kind, post, X, Xnew, variance, lengthscale, ard=True, n
 # ----------------------------------------------------------------------------------------------------------------------
 # L2/L3  GPyOpt adaptor + acquisitions (models/gpmodel.py, util/general.py, acquisitions/{EI,LCB,base}.py)
 # ----------------------------------------------------------------------------------------------------------------------
-def gpmodel_predict(kind, post, X, Xnew, variance, lengthscale, noise, ard=True, with_noise=True):
+def gpmodel_predict(kind, post, X, Xnew, variance, lengthscale, noise, ard=True, with_noise=True, gower=None):
     """gpmodel.py:95-112: clip v at 1e-10 AFTER adding the noise, return (m, sqrt(v))."""
     if Xnew.ndim == 1:
         Xnew = Xnew[None, :]
-    m, v = predict(kind, post, X, Xnew, variance, lengthscale, noise, ard, include_likelihood=with_noise)
+    m, v = predict(kind, post, X, Xnew, variance, lengthscale, noise, ard, include_likelihood=with_noise, gower=gower)
     v = np.clip(v, 1e-10, np.inf)
     return m, np.sqrt(v)
 
 
-def gpmodel_get_fmin(kind, post, X, variance, lengthscale, noise, ard=True):
+def gpmodel_get_fmin(kind, post, X, variance, lengthscale, noise, ard=True, gower=None):
     """gpmodel.py:125-129"""
-    return predict(kind, post, X, X, variance, lengthscale, noise, ard)[0].min()
+    return predict(kind, post, X, X, variance, lengthscale, noise, ard, gower=gower)[0].min()
 
 
-def gpmodel_predict_withGradients(kind, post, X, Xnew, variance, lengthscale, noise, ard=True, native=False):
+def gpmodel_predict_withGradients(kind, post, X, Xnew, variance, lengthscale, noise, ard=True, native=False, gower=None):
     """gpmodel.py:131-142"""
     if Xnew.ndim == 1:
         Xnew = Xnew[None, :]
-    m, v = predict(kind, post, X, Xnew, variance, lengthscale, noise, ard)
+    m, v = predict(kind, post, X, Xnew, variance, lengthscale, noise, ard, gower=gower)
     v = np.clip(v, 1e-10, np.inf)
-    dmdx, dvdx = predictive_gradients(kind, post, X, Xnew, variance, lengthscale, ard, native=native)
+    dmdx, dvdx = predictive_gradients(kind, post, X, Xnew, variance, lengthscale, ard, native=native, gower=gower)
     dmdx = dmdx[:, :, 0]
     dsdx = dvdx / (2 * np.sqrt(v))
     return m, np.sqrt(v), dmdx, dsdx
@@ -411,11 +436,12 @@ def acq_LCB(m, s, exploration_weight=2, dmdx=None, dsdx=None):
 class GPState(object):
     """Frozen GP (kind, data, theta, posterior): what GPModel holds after updateModel.  Convenience for tests/bench."""
 
-    def __init__(self, kind, X, Y, variance, lengthscale, noise, ard=True):
+    def __init__(self, kind, X, Y, variance, lengthscale, noise, ard=True, gower=None):
         self.kind, self.X, self.Y, self.ard = kind, np.ascontiguousarray(X, dtype=np.float64), np.asarray(Y, float), ard
         self.variance, self.lengthscale, self.noise = float(variance), _ls(lengthscale).copy(), float(noise)
+        self.gower = gower
         self.post, self.logL, self.grad_dict = exact_inference(kind, self.X, self.Y, self.variance, self.lengthscale,
-                                                               self.noise, ard)
+                                                               self.noise, ard, gower=gower)
         self._fmin = None
 
     def _a(self):
@@ -423,17 +449,17 @@ class GPState(object):
 
     def predict(self, Xnew, with_noise=True):
         return gpmodel_predict(self.kind, self.post, self.X, Xnew, self.variance, self.lengthscale, self.noise, self.ard,
-                               with_noise)
+                               with_noise, gower=self.gower)
 
     def predict_withGradients(self, Xnew, native=False):
         return gpmodel_predict_withGradients(self.kind, self.post, self.X, Xnew, self.variance, self.lengthscale,
-                                             self.noise, self.ard, native=native)
+                                             self.noise, self.ard, native=native, gower=self.gower)
 
     def get_fmin(self):
         # the reference recomputes this on every acquisition call (gpmodel.py:125-129); the value only depends on the model
         if self._fmin is None:
             self._fmin = gpmodel_get_fmin(self.kind, self.post, self.X, self.variance, self.lengthscale, self.noise,
-                                          self.ard)
+                                          self.ard, gower=self.gower)
         return self._fmin
 
     def acquisition(self, acq, Xnew, par=None, with_gradients=False, native=False):

@@ -29,3 +29,24 @@ def golden(request):
     d["noise"] = float(d["noise"])
     d["name"] = request.param
     return d
+
+
+GOWER_DIR = os.path.join(GOLDEN_DIR, "gower")
+
+
+def gower_names():
+    return sorted(f[:-4] for f in os.listdir(GOWER_DIR) if f.endswith(".npz")) if os.path.isdir(GOWER_DIR) else []
+
+
+@pytest.fixture(params=gower_names())
+def gower_golden(request):
+    """Vectors of the reference's Gower mixed-variable kernel patch (tests/golden/make_golden_gower.py)."""
+    import numpy as np
+    z = np.load(os.path.join(GOWER_DIR, request.param + ".npz"), allow_pickle=False)
+    d = {k: z[k] for k in z.files}
+    d["ard"] = bool(d["ard"])
+    d["variance"] = float(d["variance"])
+    d["noise"] = float(d["noise"])
+    d["gower"] = ([int(i) for i in d["cont_dims"]], [int(i) for i in d["disc_dims"]], [float(r) for r in d["ranges"]])
+    d["name"] = request.param
+    return d

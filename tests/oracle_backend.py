@@ -14,9 +14,9 @@ from oracle import gp_oracle as O
 
 
 class OraclePosterior(object):
-    def __init__(self, kind, ard, X, variance, lengthscale, noise, post):
+    def __init__(self, kind, ard, X, variance, lengthscale, noise, post, gower=None):
         self.kind, self.ard, self.X = kind, ard, X
-        self.variance, self.lengthscale, self.noise, self.post = variance, lengthscale, noise, post
+        self.variance, self.lengthscale, self.noise, self.post, self.gower = variance, lengthscale, noise, post, gower
 
     woodbury_chol = property(lambda self: self.post.woodbury_chol)
     woodbury_vector = property(lambda self: self.post.woodbury_vector)
@@ -28,26 +28,27 @@ class OraclePosterior(object):
 
     def _raw_predict(self, kern, Xnew, pred_var, full_cov=False):
         return O.raw_predict(self.kind, self.post, self.X, np.asarray(Xnew, dtype=np.float64), self.variance, self.lengthscale,
-                             self.ard, full_cov)
+                             self.ard, full_cov, self.gower)
 
     def predictive_gradients(self, Xnew, want_var=True):
-        return O.predictive_gradients(self.kind, self.post, self.X, Xnew, self.variance, self.lengthscale, self.ard)
+        return O.predictive_gradients(self.kind, self.post, self.X, Xnew, self.variance, self.lengthscale, self.ard, gower=self.gower)
 
     def fmin(self):
-        return O.gpmodel_get_fmin(self.kind, self.post, self.X, self.variance, self.lengthscale, self.noise, self.ard)
+        return O.gpmodel_get_fmin(self.kind, self.post, self.X, self.variance, self.lengthscale, self.noise, self.ard, gower=self.gower)
 
     def acquisition(self, acq, par, fmin, X, with_gradients=False, want_moments=False):
         X = np.atleast_2d(np.asarray(X, dtype=np.float64))
         r = {}
         if with_gradients:
             m, s, dmdx, dsdx = O.gpmodel_predict_withGradients(self.kind, self.post, self.X, X, self.variance, self.lengthscale,
-                                                               self.noise, self.ard)
+                                                               self.noise, self.ard, gower=self.gower)
             if want_moments:
                 r["m"], r["s"], r["dmdx"], r["dsdx"] = m, s.copy(), dmdx, dsdx
             f, df = (O.acq_EI(m, s, fmin, par, dmdx, dsdx) if acq == "EI" else O.acq_LCB(m, s, par, dmdx, dsdx))
             r["f"], r["df"] = -f, -df
         else:
-            m, s = O.gpmodel_predict(self.kind, self.post, self.X, X, self.variance, self.lengthscale, self.noise, self.ard)
+            m, s = O.gpmodel_predict(self.kind, self.post, self.X, X, self.variance, self.lengthscale, self.noise, self.ard,
+                                     gower=self.gower)
             if want_moments:
                 r["m"], r["s"] = m, s.copy()
             f = O.acq_EI(m, s, fmin, par) if acq == "EI" else O.acq_LCB(m, s, par)
@@ -73,10 +74,11 @@ class OracleInference(object):
         v = float(kern.variance.values[0])
         ls = kern.lengthscale.values.copy()
         noise = float(np.asarray(likelihood.gaussian_variance()).ravel()[0])
-        logL, grads, post = O.log_likelihood_and_gradients(kern._kind, X, Y, v, ls, noise, ard=kern.ARD)
+        gw = kern.gower_config()
+        logL, grads, post = O.log_likelihood_and_gradients(kern._kind, X, Y, v, ls, noise, ard=kern.ARD, gower=gw)
         self._last_grads = grads
         gd = {"dL_dthetaL": grads[-1], "dL_dm": post.woodbury_vector}
-        return OraclePosterior(kern._kind, kern.ARD, X, v, ls, noise, post), logL, gd
+        return OraclePosterior(kern._kind, kern.ARD, X, v, ls, noise, post, gw), logL, gd
 
 
 def oracle_gp_regression(X, Y, kernel, noise_var=1.):
@@ -89,7 +91,7 @@ class OracleGPModel(gpyopt.GPModel):
     def _create_model(self, X, Y):
         self.input_dim = X.shape[1]
         if self.kernel is None:
-            kern = _kern.Matern52(self.input_dim, variance=1., ARD=self.ARD)
+            kern = _kern.Matern52(self.input_dim, variance=1., ARD=self.ARD, Gower=self.Gower, space=self.space)
         else:
             kern = self.kernel
             self.kernel = None

@@ -403,3 +403,90 @@ def test_distributed_restarts_match_sequential(tmp_path):
         assert_allclose(z["x"], m.optimizer_array, rtol=1e-12)
         assert_allclose(z["theta"], m[:], rtol=1e-12)
         assert z["rng"] == rng_after            # the global NumPy stream advanced exactly as in the sequential run
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's local Gower mixed-variable kernel patch (stationary.py:116-135), as run.py uses it (Gower=True)
+# ---------------------------------------------------------------------------------------------------------------------
+GOWER_DOMAIN = [{'name': 'a', 'type': 'discrete', 'domain': (0, 1, 2, 3)}, {'name': 'x', 'type': 'continuous', 'domain': (-5., 10.)},
+                {'name': 'b', 'type': 'discrete', 'domain': (1, 2, 3)}, {'name': 'y', 'type': 'continuous', 'domain': (1., 15.)}]
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_gower_kernel_public_classes(backend, gower_golden):
+    g = gower_golden
+    space = GPyOpt.Design_space(GOWER_DOMAIN)
+    assert space.get_continuous_dims() == list(g["cont_dims"]) and space.get_discrete_dims() == list(g["disc_dims"])
+    assert_allclose(space.lengthscales(), g["ranges"])
+    w = np.linalg.eigvalsh(g["K"] + (g["noise"] + 1e-8) * np.eye(g["K"].shape[0]))
+    ct = max(1.0, w[-1] / w[0] * 2.2e-16 / 1e-12)
+    k = GPy.kern.Matern52(4, variance=g["variance"], lengthscale=g["lengthscale"], ARD=g["ard"], Gower=True, space=space)
+    if backend == "cuda":      # Kern contract on the device
+        assert_allclose(k.K(g["X"]), g["K"], rtol=1e-9)
+        assert_allclose(k.K(g["Xs"], g["X"]), g["K_cross"], rtol=1e-9)
+        k.update_gradients_full(g["G_sq"], g["X"])
+        assert_allclose(np.ravel(k.variance.gradient), g["ugf_sq_var"].ravel(), rtol=1e-7)
+        assert_allclose(np.ravel(k.lengthscale.gradient), g["ugf_sq_len"].ravel(), rtol=1e-7)
+        k.update_gradients_full(g["G_rect"], g["Xs"], g["X"])
+        assert_allclose(np.ravel(k.variance.gradient), g["ugf_rect_var"].ravel(), rtol=1e-7)
+        assert_allclose(np.ravel(k.lengthscale.gradient), g["ugf_rect_len"].ravel(), rtol=1e-7)
+    m = make_gpr(backend, g["X"], g["Y"], k, noise_var=g["noise"])
+    assert_allclose(m.log_likelihood(), g["logL"], rtol=1e-9 * ct)
+    assert_allclose(np.ravel(k.variance.gradient), g["grad_var"].ravel(), rtol=1e-7 * ct)
+    assert_allclose(np.ravel(k.lengthscale.gradient), g["grad_len"].ravel(), rtol=1e-7 * ct)
+    assert_allclose(np.ravel(m.likelihood.variance.gradient), g["grad_noise"].ravel(), rtol=1e-7 * ct)
+    assert_allclose(m.posterior.woodbury_chol, g["L"], rtol=1e-9, atol=1e-12)
+    mu, var = m.predict(g["Xs"])
+    assert_allclose(mu, g["pred_mu"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(var, g["pred_var"], rtol=1e-9 * ct, atol=1e-12 * ct)
+    gm = make_gpmodel(backend, exact_feval=False, verbose=False)
+    gm.model = m
+    mm, ss, dmdx, dsdx = gm.predict_withGradients(g["Xs"])
+    assert_allclose(mm, g["gpm_m"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(ss, g["gpm_s"], rtol=1e-8 * ct)
+    assert_allclose(dmdx, g["gpm_dmdx"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["gpm_dmdx"]).max())
+    assert_allclose(dsdx, g["gpm_dsdx"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["gpm_dsdx"]).max())
+    assert_allclose(gm.get_fmin(), g["fmin"], rtol=1e-9 * ct)
+    unconstrained = GPyOpt.Design_space([{'name': 'x', 'type': 'continuous', 'domain': (-10, 20), 'dimensionality': 4}])
+    ei = GPyOpt.acquisitions.AcquisitionEI(gm, unconstrained, optimizer=None, jitter=0.01)
+    lcb = GPyOpt.acquisitions.AcquisitionLCB(gm, unconstrained, optimizer=None, exploration_weight=2)
+    f, df = ei.acquisition_function_withGradients(g["Xs"])
+    assert_allclose(f, g["ei_f"], rtol=1e-7 * ct, atol=1e-14)
+    assert_allclose(df, g["ei_df"], rtol=1e-6 * ct, atol=1e-9 * ct * np.abs(g["ei_df"]).max())
+    f, df = lcb.acquisition_function_withGradients(g["Xs"])
+    assert_allclose(f, g["lcb_f"], rtol=1e-9 * ct, atol=1e-11 * ct)
+    assert_allclose(df, g["lcb_df"], rtol=1e-7 * ct, atol=1e-9 * ct * np.abs(g["lcb_df"]).max())
+    lp = GPyOpt.acquisitions.AcquisitionLP(gm, unconstrained, None, ei)
+    lp.update_batches(g["lp_Xb"], 1.5, float(g["Y"].min()))
+    assert_allclose(lp.acquisition_function(g["Xs"][8:]), g["lp_f"], rtol=1e-7 * ct, atol=1e-7 * ct)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_bo_mixed_space_gower_local_penalization(backend):
+    """The configuration of run.py:1207-1224 in miniature: mixed discrete / continuous space, Gower=True, exact_feval,
+    local-penalisation batches, then scoring an explicit candidate list with the (penalised) acquisition (run.py:1234-1253)."""
+    def f(X):
+        X = np.atleast_2d(X)
+        return (np.sin(X[:, 1] / 3) + 0.3 * X[:, 0] - 0.2 * (X[:, 2] == 2) + 0.01 * X[:, 3] ** 2).reshape(-1, 1)
+    np.random.seed(7)
+    space = GPyOpt.Design_space(GOWER_DOMAIN)
+    X0 = GPyOpt.experiment_design.initial_design('random', space, 12)
+    kw = dict(f=None, domain=GOWER_DOMAIN, X=X0, Y=f(X0), acquisition_type='EI', normalize_Y=True, exact_feval=True,
+              evaluator_type='local_penalization', batch_size=3, de_duplication=True, Gower=True, noise_var=0, optimize_restarts=2)
+    if backend == "oracle":
+        kw["model"] = OB.OracleGPModel(noise_var=0, exact_feval=True, optimize_restarts=2, verbose=False, Gower=True, space=space)
+    bo = GPyOpt.methods.BayesianOptimization(**kw)
+    Xn = bo.suggest_next_locations()
+    assert Xn.shape == (3, 4)
+    assert set(Xn[:, 0]) <= {0., 1., 2., 3.} and set(Xn[:, 2]) <= {1., 2., 3.}          # discrete variables are rounded to their domain
+    assert bo.model.model.kern.gower_config() is not None
+    cand = GPyOpt.experiment_design.initial_design('random', space, 200)
+    acq = bo.evaluator.acquisition
+    acq.update_batches(None, None, None)
+    v0 = acq.acquisition_function(cand)
+    assert v0.shape == (200,) and np.all(np.isfinite(v0))
+    L = GPyOpt.core.evaluators.batch_local_penalization.estimate_L(bo.model.model, space.get_bounds())
+    acq.update_batches(cand[int(np.argmin(v0))], L, bo.model.model.Y.min())
+    v1 = acq.acquisition_function(cand)
+    assert np.all(np.isfinite(v1)) and np.all(v1 >= v0 - 1e-12)    # the penalisers only add -log Phi(.) >= 0 to the minimised value
+    assert acq.r_x0.shape == (1,) and acq.s_x0.shape == (1,)
