@@ -456,6 +456,7 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
     GPB_CUDA(cudaEventRecord(m->ov->enter, m->stream));
     GPB_CUDA(cudaStreamWaitEvent(m->ov->main, m->ov->enter, 0));
     const int rc = factor_potrf_inv(fo);
+    m->f.l_pending = fo.l_pending;
     GPB_CUDA(cudaEventRecord(m->ov->leave, m->ov->main));
     GPB_CUDA(cudaStreamWaitEvent(m->stream, m->ov->leave, 0));
     GPB_TRY(rc);
@@ -523,6 +524,7 @@ int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) 
   }
   const dim3 grid((n + 255) / 256, n), gsym((n + 31) / 32, (n + 31) / 32);
   if (w == "L") {
+    GPB_TRY(factor_finalize_L(m->f));
     tril_copy_kernel<<<grid, 256, 0, s>>>(m->f.A, np, ddst, ldd, n);
   } else if (w == "Li") {
     tril_copy_kernel<<<grid, 256, 0, s>>>(m->f.Mi, np, ddst, ldd, n);
@@ -1077,6 +1079,7 @@ int gpb_pdinv(int n, const double *A, int lda, double *L, double *Ai, double *Li
     return info > n ? n : info;
   }
   if (logdet) *logdet = h[0];
+  GPB_TRY(factor_finalize_L(f));
   if (Ai) GPB_TRY(factor_potri(f));
   if (!dev && (L || Ai || Li)) GPB_TRY(outb.alloc((size_t)n * n * sizeof(double)));
   const dim3 grid((n + 255) / 256, n), gsym((n + 31) / 32, (n + 31) / 32);

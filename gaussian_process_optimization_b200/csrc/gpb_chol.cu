@@ -280,12 +280,19 @@ int launch_symmetrize_lower(double *A, int ld, int n, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------------------------------
 // potrf + triangular inverse (recursive)
 // ---------------------------------------------------------------------------------------------------------------------
-// Two-stream schedule (f.ov != nullptr): the product T21 = L21 M11 only needs L21 and M11, so it is issued on a low-priority
-// side stream (one per recursion depth) right after L21 exists and runs underneath the critical path
+// Scratch layout inside W during the factorisation (every 128-block of W is used by exactly one recursion level):
+//   strictly-lower block (i, j), i > j : L21 of the level whose (2,1) quadrant contains it  (S21 = A21 M11^T)
+//   strictly-upper block (i, j), i < j : T21^T of that level                               (T12 = M11^T L21^T)
+// Nothing on the critical path reads L back from A (a parent level only needs M11 and the untouched rows of Ky below), so
+// L21 is NOT copied into A level by level: factor_finalize_L moves all strictly-lower blocks in one pass before W is reused
+// (Ky^-1 = M^T M) or when the caller asks for L.
+//
+// Two-stream schedule (f.ov != nullptr): T12 only needs L21 and M11, so it is issued on a low-priority side stream (one per
+// recursion depth) right after L21 exists and runs underneath the critical path
 //     A22 -= L21 L21^T  ->  cholinv(A22)
 // whose lower levels (leaves, 32x32-tile GEMMs) leave most of the 148 SMs idle; M21 = -M22 T21 joins the two streams.
 // f.stream must be a high-priority stream so that the small critical-path kernels get the next free SM slots while a long
-// side GEMM is resident.  Buffers: T21 overwrites the S21 scratch, therefore the SYRK reads the copy of L21 in A21.
+// side GEMM is resident.
 static int cholinv(Factor &f, int off, int n, int depth) {
   if (n == TILE) return launch_leaf(f, off, 0);
   const int ld = f.np;
@@ -297,36 +304,60 @@ static int cholinv(Factor &f, int off, int n, int depth) {
   double *M11 = f.Mi + (size_t)off * ld + off;
   double *M21 = f.Mi + (size_t)(off + h) * ld + off;
   double *M22 = f.Mi + (size_t)(off + h) * ld + off + h;
-  double *S21 = f.W + (size_t)(off + h) * ld + off;  // scratch with the shape of the (2,1) block
+  double *S21 = f.W + (size_t)(off + h) * ld + off;   // r x h: L21
+  double *T12 = f.W + (size_t)off * ld + off + h;     // h x r: T21^T
   const bool fork = f.ov != nullptr && depth < FactorOverlap::MAX_DEPTH && n >= f.ov->min_n;
   GemmArgs g;
-  // S21 = A21 * M11^T      (M11 lower: k <= column tile)
+  // L21 = A21 * M11^T      (M11 lower: k <= column tile)
   g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 0, 2};
   GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
-  GPB_TRY(launch_copy2d(A21, ld, S21, ld, r, h, f.stream));  // A21 <- L21
   cudaStream_t s5 = f.stream;
   if (fork) {
     s5 = f.ov->side[depth];
     GPB_CUDA(cudaEventRecord(f.ov->fork[depth], f.stream));
     GPB_CUDA(cudaStreamWaitEvent(s5, f.ov->fork[depth], 0));
-    // T21 = L21 * M11      (M11 lower: k >= column tile)   -- side stream, overwrites S21
-    g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 2, 0};
-    GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, s5));
-    GPB_CUDA(cudaEventRecord(f.ov->join[depth], s5));
   }
+  // T12 = M11^T * L21^T    (M11 lower: k >= row tile of T12)
+  g = GemmArgs{M11, ld, S21, ld, T12, ld, h, r, h, 1.0, 0.0, 0, 1, 0};
+  GPB_TRY(gemm_launch(LAYOUT_COLK, LAYOUT_ROWK, g, s5));
+  if (fork) GPB_CUDA(cudaEventRecord(f.ov->join[depth], s5));
   // A22 -= L21 * L21^T     (lower tiles)
-  g = GemmArgs{A21, ld, A21, ld, A22, ld, r, r, h, -1.0, 1.0, 1, 0, 0};
+  g = GemmArgs{S21, ld, S21, ld, A22, ld, r, r, h, -1.0, 1.0, 1, 0, 0};
   GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
   GPB_TRY(cholinv(f, off + h, r, depth + 1));
-  if (fork) {
-    GPB_CUDA(cudaStreamWaitEvent(f.stream, f.ov->join[depth], 0));
-  } else {
-    g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 2, 0};
-    GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, f.stream));
+  if (fork) GPB_CUDA(cudaStreamWaitEvent(f.stream, f.ov->join[depth], 0));
+  // M21 = -M22 * T21       (M22 lower: k <= row tile; T21 read through its transpose T12, k-contiguous)
+  g = GemmArgs{M22, ld, T12, ld, M21, ld, r, h, r, -1.0, 0.0, 0, 0, 1};
+  GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
+  return 0;
+}
+
+// dst block (bi, bj) = src block (bi, bj) for all 128-blocks strictly below the diagonal
+__global__ void copy_lower_blocks_kernel(double *__restrict__ dst, const double *__restrict__ src, int ld, int nb) {
+  const int t = blockIdx.x;  // strictly-lower block index: t = bi (bi - 1) / 2 + bj, bi >= 1
+  int bi = (int)((sqrt(8.0 * (double)t + 1.0) + 1.0) * 0.5);
+  while (bi * (bi - 1) / 2 > t) --bi;
+  while ((bi + 1) * bi / 2 <= t) ++bi;
+  const int bj = t - bi * (bi - 1) / 2;
+  if (bi >= nb) return;
+  const size_t base = (size_t)(bi * TILE) * ld + bj * TILE;
+  for (int e = threadIdx.x; e < TILE * TILE / 2; e += blockDim.x) {
+    const int rrow = e >> 6, c2 = e & 63;
+    reinterpret_cast<double2 *>(dst + base + (size_t)rrow * ld)[c2] = reinterpret_cast<const double2 *>(src + base + (size_t)rrow * ld)[c2];
   }
-  // M21 = -M22 * T21       (M22 lower: k <= row tile)
-  g = GemmArgs{M22, ld, S21, ld, M21, ld, r, h, r, -1.0, 0.0, 0, 0, 1};
-  GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, f.stream));
+}
+
+// Move the off-diagonal blocks of L from their scratch place in W into A (no-op when already done).
+int factor_finalize_L(Factor &f) {
+  if (!f.l_pending) return 0;
+  const int nb = f.np / TILE;
+  const int blocks = nb * (nb - 1) / 2;
+  if (blocks > 0) {
+    copy_lower_blocks_kernel<<<blocks, 256, 0, f.stream>>>(f.A, f.W, f.np, nb);
+    count_launch();
+    GPB_CHECK_LAUNCH();
+  }
+  f.l_pending = false;
   return 0;
 }
 
@@ -388,11 +419,13 @@ int factor_trtri(Factor &f) {
 int factor_potrf_inv(Factor &f) {
   GPB_REQUIRE(f.np % TILE == 0 && f.np >= TILE, "factor: padded size must be a multiple of 128");
   GPB_CUDA(cudaMemsetAsync(f.info, 0, sizeof(int), f.stream));
+  f.l_pending = true;
   return cholinv(f, 0, f.np, 0);
 }
 
 // Ky^-1 = M^T M: W[i][j] = sum_{k >= max(i,j)} M[k][i] M[k][j]; lower tiles only (diagonal tiles complete).
 int factor_potri(Factor &f) {
+  GPB_TRY(factor_finalize_L(f));   // W still holds the off-diagonal blocks of L
   GemmArgs g{f.Mi, f.np, f.Mi, f.np, f.W, f.np, f.np, f.np, f.np, 1.0, 0.0, 1, 1, 0};
   return gemm_launch(LAYOUT_COLK, LAYOUT_COLK, g, f.stream);
 }
