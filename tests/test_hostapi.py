@@ -490,3 +490,64 @@ def test_bo_mixed_space_gower_local_penalization(backend):
     v1 = acq.acquisition_function(cand)
     assert np.all(np.isfinite(v1)) and np.all(v1 >= v0 - 1e-12)    # the penalisers only add -log Phi(.) >= 0 to the minimised value
     assert acq.r_x0.shape == (1,) and acq.s_x0.shape == (1,)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# check_kernel_gradient_functions (GPy/GPy/testing/kernel_tests.py:23-349; instantiated for Matern52 :414-417 and RBF(ARD)
+# :419-422 with N = 10, N2 = 20, D = 5 :352-356): the Kern contract against central differences of sum(dL_dK * K)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("kname,ard", [("Matern52", False), ("RBF", True), ("Matern52", True), ("RBF", False)])
+def test_kernel_gradient_functions(kname, ard):
+    rs = np.random.RandomState(31)
+    N, N2, D = 10, 20, 5
+    X, X2 = rs.randn(N, D), rs.randn(N2, D)
+    k = getattr(GPy.kern, kname)(D, ARD=ard)
+    k.variance[...] = 1.0 + 0.1 * rs.randn()                      # kernel.randomize(loc=1, scale=0.1)
+    k.lengthscale[...] = 1.0 + 0.1 * rs.randn(k.lengthscale.size)
+
+    # positive semi-definiteness and Kdiag (kernel_tests.py:47-53, Kern_check_dKdiag_dtheta)
+    Kxx = k.K(X)
+    assert np.linalg.eigvalsh(Kxx).min() > -1e-10
+    assert_allclose(k.Kdiag(X), np.diag(Kxx), rtol=1e-12)
+    assert_allclose(Kxx, Kxx.T, rtol=0, atol=0)
+
+    for Xb, G in ((None, rs.rand(N, N)), (X2, rs.rand(N, N2))):
+        f = lambda: float(np.sum(G * k.K(X, Xb)))                 # noqa: E731  Kern_check_model.log_likelihood
+        # dK/dtheta (Kern_check_dK_dtheta)
+        k.update_gradients_full(G, X, Xb)
+        g_var, g_len = float(np.ravel(k.variance.gradient)[0]), np.ravel(k.lengthscale.gradient).copy()
+        h = 1e-6
+        v0 = float(k.variance.values[0])
+        k.variance[...] = v0 + h
+        fp = f()
+        k.variance[...] = v0 - h
+        fm = f()
+        k.variance[...] = v0
+        assert_allclose(g_var, (fp - fm) / (2 * h), rtol=1e-6)
+        l0 = k.lengthscale.values.copy()
+        for q in range(l0.size):
+            lp, lm = l0.copy(), l0.copy()
+            lp[q] += h
+            lm[q] -= h
+            k.lengthscale[...] = lp
+            fp = f()
+            k.lengthscale[...] = lm
+            fm = f()
+            k.lengthscale[...] = l0
+            assert_allclose(g_len[q], (fp - fm) / (2 * h), rtol=1e-5, atol=1e-8)
+        # dK/dX (Kern_check_dK_dX): gradient of sum(G * K(X, Xb)) with respect to X
+        gX = k.gradients_X(G, X, Xb)
+        assert gX.shape == X.shape
+        num = np.zeros_like(X)
+        for i in range(N):
+            for q in range(D):
+                Xp, Xm = X.copy(), X.copy()
+                Xp[i, q] += h
+                Xm[i, q] -= h
+                if Xb is None:
+                    num[i, q] = (np.sum(G * k.K(Xp)) - np.sum(G * k.K(Xm))) / (2 * h)
+                else:
+                    num[i, q] = (np.sum(G * k.K(Xp, Xb)) - np.sum(G * k.K(Xm, Xb))) / (2 * h)
+        assert_allclose(gX, num, rtol=1e-5, atol=1e-7)
+    assert np.all(k.gradients_X_diag(np.ones(N), X) == 0.0)      # stationary.py:366-367
