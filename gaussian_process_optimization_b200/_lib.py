@@ -49,6 +49,7 @@ SIGNATURES = {
     "gpb_model_set_data": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int]),
     "gpb_model_set_theta": (c_int, [c_void_p, ctypes.c_double, c_double_p, ctypes.c_double]),
     "gpb_model_fit": (c_int, [c_void_p, c_int, ctypes.c_double, c_double_p]),
+    "gpb_model_append": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_double_p]),
     "gpb_model_get": (c_int, [c_void_p, ctypes.c_char_p, c_void_p, c_int, c_int]),
     "gpb_model_predict": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int]),
     "gpb_model_predict_full_cov": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int]),

@@ -420,10 +420,9 @@ static int ensure_wi(gpb_model *m) {
   return 0;
 }
 
-int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out) {
-  GPB_REQUIRE(m && out, "fit: NULL argument");
-  GPB_TRY(check_device(m, "fit"));
-  GPB_REQUIRE(m->have_data, "fit: set_data has not been called");
+// append_from > 0: the leading append_from x append_from block of the factorisation is valid for the current hyper-parameters
+// (gpb_model_append); only the block rows from there on are built and factorised.
+static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *out, int append_from) {
   // Hyper-parameters outside the domain (an L-BFGS-B line search can push the transformed parameters to 0, inf or NaN):
   // the reference's NumPy path turns those into NaNs and ends in jitchol's LinAlgError (linalg.py:62-75), which paramz
   // catches.  Same contract here: GPB_ERR_DOMAIN -> LinAlgError in the Python layer.  variance == 0 is legal (K = 0).
@@ -444,7 +443,7 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
   // Ky = K + (noise + 1e-8 [+ jitter]) I     exact_gaussian_inference.py:55-56
   const KCoords kc = train_coords(m);
   GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, d, n, n, kc.var, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np, np,
-                      m->stream, kc.gflag));
+                      m->stream, kc.gflag, append_from));
   // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
   const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / 8) : 0;
   if (m->ov && fork_min_n > 0 && np >= fork_min_n) {
@@ -455,13 +454,14 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
     m->ov->min_n = fork_min_n;
     GPB_CUDA(cudaEventRecord(m->ov->enter, m->stream));
     GPB_CUDA(cudaStreamWaitEvent(m->ov->main, m->ov->enter, 0));
-    const int rc = factor_potrf_inv(fo);
+    const int rc = append_from > 0 ? factor_append(fo, append_from) : factor_potrf_inv(fo);
     m->f.l_pending = fo.l_pending;
+    m->f.l_from = fo.l_from;
     GPB_CUDA(cudaEventRecord(m->ov->leave, m->ov->main));
     GPB_CUDA(cudaStreamWaitEvent(m->stream, m->ov->leave, 0));
     GPB_TRY(rc);
   } else {
-    GPB_TRY(factor_potrf_inv(m->f));
+    GPB_TRY(append_from > 0 ? factor_append(m->f, append_from) : factor_potrf_inv(m->f));
   }
   GPB_TRY(factor_solve(m->f, m->Yc, p, m->z, m->alpha));
   GPB_TRY(factor_logdet(m->f, m->scal + 0));
@@ -501,6 +501,49 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
   }
   m->fitted = true;
   return 0;
+}
+
+int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out) {
+  GPB_REQUIRE(m && out, "fit: NULL argument");
+  GPB_TRY(check_device(m, "fit"));
+  GPB_REQUIRE(m->have_data, "fit: set_data has not been called");
+  return fit_core(m, want_grad, extra_jitter, out, 0);
+}
+
+int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall, int dev, int want_grad, double *out) {
+  GPB_REQUIRE(m && Xnew && Yall && out, "append: NULL argument");
+  GPB_TRY(check_device(m, "append"));
+  GPB_REQUIRE(m->fitted && m->jitter == 0.0, "append: needs a model fitted (without extra jitter) for the current hyper-parameters");
+  GPB_REQUIRE(b >= 1 && m->n + b <= m->n_cap, "append: %d + %d points exceed the model capacity %d", m->n, b, m->n_cap);
+  const int n_old = m->n, np_old = m->np, n_new = n_old + b, np_new = round_up(n_new, TILE), d = m->d;
+  cudaStream_t s = m->stream;
+  GPB_TRY(factor_finalize_L(m->f));                     // W is about to be reused
+  if (np_new != np_old) {
+    // the three N x N matrices are stored with leading dimension np: re-stride L and M through W (Ky^-1 is recomputed on demand)
+    for (double *mat : {m->f.A, m->f.Mi}) {
+      GPB_TRY(launch_copy2d(m->f.W, np_new, mat, np_old, np_old, np_old, s));
+      GPB_TRY(launch_copy2d(mat, np_new, m->f.W, np_new, np_old, np_old, s));
+    }
+  }
+  GPB_CUDA(cudaMemcpyAsync(m->X + (size_t)n_old * d, Xnew, (size_t)b * d * sizeof(double),
+                           dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  m->n = n_new;
+  m->np = np_new;
+  m->f.n = n_new;
+  m->f.np = np_new;
+  DevBuf tmp;
+  const double *Yd = nullptr;
+  GPB_TRY(to_device(tmp, Yall, (size_t)n_new * m->p, dev, &Yd, s));
+  pack_cols_kernel<<<(m->p * np_new + 255) / 256, 256, 0, s>>>(Yd, n_new, m->p, np_new, m->Yc);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  GPB_CUDA(cudaStreamSynchronize(s));
+  m->scaled_valid = false;
+  // block rows from h on are rebuilt: the last, partially filled block row of the old factor and everything new
+  const int h = (n_old / TILE) * TILE;
+  const int rc = fit_core(m, want_grad, 0.0, out, h);
+  if (rc != 0) m->fitted = false;   // the factor is in an undefined state: the caller must run a full fit
+  return rc;
 }
 
 int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) {

@@ -293,12 +293,14 @@ int launch_symmetrize_lower(double *A, int ld, int n, cudaStream_t s) {
 // whose lower levels (leaves, 32x32-tile GEMMs) leave most of the 148 SMs idle; M21 = -M22 T21 joins the two streams.
 // f.stream must be a high-priority stream so that the small critical-path kernels get the next free SM slots while a long
 // side GEMM is resident.
-static int cholinv(Factor &f, int off, int n, int depth) {
+// split > 0 (top level of an append): the leading split x split block is already factorised and inverted -- only the
+// trailing block rows are (re)computed: O(N^2 r) instead of O(N^3).
+static int cholinv(Factor &f, int off, int n, int depth, int split = 0) {
   if (n == TILE) return launch_leaf(f, off, 0);
   const int ld = f.np;
-  const int h = ((n / TILE) / 2) * TILE;  // first half (multiple of 128), second half n - h >= h
+  const int h = split > 0 ? split : ((n / TILE) / 2) * TILE;  // first part (multiple of 128); default: half, n - h >= h
   const int r = n - h;
-  GPB_TRY(cholinv(f, off, h, depth + 1));
+  if (split == 0) GPB_TRY(cholinv(f, off, h, depth + 1));
   double *A21 = f.A + (size_t)(off + h) * ld + off;
   double *A22 = f.A + (size_t)(off + h) * ld + off + h;
   double *M11 = f.Mi + (size_t)off * ld + off;
@@ -332,9 +334,9 @@ static int cholinv(Factor &f, int off, int n, int depth) {
   return 0;
 }
 
-// dst block (bi, bj) = src block (bi, bj) for all 128-blocks strictly below the diagonal
-__global__ void copy_lower_blocks_kernel(double *__restrict__ dst, const double *__restrict__ src, int ld, int nb) {
-  const int t = blockIdx.x;  // strictly-lower block index: t = bi (bi - 1) / 2 + bj, bi >= 1
+// dst block (bi, bj) = src block (bi, bj) for the 128-blocks strictly below the diagonal in block rows bi >= bi0
+__global__ void copy_lower_blocks_kernel(double *__restrict__ dst, const double *__restrict__ src, int ld, int nb, int t0) {
+  const int t = blockIdx.x + t0;  // strictly-lower block index: t = bi (bi - 1) / 2 + bj, bi >= 1
   int bi = (int)((sqrt(8.0 * (double)t + 1.0) + 1.0) * 0.5);
   while (bi * (bi - 1) / 2 > t) --bi;
   while ((bi + 1) * bi / 2 <= t) ++bi;
@@ -351,9 +353,10 @@ __global__ void copy_lower_blocks_kernel(double *__restrict__ dst, const double 
 int factor_finalize_L(Factor &f) {
   if (!f.l_pending) return 0;
   const int nb = f.np / TILE;
-  const int blocks = nb * (nb - 1) / 2;
+  const int t0 = f.l_from * (f.l_from - 1) / 2;          // blocks of the block rows < l_from are already in place
+  const int blocks = nb * (nb - 1) / 2 - (t0 > 0 ? t0 : 0);
   if (blocks > 0) {
-    copy_lower_blocks_kernel<<<blocks, 256, 0, f.stream>>>(f.A, f.W, f.np, nb);
+    copy_lower_blocks_kernel<<<blocks, 256, 0, f.stream>>>(f.A, f.W, f.np, nb, t0 > 0 ? t0 : 0);
     count_launch();
     GPB_CHECK_LAUNCH();
   }
@@ -420,7 +423,19 @@ int factor_potrf_inv(Factor &f) {
   GPB_REQUIRE(f.np % TILE == 0 && f.np >= TILE, "factor: padded size must be a multiple of 128");
   GPB_CUDA(cudaMemsetAsync(f.info, 0, sizeof(int), f.stream));
   f.l_pending = true;
+  f.l_from = 0;
   return cholinv(f, 0, f.np, 0);
+}
+
+// Append: the leading h x h part of A / Mi holds a valid factor and inverse factor, the block rows from h on hold fresh rows of
+// Ky (lower blocks).  Factorises them against the existing part.  h multiple of 128, 0 < h < np.
+int factor_append(Factor &f, int h) {
+  GPB_REQUIRE(f.np % TILE == 0 && h % TILE == 0 && h > 0 && h < f.np, "factor_append: bad split %d of %d", h, f.np);
+  GPB_REQUIRE(!f.l_pending, "factor_append: finalize L first");
+  GPB_CUDA(cudaMemsetAsync(f.info, 0, sizeof(int), f.stream));
+  f.l_pending = true;
+  f.l_from = h / TILE;
+  return cholinv(f, 0, f.np, 0, h);
 }
 
 // Ky^-1 = M^T M: W[i][j] = sum_{k >= max(i,j)} M[k][i] M[k][j]; lower tiles only (diagonal tiles complete).

@@ -170,6 +170,7 @@ struct Factor {
   cudaStream_t stream = 0;
   FactorOverlap *ov = nullptr;  // non-null: two-stream schedule (stream must then be ov->main)
   bool l_pending = false;       // the off-diagonal blocks of L still sit in W (factor_finalize_L moves them into A)
+  int l_from = 0;               // ... for the block rows >= l_from (0 after a full factorisation, h / 128 after an append)
 };
 
 // gemm engine (gpb_gemm.cu)
@@ -195,6 +196,7 @@ int factor_potrf_inv(Factor &f);                 // A -> L, Mi = L^-1, *info
 int factor_trtri(Factor &f);                     // A holds a lower-triangular L (diag blocks clean) -> Mi = L^-1
 int factor_potri(Factor &f);                     // W = Mi^T Mi (lower tiles)
 int factor_finalize_L(Factor &f);                // off-diagonal blocks of L: W -> A (idempotent)
+int factor_append(Factor &f, int h);             // leading h x h part already factorised: factor the block rows from h on
 int factor_solve(Factor &f, const double *Y, int p, double *z, double *alpha);  // alpha = Mi^T (Mi Y);  Y, z, alpha: np x p col-major (p vectors of np)
 int factor_logdet(Factor &f, double *out_dev);   // 2 sum log L_ii, i < n
 // Z[c] = Mi B[c], U[c] = Mi^T Z[c] for c in {1,2,4,8} vectors stored as rows (U may be NULL); part: 8 * 16 * np doubles

@@ -56,11 +56,12 @@ int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, 
 template <int KIND, int GOWER>
 __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
                                                       int n_rows, int n_cols, double variance, double diag_add, int mode,
-                                                      double *__restrict__ out, int ldo, const double *__restrict__ gflag) {
+                                                      double *__restrict__ out, int ldo, const double *__restrict__ gflag,
+                                                      int row_blk0) {
   extern __shared__ double sm[];
   double *xa = sm;              // [d][64]
   double *xb = sm + d * KTILE;  // [d][64]
-  const int row0 = blockIdx.y * KTILE, col0 = blockIdx.x * KTILE;
+  const int row0 = (blockIdx.y + row_blk0) * KTILE, col0 = blockIdx.x * KTILE;   // row_blk0 > 0: only the rows from there on
   if (mode == 3) {
     // Ky for the factorisation: nothing reads the 128-blocks strictly above the diagonal (gpb_chol.cu only touches lower
     // blocks and complete diagonal blocks), so half of the exp() work and of the HBM writes is skipped
@@ -124,18 +125,20 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__
 
 int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                 double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
-                cudaStream_t s, const double *gflag) {
+                cudaStream_t s, const double *gflag, int row_start) {
   const size_t smem = (size_t)2 * d * KTILE * sizeof(double);
   GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large", d);
   GPB_REQUIRE(rows_pad % KTILE == 0 && cols_pad % KTILE == 0, "kmat: padded sizes must be multiples of %d", KTILE);
-  dim3 grid(cols_pad / KTILE, rows_pad / KTILE);
+  GPB_REQUIRE(row_start % KTILE == 0 && row_start >= 0 && row_start <= rows_pad, "kmat: bad row_start %d", row_start);
+  dim3 grid(cols_pad / KTILE, (rows_pad - row_start) / KTILE);
+  const int row_blk0 = row_start / KTILE;
   if (grid.x == 0 || grid.y == 0) return 0;
 #define GPB_KMAT(K_, G_)                                                                                                  \
   do {                                                                                                                    \
     if (smem > 48 * 1024)                                                                                                 \
       GPB_CUDA(cudaFuncSetAttribute(kmat_kernel<K_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kmat_kernel<K_, G_><<<grid, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, diag_add, mode, out, ldo, \
-                                                gflag);                                                                   \
+                                                gflag, row_blk0);                                                         \
   } while (0)
   if (kind == GPB_KERN_RBF) {
     if (gflag) GPB_KMAT(GPB_KERN_RBF, 1); else GPB_KMAT(GPB_KERN_RBF, 0);

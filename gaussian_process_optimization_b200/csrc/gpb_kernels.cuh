@@ -20,7 +20,7 @@ int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, 
 // a discrete dimension, `variance` is variance^d)
 int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                 double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
-                cudaStream_t s, const double *gflag = nullptr);
+                cudaStream_t s, const double *gflag = nullptr, int row_start = 0);   // row_start: only rows >= it (multiple of 64)
 // out_dev[0] = sum K_gower . G  (variance-gradient term under the Gower patch); part: tiles doubles
 int launch_kvar_gower(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                       double vpow, const double *gflag, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out,

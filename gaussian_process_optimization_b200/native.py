@@ -273,6 +273,21 @@ class NativeModel(object):
             return rc, None, None
         return 0, float(out[0]), (out[1:].copy() if want_grad else None)
 
+    def append(self, Xnew, Yall, want_grad=True):
+        """Extend the fitted model by the rows Xnew (targets replaced by Yall) without refactorising: O(N^2 b).
+        -> (info, log_marginal, grads or None) like fit()."""
+        Xnew, Yall = as_host(Xnew), as_host(Yall)
+        b = Xnew.shape[0]
+        assert Xnew.shape[1] == self.d and Yall.shape == (self.n + b, self.p)
+        out = np.zeros(3 + self.nls)
+        rc = self._lib.gpb_model_append(self._h, b, ptr(Xnew), ptr(Yall), 0, int(want_grad), dptr(out))
+        if rc < 0:
+            check(rc, "append")
+        self.n += b
+        if rc > 0:
+            return rc, None, None
+        return 0, float(out[0]), (out[1:].copy() if want_grad else None)
+
     def get(self, what, out=None):
         n = self.n
         shape = (n, self.p) if what == "alpha" else (n, n)

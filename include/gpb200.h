@@ -101,6 +101,13 @@ int gpb_model_set_theta(gpb_model *m, double variance, const double *lengthscale
  * out (host): [log_marginal, dL/dvariance, dL/dlengthscale[nls], dL/dnoise]  (want_grad = 0 -> only out[0]).
  * Returns 0 or info > 0 (not positive definite). */
 int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out);
+/* GP.set_XY (core/gp.py:202-238) when the new inputs extend the old ones and no hyper-parameter changed: appends b rows
+ * Xnew (b x d) to the inputs, replaces the targets by Yall ((n + b) x p; GPyOpt re-normalises all of Y every step,
+ * GPyOpt/GPyOpt/core/bo.py:246-247) and extends the resident factorisation by the new block rows in O(N^2 b) instead of
+ * refactorising in O(N^3) (what GPModel.updateModel pays on every step, gpmodel.py:78-93 -> core/gp.py:258-271).
+ * Needs a model fitted with extra_jitter = 0 for the current hyper-parameters; out as gpb_model_fit.  On info > 0 the
+ * model must be refitted with gpb_model_fit. */
+int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall, int dev, int want_grad, double *out);
 /* Posterior accessors (posterior.py:79-218): woodbury_chol L (n x n), woodbury_inv (n x n, symmetric), woodbury_vector
  * alpha (n x p), K (n x n, recomputed), dL_dK (n x n; exact_gaussian_inference.py:70).  dst may be host or device. */
 int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev);

@@ -392,3 +392,47 @@ def test_ill_conditioned_exact_feval_models(kind, N, D, noise):
     print("cond(Ky) = %.2e, |dlogL|/|logL| = %.2e, max |dmu| = %.2e, max |dvar| = %.2e" %
           (cond, abs(logL - l_ref) / abs(l_ref), np.abs(mu - mu_r).max(), np.abs(var - var_r).max()))
     m.close()
+
+
+@pytest.mark.parametrize("kind,n0,steps", [("mat52", 100, (5, 23, 1, 150, 64)), ("rbf", 384, (128, 1, 300))])
+def test_append_extends_the_factorisation(kind, n0, steps):
+    """gpb_model_append: the block rows of the new points are factorised against the resident factor; everything must equal a
+    full refit on the extended data (within the padding block, across 128-boundaries, several blocks at once)."""
+    D = 3
+    X, Y, ls = _synth(n0 + sum(steps), D, seed=5)
+    m = native.NativeModel(kind, True, D, 1, n_cap=X.shape[0], cand_block=128)
+    ref = native.NativeModel(kind, True, D, 1, n_cap=X.shape[0], cand_block=128)
+    theta = (1.2, ls, 1e-3)
+    m.set_data(X[:n0], Y[:n0])
+    m.set_theta(*theta)
+    assert m.fit(False)[0] == 0
+    n = n0
+    Xc = np.random.RandomState(1).uniform(0, 1, (40, D))
+    for i, b in enumerate(steps):
+        Yn = Y[:n + b] * (1.0 + 0.01 * i)            # GPyOpt re-normalises all targets on every step
+        want_grad = i % 2 == 0
+        info, logL, g = m.append(X[n:n + b], Yn, want_grad=want_grad)
+        n += b
+        assert info == 0 and m.n == n
+        ref.set_data(X[:n], Yn)
+        ref.set_theta(*theta)
+        info, l_ref, g_ref = ref.fit(True)
+        assert info == 0
+        assert_allclose(logL, l_ref, rtol=1e-10)
+        if want_grad:
+            assert_allclose(g, g_ref, rtol=1e-7)
+        for what in ("L", "Li", "alpha"):
+            a, b_ = m.get(what), ref.get(what)
+            assert_allclose(a, b_, rtol=1e-7, atol=1e-9 * np.abs(b_).max())
+        mu, var = m.predict(Xc)
+        mu_r, var_r = ref.predict(Xc)
+        # different blocking of the same arithmetic: agreement to cond(Ky) * eps (the smooth RBF case has cond ~ 1e7)
+        assert_allclose(mu, mu_r, rtol=1e-8, atol=1e-10)
+        assert_allclose(var, var_r, rtol=1e-8, atol=1e-11)
+        dm, dv = m.predictive_gradients(Xc)
+        dm_r, dv_r = ref.predictive_gradients(Xc)
+        assert_allclose(dm, dm_r, rtol=1e-7, atol=1e-9 * np.abs(dm_r).max())
+        assert_allclose(dv, dv_r, rtol=1e-7, atol=1e-9 * np.abs(dv_r).max())
+    assert_allclose(m.get("Wi"), ref.get("Wi"), rtol=1e-7, atol=1e-9 * np.abs(ref.get("Wi")).max())
+    m.close()
+    ref.close()
