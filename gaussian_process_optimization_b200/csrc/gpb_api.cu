@@ -150,6 +150,7 @@ struct gpb_model {
   double variance = 1.0, noise = 1.0, jitter = 0.0;
   std::vector<double> ls;
   bool have_data = false, scaled_valid = false, fitted = false, have_wi = false;
+  int wi_from = 0;  // > 0 (after gpb_model_append): the leading wi_from block of W holds the old Ky^-1, downdated; rows beyond are stale
   cudaStream_t stream = 0;
   void *ws = nullptr;
   bool own_ws = false;
@@ -351,6 +352,7 @@ int gpb_model_set_data(gpb_model *m, int n, const double *X, const double *Y, in
   m->scaled_valid = false;
   m->fitted = false;
   m->have_wi = false;
+  m->wi_from = 0;
   return 0;
 }
 
@@ -360,6 +362,7 @@ int gpb_model_set_gower(gpb_model *m, int enable, const int *discrete, const dou
   m->scaled_valid = false;
   m->fitted = false;
   m->have_wi = false;
+  m->wi_from = 0;
   if (!enable) {
     m->gower = false;
     return 0;
@@ -385,12 +388,19 @@ int gpb_model_set_gower(gpb_model *m, int enable, const int *discrete, const dou
 
 int gpb_model_set_theta(gpb_model *m, double variance, const double *lengthscale, double noise) {
   GPB_REQUIRE(m && lengthscale, "set_theta: NULL argument");
+  {
+    // bit-identical hyper-parameters keep the factorisation (what makes gpb_model_append usable after GP.set_XY)
+    bool same = m->variance == variance && m->noise == noise;
+    for (int q = 0; q < m->nls; ++q) same = same && m->ls[q] == lengthscale[q];
+    if (same) return 0;
+  }
   m->variance = variance;
   m->noise = noise;
   for (int q = 0; q < m->nls; ++q) m->ls[q] = lengthscale[q];
   m->scaled_valid = false;
   m->fitted = false;
   m->have_wi = false;
+  m->wi_from = 0;
   return 0;
 }
 
@@ -415,8 +425,9 @@ static KCoords train_coords(const gpb_model *m) {
 
 static int ensure_wi(gpb_model *m) {
   if (m->have_wi) return 0;
-  GPB_TRY(factor_potri(m->f));
+  GPB_TRY(m->wi_from > 0 ? factor_potri_append(m->f, m->wi_from) : factor_potri(m->f));
   m->have_wi = true;
+  m->wi_from = 0;
   return 0;
 }
 
@@ -507,6 +518,7 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
   GPB_REQUIRE(m && out, "fit: NULL argument");
   GPB_TRY(check_device(m, "fit"));
   GPB_REQUIRE(m->have_data, "fit: set_data has not been called");
+  m->wi_from = 0;
   return fit_core(m, want_grad, extra_jitter, out, 0);
 }
 
@@ -517,12 +529,35 @@ int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall
   GPB_REQUIRE(b >= 1 && m->n + b <= m->n_cap, "append: %d + %d points exceed the model capacity %d", m->n, b, m->n_cap);
   const int n_old = m->n, np_old = m->np, n_new = n_old + b, np_new = round_up(n_new, TILE), d = m->d;
   cudaStream_t s = m->stream;
-  GPB_TRY(factor_finalize_L(m->f));                     // W is about to be reused
+  // block rows from h on are rebuilt: the last, partially filled block row of the old factor and everything new
+  const int h = (n_old / TILE) * TILE;
+  // Ky^-1: keep the leading h block across the append (factor_potri_append completes it in O(N^2 r))
+  int wi_keep = 0;
+  if (h > 0 && m->have_wi) {
+    GPB_TRY(factor_potri_downdate(m->f, h, np_old));
+    wi_keep = h;
+  } else if (h > 0 && m->wi_from > 0) {
+    wi_keep = m->wi_from;                               // an earlier append whose inverse was never asked for
+  }
+  GPB_TRY(factor_finalize_L(m->f));                     // moves L out of W (no-op when W holds the inverse)
   if (np_new != np_old) {
-    // the three N x N matrices are stored with leading dimension np: re-stride L and M through W (Ky^-1 is recomputed on demand)
-    for (double *mat : {m->f.A, m->f.Mi}) {
-      GPB_TRY(launch_copy2d(m->f.W, np_new, mat, np_old, np_old, np_old, s));
-      GPB_TRY(launch_copy2d(mat, np_new, m->f.W, np_new, np_old, np_old, s));
+    // the three N x N matrices are stored with leading dimension np: re-stride them through a temporary (or, when that
+    // allocation fails, through W, giving up the inverse)
+    double *tmp = nullptr;
+    const size_t cnt = (size_t)np_old * np_old;
+    if (cudaMalloc(&tmp, cnt * sizeof(double)) != cudaSuccess) {
+      (void)cudaGetLastError();
+      tmp = m->f.W;
+      wi_keep = 0;
+    }
+    for (double *mat : {m->f.A, m->f.Mi, m->f.W}) {
+      if (mat == m->f.W && (wi_keep == 0 || tmp == m->f.W)) continue;
+      GPB_CUDA(cudaMemcpyAsync(tmp, mat, cnt * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      GPB_TRY(launch_copy2d(mat, np_new, tmp, np_old, np_old, np_old, s));
+    }
+    if (tmp != m->f.W) {
+      GPB_CUDA(cudaStreamSynchronize(s));
+      GPB_CUDA(cudaFree(tmp));
     }
   }
   GPB_CUDA(cudaMemcpyAsync(m->X + (size_t)n_old * d, Xnew, (size_t)b * d * sizeof(double),
@@ -539,10 +574,12 @@ int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall
   GPB_CHECK_LAUNCH();
   GPB_CUDA(cudaStreamSynchronize(s));
   m->scaled_valid = false;
-  // block rows from h on are rebuilt: the last, partially filled block row of the old factor and everything new
-  const int h = (n_old / TILE) * TILE;
+  m->wi_from = wi_keep;
   const int rc = fit_core(m, want_grad, 0.0, out, h);
-  if (rc != 0) m->fitted = false;   // the factor is in an undefined state: the caller must run a full fit
+  if (rc != 0) {                    // the factor is in an undefined state: the caller must run a full fit
+    m->fitted = false;
+    m->wi_from = 0;
+  }
   return rc;
 }
 

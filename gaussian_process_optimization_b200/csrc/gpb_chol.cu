@@ -445,6 +445,33 @@ int factor_potri(Factor &f) {
   return gemm_launch(LAYOUT_COLK, LAYOUT_COLK, g, f.stream);
 }
 
+// Ky^-1 across an append at h (W11 = leading h x h block of W, lower tiles): with M = [M11 0; M21 M22],
+//     Ky^-1 = M^T M = [M11^T M11 + M21^T M21   . ;  M22^T M21   M22^T M22]
+// so the old inverse only needs the rank-r term of the new block rows added: O(N^2 r) instead of N^3 / 3.
+// factor_potri_downdate removes the term of the block rows [h, np_old) of the OLD factor (the partially filled last block row,
+// which the append recomputes) while those rows still exist; factor_potri_append adds the term of the new rows and fills the
+// block rows from h on.
+int factor_potri_downdate(Factor &f, int h, int np_old) {
+  if (np_old <= h) return 0;
+  const int ld = f.np;
+  GemmArgs g{f.Mi + (size_t)h * ld, ld, f.Mi + (size_t)h * ld, ld, f.W, ld, h, h, np_old - h, -1.0, 1.0, 1, 0, 0};
+  return gemm_launch(LAYOUT_COLK, LAYOUT_COLK, g, f.stream);
+}
+
+int factor_potri_append(Factor &f, int h) {
+  GPB_REQUIRE(f.np % TILE == 0 && h % TILE == 0 && h > 0 && h < f.np, "factor_potri_append: bad split %d of %d", h, f.np);
+  GPB_TRY(factor_finalize_L(f));   // W[h:, :] still holds L21 and the scratch of the trailing recursion
+  const int ld = f.np, r = f.np - h;
+  const double *M21 = f.Mi + (size_t)h * ld, *M22 = f.Mi + (size_t)h * ld + h;
+  GemmArgs g;
+  g = GemmArgs{M21, ld, M21, ld, f.W, ld, h, h, r, 1.0, 1.0, 1, 0, 0};                                  // W11 += M21^T M21
+  GPB_TRY(gemm_launch(LAYOUT_COLK, LAYOUT_COLK, g, f.stream));
+  g = GemmArgs{M22, ld, M21, ld, f.W + (size_t)h * ld, ld, r, h, r, 1.0, 0.0, 0, 1, 0};                 // W21 = M22^T M21
+  GPB_TRY(gemm_launch(LAYOUT_COLK, LAYOUT_COLK, g, f.stream));
+  g = GemmArgs{M22, ld, M22, ld, f.W + (size_t)h * ld + h, ld, r, r, r, 1.0, 0.0, 1, 1, 0};             // W22 = M22^T M22
+  return gemm_launch(LAYOUT_COLK, LAYOUT_COLK, g, f.stream);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // triangular matrix-vector products with M = L^-1 (dpotrs replacement): z = M y, alpha = M^T z
 // ---------------------------------------------------------------------------------------------------------------------

@@ -197,6 +197,8 @@ int factor_trtri(Factor &f);                     // A holds a lower-triangular L
 int factor_potri(Factor &f);                     // W = Mi^T Mi (lower tiles)
 int factor_finalize_L(Factor &f);                // off-diagonal blocks of L: W -> A (idempotent)
 int factor_append(Factor &f, int h);             // leading h x h part already factorised: factor the block rows from h on
+int factor_potri_downdate(Factor &f, int h, int np_old);  // W11 -= (rows [h, np_old) of Mi)^T (same rows): before an append
+int factor_potri_append(Factor &f, int h);       // W: inverse of the leading h block (downdated) -> Ky^-1 of the extended matrix
 int factor_solve(Factor &f, const double *Y, int p, double *z, double *alpha);  // alpha = Mi^T (Mi Y);  Y, z, alpha: np x p col-major (p vectors of np)
 int factor_logdet(Factor &f, double *out_dev);   // 2 sum log L_ii, i < n
 // Z[c] = Mi B[c], U[c] = Mi^T Z[c] for c in {1,2,4,8} vectors stored as rows (U may be NULL); part: 8 * 16 * np doubles

@@ -163,9 +163,17 @@ class PosteriorExact(object):
 class ExactGaussianInference(object):
     """exact_gaussian_inference.py:11-74.  `inference` returns (PosteriorExact, log_marginal, grad_dict)."""
 
-    def __init__(self):
+    INCREMENTAL = True      # default of `incremental` for instances created without the argument (GPRegression, GPModel)
+
+    def __init__(self, incremental=None):
         self._nat = None
         self._sig = None
+        # incremental: when set_XY only appended rows and no hyper-parameter changed, the resident factorisation is extended
+        # in O(N^2 b) (gpb_model_append) instead of rebuilt in O(N^3) -- what GPModel.updateModel pays in the reference on
+        # every step (gpmodel.py:78-93 -> core/gp.py:202-238,258-271).  Same L, alpha, log-likelihood and gradients up to rounding.
+        self.incremental = self.INCREMENTAL if incremental is None else bool(incremental)
+        self._resident = None      # (nat, theta, gower key, X) of the last successful jitter-free fit
+        self.n_appends = 0
 
     def on_optimization_start(self):
         pass
@@ -197,18 +205,32 @@ class ExactGaussianInference(object):
         noise = float(np.asarray(variance).ravel()[0])
         nat = self._native_for(kern, X.shape[0], X.shape[1], Y.shape[1])
         data_id = (id(X), id(Y), X.shape, Y.shape)
-        if getattr(self, "_data_id", None) != data_id or getattr(self, "_data_dirty", True):
-            nat.set_data(X, Y)
-            self._data_id, self._data_dirty = data_id, False
-            self._data_refs = (X, Y)   # keep the arrays alive so that id() stays unique
         gw = kern.gower_config()
         gw_key = None if gw is None else tuple(map(tuple, gw))
-        if getattr(self, "_gower_key", "unset") != (id(nat), gw_key):
-            nat.set_gower(gw)
-            self._gower_key = (id(nat), gw_key)
-        nat.set_theta(float(kern.variance.values[0]), kern.lengthscale.values, noise)
-        # jitchol (linalg.py:56-75): try as is; on failure raise if the diagonal is not positive, else the jitter ladder
-        info, logL, grads = nat.fit(True)
+        theta = (float(kern.variance.values[0]), tuple(float(v) for v in kern.lengthscale.values), noise)
+        new_data = getattr(self, "_data_id", None) != data_id or getattr(self, "_data_dirty", True)
+        info = None
+        res = self._resident
+        if (new_data and self.incremental and res is not None and res[0] is nat and res[1] == theta and res[2] == gw_key
+                and X.shape[0] > res[3].shape[0] and X.shape[0] <= nat.n_cap and nat.n == res[3].shape[0]
+                and np.array_equal(X[:res[3].shape[0]], res[3])):
+            info, logL, grads = nat.append(X[res[3].shape[0]:], Y, True)
+            if info == 0:
+                self._data_id, self._data_dirty = data_id, False
+                self._data_refs = (X, Y)
+                self.n_appends += 1
+        if info != 0:
+            if new_data:
+                nat.set_data(X, Y)
+                self._data_id, self._data_dirty = data_id, False
+                self._data_refs = (X, Y)   # keep the arrays alive so that id() stays unique
+            if getattr(self, "_gower_key", "unset") != (id(nat), gw_key):
+                nat.set_gower(gw)
+                self._gower_key = (id(nat), gw_key)
+            nat.set_theta(theta[0], kern.lengthscale.values, noise)
+            # jitchol (linalg.py:56-75): try as is; on failure raise if the diagonal is not positive, else the jitter ladder
+            info, logL, grads = nat.fit(True)
+        self._resident = (nat, theta, gw_key, X) if info == 0 else None
         if info != 0:
             diag = float(kern.variance.values[0]) + noise + 1e-8
             if not diag > 0.:

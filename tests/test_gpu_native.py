@@ -394,10 +394,14 @@ def test_ill_conditioned_exact_feval_models(kind, N, D, noise):
     m.close()
 
 
-@pytest.mark.parametrize("kind,n0,steps", [("mat52", 100, (5, 23, 1, 150, 64)), ("rbf", 384, (128, 1, 300))])
-def test_append_extends_the_factorisation(kind, n0, steps):
+@pytest.mark.parametrize("kind,n0,steps,grad_every", [("mat52", 100, (5, 23, 1, 150, 64), 2), ("rbf", 384, (128, 1, 300), 2),
+                                                      ("mat52", 200, (56, 1, 127, 1, 300, 2), 1),
+                                                      ("rbf", 130, (1, 1, 1, 130, 1), 3)])
+def test_append_extends_the_factorisation(kind, n0, steps, grad_every):
     """gpb_model_append: the block rows of the new points are factorised against the resident factor; everything must equal a
-    full refit on the extended data (within the padding block, across 128-boundaries, several blocks at once)."""
+    full refit on the extended data (within the padding block, across 128-boundaries, several blocks at once).  Ky^-1 is carried
+    across appends as well (downdate of the recomputed block row + rank-r update), also when it is only asked for several appends
+    later (grad_every > 1)."""
     D = 3
     X, Y, ls = _synth(n0 + sum(steps), D, seed=5)
     m = native.NativeModel(kind, True, D, 1, n_cap=X.shape[0], cand_block=128)
@@ -410,7 +414,7 @@ def test_append_extends_the_factorisation(kind, n0, steps):
     Xc = np.random.RandomState(1).uniform(0, 1, (40, D))
     for i, b in enumerate(steps):
         Yn = Y[:n + b] * (1.0 + 0.01 * i)            # GPyOpt re-normalises all targets on every step
-        want_grad = i % 2 == 0
+        want_grad = i % grad_every == 0
         info, logL, g = m.append(X[n:n + b], Yn, want_grad=want_grad)
         n += b
         assert info == 0 and m.n == n
@@ -421,6 +425,8 @@ def test_append_extends_the_factorisation(kind, n0, steps):
         assert_allclose(logL, l_ref, rtol=1e-10)
         if want_grad:
             assert_allclose(g, g_ref, rtol=1e-7)
+            if grad_every == 1:
+                assert_allclose(m.get("Wi"), ref.get("Wi"), rtol=1e-7, atol=1e-9 * np.abs(ref.get("Wi")).max())
         for what in ("L", "Li", "alpha"):
             a, b_ = m.get(what), ref.get(what)
             assert_allclose(a, b_, rtol=1e-7, atol=1e-9 * np.abs(b_).max())

@@ -551,3 +551,67 @@ def test_kernel_gradient_functions(kname, ard):
                     num[i, q] = (np.sum(G * k.K(Xp, Xb)) - np.sum(G * k.K(Xm, Xb))) / (2 * h)
         assert_allclose(gX, num, rtol=1e-5, atol=1e-7)
     assert np.all(k.gradients_X_diag(np.ones(N), X) == 0.0)      # stationary.py:366-367
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# set_XY that only appends rows under unchanged hyper-parameters extends the resident factorisation
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_set_xy_append_is_incremental_and_equal_to_a_rebuild():
+    rs = np.random.RandomState(11)
+    D, n0 = 3, 120
+    X = rs.uniform(0, 1, (n0 + 40, D))
+    Y = np.sin(X @ np.array([3., 2., 1.]))[:, None] + 0.05 * rs.randn(X.shape[0], 1)
+    m = GPy.models.GPRegression(X[:n0], Y[:n0], kernel=GPy.kern.Matern52(D, ARD=True), noise_var=0.05)
+    inf = m.inference_method
+    assert inf.incremental and inf.n_appends == 0
+    Xc = rs.uniform(0, 1, (30, D))
+    n = n0
+    for b in (1, 5, 9, 1):                        # crosses the 128 boundary at the third step
+        n += b
+        Yn = (Y[:n] - Y[:n].mean()) / Y[:n].std()  # GPyOpt re-normalises every target on every step (bo.py:246-247)
+        m.set_XY(X[:n], Yn)
+        ref = GPy.models.GPRegression(X[:n], Yn, kernel=GPy.kern.Matern52(D, ARD=True), noise_var=0.05)
+        assert ref.inference_method.n_appends == 0
+        assert_allclose(m.log_likelihood(), ref.log_likelihood(), rtol=1e-10)
+        assert_allclose(m.gradient, ref.gradient, rtol=1e-7, atol=1e-9)
+        for a, r in zip(m.predict(Xc), ref.predict(Xc)):
+            assert_allclose(a, r, rtol=1e-8, atol=1e-11)
+        for a, r in zip(m.predictive_gradients(Xc), ref.predictive_gradients(Xc)):
+            assert_allclose(a, r, rtol=1e-7, atol=1e-9 * np.abs(r).max())
+        assert_allclose(m.posterior.woodbury_inv, ref.posterior.woodbury_inv, rtol=1e-7, atol=1e-9 * np.abs(ref.posterior.woodbury_inv).max())
+    assert inf.n_appends == 4
+    # anything but "same rows + more rows, same hyper-parameters" takes the full path
+    Xp = X[:n + 3].copy()
+    Xp[0, 0] += 1e-3
+    m.set_XY(Xp, Y[:n + 3])
+    assert inf.n_appends == 4
+    m.set_XY(X[:n + 3], Y[:n + 3])                 # first row differs from the resident one again
+    assert inf.n_appends == 4
+    m.kern.lengthscale[:] = 0.7
+    m.set_XY(X[:n + 6], Y[:n + 6])
+    assert inf.n_appends == 5                      # the hyper-parameter change refitted first; the set_XY then appended
+    m.set_XY(X[:n + 2], Y[:n + 2])                 # fewer rows
+    assert inf.n_appends == 5
+    ref = GPy.models.GPRegression(X[:n + 2], Y[:n + 2], kernel=GPy.kern.Matern52(D, ARD=True, lengthscale=0.7), noise_var=0.05)
+    assert_allclose(m.log_likelihood(), ref.log_likelihood(), rtol=1e-10)
+
+
+@pytest.mark.gpu
+def test_bo_frozen_hyperparameters_incremental_matches_rebuild(monkeypatch):
+    """GPModel(max_iters=0): the hyper-parameters never move, so every updateModel is an append.  Same trajectory as rebuilding
+    the model on every step (what the reference does, gpmodel.py:78-93)."""
+    from gaussian_process_optimization_b200 import models as _models
+    res = {}
+    for incremental in (True, False):
+        monkeypatch.setattr(_models.ExactGaussianInference, "INCREMENTAL", incremental)
+        np.random.seed(3)
+        model = GPyOpt.models.GPModel(kernel=GPy.kern.Matern52(2, ARD=True, lengthscale=[4., 5.], variance=2.), exact_feval=True,
+                                      verbose=False, max_iters=0)
+        bo = GPyOpt.methods.BayesianOptimization(branin, domain=BRANIN_DOMAIN, model=model, acquisition_type='EI',
+                                                 exact_feval=True, initial_design_numdata=122, initial_design_type='random')
+        bo.run_optimization(max_iter=10)
+        res[incremental] = (bo.X.copy(), bo.Y.copy(), model.model.inference_method.n_appends)
+    assert res[True][2] >= 9 and res[False][2] == 0
+    assert res[True][0].shape == res[False][0].shape
+    assert_allclose(res[True][0], res[False][0], rtol=0, atol=1e-5 * 15)
