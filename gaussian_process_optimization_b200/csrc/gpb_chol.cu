@@ -12,6 +12,8 @@
 // so that every flop above the 128x128 leaves runs in the DMMA GEMM engine (gpb_gemm.cu) on large, regular tiles, and
 // Ky^-1 = M^T M is one more lower-tile GEMM.  Flops: N^3/3 (L) + N^3/3 (M) + N^3/3 (M^T M) = N^3, the same count as
 // dpotrf + dpotri.  The leaf factors a 128x128 block and inverts its factor in ONE fused rank-1 sweep held in registers.
+#include <stdlib.h>
+
 #include "gpb_common.cuh"
 
 namespace gpb {
@@ -209,7 +211,363 @@ leaf_potrf_inv_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Blocked leaf (MODE 0 only): the 128x128 block lives in shared memory as 8 x 8 sub-blocks of 16 x 16 and every flop outside
+// the 16 x 16 diagonal factorisations is a DMMA.8x8x4 issued by one of the 8 warps:
+//     for k = 0..7:   warp 0:     L_kk, M_kk = chol + inverse of the 16 x 16 diagonal block, in registers ([D | I] elimination,
+//                                 one column per lane, pivot column broadcast by shuffles)
+//                     warps 1-7:  meanwhile, block row k-1 of M:  M_(k-1)j = -M_(k-1)(k-1) sum_m L_(k-1)m M_mj
+//                     panel       L_ik = A_ik M_kk^T                      (i > k, one sub-block per warp)
+//                     trailing    A_ij -= L_ik L_jk^T                     (i >= j > k, sub-blocks round robin over the warps)
+// The lower triangle of the shared array holds A -> L, the strictly-upper sub-blocks hold M^T, the diagonal sub-blocks of M sit
+// in their own array.  Row stride 132 == 4 (mod 16): the 8 x 4 DMMA operand fragments are bank-conflict free in both
+// orientations ([row][k] and [k][row]).  The serial chain is 128 pivots x ~100 cycles instead of 128 block-wide barriers.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef GPB_LEAF_TIMING
+__device__ long long g_leaf_clk[64];
+#define LEAF_CLK(i) do { if (threadIdx.x == 0) g_leaf_clk[i] = clock64(); } while (0)
+#else
+#define LEAF_CLK(i) do { } while (0)
+#endif
+constexpr int LB = 16;            // sub-block size
+constexpr int LNB = TILE / LB;    // 8 sub-blocks per side
+constexpr int LSD = TILE + 4;     // row stride of the 128 x 128 array
+constexpr int LMD = LB + 4;       // row stride of a 16 x 16 sub-block held separately
+
+__device__ __forceinline__ void leaf_dmma(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// c (16 x 16, as 2 x 2 accumulator fragments) += sa * A * B.  A_KM: A is stored [k][m] instead of [m][k]; B_KN: B is stored
+// [k][n] instead of [n][k].
+template <bool A_KM, bool B_KN>
+__device__ __forceinline__ void blk_mma(double (&c)[2][2][2], const double *__restrict__ A, int lda, const double *__restrict__ B,
+                                        int ldb, double sa, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < LB; kk += 4) {
+    double a[2], b[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      a[i] = sa * (A_KM ? A[(kk + t) * lda + 8 * i + g] : A[(8 * i + g) * lda + kk + t]);
+      b[i] = B_KN ? B[(kk + t) * ldb + 8 * i + g] : B[(8 * i + g) * ldb + kk + t];
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) leaf_dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+  }
+}
+__device__ __forceinline__ void blk_zero(double (&c)[2][2][2]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+}
+__device__ __forceinline__ void blk_load(double (&c)[2][2][2], const double *S, int ld, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double2 v = *reinterpret_cast<const double2 *>(S + (8 * i + g) * ld + 8 * j + 2 * t);
+      c[i][j][0] = v.x;
+      c[i][j][1] = v.y;
+    }
+}
+__device__ __forceinline__ void blk_store(const double (&c)[2][2][2], double *S, int ld, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) *reinterpret_cast<double2 *>(S + (8 * i + g) * ld + 8 * j + 2 * t) = make_double2(c[i][j][0], c[i][j][1]);
+}
+// S[n][m] = c(m, n)
+__device__ __forceinline__ void blk_store_t(const double (&c)[2][2][2], double *S, int ld, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      S[(8 * j + 2 * t) * ld + 8 * i + g] = c[i][j][0];
+      S[(8 * j + 2 * t + 1) * ld + 8 * i + g] = c[i][j][1];
+    }
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// fp64 reciprocal / reciprocal square root off the MUFU seed (~20 bits) + Newton steps: a few dependent DFMAs instead of the
+// division / sqrt slow paths; the pivot chain of the diagonal sub-blocks is the critical path of the leaf.  Not correctly
+// rounded (<= 1 ulp); non-positive or NaN inputs give garbage, which the caller has already flagged as "not positive definite".
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const double e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
+  return y;
+}
+
+// One warp: D (16 x 16 symmetric positive definite, lower triangle stored at Dblk) -> L (lower triangle written back in place)
+// and M = L^-1 (full 16 x 16 with explicit zeros above the diagonal, written to Mblk).  Lane y < 16 holds column y of D, lane
+// 16 + y column y of the identity; the row operations row_x -= (D_xj / D_jj) row_j, x > j, leave U = diag(p) Lt^T in the D
+// part and Lt^-1 (unit lower) in the identity part; L = Lt diag(sqrt p), M = diag(1 / sqrt p) Lt^-1.
+// Per pivot the dependent chain is: shuffle (pivot) -> MUFU seed -> 3 DFMA (third-order Newton step, folded into the scaled
+// pivot-row entry t) -> DFMA (update) -> next shuffle; the column entries arrive by shuffles that do not depend on the pivot.
+// Returns 0 or 1 + index of the first non-positive pivot.
+__device__ __forceinline__ int leaf_diag_factor(double *Dblk, double *Mblk, int lane) {
+  const int y = lane & 15;
+  const bool is_d = lane < 16;
+  double v[LB], p[LB];
+#pragma unroll
+  for (int x = 0; x < LB; ++x) {
+    const double dv = (x >= y) ? Dblk[x * LSD + y] : Dblk[y * LSD + x];
+    v[x] = is_d ? dv : (x == y ? 1.0 : 0.0);
+  }
+  int fail = 0;
+#pragma unroll
+  for (int j = 0; j < LB; ++j) {
+    const double pj = shfl_d(v[j], j);
+    p[j] = pj;
+    if (!(pj > 0.0) && fail == 0) fail = j + 1;
+    // t = -v[j] / pj:  r0 ~ 1/pj (20 bits), e = 1 - pj r0, 1/pj = r0 (1 + e + e^2 + O(e^3))
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(pj));
+    const double t0 = -r0 * v[j];
+    const double e = fma(-pj, r0, 1.0);
+    const double s2 = fma(e, e, e);
+    const double t = fma(t0, s2, t0);
+#pragma unroll
+    for (int x = j + 1; x < LB; ++x) v[x] = fma(shfl_d(v[x], j), t, v[x]);
+  }
+  double py = p[0];
+#pragma unroll
+  for (int x = 1; x < LB; ++x) py = (x == y) ? p[x] : py;
+  const double rs_own = fast_rsqrt(py);
+  // branch-free write-out: lanes < 16 store row y of L (x <= y), lanes >= 16 column y of M
+  double *dst = is_d ? Dblk + y * LSD : Mblk + y;
+  const int step = is_d ? 1 : LMD;
+  const int xmax = is_d ? y : LB;
+#pragma unroll
+  for (int x = 0; x < LB; ++x) {
+    const double val = v[x] * shfl_d(rs_own, x);   // L[y][x] = U[x][y] / sqrt(p_x);  M[x][y] = Lt^-1[x][y] / sqrt(p_x)
+    if (x <= xmax) dst[x * step] = val;
+  }
+  return fail;
+}
+
+// Diagonal sub-block k of both results, shared -> global (one warp; row segments of 128 bytes; zeros above the diagonal of L)
+__device__ __forceinline__ void leaf_diag_writeout(const double *Dblk, const double *Mblk, double *__restrict__ gL, int lda,
+                                                   double *__restrict__ gM, int ldm, int lane) {
+  const int y = lane & 15;
+#pragma unroll
+  for (int it = 0; it < LB / 2; ++it) {
+    const int r = 2 * it + (lane >> 4);
+    gL[(size_t)r * lda + y] = (y <= r) ? Dblk[r * LSD + y] : 0.0;
+    gM[(size_t)r * ldm + y] = Mblk[r * LMD + y];
+  }
+}
+
+// c (accumulator fragments) -> global 16 x 16 sub-block, 16 bytes per lane
+__device__ __forceinline__ void blk_store_global(const double (&c)[2][2][2], double *__restrict__ G, int ld, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<double2 *>(G + (size_t)(8 * i + g) * ld + 8 * j + 2 * t) = make_double2(c[i][j][0], c[i][j][1]);
+}
+
+// Block row r of M (off-diagonal part):   M_rj = -M_rr T_rj,  T_rj = sum_{m=j}^{r-1} L_rm M_mj.
+// leaf_inv_accum adds the terms m_lo <= m < m_hi to the accumulators; leaf_inv_finish multiplies by -M_rr, keeps the result
+// transposed in the upper triangle of S (operand of the rows below) and writes it to Mi.
+__device__ __forceinline__ void leaf_inv_accum(double (&c)[2][2][2], const double *S, const double *Md, int r, int j, int m_lo, int m_hi,
+                                               int lane) {
+  for (int m = m_lo; m < m_hi; ++m) {
+    if (m == j)
+      blk_mma<false, true>(c, S + (r * LB) * LSD + j * LB, LSD, Md + j * LB * LMD, LMD, 1.0, lane);            // M_jj
+    else
+      blk_mma<false, false>(c, S + (r * LB) * LSD + m * LB, LSD, S + (j * LB) * LSD + m * LB, LSD, 1.0, lane);  // M_mj stored transposed
+  }
+}
+__device__ __forceinline__ void leaf_inv_finish(double (&c)[2][2][2], double *S, const double *Md, double *T, double *__restrict__ Mi,
+                                                int ldm, int r, int j, int lane) {
+  __syncwarp();
+  blk_store(c, T, LMD, lane);
+  __syncwarp();
+  blk_zero(c);
+  blk_mma<false, true>(c, Md + r * LB * LMD, LMD, T, LMD, -1.0, lane);
+  blk_store_t(c, S + (j * LB) * LSD + r * LB, LSD, lane);
+  blk_store_global(c, Mi + (size_t)(r * LB) * ldm + j * LB, ldm, lane);
+}
+// tasks j = w, w + nw, ... < r
+__device__ __forceinline__ void leaf_inverse_row(double *S, const double *Md, double *T, double *__restrict__ Mi, int ldm, int r, int w,
+                                                 int nw, int lane) {
+  for (int j = w; j < r; j += nw) {
+    double c[2][2][2];
+    blk_zero(c);
+    leaf_inv_accum(c, S, Md, r, j, j, r, lane);
+    leaf_inv_finish(c, S, Md, T, Mi, ldm, r, j, lane);
+  }
+}
+
+// A_ij -= L_ik L_jk^T for one sub-block
+__device__ __forceinline__ void leaf_trailing_block(double *S, int bi, int bj, int k, int lane) {
+  double c[2][2][2];
+  double *blk = S + (bi * LB) * LSD + bj * LB;
+  blk_load(c, blk, LSD, lane);
+  blk_mma<false, false>(c, S + (bi * LB) * LSD + k * LB, LSD, S + (bj * LB) * LSD + k * LB, LSD, -1.0, lane);
+  blk_store(c, blk, LSD, lane);
+}
+
+__device__ __forceinline__ void leaf_cp_async16(double *smem_dst, const double *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+
+// Schedule (look-ahead): after the panel of step k, warp 0 updates the next diagonal sub-block and factors it right away while
+// warps 1-7 finish the trailing update of step k and compute block row k of M; one barrier pair per step.  Results leave for
+// global memory from the accumulator fragments as they are produced (no epilogue); the zeros above the diagonal are stored
+// first and complete under the computation.
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_blocked_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, int ldm, int index_base, int *info) {
+  extern __shared__ double sm[];
+  double *S = sm;                          // 128 x 132
+  double *Md = S + TILE * LSD;             // 8 x (16 x 20): diagonal sub-blocks of M
+  double *Tw = Md + LNB * LB * LMD;        // 8 x (16 x 20): per-warp scratch
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role branches below stay convergent
+  constexpr int NW = LEAF_THREADS / 32;
+  double *T = Tw + warp * LB * LMD;
+  LEAF_CLK(0);
+  // lower triangle of the block -> shared memory (asynchronous copies, all in flight together)
+#pragma unroll
+  for (int it = 0; it < TILE * (TILE / 2) / LEAF_THREADS; ++it) {
+    const int e = tid + it * LEAF_THREADS, r = e >> 6, c = (e & 63) * 2;
+    if (c <= r) leaf_cp_async16(S + r * LSD + c, A + (size_t)r * lda + c);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  LEAF_CLK(1);
+
+  int fail = 0;
+  double pre[2][2][2];   // warps 1-7: partial sum of their task of the last block row of M, carried across the last barrier
+  blk_zero(pre);
+  // step k = -1 only factors the first diagonal sub-block (one code site for the factorisation: it stays in the instruction cache)
+#pragma unroll 1
+  for (int k = -1; k < LNB; ++k) {
+    LEAF_CLK(2 + 4 * (k + 1));
+    if (k >= 0) {
+      // panel: L_ik = A_ik M_kk^T; warp 0 has sub-block k+1 and goes straight on to the next diagonal sub-block, the others
+      // wait (named barrier 1) until the whole panel is in shared memory
+      for (int i = k + 1 + warp; i < LNB; i += NW) {
+        double c[2][2][2];
+        blk_zero(c);
+        double *blk = S + (i * LB) * LSD + k * LB;
+        blk_mma<false, false>(c, blk, LSD, Md + k * LB * LMD, LMD, 1.0, lane);
+        __syncwarp();
+        blk_store(c, blk, LSD, lane);
+        blk_store_global(c, A + (size_t)(i * LB) * lda + k * LB, lda, lane);
+      }
+      if (warp == 0) {
+        __threadfence_block();
+        asm volatile("bar.arrive 1, %0;" ::"n"(LEAF_THREADS) : "memory");
+      } else {
+        asm volatile("bar.sync 1, %0;" ::"n"(LEAF_THREADS) : "memory");
+      }
+    }
+    LEAF_CLK(3 + 4 * (k + 1));
+    if (warp == 0) {
+      if (k + 1 < LNB) {
+        if (k >= 0) {
+          __syncwarp();
+          leaf_trailing_block(S, k + 1, k + 1, k, lane);
+          __syncwarp();
+        }
+        const int o = (k + 1) * LB;
+        const int f = leaf_diag_factor(S + o * LSD + o, Md + (k + 1) * LB * LMD, lane);
+        if (f != 0 && fail == 0) fail = o + f;
+      }
+      LEAF_CLK(4 + 4 * (k + 1));
+    } else if (k < 0) {
+      // meanwhile: explicit zeros above the diagonal of both outputs, outside the diagonal sub-blocks (leaf_diag_writeout has
+      // those); plain stores that complete under the computation
+      for (int e = tid - 32; e < TILE * (TILE / 2); e += LEAF_THREADS - 32) {
+        const int r = e >> 6, c = (e & 63) * 2;
+        if (c > r && (c >> 4) != (r >> 4)) {
+          *reinterpret_cast<double2 *>(A + (size_t)r * lda + c) = make_double2(0.0, 0.0);
+          *reinterpret_cast<double2 *>(Mi + (size_t)r * ldm + c) = make_double2(0.0, 0.0);
+        }
+      }
+    } else {
+      if (warp == 1 + (k % (NW - 1))) {
+        const int o = k * LB;
+        leaf_diag_writeout(S + o * LSD + o, Md + k * LB * LMD, A + (size_t)o * lda + o, lda, Mi + (size_t)o * ldm + o, ldm, lane);
+      }
+      // trailing update A_ij -= L_ik L_jk^T, i >= j > k, without the next diagonal sub-block (warp 0 has it)
+      const int nt = (LNB - 1 - k) * (LNB - k) / 2;
+      for (int t = warp; t < nt; t += NW - 1) {   // t = 0 is sub-block (k+1, k+1)
+        int i = 0, rem = t;
+        while (rem > i) {
+          rem -= i + 1;
+          ++i;
+        }
+        leaf_trailing_block(S, k + 1 + i, k + 1 + rem, k, lane);
+      }
+      // The last block row of M is the only one without a diagonal factorisation to hide under: warp w owns its task
+      // j = LNB - 1 - w and sums the terms m < LNB - 2 one step early (they only need finished rows of M); the pairing evens out
+      // the work with this step's row (task w - 1), so that only two products per warp remain after the last factorisation.
+      const int jl = LNB - 1 - warp;
+      if (k + 1 < LNB) {
+        leaf_inverse_row(S, Md, T, Mi, ldm, k, warp - 1, NW - 1, lane);
+        if (k + 2 == LNB) {
+          blk_zero(pre);
+          leaf_inv_accum(pre, S, Md, LNB - 1, jl, jl, LNB - 2, lane);
+        }
+      } else {
+        leaf_inv_accum(pre, S, Md, LNB - 1, jl, jl > LNB - 2 ? jl : LNB - 2, LNB - 1, lane);
+        leaf_inv_finish(pre, S, Md, T, Mi, ldm, LNB - 1, jl, lane);
+      }
+    }
+    __syncthreads();
+    LEAF_CLK(5 + 4 * (k + 1));
+  }
+  if (warp == 0 && lane == 0 && fail != 0) atomicCAS(info, 0, index_base + fail);
+  LEAF_CLK(40);
+  LEAF_CLK(41);
+}
+
+static int g_leaf_variant = -1;  // 1: blocked DMMA leaf (default), 0: register rank-1 sweep (GPB_LEAF=0)
+
 static int launch_leaf(Factor &f, int off, int mode) {
+  if (g_leaf_variant < 0) {
+    const char *e = getenv("GPB_LEAF");
+    g_leaf_variant = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (mode == 0 && g_leaf_variant == 1) {
+    const size_t smem_b = (size_t)(TILE * LSD + 2 * LNB * LB * LMD) * sizeof(double);
+    static unsigned long long configured_b = 0;
+    if (needs_func_config(configured_b))
+      GPB_CUDA(cudaFuncSetAttribute(leaf_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    leaf_blocked_kernel<<<1, LEAF_THREADS, smem_b, f.stream>>>(f.A + (size_t)off * f.np + off, f.np, f.Mi + (size_t)off * f.np + off,
+                                                               f.np, off, f.info);
+    count_launch();
+    GPB_CHECK_LAUNCH();
+    return 0;
+  }
   const size_t smem = (size_t)(2 + 3 * TILE + TILE * LEAF_LD) * sizeof(double);
   static unsigned long long configured = 0;
   if (needs_func_config(configured)) {
