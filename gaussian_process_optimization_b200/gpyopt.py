@@ -765,10 +765,43 @@ class AcquisitionOptimizer(object):
         self.f, self.df, self.f_df = f, df, f_df
         self.optimizer = OptLbfgs(self.space.get_bounds())
         anchor_points = ObjectiveAnchorPointsGenerator(self.space, 'random', f).get(duplicate_manager=duplicate_manager)
-        optimized_points = [apply_optimizer(self.optimizer, a, f=f, df=None, f_df=f_df, duplicate_manager=duplicate_manager,
-                                            space=self.space) for a in anchor_points]
+        run = lambda a: apply_optimizer(self.optimizer, a, f=f, df=None, f_df=f_df, duplicate_manager=duplicate_manager,  # noqa: E731
+                                        space=self.space)
+        world, rank = self._world()
+        if world > 1:
+            optimized_points = self._optimize_anchors_distributed(anchor_points, run, world, rank)
+        else:
+            optimized_points = [run(a) for a in anchor_points]
         x_min, fx_min = min(optimized_points, key=lambda t: t[1])
         return x_min, fx_min
+
+    # -- one L-BFGS-B refinement per torch.distributed rank (kwarg distributed_anchors=True) ---------------------------------
+    # The refinements of the anchor points (acquisition_optimizer.py:68-72) are independent and deterministic, so rank r runs
+    # anchors r, r + world, ...; one all-reduce of an (anchors x (1 + d)) table (every row written by exactly one rank) gives
+    # every rank the list the sequential loop would have produced, in the same order: same minimum, same tie-breaking.  Every
+    # rank must hold the same model and the same NumPy RNG state (the anchors are drawn on every rank).
+    def _world(self):
+        if not self.kwargs.get('distributed_anchors', False):
+            return 1, 0
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1, 0
+        return dist.get_world_size(), dist.get_rank()
+
+    def _optimize_anchors_distributed(self, anchor_points, run, world, rank):
+        import torch
+        import torch.distributed as dist
+        anchor_points = np.atleast_2d(anchor_points)
+        na, d = anchor_points.shape
+        table = np.full((na, 1 + d), np.inf)
+        for i in range(rank, na, world):
+            x, fx = run(anchor_points[i])
+            table[i, 0], table[i, 1:] = float(np.asarray(fx).ravel()[0]), np.asarray(x).ravel()
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(table).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        table = t.cpu().numpy()
+        return [(table[i, 1:][None, :].copy(), np.array([[table[i, 0]]])) for i in range(na)]
 
 
 class Sequential(object):
@@ -970,7 +1003,8 @@ class BayesianOptimization(BO):
         else:
             self.model = self._model_chooser()
         self.acquisition_optimizer_type = acquisition_optimizer_type
-        self.acquisition_optimizer = AcquisitionOptimizer(self.space, self.acquisition_optimizer_type, model=self.model)
+        self.acquisition_optimizer = AcquisitionOptimizer(self.space, self.acquisition_optimizer_type, model=self.model,
+                                                          distributed_anchors=kwargs.get('distributed_anchors', False))
         self.acquisition_type = acquisition_type
         if 'acquisition' in kwargs and isinstance(kwargs['acquisition'], AcquisitionBase):
             self.acquisition = kwargs['acquisition']

@@ -405,6 +405,42 @@ def test_distributed_restarts_match_sequential(tmp_path):
         assert z["rng"] == rng_after            # the global NumPy stream advanced exactly as in the sequential run
 
 
+def _anchor_bo(distributed):
+    np.random.seed(7)
+    model = make_gpmodel("oracle", kernel=GPy.kern.Matern52(2), exact_feval=True, verbose=False, optimize_restarts=1)
+    bo = GPyOpt.methods.BayesianOptimization(branin, domain=BRANIN_DOMAIN, model=model, acquisition_type='EI', exact_feval=True,
+                                             initial_design_numdata=6, evaluator_type='local_penalization', batch_size=2,
+                                             distributed_anchors=distributed)
+    bo.run_optimization(max_iter=2)
+    return bo.X.copy(), bo.Y.copy(), np.random.uniform()
+
+
+def _anchor_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, Y, rng = _anchor_bo(True)
+    np.savez(out % rank, X=X, Y=Y, rng=rng)
+    dist.destroy_process_group()
+
+
+def test_distributed_anchor_refinement_matches_sequential(tmp_path):
+    """AcquisitionOptimizer(distributed_anchors=True): one L-BFGS-B refinement per rank (gloo, world size 2); the BO run
+    (local-penalisation batches) proposes the same points as the sequential loop and leaves the NumPy stream in the same state."""
+    import os
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "a%d.npz")
+    mp.spawn(_anchor_worker, args=(2, 31700 + (os.getpid() % 2000), out), nprocs=2, join=True)
+    X, Y, rng = _anchor_bo(False)
+    for r in range(2):
+        z = np.load(out % r)
+        assert_allclose(z["X"], X, rtol=0, atol=1e-12)
+        assert_allclose(z["Y"], Y, rtol=0, atol=1e-12)
+        assert z["rng"] == rng
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # The reference's local Gower mixed-variable kernel patch (stationary.py:116-135), as run.py uses it (Gower=True)
 # ---------------------------------------------------------------------------------------------------------------------
