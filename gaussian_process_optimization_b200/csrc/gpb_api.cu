@@ -648,11 +648,26 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
     XcK = m->XcgT;
   }
   GPB_TRY(launch_kmat(m->kind, XcK, cpad, kc.XT, np, d, mcb, n, kc.var, 0.0, 2, m->KxT, np, cpad, np, s, kc.gflag));
+  // A handful of candidates (the M = 1 calls of the L-BFGS-B refinement, optimizer.py:46-51): one bandwidth-bound pass over
+  // the triangle of M per product instead of a 128-row padded GEMM, and the row reductions (mean, variance, both input
+  // gradients) split over the training points in one fused pass (launch_skinny_moments) instead of one warp per candidate.
+  const bool skinny = mcb <= 8;
+  if (skinny && p == 1) {
+    const double var_base = m->variance + (include_likelihood ? m->noise : 0.0);
+    const double *Vt = nullptr, *Ut = nullptr;
+    if (level == 1 || level == 2) {
+      const int c = mcb <= 1 ? 1 : mcb <= 2 ? 2 : mcb <= 4 ? 4 : 8;   // rows mcb .. c of KxT are zero (mode 2 padding)
+      GPB_TRY(factor_skinny_products(m->f, c, m->KxT, np, m->Vt, np, level >= 2 ? m->Ut : nullptr, np, m->f.part));
+      Vt = m->Vt;
+      if (level == 2) Ut = m->Ut;
+    }
+    // mu = Kx^T alpha; var = Kdiag - sum(tmp^2) (+ noise); dmu = gradients_X(alpha^T, X*, X); dvar = gradients_X(-2 Kx^T Wi, X*, X)
+    //                                                         posterior.py:276,294-295, gaussian.py:109, core/gp.py:431-434,450-453
+    return launch_skinny_moments(m->kind, m->KxT, Vt, Ut, np, mcb, n, m->alpha, m->XcT, cpad, m->XsT, np, d, m->variance, m->inv_ls_dev,
+                                 var_base, level >= 2 ? 1 : 0, m->f.part, m->mu, m->var, m->dmu, m->dvar, s);
+  }
   // mu = Kx^T alpha                                                 posterior.py:276
   GPB_TRY(launch_rowdot(m->KxT, np, mcb, n, m->alpha, np, p, m->mu, s));
-  // A handful of candidates (the M = 1 calls of the L-BFGS-B refinement, optimizer.py:46-51): one bandwidth-bound pass over
-  // the triangle of M per product instead of a 128-row padded GEMM.
-  const bool skinny = mcb <= 8;
   if (level == 3) {
     GPB_REQUIRE(p == 1, "predictive gradients are implemented for a single output column (got %d)", p);
     GPB_TRY(launch_gradx(m->kind, m->XcT, cpad, mcb, m->XsT, np, n, d, m->variance, m->inv_ls_dev, m->alpha, 0, 1.0, 0, nullptr, 0,

@@ -927,37 +927,41 @@ __global__ void __launch_bounds__(256) trmm_lower_skinny_kernel(const double *__
 
 constexpr int TRMM_T_SPLITS = 16;
 
-// part[(c * S + s) * np + j] = sum over the 128-row chunks rc >= cb with rc % S == s of sum_i M[i][j] Z[c][i]
+// Column block cb (128 columns) has nb - cb row chunks below and on the diagonal; they are cut into runs of `run` consecutive
+// chunks, one CTA each, so that every CTA streams about the same number of bytes (a fixed number of splits per column block
+// left the CTAs of the short columns idle for half of the kernel).  run = ceil(nb / TRMM_T_SPLITS) keeps splits <= 16.
+//   part[(c * S + s) * np + j] = sum over the rows of run s of column block j / 128 of  M[i][j] Z[c][i]
 template <int C>
 __global__ void __launch_bounds__(TILE) trmm_lower_t_skinny_partial_kernel(const double *__restrict__ M, int ld,
                                                                            const double *__restrict__ Z, int ldz,
-                                                                           double *__restrict__ part, int np) {
+                                                                           double *__restrict__ part, int np, int run) {
   const int cb = blockIdx.x, s = blockIdx.y, nb = np / TILE;
+  const int rc0 = cb + s * run, rc1 = min(nb, rc0 + run);
+  if (rc0 >= nb) return;
   const int j = cb * TILE + threadIdx.x;
   double acc[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) acc[c] = 0.0;
-  int rc = cb + ((s - cb) % TRMM_T_SPLITS + TRMM_T_SPLITS) % TRMM_T_SPLITS;  // first chunk >= cb congruent to s
-  for (; rc < nb; rc += TRMM_T_SPLITS) {
-    const double *p = M + (size_t)(rc * TILE) * ld + j;
-    const double *zz = Z + rc * TILE;
-#pragma unroll 8
-    for (int i = 0; i < TILE; ++i) {
-      const double m = p[(size_t)i * ld];
+  const double *p = M + (size_t)(rc0 * TILE) * ld + j;
+  const double *zz = Z + rc0 * TILE;
+  const int rows = (rc1 - rc0) * TILE;
+#pragma unroll 16
+  for (int i = 0; i < rows; ++i) {
+    const double m = p[(size_t)i * ld];
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = fma(m, zz[(size_t)c * ldz + i], acc[c]);
-    }
+    for (int c = 0; c < C; ++c) acc[c] = fma(m, zz[(size_t)c * ldz + i], acc[c]);
   }
 #pragma unroll
   for (int c = 0; c < C; ++c) part[((size_t)c * TRMM_T_SPLITS + s) * np + j] = acc[c];
 }
 
-__global__ void trmm_lower_t_skinny_reduce_kernel(const double *__restrict__ part, int np, int C, double *__restrict__ U, int ldu) {
+__global__ void trmm_lower_t_skinny_reduce_kernel(const double *__restrict__ part, int np, int C, double *__restrict__ U, int ldu, int run) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
   if (j >= np || c >= C) return;
+  const int nb = np / TILE, cb = j / TILE;
+  const int splits = (nb - cb + run - 1) / run;   // runs that exist for this column block
   double acc = 0.0;
-#pragma unroll
-  for (int s = 0; s < TRMM_T_SPLITS; ++s) acc += part[((size_t)c * TRMM_T_SPLITS + s) * np + j];
+  for (int s = 0; s < splits; ++s) acc += part[((size_t)c * TRMM_T_SPLITS + s) * np + j];
   U[(size_t)c * ldu + j] = acc;
 }
 
@@ -967,6 +971,7 @@ int factor_skinny_products(Factor &f, int c, const double *B, int ldb, double *Z
   GPB_REQUIRE(c == 1 || c == 2 || c == 4 || c == 8, "skinny products: C must be 1, 2, 4 or 8 (got %d)", c);
   const int np = f.np, nb = np / TILE;
   const int blocks = (np * 32 + 255) / 256;
+  const int run = (nb + TRMM_T_SPLITS - 1) / TRMM_T_SPLITS;
   const dim3 gp(nb, TRMM_T_SPLITS), gr((np + 255) / 256, c);
 #define GPB_SK(C_)                                                                                     \
   do {                                                                                                 \
@@ -974,9 +979,9 @@ int factor_skinny_products(Factor &f, int c, const double *B, int ldb, double *Z
     GPB_CHECK_LAUNCH();                                                                                \
     count_launch();                                                                                    \
     if (U) {                                                                                           \
-      trmm_lower_t_skinny_partial_kernel<C_><<<gp, TILE, 0, f.stream>>>(f.Mi, np, Z, ldz, part, np);    \
+      trmm_lower_t_skinny_partial_kernel<C_><<<gp, TILE, 0, f.stream>>>(f.Mi, np, Z, ldz, part, np, run); \
       GPB_CHECK_LAUNCH();                                                                              \
-      trmm_lower_t_skinny_reduce_kernel<<<gr, 256, 0, f.stream>>>(part, np, C_, U, ldu);               \
+      trmm_lower_t_skinny_reduce_kernel<<<gr, 256, 0, f.stream>>>(part, np, C_, U, ldu, run);          \
       GPB_CHECK_LAUNCH();                                                                              \
       count_launch(2);                                                                                 \
     }                                                                                                  \

@@ -41,6 +41,13 @@ int launch_gradx(int kind, const double *XcT, int ldc, int n_c, const double *XT
 int launch_rowdot(const double *KxT, int ld, int n_c, int n, const double *alpha, int ld_alpha, int p, double *mu, cudaStream_t s);
 // var[c] = base - sum_n Vt[c][n]^2
 int launch_var_from_vt(const double *Vt, int ld, int n_c, int n, double base, double *var, cudaStream_t s);
+// n_c <= 8 candidates: mu (KxT), var = var_base - sum Vt^2 (Vt), dmu (want_g) and dvar (want_g, Ut) with the training points split
+// over many CTAs; part: skinny_moments_part_doubles(n_c, np, d) doubles of scratch
+size_t skinny_moments_part_doubles(int n_c, int np, int d);
+int launch_skinny_moments(int kind, const double *KxT, const double *Vt, const double *Ut, int ld, int n_c, int n, const double *alpha,
+                          const double *XcT, int ldc, const double *XT, int ldx, int d, double variance, const double *inv_ls,
+                          double var_base, int want_g, double *part, double *mu, double *var, double *dmu, double *dvar,
+                          cudaStream_t s);
 // GPModel.predict clip + get_quantiles + EI/LCB (+ gradients) + AcquisitionBase sign
 int launch_acq_epilogue(int acq, double par, double fmin, int n_c, int d, const double *mu, const double *var, const double *dmu,
                         const double *dvar, double *f, double *df, double *mean_out, double *sd_out, double *dmdx_out,

@@ -7,6 +7,8 @@
 // anchor selection np.argsort(scores)[:k] (optimization/anchor_points_generator.py:58-63).
 #include <float.h>
 
+#include <algorithm>
+
 #include "gpb_common.cuh"
 #include "gpb_kernels.cuh"
 
@@ -50,6 +52,147 @@ int launch_var_from_vt(const double *Vt, int ld, int n_c, int n, double base, do
   count_launch();
   GPB_CHECK_LAUNCH();
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A handful of candidates (the M = 1 .. 8 calls L-BFGS-B makes from every anchor point, optimizer.py:46-51, and estimate_L's
+// calls, batch_local_penalization.py:56-58): one warp per candidate leaves 147 SMs idle and serialises N / 32 dependent
+// iterations.  Here the training points are split over `splits` CTAs per candidate; one kernel forms the partial sums of
+//     mu = Kx^T alpha,   sum_n Vt^2,   d mu / dx* = gradients_X(alpha^T),   d var / dx* = gradients_X(-2 Kx^T Ky^-1)
+// (posterior.py:276,294; core/gp.py:431-434,450-453; stationary.py:354-364) and a second one adds the partials in a fixed order
+// (bitwise reproducible run to run) and applies the scalings.  Slots per (candidate, split): [mu, vv, g1[DCAP], g2[DCAP]].
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SKM_THREADS = 128;
+
+template <int KIND, int DCAP>
+__global__ void __launch_bounds__(SKM_THREADS) skinny_moments_partial_kernel(
+    const double *__restrict__ KxT, const double *__restrict__ Vt, const double *__restrict__ Ut, int ld, int n, int chunk,
+    const double *__restrict__ alpha, const double *__restrict__ XcT, int ldc, const double *__restrict__ XT, int ldx, int d,
+    double variance, int want_g, double *__restrict__ part) {
+  constexpr int K = 2 + 2 * DCAP;
+  __shared__ double red[SKM_THREADS / 32][K];
+  const int c = blockIdx.y, sp = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j0 = sp * chunk, j1 = min(n, j0 + chunk);
+  double acc[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) acc[i] = 0.0;
+  double xc[DCAP];
+#pragma unroll
+  for (int q = 0; q < DCAP; ++q) xc[q] = (want_g && q < d) ? XcT[(size_t)q * ldc + c] : 0.0;
+  for (int j = j0 + tid; j < j1; j += SKM_THREADS) {
+    const double a = alpha[j];
+    if (KxT) acc[0] = fma(KxT[(size_t)c * ld + j], a, acc[0]);
+    if (Vt) {
+      const double v = Vt[(size_t)c * ld + j];
+      acc[1] = fma(v, v, acc[1]);
+    }
+    if (want_g) {
+      double df[DCAP], r2 = 0.0;
+#pragma unroll
+      for (int q = 0; q < DCAP; ++q) {
+        df[q] = (q < d) ? xc[q] - XT[(size_t)q * ldx + j] : 0.0;
+        r2 = fma(df[q], df[q], r2);
+      }
+      double k, dk;
+      cov_k_dk<KIND>(r2, variance, k, dk);
+      const double w1 = dk * a;
+      const double w2 = Ut ? dk * Ut[(size_t)c * ld + j] : 0.0;
+#pragma unroll
+      for (int q = 0; q < DCAP; ++q) {
+        acc[2 + q] = fma(w1, df[q], acc[2 + q]);
+        acc[2 + DCAP + q] = fma(w2, df[q], acc[2 + DCAP + q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    const double v = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < K; i += SKM_THREADS) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < SKM_THREADS / 32; ++w) v += red[w][i];
+    part[((size_t)c * gridDim.x + sp) * K + i] = v;
+  }
+}
+
+// grid (K, n_c): slot i of candidate c = sum over the splits, then scaled and stored where the one-warp kernels put it
+template <int DCAP>
+__global__ void __launch_bounds__(128) skinny_moments_reduce_kernel(const double *__restrict__ part, int splits, int d, double var_base,
+                                                                    const double *__restrict__ inv_ls, double s1, double s2,
+                                                                    double *__restrict__ mu, double *__restrict__ var,
+                                                                    double *__restrict__ dmu, double *__restrict__ dvar) {
+  constexpr int K = 2 + 2 * DCAP;
+  __shared__ double scratch[32];
+  const int i = blockIdx.x, c = blockIdx.y;
+  double acc = 0.0;
+  for (int sp = threadIdx.x; sp < splits; sp += 128) acc += part[((size_t)c * splits + sp) * K + i];
+  acc = block_sum<128>(acc, scratch);
+  if (threadIdx.x != 0) return;
+  if (i == 0) {
+    if (mu) mu[c] = acc;
+  } else if (i == 1) {
+    if (var) var[c] = var_base - acc;
+  } else if (i < 2 + DCAP) {
+    const int q = i - 2;
+    if (dmu && q < d) dmu[(size_t)c * d + q] = s1 * inv_ls[q] * acc;
+  } else {
+    const int q = i - 2 - DCAP;
+    if (dvar && q < d) dvar[(size_t)c * d + q] = s2 * inv_ls[q] * acc;
+  }
+}
+
+size_t skinny_moments_part_doubles(int n_c, int np, int d) {
+  const int dcap = d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : 64;
+  return (size_t)n_c * (np / SKM_THREADS) * (2 + 2 * dcap);
+}
+
+template <int KIND, int DCAP>
+static int launch_skinny_moments_t(const double *KxT, const double *Vt, const double *Ut, int ld, int n_c, int n, const double *alpha,
+                                   const double *XcT, int ldc, const double *XT, int ldx, int d, double variance,
+                                   const double *inv_ls, double var_base, int want_g, double *part, double *mu, double *var,
+                                   double *dmu, double *dvar, cudaStream_t s) {
+  // about four CTAs per SM in total, at least one 128-point chunk each
+  const int max_splits = (n + SKM_THREADS - 1) / SKM_THREADS;
+  int splits = std::max(1, std::min(max_splits, (148 * 4) / n_c));
+  const int chunk = ((n + splits - 1) / splits + SKM_THREADS - 1) / SKM_THREADS * SKM_THREADS;
+  splits = (n + chunk - 1) / chunk;
+  skinny_moments_partial_kernel<KIND, DCAP><<<dim3(splits, n_c), SKM_THREADS, 0, s>>>(KxT, Vt, Ut, ld, n, chunk, alpha, XcT, ldc, XT, ldx,
+                                                                                    d, variance, want_g, part);
+  GPB_CHECK_LAUNCH();
+  skinny_moments_reduce_kernel<DCAP><<<dim3(2 + 2 * DCAP, n_c), 128, 0, s>>>(part, splits, d, var_base, inv_ls, 1.0, -2.0, mu, var, dmu,
+                                                                            dvar);
+  count_launch(2);
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+// mu (KxT != NULL), var = var_base - sum Vt^2 (Vt != NULL), dmu (want_g), dvar (want_g and Ut != NULL) for n_c <= 8 candidates
+int launch_skinny_moments(int kind, const double *KxT, const double *Vt, const double *Ut, int ld, int n_c, int n, const double *alpha,
+                          const double *XcT, int ldc, const double *XT, int ldx, int d, double variance, const double *inv_ls,
+                          double var_base, int want_g, double *part, double *mu, double *var, double *dmu, double *dvar,
+                          cudaStream_t s) {
+  if (n_c == 0) return 0;
+  GPB_REQUIRE(d <= 64, "gradients_X: input dimension %d > 64 not supported", d);
+#define GPB_SKM(K_, D_)                                                                                                          \
+  return launch_skinny_moments_t<K_, D_>(KxT, Vt, Ut, ld, n_c, n, alpha, XcT, ldc, XT, ldx, d, variance, inv_ls, var_base, want_g, \
+                                         part, mu, var, want_g ? dmu : nullptr, (want_g && Ut) ? dvar : nullptr, s)
+  if (kind == GPB_KERN_RBF) {
+    if (d <= 4) GPB_SKM(GPB_KERN_RBF, 4);
+    if (d <= 8) GPB_SKM(GPB_KERN_RBF, 8);
+    if (d <= 16) GPB_SKM(GPB_KERN_RBF, 16);
+    if (d <= 32) GPB_SKM(GPB_KERN_RBF, 32);
+    GPB_SKM(GPB_KERN_RBF, 64);
+  } else {
+    if (d <= 4) GPB_SKM(GPB_KERN_MATERN52, 4);
+    if (d <= 8) GPB_SKM(GPB_KERN_MATERN52, 8);
+    if (d <= 16) GPB_SKM(GPB_KERN_MATERN52, 16);
+    if (d <= 32) GPB_SKM(GPB_KERN_MATERN52, 32);
+    GPB_SKM(GPB_KERN_MATERN52, 64);
+  }
+#undef GPB_SKM
 }
 
 // One thread per candidate.  var already includes the likelihood variance (GP.predict include_likelihood=True).

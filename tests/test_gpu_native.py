@@ -318,11 +318,11 @@ def test_not_positive_definite_returns_info():
     m.close()
 
 
-@pytest.mark.parametrize("kind", ["rbf", "mat52"])
-def test_small_candidate_counts_use_the_skinny_products(kind):
+@pytest.mark.parametrize("kind,N,D", [("rbf", 700, 6), ("mat52", 700, 6), ("mat52", 1301, 20), ("rbf", 333, 40), ("mat52", 90, 3)])
+def test_small_candidate_counts_use_the_skinny_products(kind, N, D):
     """M = 1 .. 8 candidates (the L-BFGS-B refinement calls, optimizer.py:46-51) take the bandwidth-bound triangular
-    matrix-vector path; M = 9 takes the GEMM path.  Both must match the oracle and each other."""
-    N, D = 700, 6
+    matrix-vector path with the fused split-N row reductions; M = 9 takes the GEMM path.  Both must match the oracle and each
+    other (every register-array size of the reduction kernel: D <= 4, 8, 16, 32, 64; N not a multiple of the chunk)."""
     X, Y, ls = _synth(N, D)
     st = O.GPState(kind, X, Y, 1.1, ls, 1e-3)
     m = native.NativeModel(kind, True, D, 1, n_cap=N, cand_block=256)
@@ -344,6 +344,16 @@ def test_small_candidate_counts_use_the_skinny_products(kind):
         mu_r, var_r = O.predict(kind, st.post, X, Xc[:mc], 1.1, ls, 1e-3)
         assert_allclose(mu, mu_r, rtol=1e-9, atol=1e-11)
         assert_allclose(var, var_r, rtol=1e-9, atol=1e-12)
+        mu0, none = m.predict(Xc[:mc], want_var=False)                  # mean only
+        assert none is None
+        assert_allclose(mu0, mu, rtol=1e-13, atol=0)
+        dm, dv = m.predictive_gradients(Xc[:mc])
+        dm9, dv9 = m.predictive_gradients(Xc)
+        assert_allclose(dm, dm9[:mc], rtol=1e-9, atol=1e-12 * np.abs(dm9).max())
+        assert_allclose(dv, dv9[:mc], rtol=1e-9, atol=1e-12 * np.abs(dv9).max())
+        dm1, none = m.predictive_gradients(Xc[:mc], want_var=False)     # estimate_L's call: mean gradient only
+        assert none is None
+        assert_allclose(dm1, dm, rtol=1e-13, atol=0)
     m.close()
 
 
