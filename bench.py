@@ -271,6 +271,13 @@ def run_gpu(args, rank, world, local_rank):
         aux = bench_acquisition(args, model, rank, world, barrier)
     except Exception as exc:  # report, never hide
         aux = {"error": repr(exc)}
+    # ---- aux: the M = 1 value+gradient call L-BFGS-B makes from every anchor point (two HBM passes over the triangle of L^-1) ----
+    aux_m1 = None
+    if rank == 0:
+        try:
+            aux_m1 = bench_refinement_call(model)
+        except Exception as exc:
+            aux_m1 = {"error": repr(exc)}
     # ---- the other NLL+grad configurations of BASELINE.json (parity-test sizes; reported, not the headline) ----
     other = None
     if rank == 0:
@@ -323,6 +330,8 @@ def run_gpu(args, rank, world, local_rank):
             line["cpu_baseline"] = cpu
         if aux is not None:
             line["aux"] = aux
+        if aux_m1 is not None:
+            line["aux_m1"] = aux_m1
         if other is not None:
             line["other_configs"] = other
         print(json.dumps(line), flush=True)
@@ -354,6 +363,36 @@ def bench_other_configs(model16k):
         m.close()
         out[name] = {"ms_per_eval": best * 1e3, "evals_per_s": 1.0 / best,
                      "algorithmic_tflops": algorithmic_flops(N, D) / best / 1e12}
+    return out
+
+
+def bench_refinement_call(model):
+    """EI value + gradient at ONE candidate (optimizer.py:46-51: what L-BFGS-B calls hundreds of times per BO step), host in /
+    host out through the C ABI.  Bound: HBM -- M k* and M^T (M k*) each stream the lower triangle of M = L^-1 once."""
+    import torch
+    fmin = model.fmin()
+    rs = np.random.RandomState(77)
+    xs = rs.uniform(0, 1, (24, 1, DIM))
+    for i in range(4):
+        model.acquisition("EI", 0.01, fmin, xs[i], with_gradients=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(4, 24):
+        model.acquisition("EI", 0.01, fmin, xs[i], with_gradients=True)
+    torch.cuda.synchronize()
+    t = (time.perf_counter() - t0) / 20
+    nbytes = 2 * 8.0 * N_TRAIN * (N_TRAIN + 128) / 2          # two passes over the lower 128-blocks of M
+    peak = None
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    out = {"metric": "ei_value_gradient_m1_calls_per_s", "value": 1.0 / t, "unit": "calls/s", "ms_per_call": t * 1e3, "model_N": N_TRAIN,
+           "D": DIM, "roofline": {"bound": "hbm", "achieved": nbytes / t / 1e9, "unit": "GB/s", "peak": peak,
+                                  "frac": (nbytes / t / 1e9 / peak) if peak else None,
+                                  "algorithmic_bytes_per_call": nbytes,
+                                  "note": "wall clock around the whole C-ABI call (H2D of x*, 9 launches, D2H of f and df), not the "
+                                          "two streaming kernels alone; peak = MEASURED_PEAKS.json hbm_gbs"}}
     return out
 
 

@@ -651,3 +651,22 @@ def test_bo_frozen_hyperparameters_incremental_matches_rebuild(monkeypatch):
     assert res[True][2] >= 9 and res[False][2] == 0
     assert res[True][0].shape == res[False][0].shape
     assert_allclose(res[True][0], res[False][0], rtol=0, atol=1e-5 * 15)
+
+
+@pytest.mark.gpu
+def test_set_xy_append_under_the_gower_patch():
+    """The appended block rows are built with the same (Gower) covariance as a rebuild (run.py's configuration: Gower=True)."""
+    space = GPyOpt.Design_space(GOWER_DOMAIN)
+    np.random.seed(2)
+    X = GPyOpt.experiment_design.initial_design('random', space, 150)
+    Y = (np.sin(X[:, 1] / 3) + 0.3 * X[:, 0] - 0.2 * (X[:, 2] == 2) + 0.01 * X[:, 3] ** 2).reshape(-1, 1)
+    mk = lambda: GPy.kern.Matern52(4, variance=1.3, ARD=False, Gower=True, space=space)   # noqa: E731
+    m = GPy.models.GPRegression(X[:120], Y[:120], kernel=mk(), noise_var=0.05)
+    for n in (125, 131, 150):
+        m.set_XY(X[:n], Y[:n])
+        ref = GPy.models.GPRegression(X[:n], Y[:n], kernel=mk(), noise_var=0.05)
+        assert_allclose(m.log_likelihood(), ref.log_likelihood(), rtol=1e-10)
+        assert_allclose(m.gradient, ref.gradient, rtol=1e-7, atol=1e-9)
+        for a, r in zip(m.predict(X[140:150]), ref.predict(X[140:150])):
+            assert_allclose(a, r, rtol=1e-8, atol=1e-11)
+    assert m.inference_method.n_appends == 3
