@@ -299,7 +299,7 @@ def run_gpu(args, rank, world, local_rank):
             except Exception:
                 traffic = None
         # the single largest launch (M^T M, lower tiles): algorithmic N^3 / 3 flops against its own event-timed duration
-        dominant = {"launch": "gemm_dmma_kernel<COLK,COLK,64x128> Ky^-1 = M^T M (lower tiles), grid %d" % ((N_TRAIN // 128) * (N_TRAIN // 128 + 1)),
+        dominant = {"launch": "gemm_dmma_kernel<COLK,COLK,64x64> Ky^-1 = M^T M (lower tiles), grid %d" % (2 * (N_TRAIN // 128) * (N_TRAIN // 128 + 1)),
                     "algorithmic_flops": float(N_TRAIN) ** 3 / 3.0, "ms": last_ms,
                     "achieved": (float(N_TRAIN) ** 3 / 3.0) / (last_ms * 1e-3) / 1e12 if last_ms > 0 else None,
                     "executed_tflops": last_flops / (last_ms * 1e-3) / 1e12 if last_ms > 0 else None,

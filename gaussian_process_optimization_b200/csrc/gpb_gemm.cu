@@ -92,19 +92,37 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_k
   int tm, tn;
   const int t = blockIdx.x;
   if (p.tri_out) {
-    // Tiles are enumerated by 128-row "super rows": super row i holds R = 128 / BM tile rows, each with
-    // C_i = (i + 1) * (128 / BN) tile columns (everything left of and including the diagonal 128-block).
+    // Lower 128-blocks are enumerated band by band: a band is G consecutive block rows, walked as G x G squares from the left
+    // (then the triangle on the diagonal), so that the ~148 blocks resident at a time share 2 G operand panels instead of a
+    // whole block row's worth (row-major order re-read every column panel once per block row: 74 GB of DRAM reads for
+    // Ky^-1 = M^T M at N = 16384 against 3 GB of operands).  Bands run top to bottom, which keeps "longest k-range first" for
+    // klo_mode 1 (k >= row block).
     constexpr int R = 128 / BM, CW = 128 / BN;
-    const int per = R * CW;  // tiles of one 128x128 block
-    // tiles before super row i: per * i (i + 1) / 2
-    const int q = t / per;   // index in units of 128-blocks (lower-triangular enumeration, row-major)
-    int i = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+    constexpr int per = R * CW;   // tiles of one 128x128 block
+    constexpr int G = 12;         // 144 blocks per square ~ one wave of resident CTAs
+    const int nb = p.M / 128;
+    const int q = t / per, w_in = t - q * per;
+    int i = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);   // block row of q in row-major triangular order
     while ((i + 1) * (i + 2) / 2 <= q) ++i;
     while (i * (i + 1) / 2 > q) --i;
-    const int rem = t - per * (i * (i + 1) / 2);  // index inside super row i: R rows x (i + 1) * CW cols
-    const int cols = (i + 1) * CW;
-    tm = i * R + rem / cols;
-    tn = rem % cols;
+    const int b0 = (i / G) * G;                                 // first block row of the band
+    const int gb = min(G, nb - b0);                             // block rows in the band
+    int qq = q - b0 * (b0 + 1) / 2;                             // index inside the band
+    int bi, bj;
+    if (qq < gb * b0) {                                         // rectangular part left of the diagonal squares
+      const int cg = qq / (gb * G), w = qq - cg * (gb * G);
+      bi = b0 + w % gb;
+      bj = cg * G + w / gb;
+    } else {                                                    // triangle on the diagonal
+      qq -= gb * b0;
+      int r = (int)((sqrt(8.0 * (double)qq + 1.0) - 1.0) * 0.5);
+      while ((r + 1) * (r + 2) / 2 <= qq) ++r;
+      while (r * (r + 1) / 2 > qq) --r;
+      bi = b0 + r;
+      bj = b0 + qq - r * (r + 1) / 2;
+    }
+    tm = bi * R + w_in / CW;
+    tn = bj * CW + w_in % CW;
   } else {
     // grouped rasterisation: GROUP consecutive tile rows share their B panels while they are L2 resident
     const int tiles_m = p.M / BM, tiles_n = p.N / BN;
