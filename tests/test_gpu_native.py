@@ -452,3 +452,53 @@ def test_append_extends_the_factorisation(kind, n0, steps, grad_every):
     assert_allclose(m.get("Wi"), ref.get("Wi"), rtol=1e-7, atol=1e-9 * np.abs(ref.get("Wi")).max())
     m.close()
     ref.close()
+
+
+def test_edge_sizes_one_point_empty_candidates_two_outputs():
+    """N = 1 and N = 2 training points, an empty candidate set, and P = 2 output columns (exact_gaussian_inference.py:62,70 carry
+    the factor P; posterior.py:276 gives one mean column per output)."""
+    rs = np.random.RandomState(9)
+    for n in (1, 2):
+        X, Y = rs.uniform(0, 1, (n, 3)), rs.randn(n, 1)
+        ls = np.array([0.4, 0.6, 0.9])
+        m = native.NativeModel("rbf", True, 3, 1, n_cap=4, cand_block=128)
+        m.set_data(X, Y)
+        m.set_theta(0.8, ls, 0.1)
+        info, logL, g = m.fit(True)
+        l_ref, g_ref, post = O.log_likelihood_and_gradients("rbf", X, Y, 0.8, ls, 0.1)
+        assert info == 0
+        assert_allclose(logL, l_ref, rtol=1e-12)
+        assert_allclose(g, g_ref, rtol=1e-9, atol=1e-14)
+        Xc = rs.uniform(0, 1, (5, 3))
+        mu, var = m.predict(Xc)
+        mu_r, var_r = O.predict("rbf", post, X, Xc, 0.8, ls, 0.1)
+        assert_allclose(mu, mu_r, rtol=1e-12, atol=1e-15)
+        assert_allclose(var, var_r, rtol=1e-12)
+        mu0, var0 = m.predict(np.zeros((0, 3)))
+        assert mu0.shape == (0, 1) and var0.shape == (0, 1)
+        r = m.acquisition("EI", 0.01, m.fmin(), np.zeros((0, 3)), with_gradients=True)
+        assert r["f"].shape == (0, 1) and r["df"].shape == (0, 3)
+        m.close()
+    # two output columns
+    N, D, P = 200, 4, 2
+    X = rs.uniform(0, 1, (N, D))
+    Y = np.stack([np.sin(3 * X[:, 0]) + X[:, 1], np.cos(2 * X[:, 2]) * X[:, 3]], 1) + 0.05 * rs.randn(N, P)
+    ls = np.array([0.5, 0.7, 0.9, 1.1])
+    for kind in ("rbf", "mat52"):
+        m = native.NativeModel(kind, True, D, P, n_cap=N, cand_block=128)
+        m.set_data(X, Y)
+        m.set_theta(1.4, ls, 0.02)
+        info, logL, g = m.fit(True)
+        assert info == 0
+        l_ref, g_ref, post = O.log_likelihood_and_gradients(kind, X, Y, 1.4, ls, 0.02)
+        assert_allclose(logL, l_ref, rtol=1e-10)
+        assert_allclose(g, g_ref, rtol=1e-7, atol=1e-10)
+        assert_allclose(m.get("alpha"), post.woodbury_vector, rtol=1e-8, atol=1e-10)
+        for mc in (3, 40):                       # the skinny path is single-output: both sizes take the general one
+            Xc = rs.uniform(0, 1, (mc, D))
+            mu, var = m.predict(Xc)
+            mu_r, var_r = O.predict(kind, post, X, Xc, 1.4, ls, 0.02)
+            assert mu.shape == (mc, P)
+            assert_allclose(mu, mu_r, rtol=1e-9, atol=1e-11)
+            assert_allclose(var, var_r, rtol=1e-9, atol=1e-12)
+        m.close()
