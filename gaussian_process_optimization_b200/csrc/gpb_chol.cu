@@ -451,6 +451,8 @@ leaf_blocked_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, in
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role branches below stay convergent
   constexpr int NW = LEAF_THREADS / 32;
   double *T = Tw + warp * LB * LMD;
+  pdl_trigger();
+  pdl_wait();
   LEAF_CLK(0);
   // lower triangle of the block -> shared memory (asynchronous copies, all in flight together)
 #pragma unroll
@@ -562,10 +564,9 @@ static int launch_leaf(Factor &f, int off, int mode) {
     static unsigned long long configured_b = 0;
     if (needs_func_config(configured_b))
       GPB_CUDA(cudaFuncSetAttribute(leaf_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    leaf_blocked_kernel<<<1, LEAF_THREADS, smem_b, f.stream>>>(f.A + (size_t)off * f.np + off, f.np, f.Mi + (size_t)off * f.np + off,
-                                                               f.np, off, f.info);
+    GPB_CUDA(launch_pdl(leaf_blocked_kernel, dim3(1), dim3(LEAF_THREADS), smem_b, f.stream, f.A + (size_t)off * f.np + off, f.np,
+                        f.Mi + (size_t)off * f.np + off, f.np, off, f.info));
     count_launch();
-    GPB_CHECK_LAUNCH();
     return 0;
   }
   const size_t smem = (size_t)(2 + 3 * TILE + TILE * LEAF_LD) * sizeof(double);

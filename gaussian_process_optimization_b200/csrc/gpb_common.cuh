@@ -63,6 +63,30 @@ inline bool needs_func_config(unsigned long long &done) {
   return true;
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------------
+// The factorisation is a chain of several hundred short dependent kernels on one stream.  Kernels launched through launch_pdl
+// may be scheduled while the previous kernel of the stream drains (its CTAs signal pdl_trigger() at their start; the hardware
+// acts once every CTA of that grid has signalled or exited) and run their prologue (index arithmetic, shared-memory set-up) in
+// that shadow; pdl_wait() then blocks until the previous grid has completed and its memory is visible, so it must precede the
+// first global access.  In a kernel launched the ordinary way both instructions are no-ops.  GPB_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- stationary covariance functions of the scaled squared distance ---------------------------------------------------
 // k(r) and k'(r)/r for r = sqrt(r2).  The reference forms dK_dr * inv_dist (stationary.py:227-230,251-258) with inv_dist := 0
 // where r == 0; k'(r)/r is finite at 0 and is only ever multiplied by (x - x') which vanishes there, so the closed form

@@ -17,11 +17,22 @@
 // Triangular structure is exploited at 128-block granularity through a per-tile k-range (klo_mode / khi_mode) and through
 // tri_out (only tiles touching the lower triangle are produced): operands that are triangular carry explicit zeros inside
 // their 128x128 diagonal blocks, blocks strictly above the diagonal are never read.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "gpb_common.cuh"
 
 namespace gpb {
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char *e = getenv("GPB_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 constexpr int BK_MIN = 16;  // every k-range is a multiple of this (and of every BK used below)
 
@@ -88,6 +99,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_k
   double *sA = smem;
   double *sB = smem + STAGES * A_TILE;
 
+  pdl_trigger();
   // ---- tile coordinates ----
   int tm, tn;
   const int t = blockIdx.x;
@@ -160,6 +172,7 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_k
 #pragma unroll
     for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  pdl_wait();   // everything above is arithmetic on the launch arguments; the operands belong to the previous kernels
   // ---- prologue ----
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -329,9 +342,8 @@ static int launch_t(const GemmArgs &g, cudaStream_t s) {
   const int tiles = blocks128 * (128 / BM) * (128 / BN);
   if (tiles == 0) return 0;
   if (g_prof.on) GPB_TRY(prof_event(s));
-  gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS, BK, STAGES><<<tiles, THREADS, smem, s>>>(g);
+  GPB_CUDA(launch_pdl(gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS, BK, STAGES>, dim3(tiles), dim3(THREADS), smem, s, g));
   count_launch();
-  GPB_CHECK_LAUNCH();
   if (g_prof.on) {
     GPB_TRY(prof_event(s));
     g_last_flops = block_flops(g);
