@@ -362,7 +362,17 @@ static int launch_cfg(const GemmArgs &g, cudaStream_t s) {
   // storage order (scripts/gemm_sweep.py: 35.4 / 34.9 / 35.0 vs 34.6 / 34.1 / 34.4 TFLOP/s at 8192^3; cuBLAS 36.2): with the
   // DMMA issue slot held 16 cycles per instruction, more resident warps hide the fragment-load latency better than bigger
   // register tiles do
-  if (cfg == 0) cfg = (blocks128 >= 20) ? g_big_config : 3;
+  // Up to a few hundred output blocks the 32x32 tiles win although they load twice the operand fragments per DMMA: 1024^3
+  // takes 83 us with them against 138 us with 64x64 tiles, which leave 148 SMs with 256 CTAs (scripts/gemm_mid_sweep.py).  Alone,
+  // 64x64 is ahead again from 1536^3 on, but inside the factorisation (triangular k-ranges, a side-stream product running
+  // underneath) the 256-block launches of the 2048 level are still faster with 32x32: NLL+grad at N = 16384 takes 136.9 ms with
+  // a threshold of 20 blocks, 136.0 with 100, 135.6 with 260..400, 136.0 with 600 (GPB_BIG_MIN_BLOCKS).
+  static int big_min_blocks = -1;
+  if (big_min_blocks < 0) {
+    const char *e = getenv("GPB_BIG_MIN_BLOCKS");
+    big_min_blocks = e ? atoi(e) : 260;
+  }
+  if (cfg == 0) cfg = (blocks128 >= big_min_blocks) ? g_big_config : 3;
   if (cfg == 1 && g_forced_config == 0 && blocks128 < 148) cfg = 2;   // the 64x128 policy of the first version, kept selectable
   // both operands k-contiguous: BK = 32 with two stages halves the per-k-tile barriers (+1.8% at 8192^3); the strided
   // layouts are faster with BK = 16 and three stages (scripts/gemm_sweep.py)
