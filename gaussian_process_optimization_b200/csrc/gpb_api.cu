@@ -456,7 +456,12 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
   GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, d, n, n, kc.var, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np, np,
                       m->stream, kc.gflag, append_from));
   // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
-  const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / 8) : 0;
+  static int fork_div = -1;
+  if (fork_div < 0) {
+    const char *e = getenv("GPB_FORK_DIV");
+    fork_div = e ? std::max(1, atoi(e)) : 8;
+  }
+  const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / fork_div) : 0;
   if (m->ov && fork_min_n > 0 && np >= fork_min_n) {
     // critical path on the model's high-priority stream, T21 products on its low-priority side streams (gpb_chol.cu)
     Factor fo = m->f;
