@@ -12,7 +12,7 @@
 namespace gpb {
 
 static thread_local char g_err[1024] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -245,7 +245,7 @@ extern "C" {
 
 int gpb_version(void) { return 100; }
 const char *gpb_last_error(void) { return g_err; }
-long long gpb_launch_count(void) { return g_launches; }
+long long gpb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int gpb_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

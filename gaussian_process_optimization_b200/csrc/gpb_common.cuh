@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/gpb200.h"
 
 namespace gpb {
@@ -18,8 +20,8 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 // ---- error plumbing -------------------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
-extern long long g_launches;  // kernels launched by this library (bench.py's gpu_launches)
-inline void count_launch(int n = 1) { g_launches += n; }
+extern std::atomic<long long> g_launches;  // kernels launched by this library (bench.py's gpu_launches); models may be driven from several host threads
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 #define GPB_CUDA(call)                                                                         \
   do {                                                                                         \

@@ -333,9 +333,11 @@ class GPModel(BOModel):
     """models/gpmodel.py:9-177 on the B200 GPRegression."""
 
     analytical_gradient_prediction = True
+    CONCURRENT_MIN_N, CONCURRENT_MAX_N = 384, 6144     # where several restarts at a time pay (scripts/concurrent_restarts_perf.py)
 
     def __init__(self, kernel=None, noise_var=None, exact_feval=False, optimizer='bfgs', max_iters=1000, optimize_restarts=5,
-                 sparse=False, num_inducing=10, verbose=True, ARD=False, Gower=False, space=None, distributed_restarts=False):
+                 sparse=False, num_inducing=10, verbose=True, ARD=False, Gower=False, space=None, distributed_restarts=False,
+                 concurrent_restarts=0):
         if sparse:
             raise NotImplementedError("sparse GPs are outside the B200 hot path (exact N x N on one GPU)")
         self.Gower, self.space = Gower, space
@@ -345,6 +347,9 @@ class GPModel(BOModel):
         self._fmin = None
         # one optimize_restarts restart per torch.distributed rank (every rank must hold the same data and RNG state)
         self.distributed_restarts = distributed_restarts
+        # > 1: that many optimize_restarts restarts at a time on this GPU (host threads, one model copy and CUDA stream each);
+        # pays while one evaluation cannot fill the GPU and costs more than the thread set-up: CONCURRENT_MIN_N .. CONCURRENT_MAX_N points
+        self.concurrent_restarts = concurrent_restarts
 
     @staticmethod
     def fromConfig(config):
@@ -376,9 +381,12 @@ class GPModel(BOModel):
             if self.optimize_restarts == 1:
                 self.model.optimize(optimizer=self.optimizer, max_iters=self.max_iters, messages=False, ipython_notebook=False)
             else:
+                extra = {"distributed": True} if self.distributed_restarts else {}
+                if (self.concurrent_restarts > 1 and self.CONCURRENT_MIN_N <= self.model.X.shape[0] <= self.CONCURRENT_MAX_N
+                        and not self.distributed_restarts):
+                    extra = {"concurrent": self.concurrent_restarts}
                 self.model.optimize_restarts(num_restarts=self.optimize_restarts, optimizer=self.optimizer,
-                                             max_iters=self.max_iters, verbose=self.verbose,
-                                             **({"distributed": True} if self.distributed_restarts else {}))
+                                             max_iters=self.max_iters, verbose=self.verbose, **extra)
         self._fmin = None
 
     def _nat(self):

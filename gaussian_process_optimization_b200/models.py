@@ -367,7 +367,8 @@ class GP(Model):
         return cov[:X1.shape[0], X1.shape[0]:]
 
     def copy(self):
-        return GP(self.X.copy(), self.Y.copy(), self.kern.copy(), self.likelihood.copy(), name=self.name)
+        return GP(self.X.copy(), self.Y.copy(), self.kern.copy(), self.likelihood.copy(), name=self.name,
+                  inference_method=type(self.inference_method)())
 
     def __str__(self):
         return "{}: N={}, D={}, log-likelihood={}\n  {}\n  noise variance={}".format(

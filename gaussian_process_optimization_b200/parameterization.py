@@ -441,8 +441,9 @@ class Model(Parameterized):
         table = np.full((num_restarts, 3 + n), np.inf)        # f_opt, funct_eval, ok flag, x_opt
         for i in range(rank, num_restarts, world):
             try:
-                self.optimizer_array = starts[i]
-                run = self.optimize(start=starts[i], **kwargs)
+                if i > 0:                                     # restart 0 continues from the current parameters (sequential loop)
+                    self.optimizer_array = starts[i]
+                run = self.optimize(**kwargs)                 # reads its start back through the parameter transforms, like randomize() + optimize()
                 table[i, 0], table[i, 1], table[i, 2], table[i, 3:] = run.f_opt, run.funct_eval, 1.0, run.x_opt
                 self.optimization_runs.pop()                  # re-appended below in restart order on every rank
             except Exception as e:
@@ -460,8 +461,77 @@ class Model(Parameterized):
                 print("Optimization restart {0}/{1}, f = {2}".format(i + 1, num_restarts, table[i, 0]))
         return done, table
 
+    def _optimize_restarts_concurrent(self, num_restarts, robust, verbose, workers, **kwargs):
+        """Restarts on one GPU, `workers` at a time: below a few thousand training points a single NLL+grad evaluation is a chain
+        of short kernels that leaves most of the 148 SMs idle, and the restarts are independent once their starting points are
+        drawn.  Every worker thread owns a copy of the model (its own device workspace and CUDA stream; the C library holds no
+        shared mutable state besides a launch counter) and runs restarts w, w + workers, ...; ctypes releases the GIL during
+        the device calls, so the kernels of different restarts overlap.  The starts are drawn exactly as the sequential loop
+        draws them and every run is deterministic, so runs, optimum and the NumPy stream equal the sequential ones."""
+        import threading
+        n = self._size_transformed()
+        starts = [self.optimizer_array.copy()] + [np.random.normal(size=n) for _ in range(1, num_restarts)]
+        runs, errors = [None] * num_restarts, [None] * num_restarts
+        dev = None
+        try:
+            import torch
+            if torch.cuda.is_available() and torch.cuda.is_initialized():
+                dev = torch.cuda.current_device()
+        except ImportError:
+            torch = None
+
+        def work(w):
+            import contextlib
+            ctx = contextlib.nullcontext()
+            if dev is not None:
+                torch.cuda.set_device(dev)                     # the current device is per host thread
+                ctx = torch.cuda.stream(torch.cuda.Stream())
+            with ctx:
+                m = None
+                for i in range(w, num_restarts, workers):
+                    try:
+                        if m is None:
+                            m = self.copy()
+                        # like the sequential loop: restart 0 continues from the current parameters, the others from
+                        # randomize(); optimize() then reads its start back through the parameter transforms
+                        if i > 0:
+                            m.optimizer_array = starts[i]
+                        runs[i] = m.optimize(**kwargs)
+                    except Exception as e:                      # reported in restart order by the caller
+                        errors[i] = e
+                nat = getattr(getattr(m, "inference_method", None), "_nat", None)
+                if nat is not None:
+                    nat.close()
+
+        threads = [threading.Thread(target=work, args=(w,)) for w in range(min(workers, num_restarts))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        done = []
+        for i in range(num_restarts):
+            if errors[i] is not None:
+                if not robust:
+                    raise errors[i]
+                print("Warning - optimization restart {0}/{1} failed".format(i + 1, num_restarts))
+            elif runs[i] is not None:
+                self.optimization_runs.append(runs[i])
+                done.append(i)
+                if verbose:
+                    print("Optimization restart {0}/{1}, f = {2}".format(i + 1, num_restarts, runs[i].f_opt))
+        return done, runs
+
     def optimize_restarts(self, num_restarts=10, robust=False, verbose=True, parallel=False, num_processes=None, distributed=False,
-                          group=None, **kwargs):
+                          group=None, concurrent=0, **kwargs):
+        if concurrent and concurrent > 1 and num_restarts > 1:
+            initial_parameters = self.optimizer_array.copy()
+            done, runs = self._optimize_restarts_concurrent(num_restarts, robust, verbose, int(concurrent), **kwargs)
+            if done:
+                best = done[int(np.argmin([runs[i].f_opt for i in done]))]
+                self.optimizer_array = runs[best].x_opt
+            else:
+                self.optimizer_array = initial_parameters
+            return self.optimization_runs
         if distributed:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

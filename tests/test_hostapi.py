@@ -405,6 +405,32 @@ def test_distributed_restarts_match_sequential(tmp_path):
         assert z["rng"] == rng_after            # the global NumPy stream advanced exactly as in the sequential run
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_concurrent_restarts_match_sequential(backend):
+    """optimize_restarts(concurrent=K): K restarts at a time in host threads (own model copy and stream each).  Same runs,
+    optimum, parameters and NumPy stream as the sequential loop."""
+    X, Y = _opt_problem()
+    res = {}
+    for conc in (0, 3):
+        m = make_gpr(backend, X, Y, GPy.kern.Matern52(3, ARD=True), noise_var=0.1)
+        m.Gaussian_noise.constrain_bounded(1e-9, 1e6, warning=False)
+        np.random.seed(0)
+        m.optimize_restarts(num_restarts=5, optimizer='lbfgs', max_iters=60, verbose=False, concurrent=conc)
+        res[conc] = ([r.f_opt for r in m.optimization_runs], [r.funct_eval for r in m.optimization_runs], m.optimizer_array.copy(),
+                     m[:].copy(), float(m.log_likelihood()), np.random.uniform())
+    assert len(res[3][0]) == 5
+    # the device path is bitwise reproducible (fixed-order reductions); the CPU oracle's multi-threaded BLAS is not when several
+    # host threads call it at once, so its runs only agree to rounding
+    exact = backend == "cuda"
+    assert_allclose(res[3][0], res[0][0], rtol=1e-12 if exact else 1e-7)
+    if exact:
+        assert res[3][1] == res[0][1]
+    assert_allclose(res[3][2], res[0][2], rtol=1e-12 if exact else 1e-4, atol=0 if exact else 1e-5)
+    assert_allclose(res[3][3], res[0][3], rtol=1e-12 if exact else 1e-4, atol=0 if exact else 1e-6)
+    assert_allclose(res[3][4], res[0][4], rtol=1e-12 if exact else 1e-7)
+    assert res[3][5] == res[0][5]
+
+
 def _anchor_bo(distributed):
     np.random.seed(7)
     model = make_gpmodel("oracle", kernel=GPy.kern.Matern52(2), exact_feval=True, verbose=False, optimize_restarts=1)
