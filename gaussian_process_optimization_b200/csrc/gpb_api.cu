@@ -341,9 +341,12 @@ int gpb_model_set_data(gpb_model *m, int n, const double *X, const double *Y, in
   const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   GPB_CUDA(cudaMemcpyAsync(m->X, X, (size_t)n * m->d * sizeof(double), kind, m->stream));
   // Y -> column blocks; stage the row-major copy in z (same size class) first when it comes from the host
-  DevBuf tmp;
-  const double *Yd = nullptr;
-  GPB_TRY(to_device(tmp, Y, (size_t)n * m->p, dev, &Yd, m->stream));
+  // (no temporary allocation: cudaMalloc / cudaFree per update cost milliseconds in a BO loop that appends a point per step)
+  const double *Yd = Y;
+  if (!dev) {
+    GPB_CUDA(cudaMemcpyAsync(m->z, Y, (size_t)n * m->p * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    Yd = m->z;
+  }
   pack_cols_kernel<<<(m->p * m->np + 255) / 256, 256, 0, m->stream>>>(Yd, n, m->p, m->np, m->Yc);
   count_launch();
   GPB_CHECK_LAUNCH();
@@ -449,8 +452,24 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
   m->fitted = false;
   m->have_wi = false;
   m->jitter = extra_jitter;
-  GPB_TRY(ensure_scaled(m));
   const int n = m->n, np = m->np, d = m->d, p = m->p;
+  static int tiny_on = -1;
+  if (tiny_on < 0) {
+    const char *e = getenv("GPB_TINY");
+    tiny_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool tiny = tiny_on && np == TILE && !m->gower && p == 1 && d <= 32 && append_from == 0;
+  if (tiny) {
+    // N <= 128 (an ordinary BO run): the whole evaluation -- input scaling included -- in one kernel instead of a dozen launches
+    // and two small uploads; the status travels with the results
+    double lsq[32];
+    for (int q = 0; q < d; ++q) lsq[q] = m->ls[m->nls == 1 ? 0 : q];
+    GPB_TRY(launch_tiny_fit(m->kind, m->X, lsq, m->XsT, m->ls_dev, m->inv_ls_dev, n, d, m->variance, m->noise + 1e-8 + extra_jitter, m->Yc,
+                            m->f, m->z, m->alpha, m->scal, want_grad));
+    m->scaled_valid = true;
+    if (want_grad) m->have_wi = true;
+  } else {
+  GPB_TRY(ensure_scaled(m));
   // Ky = K + (noise + 1e-8 [+ jitter]) I     exact_gaussian_inference.py:55-56
   const KCoords kc = train_coords(m);
   GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, d, n, n, kc.var, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np, np,
@@ -493,10 +512,11 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
       GPB_TRY(launch_kvar_gower(m->kind, 1, kc.XT, np, kc.XT, np, d, n, n, kc.var, kc.gflag, m->f.W, np, m->alpha, np, p, m->gpart,
                                 m->scal + 2, m->stream));
   }
-  GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 4) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-  GPB_CUDA(cudaMemcpyAsync(m->pinned + 128, m->f.info, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  }
+  GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 5) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  if (!tiny) GPB_CUDA(cudaMemcpyAsync(m->pinned + 128, m->f.info, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
   GPB_CUDA(cudaStreamSynchronize(m->stream));
-  const int info = *reinterpret_cast<int *>(m->pinned + 128);
+  const int info = tiny ? (int)m->pinned[d + 4] : *reinterpret_cast<int *>(m->pinned + 128);
   if (info != 0) {
     set_error("fit: matrix not positive definite (leading minor %d)", info);
     return info > n ? n : info;
@@ -571,9 +591,11 @@ int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall
   m->np = np_new;
   m->f.n = n_new;
   m->f.np = np_new;
-  DevBuf tmp;
-  const double *Yd = nullptr;
-  GPB_TRY(to_device(tmp, Yall, (size_t)n_new * m->p, dev, &Yd, s));
+  const double *Yd = Yall;
+  if (!dev) {
+    GPB_CUDA(cudaMemcpyAsync(m->z, Yall, (size_t)n_new * m->p * sizeof(double), cudaMemcpyHostToDevice, s));
+    Yd = m->z;
+  }
   pack_cols_kernel<<<(m->p * np_new + 255) / 256, 256, 0, s>>>(Yd, n_new, m->p, np_new, m->Yc);
   count_launch();
   GPB_CHECK_LAUNCH();

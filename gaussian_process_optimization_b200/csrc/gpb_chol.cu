@@ -441,30 +441,13 @@ __device__ __forceinline__ void leaf_cp_async16(double *smem_dst, const double *
 // warps 1-7 finish the trailing update of step k and compute block row k of M; one barrier pair per step.  Results leave for
 // global memory from the accumulator fragments as they are produced (no epilogue); the zeros above the diagonal are stored
 // first and complete under the computation.
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
-leaf_blocked_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, int ldm, int index_base, int *info) {
-  extern __shared__ double sm[];
-  double *S = sm;                          // 128 x 132
-  double *Md = S + TILE * LSD;             // 8 x (16 x 20): diagonal sub-blocks of M
-  double *Tw = Md + LNB * LB * LMD;        // 8 x (16 x 20): per-warp scratch
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role branches below stay convergent
+// The factorisation proper: S holds the lower triangle of the block (all threads have synchronised after filling it); on return
+// (after a __syncthreads) S holds L in its lower triangle and M^T in its strictly-upper sub-blocks, Md the diagonal sub-blocks
+// of M, and both results are on their way to A / Mi.  Returns 0 or 1 + index of the first non-positive pivot (valid in warp 0).
+__device__ __forceinline__ int leaf_core(double *S, double *Md, double *Tw, double *__restrict__ A, int lda, double *__restrict__ Mi,
+                                         int ldm, int tid, int lane, int warp) {
   constexpr int NW = LEAF_THREADS / 32;
   double *T = Tw + warp * LB * LMD;
-  pdl_trigger();
-  pdl_wait();
-  LEAF_CLK(0);
-  // lower triangle of the block -> shared memory (asynchronous copies, all in flight together)
-#pragma unroll
-  for (int it = 0; it < TILE * (TILE / 2) / LEAF_THREADS; ++it) {
-    const int e = tid + it * LEAF_THREADS, r = e >> 6, c = (e & 63) * 2;
-    if (c <= r) leaf_cp_async16(S + r * LSD + c, A + (size_t)r * lda + c);
-  }
-  asm volatile("cp.async.commit_group;\n" ::);
-  asm volatile("cp.async.wait_group 0;\n" ::);
-  __syncthreads();
-  LEAF_CLK(1);
-
   int fail = 0;
   double pre[2][2][2];   // warps 1-7: partial sum of their task of the last block row of M, carried across the last barrier
   blk_zero(pre);
@@ -547,9 +530,292 @@ leaf_blocked_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, in
     __syncthreads();
     LEAF_CLK(5 + 4 * (k + 1));
   }
+  return fail;
+}
+
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+leaf_blocked_kernel(double *__restrict__ A, int lda, double *__restrict__ Mi, int ldm, int index_base, int *info) {
+  extern __shared__ double sm[];
+  double *S = sm;                          // 128 x 132
+  double *Md = S + TILE * LSD;             // 8 x (16 x 20): diagonal sub-blocks of M
+  double *Tw = Md + LNB * LB * LMD;        // 8 x (16 x 20): per-warp scratch
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role branches below stay convergent
+  pdl_trigger();
+  pdl_wait();
+  LEAF_CLK(0);
+  // lower triangle of the block -> shared memory (asynchronous copies, all in flight together)
+#pragma unroll
+  for (int it = 0; it < TILE * (TILE / 2) / LEAF_THREADS; ++it) {
+    const int e = tid + it * LEAF_THREADS, r = e >> 6, c = (e & 63) * 2;
+    if (c <= r) leaf_cp_async16(S + r * LSD + c, A + (size_t)r * lda + c);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+  LEAF_CLK(1);
+  const int fail = leaf_core(S, Md, Tw, A, lda, Mi, ldm, tid, lane, warp);
   if (warp == 0 && lane == 0 && fail != 0) atomicCAS(info, 0, index_base + fail);
   LEAF_CLK(40);
   LEAF_CLK(41);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// N <= 128: the whole NLL + gradient evaluation in ONE kernel (one CTA).  At the sizes of an ordinary BO run (the reference's
+// own examples, BASELINE config 1) an evaluation through the general path is eleven launches of a few microseconds each;
+// here the covariance block is built straight into the shared array of the blocked leaf, factorised and inverted in place,
+// and alpha = M^T (M y), log det, alpha.y, Ky^-1 = M^T M and the D + 2 gradient sums follow without leaving the SM.
+// Same formulas and outputs as kmat_kernel (mode 3) -> leaf -> trmv -> logdet / dot -> potri -> kgrad_kernel<.., FUSED>:
+//   scal[0] = log det, scal[1] = alpha.y, scal[2] = sum K.G, scal[3] = tr G, scal[4 + q] = sum (k'/r) G ds_q^2,  G = (alpha alpha^T - W) / 2
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TINY_DMAX = 32;
+
+struct TinyLs {
+  double ls[TINY_DMAX];   // per-dimension lengthscales, by value: no upload, no separate scaling kernel
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+tiny_fit_kernel(const double *__restrict__ X, TinyLs lsv, double *__restrict__ XsT, double *__restrict__ ls_dev, double *__restrict__ inv_ls_dev,
+                int n, int d, double variance, double diag_add, const double *__restrict__ y, double *__restrict__ A,
+                double *__restrict__ Mi, double *__restrict__ W, int ld, double *__restrict__ z_out, double *__restrict__ alpha_out,
+                double *__restrict__ scal, int want_grad, int *info) {
+  extern __shared__ double sm[];
+  double *S = sm;
+  double *Md = S + TILE * LSD;
+  double *Tw = Md + LNB * LB * LMD;
+  double *xs = Tw + LNB * LB * LMD;        // d x 128 scaled inputs, dimension-major
+  double *yv = xs + TINY_DMAX * TILE;      // 128
+  double *zv = yv + TILE;                  // 128
+  double *av = zv + TILE;                  // 128
+  double *red = av + TILE;                 // 8 x (TINY_DMAX + 2)
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  constexpr int NW = LEAF_THREADS / 32;
+  pdl_trigger();
+  pdl_wait();
+  // scaled inputs, dimension-major (scale_transpose_kernel): kept for the predictive calls that follow
+  for (int e = tid; e < d * TILE; e += LEAF_THREADS) {
+    const int q = e >> 7, i = e & 127;
+    double v = (i < n) ? X[(size_t)i * d + q] / lsv.ls[q] : 0.0;
+    v = v > 1e150 ? 1e150 : (v < -1e150 ? -1e150 : v);
+    xs[e] = v;
+    XsT[e] = v;
+  }
+  if (tid < d) {
+    ls_dev[tid] = lsv.ls[tid];
+    inv_ls_dev[tid] = 1.0 / lsv.ls[tid];
+  }
+  if (tid < TILE) yv[tid] = (tid < n) ? y[tid] : 0.0;
+  __syncthreads();
+  // ---- Ky = K + diag_add I, identity padding (exact_gaussian_inference.py:55-56), lower triangle ----
+  // 16 x 16 threads, 8 x 8 register tile: thread (ty, tx) owns the pairs (ty + 16 a, tx + 16 b), b <= a (like kmat_kernel)
+  const int tx = tid & 15, ty = tid >> 4;
+  {
+    double r2[LNB][LNB];
+#pragma unroll
+    for (int a2 = 0; a2 < LNB; ++a2)
+#pragma unroll
+      for (int b2 = 0; b2 < LNB; ++b2) r2[a2][b2] = 0.0;
+    for (int q = 0; q < d; ++q) {
+      double va[LNB], vb[LNB];
+#pragma unroll
+      for (int a2 = 0; a2 < LNB; ++a2) {
+        va[a2] = xs[q * TILE + ty + LB * a2];
+        vb[a2] = xs[q * TILE + tx + LB * a2];
+      }
+#pragma unroll
+      for (int a2 = 0; a2 < LNB; ++a2)
+#pragma unroll
+        for (int b2 = 0; b2 <= a2; ++b2) {
+          const double df = va[a2] - vb[b2];
+          r2[a2][b2] = fma(df, df, r2[a2][b2]);
+        }
+    }
+#pragma unroll
+    for (int a2 = 0; a2 < LNB; ++a2)
+#pragma unroll
+      for (int b2 = 0; b2 <= a2; ++b2) {
+        const int i = ty + LB * a2, j = tx + LB * b2;
+        if (j > i) continue;
+        double v;
+        if (i < n) {
+          v = cov_k<KIND>(r2[a2][b2], variance);
+          if (i == j) v += diag_add;
+        } else {
+          v = (i == j) ? 1.0 : 0.0;
+        }
+        S[i * LSD + j] = v;
+      }
+  }
+  __syncthreads();
+  const int fail = leaf_core(S, Md, Tw, A, ld, Mi, ld, tid, lane, warp);
+  if (warp == 0 && lane == 0) {
+    *info = fail;
+    scal[d + 4] = (double)fail;   // travels with the results: one device-to-host copy per evaluation
+  }
+  // ---- z = M y, alpha = M^T z (dpotrs, linalg.py:116-125); M[r][c] = S[c][r] outside the diagonal sub-blocks, Md inside ----
+  if (tid < TILE) {
+    const int r = tid, rb = r >> 4;
+    double acc = 0.0;
+    for (int c = 0; c < rb * LB; ++c) acc = fma(S[c * LSD + r], yv[c], acc);
+    for (int c = rb * LB; c <= r; ++c) acc = fma(Md[rb * LB * LMD + (r & 15) * LMD + (c & 15)], yv[c], acc);
+    zv[r] = acc;
+  }
+  __syncthreads();
+  if (tid < TILE) {
+    const int c = tid, cb = c >> 4;
+    double acc = 0.0;
+    for (int r = c; r < (cb + 1) * LB; ++r) acc = fma(Md[cb * LB * LMD + (r & 15) * LMD + (c & 15)], zv[r], acc);
+    for (int r = (cb + 1) * LB; r < TILE; ++r) acc = fma(S[c * LSD + r], zv[r], acc);
+    av[c] = acc;
+    alpha_out[c] = acc;
+    z_out[c] = zv[c];
+  } else {
+    // log det = 2 sum log L_ii and alpha.y come from the second half of the block
+    const int t = tid - TILE;
+    double ld_acc = (t < n) ? log(S[t * LSD + t]) : 0.0;
+    ld_acc = warp_sum(ld_acc);
+    if (lane == 0) red[warp] = ld_acc;
+  }
+  __syncthreads();
+  if (tid == 0) scal[0] = 2.0 * ((red[4] + red[5]) + (red[6] + red[7]));
+  if (warp == 1) {
+    double acc = 0.0;
+    for (int i = lane; i < TILE; i += 32) acc = fma(av[i], yv[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) scal[1] = acc;
+  }
+  if (!want_grad) return;
+  __syncthreads();   // everyone is done with L (log det) before W overwrites the lower triangle
+  // ---- W = Ky^-1 = M^T M (dpotri): sub-block (i, j), i >= j:  sum_{k >= i} M_ki^T M_kj; kept in S (lower) and written to W in full ----
+  for (int t = warp; t < LNB * (LNB + 1) / 2; t += NW) {
+    int i = 0, rem = t;
+    while (rem > i) {
+      rem -= i + 1;
+      ++i;
+    }
+    const int j = rem;
+    double c[2][2][2];
+    blk_zero(c);
+    // k = i: M_ii^T from Md; M_ij from the upper triangle (or Md when j == i)
+    if (j == i)
+      blk_mma<true, true>(c, Md + i * LB * LMD, LMD, Md + i * LB * LMD, LMD, 1.0, lane);
+    else
+      blk_mma<true, false>(c, Md + i * LB * LMD, LMD, S + (j * LB) * LSD + i * LB, LSD, 1.0, lane);
+    for (int k = i + 1; k < LNB; ++k)
+      blk_mma<false, false>(c, S + (i * LB) * LSD + k * LB, LSD, S + (j * LB) * LSD + k * LB, LSD, 1.0, lane);
+    // the products only read the upper triangle and Md, so the lower triangle (L, already in A) can take W
+    blk_store(c, S + (i * LB) * LSD + j * LB, LSD, lane);
+    blk_store_global(c, W + (size_t)(i * LB) * ld + j * LB, ld, lane);
+    if (j != i) {
+      const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          W[(size_t)(j * LB + 8 * b + 2 * tq) * ld + i * LB + 8 * a + g] = c[a][b][0];
+          W[(size_t)(j * LB + 8 * b + 2 * tq + 1) * ld + i * LB + 8 * a + g] = c[a][b][1];
+        }
+    }
+  }
+  __syncthreads();
+  // ---- gradient sums over all pairs (update_gradients_full, stationary.py:218-238, with dL_dK = (alpha alpha^T - W) / 2) ----
+  // same register tiling as the build; the pair weights replace r2, then one pass per dimension (like kgrad_kernel)
+  double r2[LNB][LNB];
+#pragma unroll
+  for (int a2 = 0; a2 < LNB; ++a2)
+#pragma unroll
+    for (int b2 = 0; b2 < LNB; ++b2) r2[a2][b2] = 0.0;
+  for (int q = 0; q < d; ++q) {
+    double va[LNB], vb[LNB];
+#pragma unroll
+    for (int a2 = 0; a2 < LNB; ++a2) {
+      va[a2] = xs[q * TILE + ty + LB * a2];
+      vb[a2] = xs[q * TILE + tx + LB * a2];
+    }
+#pragma unroll
+    for (int a2 = 0; a2 < LNB; ++a2)
+#pragma unroll
+      for (int b2 = 0; b2 <= a2; ++b2) {
+        const double df = va[a2] - vb[b2];
+        r2[a2][b2] = fma(df, df, r2[a2][b2]);
+      }
+  }
+  double acc_var = 0.0, acc_tr = 0.0;
+#pragma unroll
+  for (int a2 = 0; a2 < LNB; ++a2)
+#pragma unroll
+    for (int b2 = 0; b2 <= a2; ++b2) {
+      const int i = ty + LB * a2, j = tx + LB * b2;
+      double wgt = 0.0;
+      if (j <= i && i < n) {
+        const double g = 0.5 * (av[i] * av[j] - S[i * LSD + j]);
+        const double wt = (i == j) ? 1.0 : 2.0;
+        if (i == j) acc_tr += g;
+        double k, dk;
+        cov_k_dk<KIND>(r2[a2][b2], variance, k, dk);
+        acc_var = fma(wt * k, g, acc_var);
+        wgt = wt * dk * g;
+      }
+      r2[a2][b2] = wgt;
+    }
+  acc_var = warp_sum(acc_var);
+  acc_tr = warp_sum(acc_tr);
+  if (lane == 0) {
+    red[warp * (TINY_DMAX + 2) + 0] = acc_var;
+    red[warp * (TINY_DMAX + 2) + 1] = acc_tr;
+  }
+  for (int q = 0; q < d; ++q) {
+    double va[LNB], vb[LNB];
+#pragma unroll
+    for (int a2 = 0; a2 < LNB; ++a2) {
+      va[a2] = xs[q * TILE + ty + LB * a2];
+      vb[a2] = xs[q * TILE + tx + LB * a2];
+    }
+    double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a2 = 0; a2 < LNB; ++a2)
+#pragma unroll
+      for (int b2 = 0; b2 <= a2; ++b2) {
+        const double df = va[a2] - vb[b2];
+        acc4[a2 & 3] = fma(r2[a2][b2], df * df, acc4[a2 & 3]);
+      }
+    const double v = warp_sum((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
+    if (lane == 0) red[warp * (TINY_DMAX + 2) + 2 + q] = v;
+  }
+  __syncthreads();
+  if (tid < d + 2) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += red[w * (TINY_DMAX + 2) + tid];
+    scal[2 + tid] = v;
+  }
+}
+
+// want_grad: also W = Ky^-1 and the gradient sums.  X: n x d raw inputs; ls: d lengthscales (host); XsT (d x 128), ls_dev, inv_ls_dev:
+// outputs for the predictive calls; y, z, alpha: 128-vectors; scal: d + 5 doubles (the last one = info).
+int launch_tiny_fit(int kind, const double *X, const double *ls_host, double *XsT, double *ls_dev, double *inv_ls_dev, int n, int d,
+                    double variance, double diag_add, const double *y, Factor &f, double *z, double *alpha, double *scal, int want_grad) {
+  GPB_REQUIRE(f.np == TILE && n <= TILE && d <= TINY_DMAX, "tiny fit: needs N <= 128 and D <= %d", TINY_DMAX);
+  const size_t smem = (size_t)(TILE * LSD + 2 * LNB * LB * LMD + TINY_DMAX * TILE + 3 * TILE + (LEAF_THREADS / 32) * (TINY_DMAX + 2)) * sizeof(double);
+  static unsigned long long configured = 0;
+  if (needs_func_config(configured)) {
+    GPB_CUDA(cudaFuncSetAttribute(tiny_fit_kernel<GPB_KERN_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GPB_CUDA(cudaFuncSetAttribute(tiny_fit_kernel<GPB_KERN_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  TinyLs lsv;
+  for (int q = 0; q < TINY_DMAX; ++q) lsv.ls[q] = q < d ? ls_host[q] : 1.0;
+  if (kind == GPB_KERN_RBF)
+    GPB_CUDA(launch_pdl(tiny_fit_kernel<GPB_KERN_RBF>, dim3(1), dim3(LEAF_THREADS), smem, f.stream, X, lsv, XsT, ls_dev, inv_ls_dev, n, d,
+                        variance, diag_add, y, f.A, f.Mi, f.W, TILE, z, alpha, scal, want_grad, f.info));
+  else
+    GPB_CUDA(launch_pdl(tiny_fit_kernel<GPB_KERN_MATERN52>, dim3(1), dim3(LEAF_THREADS), smem, f.stream, X, lsv, XsT, ls_dev, inv_ls_dev, n,
+                        d, variance, diag_add, y, f.A, f.Mi, f.W, TILE, z, alpha, scal, want_grad, f.info));
+  count_launch();
+  f.l_pending = false;
+  f.l_from = 0;
+  return 0;
 }
 
 static int g_leaf_variant = -1;  // 1: blocked DMMA leaf (default), 0: register rank-1 sweep (GPB_LEAF=0)

@@ -223,6 +223,9 @@ int factor_trtri(Factor &f);                     // A holds a lower-triangular L
 int factor_potri(Factor &f);                     // W = Mi^T Mi (lower tiles)
 int factor_finalize_L(Factor &f);                // off-diagonal blocks of L: W -> A (idempotent)
 int factor_append(Factor &f, int h);             // leading h x h part already factorised: factor the block rows from h on
+// N <= 128, D <= 32, one output: Ky build + factor + inverse + solve + log det (+ Ky^-1 and the gradient sums) in one kernel
+int launch_tiny_fit(int kind, const double *X, const double *ls_host, double *XsT, double *ls_dev, double *inv_ls_dev, int n, int d,
+                    double variance, double diag_add, const double *y, Factor &f, double *z, double *alpha, double *scal, int want_grad);
 int factor_potri_downdate(Factor &f, int h, int np_old);  // W11 -= (rows [h, np_old) of Mi)^T (same rows): before an append
 int factor_potri_append(Factor &f, int h);       // W: inverse of the leading h block (downdated) -> Ky^-1 of the extended matrix
 int factor_solve(Factor &f, const double *Y, int p, double *z, double *alpha);  // alpha = Mi^T (Mi Y);  Y, z, alpha: np x p col-major (p vectors of np)

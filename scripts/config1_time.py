@@ -33,7 +33,10 @@ for backend in ("cuda", "cuda", "oracle"):           # the first CUDA run warms 
                                              initial_design_numdata=5, initial_design_type='random')
     bo.run_optimization(max_iter=30)
     dt = time.perf_counter() - t0
-    out[backend] = {"seconds": dt, "evaluations": int(bo.X.shape[0]), "best": float(bo.Y.min())}
+    from gaussian_process_optimization_b200 import native
+    out[backend] = {"seconds": dt, "evaluations": int(bo.X.shape[0]), "best": float(bo.Y.min()),
+                    "kernel_launches_total": int(native.launch_count()) if backend == "cuda" else 0,
+                    "hyperparameter_evaluations": int(sum(r.funct_eval for r in model.model.optimization_runs))}
     print(backend, out[backend], flush=True)
 out["same_trajectory"] = bool(abs(out["cuda"]["best"] - out["oracle"]["best"]) < 1e-6)
 os.makedirs("gpurun_out", exist_ok=True)
