@@ -136,6 +136,27 @@ static int upload_ls(const double *ls, int nls, int d, double *ls_dev, double *i
   return 0;
 }
 
+// the same without uploads or a synchronisation: the lengthscales travel as a kernel argument (d <= 64)
+struct LsArg {
+  double v[64];
+};
+__global__ void set_ls_kernel(LsArg a, int d, double *__restrict__ ls_dev, double *__restrict__ inv_ls_dev) {
+  const int q = threadIdx.x;
+  if (q < d) {
+    ls_dev[q] = a.v[q];
+    inv_ls_dev[q] = 1.0 / a.v[q];
+  }
+}
+static int set_ls(const double *ls, int nls, int d, double *ls_dev, double *inv_ls_dev, cudaStream_t s) {
+  if (d > 64) return upload_ls(ls, nls, d, ls_dev, inv_ls_dev, s);
+  LsArg a;
+  for (int q = 0; q < 64; ++q) a.v[q] = q < d ? ls[nls == 1 ? 0 : q] : 1.0;
+  set_ls_kernel<<<1, 64, 0, s>>>(a, d, ls_dev, inv_ls_dev);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace gpb
 
 using namespace gpb;
@@ -409,7 +430,7 @@ int gpb_model_set_theta(gpb_model *m, double variance, const double *lengthscale
 
 static int ensure_scaled(gpb_model *m) {
   if (m->scaled_valid) return 0;
-  GPB_TRY(upload_ls(m->ls.data(), m->nls, m->d, m->ls_dev, m->inv_ls_dev, m->stream));
+  GPB_TRY(set_ls(m->ls.data(), m->nls, m->d, m->ls_dev, m->inv_ls_dev, m->stream));
   GPB_TRY(launch_scale_transpose(m->X, m->n, m->d, m->ls_dev, m->XsT, m->np, m->stream));
   if (m->gower) GPB_TRY(launch_scale_transpose(m->X, m->n, m->d, m->ginv_dev, m->XgT, m->np, m->stream, 1));
   m->scaled_valid = true;
