@@ -99,14 +99,34 @@ __global__ void pad_sym_kernel(const double *__restrict__ src, int lds, int n, d
 }
 
 // ---- RAII device temp ------------------------------------------------------------------------------------------------
+// Temporary device memory of one API call, stream-ordered (cudaMallocAsync / cudaFreeAsync on the call's stream, pool kept
+// warm): a cudaMalloc / cudaFree pair costs milliseconds and synchronises the device, which the stateless Kern / linalg entry
+// points would otherwise pay several times per call.  AllocStream names the stream for the DevBufs of the current scope.
+static thread_local cudaStream_t g_alloc_stream = 0;
+struct AllocStream {
+  cudaStream_t prev;
+  explicit AllocStream(cudaStream_t s) : prev(g_alloc_stream) { g_alloc_stream = s; }
+  ~AllocStream() { g_alloc_stream = prev; }
+};
 struct DevBuf {
   void *p = nullptr;
+  cudaStream_t s = 0;
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, s);
   }
   int alloc(size_t bytes) {
     if (bytes == 0) bytes = 8;
-    GPB_CUDA(cudaMalloc(&p, bytes));
+    static unsigned long long configured = 0;
+    if (needs_func_config(configured)) {          // once per device: keep freed blocks in the pool instead of returning them
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+    }
+    s = g_alloc_stream;
+    GPB_CUDA(cudaMallocAsync(&p, bytes, s));
     return 0;
   }
   double *d() { return reinterpret_cast<double *>(p); }
@@ -575,6 +595,7 @@ int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall
   GPB_REQUIRE(b >= 1 && m->n + b <= m->n_cap, "append: %d + %d points exceed the model capacity %d", m->n, b, m->n_cap);
   const int n_old = m->n, np_old = m->np, n_new = n_old + b, np_new = round_up(n_new, TILE), d = m->d;
   cudaStream_t s = m->stream;
+  AllocStream alloc_scope(s);
   // block rows from h on are rebuilt: the last, partially filled block row of the old factor and everything new
   const int h = (n_old / TILE) * TILE;
   // Ky^-1: keep the leading h block across the append (factor_potri_append completes it in O(N^2 r))
@@ -637,6 +658,7 @@ int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) 
   const std::string w(what);
   const int n = m->n, np = m->np, p = m->p;
   cudaStream_t s = m->stream;
+  AllocStream alloc_scope(s);
   const bool is_mat = (w == "L" || w == "Li" || w == "Wi" || w == "K" || w == "dL_dK");
   GPB_REQUIRE(is_mat || w == "alpha", "get: unknown quantity '%s'", what);
   if (w != "K") GPB_REQUIRE(m->fitted, "get: model has not been fitted");
@@ -686,6 +708,7 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   const int n = m->n, np = m->np, d = m->d, p = m->p;
   const int cpad = round_up(mcb, TILE);
   cudaStream_t s = m->stream;
+  AllocStream alloc_scope(s);
   GPB_CUDA(cudaMemcpyAsync(m->Xc, Xc, (size_t)mcb * d * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
   GPB_TRY(launch_scale_transpose(m->Xc, mcb, d, m->ls_dev, m->XcT, cpad, s));
   // KxT[c][n] = k(x*_c, x_n)                                        posterior.py:275 (stored transposed)
@@ -776,6 +799,7 @@ int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int inclu
   GPB_REQUIRE(mc >= 1 && mc <= m->cb, "predict_full_cov: mc = %d exceeds the candidate block %d", mc, m->cb);
   const int cpad = round_up(mc, TILE), np = m->np;
   cudaStream_t s = m->stream;
+  AllocStream alloc_scope(s);
   GPB_TRY(predict_block(m, Xc, mc, dev, 1, include_likelihood));
   // cov = Kxx - tmp^T tmp (+ noise I)      posterior.py:281-284, gaussian.py:104-107
   DevBuf cbuf;
@@ -913,6 +937,7 @@ int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int 
   const int d = m->d;
   const bool grad = df != nullptr;
   cudaStream_t s = m->stream;
+  AllocStream alloc_scope(s);
   GPB_TRY(launch_topk_init(m->topv, m->topi, k, s));
   for (int c0 = 0; c0 < mc; c0 += m->cb) {
     const int mcb = std::min(m->cb, mc - c0);
@@ -966,7 +991,7 @@ static int kern_prepare(KernTmp &t, int d, int n, const double *X, int m, const 
   GPB_TRY(t.ls.alloc(2 * d * sizeof(double)));
   t.ls_dev = t.ls.d();
   t.inv_ls_dev = t.ls.d() + d;
-  GPB_TRY(upload_ls(ls, nls, d, t.ls_dev, t.inv_ls_dev, s));
+  GPB_TRY(set_ls(ls, nls, d, t.ls_dev, t.inv_ls_dev, s));
   GPB_TRY(t.xat.alloc((size_t)d * t.npa * sizeof(double)));
   t.XaT = t.xat.d();
   GPB_TRY(launch_scale_transpose(t.Xa, n, d, t.ls_dev, t.XaT, t.npa, s));
@@ -987,6 +1012,7 @@ static int kern_prepare(KernTmp &t, int d, int n, const double *X, int m, const 
 int gpb_kern_K(int kind, int d, int n, const double *X, int m, const double *X2, double variance, const double *lengthscale,
                int nls, double *K, int ldk, int dev, void *stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AllocStream alloc_scope(s);
   GPB_REQUIRE(K != nullptr, "kern_K: K is NULL");
   GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "kern_K: unknown kernel kind %d", kind);
   KernTmp t;
@@ -1053,6 +1079,7 @@ static int gower_prepare(GowerTmp &t, int d, int n, const double *X, int m, cons
 int gpb_kern_K_gower(int kind, int d, int n, const double *X, int m, const double *X2, double variance, const int *discrete,
                      const double *ranges, double *K, int ldk, int dev, void *stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AllocStream alloc_scope(s);
   GPB_REQUIRE(K != nullptr, "kern_K: K is NULL");
   GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "kern_K: unknown kernel kind %d", kind);
   GowerTmp t;
@@ -1085,6 +1112,7 @@ int gpb_kern_update_gradients_full_gower(int kind, int d, int n, const double *X
   GPB_TRY(gpb_kern_update_gradients_full(kind, d, n, X, m, X2, dL_dK, ld, variance, lengthscale, nls, out, dev, stream));
   // variance term: sum(K_gower * dL_dK) / variance (stationary.py:224 with the patched K)
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AllocStream alloc_scope(s);
   GowerTmp t;
   GPB_TRY(gower_prepare(t, d, n, X, m, X2, discrete, ranges, dev, s));
   const int cols = X2 ? m : n;
@@ -1112,6 +1140,7 @@ int gpb_kern_update_gradients_full_gower(int kind, int d, int n, const double *X
 int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
                                    double variance, const double *lengthscale, int nls, double *out, int dev, void *stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AllocStream alloc_scope(s);
   GPB_REQUIRE(dL_dK && out, "update_gradients_full: NULL argument");
   GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "update_gradients_full: unknown kernel kind %d", kind);
   KernTmp t;
@@ -1148,6 +1177,7 @@ int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int 
 int gpb_kern_gradients_X(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
                          double variance, const double *lengthscale, int nls, double *out, int dev, void *stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AllocStream alloc_scope(s);
   GPB_REQUIRE(dL_dK && out, "gradients_X: NULL argument");
   GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "gradients_X: unknown kernel kind %d", kind);
   KernTmp t;
@@ -1181,6 +1211,7 @@ int gpb_kern_gradients_X(int kind, int d, int n, const double *X, int m, const d
 // =====================================================================================================================
 int gpb_pdinv(int n, const double *A, int lda, double *L, double *Ai, double *Li, double *logdet, int dev, void *stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AllocStream alloc_scope(s);
   GPB_REQUIRE(A && n >= 1 && lda >= n, "pdinv: bad arguments");
   GPB_REQUIRE(gpb_device_count() > 0, "pdinv: no CUDA device visible -- libgpb200 has no CPU fallback");
   const int np = round_up(n, TILE), nb = np / TILE;
@@ -1247,6 +1278,7 @@ int gpb_pdinv(int n, const double *A, int lda, double *L, double *Ai, double *Li
 int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, void *stream) {
   // (L L^T) X = B as X = M^T (M B) with M = L^-1 rebuilt by the triangular-inverse recursion (factor_trtri).
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AllocStream alloc_scope(s);
   GPB_REQUIRE(L && B && n >= 1 && ldl >= n && nrhs >= 1, "potrs: bad arguments");
   GPB_REQUIRE(gpb_device_count() > 0, "potrs: no CUDA device visible -- libgpb200 has no CPU fallback");
   const int np = round_up(n, TILE), nb = np / TILE;
@@ -1307,6 +1339,7 @@ int gpb_potri(int n, const double *L, int ldl, double *Ai, int ldai, int dev, vo
   // A^-1 = L^-T L^-1 from the Cholesky factor: triangular-inverse recursion (dtrtri) + the lower-tile product M^T M
   // (dlauum), then mirrored like GPy's symmetrify.
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  AllocStream alloc_scope(s);
   GPB_REQUIRE(L && Ai && n >= 1 && ldl >= n && ldai >= n, "potri: bad arguments");
   GPB_REQUIRE(gpb_device_count() > 0, "potri: no CUDA device visible -- libgpb200 has no CPU fallback");
   const int np = round_up(n, TILE);
