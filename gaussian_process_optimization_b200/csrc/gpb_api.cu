@@ -201,6 +201,18 @@ struct gpb_model {
   double variance = 1.0, noise = 1.0, jitter = 0.0;
   std::vector<double> ls;
   bool have_data = false, scaled_valid = false, fitted = false, have_wi = false;
+  // CUDA-graph replay of the NLL+grad launch sequence (small / medium N: an evaluation is a chain of tens to hundreds of short
+  // kernels whose host-side launch cost is a good part of the wall time).  One executable graph per want_grad, valid for one
+  // (n, np, configuration epoch); the hyper-parameters reach the kernels through theta_dev and the pinned block.
+  struct FitGraph {
+    cudaGraphExec_t exec = nullptr;
+    int n = -1, np = -1, epoch = -1, seen = 0;
+    long long launches = 0;
+    bool l_pending = false, have_wi = false;
+    int l_from = 0;
+  } graphs[2];
+  bool graph_failed = false, own_stream = false;
+  double *theta_dev = nullptr;
   int wi_from = 0;  // > 0 (after gpb_model_append): the leading wi_from block of W holds the old Ky^-1, downdated; rows beyond are stale
   cudaStream_t stream = 0;
   void *ws = nullptr;
@@ -236,6 +248,7 @@ static int check_device(const gpb_model *m, const char *what) {
 }
 
 static int g_overlap_min_n = 512;  // 0 disables the two-stream schedule (gpb_set_overlap)
+static int g_config_epoch = 0;     // bumped by the tuning entry points: captured launch sequences are stale afterwards
 
 static size_t carve(int n_cap, int d, int p, int cb, gpb_model *m, char *base) {
   const size_t np = round_up(std::max(n_cap, 1), TILE);
@@ -263,6 +276,7 @@ static size_t carve(int n_cap, int d, int p, int cb, gpb_model *m, char *base) {
   take(d, m ? &m->gflag_dev : nullptr);
   take(d, m ? &m->ginv_dev : nullptr);
   take(d + 16, m ? &m->scal : nullptr);
+  take(8, m ? &m->theta_dev : nullptr);
   take((size_t)cb * d, m ? &m->Xc : nullptr);
   take((size_t)cb * d, m ? &m->XcT : nullptr);
   take((size_t)cb * np, m ? &m->KxT : nullptr);
@@ -330,6 +344,17 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
   m->nls = ard ? d : 1;
   m->ls.assign(m->nls, 1.0);
   m->stream = reinterpret_cast<cudaStream_t>(stream);
+  if (m->stream == nullptr) {
+    // The legacy default stream cannot be captured into a CUDA graph.  A blocking stream of the model's own takes its place:
+    // it synchronises implicitly with the legacy stream in both directions, so work the caller has queued there (and reads of
+    // our results from there) stay ordered exactly as before.
+    if (cudaStreamCreate(&m->stream) == cudaSuccess) {
+      m->own_stream = true;
+    } else {
+      (void)cudaGetLastError();
+      m->stream = nullptr;
+    }
+  }
   if (cudaGetDevice(&m->device) != cudaSuccess) {
     delete m;
     set_error("model_create: cudaGetDevice failed");
@@ -373,7 +398,10 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
 int gpb_model_destroy(gpb_model *m) {
   if (!m) return 0;
   cudaStreamSynchronize(m->stream);
+  for (auto &g : m->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   factor_overlap_destroy(m->ov);
+  if (m->own_stream) cudaStreamDestroy(m->stream);
   if (m->lp_buf) cudaFree(m->lp_buf);
   if (m->own_ws && m->ws) cudaFree(m->ws);
   if (m->pinned) cudaFreeHost(m->pinned);
@@ -487,6 +515,124 @@ static int ensure_wi(gpb_model *m) {
 
 // append_from > 0: the leading append_from x append_from block of the factorisation is valid for the current hyper-parameters
 // (gpb_model_append); only the block rows from there on are built and factorised.
+// The launch sequence of one evaluation through the general path, results to the pinned block; no synchronisation, so that it
+// can be captured.  theta != NULL (graph capture): hyper-parameters come from device memory fed by the pinned block
+// [136] variance, [137] diag_add, [138 ..) ls[d], inv_ls[d].
+static int fit_launch_general(gpb_model *m, int want_grad, double extra_jitter, int append_from, const double *theta) {
+  const int n = m->n, np = m->np, d = m->d, p = m->p;
+  if (theta) {
+    GPB_CUDA(cudaMemcpyAsync(m->theta_dev, m->pinned + 136, 2 * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    GPB_CUDA(cudaMemcpyAsync(m->ls_dev, m->pinned + 138, d * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    GPB_CUDA(cudaMemcpyAsync(m->inv_ls_dev, m->pinned + 138 + d, d * sizeof(double), cudaMemcpyHostToDevice, m->stream));
+    GPB_TRY(launch_scale_transpose(m->X, n, d, m->ls_dev, m->XsT, np, m->stream));
+    m->scaled_valid = true;
+  } else {
+    GPB_TRY(ensure_scaled(m));
+  }
+  // Ky = K + (noise + 1e-8 [+ jitter]) I     exact_gaussian_inference.py:55-56
+  const KCoords kc = train_coords(m);
+  GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, d, n, n, kc.var, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np, np,
+                      m->stream, kc.gflag, append_from, theta));
+  // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
+  static int fork_div = -1;
+  if (fork_div < 0) {
+    const char *e = getenv("GPB_FORK_DIV");
+    fork_div = e ? std::max(1, atoi(e)) : 8;
+  }
+  const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / fork_div) : 0;
+  if (m->ov && fork_min_n > 0 && np >= fork_min_n) {
+    // critical path on the model's high-priority stream, T21 products on its low-priority side streams (gpb_chol.cu)
+    Factor fo = m->f;
+    fo.stream = m->ov->main;
+    fo.ov = m->ov;
+    m->ov->min_n = fork_min_n;
+    GPB_CUDA(cudaEventRecord(m->ov->enter, m->stream));
+    GPB_CUDA(cudaStreamWaitEvent(m->ov->main, m->ov->enter, 0));
+    const int rc = append_from > 0 ? factor_append(fo, append_from) : factor_potrf_inv(fo);
+    m->f.l_pending = fo.l_pending;
+    m->f.l_from = fo.l_from;
+    GPB_CUDA(cudaEventRecord(m->ov->leave, m->ov->main));
+    GPB_CUDA(cudaStreamWaitEvent(m->stream, m->ov->leave, 0));
+    GPB_TRY(rc);
+  } else {
+    GPB_TRY(append_from > 0 ? factor_append(m->f, append_from) : factor_potrf_inv(m->f));
+  }
+  GPB_TRY(factor_solve(m->f, m->Yc, p, m->z, m->alpha));
+  GPB_TRY(factor_logdet(m->f, m->scal + 0));
+  dot_kernel<<<1, 1024, 0, m->stream>>>(m->alpha, m->Yc, p * np, m->scal + 1);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  if (want_grad) {
+    GPB_TRY(ensure_wi(m));
+    GPB_TRY(launch_kgrad(m->kind, 1, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->f.W, np, m->alpha, np, p, m->gpart,
+                         m->scal + 2, m->stream, theta));
+    // Gower patch: only the variance term sees the patched K (stationary.py:224); it overwrites kgrad's Euclidean one
+    if (m->gower)
+      GPB_TRY(launch_kvar_gower(m->kind, 1, kc.XT, np, kc.XT, np, d, n, n, kc.var, kc.gflag, m->f.W, np, m->alpha, np, p, m->gpart,
+                                m->scal + 2, m->stream));
+  }
+  GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 5) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  GPB_CUDA(cudaMemcpyAsync(m->pinned + 128, m->f.info, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  return 0;
+}
+
+// Replay (or first capture) of the general launch sequence as a CUDA graph.  Returns 0 when the evaluation has been enqueued,
+// 1 when the caller must take the ordinary path (first sight of this shape, or graphs unavailable), < 0 on error.
+static int fit_launch_graph(gpb_model *m, int want_grad, double extra_jitter) {
+  gpb_model::FitGraph &g = m->graphs[want_grad ? 1 : 0];
+  const int n = m->n, np = m->np, d = m->d;
+  if (g.n != n || g.np != np || g.epoch != g_config_epoch) {   // new shape: one ordinary evaluation first (it also configures
+    if (g.exec) cudaGraphExecDestroy(g.exec);                  // the kernels' attributes, which must not happen inside a capture)
+    g = gpb_model::FitGraph();
+    g.n = n;
+    g.np = np;
+    g.epoch = g_config_epoch;
+    g.seen = 1;
+    return 1;
+  }
+  m->pinned[136] = m->variance;
+  m->pinned[137] = m->noise + 1e-8 + extra_jitter;
+  for (int q = 0; q < d; ++q) {
+    const double l = m->ls[m->nls == 1 ? 0 : q];
+    m->pinned[138 + q] = l;
+    m->pinned[138 + d + q] = 1.0 / l;
+  }
+  if (!g.exec) {
+    const long long l0 = g_launches.load(std::memory_order_relaxed);
+    if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      (void)cudaGetLastError();
+      m->graph_failed = true;
+      return 1;
+    }
+    const int rc = fit_launch_general(m, want_grad, extra_jitter, 0, m->theta_dev);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(m->stream, &graph);
+    if (rc != 0 || e != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+      (void)cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      g.exec = nullptr;
+      m->graph_failed = true;   // this model stays on the ordinary path
+      m->scaled_valid = false;
+      m->have_wi = false;
+      return 1;
+    }
+    cudaGraphDestroy(graph);
+    g.launches = g_launches.load(std::memory_order_relaxed) - l0;
+    g.l_pending = m->f.l_pending;
+    g.l_from = m->f.l_from;
+    g.have_wi = m->have_wi;
+  } else {
+    count_launch((int)g.launches);
+  }
+  GPB_CUDA(cudaGraphLaunch(g.exec, m->stream));
+  m->scaled_valid = true;
+  m->f.l_pending = g.l_pending;
+  m->f.l_from = g.l_from;
+  m->have_wi = g.have_wi;
+  m->wi_from = 0;
+  return 0;
+}
+
 static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *out, int append_from) {
   // Hyper-parameters outside the domain (an L-BFGS-B line search can push the transformed parameters to 0, inf or NaN):
   // the reference's NumPy path turns those into NaNs and ends in jitchol's LinAlgError (linalg.py:62-75), which paramz
@@ -520,52 +666,18 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
     m->scaled_valid = true;
     if (want_grad) m->have_wi = true;
   } else {
-  GPB_TRY(ensure_scaled(m));
-  // Ky = K + (noise + 1e-8 [+ jitter]) I     exact_gaussian_inference.py:55-56
-  const KCoords kc = train_coords(m);
-  GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, d, n, n, kc.var, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np, np,
-                      m->stream, kc.gflag, append_from));
-  // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
-  static int fork_div = -1;
-  if (fork_div < 0) {
-    const char *e = getenv("GPB_FORK_DIV");
-    fork_div = e ? std::max(1, atoi(e)) : 8;
+    static int graph_max_np = -1;
+    if (graph_max_np < 0) {
+      const char *e = getenv("GPB_GRAPH_MAX_NP");
+      graph_max_np = e ? atoi(e) : 2048;   // replay pays up to here (scripts/small_n_perf.py: -16% at N = 256, -6% at 1024, nothing at 4096)
+    }
+    int rc = 1;
+    if (np <= graph_max_np && append_from == 0 && !m->gower && d <= 32 && !m->graph_failed && !gemm_profile_is_on())
+      rc = fit_launch_graph(m, want_grad, extra_jitter);
+    if (rc < 0) return rc;
+    if (rc == 1) GPB_TRY(fit_launch_general(m, want_grad, extra_jitter, append_from, nullptr));
   }
-  const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / fork_div) : 0;
-  if (m->ov && fork_min_n > 0 && np >= fork_min_n) {
-    // critical path on the model's high-priority stream, T21 products on its low-priority side streams (gpb_chol.cu)
-    Factor fo = m->f;
-    fo.stream = m->ov->main;
-    fo.ov = m->ov;
-    m->ov->min_n = fork_min_n;
-    GPB_CUDA(cudaEventRecord(m->ov->enter, m->stream));
-    GPB_CUDA(cudaStreamWaitEvent(m->ov->main, m->ov->enter, 0));
-    const int rc = append_from > 0 ? factor_append(fo, append_from) : factor_potrf_inv(fo);
-    m->f.l_pending = fo.l_pending;
-    m->f.l_from = fo.l_from;
-    GPB_CUDA(cudaEventRecord(m->ov->leave, m->ov->main));
-    GPB_CUDA(cudaStreamWaitEvent(m->stream, m->ov->leave, 0));
-    GPB_TRY(rc);
-  } else {
-    GPB_TRY(append_from > 0 ? factor_append(m->f, append_from) : factor_potrf_inv(m->f));
-  }
-  GPB_TRY(factor_solve(m->f, m->Yc, p, m->z, m->alpha));
-  GPB_TRY(factor_logdet(m->f, m->scal + 0));
-  dot_kernel<<<1, 1024, 0, m->stream>>>(m->alpha, m->Yc, p * np, m->scal + 1);
-  count_launch();
-  GPB_CHECK_LAUNCH();
-  if (want_grad) {
-    GPB_TRY(ensure_wi(m));
-    GPB_TRY(launch_kgrad(m->kind, 1, m->XsT, np, m->XsT, np, d, n, n, m->variance, m->f.W, np, m->alpha, np, p, m->gpart,
-                         m->scal + 2, m->stream));
-    // Gower patch: only the variance term sees the patched K (stationary.py:224); it overwrites kgrad's Euclidean one
-    if (m->gower)
-      GPB_TRY(launch_kvar_gower(m->kind, 1, kc.XT, np, kc.XT, np, d, n, n, kc.var, kc.gflag, m->f.W, np, m->alpha, np, p, m->gpart,
-                                m->scal + 2, m->stream));
-  }
-  }
-  GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 5) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
-  if (!tiny) GPB_CUDA(cudaMemcpyAsync(m->pinned + 128, m->f.info, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  if (tiny) GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 5) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   GPB_CUDA(cudaStreamSynchronize(m->stream));
   const int info = tiny ? (int)m->pinned[d + 4] : *reinterpret_cast<int *>(m->pinned + 128);
   if (info != 0) {
@@ -1405,10 +1517,14 @@ int gpb_potri(int n, const double *L, int ldl, double *Ai, int ldai, int dev, vo
 
 int gpb_set_overlap(int min_n) {
   g_overlap_min_n = min_n < 0 ? 0 : min_n;
+  ++g_config_epoch;
   return 0;
 }
 int gpb_profile_gemm(int enable) { return gemm_profile_enable(enable); }
-int gpb_gemm_config(int cfg) { return gemm_force_config(cfg); }
+int gpb_gemm_config(int cfg) {
+  ++g_config_epoch;
+  return gemm_force_config(cfg);
+}
 int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches) { return gemm_profile_collect(ms, flops, launches); }
 int gpb_profile_gemm_last(double *ms, double *flops) { return gemm_profile_last(ms, flops); }
 

@@ -213,6 +213,7 @@ struct GemmArgs {
 };
 int gemm_launch(int layout_a, int layout_b, const GemmArgs &g, cudaStream_t s);
 int gemm_profile_enable(int on);
+bool gemm_profile_is_on();
 int gemm_force_config(int cfg);  // 0 auto, 1 BIG (64x128), 2 MID (64x64), 3 SMALL (32x32)
 int gemm_profile_collect(double *ms, double *flops, long long *launches);
 int gemm_profile_last(double *ms, double *flops);

@@ -256,6 +256,8 @@ int gemm_profile_enable(int on) {
 
 static int g_big_config = 9;     // configuration of launches with >= 20 output blocks of 128x128 (100 + cfg selects it)
 
+bool gemm_profile_is_on() { return g_prof.on; }
+
 int gemm_force_config(int cfg) {
   if (cfg >= 100)
     g_big_config = cfg - 100;

@@ -57,10 +57,14 @@ template <int KIND, int GOWER>
 __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
                                                       int n_rows, int n_cols, double variance, double diag_add, int mode,
                                                       double *__restrict__ out, int ldo, const double *__restrict__ gflag,
-                                                      int row_blk0) {
+                                                      int row_blk0, const double *__restrict__ theta) {
   extern __shared__ double sm[];
   double *xa = sm;              // [d][64]
   double *xb = sm + d * KTILE;  // [d][64]
+  if (theta) {                  // CUDA-graph replays: the hyper-parameters live in device memory, not in the baked arguments
+    variance = theta[0];
+    diag_add = theta[1];
+  }
   const int row0 = (blockIdx.y + row_blk0) * KTILE, col0 = blockIdx.x * KTILE;   // row_blk0 > 0: only the rows from there on
   if (mode == 3) {
     // Ky for the factorisation: nothing reads the 128-blocks strictly above the diagonal (gpb_chol.cu only touches lower
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(256, 4) kmat_kernel(const double *__restrict__
 
 int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                 double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
-                cudaStream_t s, const double *gflag, int row_start) {
+                cudaStream_t s, const double *gflag, int row_start, const double *theta) {
   const size_t smem = (size_t)2 * d * KTILE * sizeof(double);
   GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large", d);
   GPB_REQUIRE(rows_pad % KTILE == 0 && cols_pad % KTILE == 0, "kmat: padded sizes must be multiples of %d", KTILE);
@@ -138,7 +142,7 @@ int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb
     if (smem > 48 * 1024)                                                                                                 \
       GPB_CUDA(cudaFuncSetAttribute(kmat_kernel<K_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kmat_kernel<K_, G_><<<grid, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, diag_add, mode, out, ldo, \
-                                                gflag, row_blk0);                                                         \
+                                                gflag, row_blk0, theta);                                                  \
   } while (0)
   if (kind == GPB_KERN_RBF) {
     if (gflag) GPB_KMAT(GPB_KERN_RBF, 1); else GPB_KMAT(GPB_KERN_RBF, 0);
@@ -167,8 +171,9 @@ template <int KIND, int FUSED>
 __global__ void __launch_bounds__(256, 3) kgrad_kernel(const double *__restrict__ XaT, int lda, const double *__restrict__ XbT, int ldb, int d,
                                                        int n_rows, int n_cols, double variance, const double *__restrict__ G, int ldg,
                                                        const double *__restrict__ alpha, int ld_alpha, int p_out, int tiles_x,
-                                                       double *__restrict__ part) {
+                                                       double *__restrict__ part, const double *__restrict__ theta) {
   extern __shared__ double sm[];
+  if (theta) variance = theta[0];    // CUDA-graph replays (see kmat_kernel)
   double *xa = sm;                   // [d][64]
   double *xb = sm + d * KTILE;       // [d][64]
   double *wacc = xb + d * KTILE;     // [8 warps][d + 2]
@@ -410,7 +415,7 @@ int launch_kvar_gower(int kind, int fused, const double *XaT, int lda, const dou
 
 int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                  double variance, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out, double *part,
-                 double *out_dev, cudaStream_t s) {
+                 double *out_dev, cudaStream_t s, const double *theta) {
   const size_t smem = (size_t)(2 * d * KTILE + 8 * (d + 2)) * sizeof(double);
   GPB_REQUIRE(smem <= 200 * 1024, "input dimension %d too large", d);
   const int tr = (n_rows + KTILE - 1) / KTILE, tc = (n_cols + KTILE - 1) / KTILE;
@@ -421,7 +426,7 @@ int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *
     if (smem > 48 * 1024)                                                                                                 \
       GPB_CUDA(cudaFuncSetAttribute(kgrad_kernel<K_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
     kgrad_kernel<K_, F_><<<tiles, 256, smem, s>>>(XaT, lda, XbT, ldb, d, n_rows, n_cols, variance, G, ldg, alpha, ld_alpha, \
-                                                  p_out, tc, part);                                                       \
+                                                  p_out, tc, part, theta);                                                \
   } while (0)
   if (kind == GPB_KERN_RBF) {
     if (fused) GPB_KGRAD(GPB_KERN_RBF, 1); else GPB_KGRAD(GPB_KERN_RBF, 0);

@@ -20,7 +20,8 @@ int launch_scale_transpose(const double *X, int n, int d, const double *ls_dev, 
 // a discrete dimension, `variance` is variance^d)
 int launch_kmat(int kind, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                 double variance, double diag_add, int mode, double *out, int ldo, int rows_pad, int cols_pad,
-                cudaStream_t s, const double *gflag = nullptr, int row_start = 0);   // row_start: only rows >= it (multiple of 64)
+                cudaStream_t s, const double *gflag = nullptr, int row_start = 0,    // row_start: only rows >= it (multiple of 64)
+                const double *theta = nullptr);   // theta != NULL: variance = theta[0], diag_add = theta[1] read on the device
 // out_dev[0] = sum K_gower . G  (variance-gradient term under the Gower patch); part: tiles doubles
 int launch_kvar_gower(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                       double vpow, const double *gflag, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out,
@@ -30,7 +31,7 @@ int launch_kvar_gower(int kind, int fused, const double *XaT, int lda, const dou
 // part: scratch of tiles * (d + 2) doubles.
 int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *XbT, int ldb, int d, int n_rows, int n_cols,
                  double variance, const double *G, int ldg, const double *alpha, int ld_alpha, int p_out, double *part,
-                 double *out_dev, cudaStream_t s);
+                 double *out_dev, cudaStream_t s, const double *theta = nullptr);   // theta != NULL: variance = theta[0] on the device
 
 int launch_gradx(int kind, const double *XcT, int ldc, int n_c, const double *XT, int ldx, int n, int d, double variance,
                  const double *inv_ls, const double *G1, int ldg1, double s1, int add_t, const double *G2, int ldg2, double s2,
