@@ -36,7 +36,7 @@ GPy = _NS(
 )
 
 GPyOpt = _NS(
-    methods=_NS(BayesianOptimization=_g.BayesianOptimization),
+    methods=_NS(BayesianOptimization=_g.BayesianOptimization, ModularBayesianOptimization=_g.ModularBayesianOptimization),
     models=_NS(GPModel=_g.GPModel, BOModel=_g.BOModel, base=_NS(BOModel=_g.BOModel), gpmodel=_NS(GPModel=_g.GPModel)),
     acquisitions=_NS(AcquisitionBase=_g.AcquisitionBase, AcquisitionEI=_g.AcquisitionEI, AcquisitionLCB=_g.AcquisitionLCB,
                      AcquisitionLP=_g.AcquisitionLP),

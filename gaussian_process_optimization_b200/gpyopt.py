@@ -1077,3 +1077,17 @@ class BayesianOptimization(BO):
             def f(x):
                 return -f_copy(x)
         return f
+
+
+class ModularBayesianOptimization(BO):
+    """methods/modular_bayesian_optimization.py:6-40: the BO loop around handlers the caller built (model, space, objective,
+    acquisition, evaluator, initial data) -- the second plug-in level of SURVEY 8b."""
+
+    def __init__(self, model, space, objective, acquisition, evaluator, X_init, Y_init=None, cost=None, normalize_Y=True,
+                 model_update_interval=1, de_duplication=False):
+        self.initial_iter = True
+        self.modular_optimization = True
+        super(ModularBayesianOptimization, self).__init__(model=model, space=space, objective=objective, acquisition=acquisition,
+                                                          evaluator=evaluator, X_init=X_init, Y_init=Y_init, cost=cost,
+                                                          normalize_Y=normalize_Y, model_update_interval=model_update_interval,
+                                                          de_duplication=de_duplication)

@@ -354,6 +354,26 @@ def test_bo_branin_runs_on_oracle_backend():
     assert bo.model_parameters_iterations.shape[1] == 3
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_modular_bo_equals_the_wrapper(backend):
+    """methods/modular_bayesian_optimization.py:24: the loop assembled from caller-built handlers proposes the same points
+    as BayesianOptimization assembling them itself (same seed, same initial design)."""
+    iters = 4
+    ref = _run_bo(backend, iters, restarts=2)
+    np.random.seed(0)
+    space = GPyOpt.Design_space(BRANIN_DOMAIN)
+    objective = GPyOpt.core.task.SingleObjective(branin)
+    X_init = GPyOpt.experiment_design.initial_design('random', space, 5)
+    model = make_gpmodel(backend, kernel=GPy.kern.RBF(2), exact_feval=True, verbose=False, optimize_restarts=2)
+    aopt = GPyOpt.optimization.AcquisitionOptimizer(space, 'lbfgs', model=model)
+    acq = GPyOpt.acquisitions.AcquisitionEI(model, space, aopt, None, 0.01)
+    bo = GPyOpt.methods.ModularBayesianOptimization(model, space, objective, acq, GPyOpt.core.evaluators.Sequential(acq), X_init)
+    bo.run_optimization(max_iter=iters)
+    assert bo.modular_optimization and bo.X.shape == (5 + iters, 2)
+    assert_allclose(bo.X, ref.X, rtol=1e-9, atol=1e-9)
+    assert_allclose(bo.Y, ref.Y, rtol=1e-9, atol=1e-9)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("acq", ["EI", "LCB"])
 def test_bo_branin_trajectory_matches_oracle(acq):
