@@ -71,6 +71,9 @@ SIGNATURES = {
     "gpb_profile_gemm_last": (c_int, [c_double_p, c_double_p]),
     "gpb_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.c_double, c_void_p, c_int, c_void_p, c_int, ctypes.c_double,
                           c_void_p, c_int, c_void_p]),
+    "gpb_ozaki_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.c_double, c_void_p, c_int, c_void_p, c_int, ctypes.c_double,
+                                c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "gpb_set_ozaki": (c_int, [c_int, c_int]),
 }
 
 _lib = None

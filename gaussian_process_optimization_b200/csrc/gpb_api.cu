@@ -1535,4 +1535,15 @@ int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A
   return gemm_launch(ta ? LAYOUT_COLK : LAYOUT_ROWK, tb ? LAYOUT_COLK : LAYOUT_ROWK, g, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// fp64 product through the int8 tensor cores (gpb_ozaki.cu); experimental, see include/gpb200.h
+int gpb_ozaki_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb,
+                    double beta, double *C, int ldc, int tri_out, int klo_mode, int khi_mode, int tri_a, int tri_b, int slices,
+                    void *stream) {
+  GPB_REQUIRE(A && B && C, "ozaki_dgemm: NULL argument");
+  GemmArgs g{A, lda, B, ldb, C, ldc, m, n, k, alpha, beta, tri_out, klo_mode, khi_mode};
+  return ozaki_gemm_launch(ta ? LAYOUT_COLK : LAYOUT_ROWK, tb ? LAYOUT_COLK : LAYOUT_ROWK, g, tri_a, tri_b, slices,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+int gpb_set_ozaki(int min_n, int slices) { return ozaki_configure(min_n, slices); }
+
 }  // extern "C"

@@ -218,6 +218,11 @@ int gemm_force_config(int cfg);  // 0 auto, 1 BIG (64x128), 2 MID (64x64), 3 SMA
 int gemm_profile_collect(double *ms, double *flops, long long *launches);
 int gemm_profile_last(double *ms, double *flops);
 
+// int8 tensor-core (tcgen05) Ozaki engine for the large products (gpb_ozaki.cu); experimental, off unless configured
+int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, int tri_b, int slices, cudaStream_t s);
+int ozaki_min_n();                           // products of the recursion with n >= this go through the engine (0 = off)
+int ozaki_configure(int min_n, int slices);
+
 // linalg drivers (gpb_chol.cu)
 int factor_potrf_inv(Factor &f);                 // A -> L, Mi = L^-1, *info
 int factor_trtri(Factor &f);                     // A holds a lower-triangular L (diag blocks clean) -> Mi = L^-1

@@ -1,0 +1,512 @@
+// fp64 products on the INT8 tensor cores (tcgen05.mma kind::i8, accumulators in TMEM, operands by TMA): an Ozaki-scheme GEMM
+// engine for the large products of the cholinv recursion (gpb_chol.cu).  EXPERIMENTAL, off by default (GPB_OZAKI_MIN_N /
+// gpb_set_ozaki): the default path of libgpb200 stays the fp64 DMMA engine of gpb_gemm.cu.
+//
+// Why: on sm_100a the fp64 tensor path is the warp-level DMMA (64 FMA/clk/SM = 37 TFLOP/s, shared with DFMA) -- tcgen05 has no
+// f64 kind -- while the int8 kind runs at ~4.5 POP/s.  Every fp64 operand is cut, row by row, into S signed 7-bit digits
+//     a_ik = 2^ea_i * sum_s A_s[i][k] 2^(-7 s),   |A_s| <= 127   (error-free: scaling by powers of two, trunc, subtract),
+// and the product is the sum over digit pairs of EXACT integer products
+//     C_ij = 2^(ea_i + eb_j) * sum_w 2^(-7 w) * sum_{s + t = w} (A_s B_t^T)_ij,       w = 2 .. S + 1  (pairs with s + t > S + 1
+// fall below the last digit and are dropped), S (S + 1) / 2 int8 products in all.  With S = 8 the result is as accurate as a
+// DGEMM (profiles/r1i_ozaki_numerics_study.json: log-likelihood and gradients of the whole evaluation to 1e-12).
+//
+// One kernel does the whole product for a 128 x 256 output tile: for each weight w (smallest first) the digit pairs s + t = w
+// are chained along k into ONE int32 accumulation in TMEM (at most 1024 k-blocks per accumulation: 127^2 * 128 * 1024 < 2^31),
+// drained by the epilogue warps into an fp64 running sum (read-modify-write of a tile that stays in L2) while the MMA warp
+// fills the second TMEM buffer with the next weight; the last drain applies the row / column scales, alpha and beta.
+// Triangular operands are exploited as in gpb_gemm.cu (per-tile k-ranges at 128 granularity, lower tiles only).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
+// warps 2-5 = epilogue (TMEM lane quarter = warp % 4).  4-stage smem ring of {A digit tile 128 x 128 B, B digit tile 256 x 128 B},
+// 128-byte swizzle, K-major.
+#include <cuda.h>
+
+#include "gpb_common.cuh"
+
+namespace gpb {
+
+namespace oz {
+constexpr int BM = 128, BN = 256, BKB = 128;   // output tile; bytes (= int8 elements) of k per stage
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BKB, B_BYTES = BN * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int NTHREADS = 192;
+constexpr int GROUP_KB = 1024;                 // k-blocks per int32 accumulation: 127^2 * 128 * 1024 = 2.11e9 < 2^31
+constexpr int DIGIT_BITS = 7;
+constexpr int MAX_S = 12;
+
+struct Params {
+  int M, N, K, S;
+  int tri_out, klo_mode, khi_mode;
+  double alpha, beta;
+  const double *ra, *rb;   // 2^ea_i (M), 2^eb_j (N)
+  double *C; int ldc;
+  double *T; int ldt;      // running sum (aliases C when beta == 0)
+  int tiles_m, tiles_n;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a pipeline bug traps (the launch fails with an error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO = 64 x 16 B), descriptor
+// version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  The tile base is 1024-byte aligned; a k-step of 32 bytes inside the
+// swizzle atom advances the start-address field by 2.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::i8: D = s32 (bits 4-5 = 2), A = B = signed 8 bit (bits 7-9, 10-12 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+  // ---- tile coordinates (longest k-ranges first) ----
+  int tm, tn;
+  {
+    constexpr int GROUP = 8;
+    const int t = blockIdx.x;
+    const int in_group = GROUP * p.tiles_n;
+    const int gid = t / in_group, first = gid * GROUP;
+    const int gsz = min(p.tiles_m - first, GROUP);
+    const int r = t - gid * in_group;
+    tm = first + r % gsz;
+    tn = r / gsz;
+    if (p.khi_mode == 2) tn = p.tiles_n - 1 - tn;
+    if (p.khi_mode == 1) tm = p.tiles_m - 1 - tm;
+  }
+  const int row0 = tm * BM, col0 = tn * BN;
+  if (p.tri_out && col0 > row0 + BM - 1) return;          // tile entirely above the diagonal
+  const int col_last = min(col0 + BN, p.N) - 128;          // first column of the last 128-block of the tile
+  int klo = (p.klo_mode == 1) ? row0 : (p.klo_mode == 2) ? col0 : 0;
+  int khi = (p.khi_mode == 1) ? row0 + 128 : (p.khi_mode == 2) ? col_last + 128 : p.K;
+  if (khi > p.K) khi = p.K;
+  const int kb0 = klo / BKB, nkb = (khi - klo) / BKB;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE_BYTES;       // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = p.S + 1; w >= 2; --w) {
+        const int s_lo = max(1, w - p.S), s_hi = min(p.S, w - 1);
+        for (int s = s_lo; s <= s_hi; ++s) {
+          const int t = w - s;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+            const uint32_t dst = base + stage * STAGE_BYTES;
+            tma_load_3d(dst, &mapA, (kb0 + kb) * BKB, row0, s - 1, full_bar(stage));
+            tma_load_3d(dst + A_BYTES, &mapB, (kb0 + kb) * BKB, col0, t - 1, full_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issue =====
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase[2] = {0, 0};
+      for (int w = p.S + 1; w >= 2; --w) {
+        const int npairs = min(p.S, w - 1) - max(1, w - p.S) + 1;
+        const int total = npairs * nkb;
+        for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
+          const int g1 = min(total, g0 + GROUP_KB);
+          mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          for (int idx = g0; idx < g1; ++idx) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = base + stage * STAGE_BYTES, b_addr = a_addr + A_BYTES;
+            const uint64_t ad = smem_desc(a_addr), bd = smem_desc(b_addr);
+#pragma unroll
+            for (int k = 0; k < BKB / 32; ++k) umma_i8(d_tmem, ad + 2 * k, bd + 2 * k, IDESC, (idx > g0 || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(tfull_bar(acc));
+          acc_phase[acc] ^= 1;
+          acc ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: TMEM -> fp64 running sum (global, L2 resident) -> final scaling =====
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int row = row0 + q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    bool first = true;
+    double *Trow = p.T + (size_t)row * p.ldt + col0;
+    double *Crow = p.C + (size_t)row * p.ldc + col0;
+    const double ra = p.alpha * p.ra[row];
+    int ncols = min(BN, p.N - col0);
+    if (p.tri_out) ncols = min(ncols, row0 + BM - col0);    // 128-blocks above the diagonal are left untouched
+    for (int w = p.S + 1; w >= 2; --w) {
+      const int npairs = min(p.S, w - 1) - max(1, w - p.S) + 1;
+      const int total = npairs * nkb;
+      const double sc = exp2((double)(-DIGIT_BITS * w));
+      for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
+        const bool last = (w == 2) && (g0 + GROUP_KB >= total);
+        mbar_wait(tfull_bar(acc), acc_phase[acc]);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c0, v);
+          if (!last) {
+            if (first) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                double2 o = make_double2(sc * (double)(int)v[j], sc * (double)(int)v[j + 1]);
+                *reinterpret_cast<double2 *>(Trow + c0 + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                double2 o = *reinterpret_cast<double2 *>(Trow + c0 + j);
+                o.x = fma(sc, (double)(int)v[j], o.x);
+                o.y = fma(sc, (double)(int)v[j + 1], o.y);
+                *reinterpret_cast<double2 *>(Trow + c0 + j) = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              double2 o = first ? make_double2(0.0, 0.0) : *reinterpret_cast<double2 *>(Trow + c0 + j);
+              o.x = fma(sc, (double)(int)v[j], o.x) * (ra * p.rb[col0 + c0 + j]);
+              o.y = fma(sc, (double)(int)v[j + 1], o.y) * (ra * p.rb[col0 + c0 + j + 1]);
+              if (p.beta != 0.0) {
+                const double2 c = *reinterpret_cast<double2 *>(Crow + c0 + j);
+                o.x = fma(p.beta, c.x, o.x);
+                o.y = fma(p.beta, c.y, o.y);
+              }
+              *reinterpret_cast<double2 *>(Crow + c0 + j) = o;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
+        first = false;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- digit extraction ------------------------------------------------------------------------------------------------------
+// op(P)[i][k] = P[i * ld + k] (LAYOUT_ROWK) or P[k * ld + i] (LAYOUT_COLK); tri: 0 = full, 1 = valid where k-block <= i-block
+// (lower-triangular factor, row-major), 2 = valid where k-block >= i-block (its transpose).  Invalid 128-blocks are never read
+// (they hold scratch of the recursion) and get zero digits.
+__device__ __forceinline__ bool block_valid(int tri, int ib, int kb) { return tri == 0 || (tri == 1 ? kb <= ib : kb >= ib); }
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) oz_absmax_kernel(const double *__restrict__ P, int ld, int tri, unsigned long long *amax) {
+  const int ib = blockIdx.x, kb = blockIdx.y;
+  if (!block_valid(tri, ib, kb)) return;
+  const int tid = threadIdx.x;
+  if (LAYOUT == LAYOUT_ROWK) {
+    const int tx = tid & 31, ty = tid >> 5;
+    for (int rr = ty; rr < 128; rr += 8) {
+      const double *row = P + (size_t)(ib * 128 + rr) * ld + kb * 128;
+      double m = fmax(fmax(fabs(row[tx]), fabs(row[tx + 32])), fmax(fabs(row[tx + 64]), fabs(row[tx + 96])));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (tx == 0) atomicMax(amax + ib * 128 + rr, (unsigned long long)__double_as_longlong(m));
+    }
+  } else {
+    __shared__ double sm[128];
+    const int i = tid & 127, half = tid >> 7;
+    const double *col = P + (size_t)(kb * 128 + half * 64) * ld + ib * 128 + i;
+    double m = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) m = fmax(m, fabs(col[(size_t)k * ld]));
+    if (half == 1) sm[i] = m;
+    __syncthreads();
+    if (half == 0) atomicMax(amax + ib * 128 + i, (unsigned long long)__double_as_longlong(fmax(m, sm[i])));
+  }
+}
+
+// One CTA per 64 (i) x 64 (k) sub-block: stage through shared memory, then every thread cuts 16 consecutive k of one row into S
+// digits and stores them as one 16-byte vector per digit plane.  digits: [S][R][K] int8, k contiguous.
+template <int LAYOUT>
+__global__ void __launch_bounds__(256)
+oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int S, const unsigned long long *__restrict__ amax,
+                int8_t *__restrict__ digits, double *__restrict__ scale) {
+  __shared__ double sm[64][65];
+  const int i0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int tid = threadIdx.x;
+  const bool valid = block_valid(tri, i0 >> 7, k0 >> 7);
+  const int r = tid >> 2, seg = (tid & 3) * 16;
+  const size_t plane = (size_t)R * K;
+  int8_t *out = digits + (size_t)(i0 + r) * K + k0 + seg;
+  if (!valid) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int s = 0; s < S; ++s) *reinterpret_cast<uint4 *>(out + s * plane) = z;
+    return;
+  }
+  if (LAYOUT == LAYOUT_ROWK) {
+    const int c = tid & 63, rr0 = tid >> 6;
+    for (int rr = rr0; rr < 64; rr += 4) sm[rr][c] = P[(size_t)(i0 + rr) * ld + k0 + c];
+  } else {
+    const int c = tid & 63, kk0 = tid >> 6;
+    for (int kk = kk0; kk < 64; kk += 4) sm[c][kk] = P[(size_t)(k0 + kk) * ld + i0 + c];
+  }
+  __syncthreads();
+  const double am = __longlong_as_double((long long)amax[i0 + r]);
+  int e = 0;
+  if (am > 0.0 && am < 1e308) frexp(am, &e);            // am = f 2^e, f in [0.5, 1): |x| 2^-e < 1
+  const double inv = ldexp(1.0, -e);
+  if (seg == 0) scale[i0 + r] = ldexp(1.0, e);          // every valid sub-block of the row writes the same value
+  double x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = sm[r][seg + j] * inv;
+  for (int s = 0; s < S; ++s) {
+    uint32_t wds[4];
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      uint32_t wv = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        double &v = x[q4 * 4 + b];
+        v *= 128.0;
+        const double d = trunc(v);
+        v -= d;
+        wv |= ((uint32_t)(int)d & 0xFFu) << (8 * b);
+      }
+      wds[q4] = wv;
+    }
+    *reinterpret_cast<uint4 *>(out + s * plane) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// digits [S][R][K] int8 -> 3-d tensor map, box {128 bytes of k, box_rows, 1}, 128-byte swizzle
+static int make_map(CUtensorMap *map, const int8_t *digits, int R, int K, int S, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  GPB_REQUIRE(fn != nullptr, "ozaki: cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)S};
+  cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)R * (cuuint64_t)K};
+  cuuint32_t box[3] = {(cuuint32_t)BKB, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)digits, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GPB_REQUIRE(r == CUDA_SUCCESS, "ozaki: cuTensorMapEncodeTiled failed (%d) for R=%d K=%d S=%d", (int)r, R, K, S);
+  return 0;
+}
+
+struct Workspace {
+  int8_t *dA = nullptr, *dB = nullptr;
+  size_t capA = 0, capB = 0;
+  double *ra = nullptr, *rb = nullptr;
+  unsigned long long *amax = nullptr;   // [0, cap) for A, [cap, 2 cap) for B
+  size_t cap_rows = 0;
+  double *T = nullptr;
+  size_t capT = 0;
+};
+static Workspace g_ws[64];
+
+static int ensure(void **p, size_t *cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*p) GPB_CUDA(cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  GPB_CUDA(cudaMalloc(p, need));
+  *cap = need;
+  return 0;
+}
+
+static int g_slices = 8;
+static int g_min_n = -1;   // -1: read GPB_OZAKI_MIN_N once; 0: off
+
+}  // namespace oz
+
+int ozaki_min_n() {
+  if (oz::g_min_n < 0) {
+    const char *e = getenv("GPB_OZAKI_MIN_N");
+    oz::g_min_n = e ? atoi(e) : 0;
+    const char *s = getenv("GPB_OZAKI_SLICES");
+    if (s && atoi(s) >= 1 && atoi(s) <= oz::MAX_S) oz::g_slices = atoi(s);
+  }
+  return oz::g_min_n;
+}
+int ozaki_configure(int min_n, int slices) {
+  GPB_REQUIRE(min_n >= 0 && slices >= 1 && slices <= oz::MAX_S, "ozaki: min_n >= 0 and 1 <= slices <= %d", oz::MAX_S);
+  oz::g_min_n = min_n;
+  oz::g_slices = slices;
+  return 0;
+}
+
+// C = alpha op(A) op(B)^T + beta C through the int8 tensor cores.  Same argument meaning as gemm_launch (gpb_gemm.cu); tri_a /
+// tri_b: validity pattern of the stored operand (see oz_split_kernel).  M, N, K multiples of 128.
+int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, int tri_b, int slices, cudaStream_t st) {
+  using namespace oz;
+  const int S = slices > 0 ? slices : g_slices;
+  GPB_REQUIRE(g.M % 128 == 0 && g.N % 128 == 0 && g.K % 128 == 0 && g.M > 0 && g.N > 0 && g.K > 0, "ozaki: sizes must be multiples of 128");
+  GPB_REQUIRE(!g.tri_out || g.M == g.N, "ozaki: tri_out needs a square output");
+  GPB_REQUIRE(S >= 1 && S <= MAX_S, "ozaki: bad digit count %d", S);
+  int dev = 0;
+  GPB_CUDA(cudaGetDevice(&dev));
+  GPB_REQUIRE(dev >= 0 && dev < 64, "ozaki: device ordinal");
+  Workspace &ws = g_ws[dev];
+  const bool same = (g.A == g.B && g.lda == g.ldb && layout_a == layout_b && tri_a == tri_b && g.M == g.N);
+  GPB_TRY(ensure((void **)&ws.dA, &ws.capA, (size_t)S * g.M * g.K));
+  if (!same) GPB_TRY(ensure((void **)&ws.dB, &ws.capB, (size_t)S * g.N * g.K));
+  const size_t rows = (size_t)(g.M > g.N ? g.M : g.N);
+  if (ws.cap_rows < rows) {
+    if (ws.ra) { GPB_CUDA(cudaFree(ws.ra)); GPB_CUDA(cudaFree(ws.rb)); GPB_CUDA(cudaFree(ws.amax)); }
+    ws.cap_rows = 0;
+    GPB_CUDA(cudaMalloc((void **)&ws.ra, rows * sizeof(double)));
+    GPB_CUDA(cudaMalloc((void **)&ws.rb, rows * sizeof(double)));
+    GPB_CUDA(cudaMalloc((void **)&ws.amax, 2 * rows * sizeof(unsigned long long)));
+    ws.cap_rows = rows;
+  }
+  double *T = g.C;
+  int ldt = g.ldc;
+  if (g.beta != 0.0) {
+    GPB_TRY(ensure((void **)&ws.T, &ws.capT, (size_t)g.M * g.N * sizeof(double)));
+    T = ws.T;
+    ldt = g.N;
+  }
+  GPB_CUDA(cudaMemsetAsync(ws.amax, 0, 2 * ws.cap_rows * sizeof(unsigned long long), st));
+  auto split = [&](int layout, const double *P, int ld, int R, int tri, unsigned long long *amax, int8_t *dig, double *scale) -> int {
+    dim3 g1(R / 128, g.K / 128), g2(R / 64, g.K / 64);
+    if (layout == LAYOUT_ROWK) {
+      oz_absmax_kernel<LAYOUT_ROWK><<<g1, 256, 0, st>>>(P, ld, tri, amax);
+      oz_split_kernel<LAYOUT_ROWK><<<g2, 256, 0, st>>>(P, ld, R, g.K, tri, S, amax, dig, scale);
+    } else {
+      oz_absmax_kernel<LAYOUT_COLK><<<g1, 256, 0, st>>>(P, ld, tri, amax);
+      oz_split_kernel<LAYOUT_COLK><<<g2, 256, 0, st>>>(P, ld, R, g.K, tri, S, amax, dig, scale);
+    }
+    count_launch(2);
+    GPB_CHECK_LAUNCH();
+    return 0;
+  };
+  GPB_TRY(split(layout_a, g.A, g.lda, g.M, tri_a, ws.amax, ws.dA, ws.ra));
+  if (!same) GPB_TRY(split(layout_b, g.B, g.ldb, g.N, tri_b, ws.amax + ws.cap_rows, ws.dB, ws.rb));
+  CUtensorMap mapA, mapB;
+  GPB_TRY(make_map(&mapA, ws.dA, g.M, g.K, S, BM));
+  GPB_TRY(make_map(&mapB, same ? ws.dA : ws.dB, g.N, g.K, S, BN));
+  Params p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.S = S;
+  p.tri_out = g.tri_out; p.klo_mode = g.klo_mode; p.khi_mode = g.khi_mode;
+  p.alpha = g.alpha; p.beta = g.beta;
+  p.ra = ws.ra; p.rb = same ? ws.ra : ws.rb;
+  p.C = g.C; p.ldc = g.ldc; p.T = T; p.ldt = ldt;
+  p.tiles_m = g.M / BM; p.tiles_n = (g.N + BN - 1) / BN;
+  static unsigned long long configured = 0;
+  if (needs_func_config(configured))
+    GPB_CUDA(cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  ozaki_mma_kernel<<<p.tiles_m * p.tiles_n, NTHREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace gpb

@@ -169,6 +169,23 @@ def dgemm(ta, tb, alpha, A, B, beta, C):
     return C
 
 
+def ozaki_dgemm(ta, tb, alpha, A, B, beta, C, slices=0, tri_out=0, klo_mode=0, khi_mode=0, tri_a=0, tri_b=0):
+    """Experimental: the same product through the int8 tensor cores (Ozaki scheme, csrc/gpb_ozaki.cu).  C is updated in place."""
+    lib = _lib.require_gpu()
+    assert is_torch(A) and is_torch(B) and is_torch(C)
+    m, n = C.shape
+    k = A.shape[0] if ta else A.shape[1]
+    check(lib.gpb_ozaki_dgemm(int(ta), int(tb), m, n, k, float(alpha), ptr(A), A.stride(0), ptr(B), B.stride(0), float(beta), ptr(C),
+                              C.stride(0), int(tri_out), int(klo_mode), int(khi_mode), int(tri_a), int(tri_b), int(slices),
+                              _lib.current_stream()), "ozaki_dgemm")
+    return C
+
+
+def set_ozaki(min_n, slices=8):
+    """Experimental: products of the factorisation with >= min_n rows go through the int8 engine (0 = off, the default)."""
+    check(_lib.load().gpb_set_ozaki(int(min_n), int(slices)), "set_ozaki")
+
+
 def gemm_config(cfg):
     """0 auto, 1 = 64x128, 2 = 64x64, 3 = 32x32 CTA tiles (tuning / tests)."""
     check(_lib.load().gpb_gemm_config(int(cfg)), "gemm_config")

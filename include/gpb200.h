@@ -169,6 +169,20 @@ int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches);
 /* Duration (ms) and executed flops of the last recorded GEMM launch (call before collect). */
 int gpb_profile_gemm_last(double *ms, double *flops);
 
+/* ---- experimental: fp64 products on the INT8 tensor cores (Ozaki scheme; csrc/gpb_ozaki.cu) ------------------------- */
+/* C = alpha op(A) op(B)^T + beta C like gpb_dgemm, computed as `slices` (0 = default 8) signed 7-bit digits per operand and
+ * slices (slices + 1) / 2 exact int8 x int8 -> int32 products on tcgen05 (kind::i8, TMEM accumulators, TMA operands), recombined
+ * in fp64.  tri_out / klo_mode / khi_mode: lower-tile output and per-tile k-ranges at 128 granularity (0 / 0 / 0 = plain product);
+ * tri_a / tri_b: 0 = full operand, 1 = only the 128-blocks with k-block <= row-block are valid, 2 = k-block >= row-block.
+ * m, n, k multiples of 128.  Device pointers only.  Replaces nothing in the reference by itself: it is an alternative engine for
+ * the products inside pdinv (GPy/GPy/util/linalg.py:193-214). */
+int gpb_ozaki_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb,
+                    double beta, double *C, int ldc, int tri_out, int klo_mode, int khi_mode, int tri_a, int tri_b, int slices,
+                    void *stream);
+/* Products of gpb_model_fit's factorisation with at least min_n rows go through the int8 engine (0 = off, the default; also
+ * GPB_OZAKI_MIN_N / GPB_OZAKI_SLICES in the environment). */
+int gpb_set_ozaki(int min_n, int slices);
+
 #ifdef __cplusplus
 }
 #endif
