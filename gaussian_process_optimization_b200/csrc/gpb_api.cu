@@ -672,7 +672,8 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
       graph_max_np = e ? atoi(e) : 2048;   // replay pays up to here (scripts/small_n_perf.py: -16% at N = 256, -6% at 1024, nothing at 4096)
     }
     int rc = 1;
-    if (np <= graph_max_np && append_from == 0 && !m->gower && d <= 32 && !m->graph_failed && !gemm_profile_is_on())
+    if (np <= graph_max_np && append_from == 0 && !m->gower && d <= 32 && !m->graph_failed && !gemm_profile_is_on() &&
+        !(ozaki_min_n() > 0 && np >= ozaki_min_n()))   // the int8 engine allocates its digit workspace on first use: not capturable
       rc = fit_launch_graph(m, want_grad, extra_jitter);
     if (rc < 0) return rc;
     if (rc == 1) GPB_TRY(fit_launch_general(m, want_grad, extra_jitter, append_from, nullptr));

@@ -933,11 +933,15 @@ static int cholinv(Factor &f, int off, int n, int depth, int split = 0) {
   double *M22 = f.Mi + (size_t)(off + h) * ld + off + h;
   double *S21 = f.W + (size_t)(off + h) * ld + off;   // r x h: L21
   double *T12 = f.W + (size_t)off * ld + off + h;     // h x r: T21^T
-  const bool fork = f.ov != nullptr && depth < FactorOverlap::MAX_DEPTH && n >= f.ov->min_n;
+  // n >= ozaki_min_n(): the four products of this level run on the int8 tensor cores (gpb_ozaki.cu; experimental, off by default).
+  // They share one digit workspace per stream, so such a level does not fork its T12 product.
+  const bool oz = split == 0 && ozaki_min_n() > 0 && n >= ozaki_min_n();   // (an append keeps the DMMA engine: r is small)
+  const bool fork = !oz && f.ov != nullptr && depth < FactorOverlap::MAX_DEPTH && n >= f.ov->min_n;
   GemmArgs g;
   // L21 = A21 * M11^T      (M11 lower: k <= column tile)
   g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 0, 2};
-  GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
+  if (oz) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, 0, 1, 0, f.stream));
+  else GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
   cudaStream_t s5 = f.stream;
   if (fork) {
     s5 = f.ov->side[depth];
@@ -946,16 +950,19 @@ static int cholinv(Factor &f, int off, int n, int depth, int split = 0) {
   }
   // T12 = M11^T * L21^T    (M11 lower: k >= row tile of T12)
   g = GemmArgs{M11, ld, S21, ld, T12, ld, h, r, h, 1.0, 0.0, 0, 1, 0};
-  GPB_TRY(gemm_launch(LAYOUT_COLK, LAYOUT_ROWK, g, s5));
+  if (oz) GPB_TRY(ozaki_gemm_launch(LAYOUT_COLK, LAYOUT_ROWK, g, 2, 0, 0, s5));
+  else GPB_TRY(gemm_launch(LAYOUT_COLK, LAYOUT_ROWK, g, s5));
   if (fork) GPB_CUDA(cudaEventRecord(f.ov->join[depth], s5));
   // A22 -= L21 * L21^T     (lower tiles)
   g = GemmArgs{S21, ld, S21, ld, A22, ld, r, r, h, -1.0, 1.0, 1, 0, 0};
-  GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
+  if (oz) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, 0, 0, 0, f.stream));
+  else GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
   GPB_TRY(cholinv(f, off + h, r, depth + 1));
   if (fork) GPB_CUDA(cudaStreamWaitEvent(f.stream, f.ov->join[depth], 0));
   // M21 = -M22 * T21       (M22 lower: k <= row tile; T21 read through its transpose T12, k-contiguous)
   g = GemmArgs{M22, ld, T12, ld, M21, ld, r, h, r, -1.0, 0.0, 0, 0, 1};
-  GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
+  if (oz) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, 1, 0, 0, f.stream));
+  else GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, f.stream));
   return 0;
 }
 
@@ -1067,6 +1074,7 @@ int factor_append(Factor &f, int h) {
 int factor_potri(Factor &f) {
   GPB_TRY(factor_finalize_L(f));   // W still holds the off-diagonal blocks of L
   GemmArgs g{f.Mi, f.np, f.Mi, f.np, f.W, f.np, f.np, f.np, f.np, 1.0, 0.0, 1, 1, 0};
+  if (ozaki_min_n() > 0 && f.np >= ozaki_min_n()) return ozaki_gemm_launch(LAYOUT_COLK, LAYOUT_COLK, g, 2, 2, 0, f.stream);
   return gemm_launch(LAYOUT_COLK, LAYOUT_COLK, g, f.stream);
 }
 

@@ -21,6 +21,9 @@
 // 128-byte swizzle, K-major.
 #include <cuda.h>
 
+#include <mutex>
+#include <vector>
+
 #include "gpb_common.cuh"
 
 namespace gpb {
@@ -410,7 +413,17 @@ struct Workspace {
   double *T = nullptr;
   size_t capT = 0;
 };
-static Workspace g_ws[64];
+// One workspace per (device, stream): models driven from several host threads (concurrent restarts) run on streams of their own.
+struct Slot { int dev; cudaStream_t st; Workspace *ws; };
+static std::mutex g_ws_mutex;
+static std::vector<Slot> g_slots;
+static Workspace *workspace_for(int dev, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (auto &s : g_slots)
+    if (s.dev == dev && s.st == st) return s.ws;
+  g_slots.push_back(Slot{dev, st, new Workspace()});
+  return g_slots.back().ws;
+}
 
 static int ensure(void **p, size_t *cap, size_t need) {
   if (*cap >= need) return 0;
@@ -453,8 +466,7 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   GPB_REQUIRE(S >= 1 && S <= MAX_S, "ozaki: bad digit count %d", S);
   int dev = 0;
   GPB_CUDA(cudaGetDevice(&dev));
-  GPB_REQUIRE(dev >= 0 && dev < 64, "ozaki: device ordinal");
-  Workspace &ws = g_ws[dev];
+  Workspace &ws = *workspace_for(dev, st);
   const bool same = (g.A == g.B && g.lda == g.ldb && layout_a == layout_b && tri_a == tri_b && g.M == g.N);
   GPB_TRY(ensure((void **)&ws.dA, &ws.capA, (size_t)S * g.M * g.K));
   if (!same) GPB_TRY(ensure((void **)&ws.dB, &ws.capB, (size_t)S * g.N * g.K));

@@ -1,0 +1,142 @@
+"""GPU parity of the experimental int8 tensor-core engine (csrc/gpb_ozaki.cu: tcgen05 kind::i8 products of 7-bit digits,
+recombined in fp64) -- as a GEMM against fp64 references, with the triangular k-ranges of the cholinv recursion, and as the
+engine of a whole NLL + gradient evaluation against the CPU oracle at north_star's tolerances (rtol 1e-9 log-likelihood,
+1e-7 gradients).  The engine is off by default; these tests switch it on explicitly."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+native = pytest.importorskip("gaussian_process_optimization_b200.native")
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 384, 640), (640, 1152, 256)])
+def test_ozaki_dgemm_layouts(ta, tb, m, n, k):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(m + 7 * n + 13 * k + ta + 2 * tb)
+    A = torch.randn((k, m) if ta else (m, k), generator=g, dtype=torch.float64)
+    B = torch.randn((k, n) if tb else (n, k), generator=g, dtype=torch.float64)
+    A[0] *= 1e6                     # rows / columns of very different magnitude: the scaling is per row of op(A), op(B)
+    B[-1] *= 1e-7
+    C = torch.randn((m, n), generator=g, dtype=torch.float64)
+    opA, opB = (A.T if ta else A), (B if tb else B.T)
+    ref = 1.5 * (opA @ opB) - 0.5 * C
+    bound = 1.5 * (opA.abs() @ opB.abs()) + 0.5 * C.abs()       # componentwise scale of a floating-point product
+    Cd = C.cuda()
+    native.ozaki_dgemm(ta, tb, 1.5, A.cuda(), B.cuda(), -0.5, Cd, slices=8)
+    torch.cuda.synchronize()
+    err = (Cd.cpu() - ref).abs()
+    # 8 digits of 7 bits relative to the row / column maxima: 2^-56 * k terms, i.e. norm-wise fp64 accuracy
+    rowmax = opA.abs().amax(dim=1, keepdim=True)
+    colmax = opB.abs().amax(dim=0, keepdim=True)
+    assert float((err / (k * rowmax * colmax * 2.0 ** -52 + 1e-15 * bound)).max()) < 1.0
+
+
+def test_ozaki_exact_on_integers():
+    """Small integers fit the first two digits exactly: the int8 products and their fp64 recombination are error free."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(5)
+    A = torch.randint(-8000, 8001, (256, 384), generator=g).double()
+    B = torch.randint(-8000, 8001, (512, 384), generator=g).double()
+    C = torch.zeros(256, 512, dtype=torch.float64, device="cuda")
+    native.ozaki_dgemm(0, 0, 1.0, A.cuda(), B.cuda(), 0.0, C, slices=3)
+    torch.cuda.synchronize()
+    assert torch.equal(C.cpu(), A @ B.T)
+
+
+def _block_lower(n, g, fill):
+    """Lower-triangular by 128-blocks (explicit zeros above the diagonal inside the diagonal blocks), `fill` in the blocks above."""
+    import torch
+    M = torch.randn(n, n, generator=g, dtype=torch.float64)
+    clean = torch.tril(M)
+    dirty = clean.clone()
+    for bi in range(n // 128):
+        dirty[bi * 128:(bi + 1) * 128, (bi + 1) * 128:] = fill
+    return clean, dirty
+
+
+def test_ozaki_triangular_products_of_the_recursion():
+    """The five products of cholinv / potri with their k-ranges; the 128-blocks above the diagonal of the triangular operands
+    hold NaN (scratch in the real recursion) and must never be read."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(11)
+    h, r = 512, 640
+    M11c, M11d = _block_lower(h, g, float("nan"))
+    M22c, M22d = _block_lower(r, g, float("nan"))
+    A21 = torch.randn(r, h, generator=g, dtype=torch.float64)
+    T12 = torch.randn(h, r, generator=g, dtype=torch.float64)
+    A22 = torch.randn(r, r, generator=g, dtype=torch.float64)
+
+    def run(ta, tb, alpha, A, B, beta, C, **kw):
+        Cd = C.cuda()
+        native.ozaki_dgemm(ta, tb, alpha, A.cuda(), B.cuda(), beta, Cd, slices=8, **kw)
+        torch.cuda.synchronize()
+        return Cd.cpu()
+
+    def close(got, ref, scale):
+        assert torch.isfinite(got).all()
+        assert float((got - ref).abs().max()) <= 1e-13 * float(scale)
+
+    # L21 = A21 M11^T  (k <= column block)
+    got = run(0, 0, 1.0, A21, M11d, 0.0, torch.zeros(r, h, dtype=torch.float64), khi_mode=2, tri_b=1)
+    close(got, A21 @ M11c.T, (A21.abs() @ M11c.abs().T).max())
+    # T12 = M11^T L21^T  (k >= row block)
+    got = run(1, 0, 1.0, M11d, A21, 0.0, torch.zeros(h, r, dtype=torch.float64), klo_mode=1, tri_a=2)
+    close(got, M11c.T @ A21.T, (M11c.abs().T @ A21.abs().T).max())
+    # A22 -= L21 L21^T  (lower tiles; the blocks above the diagonal stay untouched)
+    got = run(0, 0, -1.0, A21, A21, 1.0, A22.clone(), tri_out=1)
+    ref = A22 - A21 @ A21.T
+    for bi in range(r // 128):
+        sl = slice(bi * 128, (bi + 1) * 128)
+        close(got[sl, :(bi + 1) * 128], ref[sl, :(bi + 1) * 128], (A21.abs() @ A21.abs().T).max())
+        assert torch.equal(got[sl, (bi + 1) * 128:], A22[sl, (bi + 1) * 128:])
+    # M21 = -M22 T21  (k <= row block; T21 through its transpose)
+    got = run(0, 0, -1.0, M22d, T12, 0.0, torch.zeros(r, h, dtype=torch.float64), khi_mode=1, tri_a=1)
+    close(got, -M22c @ T12.T, (M22c.abs() @ T12.abs().T).max())
+    # W = M^T M  (lower tiles, k >= row block)
+    got = run(1, 1, 1.0, M22d, M22d, 0.0, torch.zeros(r, r, dtype=torch.float64), tri_out=1, klo_mode=1, tri_a=2, tri_b=2)
+    ref = M22c.T @ M22c
+    for bi in range(r // 128):
+        sl = slice(bi * 128, (bi + 1) * 128)
+        close(got[sl, :(bi + 1) * 128], ref[sl, :(bi + 1) * 128], (M22c.abs().T @ M22c.abs()).max())
+
+
+@pytest.fixture
+def ozaki_on():
+    native.set_ozaki(256, 8)
+    yield
+    native.set_ozaki(0, 8)
+
+
+@pytest.mark.parametrize("kind,noise,N,D", [("rbf", 1e-2, 1100, 5), ("mat52", 1e-6, 1500, 8), ("rbf", 1e-6, 900, 3)])
+def test_nll_and_gradients_through_the_int8_engine(ozaki_on, kind, noise, N, D):
+    """Every product of the factorisation with >= 256 rows on the int8 tensor cores: the evaluation still meets the parity bars
+    against the oracle (LAPACK), the ill-conditioned exact-evaluation noise level included."""
+    rs = np.random.RandomState(N)
+    X = rs.uniform(0, 1, (N, D))
+    Y = np.sin(X @ rs.randn(D))[:, None] + 0.05 * rs.randn(N, 1)
+    Y = (Y - Y.mean()) / Y.std()
+    ls = 0.5 + 0.5 * np.arange(D) / D
+    m = native.NativeModel(kind, True, D, 1, n_cap=N, cand_block=256)
+    m.set_data(X, Y)
+    m.set_theta(1.3, ls, noise)
+    before = native.launch_count()
+    info, logL, grads = m.fit(True)
+    assert info == 0 and native.launch_count() > before
+    l_ref, g_ref, _ = O.log_likelihood_and_gradients(kind, X, Y, 1.3, ls, noise)
+    Ky = O.K(kind, X, None, 1.3, ls) + (noise + 1e-8) * np.eye(N)
+    w = np.linalg.eigvalsh(Ky)
+    widen = max(1.0, w[-1] / w[0] * 2.2e-16 / 1e-12)              # same allowance as tests/test_gpu_native.py::_cond_tol
+    assert_allclose(logL, l_ref, rtol=1e-9 * widen)
+    assert_allclose(grads, g_ref, rtol=1e-7 * widen, atol=1e-7 * widen * np.abs(g_ref).max())
+    # the posterior the predictive calls use comes from the same factorisation
+    Xc = rs.uniform(0, 1, (64, D))
+    st = O.GPState(kind, X, Y, 1.3, ls, noise)
+    r = m.acquisition("EI", 0.01, m.fmin(), Xc, with_gradients=False)
+    f_ref = st.acquisition("EI", Xc, with_gradients=False)
+    assert_allclose(r["f"], f_ref, rtol=1e-6 * widen, atol=1e-9)
+    m.close()
