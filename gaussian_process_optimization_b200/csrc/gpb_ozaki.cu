@@ -3,22 +3,27 @@
 // gpb_set_ozaki): the default path of libgpb200 stays the fp64 DMMA engine of gpb_gemm.cu.
 //
 // Why: on sm_100a the fp64 tensor path is the warp-level DMMA (64 FMA/clk/SM = 37 TFLOP/s, shared with DFMA) -- tcgen05 has no
-// f64 kind -- while the int8 kind runs at ~4.5 POP/s.  Every fp64 operand is cut, row by row, into S signed 7-bit digits
-//     a_ik = 2^ea_i * sum_s A_s[i][k] 2^(-7 s),   |A_s| <= 127   (error-free: scaling by powers of two, trunc, subtract),
-// and the product is the sum over digit pairs of EXACT integer products
-//     C_ij = 2^(ea_i + eb_j) * sum_w 2^(-7 w) * sum_{s + t = w} (A_s B_t^T)_ij,       w = 2 .. S + 1  (pairs with s + t > S + 1
-// fall below the last digit and are dropped), S (S + 1) / 2 int8 products in all.  With S = 8 the result is as accurate as a
-// DGEMM (profiles/r1i_ozaki_numerics_study.json: log-likelihood and gradients of the whole evaluation to 1e-12).
+// f64 kind -- while the int8 kind runs at ~4.5 POP/s.  Every fp64 operand is cut, row by row, into S balanced radix-256 digits
+//     a_ik = 2^ea_i * sum_s A_s[i][k] 2^(1 - 8 s),   A_s in [-128, 127]
+// (error-free up to the rounding of the last digit: a_ik / 2^ea_i, |.| < 1/2, becomes the 64-bit integer q = rint(. 2^(8 S - 1)),
+// whose bytes are taken from the low end with carries), and the product is the sum over digit pairs of EXACT integer products
+//     C_ij = 2^(ea_i + eb_j) * sum_w 2^(2 - 8 w) * sum_{s + t = w} (A_s B_t^T)_ij,       w = 2 .. S + 1  (pairs with s + t > S + 1
+// fall below the last digit and are dropped; balanced digits make them zero-mean), S (S + 1) / 2 int8 products in all.
+// S = 7 (28 products, 53 bits relative to the largest entry of a row) keeps a whole NLL + gradient evaluation within 6e-11 /
+// 4e-10 of LAPACK at cond(Ky) ~ 1e8 and 1e-13 in ordinary cases; S = 8 is indistinguishable from the fp64 recursion
+// (scripts/ozaki_numerics_study.py -> profiles/r1i_ozaki_numerics_study.json).
 //
-// One kernel does the whole product for a 128 x 256 output tile: for each weight w (smallest first) the digit pairs s + t = w
-// are chained along k into ONE int32 accumulation in TMEM (at most 1024 k-blocks per accumulation: 127^2 * 128 * 1024 < 2^31),
-// drained by the epilogue warps into an fp64 running sum (read-modify-write of a tile that stays in L2) while the MMA warp
-// fills the second TMEM buffer with the next weight; the last drain applies the row / column scales, alpha and beta.
+// One kernel does the whole product for a 256 x 256 output tile: for each weight w (smallest first) the digit pairs s + t = w
+// are chained along k into ONE int32 accumulation in TMEM (two M = 128 accumulators = all 512 columns; at most 1023 k-blocks per
+// accumulation: 128^2 * 128 * 1023 < 2^31), drained by the epilogue warps into an fp64 running sum (read-modify-write of a tile
+// that stays in L2); the last drain applies the row / column scales, alpha and beta.  The 256 x 256 tile is what the operand
+// traffic asks for: with 128 x 256 tiles and a double-buffered accumulator the kernel was bound by the L2 -> shared-memory fill
+// (90 B/clk/SM; 16.0 ms for 8192^3 against 10.7 ms with the loads switched off, profiles/r1i_ozaki_products_perf.md).
 // Triangular operands are exploited as in gpb_gemm.cu (per-tile k-ranges at 128 granularity, lower tiles only).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
-// warps 2-5 = epilogue (TMEM lane quarter = warp % 4).  4-stage smem ring of {A digit tile 128 x 128 B, B digit tile 256 x 128 B},
-// 128-byte swizzle, K-major.
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
+// warps 2-9 = epilogue (TMEM lane quarter = warp % 4, accumulator = (warp - 2) / 4).  3-stage smem ring of {A digit tile
+// 256 x 128 B, B digit tile 256 x 128 B}, 128-byte swizzle, K-major.
 #include <cuda.h>
 
 #include <mutex>
@@ -29,14 +34,13 @@
 namespace gpb {
 
 namespace oz {
-constexpr int BM = 128, BN = 256, BKB = 128;   // output tile; bytes (= int8 elements) of k per stage
-constexpr int STAGES = 4;
+constexpr int BM = 256, BN = 256, BKB = 128;   // output tile of a CTA (two M = 128 accumulators); bytes (= int8 elements) of k per stage
+constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BKB, B_BYTES = BN * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int NTHREADS = 192;
-constexpr int GROUP_KB = 1024;                 // k-blocks per int32 accumulation: 127^2 * 128 * 1024 = 2.11e9 < 2^31
-constexpr int DIGIT_BITS = 7;
-constexpr int MAX_S = 12;
+constexpr int NTHREADS = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int GROUP_KB = 1023;                 // k-blocks per int32 accumulation: 128^2 * 128 * 1023 = 2.145e9 < 2^31
+constexpr int MAX_S = 8;                        // 8 S - 1 <= 63: the scaled operand must fit a 64-bit integer
 
 struct Params {
   int M, N, K, S;
@@ -46,6 +50,7 @@ struct Params {
   double *C; int ldc;
   double *T; int ldt;      // running sum (aliases C when beta == 0)
   int tiles_m, tiles_n;
+  int dbg;                 // measurement only: 1 = no TMA loads (MMA-bound rate), 2 = no epilogue memory traffic
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,40 +116,52 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 // kind::i8: D = s32 (bits 4-5 = 2), A = B = signed 8 bit (bits 7-9, 10-12 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
-  // ---- tile coordinates (longest k-ranges first) ----
+  // ---- tile coordinates ----
+  // CTAs start in blockIdx order, one per SM, and a tile's duration is proportional to its k-range (2 .. K / 128 blocks with the
+  // triangular modes): enumerate the tiles GLOBALLY longest first, so that the launch ends on its shortest tiles (the grouped
+  // order of the first version left a 64-block tile to start last: triangular products took 0.75 of a full one instead of 0.52).
   int tm, tn;
   {
-    constexpr int GROUP = 8;
     const int t = blockIdx.x;
-    const int in_group = GROUP * p.tiles_n;
-    const int gid = t / in_group, first = gid * GROUP;
-    const int gsz = min(p.tiles_m - first, GROUP);
-    const int r = t - gid * in_group;
-    tm = first + r % gsz;
-    tn = r / gsz;
-    if (p.khi_mode == 2) tn = p.tiles_n - 1 - tn;
-    if (p.khi_mode == 1) tm = p.tiles_m - 1 - tm;
+    if (p.khi_mode == 2) {                 // k <= column block: column by column from the right
+      tn = p.tiles_n - 1 - t / p.tiles_m;
+      tm = t % p.tiles_m;
+    } else if (p.khi_mode == 1) {          // k <= row block: row by row from the bottom
+      tm = p.tiles_m - 1 - t / p.tiles_n;
+      tn = t % p.tiles_n;
+    } else if (p.klo_mode == 1) {          // k >= row block: row by row from the top
+      tm = t / p.tiles_n;
+      tn = t % p.tiles_n;
+    } else {                               // equal lengths: groups of 4 tile rows share their B panels in L2
+      constexpr int GROUP = 4;
+      const int in_group = GROUP * p.tiles_n;
+      const int gid = t / in_group, first = gid * GROUP;
+      const int gsz = min(p.tiles_m - first, GROUP);
+      const int r = t - gid * in_group;
+      tm = first + r % gsz;
+      tn = r / gsz;
+    }
   }
   const int row0 = tm * BM, col0 = tn * BN;
-  if (p.tri_out && col0 > row0 + BM - 1) return;          // tile entirely above the diagonal
-  const int col_last = min(col0 + BN, p.N) - 128;          // first column of the last 128-block of the tile
+  const int row_last = min(row0 + BM, p.M) - 128;          // first row / column of the last 128-block of the tile
+  const int col_last = min(col0 + BN, p.N) - 128;
+  if (p.tri_out && col0 > row_last + 127) return;          // tile entirely above the diagonal
   int klo = (p.klo_mode == 1) ? row0 : (p.klo_mode == 2) ? col0 : 0;
-  int khi = (p.khi_mode == 1) ? row0 + 128 : (p.khi_mode == 2) ? col_last + 128 : p.K;
+  int khi = (p.khi_mode == 1) ? row_last + 128 : (p.khi_mode == 2) ? col_last + 128 : p.K;
   if (khi > p.K) khi = p.K;
   const int kb0 = klo / BKB, nkb = (khi - klo) / BKB;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + STAGES * STAGE_BYTES;       // full[STAGES], empty[STAGES], tfull[2], tempty[2], tmem slot
+  const uint32_t bars = base + STAGES * STAGE_BYTES;       // full[STAGES], empty[STAGES], tfull, tempty, tmem slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  const uint32_t tfull_bar = bars + 8u * (2 * STAGES), tempty_bar = bars + 8u * (2 * STAGES + 1);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2);
   volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,10 +170,8 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
-    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, NTHREADS / 32 - 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -179,68 +194,77 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int t = w - s;
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-            const uint32_t dst = base + stage * STAGE_BYTES;
-            tma_load_3d(dst, &mapA, (kb0 + kb) * BKB, row0, s - 1, full_bar(stage));
-            tma_load_3d(dst + A_BYTES, &mapB, (kb0 + kb) * BKB, col0, t - 1, full_bar(stage));
+            if (p.dbg == 1) {
+              mbar_arrive(full_bar(stage));
+            } else {
+              mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+              const uint32_t dst = base + stage * STAGE_BYTES;
+              tma_load_3d(dst, &mapA, (kb0 + kb) * BKB, row0, s - 1, full_bar(stage));
+              tma_load_3d(dst + A_BYTES, &mapB, (kb0 + kb) * BKB, col0, t - 1, full_bar(stage));
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issue =====
+    // ===== MMA issue: two M = 128 accumulators (rows 0-127 -> TMEM columns 0-255, rows 128-255 -> columns 256-511) =====
     if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase[2] = {0, 0};
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
       for (int w = p.S + 1; w >= 2; --w) {
         const int npairs = min(p.S, w - 1) - max(1, w - p.S) + 1;
         const int total = npairs * nkb;
         for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
           const int g1 = min(total, g0 + GROUP_KB);
-          mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1);
+          mbar_wait(tempty_bar, acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int idx = g0; idx < g1; ++idx) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t a_addr = base + stage * STAGE_BYTES, b_addr = a_addr + A_BYTES;
             const uint64_t ad = smem_desc(a_addr), bd = smem_desc(b_addr);
 #pragma unroll
-            for (int k = 0; k < BKB / 32; ++k) umma_i8(d_tmem, ad + 2 * k, bd + 2 * k, IDESC, (idx > g0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BKB / 32; ++k) {
+              const uint32_t accum = (idx > g0 || k > 0) ? 1u : 0u;
+              umma_i8(tmem_base, ad + 2 * k, bd + 2 * k, IDESC, accum);
+              umma_i8(tmem_base + BN, ad + (128 * BKB / 16) + 2 * k, bd + 2 * k, IDESC, accum);
+            }
             umma_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(tfull_bar(acc));
-          acc_phase[acc] ^= 1;
-          acc ^= 1;
+          umma_commit(tfull_bar);
+          acc_phase ^= 1;
         }
       }
     }
   } else {
-    // ===== epilogue: TMEM -> fp64 running sum (global, L2 resident) -> final scaling =====
+    // ===== epilogue (8 warps): TMEM -> fp64 running sum (global, L2 resident) -> final scaling =====
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
-    const int row = row0 + q * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase[2] = {0, 0};
+    const int half = (warp - 2) >> 2;                     // which accumulator (row half of the tile)
+    const int row = row0 + half * 128 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    uint32_t acc_phase = 0;
     bool first = true;
-    double *Trow = p.T + (size_t)row * p.ldt + col0;
-    double *Crow = p.C + (size_t)row * p.ldc + col0;
-    const double ra = p.alpha * p.ra[row];
+    double *Trow = p.T + (size_t)(row_ok ? row : 0) * p.ldt + col0;
+    double *Crow = p.C + (size_t)(row_ok ? row : 0) * p.ldc + col0;
+    const double ra = row_ok ? p.alpha * p.ra[row] : 0.0;
     int ncols = min(BN, p.N - col0);
-    if (p.tri_out) ncols = min(ncols, row0 + BM - col0);    // 128-blocks above the diagonal are left untouched
+    if (p.tri_out) ncols = min(ncols, row0 + half * 128 + 128 - col0);   // 128-blocks above the diagonal are left untouched
+    if (!row_ok) ncols = 0;
     for (int w = p.S + 1; w >= 2; --w) {
       const int npairs = min(p.S, w - 1) - max(1, w - p.S) + 1;
       const int total = npairs * nkb;
-      const double sc = exp2((double)(-DIGIT_BITS * w));
+      const double sc = exp2((double)(2 - 8 * w));
       for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
         const bool last = (w == 2) && (g0 + GROUP_KB >= total);
-        mbar_wait(tfull_bar(acc), acc_phase[acc]);
+        mbar_wait(tfull_bar, acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BN);
         for (int c0 = 0; c0 < ncols; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c0, v);
+          if (p.dbg == 2 && !last) continue;
           if (!last) {
             if (first) {
 #pragma unroll
@@ -274,9 +298,8 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        acc_phase[acc] ^= 1;
-        acc ^= 1;
+        if (lane == 0) mbar_arrive(tempty_bar);
+        acc_phase ^= 1;
         first = false;
       }
     }
@@ -350,23 +373,23 @@ oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int
   __syncthreads();
   const double am = __longlong_as_double((long long)amax[i0 + r]);
   int e = 0;
-  if (am > 0.0 && am < 1e308) frexp(am, &e);            // am = f 2^e, f in [0.5, 1): |x| 2^-e < 1
-  const double inv = ldexp(1.0, -e);
+  if (am > 0.0 && am < 1e308) frexp(am, &e);            // am = f 2^e, f in [0.5, 1)
+  e += 1;                                               // |x| 2^-e < 1/2: the leading digit stays within [-64, 64] + carry
   if (seg == 0) scale[i0 + r] = ldexp(1.0, e);          // every valid sub-block of the row writes the same value
-  double x[16];
+  const double up = ldexp(1.0, 8 * S - 1 - e);          // x -> q = rint(x 2^-e 2^(8 S - 1)), |q| < 2^(8 S - 2) <= 2^62
+  long long q[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = sm[r][seg + j] * inv;
-  for (int s = 0; s < S; ++s) {
+  for (int j = 0; j < 16; ++j) q[j] = __double2ll_rn(sm[r][seg + j] * up);
+  for (int s = S - 1; s >= 0; --s) {                    // low byte first; balanced: d in [-128, 127], carry into the next byte
     uint32_t wds[4];
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
       uint32_t wv = 0;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        double &v = x[q4 * 4 + b];
-        v *= 128.0;
-        const double d = trunc(v);
-        v -= d;
+        long long &v = q[q4 * 4 + b];
+        const long long d = (s == 0) ? v : (((v + 128) & 255) - 128);
+        v = (v - d) >> 8;
         wv |= ((uint32_t)(int)d & 0xFFu) << (8 * b);
       }
       wds[q4] = wv;
@@ -435,7 +458,7 @@ static int ensure(void **p, size_t *cap, size_t need) {
   return 0;
 }
 
-static int g_slices = 8;
+static int g_slices = 7;
 static int g_min_n = -1;   // -1: read GPB_OZAKI_MIN_N once; 0: off
 
 }  // namespace oz
@@ -511,7 +534,10 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   p.alpha = g.alpha; p.beta = g.beta;
   p.ra = ws.ra; p.rb = same ? ws.ra : ws.rb;
   p.C = g.C; p.ldc = g.ldc; p.T = T; p.ldt = ldt;
-  p.tiles_m = g.M / BM; p.tiles_n = (g.N + BN - 1) / BN;
+  p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + BN - 1) / BN;
+  static int dbg = -1;
+  if (dbg < 0) { const char *e = getenv("GPB_OZAKI_DBG"); dbg = e ? atoi(e) : 0; }
+  p.dbg = dbg;
   static unsigned long long configured = 0;
   if (needs_func_config(configured))
     GPB_CUDA(cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

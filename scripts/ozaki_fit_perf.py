@@ -12,8 +12,9 @@ sys.path.insert(0, ".")
 from bench import synth  # noqa: E402
 from gaussian_process_optimization_b200 import native  # noqa: E402
 
+SLICES = int(os.environ.get("OZAKI_SLICES", "7"))
 sizes = [int(a) for a in sys.argv[1:]] or [4096, 8192, 16384]
-out = {}
+out = {"slices": SLICES}
 for N in sizes:
     D = 16
     X, Y, ls = synth(N, D)
@@ -22,7 +23,7 @@ for N in sizes:
     res = {}
     base = None
     for min_n in [0] + [t for t in (1024, 2048, 4096, 8192, 16384) if t <= N]:
-        native.set_ozaki(min_n, 8)
+        native.set_ozaki(min_n, SLICES)
         ts = []
         for i in range(4):
             m.set_theta(1.0, ls, 1e-2)
@@ -36,7 +37,7 @@ for N in sizes:
         res["min_n_%d" % min_n] = {"ms": min(ts[1:]) * 1e3, "info": int(info), "logL_rel_vs_dmma": abs(logL - base[0]) / abs(base[0]),
                                    "grad_rel_vs_dmma": float(np.max(np.abs(g - base[1])) / np.max(np.abs(base[1])))}
         print(N, min_n, res["min_n_%d" % min_n], flush=True)
-    native.set_ozaki(0, 8)
+    native.set_ozaki(0, SLICES)
     out["N%d" % N] = res
     m.close()
 os.makedirs("gpurun_out", exist_ok=True)

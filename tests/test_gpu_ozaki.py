@@ -1,4 +1,4 @@
-"""GPU parity of the experimental int8 tensor-core engine (csrc/gpb_ozaki.cu: tcgen05 kind::i8 products of 7-bit digits,
+"""GPU parity of the experimental int8 tensor-core engine (csrc/gpb_ozaki.cu: tcgen05 kind::i8 products of balanced radix-256 digits,
 recombined in fp64) -- as a GEMM against fp64 references, with the triangular k-ranges of the cholinv recursion, and as the
 engine of a whole NLL + gradient evaluation against the CPU oracle at north_star's tolerances (rtol 1e-9 log-likelihood,
 1e-7 gradients).  The engine is off by default; these tests switch it on explicitly."""
@@ -30,7 +30,7 @@ def test_ozaki_dgemm_layouts(ta, tb, m, n, k):
     native.ozaki_dgemm(ta, tb, 1.5, A.cuda(), B.cuda(), -0.5, Cd, slices=8)
     torch.cuda.synchronize()
     err = (Cd.cpu() - ref).abs()
-    # 8 digits of 7 bits relative to the row / column maxima: 2^-56 * k terms, i.e. norm-wise fp64 accuracy
+    # 8 balanced radix-256 digits: 2^-61 relative to the row / column maxima per term, i.e. norm-wise fp64 accuracy
     rowmax = opA.abs().amax(dim=1, keepdim=True)
     colmax = opB.abs().amax(dim=0, keepdim=True)
     assert float((err / (k * rowmax * colmax * 2.0 ** -52 + 1e-15 * bound)).max()) < 1.0
@@ -107,9 +107,9 @@ def test_ozaki_triangular_products_of_the_recursion():
 
 @pytest.fixture
 def ozaki_on():
-    native.set_ozaki(256, 8)
+    native.set_ozaki(256, 7)
     yield
-    native.set_ozaki(0, 8)
+    native.set_ozaki(0, 7)
 
 
 @pytest.mark.parametrize("kind,noise,N,D", [("rbf", 1e-2, 1100, 5), ("mat52", 1e-6, 1500, 8), ("rbf", 1e-6, 900, 3)])
