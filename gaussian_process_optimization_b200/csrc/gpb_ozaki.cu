@@ -38,6 +38,7 @@ constexpr int BM = 256, BN = 256, BKB = 128;   // output tile of a CTA (two M = 
 constexpr int STAGES = 3;
 constexpr int A_BYTES = BM * BKB, B_BYTES = BN * BKB, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int PREFETCH = 6;                     // k-blocks of L2 prefetch distance in the TMA producer
 constexpr int NTHREADS = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int GROUP_KB = 1023;                 // k-blocks per int32 accumulation: 128^2 * 128 * 1023 = 2.145e9 < 2^31
 constexpr int MAX_S = 8;                        // 8 S - 1 <= 63: the scaled operand must fit a 64-bit integer
@@ -48,7 +49,8 @@ struct Params {
   double alpha, beta;
   const double *ra, *rb;   // 2^ea_i (M), 2^eb_j (N)
   double *C; int ldc;
-  double *T; int ldt;      // running sum (aliases C when beta == 0)
+  uint4 *P; size_t plane;  // int32 parking space of the drains, in uint4: [drain][tile][epilogue warp 8][chunk 8][j 8][lane 32] --
+                           // every warp store / load is one contiguous 512-byte line (the owner lane reads back what it wrote)
   int tiles_m, tiles_n;
   int dbg;                 // measurement only: 1 = no TMA loads (MMA-bound rate), 2 = no epilogue memory traffic
 };
@@ -85,6 +87,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -201,6 +206,11 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               const uint32_t dst = base + stage * STAGE_BYTES;
               tma_load_3d(dst, &mapA, (kb0 + kb) * BKB, row0, s - 1, full_bar(stage));
               tma_load_3d(dst + A_BYTES, &mapB, (kb0 + kb) * BKB, col0, t - 1, full_bar(stage));
+              // pull the tiles PREFETCH k-blocks ahead into L2: the 3-stage ring alone cannot cover a DRAM miss
+              if (kb + PREFETCH < nkb) {
+                tma_prefetch_3d(&mapA, (kb0 + kb + PREFETCH) * BKB, row0, s - 1);
+                tma_prefetch_3d(&mapB, (kb0 + kb + PREFETCH) * BKB, col0, t - 1);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -245,48 +255,65 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int row = row0 + half * 128 + q * 32 + lane;
     const bool row_ok = row < p.M;
     uint32_t acc_phase = 0;
-    bool first = true;
-    double *Trow = p.T + (size_t)(row_ok ? row : 0) * p.ldt + col0;
+    int drain = 0;
+    uint4 *Pw = p.P + ((size_t)(tm * p.tiles_n + tn) * 8 + (warp - 2)) * (8 * 8 * 32) + lane;
     double *Crow = p.C + (size_t)(row_ok ? row : 0) * p.ldc + col0;
     const double ra = row_ok ? p.alpha * p.ra[row] : 0.0;
     int ncols = min(BN, p.N - col0);
     if (p.tri_out) ncols = min(ncols, row0 + half * 128 + 128 - col0);   // 128-blocks above the diagonal are left untouched
     if (!row_ok) ncols = 0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BN);
     for (int w = p.S + 1; w >= 2; --w) {
       const int npairs = min(p.S, w - 1) - max(1, w - p.S) + 1;
       const int total = npairs * nkb;
-      const double sc = exp2((double)(2 - 8 * w));
       for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
         const bool last = (w == 2) && (g0 + GROUP_KB >= total);
         mbar_wait(tfull_bar, acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BN);
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c0, v);
-          if (p.dbg == 2 && !last) continue;
-          if (!last) {
-            if (first) {
+        if (!last) {
+          // park the exact int32 sums of this drain (write only; the combination happens once, below)
+          uint4 *dst = Pw + (size_t)drain * p.plane;
+          for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            if (p.dbg == 2) continue;
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                double2 o = make_double2(sc * (double)(int)v[j], sc * (double)(int)v[j + 1]);
-                *reinterpret_cast<double2 *>(Trow + c0 + j) = o;
-              }
-            } else {
+            for (int j = 0; j < 32; j += 4) dst[(c0 + j) * 8] = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);   // ((c0/32)*8 + j/4)*32
+          }
+        } else {
+          // C = alpha 2^(ea + eb) sum_drains 2^(2 - 8 w) P + beta C, smallest terms first
+          for (int c0 = 0; c0 < ncols; c0 += 32) {
+            double acc[32];
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                double2 o = *reinterpret_cast<double2 *>(Trow + c0 + j);
-                o.x = fma(sc, (double)(int)v[j], o.x);
-                o.y = fma(sc, (double)(int)v[j + 1], o.y);
-                *reinterpret_cast<double2 *>(Trow + c0 + j) = o;
+            for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+            int d = 0;
+            for (int w2 = p.S + 1; w2 >= 2; --w2) {
+              const int np2 = min(p.S, w2 - 1) - max(1, w2 - p.S) + 1;
+              const int tot2 = np2 * nkb;
+              const double sc = exp2((double)(2 - 8 * w2));
+              for (int h0 = 0; h0 < tot2; h0 += GROUP_KB) {
+                if (w2 == 2 && h0 + GROUP_KB >= tot2) break;       // the drain still in TMEM
+                const uint4 *src = Pw + (size_t)d * p.plane;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const uint4 uu = src[(c0 + j) * 8];
+                  const int4 u = make_int4((int)uu.x, (int)uu.y, (int)uu.z, (int)uu.w);
+                  acc[j] = fma(sc, (double)u.x, acc[j]);
+                  acc[j + 1] = fma(sc, (double)u.y, acc[j + 1]);
+                  acc[j + 2] = fma(sc, (double)u.z, acc[j + 2]);
+                  acc[j + 3] = fma(sc, (double)u.w, acc[j + 3]);
+                }
+                ++d;
               }
             }
-          } else {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
+            const double sc = exp2((double)(2 - 8 * 2));
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              double2 o = first ? make_double2(0.0, 0.0) : *reinterpret_cast<double2 *>(Trow + c0 + j);
-              o.x = fma(sc, (double)(int)v[j], o.x) * (ra * p.rb[col0 + c0 + j]);
-              o.y = fma(sc, (double)(int)v[j + 1], o.y) * (ra * p.rb[col0 + c0 + j + 1]);
+              double2 o;
+              o.x = fma(sc, (double)(int)v[j], acc[j]) * (ra * p.rb[col0 + c0 + j]);
+              o.y = fma(sc, (double)(int)v[j + 1], acc[j + 1]) * (ra * p.rb[col0 + c0 + j + 1]);
               if (p.beta != 0.0) {
                 const double2 c = *reinterpret_cast<double2 *>(Crow + c0 + j);
                 o.x = fma(p.beta, c.x, o.x);
@@ -300,7 +327,7 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar);
         acc_phase ^= 1;
-        first = false;
+        ++drain;
       }
     }
   }
@@ -433,7 +460,7 @@ struct Workspace {
   double *ra = nullptr, *rb = nullptr;
   unsigned long long *amax = nullptr;   // [0, cap) for A, [cap, 2 cap) for B
   size_t cap_rows = 0;
-  double *T = nullptr;
+  void *T = nullptr;                    // int32 planes of the drains
   size_t capT = 0;
 };
 // One workspace per (device, stream): models driven from several host threads (concurrent restarts) run on streams of their own.
@@ -502,13 +529,14 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
     GPB_CUDA(cudaMalloc((void **)&ws.amax, 2 * rows * sizeof(unsigned long long)));
     ws.cap_rows = rows;
   }
-  double *T = g.C;
-  int ldt = g.ldc;
-  if (g.beta != 0.0) {
-    GPB_TRY(ensure((void **)&ws.T, &ws.capT, (size_t)g.M * g.N * sizeof(double)));
-    T = ws.T;
-    ldt = g.N;
+  // int32 planes for every drain but the last: drains of weight w = ceil(pairs(w) * (K / 128) / GROUP_KB) at most
+  int drains = 0;
+  for (int w = S + 1; w >= 2; --w) {
+    const int npairs = (S < w - 1 ? S : w - 1) - (1 > w - S ? 1 : w - S) + 1;
+    drains += (npairs * (g.K / BKB) + GROUP_KB - 1) / GROUP_KB;
   }
+  const size_t plane = (size_t)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * (BM * BN / 4);   // uint4 per drain
+  GPB_TRY(ensure((void **)&ws.T, &ws.capT, (size_t)(drains > 1 ? drains - 1 : 1) * plane * sizeof(uint4)));
   GPB_CUDA(cudaMemsetAsync(ws.amax, 0, 2 * ws.cap_rows * sizeof(unsigned long long), st));
   auto split = [&](int layout, const double *P, int ld, int R, int tri, unsigned long long *amax, int8_t *dig, double *scale) -> int {
     dim3 g1(R / 128, g.K / 128), g2(R / 64, g.K / 64);
@@ -533,7 +561,7 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   p.tri_out = g.tri_out; p.klo_mode = g.klo_mode; p.khi_mode = g.khi_mode;
   p.alpha = g.alpha; p.beta = g.beta;
   p.ra = ws.ra; p.rb = same ? ws.ra : ws.rb;
-  p.C = g.C; p.ldc = g.ldc; p.T = T; p.ldt = ldt;
+  p.C = g.C; p.ldc = g.ldc; p.P = (uint4 *)ws.T; p.plane = plane;
   p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + BN - 1) / BN;
   static int dbg = -1;
   if (dbg < 0) { const char *e = getenv("GPB_OZAKI_DBG"); dbg = e ? atoi(e) : 0; }
