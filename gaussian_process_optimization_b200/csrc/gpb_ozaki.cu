@@ -111,8 +111,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO = 64 x 16 B), descriptor
 // version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  The tile base is 1024-byte aligned; a k-step of 32 bytes inside the
@@ -273,16 +273,22 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (!last) {
           // park the exact int32 sums of this drain (write only; the combination happens once, below)
           uint4 *dst = Pw + (size_t)drain * p.plane;
-          for (int c0 = 0; c0 < ncols; c0 += 32) {
-            uint32_t v[32];
+          for (int c0 = 0; c0 < ncols; c0 += 64) {             // ncols is a multiple of 128; two loads in flight per wait
+            uint32_t v[32], v2[32];
             tmem_ld32(taddr + c0, v);
+            tmem_ld32(taddr + c0 + 32, v2);
+            tmem_ld_wait();
             if (p.dbg == 2) continue;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) dst[(c0 + j) * 8] = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);   // ((c0/32)*8 + j/4)*32
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) dst[(c0 + 32 + j) * 8] = make_uint4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
           }
         } else {
           // C = alpha 2^(ea + eb) sum_drains 2^(2 - 8 w) P + beta C, smallest terms first
           for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);                            // in flight under the plane reads below
             double acc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = 0.0;
@@ -306,8 +312,7 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 ++d;
               }
             }
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
+            tmem_ld_wait();
             const double sc = exp2((double)(2 - 8 * 2));
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
