@@ -361,6 +361,12 @@ def bench_int8_engine(args, model, theta, dmma_s_per_eval, dgemm_peak_tflops):
     v, l, nz = theta(3)
     model.set_theta(v, l, nz)
     info0, logL0, g0 = model.fit(True)
+    # the EI value + gradient pass of config 4 on one shard, both engines on the same fitted hyper-parameters
+    chunk = np.random.RandomState(4321).uniform(0, 1, (2 ** 15, DIM))
+    shard = torch.from_numpy(np.ascontiguousarray(chunk)).cuda()
+    fmin0 = model.fmin()
+    vals0, idx0, pts0, f0, df0 = model.acq_topk_full("EI", 0.01, fmin0, shard, 5)
+    f0, df0 = f0.cpu().numpy().copy(), df0.cpu().numpy().copy()
     native.set_ozaki(MIN_N, SLICES)
     try:
         for i in range(2):
@@ -378,6 +384,23 @@ def bench_int8_engine(args, model, theta, dmma_s_per_eval, dgemm_peak_tflops):
         e1.record()
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) * 1e-3 / args.steps
+        model.set_theta(v, l, nz)
+        model.fit(True)
+        fmin1 = model.fmin()
+        model.acq_topk_full("EI", 0.01, fmin1, shard[:4096], 5)            # warm-up: cuts the digit planes of L^-1 once
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        vals1, idx1, pts1, f1, df1 = model.acq_topk_full("EI", 0.01, fmin1, shard, 5)
+        c1.record()
+        torch.cuda.synchronize()
+        t_acq = c0.elapsed_time(c1) * 1e-3
+        acq = {"metric": "ei_value_gradient_candidates_per_s", "value": shard.shape[0] / t_acq, "unit": "candidates/s",
+               "candidates": int(shard.shape[0]), "seconds": t_acq,
+               "algorithmic_tflops_fp64_equivalent": (2.0 * N_TRAIN ** 2 + N_TRAIN * (6 * DIM + 40)) * shard.shape[0] / t_acq / 1e12,
+               "agreement_with_dmma_engine": {"same_top5": bool(list(idx0) == list(idx1)),
+                                              "f_rel_to_max": float(np.max(np.abs(f1.cpu().numpy() - f0)) / np.max(np.abs(f0))),
+                                              "df_rel_to_max": float(np.max(np.abs(df1.cpu().numpy() - df0)) / np.max(np.abs(df0)))}}
         # the engine alone on a square product, and the library int8 GEMM of the same shape as its roofline
         n = 8192
         A = torch.randn(n, n, dtype=torch.float64, device="cuda")
@@ -420,6 +443,7 @@ def bench_int8_engine(args, model, theta, dmma_s_per_eval, dgemm_peak_tflops):
                        "products_on_the_engine": "the four products of the two top recursion levels and Ky^-1 = M^T M; everything below stays on DMMA"},
             "agreement_with_dmma_engine": {"logL_rel": abs(logL1 - logL0) / abs(logL0),
                                            "grad_rel_to_max": float(np.max(np.abs(g1 - g0)) / np.max(np.abs(g0))), "info": int(info1)},
+            "aux": acq,
             "roofline": {"bound": "tensor (int8, tcgen05 kind::i8)", "kernel": "ozaki_mma_kernel on an 8192^3 fp64-equivalent product (digit extraction included)",
                          "ms": best * 1e3, "effective_fp64_tflops": 2.0 * n ** 3 / best / 1e12, "achieved": int8_tops, "peak": lib_tops,
                          "unit": "TOP/s", "frac": int8_tops / lib_tops, "rel_err_vs_fp64_matmul": gemm_err,

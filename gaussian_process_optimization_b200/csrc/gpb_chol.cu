@@ -1048,6 +1048,7 @@ static int trtri_rec(Factor &f, int off, int n) {
 int factor_trtri(Factor &f) {
   GPB_REQUIRE(f.np % TILE == 0 && f.np >= TILE, "factor: padded size must be a multiple of 128");
   GPB_CUDA(cudaMemsetAsync(f.info, 0, sizeof(int), f.stream));
+  ozaki_invalidate();
   return trtri_rec(f, 0, f.np);
 }
 
@@ -1056,6 +1057,7 @@ int factor_potrf_inv(Factor &f) {
   GPB_CUDA(cudaMemsetAsync(f.info, 0, sizeof(int), f.stream));
   f.l_pending = true;
   f.l_from = 0;
+  ozaki_invalidate();
   return cholinv(f, 0, f.np, 0);
 }
 
@@ -1067,6 +1069,7 @@ int factor_append(Factor &f, int h) {
   GPB_CUDA(cudaMemsetAsync(f.info, 0, sizeof(int), f.stream));
   f.l_pending = true;
   f.l_from = h / TILE;
+  ozaki_invalidate();
   return cholinv(f, 0, f.np, 0, h);
 }
 

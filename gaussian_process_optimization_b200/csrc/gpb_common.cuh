@@ -219,7 +219,8 @@ int gemm_profile_collect(double *ms, double *flops, long long *launches);
 int gemm_profile_last(double *ms, double *flops);
 
 // int8 tensor-core (tcgen05) Ozaki engine for the large products (gpb_ozaki.cu); experimental, off unless configured
-int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, int tri_b, int slices, cudaStream_t s);
+int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, int tri_b, int slices, cudaStream_t s, int cache_b = 0);
+void ozaki_invalidate();                     // a factorisation ran: cached digit planes of L^-1 are stale
 int ozaki_min_n();                           // products of the recursion with n >= this go through the engine (0 = off)
 int ozaki_configure(int min_n, int slices);
 

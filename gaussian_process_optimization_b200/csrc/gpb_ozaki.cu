@@ -26,6 +26,7 @@
 // 256 x 128 B, B digit tile 256 x 128 B}, 128-byte swizzle, K-major.
 #include <cuda.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -138,6 +139,9 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     } else if (p.khi_mode == 1) {          // k <= row block: row by row from the bottom
       tm = p.tiles_m - 1 - t / p.tiles_n;
       tn = t % p.tiles_n;
+    } else if (p.klo_mode == 2) {          // k >= column block: column by column from the left
+      tn = t / p.tiles_m;
+      tm = t % p.tiles_m;
     } else if (p.klo_mode == 1) {          // k >= row block: row by row from the top
       tm = t / p.tiles_n;
       tn = t % p.tiles_n;
@@ -467,7 +471,15 @@ struct Workspace {
   size_t cap_rows = 0;
   void *T = nullptr;                    // int32 planes of the drains
   size_t capT = 0;
+  // digit planes of a B operand kept across calls (the predictive products multiply every candidate block with the same L^-1)
+  struct Cached {
+    int8_t *dig = nullptr; size_t cap = 0;
+    double *scale = nullptr; size_t cap_scale = 0;
+    const double *ptr = nullptr; int ld = 0, layout = 0, tri = 0, R = 0, K = 0, S = 0;
+    unsigned long long epoch = 0;
+  } cache[2];
 };
+static std::atomic<unsigned long long> g_epoch{1};
 // One workspace per (device, stream): models driven from several host threads (concurrent restarts) run on streams of their own.
 struct Slot { int dev; cudaStream_t st; Workspace *ws; };
 static std::mutex g_ws_mutex;
@@ -513,7 +525,11 @@ int ozaki_configure(int min_n, int slices) {
 
 // C = alpha op(A) op(B)^T + beta C through the int8 tensor cores.  Same argument meaning as gemm_launch (gpb_gemm.cu); tri_a /
 // tri_b: validity pattern of the stored operand (see oz_split_kernel).  M, N, K multiples of 128.
-int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, int tri_b, int slices, cudaStream_t st) {
+void ozaki_invalidate() { oz::g_epoch.fetch_add(1, std::memory_order_relaxed); }
+
+// cache_b = 1 or 2: keep the digit planes of B in that slot and reuse them while (pointer, shape, layout) match and no
+// factorisation has run since (ozaki_invalidate()).
+int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, int tri_b, int slices, cudaStream_t st, int cache_b) {
   using namespace oz;
   const int S = slices > 0 ? slices : g_slices;
   GPB_REQUIRE(g.M % 128 == 0 && g.N % 128 == 0 && g.K % 128 == 0 && g.M > 0 && g.N > 0 && g.K > 0, "ozaki: sizes must be multiples of 128");
@@ -524,7 +540,8 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   Workspace &ws = *workspace_for(dev, st);
   const bool same = (g.A == g.B && g.lda == g.ldb && layout_a == layout_b && tri_a == tri_b && g.M == g.N);
   GPB_TRY(ensure((void **)&ws.dA, &ws.capA, (size_t)S * g.M * g.K));
-  if (!same) GPB_TRY(ensure((void **)&ws.dB, &ws.capB, (size_t)S * g.N * g.K));
+  GPB_REQUIRE(cache_b >= 0 && cache_b <= 2 && !(cache_b && same), "ozaki: bad operand cache slot");
+  if (!same && !cache_b) GPB_TRY(ensure((void **)&ws.dB, &ws.capB, (size_t)S * g.N * g.K));
   const size_t rows = (size_t)(g.M > g.N ? g.M : g.N);
   if (ws.cap_rows < rows) {
     if (ws.ra) { GPB_CUDA(cudaFree(ws.ra)); GPB_CUDA(cudaFree(ws.rb)); GPB_CUDA(cudaFree(ws.amax)); }
@@ -557,15 +574,33 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
     return 0;
   };
   GPB_TRY(split(layout_a, g.A, g.lda, g.M, tri_a, ws.amax, ws.dA, ws.ra));
-  if (!same) GPB_TRY(split(layout_b, g.B, g.ldb, g.N, tri_b, ws.amax + ws.cap_rows, ws.dB, ws.rb));
+  const int8_t *digB = same ? ws.dA : ws.dB;
+  const double *scaleB = same ? ws.ra : ws.rb;
+  if (cache_b) {
+    Workspace::Cached &c = ws.cache[cache_b - 1];
+    const unsigned long long epoch = g_epoch.load(std::memory_order_relaxed);
+    const bool hit = c.ptr == g.B && c.ld == g.ldb && c.layout == layout_b && c.tri == tri_b && c.R == g.N && c.K == g.K && c.S == S &&
+                     c.epoch == epoch;
+    if (!hit) {
+      c.ptr = nullptr;
+      GPB_TRY(ensure((void **)&c.dig, &c.cap, (size_t)S * g.N * g.K));
+      GPB_TRY(ensure((void **)&c.scale, &c.cap_scale, (size_t)g.N * sizeof(double)));
+      GPB_TRY(split(layout_b, g.B, g.ldb, g.N, tri_b, ws.amax + ws.cap_rows, c.dig, c.scale));
+      c.ptr = g.B; c.ld = g.ldb; c.layout = layout_b; c.tri = tri_b; c.R = g.N; c.K = g.K; c.S = S; c.epoch = epoch;
+    }
+    digB = c.dig;
+    scaleB = c.scale;
+  } else if (!same) {
+    GPB_TRY(split(layout_b, g.B, g.ldb, g.N, tri_b, ws.amax + ws.cap_rows, ws.dB, ws.rb));
+  }
   CUtensorMap mapA, mapB;
   GPB_TRY(make_map(&mapA, ws.dA, g.M, g.K, S, BM));
-  GPB_TRY(make_map(&mapB, same ? ws.dA : ws.dB, g.N, g.K, S, BN));
+  GPB_TRY(make_map(&mapB, digB, g.N, g.K, S, BN));
   Params p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.S = S;
   p.tri_out = g.tri_out; p.klo_mode = g.klo_mode; p.khi_mode = g.khi_mode;
   p.alpha = g.alpha; p.beta = g.beta;
-  p.ra = ws.ra; p.rb = same ? ws.ra : ws.rb;
+  p.ra = ws.ra; p.rb = scaleB;
   p.C = g.C; p.ldc = g.ldc; p.P = (uint4 *)ws.T; p.plane = plane;
   p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + BN - 1) / BN;
   static int dbg = -1;

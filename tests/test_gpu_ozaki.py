@@ -121,7 +121,7 @@ def test_nll_and_gradients_through_the_int8_engine(ozaki_on, kind, noise, N, D):
     Y = np.sin(X @ rs.randn(D))[:, None] + 0.05 * rs.randn(N, 1)
     Y = (Y - Y.mean()) / Y.std()
     ls = 0.5 + 0.5 * np.arange(D) / D
-    m = native.NativeModel(kind, True, D, 1, n_cap=N, cand_block=256)
+    m = native.NativeModel(kind, True, D, 1, n_cap=N, cand_block=1024)
     m.set_data(X, Y)
     m.set_theta(1.3, ls, noise)
     before = native.launch_count()
@@ -133,10 +133,19 @@ def test_nll_and_gradients_through_the_int8_engine(ozaki_on, kind, noise, N, D):
     widen = max(1.0, w[-1] / w[0] * 2.2e-16 / 1e-12)              # same allowance as tests/test_gpu_native.py::_cond_tol
     assert_allclose(logL, l_ref, rtol=1e-9 * widen)
     assert_allclose(grads, g_ref, rtol=1e-7 * widen, atol=1e-7 * widen * np.abs(g_ref).max())
-    # the posterior the predictive calls use comes from the same factorisation
-    Xc = rs.uniform(0, 1, (64, D))
+    # the predictive products of a full candidate block (1024 rows) run on the engine too, against digit planes of L^-1 that are
+    # cut once and reused by the second block; a refit must invalidate them
+    Xc = rs.uniform(0, 1, (1024 + 300, D))
     st = O.GPState(kind, X, Y, 1.3, ls, noise)
-    r = m.acquisition("EI", 0.01, m.fmin(), Xc, with_gradients=False)
-    f_ref = st.acquisition("EI", Xc, with_gradients=False)
+    r = m.acquisition("EI", 0.01, m.fmin(), Xc, with_gradients=True)
+    f_ref, df_ref = st.acquisition("EI", Xc, with_gradients=True)
     assert_allclose(r["f"], f_ref, rtol=1e-6 * widen, atol=1e-9)
+    assert_allclose(r["df"], df_ref, rtol=1e-5 * widen, atol=1e-8 * widen * np.abs(df_ref).max())
+    m.set_theta(0.9, ls * 1.1, noise)
+    assert m.fit(True)[0] == 0
+    st2 = O.GPState(kind, X, Y, 0.9, ls * 1.1, noise)
+    r2 = m.acquisition("LCB", 2.0, m.fmin(), Xc[:1024], with_gradients=True)
+    f2, df2 = st2.acquisition("LCB", Xc[:1024], with_gradients=True)
+    assert_allclose(r2["f"], f2, rtol=1e-6 * widen, atol=1e-9)
+    assert_allclose(r2["df"], df2, rtol=1e-5 * widen, atol=1e-8 * widen * np.abs(df2).max())
     m.close()
