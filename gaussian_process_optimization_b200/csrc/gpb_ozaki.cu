@@ -113,6 +113,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO = 64 x 16 B), descriptor
@@ -289,40 +296,76 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int j = 0; j < 32; j += 4) dst[(c0 + 32 + j) * 8] = make_uint4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]);
           }
         } else {
-          // C = alpha 2^(ea + eb) sum_drains 2^(2 - 8 w) P + beta C, smallest terms first
-          for (int c0 = 0; c0 < ncols; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);                            // in flight under the plane reads below
-            double acc[32];
+          // C = alpha 2^(ea + eb) sum_drains 2^(2 - 8 w) P + beta C, smallest terms first.  The parked planes are read back with
+          // all planes of 16 columns in flight at once (the combination is a chain of L2 round trips otherwise).
+          constexpr int MAXP = 6;
+          double scd[MAXP];
+          int nd = 0;
+          bool fast = true;
+          for (int w2 = p.S + 1; w2 >= 2; --w2) {
+            const int np2 = min(p.S, w2 - 1) - max(1, w2 - p.S) + 1;
+            const int tot2 = np2 * nkb;
+            for (int h0 = 0; h0 < tot2; h0 += GROUP_KB) {
+              if (w2 == 2 && h0 + GROUP_KB >= tot2) break;         // the drain still in TMEM
+              if (nd < MAXP) scd[nd] = exp2((double)(2 - 8 * w2));
+              else fast = false;
+              ++nd;
+            }
+          }
+          const double sc_last = exp2((double)(2 - 8 * 2));
+          for (int c0 = 0; c0 < ncols; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);                            // in flight under the plane reads below
+            double acc[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-            int d = 0;
-            for (int w2 = p.S + 1; w2 >= 2; --w2) {
-              const int np2 = min(p.S, w2 - 1) - max(1, w2 - p.S) + 1;
-              const int tot2 = np2 * nkb;
-              const double sc = exp2((double)(2 - 8 * w2));
-              for (int h0 = 0; h0 < tot2; h0 += GROUP_KB) {
-                if (w2 == 2 && h0 + GROUP_KB >= tot2) break;       // the drain still in TMEM
-                const uint4 *src = Pw + (size_t)d * p.plane;
+            for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+            if (fast) {
+              uint4 u[MAXP][4];                                  // up to 6 planes x 16 columns in flight
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const uint4 uu = src[(c0 + j) * 8];
-                  const int4 u = make_int4((int)uu.x, (int)uu.y, (int)uu.z, (int)uu.w);
-                  acc[j] = fma(sc, (double)u.x, acc[j]);
-                  acc[j + 1] = fma(sc, (double)u.y, acc[j + 1]);
-                  acc[j + 2] = fma(sc, (double)u.z, acc[j + 2]);
-                  acc[j + 3] = fma(sc, (double)u.w, acc[j + 3]);
+              for (int d = 0; d < MAXP; ++d)
+                if (d < nd) {
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) u[d][j4] = (Pw + (size_t)d * p.plane)[(c0 + 4 * j4) * 8];
                 }
-                ++d;
+#pragma unroll
+              for (int d = 0; d < MAXP; ++d)
+                if (d < nd) {
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) {
+                    const int j = 4 * j4;
+                    acc[j] = fma(scd[d], (double)(int)u[d][j4].x, acc[j]);
+                    acc[j + 1] = fma(scd[d], (double)(int)u[d][j4].y, acc[j + 1]);
+                    acc[j + 2] = fma(scd[d], (double)(int)u[d][j4].z, acc[j + 2]);
+                    acc[j + 3] = fma(scd[d], (double)(int)u[d][j4].w, acc[j + 3]);
+                  }
+                }
+            } else {
+              int d = 0;
+              for (int w2 = p.S + 1; w2 >= 2; --w2) {
+                const int np2 = min(p.S, w2 - 1) - max(1, w2 - p.S) + 1;
+                const int tot2 = np2 * nkb;
+                const double sc = exp2((double)(2 - 8 * w2));
+                for (int h0 = 0; h0 < tot2; h0 += GROUP_KB) {
+                  if (w2 == 2 && h0 + GROUP_KB >= tot2) break;
+                  const uint4 *src = Pw + (size_t)d * p.plane;
+#pragma unroll
+                  for (int j = 0; j < 16; j += 4) {
+                    const uint4 uu = src[(c0 + j) * 8];
+                    acc[j] = fma(sc, (double)(int)uu.x, acc[j]);
+                    acc[j + 1] = fma(sc, (double)(int)uu.y, acc[j + 1]);
+                    acc[j + 2] = fma(sc, (double)(int)uu.z, acc[j + 2]);
+                    acc[j + 3] = fma(sc, (double)(int)uu.w, acc[j + 3]);
+                  }
+                  ++d;
+                }
               }
             }
             tmem_ld_wait();
-            const double sc = exp2((double)(2 - 8 * 2));
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
+            for (int j = 0; j < 16; j += 2) {
               double2 o;
-              o.x = fma(sc, (double)(int)v[j], acc[j]) * (ra * p.rb[col0 + c0 + j]);
-              o.y = fma(sc, (double)(int)v[j + 1], acc[j + 1]) * (ra * p.rb[col0 + c0 + j + 1]);
+              o.x = fma(sc_last, (double)(int)v[j], acc[j]) * (ra * p.rb[col0 + c0 + j]);
+              o.y = fma(sc_last, (double)(int)v[j + 1], acc[j + 1]) * (ra * p.rb[col0 + c0 + j + 1]);
               if (p.beta != 0.0) {
                 const double2 c = *reinterpret_cast<double2 *>(Crow + c0 + j);
                 o.x = fma(p.beta, c.x, o.x);
