@@ -829,6 +829,9 @@ int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) 
 // level 0: mean only; 1: + variance; 2: + gradients (dmu, dvar); 3: mean and its gradient only (estimate_L)
 // The two triangular products of a candidate block go through the int8 engine when it is switched on, the model is large enough
 // and the block has enough rows to fill 256-row tiles.
+// 8 digits here, not 7: the predictive variance sigma^2 - sum (M k*)^2 cancels, and the digit scheme is accurate relative to the
+// largest entry of a row of M, not entry by entry (with 7 digits LCB values of an ill-conditioned RBF model moved by 4e-10).
+constexpr int OZAKI_PREDICT_DIGITS = 8;
 static inline bool ozaki_predict(int np, int cpad) { return ozaki_min_n() > 0 && np >= ozaki_min_n() && cpad >= 1024; }
 
 static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int level, int include_likelihood) {
@@ -880,7 +883,7 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
     // Vt = KxT M^T  (== (L^-1 Kx)^T: dtrtrs of posterior.py:293 as a product with the explicit inverse factor)
     GemmArgs g{m->KxT, np, m->f.Mi, np, m->Vt, np, cpad, np, np, 1.0, 0.0, 0, 0, 2};
     // experimental int8 engine (gpb_ozaki.cu) for big candidate blocks; the digit planes of L^-1 are cut once per factorisation
-    if (ozaki_predict(np, cpad)) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, 0, 1, 0, s, 1));
+    if (ozaki_predict(np, cpad)) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, 0, 1, OZAKI_PREDICT_DIGITS, s, 1));
     else GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, s));
     // var = Kdiag - sum(tmp^2) (+ noise)                            posterior.py:294-295, gaussian.py:109
     GPB_TRY(launch_var_from_vt(m->Vt, np, mcb, n, m->variance + (include_likelihood ? m->noise : 0.0), m->var, s));
@@ -890,7 +893,7 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
     // Ut = Vt M = (Ky^-1 Kx)^T                                      core/gp.py:450-451 (woodbury_inv product as 2nd triangular product)
     if (!skinny) {
       GemmArgs g{m->Vt, np, m->f.Mi, np, m->Ut, np, cpad, np, np, 1.0, 0.0, 0, 2, 0};
-      if (ozaki_predict(np, cpad)) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, 0, 2, 0, s, 2));
+      if (ozaki_predict(np, cpad)) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, 0, 2, OZAKI_PREDICT_DIGITS, s, 2));
       else GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, s));
     }
     // dmu = gradients_X(alpha^T, X*, X); dvar = gradients_X(-2 Kx^T Wi, X*, X)     core/gp.py:431-434,450-453

@@ -53,6 +53,7 @@ struct Params {
   uint4 *P; size_t plane;  // int32 parking space of the drains, in uint4: [drain][tile][epilogue warp 8][chunk 8][j 8][lane 32] --
                            // every warp store / load is one contiguous 512-byte line (the owner lane reads back what it wrote)
   int tiles_m, tiles_n;
+  int cl, share_a;         // CTA pairs (cluster of 2) that share one operand tile by TMA multicast: A (pair along n) or B (pair along m)
   int dbg;                 // measurement only: 1 = no TMA loads (MMA-bound rate), 2 = no epilogue memory traffic
 };
 
@@ -88,6 +89,19 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -132,40 +146,55 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p) {
+ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapH,
+                 const Params p) {
   // ---- tile coordinates ----
   // CTAs start in blockIdx order, one per SM, and a tile's duration is proportional to its k-range (2 .. K / 128 blocks with the
   // triangular modes): enumerate the tiles GLOBALLY longest first, so that the launch ends on its shortest tiles (the grouped
   // order of the first version left a 64-block tile to start last: triangular products took 0.75 of a full one instead of 0.52).
+  // CTA pairs (p.cl == 2, a cluster of two consecutive CTAs): two tiles with the same k-range -- neighbours along n when the range
+  // depends on the row (they share the A tile), along m when it depends on the column (they share the B tile).  Each CTA fetches
+  // half of the shared tile and multicasts it into both shared memories: 48 KB instead of 64 KB of L2 reads per CTA and step.
   int tm, tn;
+  const int rank = (p.cl == 2) ? (int)(blockIdx.x & 1) : 0;
   {
-    const int t = blockIdx.x;
+    const int t = (p.cl == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int gm = (p.cl == 2 && !p.share_a) ? p.tiles_m / 2 : p.tiles_m;   // grid of tiles (or of tile pairs)
+    const int gn = (p.cl == 2 && p.share_a) ? p.tiles_n / 2 : p.tiles_n;
     if (p.khi_mode == 2) {                 // k <= column block: column by column from the right
-      tn = p.tiles_n - 1 - t / p.tiles_m;
-      tm = t % p.tiles_m;
+      tn = gn - 1 - t / gm;
+      tm = t % gm;
     } else if (p.khi_mode == 1) {          // k <= row block: row by row from the bottom
-      tm = p.tiles_m - 1 - t / p.tiles_n;
-      tn = t % p.tiles_n;
+      tm = gm - 1 - t / gn;
+      tn = t % gn;
     } else if (p.klo_mode == 2) {          // k >= column block: column by column from the left
-      tn = t / p.tiles_m;
-      tm = t % p.tiles_m;
+      tn = t / gm;
+      tm = t % gm;
     } else if (p.klo_mode == 1) {          // k >= row block: row by row from the top
-      tm = t / p.tiles_n;
-      tn = t % p.tiles_n;
+      tm = t / gn;
+      tn = t % gn;
     } else {                               // equal lengths: groups of 4 tile rows share their B panels in L2
       constexpr int GROUP = 4;
-      const int in_group = GROUP * p.tiles_n;
+      const int in_group = GROUP * gn;
       const int gid = t / in_group, first = gid * GROUP;
-      const int gsz = min(p.tiles_m - first, GROUP);
+      const int gsz = min(gm - first, GROUP);
       const int r = t - gid * in_group;
       tm = first + r % gsz;
       tn = r / gsz;
+    }
+    if (p.cl == 2) {
+      if (p.share_a) tn = 2 * tn + rank;
+      else tm = 2 * tm + rank;
     }
   }
   const int row0 = tm * BM, col0 = tn * BN;
   const int row_last = min(row0 + BM, p.M) - 128;          // first row / column of the last 128-block of the tile
   const int col_last = min(col0 + BN, p.N) - 128;
   if (p.tri_out && col0 > row_last + 127) return;          // tile entirely above the diagonal
+  // pair mode: is the partner tile active?  (lower-tile outputs always pair along n: the partner is the other column tile)
+  bool dual = p.cl == 2;
+  if (dual && p.tri_out) dual = ((tn ^ 1) * BN <= row_last + 127);
+  const uint16_t pair_mask = 3;
   int klo = (p.klo_mode == 1) ? row0 : (p.klo_mode == 2) ? col0 : 0;
   int khi = (p.khi_mode == 1) ? row_last + 128 : (p.khi_mode == 2) ? col_last + 128 : p.K;
   if (khi > p.K) khi = p.K;
@@ -184,7 +213,7 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), dual ? 2 : 1);               // pair mode: a stage is free when BOTH MMA warps are done with it
     }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, NTHREADS / 32 - 2);
@@ -196,6 +225,7 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (dual) cluster_sync_all();                            // the partner's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -215,8 +245,16 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             } else {
               mbar_expect_tx(full_bar(stage), STAGE_BYTES);
               const uint32_t dst = base + stage * STAGE_BYTES;
-              tma_load_3d(dst, &mapA, (kb0 + kb) * BKB, row0, s - 1, full_bar(stage));
-              tma_load_3d(dst + A_BYTES, &mapB, (kb0 + kb) * BKB, col0, t - 1, full_bar(stage));
+              if (!dual) {
+                tma_load_3d(dst, &mapA, (kb0 + kb) * BKB, row0, s - 1, full_bar(stage));
+                tma_load_3d(dst + A_BYTES, &mapB, (kb0 + kb) * BKB, col0, t - 1, full_bar(stage));
+              } else if (p.share_a) {      // own B tile; half of the common A tile to both CTAs
+                tma_load_3d(dst + A_BYTES, &mapB, (kb0 + kb) * BKB, col0, t - 1, full_bar(stage));
+                tma_load_3d_mc(dst + rank * (A_BYTES / 2), &mapH, (kb0 + kb) * BKB, row0 + rank * 128, s - 1, full_bar(stage), pair_mask);
+              } else {                     // own A tile; half of the common B tile to both CTAs
+                tma_load_3d(dst, &mapA, (kb0 + kb) * BKB, row0, s - 1, full_bar(stage));
+                tma_load_3d_mc(dst + A_BYTES + rank * (B_BYTES / 2), &mapH, (kb0 + kb) * BKB, col0 + rank * 128, t - 1, full_bar(stage), pair_mask);
+              }
               // pull the tiles PREFETCH k-blocks ahead into L2: the 3-stage ring alone cannot cover a DRAM miss
               if (kb + PREFETCH < nkb) {
                 tma_prefetch_3d(&mapA, (kb0 + kb + PREFETCH) * BKB, row0, s - 1);
@@ -251,7 +289,8 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               umma_i8(tmem_base, ad + 2 * k, bd + 2 * k, IDESC, accum);
               umma_i8(tmem_base + BN, ad + (128 * BKB / 16) + 2 * k, bd + 2 * k, IDESC, accum);
             }
-            umma_commit(empty_bar(stage));
+            if (dual) umma_commit_mc(empty_bar(stage), pair_mask);
+            else umma_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           umma_commit(tfull_bar);
@@ -385,6 +424,7 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (dual) cluster_sync_all();                            // nobody leaves while the partner may still write into this CTA
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -545,7 +585,7 @@ static int ensure(void **p, size_t *cap, size_t need) {
   return 0;
 }
 
-static int g_slices = 7;
+static int g_slices = 8;   // 8 digits: indistinguishable from the fp64 engine in every parity test; 7 is 25% faster
 static int g_min_n = -1;   // -1: read GPB_OZAKI_MIN_N once; 0: off
 
 }  // namespace oz
@@ -636,23 +676,46 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   } else if (!same) {
     GPB_TRY(split(layout_b, g.B, g.ldb, g.N, tri_b, ws.amax + ws.cap_rows, ws.dB, ws.rb));
   }
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA, mapB, mapH;
   GPB_TRY(make_map(&mapA, ws.dA, g.M, g.K, S, BM));
   GPB_TRY(make_map(&mapB, digB, g.N, g.K, S, BN));
+  // CTA pairs: the k-range must be common to the pair -> along n (shared A) unless it depends on the column (shared B)
+  static int use_pairs = -1;
+  if (use_pairs < 0) { const char *e = getenv("GPB_OZAKI_PAIRS"); use_pairs = e ? atoi(e) : 1; }
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.N + BN - 1) / BN;
+  const int share_a = (g.khi_mode == 2 || g.klo_mode == 2) ? 0 : 1;
+  const int cl = (use_pairs && (share_a ? tiles_n % 2 == 0 : tiles_m % 2 == 0) && !(g.tri_out && !share_a)) ? 2 : 1;
+  if (share_a) GPB_TRY(make_map(&mapH, ws.dA, g.M, g.K, S, 128));
+  else GPB_TRY(make_map(&mapH, digB, g.N, g.K, S, 128));
   Params p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.S = S;
   p.tri_out = g.tri_out; p.klo_mode = g.klo_mode; p.khi_mode = g.khi_mode;
   p.alpha = g.alpha; p.beta = g.beta;
   p.ra = ws.ra; p.rb = scaleB;
   p.C = g.C; p.ldc = g.ldc; p.P = (uint4 *)ws.T; p.plane = plane;
-  p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + BN - 1) / BN;
+  p.tiles_m = tiles_m; p.tiles_n = tiles_n;
+  p.cl = cl; p.share_a = share_a;
   static int dbg = -1;
   if (dbg < 0) { const char *e = getenv("GPB_OZAKI_DBG"); dbg = e ? atoi(e) : 0; }
   p.dbg = dbg;
   static unsigned long long configured = 0;
   if (needs_func_config(configured))
     GPB_CUDA(cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  ozaki_mma_kernel<<<p.tiles_m * p.tiles_n, NTHREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.tiles_m * p.tiles_n);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GPB_CUDA(cudaLaunchKernelEx(&cfg, ozaki_mma_kernel, mapA, mapB, mapH, p));
+  }
   count_launch();
   GPB_CHECK_LAUNCH();
   return 0;

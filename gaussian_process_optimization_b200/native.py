@@ -181,7 +181,7 @@ def ozaki_dgemm(ta, tb, alpha, A, B, beta, C, slices=0, tri_out=0, klo_mode=0, k
     return C
 
 
-def set_ozaki(min_n, slices=7):
+def set_ozaki(min_n, slices=8):
     """Experimental: products of the factorisation with >= min_n rows go through the int8 engine (0 = off, the default)."""
     check(_lib.load().gpb_set_ozaki(int(min_n), int(slices)), "set_ozaki")
 
