@@ -15,11 +15,15 @@
 //
 // One kernel does the whole product for a 256 x 256 output tile: for each weight w (smallest first) the digit pairs s + t = w
 // are chained along k into ONE int32 accumulation in TMEM (two M = 128 accumulators = all 512 columns; at most 1023 k-blocks per
-// accumulation: 128^2 * 128 * 1023 < 2^31), drained by the epilogue warps into an fp64 running sum (read-modify-write of a tile
-// that stays in L2); the last drain applies the row / column scales, alpha and beta.  The 256 x 256 tile is what the operand
+// accumulation: 128^2 * 128 * 1023 < 2^31), drained by the epilogue warps: every drain but the last
+// parks its exact int32 sums in a private coalesced scratch plane, the last one combines them in fp64 (smallest terms first) and
+// applies the row / column scales, alpha and beta.  The 256 x 256 tile is what the operand
 // traffic asks for: with 128 x 256 tiles and a double-buffered accumulator the kernel was bound by the L2 -> shared-memory fill
 // (90 B/clk/SM; 16.0 ms for 8192^3 against 10.7 ms with the loads switched off, profiles/r1i_ozaki_products_perf.md).
 // Triangular operands are exploited as in gpb_gemm.cu (per-tile k-ranges at 128 granularity, lower tiles only).
+//
+// CTA pairs (cluster of 2): two tiles with a common k-range fetch half of the shared operand tile each and multicast it into both
+// shared memories; the MMA warps release a stage in both CTAs (tcgen05.commit ... multicast::cluster).
 //
 // Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
 // warps 2-9 = epilogue (TMEM lane quarter = warp % 4, accumulator = (warp - 2) / 4).  3-stage smem ring of {A digit tile
