@@ -468,17 +468,18 @@ __global__ void __launch_bounds__(256) oz_absmax_kernel(const double *__restrict
   }
 }
 
-// One CTA per 64 (i) x 64 (k) sub-block: stage through shared memory, then every thread cuts 16 consecutive k of one row into S
-// digits and stores them as one 16-byte vector per digit plane.  digits: [S][R][K] int8, k contiguous.
+// One CTA per 32 (i) x 128 (k) sub-block: stage through shared memory, then every thread cuts 16 consecutive k of one row into S
+// digits and stores them as one 16-byte vector per digit plane (the 8 threads of a row write one full 128-byte line per plane).
+// digits: [S][R][K] int8, k contiguous.
 template <int LAYOUT>
 __global__ void __launch_bounds__(256)
 oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int S, const unsigned long long *__restrict__ amax,
                 int8_t *__restrict__ digits, double *__restrict__ scale) {
-  __shared__ double sm[64][65];
-  const int i0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  __shared__ double sm[32][129];
+  const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 128;
   const int tid = threadIdx.x;
   const bool valid = block_valid(tri, i0 >> 7, k0 >> 7);
-  const int r = tid >> 2, seg = (tid & 3) * 16;
+  const int r = tid >> 3, seg = (tid & 7) * 16;
   const size_t plane = (size_t)R * K;
   int8_t *out = digits + (size_t)(i0 + r) * K + k0 + seg;
   if (!valid) {
@@ -487,11 +488,13 @@ oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int
     return;
   }
   if (LAYOUT == LAYOUT_ROWK) {
-    const int c = tid & 63, rr0 = tid >> 6;
-    for (int rr = rr0; rr < 64; rr += 4) sm[rr][c] = P[(size_t)(i0 + rr) * ld + k0 + c];
+    const int c = tid & 127, rr0 = tid >> 7;
+#pragma unroll 4
+    for (int rr = rr0; rr < 32; rr += 2) sm[rr][c] = P[(size_t)(i0 + rr) * ld + k0 + c];
   } else {
-    const int c = tid & 63, kk0 = tid >> 6;
-    for (int kk = kk0; kk < 64; kk += 4) sm[c][kk] = P[(size_t)(k0 + kk) * ld + i0 + c];
+    const int c = tid & 31, kk0 = tid >> 5;
+#pragma unroll 4
+    for (int kk = kk0; kk < 128; kk += 8) sm[c][kk] = P[(size_t)(k0 + kk) * ld + i0 + c];
   }
   __syncthreads();
   const double am = __longlong_as_double((long long)amax[i0 + r]);
@@ -648,7 +651,7 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   GPB_TRY(ensure((void **)&ws.T, &ws.capT, (size_t)(drains > 1 ? drains - 1 : 1) * plane * sizeof(uint4)));
   GPB_CUDA(cudaMemsetAsync(ws.amax, 0, 2 * ws.cap_rows * sizeof(unsigned long long), st));
   auto split = [&](int layout, const double *P, int ld, int R, int tri, unsigned long long *amax, int8_t *dig, double *scale) -> int {
-    dim3 g1(R / 128, g.K / 128), g2(R / 64, g.K / 64);
+    dim3 g1(R / 128, g.K / 128), g2(R / 32, g.K / 128);
     if (layout == LAYOUT_ROWK) {
       oz_absmax_kernel<LAYOUT_ROWK><<<g1, 256, 0, st>>>(P, ld, tri, amax);
       oz_split_kernel<LAYOUT_ROWK><<<g2, 256, 0, st>>>(P, ld, R, g.K, tri, S, amax, dig, scale);

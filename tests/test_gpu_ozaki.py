@@ -48,6 +48,30 @@ def test_ozaki_exact_on_integers():
     assert torch.equal(C.cpu(), A @ B.T)
 
 
+@pytest.mark.parametrize("slices", [7, 8])
+def test_ozaki_long_k_needs_several_int32_accumulations(slices):
+    """k = 19200 = 150 k-blocks: the weights with 7 or 8 digit pairs exceed the 1023 k-blocks one int32 accumulation may hold
+    (128^2 * 128 * 1023 < 2^31), so they drain in two groups (the N = 32768 end state of BASELINE config 5 needs this)."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(3)
+    m, n, k = 256, 384, 19200
+    A = torch.randn(m, k, generator=g, dtype=torch.float64)
+    B = torch.randn(n, k, generator=g, dtype=torch.float64)
+    A[:, ::3] = A[:, ::3].abs()          # biased signs: the int32 sums actually grow with k
+    B[:, ::3] = B[:, ::3].abs()
+    C = torch.zeros(m, n, dtype=torch.float64, device="cuda")
+    native.ozaki_dgemm(0, 0, 1.0, A.cuda(), B.cuda(), 0.0, C, slices=slices)
+    torch.cuda.synchronize()
+    ref = A @ B.T
+    assert float((C.cpu() - ref).abs().max() / ref.abs().max()) < (1e-13 if slices == 8 else 2e-12)
+    # worst case for the accumulators: every digit at its extreme value
+    A = torch.full((m, k), -1.0, dtype=torch.float64)
+    B = torch.full((n, k), -1.0, dtype=torch.float64)
+    native.ozaki_dgemm(0, 0, 1.0, A.cuda(), B.cuda(), 0.0, C, slices=slices)
+    torch.cuda.synchronize()
+    assert torch.equal(C.cpu(), torch.full((m, n), float(k), dtype=torch.float64))
+
+
 def _block_lower(n, g, fill):
     """Lower-triangular by 128-blocks (explicit zeros above the diagonal inside the diagonal blocks), `fill` in the blocks above."""
     import torch
