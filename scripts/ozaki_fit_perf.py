@@ -22,7 +22,8 @@ for N in sizes:
     m.set_data(torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda())
     res = {}
     base = None
-    for min_n in [0] + [t for t in (1024, 2048, 4096, 8192, 16384) if t <= N]:
+    mins = [int(t) for t in os.environ.get("OZAKI_MIN_LIST", "1024,2048,4096,8192,16384").split(",")]
+    for min_n in [0] + [t for t in mins if t <= N]:
         native.set_ozaki(min_n, SLICES)
         ts = []
         for i in range(4):
