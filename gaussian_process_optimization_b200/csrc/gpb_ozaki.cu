@@ -19,7 +19,7 @@
 // parks its exact int32 sums in a private coalesced scratch plane, the last one combines them in fp64 (smallest terms first) and
 // applies the row / column scales, alpha and beta.  The 256 x 256 tile is what the operand
 // traffic asks for: with 128 x 256 tiles and a double-buffered accumulator the kernel was bound by the L2 -> shared-memory fill
-// (90 B/clk/SM; 16.0 ms for 8192^3 against 10.7 ms with the loads switched off, profiles/r1i_ozaki_products_perf.md).
+// (90 B/clk/SM; 16.0 ms for 8192^3 against 10.7 ms with the loads switched off; DESIGN.md section 3, "What bounds it").
 // Triangular operands are exploited as in gpb_gemm.cu (per-tile k-ranges at 128 granularity, lower tiles only).
 //
 // CTA pairs (cluster of 2): two tiles with a common k-range fetch half of the shared operand tile each and multicast it into both
