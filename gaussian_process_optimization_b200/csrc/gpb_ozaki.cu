@@ -58,7 +58,7 @@ struct Params {
                            // every warp store / load is one contiguous 512-byte line (the owner lane reads back what it wrote)
   int tiles_m, tiles_n;
   int cl, share_a;         // CTA pairs (cluster of 2) that share one operand tile by TMA multicast: A (pair along n) or B (pair along m)
-  int dbg;                 // measurement only: 1 = no TMA loads (MMA-bound rate), 2 = no epilogue memory traffic
+  int dbg;                 // measurement only: 1 = no TMA loads (MMA-bound rate), 2 = no epilogue memory traffic, 3 = no drains but the last (wrong results)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -280,8 +280,11 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const int total = npairs * nkb;
         for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
           const int g1 = min(total, g0 + GROUP_KB);
-          mbar_wait(tempty_bar, acc_phase ^ 1);
-          tc_fence_after();
+          const bool skip_drain = p.dbg == 3 && !((w == 2) && (g0 + GROUP_KB >= total));   // measurement only: no hand-over
+          if (!(p.dbg == 3 && (w != p.S + 1 || g0 != 0))) {
+            mbar_wait(tempty_bar, acc_phase ^ 1);
+            tc_fence_after();
+          }
           for (int idx = g0; idx < g1; ++idx) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -297,8 +300,10 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             else umma_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(tfull_bar);
-          acc_phase ^= 1;
+          if (!skip_drain) {
+            umma_commit(tfull_bar);
+            acc_phase ^= 1;
+          }
         }
       }
     }
@@ -322,6 +327,7 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int total = npairs * nkb;
       for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
         const bool last = (w == 2) && (g0 + GROUP_KB >= total);
+        if (p.dbg == 3 && !last) { ++drain; continue; }
         mbar_wait(tfull_bar, acc_phase);
         tc_fence_after();
         if (!last) {
