@@ -16,6 +16,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from oracle import gp_oracle as O  # noqa: E402
+from oracle import ozaki_emulation as E  # noqa: E402
 
 BITS = 7
 TILE = 128
@@ -35,39 +36,9 @@ def split_rows(A, S):
     return digits, e
 
 
-def split_rows_balanced(A, S):
-    """Radix-256 balanced digits in [-128, 127] (all signed int8): x / 2^(e + 1) = sum_s d_s 2^(1 - 8 s), |d_1| <= 65; the integer
-    q = rint(x' 2^(8 S - 1)) is cut from the low byte up with carries -- what csrc/gpb_ozaki.cu does with 64-bit integers."""
-    amax = np.maximum(np.abs(A).max(axis=1, keepdims=True), 1e-300)
-    e = np.ceil(np.log2(amax))
-    e = np.where(np.exp2(e) <= amax, e + 1, e) + 1          # |x'| < 0.5
-    F = 8 * S - 1
-    q = np.rint(A * np.exp2(-e) * 2.0 ** F)                  # exact scaling; |q| < 2^(F-1) <= 2^62
-    q = q.astype(np.int64)
-    digits = [None] * S
-    for s in range(S, 1, -1):
-        d = ((q + 128) & 255) - 128
-        digits[s - 1] = d.astype(np.float64)
-        q = (q - d) >> 8
-    digits[0] = q.astype(np.float64)
-    assert np.abs(digits[0]).max() <= 65
-    return digits, e
-
-
 def make_gemm_balanced(S):
-    def gemm_nt(A, B):
-        Da, ea = split_rows_balanced(A, S)
-        Db, eb = split_rows_balanced(B, S)
-        C = np.zeros((A.shape[0], B.shape[0]))
-        for w in range(S + 1, 1, -1):
-            acc = np.zeros_like(C)
-            for s in range(1, w):
-                t = w - s
-                if s <= S and t <= S:
-                    acc += Da[s - 1] @ Db[t - 1].T
-            C += acc * 2.0 ** (2 - 8 * w)
-        return C * np.exp2(ea) * np.exp2(eb).T
-    return gemm_nt
+    """The scheme of csrc/gpb_ozaki.cu: balanced radix-256 digits (oracle/ozaki_emulation.py)."""
+    return lambda A, B: E.gemm_nt(A, B, S)
 
 
 def make_gemm(S):
