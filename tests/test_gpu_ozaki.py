@@ -36,6 +36,29 @@ def test_ozaki_dgemm_layouts(ta, tb, m, n, k):
     assert float((err / (k * rowmax * colmax * 2.0 ** -52 + 1e-15 * bound)).max()) < 1.0
 
 
+@pytest.mark.parametrize("slices", [5, 7, 8])
+def test_ozaki_device_equals_the_numpy_emulation_bitwise(slices):
+    """Every step of the engine is exact integer arithmetic or a scaling by a power of two, and the fp64 combination adds the
+    weights in a fixed order: the device result is bit-identical to the NumPy restatement of the scheme (oracle/ozaki_emulation.py)."""
+    import torch
+    from oracle import ozaki_emulation as E
+    rs = np.random.RandomState(slices)
+    m, n, k = 384, 640, 896
+    A = rs.randn(m, k) * np.exp2(rs.randint(-30, 30, (m, 1)))
+    B = rs.randn(n, k) * np.exp2(rs.randint(-30, 30, (n, 1)))
+    B[17] = 0.0
+    C = torch.zeros(m, n, dtype=torch.float64, device="cuda")
+    native.ozaki_dgemm(0, 0, 1.0, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), 0.0, C, slices=slices)
+    torch.cuda.synchronize()
+    assert np.array_equal(C.cpu().numpy(), E.gemm_nt(A, B, slices))
+    # the transposed storage orders cut the same digits
+    Ct = torch.zeros(m, n, dtype=torch.float64, device="cuda")
+    native.ozaki_dgemm(1, 1, 1.0, torch.from_numpy(np.ascontiguousarray(A.T)).cuda(), torch.from_numpy(np.ascontiguousarray(B.T)).cuda(),
+                       0.0, Ct, slices=slices)
+    torch.cuda.synchronize()
+    assert torch.equal(C, Ct)
+
+
 def test_ozaki_exact_on_integers():
     """Small integers fit the first two digits exactly: the int8 products and their fp64 recombination are error free."""
     import torch
