@@ -137,6 +137,41 @@ def test_acquisition_topk_properties(fitted):
     assert_allclose(r["df"][c, 3], fd, rtol=1e-4, atol=1e-9)
 
 
+def test_int8_engine_at_the_headline_size(fitted):
+    """The experimental int8 tensor-core engine (csrc/gpb_ozaki.cu, off by default) on the two top recursion levels, Ky^-1 = M^T M and
+    the predictive products: same log-likelihood, gradients, residuals and anchors as the fp64 engine at N = 16384."""
+    m, X, Y, (v, ls, noise), logL, g, torch = fitted
+    dev = torch.device("cuda")
+    fmin0 = m.fmin()
+    Xc = np.random.RandomState(99).uniform(0, 1, (2 ** 13, D))
+    vals0, idx0, pts0, f0, _ = m.acq_topk_full("EI", 0.01, fmin0, Xc, 5, with_gradients=False)
+    try:
+        for digits, tl, tg in ((8, 1e-12, 1e-10), (7, 1e-10, 1e-8)):
+            native.set_ozaki(8192, digits)
+            m.set_theta(v, ls, noise)
+            info, l1, g1 = m.fit(True)
+            assert info == 0
+            assert_allclose(l1, logL, rtol=tl)
+            assert_allclose(g1, g, rtol=tg, atol=tg * np.abs(g).max())
+        # residual of the inverse built by the engine (7 digits, the looser setting): Ky^-1 Ky = I
+        K = m.get("K", out=torch.empty((N, N), dtype=torch.float64, device=dev))
+        K += (noise + 1e-8) * torch.eye(N, dtype=torch.float64, device=dev)
+        Wi = m.get("Wi", out=torch.empty((N, N), dtype=torch.float64, device=dev))
+        Q = Wi @ K
+        Q -= torch.eye(N, dtype=torch.float64, device=dev)
+        assert float(Q.abs().max()) <= 1e-8
+        del Q, K, Wi
+        fmin1 = m.fmin()
+        assert_allclose(fmin1, fmin0, rtol=1e-9)
+        vals1, idx1, pts1, f1, _ = m.acq_topk_full("EI", 0.01, fmin1, Xc, 5, with_gradients=False)
+        assert np.array_equal(idx1, idx0)
+        assert_allclose(f1, f0, rtol=1e-7, atol=1e-9 * np.abs(f0).max())
+    finally:
+        native.set_ozaki(0)
+        m.set_theta(v, ls, noise)
+        m.fit(True)                                   # leave the shared model as the fp64 engine built it
+
+
 def test_n32768_d20_end_state_of_config5():
     """BASELINE.json config 5 grows the model to N = 32768 (D = 20): three 8.6 GB matrices resident on one GPU.  Checked through
     the closed forms at the training inputs (no second N x N copy needed) and one finite difference."""
