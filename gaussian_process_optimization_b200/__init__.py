@@ -22,6 +22,14 @@ from . import sharded as _s
 
 __version__ = "0.1.0"
 
+
+def set_int8_engine(min_n=8192, digits=8):
+    """Experimental, off by default: route the products of the factorisation with at least `min_n` rows (and the predictive products of
+    candidate blocks of >= 1024 rows) through the int8 tensor-core engine (csrc/gpb_ozaki.cu).  min_n = 0 switches it off.  digits: 8
+    (indistinguishable from the fp64 engine) or 7 (25% faster, agrees to ~1e-13).  Results stay within the tolerances of tests/, but
+    are not bitwise those of the fp64 engine."""
+    native.set_ozaki(min_n, digits)
+
 GPy = _NS(
     kern=_NS(Kern=_k.Kern, Stationary=_k.Stationary, RBF=_k.RBF, Matern52=_k.Matern52),
     models=_NS(GPRegression=_m.GPRegression),
