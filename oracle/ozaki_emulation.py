@@ -44,3 +44,69 @@ def gemm_nt(A, B, S):
             acc += Da[s - 1].astype(np.float64) @ Db[w - s - 1].astype(np.float64).T     # exact: integers below 2^53
         C += acc * 2.0 ** (2 - 8 * w)
     return C * np.exp2(ea) * np.exp2(eb).T
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Next step studied on the CPU (NOT yet in the CUDA engine): modular splitting ("Ozaki scheme II").  One int8 product per
+# modulus instead of S (S + 1) / 2 digit-pair products: the operands are scaled to integers A', B' with |A' B'^T| < P / 2,
+# P = product of pairwise coprime moduli <= 256, every modulus gives (A' mod p)(B' mod p)^T with balanced int8 residues and an
+# exact int32 accumulation, and the integer product is rebuilt by the Chinese remainder theorem (Garner's mixed-radix form with
+# balanced digits, then a Horner evaluation in fp64).  16 moduli carry what 7 digits (28 products) carry; 17-18 moduli what 8
+# digits (36 products) carry.
+# ----------------------------------------------------------------------------------------------------------------------
+MODULI = (256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191, 181, 179, 173)   # pairwise coprime
+
+
+def _balanced_mod(x, p):
+    """x mod p in [-(p // 2), (p - 1) // 2] (fits int8 for p <= 256)."""
+    r = np.mod(x, p)
+    return np.where(r >= (p + 1) // 2, r - p, r)
+
+
+def crt_bits(nmod, k):
+    """Bits beta per operand such that k products of two beta-bit integers stay below P / 2."""
+    log2P = sum(np.log2(float(p)) for p in MODULI[:nmod])
+    return int(np.floor((log2P - 1.0 - np.ceil(np.log2(k))) / 2.0))
+
+
+def split_rows_integer(A, beta):
+    """A[i, :] ~ 2^(e_i - beta) * Q[i, :], Q integer with |Q| < 2^(beta - 1) (row-wise power-of-two scaling, last bit rounded)."""
+    A = np.asarray(A, dtype=np.float64)
+    amax = np.abs(A).max(axis=1, keepdims=True)
+    m, e = np.frexp(np.where(amax > 0, amax, 1.0))
+    e = np.where(amax > 0, e, 0) + 1                           # |x| 2^-e < 1/2
+    Q = np.rint(A * np.exp2(float(beta) - e)).astype(np.int64)
+    return Q, e.astype(np.float64)
+
+
+def garner_balanced(residues, moduli):
+    """Mixed-radix digits v (balanced) with X = v_0 + v_1 p_0 + v_2 p_0 p_1 + ... for the X in (-P/2, P/2) with the given residues."""
+    v = []
+    for i, p in enumerate(moduli):
+        t = residues[i].astype(np.int64)
+        for j in range(i):
+            inv = pow(int(moduli[j]), -1, int(p))
+            t = _balanced_mod((t - v[j]) * inv, p)
+        v.append(_balanced_mod(t, p))
+    return v
+
+
+def gemm_nt_crt(A, B, nmod):
+    """A @ B.T through nmod int8 products (one per modulus) and a CRT reconstruction; the fp64 Horner evaluation of the
+    mixed-radix digits rounds once per step relative to the value itself."""
+    k = A.shape[1]
+    moduli = MODULI[:nmod]
+    beta = min(crt_bits(nmod, k), 62)
+    Qa, ea = split_rows_integer(A, beta)
+    Qb, eb = split_rows_integer(B, beta)
+    residues = []
+    for p in moduli:
+        Ra = _balanced_mod(Qa, p).astype(np.float64)           # int8 planes on the device
+        Rb = _balanced_mod(Qb, p).astype(np.float64)
+        S = Ra @ Rb.T                                          # exact: |sum| <= k 128^2 < 2^53 (int32 on the device)
+        residues.append(_balanced_mod(S.astype(np.int64), p))
+    v = garner_balanced(residues, moduli)
+    X = v[-1].astype(np.float64)
+    for i in range(nmod - 2, -1, -1):                          # Horner: X = X p_i + v_i
+        X = X * float(moduli[i]) + v[i].astype(np.float64)
+    return X * np.exp2(ea - beta) * np.exp2(eb - beta).T, beta

@@ -42,6 +42,8 @@ def make_gemm_balanced(S):
 
 
 def make_gemm(S):
+    if S >= 100:                      # modular splitting with S - 100 moduli (studied for the next round, CPU emulation only)
+        return lambda A, B: E.gemm_nt_crt(A, B, S - 100)[0]
     if S < 0:
         return make_gemm_balanced(-S)
     """gemm_nt(A, B) = A @ B.T, exact fp64 (S = 0) or the S-digit emulation with the digit pairs s + t <= S + 1."""
@@ -113,11 +115,12 @@ def main():
         Ky = O.K(kind, X, None, 1.0, ls) + (noise + 1e-8) * np.eye(N)
         ev = np.linalg.eigvalsh(Ky)
         case = {"cond_Ky": float(ev[-1] / ev[0])}
-        for S in (0, 7, 8, 9, -6, -7, -8):
+        for S in (0, 7, 8, 9, -6, -7, -8, 115, 116, 117, 118):
             try:
                 l, g = evaluate(kind, X, Y, 1.0, ls, noise, S)
-                case["S%d" % S] = {"scheme": "plain fp64" if S == 0 else "7-bit truncated digits" if S > 0 else "balanced radix-256 digits",
-                                   "int8_gemms_per_product": abs(S) * (abs(S) + 1) // 2,
+                case["S%d" % S] = {"scheme": ("plain fp64" if S == 0 else "modular splitting (CRT), %d moduli" % (S - 100) if S >= 100
+                                              else "7-bit truncated digits" if S > 0 else "balanced radix-256 digits"),
+                                   "int8_gemms_per_product": (S - 100) if S >= 100 else abs(S) * (abs(S) + 1) // 2,
                                    "logL_rel": float(abs(l - l_ref) / abs(l_ref)),
                                    "grad_rel_max": float(np.max(np.abs(g - g_ref) / np.maximum(np.abs(g_ref), 1e-300))),
                                    "grad_rel_to_norm": float(np.max(np.abs(g - g_ref)) / np.max(np.abs(g_ref)))}

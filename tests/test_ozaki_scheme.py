@@ -51,3 +51,46 @@ def test_int32_accumulation_bound():
     """The kernel chains at most 1023 k-blocks of 128 into one int32 accumulation: the extreme digit product 128 * 128 fits."""
     assert 128 * 128 * 128 * 1023 < 2 ** 31
     assert 128 * 128 * 128 * 1024 >= 2 ** 31
+
+
+# ---- modular splitting (studied for the next round; CPU emulation only) ----------------------------------------------------------
+def test_moduli_are_pairwise_coprime_and_fit_int8():
+    from math import gcd
+    M = E.MODULI
+    assert all(p <= 256 for p in M)
+    assert all(gcd(M[i], M[j]) == 1 for i in range(len(M)) for j in range(i))
+    x = np.arange(-70000, 70000)
+    for p in M:
+        r = E._balanced_mod(x, p)
+        assert r.min() >= -128 and r.max() <= 127 and np.all((x - r) % p == 0)
+
+
+def test_garner_rebuilds_signed_integers_exactly():
+    rs = np.random.RandomState(0)
+    moduli = E.MODULI[:6]
+    P = int(np.prod([int(p) for p in moduli], dtype=object))
+    X = np.array([rs.randint(-(P // 2) + 1, P // 2) for _ in range(200)] + [0, 1, -1, P // 2 - 1, -(P // 2) + 1], dtype=object)
+    residues = [np.array([int(E._balanced_mod(np.int64(int(x) % p), p)) for x in X], dtype=np.int64) for p in moduli]
+    v = E.garner_balanced(residues, moduli)
+    rebuilt, radix = np.zeros(len(X), dtype=object), 1
+    for vi, p in zip(v, moduli):
+        assert vi.min() >= -(p // 2) and vi.max() <= (p - 1) // 2
+        rebuilt = rebuilt + vi.astype(object) * radix
+        radix *= int(p)
+    assert np.all(rebuilt == X)
+
+
+@pytest.mark.parametrize("nmod,bits", [(12, 38), (16, 54), (18, 61)])
+def test_crt_product_accuracy(nmod, bits):
+    rs = np.random.RandomState(nmod)
+    m, n, k = 20, 27, 700
+    A = rs.randn(m, k) * np.exp2(rs.randint(-20, 20, (m, 1)))
+    B = rs.randn(n, k)
+    ref = (A.astype(np.longdouble) @ B.astype(np.longdouble).T).astype(np.float64)
+    C, beta = E.gemm_nt_crt(A, B, nmod)
+    assert beta >= bits
+    scale = np.abs(A).max(1, keepdims=True) * np.abs(B).max(1, keepdims=True).T * k
+    assert np.all(np.abs(C - ref) <= 8 * scale * 2.0 ** -(beta - 1) + 4 * np.finfo(float).eps * np.abs(ref))
+    if nmod == 16:
+        # 16 moduli (16 int8 products) are at least as accurate as 7 balanced digits (28 products)
+        assert np.abs(C - ref).max() <= 2 * np.abs(E.gemm_nt(A, B, 7) - ref).max() + 1e-300
