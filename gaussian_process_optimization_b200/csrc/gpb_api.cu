@@ -831,7 +831,8 @@ int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) 
 // and the block has enough rows to fill 256-row tiles.
 // 8 digits here, not 7: the predictive variance sigma^2 - sum (M k*)^2 cancels, and the digit scheme is accurate relative to the
 // largest entry of a row of M, not entry by entry (with 7 digits LCB values of an ill-conditioned RBF model moved by 4e-10).
-constexpr int OZAKI_PREDICT_DIGITS = 8;
+// 8 digits, or 18 moduli (62 bits per operand) when the engine is configured in its modular mode
+#define OZAKI_PREDICT_DIGITS ozaki_predict_planes()
 static inline bool ozaki_predict(int np, int cpad) { return ozaki_min_n() > 0 && np >= ozaki_min_n() && cpad >= 1024; }
 
 static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int level, int include_likelihood) {
@@ -1556,5 +1557,13 @@ int gpb_ozaki_dgemm(int ta, int tb, int m, int n, int k, double alpha, const dou
                            reinterpret_cast<cudaStream_t>(stream));
 }
 int gpb_set_ozaki(int min_n, int slices) { return ozaki_configure(min_n, slices); }
+// modular mode of the int8 engine: operand bits, and the host restatement of its integer arithmetic (test hooks, no GPU needed)
+int gpb_ozaki_crt_bits(int nmod, long long k) { return ozaki_crt_bits(nmod, k); }
+int gpb_ozaki_crt_host_residues(const double *A, int rows, int k, int nmod, int beta, signed char *planes, double *scale) {
+  return ozaki_crt_host_residues(A, rows, k, nmod, beta, planes, scale);
+}
+int gpb_ozaki_crt_host_combine(const int *sums, long long count, int nmod, double *X) {
+  return ozaki_crt_host_combine(sums, count, nmod, X);
+}
 
 }  // extern "C"

@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "gpb_common.cuh"
+#include "gpb_crt.cuh"
 
 namespace gpb {
 
@@ -47,6 +48,10 @@ constexpr int PREFETCH = 6;                     // k-blocks of L2 prefetch dista
 constexpr int NTHREADS = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int GROUP_KB = 1023;                 // k-blocks per int32 accumulation: 128^2 * 128 * 1023 = 2.145e9 < 2^31
 constexpr int MAX_S = 8;                        // 8 S - 1 <= 63: the scaled operand must fit a 64-bit integer
+// Modular (CRT) mode: a plane count S in [crt::MINMOD, crt::MAXMOD] means "S moduli" instead of "S digits" (gpb_crt.cuh): ONE int8
+// product per modulus, every drain parks the balanced residues of its int32 sums as int8, oz_crt_combine_kernel rebuilds the
+// integer product (Garner + Horner) and writes C.  16 moduli carry 56 bits per operand at k = 16384 (7 digits: 55), 17 carry 59.
+__constant__ crt::ModTable c_mods = crt::make_table();
 
 struct Params {
   int M, N, K, S;
@@ -58,6 +63,7 @@ struct Params {
                            // every warp store / load is one contiguous 512-byte line (the owner lane reads back what it wrote)
   int tiles_m, tiles_n;
   int cl, share_a;         // CTA pairs (cluster of 2) that share one operand tile by TMA multicast: A (pair along n) or B (pair along m)
+  int nmod;                // > 0: modular mode with that many moduli (S = nmod planes per operand)
   int dbg;                 // measurement only: 1 = no TMA loads (MMA-bound rate), 2 = no epilogue memory traffic, 3 = no drains but the last (wrong results)
 };
 
@@ -233,13 +239,20 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // accumulations per tile: one per digit weight w = S + 1 .. 2 (the pairs s + t = w chained along k), or one per modulus
+  const int nW = p.nmod ? p.nmod : p.S;
+  auto weight_range = [&](int wi, int &w, int &s_lo, int &s_hi) {
+    if (p.nmod) { w = 2 * (wi + 1); s_lo = s_hi = wi + 1; }
+    else { w = p.S + 1 - wi; s_lo = max(1, w - p.S); s_hi = min(p.S, w - 1); }
+  };
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = p.S + 1; w >= 2; --w) {
-        const int s_lo = max(1, w - p.S), s_hi = min(p.S, w - 1);
+      for (int wi = 0; wi < nW; ++wi) {
+        int w, s_lo, s_hi;
+        weight_range(wi, w, s_lo, s_hi);
         for (int s = s_lo; s <= s_hi; ++s) {
           const int t = w - s;
           for (int kb = 0; kb < nkb; ++kb) {
@@ -275,13 +288,15 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int w = p.S + 1; w >= 2; --w) {
-        const int npairs = min(p.S, w - 1) - max(1, w - p.S) + 1;
+      for (int wi = 0; wi < nW; ++wi) {
+        int w, s_lo, s_hi;
+        weight_range(wi, w, s_lo, s_hi);
+        const int npairs = s_hi - s_lo + 1;
         const int total = npairs * nkb;
         for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
           const int g1 = min(total, g0 + GROUP_KB);
-          const bool skip_drain = p.dbg == 3 && !((w == 2) && (g0 + GROUP_KB >= total));   // measurement only: no hand-over
-          if (!(p.dbg == 3 && (w != p.S + 1 || g0 != 0))) {
+          const bool skip_drain = p.dbg == 3 && !((wi == nW - 1) && (g0 + GROUP_KB >= total));   // measurement only: no hand-over
+          if (!(p.dbg == 3 && (wi != 0 || g0 != 0))) {
             mbar_wait(tempty_bar, acc_phase ^ 1);
             tc_fence_after();
           }
@@ -322,15 +337,42 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (p.tri_out) ncols = min(ncols, row0 + half * 128 + 128 - col0);   // 128-blocks above the diagonal are left untouched
     if (!row_ok) ncols = 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * BN);
-    for (int w = p.S + 1; w >= 2; --w) {
-      const int npairs = min(p.S, w - 1) - max(1, w - p.S) + 1;
+    for (int wi = 0; wi < nW; ++wi) {
+      int w, s_lo, s_hi;
+      weight_range(wi, w, s_lo, s_hi);
+      const int npairs = s_hi - s_lo + 1;
       const int total = npairs * nkb;
       for (int g0 = 0; g0 < total; g0 += GROUP_KB) {
-        const bool last = (w == 2) && (g0 + GROUP_KB >= total);
+        const bool last = !p.nmod && (wi == nW - 1) && (g0 + GROUP_KB >= total);
         if (p.dbg == 3 && !last) { ++drain; continue; }
         mbar_wait(tfull_bar, acc_phase);
         tc_fence_after();
-        if (!last) {
+        if (p.nmod) {
+          // modular mode: one accumulation per modulus (the host guarantees nkb <= GROUP_KB); park the balanced residues of the
+          // exact int32 sums as int8, 16 columns per uint4, [modulus][tile][epilogue warp 8][chunk 16][lane 32]
+          const crt::ModParams mp = c_mods.m[wi];
+          uint4 *dst = p.P + (size_t)wi * p.plane + ((size_t)(tm * p.tiles_n + tn) * 8 + (warp - 2)) * (16 * 32) + lane;
+          for (int c0 = 0; c0 < ncols; c0 += 64) {
+            uint32_t v[32], v2[32];
+            tmem_ld32(taddr + c0, v);
+            tmem_ld32(taddr + c0 + 32, v2);
+            tmem_ld_wait();
+            uint32_t wd[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              uint32_t a = 0, b = 0;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                a |= ((uint32_t)crt::residue_of_sum((int)v[j + t], mp) & 0xFFu) << (8 * t);
+                b |= ((uint32_t)crt::residue_of_sum((int)v2[j + t], mp) & 0xFFu) << (8 * t);
+              }
+              wd[j / 4] = a;
+              wd[8 + j / 4] = b;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dst[(c0 / 16 + u) * 32] = make_uint4(wd[4 * u], wd[4 * u + 1], wd[4 * u + 2], wd[4 * u + 3]);
+          }
+        } else if (!last) {
           // park the exact int32 sums of this drain (write only; the combination happens once, below)
           uint4 *dst = Pw + (size_t)drain * p.plane;
           for (int c0 = 0; c0 < ncols; c0 += 64) {             // ncols is a multiple of 128; two loads in flight per wait
@@ -479,8 +521,8 @@ __global__ void __launch_bounds__(256) oz_absmax_kernel(const double *__restrict
 // digits: [S][R][K] int8, k contiguous.
 template <int LAYOUT>
 __global__ void __launch_bounds__(256)
-oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int S, const unsigned long long *__restrict__ amax,
-                int8_t *__restrict__ digits, double *__restrict__ scale) {
+oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int S, int nmod, int beta,
+                const unsigned long long *__restrict__ amax, int8_t *__restrict__ digits, double *__restrict__ scale) {
   __shared__ double sm[32][129];
   const int i0 = blockIdx.x * 32, k0 = blockIdx.y * 128;
   const int tid = threadIdx.x;
@@ -507,6 +549,27 @@ oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int
   int e = 0;
   if (am > 0.0 && am < 1e308) frexp(am, &e);            // am = f 2^e, f in [0.5, 1)
   e += 1;                                               // |x| 2^-e < 1/2: the leading digit stays within [-64, 64] + carry
+  if (nmod) {
+    // modular mode: q = rint(x 2^(beta - e)), |q| <= 2^(beta - 1) <= 2^61; plane i holds the balanced residue q mod p_i
+    if (seg == 0) scale[i0 + r] = ldexp(1.0, e - beta);
+    const double upm = ldexp(1.0, beta - e);
+    long long qm[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) qm[j] = __double2ll_rn(sm[r][seg + j] * upm);
+    for (int i = 0; i < nmod; ++i) {
+      const crt::ModParams mp = c_mods.m[i];
+      uint32_t wds[4];
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t wv = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) wv |= ((uint32_t)crt::residue_of(qm[q4 * 4 + b], mp) & 0xFFu) << (8 * b);
+        wds[q4] = wv;
+      }
+      *reinterpret_cast<uint4 *>(out + i * plane) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    }
+    return;
+  }
   if (seg == 0) scale[i0 + r] = ldexp(1.0, e);          // every valid sub-block of the row writes the same value
   const double up = ldexp(1.0, 8 * S - 1 - e);          // x -> q = rint(x 2^-e 2^(8 S - 1)), |q| < 2^(8 S - 2) <= 2^62
   long long q[16];
@@ -528,6 +591,50 @@ oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int
     }
     *reinterpret_cast<uint4 *>(out + s * plane) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
   }
+}
+
+// ---- modular mode: reconstruction ----------------------------------------------------------------------------------------
+// One thread per (row, 4 columns): reads one 32-bit word (four int8 residues) per modulus from the planes the drains parked (a warp
+// reads 128 contiguous bytes per modulus), rebuilds the four integers (crt::reconstruct: Garner's mixed-radix digits from
+// compile-time constants, Horner in fp64), applies the row / column scales, alpha and beta and writes 32 bytes of C.
+template <int NMOD>
+__global__ void __launch_bounds__(256) oz_crt_combine_kernel(const Params p) {
+  const unsigned g = blockIdx.x * 256u + threadIdx.x;
+  const int j4 = g & 3, lane = (g >> 2) & 31, chunk = (g >> 7) & 15, w8 = (g >> 11) & 7, tile = (int)(g >> 14);
+  const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+  const int q = (w8 + 2) & 3, half = w8 >> 2;               // the epilogue warp w8 + 2 of ozaki_mma_kernel owns these rows
+  const int row0 = tm * BM, col0 = tn * BN;
+  const int row = row0 + half * 128 + q * 32 + lane;
+  int ncols = min(BN, p.N - col0);
+  if (p.tri_out) ncols = min(ncols, row0 + half * 128 + 128 - col0);
+  if (row >= p.M || chunk * 16 >= ncols) return;
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(p.P + (((size_t)tile * 8 + w8) * 16 + chunk) * 32 + lane) + j4;
+  uint32_t u[NMOD];
+#pragma unroll
+  for (int i = 0; i < NMOD; ++i) u[i] = src[(size_t)i * p.plane * 4];
+  const int c = col0 + chunk * 16 + j4 * 4;
+  const double ra = p.alpha * p.ra[row];
+  double *Cp = p.C + (size_t)row * p.ldc + c;
+  double o[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    int r[NMOD];
+#pragma unroll
+    for (int i = 0; i < NMOD; ++i) r[i] = (int)(int8_t)((u[i] >> (8 * b)) & 0xFFu);
+    o[b] = crt::reconstruct<NMOD>(r) * (ra * p.rb[c + b]);
+  }
+  if (p.beta != 0.0) {
+    const double2 c0 = *reinterpret_cast<const double2 *>(Cp), c1 = *reinterpret_cast<const double2 *>(Cp + 2);
+    o[0] = fma(p.beta, c0.x, o[0]);
+    o[1] = fma(p.beta, c0.y, o[1]);
+    o[2] = fma(p.beta, c1.x, o[2]);
+    o[3] = fma(p.beta, c1.y, o[3]);
+  }
+  *reinterpret_cast<double2 *>(Cp) = make_double2(o[0], o[1]);
+  *reinterpret_cast<double2 *>(Cp + 2) = make_double2(o[2], o[3]);
+}
+template <int NMOD> static void launch_combine(const Params &p, cudaStream_t st) {
+  oz_crt_combine_kernel<NMOD><<<p.tiles_m * p.tiles_n * 64, 256, 0, st>>>(p);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
@@ -600,6 +707,7 @@ static int ensure(void **p, size_t *cap, size_t need) {
 
 static int g_slices = 8;   // 8 digits: indistinguishable from the fp64 engine in every parity test; 7 is 25% faster
 static int g_min_n = -1;   // -1: read GPB_OZAKI_MIN_N once; 0: off
+static bool valid_planes(int s) { return (s >= 1 && s <= MAX_S) || (s >= crt::MINMOD && s <= crt::MAXMOD); }
 
 }  // namespace oz
 
@@ -608,12 +716,14 @@ int ozaki_min_n() {
     const char *e = getenv("GPB_OZAKI_MIN_N");
     oz::g_min_n = e ? atoi(e) : 0;
     const char *s = getenv("GPB_OZAKI_SLICES");
-    if (s && atoi(s) >= 1 && atoi(s) <= oz::MAX_S) oz::g_slices = atoi(s);
+    if (s && oz::valid_planes(atoi(s))) oz::g_slices = atoi(s);
   }
   return oz::g_min_n;
 }
+int ozaki_predict_planes() { ozaki_min_n(); return oz::g_slices >= crt::MINMOD ? crt::MAXMOD : oz::MAX_S; }
 int ozaki_configure(int min_n, int slices) {
-  GPB_REQUIRE(min_n >= 0 && slices >= 1 && slices <= oz::MAX_S, "ozaki: min_n >= 0 and 1 <= slices <= %d", oz::MAX_S);
+  GPB_REQUIRE(min_n >= 0 && oz::valid_planes(slices), "ozaki: min_n >= 0 and 1 <= slices <= %d (digits) or %d <= slices <= %d (moduli)",
+              oz::MAX_S, crt::MINMOD, crt::MAXMOD);
   oz::g_min_n = min_n;
   oz::g_slices = slices;
   return 0;
@@ -630,7 +740,10 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   const int S = slices > 0 ? slices : g_slices;
   GPB_REQUIRE(g.M % 128 == 0 && g.N % 128 == 0 && g.K % 128 == 0 && g.M > 0 && g.N > 0 && g.K > 0, "ozaki: sizes must be multiples of 128");
   GPB_REQUIRE(!g.tri_out || g.M == g.N, "ozaki: tri_out needs a square output");
-  GPB_REQUIRE(S >= 1 && S <= MAX_S, "ozaki: bad digit count %d", S);
+  GPB_REQUIRE(valid_planes(S), "ozaki: bad digit / modulus count %d", S);
+  const int nmod = S >= crt::MINMOD ? S : 0;
+  const int beta_bits = nmod ? crt::operand_bits(nmod, g.K) : 0;
+  GPB_REQUIRE(!nmod || g.K / BKB <= GROUP_KB, "ozaki: modular mode needs k <= %d", GROUP_KB * BKB);
   int dev = 0;
   GPB_CUDA(cudaGetDevice(&dev));
   Workspace &ws = *workspace_for(dev, st);
@@ -653,17 +766,18 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
     const int npairs = (S < w - 1 ? S : w - 1) - (1 > w - S ? 1 : w - S) + 1;
     drains += (npairs * (g.K / BKB) + GROUP_KB - 1) / GROUP_KB;
   }
-  const size_t plane = (size_t)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * (BM * BN / 4);   // uint4 per drain
-  GPB_TRY(ensure((void **)&ws.T, &ws.capT, (size_t)(drains > 1 ? drains - 1 : 1) * plane * sizeof(uint4)));
+  // (modular mode: one int8 plane per modulus, a quarter of that per plane)
+  const size_t plane = (size_t)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * (nmod ? BM * BN / 16 : BM * BN / 4);   // uint4 per drain
+  GPB_TRY(ensure((void **)&ws.T, &ws.capT, (size_t)(nmod ? nmod : (drains > 1 ? drains - 1 : 1)) * plane * sizeof(uint4)));
   GPB_CUDA(cudaMemsetAsync(ws.amax, 0, 2 * ws.cap_rows * sizeof(unsigned long long), st));
   auto split = [&](int layout, const double *P, int ld, int R, int tri, unsigned long long *amax, int8_t *dig, double *scale) -> int {
     dim3 g1(R / 128, g.K / 128), g2(R / 32, g.K / 128);
     if (layout == LAYOUT_ROWK) {
       oz_absmax_kernel<LAYOUT_ROWK><<<g1, 256, 0, st>>>(P, ld, tri, amax);
-      oz_split_kernel<LAYOUT_ROWK><<<g2, 256, 0, st>>>(P, ld, R, g.K, tri, S, amax, dig, scale);
+      oz_split_kernel<LAYOUT_ROWK><<<g2, 256, 0, st>>>(P, ld, R, g.K, tri, S, nmod, beta_bits, amax, dig, scale);
     } else {
       oz_absmax_kernel<LAYOUT_COLK><<<g1, 256, 0, st>>>(P, ld, tri, amax);
-      oz_split_kernel<LAYOUT_COLK><<<g2, 256, 0, st>>>(P, ld, R, g.K, tri, S, amax, dig, scale);
+      oz_split_kernel<LAYOUT_COLK><<<g2, 256, 0, st>>>(P, ld, R, g.K, tri, S, nmod, beta_bits, amax, dig, scale);
     }
     count_launch(2);
     GPB_CHECK_LAUNCH();
@@ -710,7 +824,8 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   p.cl = cl; p.share_a = share_a;
   static int dbg = -1;
   if (dbg < 0) { const char *e = getenv("GPB_OZAKI_DBG"); dbg = e ? atoi(e) : 0; }
-  p.dbg = dbg;
+  p.dbg = (nmod && dbg == 3) ? 0 : dbg;
+  p.nmod = nmod;
   static unsigned long long configured = 0;
   if (needs_func_config(configured))
     GPB_CUDA(cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -731,6 +846,68 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   }
   count_launch();
   GPB_CHECK_LAUNCH();
+  if (nmod) {
+    switch (nmod) {
+      case 10: launch_combine<10>(p, st); break;
+      case 11: launch_combine<11>(p, st); break;
+      case 12: launch_combine<12>(p, st); break;
+      case 13: launch_combine<13>(p, st); break;
+      case 14: launch_combine<14>(p, st); break;
+      case 15: launch_combine<15>(p, st); break;
+      case 16: launch_combine<16>(p, st); break;
+      case 17: launch_combine<17>(p, st); break;
+      default: launch_combine<18>(p, st); break;
+    }
+    count_launch();
+    GPB_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
+// ---- host restatement of the modular arithmetic (the same gpb_crt.cuh code compiled for the host): test hooks behind the C ABI,
+// used by the CPU tests to hold it bit-identical to oracle/ozaki_emulation.py.  Nothing on the product path calls them.
+int ozaki_crt_bits(int nmod, long long k) { return crt::operand_bits(nmod, k); }
+int ozaki_crt_host_residues(const double *A, int rows, int k, int nmod, int beta, signed char *planes, double *scale) {
+  GPB_REQUIRE(A && planes && scale && rows > 0 && k > 0 && nmod >= crt::MINMOD && nmod <= crt::MAXMOD && beta >= 1 && beta <= 62,
+              "ozaki_crt_host_residues: bad argument");
+  static const crt::ModTable tab = crt::make_table();
+  for (int i = 0; i < rows; ++i) {
+    double am = 0.0;
+    for (int j = 0; j < k; ++j) am = fmax(am, fabs(A[(size_t)i * k + j]));
+    int e = 0;
+    if (am > 0.0 && am < 1e308) frexp(am, &e);
+    e += 1;
+    scale[i] = ldexp(1.0, e - beta);
+    const double up = ldexp(1.0, beta - e);
+    for (int j = 0; j < k; ++j) {
+      const long long q = llrint(A[(size_t)i * k + j] * up);
+      for (int m = 0; m < nmod; ++m) planes[((size_t)m * rows + i) * k + j] = (signed char)crt::residue_of(q, tab.m[m]);
+    }
+  }
+  return 0;
+}
+template <int NMOD> static void host_combine(const int *sums, size_t count, double *X) {
+  static const crt::ModTable tab = crt::make_table();
+  for (size_t e = 0; e < count; ++e) {
+    int r[NMOD];
+    for (int m = 0; m < NMOD; ++m) r[m] = crt::residue_of_sum(sums[(size_t)m * count + e], tab.m[m]);
+    X[e] = crt::reconstruct<NMOD>(r);
+  }
+}
+// sums: [nmod][count] exact int32 accumulations of the residue products -> X[count] = the integer products, rounded to fp64
+int ozaki_crt_host_combine(const int *sums, long long count, int nmod, double *X) {
+  GPB_REQUIRE(sums && X && count > 0 && nmod >= crt::MINMOD && nmod <= crt::MAXMOD, "ozaki_crt_host_combine: bad argument");
+  switch (nmod) {
+    case 10: host_combine<10>(sums, (size_t)count, X); break;
+    case 11: host_combine<11>(sums, (size_t)count, X); break;
+    case 12: host_combine<12>(sums, (size_t)count, X); break;
+    case 13: host_combine<13>(sums, (size_t)count, X); break;
+    case 14: host_combine<14>(sums, (size_t)count, X); break;
+    case 15: host_combine<15>(sums, (size_t)count, X); break;
+    case 16: host_combine<16>(sums, (size_t)count, X); break;
+    case 17: host_combine<17>(sums, (size_t)count, X); break;
+    default: host_combine<18>(sums, (size_t)count, X); break;
+  }
   return 0;
 }
 

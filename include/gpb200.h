@@ -182,6 +182,15 @@ int gpb_ozaki_dgemm(int ta, int tb, int m, int n, int k, double alpha, const dou
 /* Products of gpb_model_fit's factorisation with at least min_n rows go through the int8 engine (0 = off, the default; also
  * GPB_OZAKI_MIN_N / GPB_OZAKI_SLICES in the environment). */
 int gpb_set_ozaki(int min_n, int slices);
+/* Modular (CRT) mode of the same engine: slices in [10, 18] means "that many pairwise coprime moduli <= 256" instead of digits --
+ * ONE int8 product per modulus (16 moduli carry 56 bits per operand at k = 16384, where 7 digits = 28 products carry 55), the
+ * integer product rebuilt by the Chinese remainder theorem (csrc/gpb_crt.cuh).  gpb_ozaki_crt_bits: bits per operand for nmod moduli
+ * and inner dimension k.  The two *_host_* entry points run the engine's integer arithmetic (residues of the scaled operand rows
+ * [nmod][rows][k]; reconstruction of count integers from their [nmod][count] exact int32 residue-product sums) on the HOST: test
+ * hooks that hold the device code bit-identical to oracle/ozaki_emulation.py without a GPU; nothing on the product path uses them. */
+int gpb_ozaki_crt_bits(int nmod, long long k);
+int gpb_ozaki_crt_host_residues(const double *A, int rows, int k, int nmod, int beta, signed char *planes, double *scale);
+int gpb_ozaki_crt_host_combine(const int *sums, long long count, int nmod, double *X);
 
 #ifdef __cplusplus
 }

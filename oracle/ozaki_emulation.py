@@ -47,14 +47,16 @@ def gemm_nt(A, B, S):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# Next step studied on the CPU (NOT yet in the CUDA engine): modular splitting ("Ozaki scheme II").  One int8 product per
-# modulus instead of S (S + 1) / 2 digit-pair products: the operands are scaled to integers A', B' with |A' B'^T| < P / 2,
+# Modular splitting ("Ozaki scheme II"; the engine's modular mode, csrc/gpb_crt.cuh: slices in [10, 18]).  One int8 product per
+# modulus instead of S (S + 1) / 2 digit-pair products: the operands are scaled to integers A', B' with |A' B'^T| <= P / 2,
 # P = product of pairwise coprime moduli <= 256, every modulus gives (A' mod p)(B' mod p)^T with balanced int8 residues and an
 # exact int32 accumulation, and the integer product is rebuilt by the Chinese remainder theorem (Garner's mixed-radix form with
-# balanced digits, then a Horner evaluation in fp64).  16 moduli carry what 7 digits (28 products) carry; 17-18 moduli what 8
-# digits (36 products) carry.
+# balanced digits, then an evaluation in fp64: three digits at a time exactly as integers, Horner over those groups with one
+# rounded product and one rounded sum per step -- the order crt::reconstruct uses).  16 moduli carry what 7 digits (28 products)
+# carry; 17-18 moduli what 8 digits (36 products) carry.
 # ----------------------------------------------------------------------------------------------------------------------
 MODULI = (256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191, 181, 179, 173)   # pairwise coprime
+# (the device engine knows the first 18: crt::modulus in csrc/gpb_crt.cuh)
 
 
 def _balanced_mod(x, p):
@@ -64,9 +66,34 @@ def _balanced_mod(x, p):
 
 
 def crt_bits(nmod, k):
-    """Bits beta per operand such that k products of two beta-bit integers stay below P / 2."""
-    log2P = sum(np.log2(float(p)) for p in MODULI[:nmod])
-    return int(np.floor((log2P - 1.0 - np.ceil(np.log2(k))) / 2.0))
+    """Bits beta per operand: the scaled operands satisfy |Q| <= 2^(beta - 1), so k products stay within 2^(ceil(log2 k) + 2 beta - 2),
+    which must not exceed 2^floor(log2 P) / 2 <= P / 2 (exact integer arithmetic; crt::operand_bits does the same)."""
+    P = 1
+    for p in MODULI[:nmod]:
+        P *= int(p)
+    fl = P.bit_length() - 1
+    lk = (int(k) - 1).bit_length()
+    return min((fl + 1 - lk) // 2, 62)
+
+
+def crt_evaluate(v, moduli):
+    """Value of the mixed-radix digits v in fp64: groups of three digits exactly (< 2^24), Horner over the groups from the top."""
+    n = len(moduli)
+    groups, weights = [], []
+    for i in range(0, n, 3):
+        g = v[i].astype(np.int64)
+        if i + 2 < n:
+            g = g + int(moduli[i]) * (v[i + 1].astype(np.int64) + int(moduli[i + 1]) * v[i + 2].astype(np.int64))
+        elif i + 1 < n:
+            g = g + int(moduli[i]) * v[i + 1].astype(np.int64)
+        groups.append(g.astype(np.float64))
+        if i + 2 < n:
+            weights.append(float(int(moduli[i]) * int(moduli[i + 1]) * int(moduli[i + 2])))
+    X = groups[-1]
+    for gi in range(len(groups) - 2, -1, -1):
+        X = X * weights[gi]                                    # one rounding
+        X = X + groups[gi]                                     # one rounding
+    return X
 
 
 def split_rows_integer(A, beta):
@@ -106,7 +133,5 @@ def gemm_nt_crt(A, B, nmod):
         S = Ra @ Rb.T                                          # exact: |sum| <= k 128^2 < 2^53 (int32 on the device)
         residues.append(_balanced_mod(S.astype(np.int64), p))
     v = garner_balanced(residues, moduli)
-    X = v[-1].astype(np.float64)
-    for i in range(nmod - 2, -1, -1):                          # Horner: X = X p_i + v_i
-        X = X * float(moduli[i]) + v[i].astype(np.float64)
-    return X * np.exp2(ea - beta) * np.exp2(eb - beta).T, beta
+    X = crt_evaluate(v, moduli)
+    return X * (np.exp2(ea - beta) * np.exp2(eb - beta).T), beta

@@ -1,5 +1,5 @@
 """GPU parity of the experimental int8 tensor-core engine (csrc/gpb_ozaki.cu: tcgen05 kind::i8 products of balanced radix-256 digits,
-recombined in fp64) -- as a GEMM against fp64 references, with the triangular k-ranges of the cholinv recursion, and as the
+recombined in fp64; slices >= 10 = its modular mode, one product per modulus and a CRT reconstruction, csrc/gpb_crt.cuh) -- as a GEMM against fp64 references, with the triangular k-ranges of the cholinv recursion, and as the
 engine of a whole NLL + gradient evaluation against the CPU oracle at north_star's tolerances (rtol 1e-9 log-likelihood,
 1e-7 gradients).  The engine is off by default; these tests switch it on explicitly."""
 import numpy as np
@@ -15,7 +15,8 @@ native = pytest.importorskip("gaussian_process_optimization_b200.native")
 
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 384, 640), (640, 1152, 256)])
-def test_ozaki_dgemm_layouts(ta, tb, m, n, k):
+@pytest.mark.parametrize("slices", [8, 17])
+def test_ozaki_dgemm_layouts(ta, tb, m, n, k, slices):
     import torch
     g = torch.Generator(device="cpu").manual_seed(m + 7 * n + 13 * k + ta + 2 * tb)
     A = torch.randn((k, m) if ta else (m, k), generator=g, dtype=torch.float64)
@@ -27,16 +28,16 @@ def test_ozaki_dgemm_layouts(ta, tb, m, n, k):
     ref = 1.5 * (opA @ opB) - 0.5 * C
     bound = 1.5 * (opA.abs() @ opB.abs()) + 0.5 * C.abs()       # componentwise scale of a floating-point product
     Cd = C.cuda()
-    native.ozaki_dgemm(ta, tb, 1.5, A.cuda(), B.cuda(), -0.5, Cd, slices=8)
+    native.ozaki_dgemm(ta, tb, 1.5, A.cuda(), B.cuda(), -0.5, Cd, slices=slices)
     torch.cuda.synchronize()
     err = (Cd.cpu() - ref).abs()
-    # 8 balanced radix-256 digits: 2^-61 relative to the row / column maxima per term, i.e. norm-wise fp64 accuracy
+    # 8 balanced radix-256 digits (17 moduli: >= 59 bits): 2^-61 relative to the row / column maxima per term, i.e. norm-wise fp64 accuracy
     rowmax = opA.abs().amax(dim=1, keepdim=True)
     colmax = opB.abs().amax(dim=0, keepdim=True)
     assert float((err / (k * rowmax * colmax * 2.0 ** -52 + 1e-15 * bound)).max()) < 1.0
 
 
-@pytest.mark.parametrize("slices", [5, 7, 8])
+@pytest.mark.parametrize("slices", [5, 7, 8, 10, 16, 17, 18])
 def test_ozaki_device_equals_the_numpy_emulation_bitwise(slices):
     """Every step of the engine is exact integer arithmetic or a scaling by a power of two, and the fp64 combination adds the
     weights in a fixed order: the device result is bit-identical to the NumPy restatement of the scheme (oracle/ozaki_emulation.py)."""
@@ -50,7 +51,8 @@ def test_ozaki_device_equals_the_numpy_emulation_bitwise(slices):
     C = torch.zeros(m, n, dtype=torch.float64, device="cuda")
     native.ozaki_dgemm(0, 0, 1.0, torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), 0.0, C, slices=slices)
     torch.cuda.synchronize()
-    assert np.array_equal(C.cpu().numpy(), E.gemm_nt(A, B, slices))
+    ref = E.gemm_nt(A, B, slices) if slices <= 8 else E.gemm_nt_crt(A, B, slices)[0]     # >= 10: modular mode
+    assert np.array_equal(C.cpu().numpy(), ref)
     # the transposed storage orders cut the same digits
     Ct = torch.zeros(m, n, dtype=torch.float64, device="cuda")
     native.ozaki_dgemm(1, 1, 1.0, torch.from_numpy(np.ascontiguousarray(A.T)).cuda(), torch.from_numpy(np.ascontiguousarray(B.T)).cuda(),
@@ -71,7 +73,7 @@ def test_ozaki_exact_on_integers():
     assert torch.equal(C.cpu(), A @ B.T)
 
 
-@pytest.mark.parametrize("slices", [7, 8])
+@pytest.mark.parametrize("slices", [7, 8, 16])
 def test_ozaki_long_k_needs_several_int32_accumulations(slices):
     """k = 19200 = 150 k-blocks: the weights with 7 or 8 digit pairs exceed the 1023 k-blocks one int32 accumulation may hold
     (128^2 * 128 * 1023 < 2^31), so they drain in two groups (the N = 32768 end state of BASELINE config 5 needs this)."""
@@ -86,7 +88,7 @@ def test_ozaki_long_k_needs_several_int32_accumulations(slices):
     native.ozaki_dgemm(0, 0, 1.0, A.cuda(), B.cuda(), 0.0, C, slices=slices)
     torch.cuda.synchronize()
     ref = A @ B.T
-    assert float((C.cpu() - ref).abs().max() / ref.abs().max()) < (1e-13 if slices == 8 else 2e-12)
+    assert float((C.cpu() - ref).abs().max() / ref.abs().max()) < (1e-13 if slices == 8 else 2e-12)       # (16 moduli: one accumulation per modulus)
     # worst case for the accumulators: every digit at its extreme value
     A = torch.full((m, k), -1.0, dtype=torch.float64)
     B = torch.full((n, k), -1.0, dtype=torch.float64)
@@ -106,7 +108,8 @@ def _block_lower(n, g, fill):
     return clean, dirty
 
 
-def test_ozaki_triangular_products_of_the_recursion():
+@pytest.mark.parametrize("slices", [8, 17])
+def test_ozaki_triangular_products_of_the_recursion(slices):
     """The five products of cholinv / potri with their k-ranges; the 128-blocks above the diagonal of the triangular operands
     hold NaN (scratch in the real recursion) and must never be read."""
     import torch
@@ -120,7 +123,7 @@ def test_ozaki_triangular_products_of_the_recursion():
 
     def run(ta, tb, alpha, A, B, beta, C, **kw):
         Cd = C.cuda()
-        native.ozaki_dgemm(ta, tb, alpha, A.cuda(), B.cuda(), beta, Cd, slices=8, **kw)
+        native.ozaki_dgemm(ta, tb, alpha, A.cuda(), B.cuda(), beta, Cd, slices=slices, **kw)
         torch.cuda.synchronize()
         return Cd.cpu()
 
@@ -152,11 +155,11 @@ def test_ozaki_triangular_products_of_the_recursion():
         close(got[sl, :(bi + 1) * 128], ref[sl, :(bi + 1) * 128], (M22c.abs().T @ M22c.abs()).max())
 
 
-@pytest.fixture
-def ozaki_on():
-    native.set_ozaki(256, 7)
+@pytest.fixture(params=[7, 16])
+def ozaki_on(request):
+    native.set_ozaki(256, request.param)          # 7 digits; 16 moduli (modular mode, the predictive products then use 18)
     yield
-    native.set_ozaki(0, 7)
+    native.set_ozaki(0, 8)
 
 
 @pytest.mark.parametrize("kind,noise,N,D", [("rbf", 1e-2, 1100, 5), ("mat52", 1e-6, 1500, 8), ("rbf", 1e-6, 900, 3)])

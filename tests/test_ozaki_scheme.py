@@ -94,3 +94,86 @@ def test_crt_product_accuracy(nmod, bits):
     if nmod == 16:
         # 16 moduli (16 int8 products) are at least as accurate as 7 balanced digits (28 products)
         assert np.abs(C - ref).max() <= 2 * np.abs(E.gemm_nt(A, B, 7) - ref).max() + 1e-300
+
+
+# ---- the engine's modular mode: its integer arithmetic (csrc/gpb_crt.cuh) compiled for the host, against the restatement above ---
+def _lib():
+    from gaussian_process_optimization_b200 import _lib as L
+    return L.load()
+
+
+def test_crt_operand_bits_agree_with_the_library():
+    lib = _lib()
+    for nmod in range(10, 19):
+        for k in (128, 129, 700, 1024, 4096, 16384, 32768, 130944):
+            assert lib.gpb_ozaki_crt_bits(nmod, k) == E.crt_bits(nmod, k), (nmod, k)
+    assert E.crt_bits(16, 16384) == 56 and E.crt_bits(17, 16384) == 59 and E.crt_bits(18, 16384) == 62
+
+
+def _host_residues(A, nmod, beta):
+    lib = _lib()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    planes = np.zeros((nmod,) + A.shape, dtype=np.int8)
+    scale = np.zeros(A.shape[0])
+    assert lib.gpb_ozaki_crt_host_residues(A.ctypes.data, A.shape[0], A.shape[1], nmod, beta, planes.ctypes.data, scale.ctypes.data) == 0
+    return planes, scale
+
+
+@pytest.mark.parametrize("nmod", [10, 16, 17, 18])
+def test_crt_library_residues_equal_the_restatement(nmod):
+    """dp4a-style residue extraction (two's-complement bytes weighted by 2^(8k) mod p, one multiply-high reduction) == Q mod p."""
+    rs = np.random.RandomState(nmod)
+    A = rs.randn(37, 300) * np.exp2(rs.randint(-30, 30, (37, 1)))
+    A[3] = 0.0
+    A[5, :7] = [1.0, -1.0, 0.5, -0.5, 2.0 ** -40, -2.0 ** -40, 0.0]
+    beta = E.crt_bits(nmod, 300)
+    planes, scale = _host_residues(A, nmod, beta)
+    Q, e = E.split_rows_integer(A, beta)
+    assert np.array_equal(scale, np.exp2(e[:, 0] - beta))
+    for i, p in enumerate(E.MODULI[:nmod]):
+        assert np.array_equal(planes[i].astype(np.int64), E._balanced_mod(Q, p)), p
+    # extreme magnitudes of the scaled integer, both signs
+    ext = np.array([[0.5 - 2.0 ** -54, -(0.5 - 2.0 ** -54), 2.0 ** -62, -2.0 ** -62, 0.25, -0.25, 0.4999, -0.4999]])
+    planes, _ = _host_residues(ext, nmod, 62)
+    Q, _ = E.split_rows_integer(ext, 62)
+    for i, p in enumerate(E.MODULI[:nmod]):
+        assert np.array_equal(planes[i].astype(np.int64), E._balanced_mod(Q, p)), p
+
+
+@pytest.mark.parametrize("nmod", [10, 11, 12, 13, 14, 15, 16, 17, 18])
+def test_crt_library_reconstruction_is_bit_identical_to_the_restatement(nmod):
+    """int32 sums -> balanced residues -> Garner digits (folded compile-time constants) -> grouped Horner: the library's host build of
+    the device code gives the same doubles as gemm_nt_crt, bit for bit."""
+    lib = _lib()
+    rs = np.random.RandomState(100 + nmod)
+    m, n, k = 24, 40, 1500
+    A = rs.randn(m, k) * np.exp2(rs.randint(-10, 10, (m, 1)))
+    B = rs.randn(n, k) * np.exp2(rs.randint(-10, 10, (n, 1)))
+    beta = E.crt_bits(nmod, k)
+    Ra, sa = _host_residues(A, nmod, beta)
+    Rb, sb = _host_residues(B, nmod, beta)
+    sums = np.stack([Ra[i].astype(np.int64) @ Rb[i].astype(np.int64).T for i in range(nmod)])
+    assert np.abs(sums).max() < 2 ** 31
+    sums = np.ascontiguousarray(sums.astype(np.int32))
+    X = np.zeros((m, n))
+    assert lib.gpb_ozaki_crt_host_combine(sums.ctypes.data, m * n, nmod, X.ctypes.data) == 0
+    C = X * (sa[:, None] * sb[None, :])
+    ref, beta2 = E.gemm_nt_crt(A, B, nmod)
+    assert beta2 == beta
+    assert np.array_equal(C, ref)
+    exact = (A.astype(np.longdouble) @ B.astype(np.longdouble).T).astype(np.float64)
+    scale = np.abs(A).max(1, keepdims=True) * np.abs(B).max(1, keepdims=True).T * k
+    assert np.all(np.abs(C - exact) <= 8 * scale * 2.0 ** -(beta - 1) + 4 * np.finfo(float).eps * np.abs(exact))
+
+
+def test_crt_library_reconstruction_at_the_int32_extremes():
+    """Residue of an int32 accumulation near +-2^31 (hi * (2^16 mod p) + lo, one reduction)."""
+    lib = _lib()
+    nmod = 16
+    s = np.array([2 ** 31 - 1, -2 ** 31 + 1, 2 ** 31 - 65536, -2 ** 31 + 65536, 65535, -65536, 0, 1, -1, 123456789, -987654321],
+                 dtype=np.int64)
+    # choose the same X for every modulus: sums_i = s (a consistent residue system of the integer s itself)
+    sums = np.ascontiguousarray(np.tile(s.astype(np.int32), (nmod, 1)))
+    X = np.zeros(len(s))
+    assert lib.gpb_ozaki_crt_host_combine(sums.ctypes.data, len(s), nmod, X.ctypes.data) == 0
+    assert np.array_equal(X, s.astype(np.float64))
