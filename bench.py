@@ -400,6 +400,12 @@ def bench_int8_engine(args, model, theta, dmma_s_per_eval, dgemm_peak_tflops):
         eight = {"ms_per_eval": t8 * 1e3, "value": 1.0 / t8, "speedup_vs_dmma_engine": dmma_s_per_eval / t8,
                  "agreement_with_dmma_engine": {"logL_rel": abs(logL8 - logL0) / abs(logL0),
                                                 "grad_rel_to_max": float(np.max(np.abs(g8 - g0)) / np.max(np.abs(g0)))}}
+        # modular (CRT) mode of the same engine: 16 moduli = 16 int8 products per fp64 product (56 bits per operand at k = 16384,
+        # where 7 digits = 28 products carry 55); the predictive products then use 18 moduli (62 bits) instead of 8 digits
+        try:
+            modular = bench_int8_modular(args, model, theta, (v, l, nz), dmma_s_per_eval, MIN_N, logL0, g0, shard, idx0, f0, df0)
+        except Exception as exc:                       # the experimental block must never take the headline line down with it
+            modular = {"error": repr(exc)}
         native.set_ozaki(MIN_N, SLICES)
         model.set_theta(v, l, nz)
         model.fit(True)
@@ -461,12 +467,76 @@ def bench_int8_engine(args, model, theta, dmma_s_per_eval, dgemm_peak_tflops):
             "agreement_with_dmma_engine": {"logL_rel": abs(logL1 - logL0) / abs(logL0),
                                            "grad_rel_to_max": float(np.max(np.abs(g1 - g0)) / np.max(np.abs(g0))), "info": int(info1)},
             "with_8_digits": eight,
+            "with_16_moduli": modular,
             "aux": acq,
             "roofline": {"bound": "tensor (int8, tcgen05 kind::i8)", "kernel": "ozaki_mma_kernel on an 8192^3 fp64-equivalent product (digit extraction included)",
                          "ms": best * 1e3, "effective_fp64_tflops": 2.0 * n ** 3 / best / 1e12, "achieved": int8_tops, "peak": lib_tops,
                          "unit": "TOP/s", "frac": int8_tops / lib_tops, "rel_err_vs_fp64_matmul": gemm_err,
                          "peak_source": "cuBLASLt int8 GEMM 8192^3 through torch._int_mm measured in this run (burst, best of 4); nominal dense int8 is 4500 TOP/s"},
             "note": "experimental, off by default (gpb_set_ozaki / GPB_OZAKI_MIN_N); the headline value, e2e and roofline above are the fp64 DMMA path"}
+
+
+def bench_int8_modular(args, model, theta, theta0, dmma_s_per_eval, min_n, logL0, g0, shard, idx0, f0, df0, nmod=16):
+    """The int8 engine in its modular mode (csrc/gpb_crt.cuh): evaluation time and agreement, the EI pass, one 8192^3 product."""
+    import torch
+    from gaussian_process_optimization_b200 import native
+    native.set_ozaki(min_n, nmod)
+    v, l, nz = theta0
+    for i in range(2):
+        model.set_theta(*theta(i))
+        model.fit(True)
+    model.set_theta(v, l, nz)
+    info, logL, g = model.fit(True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        model.set_theta(*theta(100 + i))
+        model.fit(True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / args.steps
+    model.set_theta(v, l, nz)
+    model.fit(True)
+    fmin = model.fmin()
+    model.acq_topk_full("EI", 0.01, fmin, shard[:4096], 5)                 # warm-up: cuts the residue planes of L^-1 once
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    vals1, idx1, pts1, f1, df1 = model.acq_topk_full("EI", 0.01, fmin, shard, 5)
+    c1.record()
+    torch.cuda.synchronize()
+    t_acq = c0.elapsed_time(c1) * 1e-3
+    n = 8192
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    B = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    C = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    best = 1e30
+    for i in range(5):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        native.ozaki_dgemm(0, 0, 1.0, A, B, 0.0, C, slices=nmod)
+        a1.record()
+        torch.cuda.synchronize()
+        if i >= 1:
+            best = min(best, a0.elapsed_time(a1) * 1e-3)
+    ref = A @ B.t()
+    gemm_err = float((C - ref).abs().max() / ref.abs().max())
+    del A, B, C, ref
+    flops = algorithmic_flops(N_TRAIN, DIM)
+    return {"ms_per_eval": t * 1e3, "value": 1.0 / t, "speedup_vs_dmma_engine": dmma_s_per_eval / t,
+            "algorithmic_tflops_fp64_equivalent": flops / t / 1e12,
+            "engine": {"min_n": min_n, "moduli": nmod, "int8_products_per_fp64_product": nmod,
+                       "bits_per_operand": native.ozaki_crt_bits(nmod, N_TRAIN)},
+            "agreement_with_dmma_engine": {"logL_rel": abs(logL - logL0) / abs(logL0),
+                                           "grad_rel_to_max": float(np.max(np.abs(g - g0)) / np.max(np.abs(g0))), "info": int(info)},
+            "aux": {"metric": "ei_value_gradient_candidates_per_s", "value": shard.shape[0] / t_acq, "unit": "candidates/s",
+                    "candidates": int(shard.shape[0]), "seconds": t_acq, "moduli": 18,
+                    "agreement_with_dmma_engine": {"same_top5": bool(list(idx0) == list(idx1)),
+                                                   "f_rel_to_max": float(np.max(np.abs(f1.cpu().numpy() - f0)) / np.max(np.abs(f0))),
+                                                   "df_rel_to_max": float(np.max(np.abs(df1.cpu().numpy() - df0)) / np.max(np.abs(df0)))}},
+            "product_8192": {"ms": best * 1e3, "effective_fp64_tflops": 2.0 * n ** 3 / best / 1e12, "rel_err_vs_fp64_matmul": gemm_err,
+                             "kernels": "oz_absmax / oz_split (residues), ozaki_mma_kernel (16 accumulations), oz_crt_combine_kernel"}}
 
 
 def bench_other_configs(model16k):

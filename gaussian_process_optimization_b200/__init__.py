@@ -26,8 +26,10 @@ __version__ = "0.1.0"
 def set_int8_engine(min_n=8192, digits=8):
     """Experimental, off by default: route the products of the factorisation with at least `min_n` rows (and the predictive products of
     candidate blocks of >= 1024 rows) through the int8 tensor-core engine (csrc/gpb_ozaki.cu).  min_n = 0 switches it off.  digits: 8
-    (indistinguishable from the fp64 engine) or 7 (25% faster, agrees to ~1e-13).  Results stay within the tolerances of tests/, but
-    are not bitwise those of the fp64 engine."""
+    (indistinguishable from the fp64 engine) or 7 (25% faster, agrees to ~1e-13); 10..18 selects the engine's modular mode with that
+    many moduli (16: one int8 product per modulus instead of 28 digit-pair products, 56 bits per operand at N = 16384 -- the fastest
+    setting; the predictive products then use 18 moduli).  Results stay within the tolerances of tests/, but are not bitwise those of
+    the fp64 engine."""
     native.set_ozaki(min_n, digits)
 
 GPy = _NS(

@@ -182,8 +182,15 @@ def ozaki_dgemm(ta, tb, alpha, A, B, beta, C, slices=0, tri_out=0, klo_mode=0, k
 
 
 def set_ozaki(min_n, slices=8):
-    """Experimental: products of the factorisation with >= min_n rows go through the int8 engine (0 = off, the default)."""
+    """Experimental: products of the factorisation with >= min_n rows go through the int8 engine (0 = off, the default).
+    slices 1..8: balanced radix-256 digits per operand (S (S + 1) / 2 int8 products); 10..18: the modular mode, that many moduli
+    (one int8 product each, CRT reconstruction; csrc/gpb_crt.cuh)."""
     check(_lib.load().gpb_set_ozaki(int(min_n), int(slices)), "set_ozaki")
+
+
+def ozaki_crt_bits(nmod, k):
+    """Bits per operand the modular mode of the int8 engine carries with nmod moduli at inner dimension k."""
+    return int(_lib.load().gpb_ozaki_crt_bits(int(nmod), int(k)))
 
 
 def gemm_config(cfg):
