@@ -72,16 +72,32 @@ GPB_HD int reduce_balanced(int t, int p, uint32_t mg, int bias) {
   const uint32_t q = mulhi_u32(u, mg);
   return (int)(u - q * (uint32_t)p) - p / 2;
 }
+// The same in two instructions: tb = t + K p >= 0 (the multiple of p is folded into the sum by the caller), q = floor((tb + p / 2) / p)
+// as the high word of tb * magic + (p / 2) * magic (one wide multiply-add), and tb - q p is the balanced residue.
+GPB_HD constexpr int multiple_for(int p, int lim) { return ((lim + p - 1) / p) * p; }
+GPB_HD constexpr uint64_t half_magic(int p) { return (uint64_t)(p / 2) * magic(p); }
+GPB_HD int reduce_folded(int tb, int p, uint32_t mg, uint64_t hmg) {
+  const uint32_t q = (uint32_t)(((uint64_t)(uint32_t)tb * mg + hmg) >> 32);
+  return tb - (int)(q * (uint32_t)p);
+}
+GPB_HD uint32_t pack4(int r0, int r1, int r2, int r3) {                   // the low bytes of four residues
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(__byte_perm((uint32_t)r0, (uint32_t)r1, 0x0040), __byte_perm((uint32_t)r2, (uint32_t)r3, 0x0040), 0x5410);
+#else
+  return ((uint32_t)r0 & 0xFFu) | (((uint32_t)r1 & 0xFFu) << 8) | (((uint32_t)r2 & 0xFFu) << 16) | (((uint32_t)r3 & 0xFFu) << 24);
+#endif
+}
 
 // ---- per-modulus parameters for the loops that run over the moduli at run time (residue extraction, the drains) -----------
 struct ModParams {
   int p;
   uint32_t mg;
-  int bias_res;      // residue extraction: |sum of 8 byte products - sign term| <= 8 * 255 * 128 + 128
-  int bias_acc;      // drains: |hi * c16 + lo| <= 2^15 * 128 + 2^16
+  int init_res;      // residue extraction: (a multiple of p >= 8 * 255 * 128 + 128) - (2^62 mod p): the operand is biased by 2^62
+  int kp_acc;        // drains: a multiple of p >= |hi * c16 + lo|, <= 2^15 * 128 + 2^16
   int c16;           // 2^16 mod p, balanced
-  int w64;           // 2^64 mod p, balanced
   uint32_t w_lo, w_hi;   // 2^(8 k) mod p, balanced, k = 0..3 / 4..7, packed as signed bytes
+  int pad;
+  uint64_t hmg;      // (p / 2) * magic
 };
 constexpr int LIM_RES = 8 * 255 * 128 + 128, LIM_ACC = (1 << 22) + (1 << 16);
 GPB_HD constexpr ModParams mod_params(int i) {
@@ -89,10 +105,10 @@ GPB_HD constexpr ModParams mod_params(int i) {
   ModParams m = {};
   m.p = p;
   m.mg = magic(p);
-  m.bias_res = bias_for(p, LIM_RES);
-  m.bias_acc = bias_for(p, LIM_ACC);
+  m.init_res = multiple_for(p, LIM_RES) - pow2_mod(62, p);
+  m.kp_acc = multiple_for(p, LIM_ACC);
   m.c16 = pow2_mod(16, p);
-  m.w64 = pow2_mod(64, p);
+  m.hmg = half_magic(p);
   uint32_t lo = 0, hi = 0;
   for (int k = 0; k < 4; ++k) {
     lo |= ((uint32_t)pow2_mod(8 * k, p) & 0xFFu) << (8 * k);
@@ -119,17 +135,19 @@ GPB_HD int dot_u8_s8(uint32_t a, uint32_t b, int c) {                      // su
   return c;
 #endif
 }
-// balanced residue of the 64-bit integer q: its two's-complement bytes weighted by 2^(8 k) mod p, minus 2^64 mod p if q < 0
-GPB_HD int residue_of(long long q, const ModParams &m) {
-  const uint64_t u = (uint64_t)q;
-  int t = dot_u8_s8((uint32_t)u, m.w_lo, q < 0 ? -m.w64 : 0);
+// balanced residue of the integer q, |q| <= 2^61, given u = q + 2^62 > 0: the bytes of u weighted by 2^(8 k) mod p, minus 2^62 mod p
+// (no sign handling; the constant sits in the accumulator the first dp4a starts from)
+GPB_HD uint64_t bias_operand(long long q) { return (uint64_t)q + (1ull << 62); }
+GPB_HD int residue_of_biased(uint64_t u, const ModParams &m) {
+  int t = dot_u8_s8((uint32_t)u, m.w_lo, m.init_res);
   t = dot_u8_s8((uint32_t)(u >> 32), m.w_hi, t);
-  return reduce_balanced(t, m.p, m.mg, m.bias_res);
+  return reduce_folded(t, m.p, m.mg, m.hmg);
 }
-// balanced residue of an int32 accumulation s
+GPB_HD int residue_of(long long q, const ModParams &m) { return residue_of_biased(bias_operand(q), m); }
+// balanced residue of an int32 accumulation s = hi 2^16 + lo
 GPB_HD int residue_of_sum(int s, const ModParams &m) {
-  const int t = (s >> 16) * m.c16 + (s & 0xFFFF);
-  return reduce_balanced(t, m.p, m.mg, m.bias_acc);
+  const int t = (s >> 16) * m.c16 + ((s & 0xFFFF) + m.kp_acc);
+  return reduce_folded(t, m.p, m.mg, m.hmg);
 }
 
 // ---- reconstruction (compile-time moduli) -----------------------------------------------------------------------------------
@@ -138,8 +156,36 @@ template <int I> struct ECoef { static constexpr int value = e_coef(I); };
 template <int I> struct Mod {
   static constexpr int p = modulus(I);
   static constexpr uint32_t mg = magic(modulus(I));
-  static constexpr int bias = bias_for(modulus(I), (I + 1) * 128 * 128);
+  static constexpr int kp = multiple_for(modulus(I), (I + 1) * 128 * 128);
+  static constexpr uint64_t hmg = half_magic(modulus(I));
 };
+// -d_ij for j = 4 K .. 4 K + 3 (zero from j = I on) as signed bytes: the Garner sum as dp4a over packed digits (|d| <= 127: p_i odd)
+GPB_HD constexpr uint32_t d_pack_neg(int i, int k) {
+  uint32_t w = 0;
+  for (int b = 0; b < 4; ++b) {
+    const int j = 4 * k + b;
+    if (j < i) w |= ((uint32_t)(-d_coef(i, j)) & 0xFFu) << (8 * b);
+  }
+  return w;
+}
+template <int I, int K> struct DPackNeg { static constexpr uint32_t value = d_pack_neg(I, K); };
+GPB_HD int dot_s8_s8(uint32_t a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  for (int k = 0; k < 4; ++k) c += (int)(int8_t)((a >> (8 * k)) & 0xFFu) * (int)(int8_t)((b >> (8 * k)) & 0xFFu);
+  return c;
+#endif
+}
+GPB_HD uint32_t insert_byte(uint32_t w, int v, int b) {                   // byte b of w := low byte of v (b is a compile-time constant)
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(w, (uint32_t)v, b == 0 ? 0x3214 : b == 1 ? 0x3240 : b == 2 ? 0x3410 : 0x4210);
+#else
+  return (w & ~(0xFFu << (8 * b))) | (((uint32_t)v & 0xFFu) << (8 * b));
+#endif
+}
 
 template <int I, int... J> GPB_HD int garner_sum(const int *v, std::integer_sequence<int, J...>) {
   return (0 + ... + (v[J] * DCoef<I, J>::value));
@@ -148,10 +194,27 @@ template <int I, int NMOD> GPB_HD void garner_steps(const int *r, int *v) {
   if constexpr (I == 0) {
     v[0] = r[0];
   } else {
-    const int t = r[I] * ECoef<I>::value - garner_sum<I>(v, std::make_integer_sequence<int, I>{});
-    v[I] = reduce_balanced(t, Mod<I>::p, Mod<I>::mg, Mod<I>::bias);
+    const int tb = (r[I] * ECoef<I>::value + Mod<I>::kp) - garner_sum<I>(v, std::make_integer_sequence<int, I>{});
+    v[I] = reduce_folded(tb, Mod<I>::p, Mod<I>::mg, Mod<I>::hmg);
   }
   if constexpr (I + 1 < NMOD) garner_steps<I + 1, NMOD>(r, v);
+}
+// the same digits with the sums as dp4a over the digits found so far, packed four to a word (vp: (NMOD + 3) / 4 words, zeroed)
+template <int I, int... K> GPB_HD int garner_sum_packed(const uint32_t *vp, int acc, std::integer_sequence<int, K...>) {
+  ((acc = dot_s8_s8(vp[K], DPackNeg<I, K>::value, acc)), ...);
+  return acc;
+}
+template <int I, int NMOD> GPB_HD void garner_steps_packed(const int *r, int *v, uint32_t *vp) {
+  if constexpr (I == 0) {
+    v[0] = r[0];
+  } else {
+    const int tb = garner_sum_packed<I>(vp, r[I] * ECoef<I>::value + Mod<I>::kp, std::make_integer_sequence<int, (I + 3) / 4>{});
+    v[I] = reduce_folded(tb, Mod<I>::p, Mod<I>::mg, Mod<I>::hmg);
+  }
+  if constexpr (I + 1 < NMOD) {
+    vp[I / 4] = insert_byte(vp[I / 4], v[I], I % 4);
+    garner_steps_packed<I + 1, NMOD>(r, v, vp);
+  }
 }
 
 GPB_HD double mul_rn(double a, double b) {
@@ -187,9 +250,14 @@ template <int G0, int NMOD> GPB_HD double horner(const int *v, double x) {
   else return x;
 }
 // the integer with balanced residues r[0 .. NMOD) (|X| < P / 2), rounded to fp64
-template <int NMOD> GPB_HD double reconstruct(const int *r) {
+template <int NMOD, bool PACKED = false> GPB_HD double reconstruct(const int *r) {
   int v[NMOD];
-  garner_steps<0, NMOD>(r, v);
+  if constexpr (PACKED) {
+    uint32_t vp[(NMOD + 3) / 4] = {};
+    garner_steps_packed<0, NMOD>(r, v, vp);
+  } else {
+    garner_steps<0, NMOD>(r, v);
+  }
   constexpr int G = (NMOD + 2) / 3;
   double x = (double)group_value<G - 1, NMOD>(v);
   if constexpr (G > 1) x = horner<G - 2, NMOD>(v, x);

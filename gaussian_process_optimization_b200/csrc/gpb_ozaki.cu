@@ -360,14 +360,10 @@ ozaki_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             uint32_t wd[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              uint32_t a = 0, b = 0;
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                a |= ((uint32_t)crt::residue_of_sum((int)v[j + t], mp) & 0xFFu) << (8 * t);
-                b |= ((uint32_t)crt::residue_of_sum((int)v2[j + t], mp) & 0xFFu) << (8 * t);
-              }
-              wd[j / 4] = a;
-              wd[8 + j / 4] = b;
+              wd[j / 4] = crt::pack4(crt::residue_of_sum((int)v[j], mp), crt::residue_of_sum((int)v[j + 1], mp),
+                                     crt::residue_of_sum((int)v[j + 2], mp), crt::residue_of_sum((int)v[j + 3], mp));
+              wd[8 + j / 4] = crt::pack4(crt::residue_of_sum((int)v2[j], mp), crt::residue_of_sum((int)v2[j + 1], mp),
+                                         crt::residue_of_sum((int)v2[j + 2], mp), crt::residue_of_sum((int)v2[j + 3], mp));
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) dst[(c0 / 16 + u) * 32] = make_uint4(wd[4 * u], wd[4 * u + 1], wd[4 * u + 2], wd[4 * u + 3]);
@@ -553,19 +549,16 @@ oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int
     // modular mode: q = rint(x 2^(beta - e)), |q| <= 2^(beta - 1) <= 2^61; plane i holds the balanced residue q mod p_i
     if (seg == 0) scale[i0 + r] = ldexp(1.0, e - beta);
     const double upm = ldexp(1.0, beta - e);
-    long long qm[16];
+    unsigned long long qm[16];                          // q + 2^62 > 0: no sign handling in the residues
 #pragma unroll
-    for (int j = 0; j < 16; ++j) qm[j] = __double2ll_rn(sm[r][seg + j] * upm);
+    for (int j = 0; j < 16; ++j) qm[j] = crt::bias_operand(__double2ll_rn(sm[r][seg + j] * upm));
     for (int i = 0; i < nmod; ++i) {
       const crt::ModParams mp = c_mods.m[i];
       uint32_t wds[4];
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint32_t wv = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) wv |= ((uint32_t)crt::residue_of(qm[q4 * 4 + b], mp) & 0xFFu) << (8 * b);
-        wds[q4] = wv;
-      }
+      for (int q4 = 0; q4 < 4; ++q4)
+        wds[q4] = crt::pack4(crt::residue_of_biased(qm[q4 * 4], mp), crt::residue_of_biased(qm[q4 * 4 + 1], mp),
+                             crt::residue_of_biased(qm[q4 * 4 + 2], mp), crt::residue_of_biased(qm[q4 * 4 + 3], mp));
       *reinterpret_cast<uint4 *>(out + i * plane) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
     }
     return;
@@ -597,7 +590,7 @@ oz_split_kernel(const double *__restrict__ P, int ld, int R, int K, int tri, int
 // One thread per (row, 4 columns): reads one 32-bit word (four int8 residues) per modulus from the planes the drains parked (a warp
 // reads 128 contiguous bytes per modulus), rebuilds the four integers (crt::reconstruct: Garner's mixed-radix digits from
 // compile-time constants, Horner in fp64), applies the row / column scales, alpha and beta and writes 32 bytes of C.
-template <int NMOD>
+template <int NMOD, bool PACKED>
 __global__ void __launch_bounds__(256) oz_crt_combine_kernel(const Params p) {
   const unsigned g = blockIdx.x * 256u + threadIdx.x;
   const int j4 = g & 3, lane = (g >> 2) & 31, chunk = (g >> 7) & 15, w8 = (g >> 11) & 7, tile = (int)(g >> 14);
@@ -621,7 +614,7 @@ __global__ void __launch_bounds__(256) oz_crt_combine_kernel(const Params p) {
     int r[NMOD];
 #pragma unroll
     for (int i = 0; i < NMOD; ++i) r[i] = (int)(int8_t)((u[i] >> (8 * b)) & 0xFFu);
-    o[b] = crt::reconstruct<NMOD>(r) * (ra * p.rb[c + b]);
+    o[b] = crt::reconstruct<NMOD, PACKED>(r) * (ra * p.rb[c + b]);
   }
   if (p.beta != 0.0) {
     const double2 c0 = *reinterpret_cast<const double2 *>(Cp), c1 = *reinterpret_cast<const double2 *>(Cp + 2);
@@ -633,8 +626,12 @@ __global__ void __launch_bounds__(256) oz_crt_combine_kernel(const Params p) {
   *reinterpret_cast<double2 *>(Cp) = make_double2(o[0], o[1]);
   *reinterpret_cast<double2 *>(Cp + 2) = make_double2(o[2], o[3]);
 }
+// GPB_OZAKI_COMBINE=0: the Garner sums as one multiply-add per digit; 1 (default): as dp4a over packed digits (same integers)
 template <int NMOD> static void launch_combine(const Params &p, cudaStream_t st) {
-  oz_crt_combine_kernel<NMOD><<<p.tiles_m * p.tiles_n * 64, 256, 0, st>>>(p);
+  static int packed = -1;
+  if (packed < 0) { const char *e = getenv("GPB_OZAKI_COMBINE"); packed = e ? atoi(e) : 1; }
+  if (packed) oz_crt_combine_kernel<NMOD, true><<<p.tiles_m * p.tiles_n * 64, 256, 0, st>>>(p);
+  else oz_crt_combine_kernel<NMOD, false><<<p.tiles_m * p.tiles_n * 64, 256, 0, st>>>(p);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------------
@@ -891,7 +888,10 @@ template <int NMOD> static void host_combine(const int *sums, size_t count, doub
   for (size_t e = 0; e < count; ++e) {
     int r[NMOD];
     for (int m = 0; m < NMOD; ++m) r[m] = crt::residue_of_sum(sums[(size_t)m * count + e], tab.m[m]);
-    X[e] = crt::reconstruct<NMOD>(r);
+    X[e] = crt::reconstruct<NMOD, true>(r);
+    // both forms of the Garner sums give the same integers; NaN marks a disagreement for the tests
+    const double x2 = crt::reconstruct<NMOD, false>(r);
+    if (x2 != X[e]) X[e] = nan("");
   }
 }
 // sums: [nmod][count] exact int32 accumulations of the residue products -> X[count] = the integer products, rounded to fp64
