@@ -25,6 +25,10 @@
 // CTA pairs (cluster of 2): two tiles with a common k-range fetch half of the shared operand tile each and multicast it into both
 // shared memories; the MMA warps release a stage in both CTAs (tcgen05.commit ... multicast::cluster).
 //
+// Modular mode (S = 10 .. 18 planes = moduli instead of digits; gpb_crt.cuh): the planes hold the balanced residues of the scaled integer
+// operand modulo pairwise coprime p_i <= 256, the weight loop runs over the moduli with ONE product each (16 instead of 28), every drain
+// parks its sums reduced modulo p_i as int8, and oz_crt_combine_kernel rebuilds the integer product by the Chinese remainder theorem.
+//
 // Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocation + MMA issue (one lane),
 // warps 2-9 = epilogue (TMEM lane quarter = warp % 4, accumulator = (warp - 2) / 4).  3-stage smem ring of {A digit tile
 // 256 x 128 B, B digit tile 256 x 128 B}, 128-byte swizzle, K-major.

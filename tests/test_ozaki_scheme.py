@@ -53,7 +53,7 @@ def test_int32_accumulation_bound():
     assert 128 * 128 * 128 * 1024 >= 2 ** 31
 
 
-# ---- modular splitting (studied for the next round; CPU emulation only) ----------------------------------------------------------
+# ---- modular splitting (the engine's modular mode): the restatement itself --------------------------------------------------------
 def test_moduli_are_pairwise_coprime_and_fit_int8():
     from math import gcd
     M = E.MODULI
