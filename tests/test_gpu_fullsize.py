@@ -146,7 +146,8 @@ def test_int8_engine_at_the_headline_size(fitted):
     Xc = np.random.RandomState(99).uniform(0, 1, (2 ** 13, D))
     vals0, idx0, pts0, f0, _ = m.acq_topk_full("EI", 0.01, fmin0, Xc, 5, with_gradients=False)
     try:
-        for digits, tl, tg in ((8, 1e-12, 1e-10), (7, 1e-10, 1e-8)):
+        # (18 and 16: the engine's modular mode with that many moduli -- 62 and 56 bits per operand, one int8 product per modulus)
+        for digits, tl, tg in ((18, 1e-12, 1e-10), (16, 1e-10, 1e-8), (8, 1e-12, 1e-10), (7, 1e-10, 1e-8)):
             native.set_ozaki(8192, digits)
             m.set_theta(v, ls, noise)
             info, l1, g1 = m.fit(True)
