@@ -28,8 +28,7 @@ GPB_HD constexpr int modulus(int i) {
   constexpr int t[MAXMOD] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191, 181};
   return t[i];
 }
-GPB_HD constexpr int half_of(int p) { return p / 2; }                    // balanced range [-(p / 2), (p - 1) / 2]
-GPB_HD constexpr int balanced(long long x, int p) {
+GPB_HD constexpr int balanced(long long x, int p) {                      // representative in [-(p / 2), (p - 1) / 2]
   long long r = x % p;
   if (r < 0) r += p;
   return (int)(r >= (p + 1) / 2 ? r - p : r);
@@ -51,29 +50,14 @@ GPB_HD constexpr int d_coef(int i, int j) {
   return balanced((long long)inverse_mod(prefix_mod(i, modulus(i)), modulus(i)) * prefix_mod(j, modulus(i)), modulus(i));
 }
 GPB_HD constexpr uint32_t magic(int p) { return (uint32_t)((1ull << 32) / (unsigned)p) + 1u; }   // floor(u / p) = mulhi(u, magic) for u < 2^24
-// bias = p / 2 + (a multiple of p >= lim): u = t + bias >= 0 for t >= -lim, and (u mod p) - p / 2 is the balanced residue of t
-GPB_HD constexpr int bias_for(int p, int lim) { return p / 2 + ((lim + p - 1) / p) * p; }
 GPB_HD constexpr int pow2_mod(int bits, int p) {                          // 2^bits mod p, balanced
   long long r = 1 % p;
   for (int b = 0; b < bits; ++b) r = (r * 2) % p;
   return balanced(r, p);
 }
 
-GPB_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
-#if defined(__CUDA_ARCH__)
-  return __umulhi(a, b);
-#else
-  return (uint32_t)(((uint64_t)a * b) >> 32);
-#endif
-}
-// balanced residue of t, |t| <= lim (bias = bias_for(p, lim) and t + bias < 2^24)
-GPB_HD int reduce_balanced(int t, int p, uint32_t mg, int bias) {
-  const uint32_t u = (uint32_t)(t + bias);
-  const uint32_t q = mulhi_u32(u, mg);
-  return (int)(u - q * (uint32_t)p) - p / 2;
-}
-// The same in two instructions: tb = t + K p >= 0 (the multiple of p is folded into the sum by the caller), q = floor((tb + p / 2) / p)
-// as the high word of tb * magic + (p / 2) * magic (one wide multiply-add), and tb - q p is the balanced residue.
+// Balanced residue of t in two instructions: tb = t + K p >= 0 (the multiple of p is folded into the sum by the caller, tb + p / 2 < 2^24),
+// q = floor((tb + p / 2) / p) as the high word of tb * magic + (p / 2) * magic (one wide multiply-add), and tb - q p is the residue.
 GPB_HD constexpr int multiple_for(int p, int lim) { return ((lim + p - 1) / p) * p; }
 GPB_HD constexpr uint64_t half_magic(int p) { return (uint64_t)(p / 2) * magic(p); }
 GPB_HD int reduce_folded(int tb, int p, uint32_t mg, uint64_t hmg) {

@@ -6,7 +6,8 @@ The emulation is simulated EXACTLY in fp64 on the CPU: the digit matrices are sm
 fp64 (k * 127^2 < 2^53), which is what int8 x int8 -> int32 tensor-core products would return.  The recursion, leaves
 (LAPACK on 128 x 128 blocks) and the downstream formulas are this repo's; the comparison target is the oracle (LAPACK path).
 
-    python scripts/ozaki_numerics_study.py [N]        # writes profiles/r1i_ozaki_numerics_study.json
+    python scripts/ozaki_numerics_study.py [N]        # writes profiles/r1k_ozaki_numerics_study.json (r1i: before the engine's
+                                                      # modular mode existed; r1k: with its operand bits and evaluation order)
 """
 import json
 import os
@@ -42,7 +43,7 @@ def make_gemm_balanced(S):
 
 
 def make_gemm(S):
-    if S >= 100:                      # modular splitting with S - 100 moduli (studied for the next round, CPU emulation only)
+    if S >= 100:                      # modular splitting with S - 100 moduli (the engine's modular mode, csrc/gpb_crt.cuh)
         return lambda A, B: E.gemm_nt_crt(A, B, S - 100)[0]
     if S < 0:
         return make_gemm_balanced(-S)
@@ -128,7 +129,8 @@ def main():
                 case["S%d" % S] = {"error": str(ex)}
             print(kind, noise, "S=%d" % S, case["S%d" % S], flush=True)
         out["%s_noise%g" % (kind, noise)] = case
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "r1i_ozaki_numerics_study.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles",
+                        os.environ.get("STUDY_OUT", "r1k_ozaki_numerics_study.json"))
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
 

@@ -177,3 +177,16 @@ def test_crt_library_reconstruction_at_the_int32_extremes():
     X = np.zeros(len(s))
     assert lib.gpb_ozaki_crt_host_combine(sums.ctypes.data, len(s), nmod, X.ctypes.data) == 0
     assert np.array_equal(X, s.astype(np.float64))
+
+
+def test_set_ozaki_accepts_digits_or_moduli_only():
+    """slices 1..8 = digits, 10..18 = moduli (modular mode); anything else is refused at the C ABI (no GPU needed)."""
+    lib = _lib()
+    try:
+        for s in (1, 7, 8, 10, 16, 18):
+            assert lib.gpb_set_ozaki(8192, s) == 0
+        for s in (0, 9, 19, -3):
+            assert lib.gpb_set_ozaki(8192, s) != 0
+        assert lib.gpb_set_ozaki(-1, 8) != 0
+    finally:
+        assert lib.gpb_set_ozaki(0, 8) == 0
