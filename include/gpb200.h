@@ -170,7 +170,8 @@ int gpb_profile_gemm_collect(double *ms, double *flops, long long *launches);
 int gpb_profile_gemm_last(double *ms, double *flops);
 
 /* ---- experimental: fp64 products on the INT8 tensor cores (Ozaki scheme; csrc/gpb_ozaki.cu) ------------------------- */
-/* C = alpha op(A) op(B)^T + beta C like gpb_dgemm, computed as `slices` (0 = default 8 = the maximum; 7 is 25% faster and still within the parity bars of tests/) balanced radix-256 digits per operand and
+/* C = alpha op(A) op(B)^T + beta C like gpb_dgemm, computed as `slices` (0 = the configured default, initially 8 = the maximum number
+ * of digits; 7 is 25% faster and still within the parity bars of tests/; 10..18 = the modular mode described below, k <= 130944) balanced radix-256 digits per operand and
  * slices (slices + 1) / 2 exact int8 x int8 -> int32 products on tcgen05 (kind::i8, TMEM accumulators, TMA operands), recombined
  * in fp64.  tri_out / klo_mode / khi_mode: lower-tile output and per-tile k-ranges at 128 granularity (0 / 0 / 0 = plain product);
  * tri_a / tri_b: 0 = full operand, 1 = only the 128-blocks with k-block <= row-block are valid, 2 = k-block >= row-block.
