@@ -3,27 +3,53 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-Metric (BASELINE.json): NLL+grad evals/s (N=16384, D=16, RBF-ARD, fp64).  One step = one pass of the hot path
-(K build -> Ky -> Cholesky + inverse -> alpha -> log-likelihood -> all D+2 gradients) over the synthetic data of SURVEY.md 8(d).
+Metric (BASELINE.json): "NLL+grad evals/s (N=16k, RBF-ARD, fp64); EI candidates/s at 1/2/4/8 GPU".  One step = one pass of the
+hot path (K build -> Ky -> Cholesky + inverse -> alpha -> log-likelihood -> all D+2 gradients) over the synthetic data of
+SURVEY.md 8(d).
 
   value     evals/s with X, Y resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e       the same through the host-buffer C-ABI call sequence (set_data: H2D of X, Y; set_theta; fit; D2H of D+3 doubles)
   roofline  the dominant kernel (DMMA GEMM engine): algorithmic N^3 flops per eval / its summed launch time per eval,
             against a cuBLAS DGEMM 8192^3 rate measured in the same process (MEASURED_PEAKS.json holds no fp64 figure)
-  cpu_baseline  the CPU oracle (oracle/gp_oracle.py, NumPy/SciPy + the reference's own C helper) on the box's host cores
-  aux       EI value+gradient candidates/s (config 4), candidates sharded over the ranks, top-5 all-gathered
+  cpu_baseline  the CPU oracle (oracle/gp_oracle.py, NumPy/SciPy + the reference's own C helper) on the box's host cores:
+            ONE REAL evaluation at N=16384 (no extrapolation), all host threads pinned explicitly
+  config.ei_*   the second half of the metric (BASELINE config 4): EI value + gradient + top-5 over a FIXED total of 2^20
+            candidates split over the ranks (strong scaling), per-shard top-5 all-gathered on the device inside the timed region,
+            the cost of getting the fitted state onto every rank (refit everywhere vs NCCL broadcast) reported beside it, and
+            GPyOpt's real anchor-scoring call (1000 candidates, anchor_points_generator.py:87) at the same N
 
 Multi-GPU: the N x N factorisation stays on one GPU (north_star) -> NLL evals are independent replicas (weak scaling);
-the acquisition shards its candidate set.  `--impl reference` times the CPU oracle (rank 0 only).
+the acquisition shards its candidate set (strong scaling, reported in config.ei_*).
+`--impl reference` times the CPU oracle (rank 0 only): real evaluations at the full size, as many as fit its time budget.
 """
-import argparse
-import json
 import os
 import sys
-import threading
-import time
 
-import numpy as np
+
+def _pin_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1, which OpenBLAS and libgomp read when they are loaded: the CPU legs would
+    run on one core.  Give them every core this process may use -- before NumPy / SciPy / the reference's C helper are imported."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    # GPU arm under torchrun (N > 1): no CPU leg runs there, leave the launcher's setting alone (N ranks x all cores would
+    # oversubscribe the host)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not any("reference" in a for a in sys.argv[1:]):
+        return cores
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)
+    return cores
+
+
+HOST_CORES = _pin_host_threads()
+
+import argparse   # noqa: E402
+import json       # noqa: E402
+import threading  # noqa: E402
+import time       # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -33,6 +59,18 @@ KIND = "rbf"
 METRIC = "nll_grad_evals_per_s"
 UNIT = "evals/s"
 WORKLOAD = "GPRegression RBF-ARD N=16384 D=16 fp64 log_likelihood+gradients (SURVEY 8d headline)"
+EI_WORKLOAD = ("AcquisitionEI value+gradient+top-5 (BASELINE config 4): Matern52-ARD N=16384 D=16 noise 1e-6 model, 2^20 candidates "
+               "(chunk 0 of SURVEY 8d) split over the ranks")
+EI_TOTAL = 2 ** 20
+EI_KIND, EI_NOISE = "mat52", 1e-6
+N_ANCHOR_CANDIDATES = 1000        # GPyOpt's real anchor-scoring call (anchor_points_generator.py:87, random_design.py:56-77)
+
+
+def base_config(world):
+    """The keys both arms print (the driver compares the two config objects): workload names only, no measured values."""
+    return {"workload": WORKLOAD, "N": N_TRAIN, "D": DIM, "kernel": "RBF-ARD", "noise": 1e-2,
+            "ei_workload": EI_WORKLOAD, "ei_total_candidates": EI_TOTAL, "ei_model": "Matern52-ARD noise 1e-6",
+            "anchor_candidates": N_ANCHOR_CANDIDATES}
 
 
 def synth(N, D, seed=1234):
@@ -53,62 +91,127 @@ def algorithmic_flops(N, D):
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU legs (oracle): the only place bench.py executes oracle/
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_eval_time(N, D, kind=KIND):
-    """One oracle NLL+grad evaluation at (N, D); returns (total s, cubic LAPACK part s)."""
+def _blas_threads():
+    """Pin every BLAS / OpenMP pool to HOST_CORES at run time as well (the environment alone is not enough when a pool was
+    initialised earlier) and report what is actually in force."""
+    import threadpoolctl
+    try:
+        threadpoolctl.threadpool_limits(limits=HOST_CORES)
+    except Exception:
+        pass
+    return int(max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1]))
+
+
+def cpu_eval(N, D, kind=KIND, noise=1e-2, keep_state=False):
+    """One oracle NLL+grad evaluation at (N, D), every step of GP.parameters_changed (core/gp.py:258-271) as the reference runs
+    it: K, pdinv INCLUDING the dtrtri whose result exact inference never uses (linalg.py:209), dpotrs, dL_dK, the kernel gradient
+    reductions with the reference's own compiled C loop.  -> (total s, cubic LAPACK part s, state or None)."""
     from oracle import gp_oracle as O
     X, Y, ls = synth(N, D)
     t0 = time.perf_counter()
     Kmat = O.K(kind, X, None, 1.0, ls, True)
     Ky = Kmat.copy()
-    Ky[np.diag_indices_from(Ky)] += 1e-2 + 1e-8
+    Ky[np.diag_indices_from(Ky)] += noise + 1e-8
     t1 = time.perf_counter()
-    Wi, LW, _, logdet = O.pdinv(Ky, with_Li=True)      # the reference's pdinv includes the unused dtrtri (linalg.py:209)
+    Wi, LW, _, logdet = O.pdinv(Ky, with_Li=True)
     alpha, _ = O.dpotrs(LW, Y, lower=1)
     t2 = time.perf_counter()
     dL_dK = 0.5 * (O.tdot(alpha) - Wi)
     O.update_gradients_full(kind, dL_dK, X, None, 1.0, ls, True, native=O.ref_native() is not None)
     t3 = time.perf_counter()
-    return t3 - t0, t2 - t1
+    state = None
+    if keep_state:
+        state = {"post": O.Posterior(LW, alpha, Kmat, Wi), "X": X, "ls": ls, "kind": kind, "noise": noise}
+    return t3 - t0, t2 - t1, state
 
 
-def cpu_baseline(sample_n=4096):
-    import threadpoolctl
-    cores = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1])
-    cpu_eval_time(1024, DIM)  # warm up BLAS threads
-    total, cubic = cpu_eval_time(sample_n, DIM)
-    scale = N_TRAIN / sample_n
-    est = cubic * scale ** 3 + (total - cubic) * scale ** 2
+def cpu_ei_rate(state, m_sample=2048):
+    """EI value + gradient on a bounded candidate sample with the oracle (GPModel.predict_withGradients + AcquisitionEI,
+    gpmodel.py:131-142, EI.py:44-51), on the posterior of the evaluation just timed.  The reference recomputes get_fmin() -- a
+    predict at all N training inputs -- inside every acquisition call (gpmodel.py:125-129, EI.py:36); it is timed separately and
+    NOT charged to the per-candidate rate (which favours the CPU number)."""
     from oracle import gp_oracle as O
-    return {"value": 1.0 / est, "unit": UNIT, "cores": int(cores), "kind": "port",
-            "sample": "one oracle eval at N=%d D=%d took %.2f s (LAPACK part %.2f s); extrapolated to N=%d as cubic x%d + "
-                      "quadratic x%d = %.1f s/eval; lengthscale loop = reference C helper %s" %
-                      (sample_n, DIM, total, cubic, N_TRAIN, scale ** 3, scale ** 2, est,
-                       "(oracle/_ref)" if O.ref_native() is not None else "unavailable -> NumPy")}, est
+    post, X, ls, kind, noise = state["post"], state["X"], state["ls"], state["kind"], state["noise"]
+    Xc = np.random.RandomState(4321).uniform(0, 1, (m_sample, X.shape[1]))
+    t0 = time.perf_counter()
+    fmin = O.gpmodel_get_fmin(kind, post, X, 1.0, ls, noise)
+    t1 = time.perf_counter()
+    m, s, dmdx, dsdx = O.gpmodel_predict_withGradients(kind, post, X, Xc, 1.0, ls, noise, native=O.ref_native() is not None)
+    f, df = O.acq_EI(m, s, fmin, 0.01, dmdx, dsdx)
+    t2 = time.perf_counter()
+    return {"candidates_per_s": m_sample / (t2 - t1), "sample_candidates": m_sample, "seconds": t2 - t1, "get_fmin_seconds": t1 - t0}
+
+
+def cpu_baseline():
+    """cpu_baseline leg of the GPU arm (N = 1 only): ONE real oracle evaluation at the headline size ('single timed
+    run for N=16384'), the small-N scaled estimate kept beside it as a cross-check.  GPB_BENCH_CPU=sample restores the bounded
+    N=4096 sample (quick local runs)."""
+    from oracle import gp_oracle as O
+    cores = _blas_threads()
+    helper = "(oracle/_ref)" if O.ref_native() is not None else "unavailable -> NumPy"
+    cpu_eval(1024, DIM)                                   # spin the BLAS threads up
+    total_s, cubic_s, _ = cpu_eval(4096, DIM)
+    est = cubic_s * 64 + (total_s - cubic_s) * 16
+    if os.environ.get("GPB_BENCH_CPU", "real") == "sample":
+        return {"value": 1.0 / est, "unit": UNIT, "cores": cores, "kind": "port", "measured": False,
+                "sample": "one oracle eval at N=4096 D=%d took %.2f s (LAPACK part %.2f s); EXTRAPOLATED to N=%d as cubic x64 + "
+                          "quadratic x16 = %.1f s/eval; lengthscale loop = reference C helper %s" % (DIM, total_s, cubic_s, N_TRAIN, est, helper)}
+    total, cubic, state = cpu_eval(N_TRAIN, DIM, keep_state=True)
+    ei = None
+    try:
+        ei = cpu_ei_rate(state)
+    except Exception as exc:
+        ei = {"error": repr(exc)}
+    return {"value": 1.0 / total, "unit": UNIT, "cores": cores, "kind": "port", "measured": True, "seconds_per_eval": total,
+            "sample": "ONE REAL oracle eval at N=%d D=%d: %.1f s (LAPACK part %.1f s) on %d threads, no extrapolation; cross-check: "
+                      "N=4096 eval %.2f s scaled (cubic x64 + quadratic x16) = %.1f s; lengthscale loop = reference C helper %s" %
+                      (N_TRAIN, DIM, total, cubic, cores, total_s, est, helper),
+            "ei": ei}
 
 
 def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU path (oracle port; the reference package itself cannot be imported) at
+    the FULL headline size on every host thread.  One evaluation takes minutes, so the arm runs as many real evaluations as fit
+    its time budget (GPB_REF_BUDGET_S, default 420 s; at least one) and prints the count it actually ran as `steps`."""
     if rank != 0:
         return
-    # each "step" = one bounded-sample oracle evaluation, reported in the metric's unit through the cubic/quadratic scaling
-    sample_n = 2048
-    ests = []
-    for i in range(args.warmup + args.steps):
-        total, cubic = cpu_eval_time(sample_n, DIM)
-        scale = N_TRAIN / sample_n
-        if i >= args.warmup:
-            ests.append(cubic * scale ** 3 + (total - cubic) * scale ** 2)
-    import threadpoolctl
-    cores = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] + [1])
-    est = float(np.mean(ests))
-    line = {"impl": "reference", "metric": METRIC, "value": 1.0 / est, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": est * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU oracle port of the reference path (the reference package cannot be "
-                       "imported here: paramz is un-vendored); each step is an N=%d evaluation scaled to N=%d" % (sample_n, N_TRAIN)},
-            "cpu_baseline": {"value": 1.0 / est, "unit": UNIT, "cores": int(cores), "kind": "port",
-                             "sample": "N=%d D=%d oracle evals, cubic part x%d + quadratic part x%d" %
-                                       (sample_n, DIM, (N_TRAIN // sample_n) ** 3, (N_TRAIN // sample_n) ** 2)},
-            "e2e": {"value": 1.0 / est, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cores = _blas_threads()
+    budget = float(os.environ.get("GPB_REF_BUDGET_S", "420"))
+    cpu_eval(1024, DIM)                                   # spin the BLAS threads up (not a step)
+    small_total, small_cubic, _ = cpu_eval(2048, DIM)
+    est = small_cubic * 512 + (small_total - small_cubic) * 64
+    times, state, t_start = [], None, time.perf_counter()
+    while True:
+        total, cubic, st = cpu_eval(N_TRAIN, DIM, keep_state=state is None)
+        state = state or st
+        times.append(total)
+        elapsed = time.perf_counter() - t_start
+        if len(times) >= args.steps or elapsed + 1.1 * total > budget:
+            break
+    per = float(np.mean(times))
+    # the other half of the metric on the CPU: EI value + gradient on a bounded sample against a Matern52 posterior of the same size
+    # would need a second 2-3 minute fit; the per-candidate cost does not depend on the kernel kind beyond the O(N D) covariance
+    # row, so the RBF posterior of the evaluation above is used and the fact is stated
+    try:
+        ei = cpu_ei_rate(state)
+    except Exception as exc:
+        ei = {"error": repr(exc)}
+    cfg = base_config(1)
+    cfg.update({"ei_candidates_per_s": ei.get("candidates_per_s"), "ei_seconds": ei.get("seconds"),
+                "ei_sample_candidates": ei.get("sample_candidates"), "ei_get_fmin_seconds": ei.get("get_fmin_seconds"),
+                "ei_note": "CPU oracle, bounded sample, on the RBF posterior of the timed evaluation; get_fmin (recomputed by the "
+                           "reference inside every acquisition call) timed separately and not charged",
+                "note": "CPU oracle port of the reference path (the reference package cannot be imported here: paramz is "
+                        "un-vendored); REAL evaluations at N=%d, %d run (requested %d) within a %.0f s budget; cross-check: N=2048 "
+                        "eval %.2f s scaled (cubic x512 + quadratic x64) = %.1f s" % (N_TRAIN, len(times), args.steps, budget, small_total, est)})
+    line = {"impl": "reference", "metric": METRIC, "value": 1.0 / per, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": 0, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": 1.0 / per, "unit": UNIT, "cores": cores, "kind": "port", "measured": True,
+                             "sample": "%d real oracle evals at N=%d D=%d, %.1f s each (min %.1f, max %.1f) on %d threads" %
+                                       (len(times), N_TRAIN, DIM, per, min(times), max(times), cores)},
+            "e2e": {"value": 1.0 / per, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -265,12 +368,12 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_res, t_e2e = float(tt[0]), float(tt[1])
 
-    # ---- aux: EI value+gradient candidates/s over a candidate set sharded across the ranks (config 4) ----
-    aux = None
+    # ---- the second half of the metric: EI over 2^20 candidates, strong-scaled over the ranks (goes into `config`) ----
+    ei = None
     try:
-        aux = bench_acquisition(args, model, rank, world, barrier)
+        ei = bench_ei_sharded(args, rank, world, barrier)
     except Exception as exc:  # report, never hide
-        aux = {"error": repr(exc)}
+        ei = {"ei_error": repr(exc)}
     # ---- aux: the M = 1 value+gradient call L-BFGS-B makes from every anchor point (two HBM passes over the triangle of L^-1) ----
     aux_m1 = None
     if rank == 0:
@@ -314,15 +417,16 @@ def run_gpu(args, rank, world, local_rank):
                     "algorithmic_bytes": 3 * 8.0 * N_TRAIN * (N_TRAIN + 128) / 2, "traffic": traffic, "traffic_note": traffic_note}
         if dominant["achieved"]:
             dominant["frac"] = dominant["achieved"] / peak_tflops
-        cpu, _ = cpu_baseline() if world == 1 else (None, None)
+        cpu = cpu_baseline() if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": "replicas x%d (N x N factorisation stays on one GPU)" % world,
-                       "l2": "inputs larger than L2 (three 2.1 GB fp64 matrices per eval vs 126 MB L2)",
-                       "algorithmic_flops_per_eval": algorithmic_flops(N_TRAIN, DIM),
-                       "algorithmic_tflops": algorithmic_flops(N_TRAIN, DIM) * args.steps / t_res / 1e12},
+            "config": dict(base_config(world), **dict({
+                "parallelism": "NLL+grad: replicas x%d (N x N factorisation stays on one GPU); EI: candidates sharded x%d" % (world, world),
+                "l2": "inputs larger than L2 (three 2.1 GB fp64 matrices per eval vs 126 MB L2)",
+                "algorithmic_flops_per_eval": algorithmic_flops(N_TRAIN, DIM),
+                "algorithmic_tflops": algorithmic_flops(N_TRAIN, DIM) * args.steps / t_res / 1e12}, **(ei or {}))),
             "e2e": {"value": world * args.steps / t_e2e, "unit": UNIT,
                     "h2d_bytes_per_step": int(X.nbytes + Y.nbytes + (DIM + 2) * 8), "d2h_bytes_per_step": int((DIM + 3) * 8 + 4)},
             "gpu_launches": int(launches),
@@ -336,8 +440,6 @@ def run_gpu(args, rank, world, local_rank):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if aux is not None:
-            line["aux"] = aux
         if aux_m1 is not None:
             line["aux_m1"] = aux_m1
         if other is not None:
@@ -595,45 +697,103 @@ def bench_refinement_call(model):
     return out
 
 
-def bench_acquisition(args, model, rank, world, barrier):
-    """Config 4: EI value + gradient over a synthetic candidate set, sharded over the ranks; per-shard top-5 all-gathered."""
+def bench_ei_sharded(args, rank, world, barrier):
+    """The second half of BASELINE.json's metric, the one path that shards (north_star (c); run.py:1240-1253 /
+    anchor_points_generator.py:85-98 scaled up): EI value + D-vector gradient for every candidate (written to HBM) and the global
+    top-5, over a FIXED total of 2^20 candidates split into contiguous ranges over the ranks -> strong scaling.  The per-shard
+    top-5 rows stay on the device, are all-gathered there and merged; all of that is inside the timed region (CUDA events, max
+    over ranks).  Model = BASELINE config 4: Matern52-ARD, N=16384, D=16, noise 1e-6 (the exact_feval level).
+
+    Also measured, outside that region: the cost of getting the fitted state onto every rank (every rank refits vs rank 0 fits and
+    NCCL-broadcasts theta, alpha, L^-1), and GPyOpt's real anchor-scoring call (1000 uniform candidates, value only)."""
     import torch
     import torch.distributed as dist
-    from gaussian_process_optimization_b200 import native
-    per_rank = 2 ** 15
-    chunk = np.random.RandomState(4321).uniform(0, 1, (2 ** 20, DIM))       # SURVEY 8(d): chunk c = RandomState(4321 + c)
-    shard = torch.from_numpy(np.ascontiguousarray(chunk[rank * per_rank:(rank + 1) * per_rank])).cuda()
-    model.set_theta(1.0, 0.5 + 0.5 * np.arange(DIM) / DIM, 1e-2)
-    info, _, _ = model.fit(False)
-    assert info == 0
+    from gaussian_process_optimization_b200 import native, sharded
+    X, Y, ls = synth(N_TRAIN, DIM)
+    model = native.NativeModel(EI_KIND, True, DIM, 1, n_cap=N_TRAIN, cand_block=2048)
+    model.set_data(torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda())
+    model.set_theta(1.0, ls, EI_NOISE)
+
+    def timed(fn, reps=1):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        barrier()
+        t = e0.elapsed_time(e1) * 1e-3 / reps
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt[0])
+        return t, out
+
+    # ---- state distribution: (a) every rank refits; (b) rank 0 fits, the others receive theta / alpha / L^-1 over NCCL ----
+    def refit():
+        model.set_theta(1.0, ls * (1 + 1e-9), EI_NOISE)      # a changed hyper-parameter forces a real refit
+        model.set_theta(1.0, ls, EI_NOISE)
+        info, logL, _ = model.fit(False)
+        assert info == 0
+        return logL
+    refit()
+    t_refit, logL = timed(refit)
+    t_bcast, state_ok = None, None
+    if world > 1:
+        model.broadcast_state(src=0)                         # warm-up (NCCL channel set-up)
+        t_bcast, _ = timed(lambda: model.broadcast_state(src=0))
+        # the adopted state must be the fitted one: compare alpha with what this rank computed itself before the broadcast
+        a_mine = model.state_tensor("alpha").clone()
+        refit()
+        state_ok = bool(torch.equal(a_mine, model.state_tensor("alpha")))
+        model.broadcast_state(src=0)
     fmin = model.fmin()
-    model.acq_topk_full("EI", 0.01, fmin, shard[:4096], 5)                   # warm-up
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    vals, idx, pts, f_all, df_all = model.acq_topk_full("EI", 0.01, fmin, shard, 5, index_offset=rank * per_rank)
-    if world > 1:
-        mine = torch.from_numpy(np.concatenate([vals, idx.astype(np.float64), pts.ravel()])).cuda()
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        allv = torch.stack(gathered).cpu().numpy()
-        cand = sorted((allv[g, i], int(allv[g, 5 + i])) for g in range(world) for i in range(5))[:5]
-    else:
-        cand = sorted(zip(vals.tolist(), idx.tolist()))[:5]
-    e1.record()
-    barrier()
-    t = e0.elapsed_time(e1) * 1e-3
-    if world > 1:
-        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t = float(tt[0])
-    n_cand = per_rank * world
+
+    # ---- strong scaling: 2^20 candidates in total ----
+    lo, hi = sharded.divide_candidates(EI_TOTAL, rank, world)
+    chunk = np.random.RandomState(4321).uniform(0, 1, (EI_TOTAL, DIM))          # SURVEY 8(d): chunk 0
+    shard = torch.from_numpy(np.ascontiguousarray(chunk[lo:hi])).cuda()
+    rows = torch.empty((5, DIM + 2), dtype=torch.float64, device="cuda")
+    model.acq_topk_dev("EI", 0.01, fmin, shard[:4096], 5, index_offset=lo, with_gradients=True, rows=rows)   # warm-up
+    torch.cuda.synchronize()
+
+    def score():
+        r, f, df = model.acq_topk_dev("EI", 0.01, fmin, shard, 5, index_offset=lo, with_gradients=True, rows=rows)
+        return sharded.all_gather_topk_device(r, 5)
+    t_ei, (tv, ti, tp) = timed(score)
+
+    # ---- parity against the reference-generated fixture: top-5 of the first 2^16 rows (tests/golden/make_golden_fullsize.py) ----
+    golden_ok = None
+    gpath = os.path.join(ROOT, "tests", "golden", "fullsize", "config4_mat52_ard_n16384_d16_exact.npz")
+    if rank == 0 and os.path.exists(gpath):
+        z = np.load(gpath)
+        pre = torch.from_numpy(np.ascontiguousarray(chunk[:2 ** 16])).cuda()
+        v5, i5, _ = model.acq_topk("EI", 0.01, fmin, pre, 5)
+        golden_ok = bool(np.array_equal(i5, z["ei_top5_idx"]) and np.allclose(v5, z["ei_top5_val"], rtol=1e-7, atol=0))
+        del pre
+
+    # ---- GPyOpt's real anchor scoring: 1000 uniform candidates, value only, top-5 (anchor_points_generator.py:58-63,87) ----
+    anchors = np.random.RandomState(4322).uniform(0, 1, (N_ANCHOR_CANDIDATES, DIM))
+    alo, ahi = sharded.divide_candidates(N_ANCHOR_CANDIDATES, rank, world)
+    ash = torch.from_numpy(np.ascontiguousarray(anchors[alo:ahi])).cuda()
+
+    def score_anchors():
+        r, _, _ = model.acq_topk_dev("EI", 0.01, fmin, ash, min(5, ahi - alo), index_offset=alo, rows=rows[:min(5, ahi - alo)])
+        return sharded.all_gather_topk_device(r, 5)
+    score_anchors()
+    t_anchor, (av, ai, ap) = timed(score_anchors, reps=10)
+    del shard, chunk
+    model.close()
     fl = 2.0 * N_TRAIN ** 2 + N_TRAIN * (6 * DIM + 40)        # SURVEY 8(d) F_acq, value + gradient
-    return {"metric": "ei_value_gradient_candidates_per_s", "value": n_cand / t, "unit": "candidates/s",
-            "candidates": n_cand, "per_rank": per_rank, "model_N": N_TRAIN, "D": DIM, "seconds": t,
-            "algorithmic_tflops": fl * n_cand / t / 1e12, "top5_global_idx": [c[1] for c in cand], "scaling": "weak",
-            "note": "one pass: EI value + D-vector gradient for every candidate (written to HBM) and the running top-5; "
-                    "per-shard top-5 all-gathered and merged inside the timed region"}
+    return {"ei_candidates_per_s": EI_TOTAL / t_ei, "ei_seconds": t_ei, "ei_candidates_per_rank": hi - lo, "ei_scaling": "strong",
+            "ei_algorithmic_tflops": fl * EI_TOTAL / t_ei / 1e12, "ei_top5_idx": [int(i) for i in ti],
+            "ei_top5_val": [float(v) for v in tv], "ei_top5_prefix65536_matches_reference_golden": golden_ok,
+            "ei_timed_region": "per-shard EI value+gradient+top-5 on device-resident candidates, device all-gather of the top-5 rows, merge",
+            "ei_state_refit_every_rank_ms": t_refit * 1e3, "ei_state_broadcast_ms": None if t_bcast is None else t_bcast * 1e3,
+            "ei_state_broadcast_bytes": int(8 * (N_TRAIN * N_TRAIN + N_TRAIN + 4 + DIM)) if world > 1 else 0,
+            "ei_state_broadcast_equals_local_fit": state_ok,
+            "anchor_call_ms": t_anchor * 1e3, "anchor_top5_idx": [int(i) for i in ai],
+            "anchor_note": "GPyOpt's own anchor-scoring call (1000 uniform candidates, value only) split over the ranks: where sharding stops paying"}
 
 
 def main():

@@ -65,6 +65,10 @@ SIGNATURES = {
     "gpb_set_overlap": (c_int, [c_int]),
     "gpb_model_acq_topk_full": (c_int, [c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_int, c_int,
                                         ctypes.c_longlong, c_double_p, c_ll_p, c_double_p, c_void_p, c_void_p]),
+    "gpb_model_acq_topk_dev": (c_int, [c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_int, c_void_p, c_int, ctypes.c_longlong,
+                                       c_void_p, c_void_p, c_void_p]),
+    "gpb_model_state_ptr": (c_int, [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
+    "gpb_model_adopt_state": (c_int, [c_void_p, ctypes.c_double, c_double_p, ctypes.c_double, ctypes.c_double, c_int]),
     "gpb_profile_gemm": (c_int, [c_int]),
     "gpb_gemm_config": (c_int, [c_int]),
     "gpb_profile_gemm_collect": (c_int, [c_double_p, c_double_p, c_ll_p]),

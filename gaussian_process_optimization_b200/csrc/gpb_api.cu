@@ -14,6 +14,17 @@ namespace gpb {
 static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
 
+std::mutex &func_config_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+
+// environment knob read once (thread-safe: C++11 static initialisation)
+static int env_int(const char *name, int fallback) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : fallback;
+}
+
 void set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -122,8 +133,9 @@ struct DevBuf {
   }
   int alloc(size_t bytes) {
     if (bytes == 0) bytes = 8;
-    static unsigned long long configured = 0;
-    if (needs_func_config(configured)) {          // once per device: keep freed blocks in the pool instead of returning them
+    static FuncConfigMask configured{0};
+    FuncConfigOnce once_configured(configured);
+    if (once_configured.needed) {          // once per device: keep freed blocks in the pool instead of returning them
       int dev = 0;
       cudaMemPool_t pool;
       if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -201,6 +213,7 @@ struct gpb_model {
   double variance = 1.0, noise = 1.0, jitter = 0.0;
   std::vector<double> ls;
   bool have_data = false, scaled_valid = false, fitted = false, have_wi = false;
+  bool l_valid = true;   // false after gpb_model_adopt_state without the L region: A does not hold the factor of this posterior
   // CUDA-graph replay of the NLL+grad launch sequence (small / medium N: an evaluation is a chain of tens to hundreds of short
   // kernels whose host-side launch cost is a good part of the wall time).  One executable graph per want_grad, valid for one
   // (n, np, configuration epoch); the hyper-parameters reach the kernels through theta_dev and the pinned block.
@@ -212,6 +225,7 @@ struct gpb_model {
     int l_from = 0;
   } graphs[2];
   bool graph_failed = false, own_stream = false;
+  cudaEvent_t entry_ev = nullptr;   // own_stream: orders the model's private non-blocking stream after the legacy default stream at call entry
   double *theta_dev = nullptr;
   int wi_from = 0;  // > 0 (after gpb_model_append): the leading wi_from block of W holds the old Ky^-1, downdated; rows beyond are stale
   cudaStream_t stream = 0;
@@ -244,6 +258,14 @@ static int check_device(const gpb_model *m, const char *what) {
   int dev = -1;
   GPB_CUDA(cudaGetDevice(&dev));
   GPB_REQUIRE(dev == m->device, "%s: the model lives on CUDA device %d but device %d is current", what, m->device, dev);
+  if (m->own_stream && m->entry_ev) {
+    // The caller asked for the legacy default stream; the model runs on a NON-blocking stream of its own (a blocking one must not be
+    // captured while any thread touches the legacy stream).  Work the caller queued on the legacy stream before this call (e.g. a
+    // torch op producing an input tensor) is ordered in front of ours explicitly; every entry point synchronises its stream before
+    // it returns, which orders the other direction.
+    GPB_CUDA(cudaEventRecord(m->entry_ev, cudaStreamLegacy));
+    GPB_CUDA(cudaStreamWaitEvent(m->stream, m->entry_ev, 0));
+  }
   return 0;
 }
 
@@ -329,11 +351,23 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
                      size_t workspace_bytes, void *stream) {
   GPB_REQUIRE(out != nullptr, "model_create: out is NULL");
   GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "model_create: unknown kernel kind %d", kind);
-  GPB_REQUIRE(d >= 1 && d <= 96, "model_create: input_dim %d out of range [1, 96]", d);
+  // 64 = what the predictive kernels (skinny moments, gradients_X) are instantiated for: a model that could be fitted but not queried
+  // would be useless to the BO loop
+  GPB_REQUIRE(d >= 1 && d <= 64, "model_create: input_dim %d out of range [1, 64]", d);
   GPB_REQUIRE(p >= 1 && p <= 16, "model_create: output_dim %d out of range [1, 16]", p);
   GPB_REQUIRE(n_cap >= 1 && cand_block >= 1, "model_create: capacities must be positive");
   GPB_REQUIRE(gpb_device_count() > 0, "model_create: no CUDA device visible -- libgpb200 has no CPU fallback");
   gpb_model *m = new gpb_model();
+  // every failure path below releases what has been created so far
+  auto fail = [&](int rc) {
+    if (m->ov) factor_overlap_destroy(m->ov);
+    if (m->pinned) cudaFreeHost(m->pinned);
+    if (m->own_ws && m->ws) cudaFree(m->ws);
+    if (m->entry_ev) cudaEventDestroy(m->entry_ev);
+    if (m->own_stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return rc;
+  };
   m->kind = kind;
   m->ard = ard ? 1 : 0;
   m->d = d;
@@ -345,51 +379,51 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
   m->ls.assign(m->nls, 1.0);
   m->stream = reinterpret_cast<cudaStream_t>(stream);
   if (m->stream == nullptr) {
-    // The legacy default stream cannot be captured into a CUDA graph.  A blocking stream of the model's own takes its place:
-    // it synchronises implicitly with the legacy stream in both directions, so work the caller has queued there (and reads of
-    // our results from there) stay ordered exactly as before.
-    if (cudaStreamCreate(&m->stream) == cudaSuccess) {
+    // The legacy default stream cannot be captured into a CUDA graph, and a BLOCKING stream must not be captured while another
+    // thread uses the legacy stream (cudaErrorStreamCaptureImplicit).  The model gets a non-blocking stream of its own and orders
+    // it against the legacy stream explicitly (check_device).
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess) {
       m->own_stream = true;
+      if (cudaEventCreateWithFlags(&m->entry_ev, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("model_create: cudaEventCreate failed");
+        return fail(-1);
+      }
     } else {
       (void)cudaGetLastError();
       m->stream = nullptr;
+      m->graph_failed = true;      // no private stream: stay on the legacy stream, never capture
     }
   }
   if (cudaGetDevice(&m->device) != cudaSuccess) {
-    delete m;
     set_error("model_create: cudaGetDevice failed");
-    return -1;
+    return fail(-1);
   }
   const size_t need = carve(n_cap, d, p, m->cb, nullptr, nullptr);
   if (workspace) {
     if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
-      delete m;
       set_error("model_create: workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, need);
-      return -2;
+      return fail(-2);
     }
     m->ws = workspace;
   } else {
     cudaError_t e = cudaMalloc(&m->ws, need);
     if (e != cudaSuccess) {
-      delete m;
+      m->ws = nullptr;
       set_error("model_create: cudaMalloc(%zu) -> %s", need, cudaGetErrorString(e));
-      return -1;
+      return fail(-1);
     }
     m->own_ws = true;
   }
   carve(n_cap, d, p, m->cb, m, reinterpret_cast<char *>(m->ws));
   m->f.stream = m->stream;
   if (cudaMallocHost(&m->pinned, 256 * sizeof(double)) != cudaSuccess) {
-    if (m->own_ws) cudaFree(m->ws);
-    delete m;
+    m->pinned = nullptr;
     set_error("model_create: cudaMallocHost failed");
-    return -1;
+    return fail(-1);
   }
   if (factor_overlap_create(&m->ov) != 0) {
-    if (m->own_ws) cudaFree(m->ws);
-    cudaFreeHost(m->pinned);
-    delete m;
-    return -1;
+    m->ov = nullptr;
+    return fail(-1);
   }
   *out = m;
   return 0;
@@ -401,6 +435,7 @@ int gpb_model_destroy(gpb_model *m) {
   for (auto &g : m->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   factor_overlap_destroy(m->ov);
+  if (m->entry_ev) cudaEventDestroy(m->entry_ev);
   if (m->own_stream) cudaStreamDestroy(m->stream);
   if (m->lp_buf) cudaFree(m->lp_buf);
   if (m->own_ws && m->ws) cudaFree(m->ws);
@@ -534,11 +569,7 @@ static int fit_launch_general(gpb_model *m, int want_grad, double extra_jitter, 
   GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, d, n, n, kc.var, m->noise + 1e-8 + extra_jitter, 3, m->f.A, np, np, np,
                       m->stream, kc.gflag, append_from, theta));
   // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
-  static int fork_div = -1;
-  if (fork_div < 0) {
-    const char *e = getenv("GPB_FORK_DIV");
-    fork_div = e ? std::max(1, atoi(e)) : 8;
-  }
+  static const int fork_div = std::max(1, env_int("GPB_FORK_DIV", 8));
   const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / fork_div) : 0;
   if (m->ov && fork_min_n > 0 && np >= fork_min_n) {
     // critical path on the model's high-priority stream, T21 products on its low-priority side streams (gpb_chol.cu)
@@ -650,11 +681,7 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
   m->have_wi = false;
   m->jitter = extra_jitter;
   const int n = m->n, np = m->np, d = m->d, p = m->p;
-  static int tiny_on = -1;
-  if (tiny_on < 0) {
-    const char *e = getenv("GPB_TINY");
-    tiny_on = (e && e[0] == '0') ? 0 : 1;
-  }
+  static const int tiny_on = env_int("GPB_TINY", 1) != 0;
   const bool tiny = tiny_on && np == TILE && !m->gower && p == 1 && d <= 32 && append_from == 0;
   if (tiny) {
     // N <= 128 (an ordinary BO run): the whole evaluation -- input scaling included -- in one kernel instead of a dozen launches
@@ -666,11 +693,8 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
     m->scaled_valid = true;
     if (want_grad) m->have_wi = true;
   } else {
-    static int graph_max_np = -1;
-    if (graph_max_np < 0) {
-      const char *e = getenv("GPB_GRAPH_MAX_NP");
-      graph_max_np = e ? atoi(e) : 2048;   // replay pays up to here (scripts/small_n_perf.py: -16% at N = 256, -6% at 1024, nothing at 4096)
-    }
+    // replay pays up to here (scripts/small_n_perf.py: -16% at N = 256, -6% at 1024, nothing at 4096)
+    static const int graph_max_np = env_int("GPB_GRAPH_MAX_NP", 2048);
     int rc = 1;
     if (np <= graph_max_np && append_from == 0 && !m->gower && d <= 32 && !m->graph_failed && !gemm_profile_is_on() &&
         !(ozaki_min_n() > 0 && np >= ozaki_min_n()))   // the int8 engine allocates its digit workspace on first use: not capturable
@@ -700,6 +724,7 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
     out[2 + m->nls] = g[1];                               // exact_gaussian_inference.py:72, gaussian.py:78-79
   }
   m->fitted = true;
+  m->l_valid = true;
   return 0;
 }
 
@@ -715,6 +740,7 @@ int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall
   GPB_REQUIRE(m && Xnew && Yall && out, "append: NULL argument");
   GPB_TRY(check_device(m, "append"));
   GPB_REQUIRE(m->fitted && m->jitter == 0.0, "append: needs a model fitted (without extra jitter) for the current hyper-parameters");
+  GPB_REQUIRE(m->l_valid, "append: the model adopted a broadcast state without the factor L (gpb_model_adopt_state have_mask bit 0)");
   GPB_REQUIRE(b >= 1 && m->n + b <= m->n_cap, "append: %d + %d points exceed the model capacity %d", m->n, b, m->n_cap);
   const int n_old = m->n, np_old = m->np, n_new = n_old + b, np_new = round_up(n_new, TILE), d = m->d;
   cudaStream_t s = m->stream;
@@ -797,6 +823,7 @@ int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) 
   }
   const dim3 grid((n + 255) / 256, n), gsym((n + 31) / 32, (n + 31) / 32);
   if (w == "L") {
+    GPB_REQUIRE(m->l_valid, "get: the model adopted a broadcast state without the factor L");
     GPB_TRY(factor_finalize_L(m->f));
     tril_copy_kernel<<<grid, 256, 0, s>>>(m->f.A, np, ddst, ldd, n);
   } else if (w == "Li") {
@@ -1061,17 +1088,13 @@ int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int
   return 0;
 }
 
-int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
-                            long long index_offset, double *vals, long long *idx, double *pts, double *f, double *df) {
-  GPB_REQUIRE(m && Xc && vals && idx, "acq_topk: NULL argument");
-  GPB_TRY(check_device(m, "acq_topk_full"));
-  GPB_REQUIRE(m->fitted, "acq_topk: model has not been fitted");
-  GPB_REQUIRE(k >= 1 && k <= 64 && k <= mc, "acq_topk: k = %d must be in [1, min(64, mc)]", k);
-  GPB_REQUIRE(m->p == 1, "acq_topk: single output only");
+// One scoring pass with a running top-k on the device.  The k result rows [value, global index, coordinates] are left in
+// out_rows_dev (device, k x (d + 2); needs device-resident candidates) when it is given.  No synchronisation at the end.
+static int acq_topk_pass(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k, long long index_offset,
+                         double *f, double *df, double *out_rows_dev) {
   const int d = m->d;
   const bool grad = df != nullptr;
   cudaStream_t s = m->stream;
-  AllocStream alloc_scope(s);
   GPB_TRY(launch_topk_init(m->topv, m->topi, k, s));
   for (int c0 = 0; c0 < mc; c0 += m->cb) {
     const int mcb = std::min(m->cb, mc - c0);
@@ -1083,6 +1106,27 @@ int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int 
     if (grad) GPB_TRY(copy_out(df + (size_t)c0 * d, m->dfbuf, (size_t)mcb * d, dev, s));
     if (!dev) GPB_CUDA(cudaStreamSynchronize(s));  // the host block may be reused by the caller's next copy
   }
+  if (out_rows_dev) GPB_TRY(launch_topk_pack(m->topv, m->topi, Xc, d, k, index_offset, out_rows_dev, s));
+  return 0;
+}
+
+static int acq_topk_check(gpb_model *m, int acq, int mc, int k, const char *what) {
+  GPB_TRY(check_device(m, what));
+  GPB_REQUIRE(m->fitted, "%s: model has not been fitted", what);
+  GPB_REQUIRE(acq == GPB_ACQ_EI || acq == GPB_ACQ_LCB, "%s: unknown acquisition type %d", what, acq);
+  GPB_REQUIRE(k >= 1 && k <= 64 && k <= mc, "%s: k = %d must be in [1, min(64, mc)]", what, k);
+  GPB_REQUIRE(m->p == 1, "%s: single output only", what);
+  return 0;
+}
+
+int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
+                            long long index_offset, double *vals, long long *idx, double *pts, double *f, double *df) {
+  GPB_REQUIRE(m && Xc && vals && idx, "acq_topk: NULL argument");
+  GPB_TRY(acq_topk_check(m, acq, mc, k, "acq_topk"));
+  const int d = m->d;
+  cudaStream_t s = m->stream;
+  AllocStream alloc_scope(s);
+  GPB_TRY(acq_topk_pass(m, acq, par, fmin, mc, Xc, dev, k, index_offset, f, df, nullptr));
   GPB_CUDA(cudaMemcpyAsync(m->pinned, m->topv, k * sizeof(double), cudaMemcpyDeviceToHost, s));
   GPB_CUDA(cudaMemcpyAsync(m->pinned + 64, m->topi, k * sizeof(long long), cudaMemcpyDeviceToHost, s));
   GPB_CUDA(cudaStreamSynchronize(s));
@@ -1090,13 +1134,84 @@ int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int 
     vals[i] = m->pinned[i];
     idx[i] = reinterpret_cast<long long *>(m->pinned + 64)[i];
   }
-  if (pts) {
-    for (int i = 0; i < k; ++i) {
-      const long long local = idx[i] - index_offset;
-      GPB_CUDA(cudaMemcpy(pts + (size_t)i * d, Xc + (size_t)local * d, d * sizeof(double),
+  // A slot that never received a candidate (NaN scores never win: fewer than k finite scores) still holds the initial sentinel:
+  // report it as (NaN, -1, NaN ...), the empty-slot convention sharded.merge_topk filters on, instead of dereferencing it.
+  for (int i = 0; i < k; ++i) {
+    const bool empty = idx[i] == LLONG_MAX;
+    if (empty) {
+      vals[i] = NAN;
+      idx[i] = -1;
+    }
+    if (!pts) continue;
+    if (empty) {
+      for (int q = 0; q < d; ++q) pts[(size_t)i * d + q] = NAN;
+    } else {
+      GPB_CUDA(cudaMemcpy(pts + (size_t)i * d, Xc + (size_t)(idx[i] - index_offset) * d, d * sizeof(double),
                           dev ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
     }
   }
+  return 0;
+}
+
+int gpb_model_acq_topk_dev(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc_dev, int k, long long index_offset,
+                           double *rows_dev, double *f_dev, double *df_dev) {
+  GPB_REQUIRE(m && Xc_dev && rows_dev, "acq_topk_dev: NULL argument");
+  GPB_TRY(acq_topk_check(m, acq, mc, k, "acq_topk_dev"));
+  AllocStream alloc_scope(m->stream);
+  return acq_topk_pass(m, acq, par, fmin, mc, Xc_dev, 1, k, index_offset, f_dev, df_dev, rows_dev);
+}
+
+// ---- multi-GPU state distribution -------------------------------------------------------------------------------------------
+int gpb_model_state_ptr(gpb_model *m, const char *what, void **ptr, size_t *count) {
+  GPB_REQUIRE(m && what && ptr && count, "state_ptr: NULL argument");
+  GPB_TRY(check_device(m, "state_ptr"));
+  const std::string w(what);
+  const size_t np = m->np;
+  if (w == "Li") {
+    *ptr = m->f.Mi;
+    *count = np * np;
+  } else if (w == "L") {
+    if (m->fitted) {
+      GPB_TRY(factor_finalize_L(m->f));
+      GPB_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    *ptr = m->f.A;
+    *count = np * np;
+  } else if (w == "Wi") {
+    if (m->fitted) {
+      GPB_TRY(factor_finalize_L(m->f));     // W doubles as the parking place of L's off-diagonal blocks
+      GPB_TRY(ensure_wi(m));
+      GPB_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    *ptr = m->f.W;
+    *count = np * np;
+  } else if (w == "alpha") {
+    *ptr = m->alpha;
+    *count = np * (size_t)m->p;
+  } else {
+    GPB_REQUIRE(false, "state_ptr: unknown region '%s' (Li, L, Wi, alpha)", what);
+  }
+  return 0;
+}
+
+int gpb_model_adopt_state(gpb_model *m, double variance, const double *lengthscale, double noise, double jitter, int have_mask) {
+  GPB_REQUIRE(m && lengthscale, "adopt_state: NULL argument");
+  GPB_TRY(check_device(m, "adopt_state"));
+  GPB_REQUIRE(m->have_data, "adopt_state: set_data has not been called (every rank holds the same X, Y)");
+  m->variance = variance;
+  m->noise = noise;
+  m->jitter = jitter;
+  for (int q = 0; q < m->nls; ++q) m->ls[q] = lengthscale[q];
+  m->scaled_valid = false;
+  GPB_TRY(ensure_scaled(m));                 // scaled inputs and the lengthscale arrays the predictive kernels read
+  ozaki_invalidate();                        // cached digit planes of the previous L^-1 are stale
+  m->f.l_pending = false;
+  m->f.l_from = 0;
+  m->wi_from = 0;
+  m->have_wi = (have_mask & 2) != 0;
+  m->l_valid = (have_mask & 1) != 0;
+  m->fitted = true;
+  GPB_CUDA(cudaStreamSynchronize(m->stream));
   return 0;
 }
 

@@ -799,8 +799,9 @@ int launch_tiny_fit(int kind, const double *X, const double *ls_host, double *Xs
                     double variance, double diag_add, const double *y, Factor &f, double *z, double *alpha, double *scal, int want_grad) {
   GPB_REQUIRE(f.np == TILE && n <= TILE && d <= TINY_DMAX, "tiny fit: needs N <= 128 and D <= %d", TINY_DMAX);
   const size_t smem = (size_t)(TILE * LSD + 2 * LNB * LB * LMD + TINY_DMAX * TILE + 3 * TILE + (LEAF_THREADS / 32) * (TINY_DMAX + 2)) * sizeof(double);
-  static unsigned long long configured = 0;
-  if (needs_func_config(configured)) {
+  static FuncConfigMask configured{0};
+  FuncConfigOnce once_configured(configured);
+  if (once_configured.needed) {
     GPB_CUDA(cudaFuncSetAttribute(tiny_fit_kernel<GPB_KERN_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GPB_CUDA(cudaFuncSetAttribute(tiny_fit_kernel<GPB_KERN_MATERN52>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -827,8 +828,9 @@ static int launch_leaf(Factor &f, int off, int mode) {
   }
   if (mode == 0 && g_leaf_variant == 1) {
     const size_t smem_b = (size_t)(TILE * LSD + 2 * LNB * LB * LMD) * sizeof(double);
-    static unsigned long long configured_b = 0;
-    if (needs_func_config(configured_b))
+    static FuncConfigMask configured_b{0};
+    FuncConfigOnce once_configured_b(configured_b);
+    if (once_configured_b.needed)
       GPB_CUDA(cudaFuncSetAttribute(leaf_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     GPB_CUDA(launch_pdl(leaf_blocked_kernel, dim3(1), dim3(LEAF_THREADS), smem_b, f.stream, f.A + (size_t)off * f.np + off, f.np,
                         f.Mi + (size_t)off * f.np + off, f.np, off, f.info));
@@ -836,8 +838,9 @@ static int launch_leaf(Factor &f, int off, int mode) {
     return 0;
   }
   const size_t smem = (size_t)(2 + 3 * TILE + TILE * LEAF_LD) * sizeof(double);
-  static unsigned long long configured = 0;
-  if (needs_func_config(configured)) {
+  static FuncConfigMask configured{0};
+  FuncConfigOnce once_configured(configured);
+  if (once_configured.needed) {
     GPB_CUDA(cudaFuncSetAttribute(leaf_potrf_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GPB_CUDA(cudaFuncSetAttribute(leaf_potrf_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
@@ -999,15 +1002,21 @@ int factor_finalize_L(Factor &f) {
 int factor_overlap_create(FactorOverlap **out) {
   FactorOverlap *ov = new FactorOverlap();
   int least = 0, greatest = 0;
-  GPB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-  GPB_CUDA(cudaStreamCreateWithPriority(&ov->main, cudaStreamNonBlocking, greatest));
+  auto ok = [&](cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    set_error("factor_overlap_create: %s -> %s", what, cudaGetErrorString(e));
+    factor_overlap_destroy(ov);          // releases whatever exists so far
+    return false;
+  };
+  if (!ok(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange")) return -1;
+  if (!ok(cudaStreamCreateWithPriority(&ov->main, cudaStreamNonBlocking, greatest), "cudaStreamCreateWithPriority")) return -1;
   for (int d = 0; d < FactorOverlap::MAX_DEPTH; ++d) {
-    GPB_CUDA(cudaStreamCreateWithPriority(&ov->side[d], cudaStreamNonBlocking, least));
-    GPB_CUDA(cudaEventCreateWithFlags(&ov->fork[d], cudaEventDisableTiming));
-    GPB_CUDA(cudaEventCreateWithFlags(&ov->join[d], cudaEventDisableTiming));
+    if (!ok(cudaStreamCreateWithPriority(&ov->side[d], cudaStreamNonBlocking, least), "cudaStreamCreateWithPriority")) return -1;
+    if (!ok(cudaEventCreateWithFlags(&ov->fork[d], cudaEventDisableTiming), "cudaEventCreateWithFlags")) return -1;
+    if (!ok(cudaEventCreateWithFlags(&ov->join[d], cudaEventDisableTiming), "cudaEventCreateWithFlags")) return -1;
   }
-  GPB_CUDA(cudaEventCreateWithFlags(&ov->enter, cudaEventDisableTiming));
-  GPB_CUDA(cudaEventCreateWithFlags(&ov->leave, cudaEventDisableTiming));
+  if (!ok(cudaEventCreateWithFlags(&ov->enter, cudaEventDisableTiming), "cudaEventCreateWithFlags")) return -1;
+  if (!ok(cudaEventCreateWithFlags(&ov->leave, cudaEventDisableTiming), "cudaEventCreateWithFlags")) return -1;
   *out = ov;
   return 0;
 }
@@ -1015,13 +1024,13 @@ int factor_overlap_create(FactorOverlap **out) {
 void factor_overlap_destroy(FactorOverlap *ov) {
   if (!ov) return;
   for (int d = 0; d < FactorOverlap::MAX_DEPTH; ++d) {
-    cudaStreamDestroy(ov->side[d]);
-    cudaEventDestroy(ov->fork[d]);
-    cudaEventDestroy(ov->join[d]);
+    if (ov->side[d]) cudaStreamDestroy(ov->side[d]);
+    if (ov->fork[d]) cudaEventDestroy(ov->fork[d]);
+    if (ov->join[d]) cudaEventDestroy(ov->join[d]);
   }
-  cudaStreamDestroy(ov->main);
-  cudaEventDestroy(ov->enter);
-  cudaEventDestroy(ov->leave);
+  if (ov->main) cudaStreamDestroy(ov->main);
+  if (ov->enter) cudaEventDestroy(ov->enter);
+  if (ov->leave) cudaEventDestroy(ov->leave);
   delete ov;
 }
 

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "../../include/gpb200.h"
 
@@ -56,14 +57,32 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
   } while (0)
 
 // Opt-in dynamic shared memory must be configured once per kernel AND per device (function attributes are per context):
-// `done` is a per-call-site bit mask over device ordinals.
-inline bool needs_func_config(unsigned long long &done) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-  if (done & (1ull << dev)) return false;
-  done |= (1ull << dev);
-  return true;
-}
+// `done` is a per-call-site bit mask over device ordinals.  Models may be driven from several host threads (concurrent restarts),
+// so the first use is serialised: the bit is published (release) only after the configuring thread has finished, and a thread
+// that finds it unset waits on the mutex instead of launching an unconfigured kernel.
+//   static FuncConfigMask configured;  FuncConfigOnce once(configured);  if (once.needed) { cudaFuncSetAttribute(...); }
+typedef std::atomic<unsigned long long> FuncConfigMask;
+std::mutex &func_config_mutex();
+struct FuncConfigOnce {
+  FuncConfigMask &done;
+  unsigned long long bit = 0;
+  bool needed = true;
+  std::unique_lock<std::mutex> lock;
+  explicit FuncConfigOnce(FuncConfigMask &d) : done(d) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;     // unknown device: configure every time
+    bit = 1ull << dev;
+    if (done.load(std::memory_order_acquire) & bit) {
+      needed = false;
+      return;
+    }
+    lock = std::unique_lock<std::mutex>(func_config_mutex());
+    needed = !(done.load(std::memory_order_acquire) & bit);
+  }
+  ~FuncConfigOnce() {
+    if (needed && bit) done.fetch_or(bit, std::memory_order_release);
+  }
+};
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------------
 // The factorisation is a chain of several hundred short dependent kernels on one stream.  Kernels launched through launch_pdl

@@ -334,8 +334,9 @@ static int launch_t(const GemmArgs &g, cudaStream_t s) {
   constexpr int B_TILE = tile_doubles<LB, BN, BK>();
   constexpr int THREADS = WARPS_M * WARPS_N * 32;
   const size_t smem = (size_t)STAGES * (A_TILE + B_TILE) * sizeof(double);
-  static unsigned long long configured = 0;
-  if (needs_func_config(configured)) {
+  static FuncConfigMask configured{0};
+  FuncConfigOnce once_configured(configured);
+  if (once_configured.needed) {
     GPB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<LA, LB, BM, BN, WARPS_M, WARPS_N, MIN_BLOCKS, BK, STAGES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }

@@ -59,6 +59,9 @@ int launch_lp_epilogue(int n_c, int d, int nb, const double *Xc, const double *X
 // running top-k of the k smallest f (ties -> lowest index); state on device: vals[k], idx[k]
 int launch_topk_init(double *vals, long long *idx, int k, cudaStream_t s);
 int launch_topk_update(const double *f, int n_c, long long index_base, double *vals, long long *idx, int k, cudaStream_t s);
+// rows [value, global index as a double, d coordinates] of the k slots into out (device, k x (d + 2)); empty slots -> [NaN, -1, NaN..]
+int launch_topk_pack(const double *vals, const long long *idx, const double *Xc_dev, int d, int k, long long index_offset, double *out,
+                     cudaStream_t s);
 int launch_min(const double *v, int n, double *out, cudaStream_t s);
 
 }  // namespace gpb

@@ -827,8 +827,9 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
   if (dbg < 0) { const char *e = getenv("GPB_OZAKI_DBG"); dbg = e ? atoi(e) : 0; }
   p.dbg = (nmod && dbg == 3) ? 0 : dbg;
   p.nmod = nmod;
-  static unsigned long long configured = 0;
-  if (needs_func_config(configured))
+  static FuncConfigMask configured{0};
+  FuncConfigOnce once_configured(configured);
+  if (once_configured.needed)
     GPB_CUDA(cudaFuncSetAttribute(ozaki_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   {
     cudaLaunchConfig_t cfg = {};

@@ -418,6 +418,31 @@ int launch_topk_update(const double *f, int n_c, long long index_base, double *v
   return 0;
 }
 
+// out[i] = [value, (double) global index, the candidate's d coordinates] for the k slots; a slot that never received a candidate
+// (fewer than k finite scores) becomes [NaN, -1, NaN ...] -- the "empty" convention of sharded.merge_topk
+__global__ void topk_pack_kernel(const double *__restrict__ vals, const long long *__restrict__ idx, const double *__restrict__ Xc, int d,
+                                 int k, long long index_offset, double *__restrict__ out) {
+  const int i = blockIdx.x;
+  if (i >= k) return;
+  const long long gi = idx[i];
+  const bool empty = gi == LLONG_MAX;
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  double *row = out + (size_t)i * (d + 2);
+  if (threadIdx.x == 0) {
+    row[0] = empty ? nan : vals[i];
+    row[1] = empty ? -1.0 : (double)gi;
+  }
+  for (int q = threadIdx.x; q < d; q += blockDim.x) row[2 + q] = empty ? nan : Xc[(size_t)(gi - index_offset) * d + q];
+}
+
+int launch_topk_pack(const double *vals, const long long *idx, const double *Xc_dev, int d, int k, long long index_offset, double *out,
+                     cudaStream_t s) {
+  topk_pack_kernel<<<k, 32, 0, s>>>(vals, idx, Xc_dev, d, k, index_offset, out);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
 __global__ void min_kernel(const double *__restrict__ v, int n, double *out) {
   __shared__ double sv[32];
   double m = DBL_MAX;

@@ -10,7 +10,7 @@ Reference interfaces mirrored (paths relative to /root/reference):
 """
 import numpy as np
 
-from . import native
+from . import _lib, native
 from .kern import Kern, RBF, Stationary
 from .parameterization import Logexp, Model, Param, Parameterized
 
@@ -63,16 +63,29 @@ class Gaussian(Parameterized):
         return c
 
 
+class StalePosteriorError(_lib.GpbError):
+    """A PosteriorExact (or its grad_dict) was used after the resident model it is a view of moved on.
+
+    Deviation from the reference, documented: GPy's Posterior is an immutable snapshot (posterior.py:19-77) holding its own N x N
+    arrays; here the N x N state lives once, on the GPU, and a posterior is a VIEW of it.  Every access checks a generation stamp:
+    after a later parameters_changed / set_XY -- or a FAILED fit (LinAlgError), after which the reference would still serve its
+    last valid posterior -- the old object raises this error instead of returning the new model's numbers (or a mix of both).
+    Host copies fetched while the posterior was current (woodbury_chol, woodbury_vector, ...) stay valid and are still served."""
+
+
 class _LazyGradDict(dict):
     """grad_dict of ExactGaussianInference.inference: 'dL_dK' (N x N) is only materialised when somebody reads it."""
 
     def __init__(self, nat, dL_dthetaL, alpha_getter):
         super(_LazyGradDict, self).__init__()
         self._nat = nat
+        self._gen = nat.generation
         dict.__setitem__(self, 'dL_dthetaL', dL_dthetaL)
         self._alpha_getter = alpha_getter
 
     def __missing__(self, key):
+        if key in ('dL_dK', 'dL_dm') and self._nat.generation != self._gen:
+            raise StalePosteriorError("grad_dict['%s'] requested after the model was refitted or its fit failed" % key)
         if key == 'dL_dK':
             v = self._nat.get("dL_dK")
         elif key == 'dL_dm':
@@ -91,13 +104,23 @@ class PosteriorExact(object):
     woodbury_inv = Ky^-1 are fetched from the device on first access."""
 
     def __init__(self, nat, kern, X):
-        self._nat = nat
+        self._native = nat
+        self._gen = nat.generation       # stamp of the fit this posterior belongs to
         self._kern = kern
         self._X = X
         self._cache = {}
 
+    @property
+    def _nat(self):
+        """The resident model, after checking that it still holds THIS posterior (see StalePosteriorError)."""
+        if self._native.generation != self._gen:
+            raise StalePosteriorError("this posterior is stale: the model behind it was refitted, received new data, or a later fit "
+                                      "failed (generation %d, posterior %d); use the model's current .posterior" %
+                                      (self._native.generation, self._gen))
+        return self._native
+
     def _get(self, what):
-        if what not in self._cache:
+        if what not in self._cache:                       # host copies made while current stay valid (a snapshot, like the reference's)
             self._cache[what] = self._nat.get(what)
         return self._cache[what]
 
@@ -232,7 +255,10 @@ class ExactGaussianInference(object):
             info, logL, grads = nat.fit(True)
         self._resident = (nat, theta, gw_key, X) if info == 0 else None
         if info != 0:
-            diag = float(kern.variance.values[0]) + noise + 1e-8
+            # mean of diag(Ky) (linalg.py:66): sigma_f^2 for the stationary kernels, sigma_f^(2 d) under the Gower patch, where
+            # K(x, x) is a product of d one-dimensional kernels that each carry the variance (stationary.py:116-135)
+            kdiag = float(kern.variance.values[0]) ** (X.shape[1] if gw is not None else 1)
+            diag = kdiag + noise + 1e-8
             if not diag > 0.:
                 raise np.linalg.LinAlgError("not pd: non-positive diagonal elements")
             jitter = diag * 1e-6

@@ -236,6 +236,10 @@ class NativeModel(object):
         self.nls = self.d if self.ard else 1
         self.n = 0
         self._ws = None
+        self._theta = (1.0, np.ones(self.nls), 1.0, 0.0)
+        # bumped by everything that changes what the resident posterior is (data, hyper-parameters, a fit, an append, an adopted
+        # broadcast): PosteriorExact objects are views of this model and compare their own stamp with it on every access
+        self.generation = 0
         ws_ptr, ws_bytes = None, 0
         if use_torch_workspace:
             try:
@@ -271,11 +275,13 @@ class NativeModel(object):
             X, Y = as_host(X), as_host(Y)
         n = X.shape[0]
         assert X.shape[1] == self.d and Y.shape == (n, self.p)
+        self.generation += 1
         check(self._lib.gpb_model_set_data(self._h, n, ptr(X), ptr(Y), int(dev)), "set_data")
         self.n = n
 
     def set_gower(self, gower):
         """Matern52(Gower=True, space=...): gower = (continuous dims, discrete dims, ranges) or None to switch it off."""
+        self.generation += 1
         if gower is None:
             check(self._lib.gpb_model_set_gower(self._h, 0, None, None), "set_gower")
             return
@@ -286,10 +292,16 @@ class NativeModel(object):
         ls = _ls(lengthscale)
         assert ls.size == self.nls
         check(self._lib.gpb_model_set_theta(self._h, float(variance), dptr(ls), float(noise)), "set_theta")
+        old = self._theta
+        if not (old[0] == float(variance) and old[2] == float(noise) and np.array_equal(old[1], ls)):   # bit-identical theta keeps
+            self.generation += 1                                                                          # the factorisation (C side)
+            self._theta = (float(variance), ls.copy(), float(noise), 0.0)
 
     def fit(self, want_grad=True, extra_jitter=0.0):
         """-> (info, log_marginal, grads or None); grads ordered [variance, lengthscale..., noise]."""
         out = np.zeros(3 + self.nls)
+        self._theta = self._theta[:3] + (float(extra_jitter),)
+        self.generation += 1
         rc = self._lib.gpb_model_fit(self._h, int(want_grad), float(extra_jitter), dptr(out))
         if rc < 0:
             check(rc, "fit")
@@ -304,6 +316,7 @@ class NativeModel(object):
         b = Xnew.shape[0]
         assert Xnew.shape[1] == self.d and Yall.shape == (self.n + b, self.p)
         out = np.zeros(3 + self.nls)
+        self.generation += 1
         rc = self._lib.gpb_model_append(self._h, b, ptr(Xnew), ptr(Yall), 0, int(want_grad), dptr(out))
         if rc < 0:
             check(rc, "append")
@@ -414,6 +427,63 @@ class NativeModel(object):
         check(self._lib.gpb_model_acq_topk_full(self._h, aid, float(par), float(fmin), mc, ptr(Xc), int(dev), int(k), int(index_offset),
                                                 dptr(vals), idx.ctypes.data_as(_lib.c_ll_p), dptr(pts), ptr(f), ptr(df)), "acq_topk_full")
         return vals, idx, pts, f, df
+
+    def acq_topk_dev(self, acq, par, fmin, Xc, k, index_offset=0, with_gradients=False, want_f=False, rows=None):
+        """Device-resident variant without a host synchronisation: Xc a CUDA tensor -> rows (k, d + 2) CUDA tensor of
+        [f, global index, coordinates] (empty slots [NaN, -1, NaN ...]) [, f (mc, 1), df (mc, d)], ready in stream order on the
+        model's stream (issue the all-gather behind it: sharded.all_gather_topk_device)."""
+        import torch
+        assert is_torch(Xc)
+        mc = Xc.shape[0]
+        if rows is None:
+            rows = torch.empty((k, self.d + 2), dtype=torch.float64, device=Xc.device)
+        f = torch.empty((mc, 1), dtype=torch.float64, device=Xc.device) if (want_f or with_gradients) else None
+        df = torch.empty((mc, self.d), dtype=torch.float64, device=Xc.device) if with_gradients else None
+        aid = acq if isinstance(acq, int) else ACQ_IDS[acq]
+        check(self._lib.gpb_model_acq_topk_dev(self._h, aid, float(par), float(fmin), mc, ptr(Xc), int(k), int(index_offset), ptr(rows),
+                                               ptr(f), ptr(df)), "acq_topk_dev")
+        return rows, f, df
+
+    # -- multi-GPU state distribution ----------------------------------------------------------------------------------
+    def state_tensor(self, what):
+        """A float64 CUDA tensor VIEW of a resident array ("Li" = L^-1, "alpha", "L", "Wi") inside the model's torch workspace."""
+        import torch
+        if self._ws is None:
+            raise _lib.GpbError("state_tensor needs the torch-owned workspace (use_torch_workspace=True)")
+        p, cnt = ctypes.c_void_p(), ctypes.c_size_t()
+        check(self._lib.gpb_model_state_ptr(self._h, what.encode(), ctypes.byref(p), ctypes.byref(cnt)), "state_ptr(%s)" % what)
+        off = p.value - self._ws.data_ptr()
+        assert 0 <= off and off + 8 * cnt.value <= self._ws.numel() and off % 8 == 0
+        return self._ws[off:off + 8 * cnt.value].view(torch.float64)
+
+    def theta(self):
+        return self._theta
+
+    def broadcast_state(self, src=0, group=None, parts=("Li", "alpha")):
+        """the rank that fitted (src) broadcasts theta, alpha and L^-1 (optionally L and Ky^-1) over NCCL; the other
+        ranks adopt them instead of refitting (GPModel.updateModel on every rank, gpmodel.py:78-93).  Every rank must hold the same
+        data (set_data).  Collective: call on every rank of the group."""
+        import torch
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        dev = self._ws.device
+        head = torch.zeros(4 + self.nls, dtype=torch.float64, device=dev)
+        if rank == src:
+            v, ls, nz, jit = self._theta
+            head[0], head[1], head[2], head[3] = float(self.n), v, nz, jit
+            head[4:] = torch.from_numpy(np.asarray(ls, dtype=np.float64))
+        dist.broadcast(head, src=src, group=group)
+        h = head.cpu().numpy()
+        assert int(h[0]) == self.n, "broadcast_state: rank %d holds %d points, the source %d" % (rank, self.n, int(h[0]))
+        for what in parts:
+            dist.broadcast(self.state_tensor(what), src=src, group=group)
+        torch.cuda.current_stream().synchronize()
+        if rank != src:
+            ls = np.ascontiguousarray(h[4:])
+            mask = (1 if "L" in parts else 0) | (2 if "Wi" in parts else 0)
+            self.generation += 1
+            check(self._lib.gpb_model_adopt_state(self._h, float(h[1]), dptr(ls), float(h[2]), float(h[3]), mask), "adopt_state")
+            self._theta = (float(h[1]), ls.copy(), float(h[2]), float(h[3]))
 
     def acq_topk(self, acq, par, fmin, Xc, k, index_offset=0):
         dev = is_torch(Xc)

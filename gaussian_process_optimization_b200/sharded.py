@@ -50,6 +50,29 @@ def all_gather_topk(vals, idx, pts, k, group=None, device=None):
     return merge_topk(allb[:, 0], allb[:, 1].astype(np.int64), allb[:, 2:], k)
 
 
+def all_gather_topk_device(rows, k, group=None):
+    """Device path of the same exchange: `rows` is the (k, d + 2) CUDA tensor NativeModel.acq_topk_dev left on the device
+    ([f, global index, coordinates]; empty slots carry index -1).  The all-gather is issued from the device buffer behind the
+    scoring kernels (same stream when the model runs on torch's current stream, ordered by NCCL's stream dependency otherwise) --
+    no device -> host -> device round trip in front of the collective; ONE small copy of world * k rows to the host at the end."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        allb = rows.cpu().numpy()
+    else:
+        world = dist.get_world_size(group)
+        if dist.get_backend(group) == "gloo":              # gloo has no CUDA all-gather (CPU tests, two ranks on one GPU): via the host
+            mine = rows.cpu()
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            allb = torch.cat(parts).numpy()
+        else:
+            out = torch.empty((world * rows.shape[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+            dist.all_gather_into_tensor(out, rows.contiguous(), group=group)
+            allb = out.cpu().numpy()
+    return merge_topk(allb[:, 0], allb[:, 1].astype(np.int64), allb[:, 2:], k)
+
+
 class ShardedAnchorScorer(object):
     """Score this rank's candidate shard and return the GLOBAL k best candidates (identical on every rank).
 

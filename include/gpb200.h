@@ -83,7 +83,7 @@ int gpb_potri(int n, const double *L, int ldl, double *Ai, int ldai, int dev, vo
 size_t gpb_model_workspace_bytes(int n_cap, int d, int p, int cand_block);
 /* GPRegression(X, Y, kernel, noise_var) (GPy/GPy/models/gp_regression.py:29-36, core/gp.py:38-110).
  * workspace: device memory owned by the caller (e.g. a torch tensor) of >= gpb_model_workspace_bytes, or NULL to let the
- * library cudaMalloc it.  ard: 1 -> d lengthscales, 0 -> one. */
+ * library cudaMalloc it.  ard: 1 -> d lengthscales, 0 -> one.  d <= 64, p <= 16. */
 int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap, int cand_block, void *workspace,
                      size_t workspace_bytes, void *stream);
 int gpb_model_destroy(gpb_model *m);
@@ -145,6 +145,25 @@ int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, c
  * gradient solves): "score a candidate list with gradients and keep the k best" (run.py:1240-1253 at scale, BASELINE config 4). */
 int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
                             long long index_offset, double *vals, long long *idx, double *pts, double *f, double *df);
+
+/* The same pass with everything left on the device and NO host synchronisation: candidates Xc_dev (mc x d), the k result rows
+ * rows_dev (k x (d + 2): [f, global index as a double, the candidate's d coordinates]; a slot that never received a candidate --
+ * fewer than k finite scores -- is [NaN, -1, NaN ...]), f_dev (mc, or NULL), df_dev (mc x d, or NULL to skip the gradient solves).
+ * Results are ready in stream order on the model's stream, so that the all-gather of the per-shard anchors
+ * (anchor_points_generator.py:58-63 on a sharded candidate set) can be issued behind it without a host round trip. */
+int gpb_model_acq_topk_dev(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc_dev, int k,
+                           long long index_offset, double *rows_dev, double *f_dev, double *df_dev);
+
+/* ---- multi-GPU state distribution (broadcast of theta, alpha, L^-1 per model update) ------------------------------ */
+/* Device address and length (doubles) of a resident array of the model, so that the caller can hand the collective library a view
+ * of it (NCCL broadcast from the rank that fitted, instead of refitting on every rank: GPModel.updateModel, gpmodel.py:78-93).
+ * what: "Li" = L^-1 (np x np, np = n rounded up to 128; what every predictive product reads), "alpha" (p x np),
+ * "L" (np x np), "Wi" = Ky^-1 (np x np; computed first if the fit did not need it).  The arrays keep their padded layout. */
+int gpb_model_state_ptr(gpb_model *m, const char *what, void **ptr, size_t *count);
+/* After the regions above have been overwritten with another rank's fitted state: adopt its hyper-parameters (and the jitter its
+ * fit needed) and mark the model fitted.  The data (gpb_model_set_data) must be the same on every rank.  have_mask: bit 0 = the
+ * "L" region was transferred, bit 1 = "Wi" was (otherwise get("L") / append are refused and Wi is rebuilt from L^-1 on demand). */
+int gpb_model_adopt_state(gpb_model *m, double variance, const double *lengthscale, double noise, double jitter, int have_mask);
 
 /* ---- raw building blocks (tests, benchmarks, roofline measurements) ------------------------------------------------ */
 /* C = alpha * op(A) op(B) + beta * C with the fp64 tensor-core (DMMA) engine; all of m, n multiples of 128, k of 16.

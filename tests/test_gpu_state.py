@@ -1,0 +1,149 @@
+"""Round-2 additions on the device path: posterior generation stamps, empty top-k slots, the input-dimension cap, and the
+multi-rank state distribution (rank 0 fits, theta / alpha / L^-1 are broadcast, the other ranks adopt them instead of refitting;
+SURVEY.md 8e) with the device-side all-gather of the per-shard anchors.
+
+The two-rank test runs both ranks on ONE GPU over the gloo backend (the driver's GPU box has a single B200; NCCL refuses two
+ranks on one device) -- the same code path as `bench.py --gpus N` over NCCL up to the transport underneath torch.distributed.
+"""
+import os
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+pytestmark = pytest.mark.gpu
+
+native = pytest.importorskip("gaussian_process_optimization_b200.native")
+from gaussian_process_optimization_b200 import GPy, _lib, sharded  # noqa: E402
+from gaussian_process_optimization_b200.models import StalePosteriorError  # noqa: E402
+
+
+def _data(n=200, d=3, seed=3):
+    rs = np.random.RandomState(seed)
+    X = rs.uniform(0, 1, (n, d))
+    Y = np.sin(X.sum(1))[:, None] + 0.05 * rs.randn(n, 1)
+    return X, (Y - Y.mean()) / Y.std()
+
+
+def test_posterior_is_a_stamped_view_of_the_resident_model():
+    X, Y = _data()
+    m = GPy.models.GPRegression(X, Y, kernel=GPy.kern.RBF(3, ARD=True), noise_var=0.1)
+    old = m.posterior
+    L_old = old.woodbury_chol.copy()               # fetched while current: a host snapshot
+    mu_old, _ = m.predict(X[:5])
+    m.kern.variance[:] = 2.0                        # parameters_changed -> a new fit, a new posterior
+    assert m.posterior is not old
+    with pytest.raises(StalePosteriorError):
+        old._raw_predict(m.kern, X[:5], X)
+    with pytest.raises(StalePosteriorError):
+        old.woodbury_inv                            # never fetched while current: would read the NEW model's Ky^-1
+    assert np.array_equal(old.woodbury_chol, L_old)  # the snapshot taken in time is still served
+    mu_new, _ = m.predict(X[:5])
+    assert not np.allclose(mu_new, mu_old)
+
+
+def test_posterior_after_a_failed_fit_is_stale_not_silently_wrong():
+    X, Y = _data(60, 2)
+    X[1] = X[0]                                     # duplicated input and (below) zero noise: not positive definite even with jitter
+    m = GPy.models.GPRegression(X, Y, kernel=GPy.kern.RBF(2), noise_var=0.1)
+    good = m.posterior
+    with pytest.raises(np.linalg.LinAlgError):
+        m.kern.lengthscale[:] = np.nan
+    with pytest.raises(StalePosteriorError):
+        good._raw_predict(m.kern, X[:3], X)
+    m.kern.lengthscale[:] = 0.7                     # a valid write refits; the model's own posterior works again
+    mu, var = m.predict(X[:3])
+    assert np.all(np.isfinite(mu)) and np.all(var > 0)
+
+
+def test_topk_slots_without_a_finite_score_are_reported_empty():
+    X, Y = _data()
+    nm = native.NativeModel("rbf", True, 3, 1, n_cap=256, cand_block=128)
+    nm.set_data(X, Y)
+    nm.set_theta(1.0, np.array([0.5, 0.6, 0.7]), 1e-2)
+    assert nm.fit(False)[0] == 0
+    fmin = nm.fmin()
+    Xc = np.random.RandomState(1).uniform(0, 1, (8, 3))
+    Xc[2:] = np.nan                                 # only two candidates have a finite score
+    vals, idx, pts = nm.acq_topk("EI", 0.01, fmin, Xc, 5)
+    assert sorted(idx[:2].tolist()) == [0, 1] and np.all(idx[2:] == -1)
+    assert np.all(np.isfinite(vals[:2])) and np.all(np.isnan(vals[2:])) and np.all(np.isnan(pts[2:]))
+    mv, mi, mp = sharded.merge_topk(vals, idx, pts, 5)
+    assert mi.tolist() == idx[:2].tolist()
+    import torch
+    rows, _, _ = nm.acq_topk_dev("EI", 0.01, fmin, torch.from_numpy(Xc).cuda(), 5)
+    torch.cuda.synchronize()
+    r = rows.cpu().numpy()
+    assert r[:2, 1].tolist() == idx[:2].astype(float).tolist() and np.all(r[2:, 1] == -1) and np.all(np.isnan(r[2:, 0]))
+    assert np.array_equal(r[:2, 0], vals[:2]) and np.array_equal(r[:2, 2:], Xc[idx[:2]])
+    nm.close()
+
+
+def test_input_dimension_cap_is_enforced_at_creation():
+    with pytest.raises(_lib.GpbError, match="input_dim"):
+        native.NativeModel("rbf", True, 65, 1, n_cap=128, cand_block=128)
+    nm = native.NativeModel("rbf", True, 64, 1, n_cap=128, cand_block=128)       # the advertised maximum: fit AND query work
+    rs = np.random.RandomState(0)
+    X = rs.uniform(0, 1, (100, 64))
+    Y = rs.randn(100, 1)
+    nm.set_data(X, Y)
+    nm.set_theta(1.0, np.full(64, 2.0), 0.1)
+    assert nm.fit(True)[0] == 0
+    r = nm.acquisition("EI", 0.01, nm.fmin(), X[:3] + 0.01, with_gradients=True)
+    assert np.all(np.isfinite(r["f"])) and np.all(np.isfinite(r["df"]))
+    nm.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _rank_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    n, d = 700, 5
+    X, Y = _data(n, d, seed=11)
+    ls = 0.4 + 0.1 * np.arange(d)
+    nm = native.NativeModel("mat52", True, d, 1, n_cap=n, cand_block=256)
+    nm.set_data(X, Y)
+    if rank == 0:                                   # only rank 0 fits
+        nm.set_theta(1.3, ls, 1e-3)
+        info, logL, _ = nm.fit(False)
+        assert info == 0
+    nm.broadcast_state(src=0)                       # the others adopt theta, alpha, L^-1
+    fmin = nm.fmin()
+    Xc = np.random.RandomState(5).uniform(0, 1, (3000, d))
+    lo, hi = sharded.divide_candidates(Xc.shape[0], rank, world)
+    rows, f, df = nm.acq_topk_dev("EI", 0.01, fmin, torch.from_numpy(Xc[lo:hi]).cuda(), 5, index_offset=lo, with_gradients=True)
+    vals, idx, pts = sharded.all_gather_topk_device(rows, 5)
+    if rank != 0:                                   # L was not part of the broadcast: asking for it is refused, not answered wrongly
+        with pytest.raises(_lib.GpbError):
+            nm.get("L")
+    np.savez(out % rank, vals=vals, idx=idx, pts=pts, fmin=fmin, f=f.cpu().numpy().ravel(), df=df.cpu().numpy(), lo=lo, hi=hi,
+             alpha=nm.get("alpha"))
+    nm.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_broadcast_the_fitted_state_and_gather_anchors_on_the_device(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r%d.npz")
+    mp.spawn(_rank_worker, args=(2, 29800 + (os.getpid() % 2000), out), nprocs=2, join=True)
+    n, d = 700, 5
+    X, Y = _data(n, d, seed=11)
+    nm = native.NativeModel("mat52", True, d, 1, n_cap=n, cand_block=256)
+    nm.set_data(X, Y)
+    nm.set_theta(1.3, 0.4 + 0.1 * np.arange(d), 1e-3)
+    assert nm.fit(False)[0] == 0
+    fmin = nm.fmin()
+    Xc = np.random.RandomState(5).uniform(0, 1, (3000, d))
+    vals, idx, pts, f, df = nm.acq_topk_full("EI", 0.01, fmin, Xc, 5)
+    z = [np.load(out % r) for r in range(2)]
+    for r in range(2):
+        assert np.array_equal(z[r]["idx"], idx) and np.array_equal(z[r]["vals"], vals) and np.array_equal(z[r]["pts"], pts)
+        assert z[r]["fmin"] == fmin
+        assert np.array_equal(z[r]["alpha"], nm.get("alpha"))            # the adopted state IS rank 0's fit, bit for bit
+        lo, hi = int(z[r]["lo"]), int(z[r]["hi"])
+        assert_allclose(z[r]["f"], f.ravel()[lo:hi], rtol=1e-13, atol=1e-300)   # (block boundaries differ between shard and full pass)
+        assert_allclose(z[r]["df"], df[lo:hi], rtol=1e-11, atol=1e-13 * np.abs(df).max())
+    nm.close()
