@@ -226,6 +226,7 @@ struct gpb_model {
   } graphs[2];
   bool graph_failed = false, own_stream = false;
   cudaEvent_t entry_ev = nullptr;   // own_stream: orders the model's private non-blocking stream after the legacy default stream at call entry
+  cudaEvent_t exit_ev = nullptr;    // ... and the legacy stream after ours at the exit of the entry points that do not synchronise
   double *theta_dev = nullptr;
   int wi_from = 0;  // > 0 (after gpb_model_append): the leading wi_from block of W holds the old Ky^-1, downdated; rows beyond are stale
   cudaStream_t stream = 0;
@@ -265,6 +266,16 @@ static int check_device(const gpb_model *m, const char *what) {
     // it returns, which orders the other direction.
     GPB_CUDA(cudaEventRecord(m->entry_ev, cudaStreamLegacy));
     GPB_CUDA(cudaStreamWaitEvent(m->stream, m->entry_ev, 0));
+  }
+  return 0;
+}
+
+// Exit of an entry point that returns WITHOUT synchronising (gpb_model_acq_topk_dev): the caller named the legacy default stream,
+// so whatever it queues there next (a collective, a copy, an event) must come after our work on the private stream.
+static int leave_stream_ordered(gpb_model *m) {
+  if (m->own_stream && m->exit_ev) {
+    GPB_CUDA(cudaEventRecord(m->exit_ev, m->stream));
+    GPB_CUDA(cudaStreamWaitEvent(cudaStreamLegacy, m->exit_ev, 0));
   }
   return 0;
 }
@@ -364,6 +375,7 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
     if (m->pinned) cudaFreeHost(m->pinned);
     if (m->own_ws && m->ws) cudaFree(m->ws);
     if (m->entry_ev) cudaEventDestroy(m->entry_ev);
+    if (m->exit_ev) cudaEventDestroy(m->exit_ev);
     if (m->own_stream) cudaStreamDestroy(m->stream);
     delete m;
     return rc;
@@ -384,7 +396,8 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
     // it against the legacy stream explicitly (check_device).
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess) {
       m->own_stream = true;
-      if (cudaEventCreateWithFlags(&m->entry_ev, cudaEventDisableTiming) != cudaSuccess) {
+      if (cudaEventCreateWithFlags(&m->entry_ev, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&m->exit_ev, cudaEventDisableTiming) != cudaSuccess) {
         set_error("model_create: cudaEventCreate failed");
         return fail(-1);
       }
@@ -436,6 +449,7 @@ int gpb_model_destroy(gpb_model *m) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
   factor_overlap_destroy(m->ov);
   if (m->entry_ev) cudaEventDestroy(m->entry_ev);
+  if (m->exit_ev) cudaEventDestroy(m->exit_ev);
   if (m->own_stream) cudaStreamDestroy(m->stream);
   if (m->lp_buf) cudaFree(m->lp_buf);
   if (m->own_ws && m->ws) cudaFree(m->ws);
@@ -1158,7 +1172,8 @@ int gpb_model_acq_topk_dev(gpb_model *m, int acq, double par, double fmin, int m
   GPB_REQUIRE(m && Xc_dev && rows_dev, "acq_topk_dev: NULL argument");
   GPB_TRY(acq_topk_check(m, acq, mc, k, "acq_topk_dev"));
   AllocStream alloc_scope(m->stream);
-  return acq_topk_pass(m, acq, par, fmin, mc, Xc_dev, 1, k, index_offset, f_dev, df_dev, rows_dev);
+  GPB_TRY(acq_topk_pass(m, acq, par, fmin, mc, Xc_dev, 1, k, index_offset, f_dev, df_dev, rows_dev));
+  return leave_stream_ordered(m);
 }
 
 // ---- multi-GPU state distribution -------------------------------------------------------------------------------------------

@@ -154,9 +154,11 @@ static int launch_skinny_moments_t(const double *KxT, const double *Vt, const do
                                    const double *XcT, int ldc, const double *XT, int ldx, int d, double variance,
                                    const double *inv_ls, double var_base, int want_g, double *part, double *mu, double *var,
                                    double *dmu, double *dvar, cudaStream_t s) {
-  // about four CTAs per SM in total, at least one 128-point chunk each
+  // about four CTAs per SM for ONE candidate, at least one 128-point chunk each.  The split of the training points must not depend
+  // on n_c: a candidate's sums are then bit-identical whether it is evaluated alone or together with up to seven others, which is
+  // what lets the host coalesce the M = 1 requests of concurrent L-BFGS-B runs into one call without changing any trajectory.
   const int max_splits = (n + SKM_THREADS - 1) / SKM_THREADS;
-  int splits = std::max(1, std::min(max_splits, (148 * 4) / n_c));
+  int splits = std::max(1, std::min(max_splits, 148 * 4));
   const int chunk = ((n + splits - 1) / splits + SKM_THREADS - 1) / SKM_THREADS * SKM_THREADS;
   splits = (n + chunk - 1) / chunk;
   skinny_moments_partial_kernel<KIND, DCAP><<<dim3(splits, n_c), SKM_THREADS, 0, s>>>(KxT, Vt, Ut, ld, n, chunk, alpha, XcT, ldc, XT, ldx,

@@ -315,6 +315,7 @@ class BOModel(object):
     """models/base.py:7-33."""
     MCMC_sampler = False
     analytical_gradient_prediction = False
+    batched_rows_bitwise = False     # True: row i of a batched predict / acquisition call equals the single-row call bit for bit
 
     def updateModel(self, X_all, Y_all, X_new, Y_new):
         raise NotImplementedError
@@ -333,6 +334,7 @@ class GPModel(BOModel):
     """models/gpmodel.py:9-177 on the B200 GPRegression."""
 
     analytical_gradient_prediction = True
+    batched_rows_bitwise = True      # the device path's per-candidate sums do not depend on how many candidates share a call
     CONCURRENT_MIN_N, CONCURRENT_MAX_N = 384, 6144     # where several restarts at a time pay (scripts/concurrent_restarts_perf.py)
 
     def __init__(self, kernel=None, noise_var=None, exact_feval=False, optimizer='bfgs', max_iters=1000, optimize_restarts=5,
@@ -476,6 +478,11 @@ class AcquisitionBase(object):
         ind = self.space.indicator_constraints(x)
         return -f_acq_cost * ind, -df_acq_cost * ind
 
+    @property
+    def batched_rows_bitwise(self):
+        """What lets AcquisitionOptimizer refine its anchors in lockstep (LockstepEvaluator): inherited from the model."""
+        return bool(getattr(self.model, 'batched_rows_bitwise', False))
+
     def optimize(self, duplicate_manager=None):
         if not self.analytical_gradient_acq:
             out = self.optimizer.optimize(f=self.acquisition_function, duplicate_manager=duplicate_manager)
@@ -564,6 +571,12 @@ class AcquisitionLP(AcquisitionBase):
         self.r_x0 = None
         self.s_x0 = None
         self._pushed_to = None
+
+    @property
+    def batched_rows_bitwise(self):
+        """Only the device pass qualifies: the reference's NumPy gradient formula broadcasts correctly for one point at a time only
+        (LP.py:129-132)."""
+        return bool(getattr(self.model, 'batched_rows_bitwise', False)) and self._native_kind() is not None
 
     # -- device path -----------------------------------------------------------------------------------------------------
     def _native_kind(self):
@@ -731,6 +744,68 @@ def apply_optimizer(optimizer, x0, f=None, df=None, f_df=None, duplicate_manager
     return suggested_x_rounded, f(suggested_x_rounded)
 
 
+class LockstepEvaluator(object):
+    """Coalesces the f_df requests of several concurrent L-BFGS-B runs into ONE device call.
+
+    The refinements of the anchor points (acquisition_optimizer.py:60-75) are independent; each one is a chain of several hundred
+    M = 1 acquisition calls, and one such call streams the whole triangle of L^-1 twice (2 x 8 N^2 / 2 bytes).  The device path
+    serves up to 8 candidates for the SAME single pass over the triangle, with per-candidate sums that are bit-identical to the
+    M = 1 call (fixed reduction orders that do not depend on the number of candidates).  So the runs are advanced in lockstep: every
+    run lives in its own host thread with an UNMODIFIED scipy.optimize.fmin_l_bfgs_b; a run that needs (f, df) parks its x here, and
+    when every still-active run has parked one, a single batched call answers all of them.  Each run sees exactly the values the
+    sequential loop would have given it -> same trajectories, same optimum, 1 / (number of runs) of the bytes streamed.
+    """
+
+    def __init__(self, f_df, n_workers, max_rows=8):
+        import threading
+        self.f_df, self.max_rows = f_df, max_rows
+        self.cv = threading.Condition()
+        self.active = n_workers
+        self.pending = {}      # worker -> x (1, d)
+        self.results = {}      # worker -> (f (1, 1), df (1, d)) or an exception
+        self.calls = 0         # device calls issued
+        self.requests = 0      # f_df requests answered
+
+    def _flush_locked(self):
+        """Called with the lock held when every active run has a request parked: answer them, max_rows per device call."""
+        workers = sorted(self.pending)
+        for a in range(0, len(workers), self.max_rows):
+            grp = workers[a:a + self.max_rows]
+            X = np.vstack([self.pending[w] for w in grp])
+            try:
+                fx, dfx = self.f_df(X)
+                fx, dfx = np.asarray(fx), np.asarray(dfx)          # row slices keep the shapes a single-row call returns
+                assert fx.shape[0] == len(grp) and dfx.shape[0] == len(grp)
+                for i, w in enumerate(grp):
+                    self.results[w] = (fx[i:i + 1].copy(), dfx[i:i + 1].copy())
+            except Exception as exc:                       # every run of the group sees the failure
+                for w in grp:
+                    self.results[w] = exc
+            self.calls += 1
+            self.requests += len(grp)
+        self.pending.clear()
+        self.cv.notify_all()
+
+    def evaluate(self, worker, x):
+        with self.cv:
+            self.pending[worker] = np.atleast_2d(np.array(x, dtype=np.float64))
+            if len(self.pending) == self.active:
+                self._flush_locked()
+            while worker not in self.results:
+                self.cv.wait()
+            r = self.results.pop(worker)
+        if isinstance(r, Exception):
+            raise r
+        return r
+
+    def retire(self, worker):
+        """The run of `worker` has ended: the others no longer wait for it."""
+        with self.cv:
+            self.active -= 1
+            if self.pending and len(self.pending) == self.active:
+                self._flush_locked()
+
+
 class ObjectiveAnchorPointsGenerator(object):
     """optimization/anchor_points_generator.py:8-98: 1000 random points, scored in ONE batched call, keep the 5 lowest."""
 
@@ -778,10 +853,62 @@ class AcquisitionOptimizer(object):
         world, rank = self._world()
         if world > 1:
             optimized_points = self._optimize_anchors_distributed(anchor_points, run, world, rank)
+        elif self._lockstep_ok(f_df, anchor_points):
+            optimized_points = self._optimize_anchors_lockstep(anchor_points, f, f_df, duplicate_manager)
         else:
             optimized_points = [run(a) for a in anchor_points]
         x_min, fx_min = min(optimized_points, key=lambda t: t[1])
         return x_min, fx_min
+
+    # -- all anchors refined concurrently, their M = 1 requests coalesced into one M <= 8 device call (LockstepEvaluator) ----------
+    # Needs an f_df whose rows are bit-identical to single-row calls: the CUDA acquisition path declares it
+    # (`batched_rows_bitwise`); the kwarg lockstep_anchors=False forces the sequential loop.
+    def _lockstep_ok(self, f_df, anchor_points):
+        if f_df is None or len(anchor_points) < 2 or not self.kwargs.get('lockstep_anchors', True):
+            return False
+        owner = getattr(f_df, '__self__', None)
+        return bool(getattr(owner, 'batched_rows_bitwise', False))
+
+    def _optimize_anchors_lockstep(self, anchor_points, f, f_df, duplicate_manager):
+        import threading
+        anchor_points = [np.atleast_2d(a) for a in anchor_points]
+        # the duplicate check of apply_optimizer happens before any evaluation: keep its error in anchor order
+        if duplicate_manager:
+            for a in anchor_points:
+                if duplicate_manager.is_unzipped_x_duplicate(a):
+                    raise ValueError("The starting point of the optimizer cannot be a duplicate.")
+        na = len(anchor_points)
+        ev = LockstepEvaluator(f_df, na)
+        out, errors = [None] * na, [None] * na
+        dev = None
+        try:
+            import torch
+            if torch.cuda.is_available() and torch.cuda.is_initialized():
+                dev = torch.cuda.current_device()
+        except ImportError:
+            torch = None
+
+        def work(i):
+            try:
+                if dev is not None:
+                    torch.cuda.set_device(dev)              # the current CUDA device is per host thread
+                out[i] = apply_optimizer(self.optimizer, anchor_points[i], f=f, df=None, f_df=lambda x: ev.evaluate(i, x),
+                                         duplicate_manager=duplicate_manager, space=self.space)
+            except Exception as exc:
+                errors[i] = exc
+            finally:
+                ev.retire(i)
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(na)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errors:
+            if e is not None:
+                raise e
+        self.lockstep_stats = {"device_calls": ev.calls, "requests": ev.requests}
+        return out
 
     # -- one L-BFGS-B refinement per torch.distributed rank (kwarg distributed_anchors=True) ---------------------------------
     # The refinements of the anchor points (acquisition_optimizer.py:68-72) are independent and deterministic, so rank r runs

@@ -149,7 +149,8 @@ int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int 
 /* The same pass with everything left on the device and NO host synchronisation: candidates Xc_dev (mc x d), the k result rows
  * rows_dev (k x (d + 2): [f, global index as a double, the candidate's d coordinates]; a slot that never received a candidate --
  * fewer than k finite scores -- is [NaN, -1, NaN ...]), f_dev (mc, or NULL), df_dev (mc x d, or NULL to skip the gradient solves).
- * Results are ready in stream order on the model's stream, so that the all-gather of the per-shard anchors
+ * Results are ready in stream order on the stream the model was created with (for a model created on the legacy default stream --
+ * which runs on a private non-blocking stream -- the legacy stream is made to wait for it), so that the all-gather of the per-shard anchors
  * (anchor_points_generator.py:58-63 on a sharded candidate set) can be issued behind it without a host round trip. */
 int gpb_model_acq_topk_dev(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc_dev, int k,
                            long long index_offset, double *rows_dev, double *f_dev, double *df_dev);

@@ -88,6 +88,8 @@ def oracle_gp_regression(X, Y, kernel, noise_var=1.):
 class OracleGPModel(gpyopt.GPModel):
     """GPyOpt GPModel whose GP runs on the oracle (same class otherwise: updateModel, optimize_restarts, predict, ...)."""
 
+    batched_rows_bitwise = False    # NumPy / BLAS pick different kernels for 1-row and 5-row products: keep the sequential anchor loop
+
     def _create_model(self, X, Y):
         self.input_dim = X.shape[1]
         if self.kernel is None:

@@ -147,3 +147,53 @@ def test_two_ranks_broadcast_the_fitted_state_and_gather_anchors_on_the_device(t
         assert_allclose(z[r]["f"], f.ravel()[lo:hi], rtol=1e-13, atol=1e-300)   # (block boundaries differ between shard and full pass)
         assert_allclose(z[r]["df"], df[lo:hi], rtol=1e-11, atol=1e-13 * np.abs(df).max())
     nm.close()
+
+
+@pytest.mark.parametrize("n,d", [(700, 5), (5000, 16)])
+def test_rows_of_a_batched_call_equal_the_single_row_calls_bitwise(n, d):
+    """What LockstepEvaluator relies on: up to 8 candidates share one pass over the triangle of L^-1 and each one's sums are the ones
+    the M = 1 call forms (EI, LCB and the penalised LP acquisition, value and gradient)."""
+    X, Y = _data(n, d, seed=n)
+    nm = native.NativeModel("mat52", True, d, 1, n_cap=n, cand_block=256)
+    nm.set_data(X, Y)
+    nm.set_theta(1.1, 0.4 + 0.05 * np.arange(d), 1e-3)
+    assert nm.fit(False)[0] == 0
+    fmin = nm.fmin()
+    rs = np.random.RandomState(8)
+    nm.set_penalizers("none", rs.uniform(0, 1, (3, d)), np.array([0.3, 0.2, 0.1]), np.array([0.05, 0.04, 0.03]))
+    for mc in (2, 3, 5, 8):
+        Xc = rs.uniform(0, 1, (mc, d))
+        for acq, par in (("EI", 0.01), ("LCB", 2.0)):
+            r = nm.acquisition(acq, par, fmin, Xc, with_gradients=True, want_moments=True)
+            f_lp, df_lp = nm.acquisition_lp(acq, par, fmin, Xc, with_gradients=True)
+            for i in range(mc):
+                r1 = nm.acquisition(acq, par, fmin, Xc[i:i + 1], with_gradients=True, want_moments=True)
+                for key in ("f", "df", "m", "s", "dmdx", "dsdx"):
+                    assert np.array_equal(r[key][i:i + 1], r1[key]), (mc, acq, key)
+                f1, df1 = nm.acquisition_lp(acq, par, fmin, Xc[i:i + 1], with_gradients=True)
+                assert np.array_equal(f_lp[i:i + 1], f1) and np.array_equal(df_lp[i:i + 1], df1)
+    nm.close()
+
+
+def test_bo_anchor_refinement_in_lockstep_equals_the_sequential_loop():
+    """AcquisitionOptimizer on the CUDA GPModel refines its 5 anchors concurrently with coalesced device calls; the suggested point
+    must be the one the sequential loop finds, bit for bit, in fewer device calls."""
+    from gaussian_process_optimization_b200 import GPyOpt
+    rs = np.random.RandomState(2)
+    X = rs.uniform(0, 1, (60, 4))
+    Y = (np.sin(3 * X[:, :1]) + (X[:, 1:2] - 0.4) ** 2 + 0.1 * X[:, 2:3] * X[:, 3:4])
+    space = GPyOpt.core.task.space.Design_space([{'name': 'x%d' % i, 'type': 'continuous', 'domain': (0, 1)} for i in range(4)])
+    out = {}
+    for mode in (True, False):
+        gm = GPyOpt.models.GPModel(exact_feval=True, optimize_restarts=1, verbose=False, max_iters=50)
+        np.random.seed(5)
+        gm.updateModel(X, Y, None, None)
+        opt = GPyOpt.optimization.AcquisitionOptimizer(space, lockstep_anchors=mode)
+        acq = GPyOpt.acquisitions.AcquisitionEI(gm, space, opt, jitter=0.01)
+        np.random.seed(7)
+        c0 = native.launch_count()
+        x, fx = acq.optimize()
+        out[mode] = (x, fx, native.launch_count() - c0, getattr(opt, "lockstep_stats", None))
+    assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
+    assert out[True][3] is not None and out[True][3]["device_calls"] < out[True][3]["requests"]
+    assert out[True][2] < out[False][2]                   # fewer kernels launched for the same answer

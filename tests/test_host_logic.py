@@ -185,3 +185,58 @@ def test_sharded_topk_gloo_world_size_2(tmp_path):
         assert np.array_equal(z["idx"], order)
         assert_allclose(z["vals"], s[order])
         assert_allclose(z["pts"], X[order])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LockstepEvaluator: concurrent L-BFGS-B runs, their f_df requests coalesced into batched calls
+# ---------------------------------------------------------------------------------------------------------------------
+def test_lockstep_evaluator_gives_every_run_its_sequential_trajectory():
+    """Five bounded L-BFGS-B runs on a row-wise function: in lockstep (threads + coalesced calls) every run must see exactly the
+    values the sequential loop gives it -- same iterates, same optimum -- while the number of batched calls is the LONGEST run's
+    request count, not the sum."""
+    from gaussian_process_optimization_b200 import gpyopt as G
+
+    class Acq(object):
+        batched_rows_bitwise = True
+
+        def __init__(self):
+            self.calls, self.rows = 0, 0
+
+        def f(self, X):
+            X = np.atleast_2d(X)
+            return (np.sum((X - 0.3) ** 2 * np.array([1.0, 10.0, 100.0]), axis=1) + np.sin(3 * X[:, 0]))[:, None]
+
+        def f_df(self, X):
+            X = np.atleast_2d(X)
+            self.calls += 1
+            self.rows += X.shape[0]
+            df = 2 * (X - 0.3) * np.array([1.0, 10.0, 100.0])
+            df[:, 0] += 3 * np.cos(3 * X[:, 0])
+            return self.f(X), df
+
+    space = G.Design_space([{'name': 'x%d' % i, 'type': 'continuous', 'domain': (0, 1)} for i in range(3)])
+    anchors = np.random.RandomState(3).uniform(0, 1, (5, 3))
+    a_seq, a_lock = Acq(), Acq()
+    opt = G.AcquisitionOptimizer(space)
+    opt.optimizer = G.OptLbfgs(space.get_bounds())
+    seq = [G.apply_optimizer(opt.optimizer, a, f=a_seq.f, f_df=a_seq.f_df, space=space) for a in anchors]
+    lock = opt._optimize_anchors_lockstep(anchors, a_lock.f, a_lock.f_df, None)
+    for (xs, fs), (xl, fl) in zip(seq, lock):
+        assert np.array_equal(xs, xl) and np.array_equal(fs, fl)
+    assert a_lock.rows == a_seq.rows                      # the same requests were answered ...
+    assert a_lock.calls < a_seq.calls                     # ... in fewer calls
+    assert opt.lockstep_stats["requests"] == a_seq.rows
+    assert opt._lockstep_ok(a_lock.f_df, anchors) and not opt._lockstep_ok(a_lock.f_df, anchors[:1])
+
+
+def test_lockstep_evaluator_propagates_errors_and_does_not_deadlock():
+    from gaussian_process_optimization_b200 import gpyopt as G
+
+    def bad(X):
+        raise RuntimeError("device call failed")
+
+    space = G.Design_space([{'name': 'x', 'type': 'continuous', 'domain': (0, 1)}])
+    opt = G.AcquisitionOptimizer(space)
+    opt.optimizer = G.OptLbfgs(space.get_bounds())
+    with pytest.raises(RuntimeError, match="device call failed"):
+        opt._optimize_anchors_lockstep(np.array([[0.2], [0.7], [0.9]]), lambda X: np.zeros((np.atleast_2d(X).shape[0], 1)), bad, None)
