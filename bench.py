@@ -668,33 +668,40 @@ def bench_other_configs(model16k):
 
 
 def bench_refinement_call(model):
-    """EI value + gradient at ONE candidate (optimizer.py:46-51: what L-BFGS-B calls hundreds of times per BO step), host in /
-    host out through the C ABI.  Bound: HBM -- M k* and M^T (M k*) each stream the lower triangle of M = L^-1 once."""
+    """EI value + gradient at M = 1, 5 and 8 candidates per call (optimizer.py:46-51: what L-BFGS-B calls hundreds of times per BO
+    step; the host's LockstepEvaluator coalesces the anchors' requests into one M <= 8 call), host in / host out through the C ABI.
+    Bound: HBM -- M k* and M^T (M k*) each stream the lower triangle of M = L^-1 once, whatever M <= 8 is."""
     import torch
     fmin = model.fmin()
     rs = np.random.RandomState(77)
-    xs = rs.uniform(0, 1, (24, 1, DIM))
-    for i in range(4):
-        model.acquisition("EI", 0.01, fmin, xs[i], with_gradients=True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(4, 24):
-        model.acquisition("EI", 0.01, fmin, xs[i], with_gradients=True)
-    torch.cuda.synchronize()
-    t = (time.perf_counter() - t0) / 20
     nbytes = 2 * 8.0 * N_TRAIN * (N_TRAIN + 128) / 2          # two passes over the lower 128-blocks of M
     peak = None
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    out = {"metric": "ei_value_gradient_m1_calls_per_s", "value": 1.0 / t, "unit": "calls/s", "ms_per_call": t * 1e3, "model_N": N_TRAIN,
-           "D": DIM, "roofline": {"bound": "hbm", "achieved": nbytes / t / 1e9, "unit": "GB/s", "peak": peak,
-                                  "frac": (nbytes / t / 1e9 / peak) if peak else None,
-                                  "algorithmic_bytes_per_call": nbytes,
-                                  "note": "wall clock around the whole C-ABI call (H2D of x*, 9 launches, D2H of f and df), not the "
-                                          "two streaming kernels alone; peak = MEASURED_PEAKS.json hbm_gbs"}}
-    return out
+    out = {}
+    for mc in (1, 5, 8):
+        xs = rs.uniform(0, 1, (44, mc, DIM))
+        for i in range(4):
+            model.acquisition("EI", 0.01, fmin, xs[i], with_gradients=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(4, 44):
+            model.acquisition("EI", 0.01, fmin, xs[i], with_gradients=True)
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) / 40
+        out["m%d" % mc] = {"ms_per_call": t * 1e3, "us_per_candidate": t * 1e6 / mc, "gbs": nbytes / t / 1e9,
+                           "frac": (nbytes / t / 1e9 / peak) if peak else None}
+    t1 = out["m1"]["ms_per_call"] * 1e-3
+    return {"metric": "ei_value_gradient_m1_calls_per_s", "value": 1.0 / t1, "unit": "calls/s", "ms_per_call": t1 * 1e3, "model_N": N_TRAIN,
+            "D": DIM, "batched": out,
+            "roofline": {"bound": "hbm", "achieved": nbytes / t1 / 1e9, "unit": "GB/s", "peak": peak,
+                         "frac": (nbytes / t1 / 1e9 / peak) if peak else None,
+                         "algorithmic_bytes_per_call": nbytes,
+                         "note": "wall clock around the whole C-ABI call (staged H2D of x*, the fused cooperative kernel "
+                                 "skinny_fused_kernel + the acquisition epilogue, staged D2H of f and df, one synchronisation), not the "
+                                 "kernel alone; peak = MEASURED_PEAKS.json hbm_gbs"}}
 
 
 def bench_ei_sharded(args, rank, world, barrier):

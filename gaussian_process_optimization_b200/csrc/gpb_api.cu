@@ -242,7 +242,12 @@ struct gpb_model {
          *dvar = nullptr, *fbuf = nullptr, *dfbuf = nullptr, *sdbuf = nullptr, *dsbuf = nullptr;
   double *topv = nullptr;
   long long *topi = nullptr;
-  double *pinned = nullptr;  // host, 256 doubles
+  double *sk_part3 = nullptr;   // per-CTA sums + arrival counter of the fused M <= 8 call (gpb_skinny.cu)
+  double *pinned = nullptr;  // host: [0, 256) results / hyper-parameters of a fit; [PIN_X, +512) staged candidates and
+                             // [PIN_OUT, +PIN_OUT_DOUBLES) staged results of the M <= 8 calls (one synchronisation per call)
+  struct Staged { double *dst; size_t off, count; };
+  std::vector<Staged> staged;  // device -> pinned copies in flight: unpacked into the caller's arrays after the synchronisation
+  size_t staged_used = 0;
   FactorOverlap *ov = nullptr;  // streams / events of the two-stream factorisation schedule
   // local-penalisation state (AcquisitionLP.update_batches): batch points and hammer-function parameters on the device
   // Gower mixed-variable kernel patch (stationary.py:116-135): per-dimension flags / inverse ranges and the coordinate copies
@@ -280,6 +285,8 @@ static int leave_stream_ordered(gpb_model *m) {
   return 0;
 }
 
+constexpr size_t PIN_X = 256, PIN_OUT = 768, PIN_OUT_DOUBLES = 8 * (3 + 3 * 64), PIN_TOTAL = PIN_OUT + PIN_OUT_DOUBLES;
+
 static int g_overlap_min_n = 512;  // 0 disables the two-stream schedule (gpb_set_overlap)
 static int g_config_epoch = 0;     // bumped by the tuning entry points: captured launch sequences are stale afterwards
 
@@ -295,7 +302,8 @@ static size_t carve(int n_cap, int d, int p, int cb, gpb_model *m, char *base) {
   take(np * np, &fa);
   take(np * np, &fm);
   take(np * np, &fw);
-  take(std::max<size_t>(nb, 128) * np, &fpart);  // GEMV partials: nb * np (factor_solve) or 8 * 16 * np (skinny products)
+  take(std::max<size_t>(nb, 128) * np, &fpart);  // GEMV partials: nb * np (factor_solve), 8 * 16 * np (skinny products), 128 np (fused skinny call)
+  take(skinny_fused_part3_doubles(d), m ? &m->sk_part3 : nullptr);
   take(kgrad_part_doubles((int)np, (int)np, d, 1), m ? &m->gpart : nullptr);
   take(np * (size_t)d, m ? &m->X : nullptr);
   take(np * (size_t)d, m ? &m->XsT : nullptr);
@@ -429,7 +437,12 @@ int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap
   }
   carve(n_cap, d, p, m->cb, m, reinterpret_cast<char *>(m->ws));
   m->f.stream = m->stream;
-  if (cudaMallocHost(&m->pinned, 256 * sizeof(double)) != cudaSuccess) {
+  // arrival counter of the fused skinny call: zero once, the kernel re-arms it
+  if (cudaMemsetAsync(m->sk_part3 + skinny_fused_part3_doubles(d) - 8, 0, 8 * sizeof(double), m->stream) != cudaSuccess) {
+    set_error("model_create: cudaMemsetAsync failed");
+    return fail(-1);
+  }
+  if (cudaMallocHost(&m->pinned, PIN_TOTAL * sizeof(double)) != cudaSuccess) {
     m->pinned = nullptr;
     set_error("model_create: cudaMallocHost failed");
     return fail(-1);
@@ -881,7 +894,22 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   const int cpad = round_up(mcb, TILE);
   cudaStream_t s = m->stream;
   AllocStream alloc_scope(s);
-  GPB_CUDA(cudaMemcpyAsync(m->Xc, Xc, (size_t)mcb * d * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  if (!dev && (size_t)mcb * d <= 512) {
+    // a pageable source makes cudaMemcpyAsync stage and wait; the pinned block turns the small uploads of the M <= 8 calls into
+    // plain asynchronous copies (every entry point synchronises before it returns, so the block is free again by the next call)
+    memcpy(m->pinned + PIN_X, Xc, (size_t)mcb * d * sizeof(double));
+    GPB_CUDA(cudaMemcpyAsync(m->Xc, m->pinned + PIN_X, (size_t)mcb * d * sizeof(double), cudaMemcpyHostToDevice, s));
+  } else {
+    GPB_CUDA(cudaMemcpyAsync(m->Xc, Xc, (size_t)mcb * d * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  }
+  // A handful of candidates (the M = 1 .. 8 calls of the L-BFGS-B refinements, optimizer.py:46-51, coalesced by the host's
+  // LockstepEvaluator): everything from the covariance row to the four reductions in ONE persistent cooperative kernel
+  // (gpb_skinny.cu) -- two streaming passes over the triangle of M.  Kx / Dk live in the first 8 rows of KxT / Vt.
+  static const int fused_on = env_int("GPB_SKINNY_FUSED", 1);
+  if (mcb <= 8 && p == 1 && !m->gower && fused_on && level >= 1)
+    return launch_skinny_fused(m->kind, m->f.Mi, np, n, d, mcb, level, m->XsT, m->Xc, m->ls_dev, m->inv_ls_dev, m->alpha, m->variance,
+                               m->variance + (include_likelihood ? m->noise : 0.0), m->KxT, m->Vt, m->f.part, m->sk_part3, m->mu, m->var,
+                               m->dmu, m->dvar, s);
   GPB_TRY(launch_scale_transpose(m->Xc, mcb, d, m->ls_dev, m->XcT, cpad, s));
   // KxT[c][n] = k(x*_c, x_n)                                        posterior.py:275 (stored transposed)
   const KCoords kc = train_coords(m);
@@ -948,6 +976,26 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
 static int copy_out(double *dst, const double *src_dev, size_t count, int dev, cudaStream_t s) {
   if (!dst) return 0;
   GPB_CUDA(cudaMemcpyAsync(dst, src_dev, count * sizeof(double), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// Small host results (the M <= 8 calls): device -> pinned block asynchronously, unpacked by finish_staged() after the call's one
+// synchronisation, instead of one blocking pageable copy per output array.
+static int copy_out_staged(gpb_model *m, double *dst, const double *src_dev, size_t count) {
+  if (!dst) return 0;
+  if (m->staged_used + count > PIN_OUT_DOUBLES) return copy_out(dst, src_dev, count, 0, m->stream);
+  GPB_CUDA(cudaMemcpyAsync(m->pinned + PIN_OUT + m->staged_used, src_dev, count * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  m->staged.push_back({dst, m->staged_used, count});
+  m->staged_used += count;
+  return 0;
+}
+static int finish_staged(gpb_model *m) {
+  const cudaError_t e = cudaStreamSynchronize(m->stream);
+  if (e == cudaSuccess)
+    for (const auto &st : m->staged) memcpy(st.dst, m->pinned + PIN_OUT + st.off, st.count * sizeof(double));
+  m->staged.clear();
+  m->staged_used = 0;
+  GPB_CUDA(e);
   return 0;
 }
 
@@ -1035,6 +1083,21 @@ int gpb_model_acquisition(gpb_model *m, int acq, double par, double fmin, int mc
   GPB_REQUIRE(m->p == 1, "acquisition: single output only");
   const bool grad = df || dmdx || dsdx;
   const int d = m->d;
+  if (!dev && mc >= 1 && mc <= 8) {
+    // the refinement call (optimizer.py:46-51): one upload, the fused kernel, the epilogue, staged results, ONE synchronisation
+    GPB_TRY(predict_block(m, Xc, mc, 0, grad ? 2 : 1, 1));
+    GPB_TRY(launch_acq_epilogue(acq, par, fmin, mc, d, m->mu, m->var, grad ? m->dmu : nullptr, grad ? m->dvar : nullptr, m->fbuf,
+                                m->dfbuf, nullptr, m->sdbuf, nullptr, m->dsbuf, m->stream));
+    GPB_TRY(copy_out_staged(m, f, m->fbuf, mc));
+    GPB_TRY(copy_out_staged(m, mean, m->mu, mc));
+    GPB_TRY(copy_out_staged(m, sd, m->sdbuf, mc));
+    if (grad) {
+      GPB_TRY(copy_out_staged(m, df, m->dfbuf, (size_t)mc * d));
+      GPB_TRY(copy_out_staged(m, dmdx, m->dmu, (size_t)mc * d));
+      GPB_TRY(copy_out_staged(m, dsdx, m->dsbuf, (size_t)mc * d));
+    }
+    return finish_staged(m);
+  }
   for (int c0 = 0; c0 < mc; c0 += m->cb) {
     const int mcb = std::min(m->cb, mc - c0);
     GPB_TRY(predict_block(m, Xc + (size_t)c0 * d, mcb, dev, grad ? 2 : 1, 1));
@@ -1086,6 +1149,16 @@ int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int
   const int d = m->d;
   const bool grad = df != nullptr;
   const double *Xb = m->lp_buf, *r = m->lp_buf + (size_t)m->lp_cap * d, *s = m->lp_buf + (size_t)m->lp_cap * (d + 1);
+  if (!dev && mc >= 1 && mc <= 8) {
+    GPB_TRY(predict_block(m, Xc, mc, 0, grad ? 2 : 1, 1));
+    GPB_TRY(launch_acq_epilogue(acq, par, fmin, mc, d, m->mu, m->var, grad ? m->dmu : nullptr, grad ? m->dvar : nullptr, m->fbuf,
+                                m->dfbuf, nullptr, nullptr, nullptr, nullptr, m->stream));
+    GPB_TRY(launch_lp_epilogue(mc, d, m->lp_nb, m->Xc, Xb, r, s, m->lp_transform, m->fbuf, grad ? m->dfbuf : nullptr, m->sdbuf,
+                               grad ? m->dsbuf : nullptr, m->stream));
+    GPB_TRY(copy_out_staged(m, f, m->sdbuf, mc));
+    if (grad) GPB_TRY(copy_out_staged(m, df, m->dsbuf, (size_t)mc * d));
+    return finish_staged(m);
+  }
   for (int c0 = 0; c0 < mc; c0 += m->cb) {
     const int mcb = std::min(m->cb, mc - c0);
     GPB_TRY(predict_block(m, Xc + (size_t)c0 * d, mcb, dev, grad ? 2 : 1, 1));

@@ -49,6 +49,13 @@ int launch_skinny_moments(int kind, const double *KxT, const double *Vt, const d
                           const double *XcT, int ldc, const double *XT, int ldx, int d, double variance, const double *inv_ls,
                           double var_base, int want_g, double *part, double *mu, double *var, double *dmu, double *dvar,
                           cudaStream_t s);
+// gpb_skinny.cu: the same call (n_c <= 8, one output column, stationary kernel) as ONE persistent cooperative kernel -- covariance row,
+// Z = M k*, U = M^T Z and all four reductions, two streaming passes over the triangle of M, 16-byte loads, grid-wide barriers
+size_t skinny_fused_part12_doubles(int np);
+size_t skinny_fused_part3_doubles(int d);
+int launch_skinny_fused(int kind, const double *M, int np, int n, int d, int mc, int level, const double *XT, const double *Xc,
+                        const double *ls, const double *inv_ls, const double *alpha, double variance, double var_base, double *Kx,
+                        double *Dk, double *part12, double *part3, double *mu, double *var, double *dmu, double *dvar, cudaStream_t s);
 // GPModel.predict clip + get_quantiles + EI/LCB (+ gradients) + AcquisitionBase sign
 int launch_acq_epilogue(int acq, double par, double fmin, int n_c, int d, const double *mu, const double *var, const double *dmu,
                         const double *dvar, double *f, double *df, double *mean_out, double *sd_out, double *dmdx_out,

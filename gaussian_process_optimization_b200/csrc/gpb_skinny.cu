@@ -1,0 +1,408 @@
+// The M = 1 .. 8 predictive call as ONE persistent cooperative kernel.
+//
+// What it serves: the f_df calls bounded L-BFGS-B makes from every anchor point (GPyOpt/GPyOpt/optimization/optimizer.py:46-51 ->
+// acquisition_function_withGradients -> GPModel.predict_withGradients, gpmodel.py:131-142 -> GP.predict + predictive_gradients,
+// core/gp.py:297-354,407-454 -> PosteriorExact._raw_predict, posterior.py:273-302) -- hundreds of them per BO step, and (through
+// the host's LockstepEvaluator) up to 8 candidates per call.
+//
+// Such a call is bound by HBM: Z = M k* and U = M^T Z (M = L^-1, lower triangular) each stream the triangle once, 2 x 8 N^2 / 2
+// bytes, whatever the number of candidates up to 8.  The multi-kernel route (scale_transpose, kmat, trmm_lower_skinny, its
+// transposed partial + reduce, skinny moments partial + reduce: 7 dependent launches around two streaming kernels) leaves a third of
+// the call to launch gaps and small kernels.  Here one grid of co-resident CTAs (cooperative launch, grid-wide barriers) does
+//   P0  k*_c[j] = k(x*_c, x_j) and k'/r, all training points j            (posterior.py:275; rbf.py:50-54, stationary.py:575-579)
+//   P1  Z_c = M k*_c           row panels of 32 rows x 128-column chunks    (the dtrtrs of posterior.py:293 as a product with L^-1)
+//   P2  U_c = M^T Z_c          the same chunks walked column block by column block     (woodbury_inv product, core/gp.py:450-451)
+//   P3  mu = k*^T alpha, var = base - |Z|^2, d mu / dx* and d var / dx*     (posterior.py:276,294-295; core/gp.py:431-434,450-453;
+//                                                                            stationary.py:354-364)
+// with the 32 KB chunks of the triangle dealt to the CTAs in contiguous, equal runs (+-1 chunk), 16-byte loads, every lane owning
+// four columns of a chunk.  All partial sums are combined in fixed orders that do not depend on the number of candidates sharing the
+// call: candidate c's results are bit-identical whether it is evaluated alone or with seven others, and run to run.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "gpb_common.cuh"
+#include "gpb_kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gpb {
+
+constexpr int SK_THREADS = 256;
+constexpr int SK_WARPS = SK_THREADS / 32;
+constexpr int SK_PH = 32;        // rows of a panel (4 per warp)
+constexpr int SK_SLOTS1 = 4;     // CTAs a row panel's chunks can be spread over     (G <= 4 (nb + 1))
+constexpr int SK_SLOTS2 = 12;    // CTAs a column block's chunks can be spread over
+constexpr int SK_QC = 8;         // input dimensions per pass of the gradient sums
+
+struct SkinnyParams {
+  const double *M;          // L^-1, np x np row-major (lower; diagonal 128-blocks carry explicit zeros above the diagonal)
+  const double *XT;         // [d][np] training inputs divided by the lengthscales
+  const double *Xc;         // [mc][d] raw candidates (device)
+  const double *ls, *inv_ls, *alpha;
+  double *Kx, *Dk;          // [C][np] scratch: k(x*_c, x_j) and k'(r) / r
+  double *part1;            // [np / 32][SK_SLOTS1][C][32]
+  double *part2;            // [np / 128][SK_SLOTS2][C][128]
+  double *part3;            // [G][C][2 + 2 d]
+  unsigned int *ticket;
+  double *mu, *var, *dmu, *dvar;
+  double variance, var_base;
+  int np, n, d, mc, level;  // level 1: mean + variance; 2: + both gradients; 3: mean and its gradient only
+};
+
+// chunks are numbered 0 .. T - 1; CTA g of G owns [g T / G, (g + 1) T / G)
+__device__ __forceinline__ int sk_owner(long long u, int G, long long T) { return (int)(((u + 1) * G - 1) / T); }
+// first chunk of row panel p (32 rows; its chunks are the column blocks 0 .. p / 4)
+__device__ __forceinline__ long long sk_prefix1(int p) {
+  const long long bi = p >> 2, s = p & 3;
+  return 2 * bi * (bi + 1) + s * (bi + 1);
+}
+// first chunk of column block cb (its chunks are the row panels 4 cb .. P - 1)
+__device__ __forceinline__ long long sk_prefix2(int cb, int P) { return (long long)cb * P - 2ll * cb * (cb - 1); }
+
+// Z_c[i] for the 32 rows of panel p = sum of the slots the owning CTAs wrote, in slot order
+template <int C>
+__device__ __forceinline__ double sk_zsum(const SkinnyParams &a, int c, int i, int G, long long T) {
+  const int p = i >> 5, r = i & 31;
+  const int first = sk_owner(sk_prefix1(p), G, T), last = sk_owner(sk_prefix1(p + 1) - 1, G, T);
+  double z = 0.0;
+  for (int s = 0; s <= last - first; ++s) z += a.part1[(((size_t)p * SK_SLOTS1 + s) * C + c) * SK_PH + r];
+  return z;
+}
+template <int C>
+__device__ __forceinline__ double sk_usum(const SkinnyParams &a, int c, int j, int G, long long T, int P) {
+  const int cb = j >> 7, r = j & 127;
+  const int first = sk_owner(sk_prefix2(cb, P), G, T), last = sk_owner(sk_prefix2(cb + 1, P) - 1, G, T);
+  double u = 0.0;
+  for (int s = 0; s <= last - first; ++s) u += a.part2[(((size_t)cb * SK_SLOTS2 + s) * C + c) * TILE + r];
+  return u;
+}
+
+template <int KIND, int C>
+__global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const SkinnyParams a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double xcs[8 * 64];              // candidates divided by the lengthscales, [c][q]
+  __shared__ double zs[C * SK_PH];            // Z of the current panel (P2)
+  __shared__ double ured[C * TILE];           // cross-warp sums of a column block (P2) / block reductions (P3)
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.x, G = gridDim.x;
+  const int np = a.np, n = a.n, d = a.d, nb = np / TILE, P = np / SK_PH;
+  const long long T = 2ll * nb * (nb + 1);
+  const bool want_var = a.level == 1 || a.level == 2, want_g = a.level >= 2, want_dvar = a.level == 2;
+
+  // ---- P0: scaled candidates, then k* and k'/r over all training points -----------------------------------------------------
+  for (int e = tid; e < C * d; e += SK_THREADS) {
+    const int c = e / d, q = e - c * d;
+    double v = (c < a.mc) ? a.Xc[(size_t)c * d + q] / a.ls[q] : 0.0;
+    v = v > 1e150 ? 1e150 : (v < -1e150 ? -1e150 : v);        // as scale_transpose_kernel
+    xcs[e] = v;
+  }
+  __syncthreads();
+  for (int j = g * SK_THREADS + tid; j < np; j += G * SK_THREADS) {
+    double r2[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) r2[c] = 0.0;
+    for (int q = 0; q < d; ++q) {
+      const double xv = a.XT[(size_t)q * np + j];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const double df = xcs[c * d + q] - xv;
+        r2[c] = fma(df, df, r2[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      double k = 0.0, dk = 0.0;
+      if (j < n && c < a.mc) cov_k_dk<KIND>(r2[c], a.variance, k, dk);
+      a.Kx[(size_t)c * np + j] = k;
+      a.Dk[(size_t)c * np + j] = dk;
+    }
+  }
+  grid.sync();
+
+  const long long u0 = (long long)g * T / G, u1 = (long long)(g + 1) * T / G;
+
+  // ---- P1: Z = M k*  (row panels; warp w owns rows 4 w .. 4 w + 3 of the panel, lane l columns 4 l .. 4 l + 3 of the chunk) ----
+  if (want_var && u0 < u1) {
+    // decode u0 -> (panel p, column block cb)
+    int p = 0;
+    {
+      long long bi = (long long)((sqrt(1.0 + 2.0 * (double)u0) - 1.0) * 0.5);
+      while (bi > 0 && 2 * bi * (bi + 1) > u0) --bi;
+      while (2 * (bi + 1) * (bi + 2) <= u0) ++bi;
+      const long long rem = u0 - 2 * bi * (bi + 1);
+      p = (int)(4 * bi + rem / (bi + 1));
+    }
+    int cb = (int)(u0 - sk_prefix1(p));
+    double acc[4][C];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[rr][c] = 0.0;
+    auto flush1 = [&](int pp) {
+      const int slot = g - sk_owner(sk_prefix1(pp), G, T);
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const double v = warp_sum(acc[rr][c]);
+          if (lane == 0) a.part1[(((size_t)pp * SK_SLOTS1 + slot) * C + c) * SK_PH + 4 * warp + rr] = v;
+          acc[rr][c] = 0.0;
+        }
+    };
+    for (long long u = u0; u < u1; ++u) {
+      const double *mrow = a.M + (size_t)(p * SK_PH + 4 * warp) * np + cb * TILE + 4 * lane;
+      double2 m[4][2];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        m[rr][0] = __ldg(reinterpret_cast<const double2 *>(mrow + (size_t)rr * np));
+        m[rr][1] = __ldg(reinterpret_cast<const double2 *>(mrow + (size_t)rr * np) + 1);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const double2 b0 = *reinterpret_cast<const double2 *>(a.Kx + (size_t)c * np + cb * TILE + 4 * lane);
+        const double2 b1 = *(reinterpret_cast<const double2 *>(a.Kx + (size_t)c * np + cb * TILE + 4 * lane) + 1);
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          double s = acc[rr][c];
+          s = fma(m[rr][0].x, b0.x, s);
+          s = fma(m[rr][0].y, b0.y, s);
+          s = fma(m[rr][1].x, b1.x, s);
+          s = fma(m[rr][1].y, b1.y, s);
+          acc[rr][c] = s;
+        }
+      }
+      if (++cb > (p >> 2)) {
+        flush1(p);
+        ++p;
+        cb = 0;
+      }
+    }
+    if (cb > 0) flush1(p);
+  }
+  if (want_var) grid.sync();
+
+  // ---- P2: U = M^T Z  (column blocks; lane l owns columns 4 l .. 4 l + 3, warp w rows 4 w .. 4 w + 3 of every panel) --------
+  if (want_dvar && u0 < u1) {
+    int cb = 0;
+    {
+      // prefix2(cb) = cb P - 2 cb (cb - 1) is increasing in cb for cb <= nb: search
+      int lo = 0, hi = nb - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sk_prefix2(mid, P) <= u0) lo = mid; else hi = mid - 1;
+      }
+      cb = lo;
+    }
+    int p = 4 * cb + (int)(u0 - sk_prefix2(cb, P));
+    double acc[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[c][k] = 0.0;
+    auto flush2 = [&](int cc) {
+      const int slot = g - sk_owner(sk_prefix2(cc, P), G, T);
+      for (int w = 0; w < SK_WARPS; ++w) {           // warps add their sums one after the other: a fixed order
+        if (warp == w) {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int idx = c * TILE + 4 * lane + k;
+              ured[idx] = (w == 0) ? acc[c][k] : ured[idx] + acc[c][k];
+              acc[c][k] = 0.0;
+            }
+        }
+        __syncthreads();
+      }
+      for (int e = tid; e < C * TILE; e += SK_THREADS) {
+        const int c = e / TILE, r = e - c * TILE;
+        a.part2[(((size_t)cc * SK_SLOTS2 + slot) * C + c) * TILE + r] = ured[e];
+      }
+      __syncthreads();
+    };
+    for (long long u = u0; u < u1; ++u) {
+      const double *mrow = a.M + (size_t)(p * SK_PH + 4 * warp) * np + cb * TILE + 4 * lane;
+      double2 m[4][2];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        m[rr][0] = __ldg(reinterpret_cast<const double2 *>(mrow + (size_t)rr * np));
+        m[rr][1] = __ldg(reinterpret_cast<const double2 *>(mrow + (size_t)rr * np) + 1);
+      }
+      __syncthreads();                                  // zs of the previous chunk has been consumed
+      if (tid < C * SK_PH) zs[tid] = sk_zsum<C>(a, tid >> 5, p * SK_PH + (tid & 31), G, T);
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const double z = zs[c * SK_PH + 4 * warp + rr];
+          acc[c][0] = fma(m[rr][0].x, z, acc[c][0]);
+          acc[c][1] = fma(m[rr][0].y, z, acc[c][1]);
+          acc[c][2] = fma(m[rr][1].x, z, acc[c][2]);
+          acc[c][3] = fma(m[rr][1].y, z, acc[c][3]);
+        }
+      }
+      if (++p == P) {
+        flush2(cb);
+        ++cb;
+        p = 4 * cb;
+      }
+    }
+    if (p > 4 * cb) flush2(cb);
+  }
+  if (want_dvar) grid.sync();
+
+  // ---- P3: the reductions over the training points; part3[g][c][2 + 2 d] -----------------------------------------------------
+  const int K3 = 2 + 2 * d;
+  double *red = ured;                                   // [SK_WARPS][2 + 2 SK_QC]
+  for (int c = 0; c < a.mc; ++c) {
+    for (int q0 = 0; q0 < (want_g ? d : 1); q0 += SK_QC) {
+      double a_mu = 0.0, a_vv = 0.0, g1[SK_QC], g2[SK_QC];
+#pragma unroll
+      for (int k = 0; k < SK_QC; ++k) g1[k] = g2[k] = 0.0;
+      for (int j = g * SK_THREADS + tid; j < n; j += G * SK_THREADS) {
+        const double al = a.alpha[j];
+        if (q0 == 0) {
+          a_mu = fma(a.Kx[(size_t)c * np + j], al, a_mu);
+          if (want_var) {
+            const double z = sk_zsum<C>(a, c, j, G, T);
+            a_vv = fma(z, z, a_vv);
+          }
+        }
+        if (want_g) {
+          const double dk = a.Dk[(size_t)c * np + j];
+          const double w1 = dk * al;
+          const double w2 = want_dvar ? dk * sk_usum<C>(a, c, j, G, T, P) : 0.0;
+#pragma unroll
+          for (int k = 0; k < SK_QC; ++k) {
+            if (q0 + k < d) {
+              const double df = xcs[c * d + q0 + k] - a.XT[(size_t)(q0 + k) * np + j];
+              g1[k] = fma(w1, df, g1[k]);
+              g2[k] = fma(w2, df, g2[k]);
+            }
+          }
+        }
+      }
+      // block sums in a fixed order: lanes by shuffle tree, warps one after the other
+      a_mu = warp_sum(a_mu);
+      a_vv = warp_sum(a_vv);
+#pragma unroll
+      for (int k = 0; k < SK_QC; ++k) {
+        g1[k] = warp_sum(g1[k]);
+        g2[k] = warp_sum(g2[k]);
+      }
+      __syncthreads();
+      if (lane == 0) {
+        double *rw = red + warp * (2 + 2 * SK_QC);
+        rw[0] = a_mu;
+        rw[1] = a_vv;
+#pragma unroll
+        for (int k = 0; k < SK_QC; ++k) {
+          rw[2 + k] = g1[k];
+          rw[2 + SK_QC + k] = g2[k];
+        }
+      }
+      __syncthreads();
+      if (tid < 2 + 2 * SK_QC) {
+        double v = 0.0;
+        for (int w = 0; w < SK_WARPS; ++w) v += red[w * (2 + 2 * SK_QC) + tid];
+        double *dst = a.part3 + ((size_t)g * C + c) * K3;
+        if (tid < 2) {
+          if (q0 == 0) dst[tid] = v;
+        } else if (tid < 2 + SK_QC) {
+          if (q0 + tid - 2 < d) dst[2 + q0 + tid - 2] = v;
+        } else {
+          if (q0 + tid - 2 - SK_QC < d) dst[2 + d + q0 + tid - 2 - SK_QC] = v;
+        }
+      }
+    }
+  }
+  // ---- the CTA that arrives last adds the per-CTA sums (CTA order, fixed) and applies the scalings ----------------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == (unsigned)(G - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int e = tid; e < a.mc * K3; e += SK_THREADS) {
+    const int c = e / K3, i = e - c * K3;
+    double v = 0.0;
+    for (int gg = 0; gg < G; ++gg) v += __ldcg(a.part3 + ((size_t)gg * C + c) * K3 + i);
+    if (i == 0) {
+      a.mu[c] = v;
+    } else if (i == 1) {
+      if (want_var) a.var[c] = a.var_base - v;
+    } else if (i < 2 + d) {
+      if (want_g) a.dmu[(size_t)c * d + (i - 2)] = a.inv_ls[i - 2] * v;                     // gradients_X(alpha^T, X*, X) / l
+    } else {
+      if (want_dvar) a.dvar[(size_t)c * d + (i - 2 - d)] = -2.0 * a.inv_ls[i - 2 - d] * v;    // gradients_X(-2 Kx^T Ky^-1, X*, X) / l
+    }
+  }
+  if (tid == 0) *a.ticket = 0u;                          // ready for the next call on this stream
+}
+
+// scratch of the fused call beyond Kx / Dk (8 x np doubles each):
+//   part12: part1 | part2 = np / 32 * SLOTS1 * 8 * 32 + np / 128 * SLOTS2 * 8 * 128 = 128 np doubles
+//   part3:  (148 * 4) CTAs x 8 candidates x (2 + 2 d) doubles, followed by 8 doubles whose first word is the arrival counter
+size_t skinny_fused_part12_doubles(int np) { return (size_t)np * (SK_SLOTS1 * 8 + SK_SLOTS2 * 8); }
+size_t skinny_fused_part3_doubles(int d) { return (size_t)(148 * 4) * 8 * (2 + 2 * d) + 8; }
+
+template <int KIND, int C>
+static int launch_skinny_fused_t(SkinnyParams &a, double *part12, double *part3, cudaStream_t s) {
+  static std::atomic<int> per_sm[64];                    // co-resident CTAs per SM of this instantiation, per device (0 = not yet known)
+  static std::atomic<int> sms[64];
+  int dev = 0;
+  GPB_CUDA(cudaGetDevice(&dev));
+  GPB_REQUIRE(dev >= 0 && dev < 64, "skinny: device ordinal %d out of range", dev);
+  if (per_sm[dev].load(std::memory_order_acquire) == 0) {
+    int occ = 0, nsm = 0, coop = 0;
+    GPB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GPB_REQUIRE(coop != 0, "skinny: the device does not support cooperative launches");
+    GPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_fused_kernel<KIND, C>, SK_THREADS, 0));
+    GPB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    GPB_REQUIRE(occ >= 1 && nsm >= 1, "skinny: kernel does not fit an SM");
+    sms[dev].store(nsm, std::memory_order_release);
+    per_sm[dev].store(std::min(occ, 4), std::memory_order_release);
+  }
+  const int nb = a.np / TILE, P = a.np / SK_PH;
+  // G <= 4 (nb + 1) keeps the chunks of one row panel within SK_SLOTS1 CTAs and those of one column block within SK_SLOTS2
+  int G = std::min(sms[dev].load() * per_sm[dev].load(), 4 * (nb + 1));
+  G = std::min(G, 148 * 4);
+  a.part1 = part12;
+  a.part2 = a.part1 + (size_t)P * SK_SLOTS1 * 8 * SK_PH;
+  a.part3 = part3;
+  a.ticket = reinterpret_cast<unsigned int *>(a.part3 + (size_t)(148 * 4) * 8 * (2 + 2 * a.d));
+  void *args[] = {&a};
+  GPB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(skinny_fused_kernel<KIND, C>), dim3(G), dim3(SK_THREADS), args, 0, s));
+  count_launch();
+  return 0;
+}
+
+// mc <= 8 candidates (raw coordinates Xc on the device).  Kx, Dk: 8 x np doubles each; part12 / part3 as sized above, the last 8
+// doubles of part3 (the arrival counter) zeroed once.  level as in predict_block (1, 2 or 3).
+int launch_skinny_fused(int kind, const double *M, int np, int n, int d, int mc, int level, const double *XT, const double *Xc,
+                        const double *ls, const double *inv_ls, const double *alpha, double variance, double var_base, double *Kx,
+                        double *Dk, double *part12, double *part3, double *mu, double *var, double *dmu, double *dvar, cudaStream_t s) {
+  GPB_REQUIRE(mc >= 1 && mc <= 8 && d >= 1 && d <= 64 && (level == 1 || level == 2 || level == 3), "skinny: bad arguments");
+  SkinnyParams a;
+  a.M = M; a.XT = XT; a.Xc = Xc; a.ls = ls; a.inv_ls = inv_ls; a.alpha = alpha;
+  a.Kx = Kx; a.Dk = Dk;
+  a.mu = mu; a.var = var; a.dmu = dmu; a.dvar = dvar;
+  a.variance = variance; a.var_base = var_base;
+  a.np = np; a.n = n; a.d = d; a.mc = mc; a.level = level;
+  const int c = mc <= 1 ? 1 : mc <= 2 ? 2 : mc <= 4 ? 4 : 8;
+#define GPB_SKF(K_)                                                     \
+  do {                                                                  \
+    if (c == 1) return launch_skinny_fused_t<K_, 1>(a, part12, part3, s);     \
+    if (c == 2) return launch_skinny_fused_t<K_, 2>(a, part12, part3, s);     \
+    if (c == 4) return launch_skinny_fused_t<K_, 4>(a, part12, part3, s);     \
+    return launch_skinny_fused_t<K_, 8>(a, part12, part3, s);                 \
+  } while (0)
+  if (kind == GPB_KERN_RBF) GPB_SKF(GPB_KERN_RBF);
+  GPB_SKF(GPB_KERN_MATERN52);
+#undef GPB_SKF
+}
+
+}  // namespace gpb

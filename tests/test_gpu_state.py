@@ -160,10 +160,12 @@ def test_rows_of_a_batched_call_equal_the_single_row_calls_bitwise(n, d):
     assert nm.fit(False)[0] == 0
     fmin = nm.fmin()
     rs = np.random.RandomState(8)
-    nm.set_penalizers("none", rs.uniform(0, 1, (3, d)), np.array([0.3, 0.2, 0.1]), np.array([0.05, 0.04, 0.03]))
+    Xb = rs.uniform(0, 1, (3, d))
     for mc in (2, 3, 5, 8):
         Xc = rs.uniform(0, 1, (mc, d))
         for acq, par in (("EI", 0.01), ("LCB", 2.0)):
+            # LCB takes the softplus transform, like the reference (LP.py:31-34: log of a negative acquisition is NaN otherwise)
+            nm.set_penalizers("none" if acq == "EI" else "softplus", Xb, np.array([0.3, 0.2, 0.1]), np.array([0.05, 0.04, 0.03]))
             r = nm.acquisition(acq, par, fmin, Xc, with_gradients=True, want_moments=True)
             f_lp, df_lp = nm.acquisition_lp(acq, par, fmin, Xc, with_gradients=True)
             for i in range(mc):
@@ -171,6 +173,7 @@ def test_rows_of_a_batched_call_equal_the_single_row_calls_bitwise(n, d):
                 for key in ("f", "df", "m", "s", "dmdx", "dsdx"):
                     assert np.array_equal(r[key][i:i + 1], r1[key]), (mc, acq, key)
                 f1, df1 = nm.acquisition_lp(acq, par, fmin, Xc[i:i + 1], with_gradients=True)
+                assert np.all(np.isfinite(f1)) and np.all(np.isfinite(df1))
                 assert np.array_equal(f_lp[i:i + 1], f1) and np.array_equal(df_lp[i:i + 1], df1)
     nm.close()
 
