@@ -14,9 +14,11 @@
 //   P2  U_c = M^T Z_c          the same chunks walked column block by column block     (woodbury_inv product, core/gp.py:450-451)
 //   P3  mu = k*^T alpha, var = base - |Z|^2, d mu / dx* and d var / dx*     (posterior.py:276,294-295; core/gp.py:431-434,450-453;
 //                                                                            stationary.py:354-364)
-// with the 32 KB chunks of the triangle dealt to the CTAs in contiguous, equal runs (+-1 chunk), 16-byte loads, every lane owning
-// four columns of a chunk.  All partial sums are combined in fixed orders that do not depend on the number of candidates sharing the
-// call: candidate c's results are bit-identical whether it is evaluated alone or with seven others, and run to run.
+// with the 32 KB chunks of the triangle dealt to the CTAs in contiguous, equal runs (+-1 chunk) and streamed through a 4-stage
+// shared-memory ring by the TMA engine (cp.async.bulk row copies completing on mbarriers: the first version, which loaded the
+// chunks into registers, kept too few bytes in flight -- 4.8 of 6.5 TB/s, ncu r2c), every lane owning four columns of a chunk.
+// All partial sums are combined in fixed orders that do not depend on the number of candidates sharing the call: candidate c's
+// results are bit-identical whether it is evaluated alone or with seven others, and run to run.
 #include <cooperative_groups.h>
 
 #include <algorithm>
@@ -34,13 +36,39 @@ constexpr int SK_PH = 32;        // rows of a panel (4 per warp)
 constexpr int SK_SLOTS1 = 4;     // CTAs a row panel's chunks can be spread over     (G <= 4 (nb + 1))
 constexpr int SK_SLOTS2 = 12;    // CTAs a column block's chunks can be spread over
 constexpr int SK_QC = 8;         // input dimensions per pass of the gradient sums
+constexpr int SK_STAGES = 4;     // shared-memory ring: stages of one chunk (32 rows x 128 doubles) + the C x 128 right-hand sides
+constexpr int SK_MTILE = SK_PH * TILE;   // doubles of a chunk
+
+__device__ __forceinline__ uint32_t sk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sk_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void sk_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  }
+}
+// one contiguous run of bytes (multiple of 16, 16-byte aligned on both sides) global -> shared through the TMA engine
+__device__ __forceinline__ void sk_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void sk_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 struct SkinnyParams {
   const double *M;          // L^-1, np x np row-major (lower; diagonal 128-blocks carry explicit zeros above the diagonal)
   const double *XT;         // [d][np] training inputs divided by the lengthscales
   const double *Xc;         // [mc][d] raw candidates (device)
   const double *ls, *inv_ls, *alpha;
-  double *Kx, *Dk;          // [C][np] scratch: k(x*_c, x_j) and k'(r) / r
+  double *Kx, *Dk, *Z;      // [C][np] scratch: k(x*_c, x_j), k'(r) / r, and Z_c = M k*_c once its partial sums are added
   double *part1;            // [np / 32][SK_SLOTS1][C][32]
   double *part2;            // [np / 128][SK_SLOTS2][C][128]
   double *part3;            // [G][C][2 + 2 d]
@@ -79,17 +107,26 @@ __device__ __forceinline__ double sk_usum(const SkinnyParams &a, int c, int j, i
 }
 
 template <int KIND, int C>
-__global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const SkinnyParams a) {
+__global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const SkinnyParams a) {
   cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(128) unsigned char sk_dyn[];   // ring: SK_STAGES x (chunk of M | C x 128 right-hand sides)
   __shared__ double xcs[8 * 64];              // candidates divided by the lengthscales, [c][q]
-  __shared__ double zs[C * SK_PH];            // Z of the current panel (P2)
-  __shared__ double ured[C * TILE];           // cross-warp sums of a column block (P2) / block reductions (P3)
+  __shared__ double zs[2][C * SK_PH];         // Z of the current / next panel (P2)
+  constexpr int RED = SK_WARPS * (2 + 2 * SK_QC);
+  __shared__ double ured[C * TILE > RED ? C * TILE : RED];   // cross-warp sums of a column block (P2) / block reductions (P3)
+  __shared__ __align__(8) unsigned long long full_bar[SK_STAGES];
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.x, G = gridDim.x;
   const int np = a.np, n = a.n, d = a.d, nb = np / TILE, P = np / SK_PH;
   const long long T = 2ll * nb * (nb + 1);
   const bool want_var = a.level == 1 || a.level == 2, want_g = a.level >= 2, want_dvar = a.level == 2;
+  constexpr int STAGE_DOUBLES = SK_MTILE + C * TILE;
+  double *ring = reinterpret_cast<double *>(sk_dyn);
+  if (tid == 0) {
+    for (int st = 0; st < SK_STAGES; ++st) sk_mbar_init(sk_smem_u32(&full_bar[st]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   // ---- P0: scaled candidates, then k* and k'/r over all training points -----------------------------------------------------
   for (int e = tid; e < C * d; e += SK_THREADS) {
@@ -119,13 +156,16 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const Skinn
       a.Dk[(size_t)c * np + j] = dk;
     }
   }
+  sk_fence_proxy_async();      // Kx is read back through the TMA engine (async proxy) by other CTAs
   grid.sync();
 
   const long long u0 = (long long)g * T / G, u1 = (long long)(g + 1) * T / G;
+  const int nu = (int)(u1 - u0);
+  int it = 0;                  // chunks consumed so far by this CTA, over both passes: stage = it % STAGES, parity = (it / STAGES) & 1
 
   // ---- P1: Z = M k*  (row panels; warp w owns rows 4 w .. 4 w + 3 of the panel, lane l columns 4 l .. 4 l + 3 of the chunk) ----
-  if (want_var && u0 < u1) {
-    // decode u0 -> (panel p, column block cb)
+  if (want_var && nu > 0) {
+    // decode u0 -> (panel p, column block cb); a second cursor (ip, icb) runs SK_STAGES chunks ahead and feeds the ring
     int p = 0;
     {
       long long bi = (long long)((sqrt(1.0 + 2.0 * (double)u0) - 1.0) * 0.5);
@@ -135,6 +175,26 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const Skinn
       p = (int)(4 * bi + rem / (bi + 1));
     }
     int cb = (int)(u0 - sk_prefix1(p));
+    int ip = p, icb = cb, issued = 0;
+    auto feed1 = [&](int slot_it) {   // warp 0: one chunk of M (32 rows of 1 KB) and the matching 1 KB of every right-hand side
+      const int st = slot_it % SK_STAGES;
+      if (warp == 0) {
+        const uint32_t bar = sk_smem_u32(&full_bar[st]);
+        double *dstM = ring + (size_t)st * STAGE_DOUBLES;
+        if (lane == 0) sk_mbar_expect_tx(bar, (uint32_t)(STAGE_DOUBLES * sizeof(double)));
+        __syncwarp();
+        sk_bulk_load(sk_smem_u32(dstM + lane * TILE), a.M + (size_t)(ip * SK_PH + lane) * np + icb * TILE, TILE * sizeof(double), bar);
+        if (lane < C)
+          sk_bulk_load(sk_smem_u32(dstM + SK_MTILE + lane * TILE), a.Kx + (size_t)lane * np + icb * TILE, TILE * sizeof(double), bar);
+      }
+      if (++icb > (ip >> 2)) {
+        ++ip;
+        icb = 0;
+      }
+      ++issued;
+    };
+    if (warp == 0) sk_fence_proxy_async();
+    for (int i = 0; i < SK_STAGES && i < nu; ++i) feed1(it + i);
     double acc[4][C];
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr)
@@ -151,26 +211,29 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const Skinn
           acc[rr][c] = 0.0;
         }
     };
-    for (long long u = u0; u < u1; ++u) {
-      const double *mrow = a.M + (size_t)(p * SK_PH + 4 * warp) * np + cb * TILE + 4 * lane;
+    for (int i = 0; i < nu; ++i, ++it) {
+      const int st = it % SK_STAGES;
+      sk_mbar_wait(sk_smem_u32(&full_bar[st]), (uint32_t)((it / SK_STAGES) & 1));
+      const double *tile = ring + (size_t)st * STAGE_DOUBLES;
+      const double *mrow = tile + (4 * warp) * TILE + 4 * lane;
       double2 m[4][2];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
-        m[rr][0] = __ldg(reinterpret_cast<const double2 *>(mrow + (size_t)rr * np));
-        m[rr][1] = __ldg(reinterpret_cast<const double2 *>(mrow + (size_t)rr * np) + 1);
+        m[rr][0] = *reinterpret_cast<const double2 *>(mrow + rr * TILE);
+        m[rr][1] = *(reinterpret_cast<const double2 *>(mrow + rr * TILE) + 1);
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const double2 b0 = *reinterpret_cast<const double2 *>(a.Kx + (size_t)c * np + cb * TILE + 4 * lane);
-        const double2 b1 = *(reinterpret_cast<const double2 *>(a.Kx + (size_t)c * np + cb * TILE + 4 * lane) + 1);
+        const double2 b0 = *reinterpret_cast<const double2 *>(tile + SK_MTILE + c * TILE + 4 * lane);
+        const double2 b1 = *(reinterpret_cast<const double2 *>(tile + SK_MTILE + c * TILE + 4 * lane) + 1);
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-          double s = acc[rr][c];
-          s = fma(m[rr][0].x, b0.x, s);
-          s = fma(m[rr][0].y, b0.y, s);
-          s = fma(m[rr][1].x, b1.x, s);
-          s = fma(m[rr][1].y, b1.y, s);
-          acc[rr][c] = s;
+          double sacc = acc[rr][c];
+          sacc = fma(m[rr][0].x, b0.x, sacc);
+          sacc = fma(m[rr][0].y, b0.y, sacc);
+          sacc = fma(m[rr][1].x, b1.x, sacc);
+          sacc = fma(m[rr][1].y, b1.y, sacc);
+          acc[rr][c] = sacc;
         }
       }
       if (++cb > (p >> 2)) {
@@ -178,13 +241,26 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const Skinn
         ++p;
         cb = 0;
       }
+      __syncthreads();                                 // every warp has read stage st: refill it
+      if (issued < nu) {
+        if (warp == 0) sk_fence_proxy_async();
+        feed1(it + SK_STAGES);
+      }
     }
     if (cb > 0) flush1(p);
   }
-  if (want_var) grid.sync();
+  if (want_var) {
+    grid.sync();
+    // Z_c = the partial sums of the (at most SK_SLOTS1) CTAs that shared a panel, added in slot order
+    for (int e = g * SK_THREADS + tid; e < C * np; e += G * SK_THREADS) {
+      const int c = e / np, i = e - c * np;
+      a.Z[e] = sk_zsum<C>(a, c, i, G, T);
+    }
+    grid.sync();
+  }
 
   // ---- P2: U = M^T Z  (column blocks; lane l owns columns 4 l .. 4 l + 3, warp w rows 4 w .. 4 w + 3 of every panel) --------
-  if (want_dvar && u0 < u1) {
+  if (want_dvar && nu > 0) {
     int cb = 0;
     {
       // prefix2(cb) = cb P - 2 cb (cb - 1) is increasing in cb for cb <= nb: search
@@ -196,6 +272,24 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const Skinn
       cb = lo;
     }
     int p = 4 * cb + (int)(u0 - sk_prefix2(cb, P));
+    int ip = p, icb = cb, issued = 0;
+    auto feed2 = [&](int slot_it) {
+      const int st = slot_it % SK_STAGES;
+      if (warp == 0) {
+        const uint32_t bar = sk_smem_u32(&full_bar[st]);
+        double *dstM = ring + (size_t)st * STAGE_DOUBLES;
+        if (lane == 0) sk_mbar_expect_tx(bar, (uint32_t)(SK_MTILE * sizeof(double)));
+        __syncwarp();
+        sk_bulk_load(sk_smem_u32(dstM + lane * TILE), a.M + (size_t)(ip * SK_PH + lane) * np + icb * TILE, TILE * sizeof(double), bar);
+      }
+      if (++ip == P) {
+        ++icb;
+        ip = 4 * icb;
+      }
+      ++issued;
+    };
+    if (warp == 0) sk_fence_proxy_async();
+    for (int i = 0; i < SK_STAGES && i < nu; ++i) feed2(it + i);
     double acc[C][4];
 #pragma unroll
     for (int c = 0; c < C; ++c)
@@ -222,33 +316,44 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const Skinn
       }
       __syncthreads();
     };
-    for (long long u = u0; u < u1; ++u) {
-      const double *mrow = a.M + (size_t)(p * SK_PH + 4 * warp) * np + cb * TILE + 4 * lane;
-      double2 m[4][2];
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        m[rr][0] = __ldg(reinterpret_cast<const double2 *>(mrow + (size_t)rr * np));
-        m[rr][1] = __ldg(reinterpret_cast<const double2 *>(mrow + (size_t)rr * np) + 1);
+    // Z of the first panel; afterwards the next panel's values are fetched one chunk ahead
+    if (tid < C * SK_PH) zs[0][tid] = a.Z[(size_t)(tid >> 5) * np + p * SK_PH + (tid & 31)];
+    __syncthreads();
+    for (int i = 0; i < nu; ++i, ++it) {
+      const int st = it % SK_STAGES;
+      int pn = p + 1, cbn = cb;                         // the chunk after this one
+      if (pn == P) {
+        ++cbn;
+        pn = 4 * cbn;
       }
-      __syncthreads();                                  // zs of the previous chunk has been consumed
-      if (tid < C * SK_PH) zs[tid] = sk_zsum<C>(a, tid >> 5, p * SK_PH + (tid & 31), G, T);
-      __syncthreads();
+      double znext = 0.0;
+      if (i + 1 < nu && tid < C * SK_PH) znext = a.Z[(size_t)(tid >> 5) * np + pn * SK_PH + (tid & 31)];
+      sk_mbar_wait(sk_smem_u32(&full_bar[st]), (uint32_t)((it / SK_STAGES) & 1));
+      const double *mrow = ring + (size_t)st * STAGE_DOUBLES + (4 * warp) * TILE + 4 * lane;
+      const double *zc = zs[i & 1];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
+        const double2 m0 = *reinterpret_cast<const double2 *>(mrow + rr * TILE);
+        const double2 m1 = *(reinterpret_cast<const double2 *>(mrow + rr * TILE) + 1);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          const double z = zs[c * SK_PH + 4 * warp + rr];
-          acc[c][0] = fma(m[rr][0].x, z, acc[c][0]);
-          acc[c][1] = fma(m[rr][0].y, z, acc[c][1]);
-          acc[c][2] = fma(m[rr][1].x, z, acc[c][2]);
-          acc[c][3] = fma(m[rr][1].y, z, acc[c][3]);
+          const double z = zc[c * SK_PH + 4 * warp + rr];
+          acc[c][0] = fma(m0.x, z, acc[c][0]);
+          acc[c][1] = fma(m0.y, z, acc[c][1]);
+          acc[c][2] = fma(m1.x, z, acc[c][2]);
+          acc[c][3] = fma(m1.y, z, acc[c][3]);
         }
       }
-      if (++p == P) {
-        flush2(cb);
-        ++cb;
-        p = 4 * cb;
+      if (tid < C * SK_PH) zs[(i + 1) & 1][tid] = znext;
+      const bool col_done = (p + 1 == P);
+      __syncthreads();                                  // stage st and zs[i & 1] are free again
+      if (issued < nu) {
+        if (warp == 0) sk_fence_proxy_async();
+        feed2(it + SK_STAGES);
       }
+      if (col_done) flush2(cb);
+      p = pn;
+      cb = cbn;
     }
     if (p > 4 * cb) flush2(cb);
   }
@@ -267,7 +372,7 @@ __global__ void __launch_bounds__(SK_THREADS, 2) skinny_fused_kernel(const Skinn
         if (q0 == 0) {
           a_mu = fma(a.Kx[(size_t)c * np + j], al, a_mu);
           if (want_var) {
-            const double z = sk_zsum<C>(a, c, j, G, T);
+            const double z = a.Z[(size_t)c * np + j];
             a_vv = fma(z, z, a_vv);
           }
         }
@@ -353,52 +458,61 @@ template <int KIND, int C>
 static int launch_skinny_fused_t(SkinnyParams &a, double *part12, double *part3, cudaStream_t s) {
   static std::atomic<int> per_sm[64];                    // co-resident CTAs per SM of this instantiation, per device (0 = not yet known)
   static std::atomic<int> sms[64];
+  static FuncConfigMask configured{0};
+  constexpr size_t smem = (size_t)SK_STAGES * (SK_MTILE + C * TILE) * sizeof(double);
   int dev = 0;
   GPB_CUDA(cudaGetDevice(&dev));
   GPB_REQUIRE(dev >= 0 && dev < 64, "skinny: device ordinal %d out of range", dev);
-  if (per_sm[dev].load(std::memory_order_acquire) == 0) {
-    int occ = 0, nsm = 0, coop = 0;
-    GPB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    GPB_REQUIRE(coop != 0, "skinny: the device does not support cooperative launches");
-    GPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_fused_kernel<KIND, C>, SK_THREADS, 0));
-    GPB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    GPB_REQUIRE(occ >= 1 && nsm >= 1, "skinny: kernel does not fit an SM");
-    sms[dev].store(nsm, std::memory_order_release);
-    per_sm[dev].store(std::min(occ, 4), std::memory_order_release);
+  {
+    FuncConfigOnce once(configured);
+    if (once.needed) {
+      int occ = 0, nsm = 0, coop = 0;
+      GPB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+      GPB_REQUIRE(coop != 0, "skinny: the device does not support cooperative launches");
+      GPB_CUDA(cudaFuncSetAttribute(skinny_fused_kernel<KIND, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      GPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, skinny_fused_kernel<KIND, C>, SK_THREADS, smem));
+      GPB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      GPB_REQUIRE(occ >= 1 && nsm >= 1, "skinny: kernel does not fit an SM");
+      sms[dev].store(nsm, std::memory_order_release);
+      per_sm[dev].store(std::min(occ, 4), std::memory_order_release);
+    }
   }
   const int nb = a.np / TILE, P = a.np / SK_PH;
-  // G <= 4 (nb + 1) keeps the chunks of one row panel within SK_SLOTS1 CTAs and those of one column block within SK_SLOTS2
+  const long long T = 2ll * nb * (nb + 1);
+  // G <= 4 (nb + 1) keeps the chunks of one row panel within SK_SLOTS1 CTAs and those of one column block within SK_SLOTS2;
+  // G <= T gives every CTA at least one chunk, so that the CTAs sharing a panel / column block are consecutive (no unwritten slot)
   int G = std::min(sms[dev].load() * per_sm[dev].load(), 4 * (nb + 1));
-  G = std::min(G, 148 * 4);
+  G = (int)std::min<long long>(std::min(G, 148 * 4), T);
   a.part1 = part12;
   a.part2 = a.part1 + (size_t)P * SK_SLOTS1 * 8 * SK_PH;
   a.part3 = part3;
   a.ticket = reinterpret_cast<unsigned int *>(a.part3 + (size_t)(148 * 4) * 8 * (2 + 2 * a.d));
   void *args[] = {&a};
-  GPB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(skinny_fused_kernel<KIND, C>), dim3(G), dim3(SK_THREADS), args, 0, s));
+  GPB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(skinny_fused_kernel<KIND, C>), dim3(G), dim3(SK_THREADS), args, smem, s));
   count_launch();
   return 0;
 }
 
-// mc <= 8 candidates (raw coordinates Xc on the device).  Kx, Dk: 8 x np doubles each; part12 / part3 as sized above, the last 8
+// mc <= 8 candidates (raw coordinates Xc on the device).  Kx, Dk, Z: 8 x np doubles each; part12 / part3 as sized above, the last 8
 // doubles of part3 (the arrival counter) zeroed once.  level as in predict_block (1, 2 or 3).
 int launch_skinny_fused(int kind, const double *M, int np, int n, int d, int mc, int level, const double *XT, const double *Xc,
                         const double *ls, const double *inv_ls, const double *alpha, double variance, double var_base, double *Kx,
-                        double *Dk, double *part12, double *part3, double *mu, double *var, double *dmu, double *dvar, cudaStream_t s) {
+                        double *Dk, double *Z, double *part12, double *part3, double *mu, double *var, double *dmu, double *dvar,
+                        cudaStream_t s) {
   GPB_REQUIRE(mc >= 1 && mc <= 8 && d >= 1 && d <= 64 && (level == 1 || level == 2 || level == 3), "skinny: bad arguments");
   SkinnyParams a;
   a.M = M; a.XT = XT; a.Xc = Xc; a.ls = ls; a.inv_ls = inv_ls; a.alpha = alpha;
-  a.Kx = Kx; a.Dk = Dk;
+  a.Kx = Kx; a.Dk = Dk; a.Z = Z;
   a.mu = mu; a.var = var; a.dmu = dmu; a.dvar = dvar;
   a.variance = variance; a.var_base = var_base;
   a.np = np; a.n = n; a.d = d; a.mc = mc; a.level = level;
   const int c = mc <= 1 ? 1 : mc <= 2 ? 2 : mc <= 4 ? 4 : 8;
-#define GPB_SKF(K_)                                                     \
-  do {                                                                  \
-    if (c == 1) return launch_skinny_fused_t<K_, 1>(a, part12, part3, s);     \
-    if (c == 2) return launch_skinny_fused_t<K_, 2>(a, part12, part3, s);     \
-    if (c == 4) return launch_skinny_fused_t<K_, 4>(a, part12, part3, s);     \
-    return launch_skinny_fused_t<K_, 8>(a, part12, part3, s);                 \
+#define GPB_SKF(K_)                                                            \
+  do {                                                                         \
+    if (c == 1) return launch_skinny_fused_t<K_, 1>(a, part12, part3, s);      \
+    if (c == 2) return launch_skinny_fused_t<K_, 2>(a, part12, part3, s);      \
+    if (c == 4) return launch_skinny_fused_t<K_, 4>(a, part12, part3, s);      \
+    return launch_skinny_fused_t<K_, 8>(a, part12, part3, s);                  \
   } while (0)
   if (kind == GPB_KERN_RBF) GPB_SKF(GPB_KERN_RBF);
   GPB_SKF(GPB_KERN_MATERN52);

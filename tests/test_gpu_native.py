@@ -346,7 +346,7 @@ def test_small_candidate_counts_use_the_skinny_products(kind, N, D):
         assert_allclose(var, var_r, rtol=1e-9, atol=1e-12)
         mu0, none = m.predict(Xc[:mc], want_var=False)                  # mean only
         assert none is None
-        assert_allclose(mu0, mu, rtol=1e-13, atol=0)
+        assert_allclose(mu0, mu, rtol=1e-11, atol=0)      # (the mean-only call sums the same products in another fixed order)
         dm, dv = m.predictive_gradients(Xc[:mc])
         dm9, dv9 = m.predictive_gradients(Xc)
         assert_allclose(dm, dm9[:mc], rtol=1e-9, atol=1e-12 * np.abs(dm9).max())

@@ -173,8 +173,8 @@ def test_rows_of_a_batched_call_equal_the_single_row_calls_bitwise(n, d):
                 for key in ("f", "df", "m", "s", "dmdx", "dsdx"):
                     assert np.array_equal(r[key][i:i + 1], r1[key]), (mc, acq, key)
                 f1, df1 = nm.acquisition_lp(acq, par, fmin, Xc[i:i + 1], with_gradients=True)
-                assert np.all(np.isfinite(f1)) and np.all(np.isfinite(df1))
-                assert np.array_equal(f_lp[i:i + 1], f1) and np.array_equal(df_lp[i:i + 1], df1)
+                # (an EI that underflows to 0 makes the reference's 1 / acq scale infinite, LP.py:121-126: inf / nan must match too)
+                assert np.array_equal(f_lp[i:i + 1], f1, equal_nan=True) and np.array_equal(df_lp[i:i + 1], df1, equal_nan=True)
     nm.close()
 
 
