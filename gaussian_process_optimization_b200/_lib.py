@@ -78,6 +78,8 @@ SIGNATURES = {
     "gpb_ozaki_dgemm": (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.c_double, c_void_p, c_int, c_void_p, c_int, ctypes.c_double,
                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "gpb_set_ozaki": (c_int, [c_int, c_int]),
+    "gpb_model_engine_report": (c_int, [c_void_p, c_int_p, c_double_p]),
+    "gpb_ozaki_fallback_count": (ctypes.c_longlong, []),
     "gpb_ozaki_crt_bits": (c_int, [c_int, ctypes.c_longlong]),
     "gpb_ozaki_crt_host_residues": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gpb_ozaki_crt_host_combine": (c_int, [c_void_p, ctypes.c_longlong, c_int, c_void_p]),

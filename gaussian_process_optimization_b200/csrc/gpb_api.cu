@@ -243,6 +243,10 @@ struct gpb_model {
   double *topv = nullptr;
   long long *topi = nullptr;
   double *sk_part3 = nullptr;   // per-CTA sums + arrival counter of the fused M <= 8 call (gpb_skinny.cu)
+  // int8 engine (experimental): every fit that used it is followed by a residual check of the solve; a failed check refits on the
+  // fp64 DMMA engine, and the predictive products of that posterior stay there as well
+  bool engine_used = false, engine_ok = true;
+  double last_residual = -1.0;
   double *pinned = nullptr;  // host: [0, 256) results / hyper-parameters of a fit; [PIN_X, +512) staged candidates and
                              // [PIN_OUT, +PIN_OUT_DOUBLES) staged results of the M <= 8 calls (one synchronisation per call)
   struct Staged { double *dst; size_t off, count; };
@@ -286,6 +290,18 @@ static int leave_stream_ordered(gpb_model *m) {
 }
 
 constexpr size_t PIN_X = 256, PIN_OUT = 768, PIN_OUT_DOUBLES = 8 * (3 + 3 * 64), PIN_TOTAL = PIN_OUT + PIN_OUT_DOUBLES;
+
+// Residual check of fits that used the int8 engine: tolerance on the componentwise backward error (0 switches the check off).  A
+// backward-stable fp64 solve sits at a few eps sqrt(N) (~1e-14); 2e-13 (~1000 eps) is what keeps every result inside the
+// cond(Ky) * eps allowances of the parity tests.
+static double ozaki_check_tol() {
+  static const double tol = [] {
+    const char *e = getenv("GPB_OZAKI_CHECK_TOL");
+    return e ? atof(e) : 2e-13;
+  }();
+  return tol;
+}
+static std::atomic<long long> g_engine_fallbacks{0};
 
 static int g_overlap_min_n = 512;  // 0 disables the two-stream schedule (gpb_set_overlap)
 static int g_config_epoch = 0;     // bumped by the tuning entry points: captured launch sequences are stale afterwards
@@ -616,6 +632,16 @@ static int fit_launch_general(gpb_model *m, int want_grad, double extra_jitter, 
     GPB_TRY(append_from > 0 ? factor_append(m->f, append_from) : factor_potrf_inv(m->f));
   }
   GPB_TRY(factor_solve(m->f, m->Yc, p, m->z, m->alpha));
+  // The int8 engine's products are accurate relative to the largest entry of an operand ROW, not entry by entry: when
+  // it took part in this factorisation, measure what that did to the solve -- the componentwise backward error of Ky alpha = y,
+  // against a Ky rebuilt from the inputs (W is free between the factorisation and the inverse) -- and let fit_core fall back.
+  m->engine_used = ozaki_min_n() > 0 && np >= ozaki_min_n() && append_from == 0;
+  if (m->engine_used && p == 1 && ozaki_check_tol() > 0.0) {
+    GPB_TRY(factor_finalize_L(m->f));
+    GPB_TRY(launch_kmat(m->kind, kc.XT, np, kc.XT, np, d, n, n, kc.var, m->noise + 1e-8 + extra_jitter, 1, m->f.W, np, np, np, m->stream,
+                        kc.gflag, 0, theta));
+    GPB_TRY(launch_solve_residual(m->f.W, np, n, m->alpha, m->Yc, m->scal + d + 8, m->stream));
+  }
   GPB_TRY(factor_logdet(m->f, m->scal + 0));
   dot_kernel<<<1, 1024, 0, m->stream>>>(m->alpha, m->Yc, p * np, m->scal + 1);
   count_launch();
@@ -629,7 +655,7 @@ static int fit_launch_general(gpb_model *m, int want_grad, double extra_jitter, 
       GPB_TRY(launch_kvar_gower(m->kind, 1, kc.XT, np, kc.XT, np, d, n, n, kc.var, kc.gflag, m->f.W, np, m->alpha, np, p, m->gpart,
                                 m->scal + 2, m->stream));
   }
-  GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 5) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+  GPB_CUDA(cudaMemcpyAsync(m->pinned, m->scal, (d + 9) * sizeof(double), cudaMemcpyDeviceToHost, m->stream));
   GPB_CUDA(cudaMemcpyAsync(m->pinned + 128, m->f.info, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
   return 0;
 }
@@ -735,6 +761,29 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
   if (info != 0) {
     set_error("fit: matrix not positive definite (leading minor %d)", info);
     return info > n ? n : info;
+  }
+  m->engine_ok = true;
+  m->last_residual = -1.0;
+  if (!tiny && m->engine_used && p == 1 && ozaki_check_tol() > 0.0) {
+    m->last_residual = m->pinned[d + 8];
+    if (!(m->last_residual <= ozaki_check_tol())) {
+      // the engine's row-wise accuracy was not enough for this matrix: the same evaluation on the fp64 DMMA engine
+      g_engine_fallbacks.fetch_add(1, std::memory_order_relaxed);
+      ozaki_suppress(1);
+      m->have_wi = false;
+      const int rc2 = fit_launch_general(m, want_grad, extra_jitter, append_from, nullptr);
+      const cudaError_t e2 = rc2 == 0 ? cudaStreamSynchronize(m->stream) : cudaSuccess;
+      ozaki_suppress(0);
+      GPB_TRY(rc2);
+      GPB_CUDA(e2);
+      m->engine_ok = false;
+      m->engine_used = false;
+      const int info2 = *reinterpret_cast<int *>(m->pinned + 128);
+      if (info2 != 0) {
+        set_error("fit: matrix not positive definite (leading minor %d)", info2);
+        return info2 > n ? n : info2;
+      }
+    }
   }
   const double logdet = m->pinned[0], ay = m->pinned[1];
   out[0] = 0.5 * (-(double)n * p * log(2.0 * M_PI) - (double)p * logdet - ay);  // exact_gaussian_inference.py:62
@@ -887,7 +936,9 @@ int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) 
 // largest entry of a row of M, not entry by entry (with 7 digits LCB values of an ill-conditioned RBF model moved by 4e-10).
 // 8 digits, or 18 moduli (62 bits per operand) when the engine is configured in its modular mode
 #define OZAKI_PREDICT_DIGITS ozaki_predict_planes()
-static inline bool ozaki_predict(int np, int cpad) { return ozaki_min_n() > 0 && np >= ozaki_min_n() && cpad >= 1024; }
+static inline bool ozaki_predict(const gpb_model *m, int np, int cpad) {
+  return m->engine_ok && ozaki_min_n() > 0 && np >= ozaki_min_n() && cpad >= 1024;
+}
 
 static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int level, int include_likelihood) {
   const int n = m->n, np = m->np, d = m->d, p = m->p;
@@ -953,7 +1004,7 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
     // Vt = KxT M^T  (== (L^-1 Kx)^T: dtrtrs of posterior.py:293 as a product with the explicit inverse factor)
     GemmArgs g{m->KxT, np, m->f.Mi, np, m->Vt, np, cpad, np, np, 1.0, 0.0, 0, 0, 2};
     // experimental int8 engine (gpb_ozaki.cu) for big candidate blocks; the digit planes of L^-1 are cut once per factorisation
-    if (ozaki_predict(np, cpad)) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, 0, 1, OZAKI_PREDICT_DIGITS, s, 1));
+    if (ozaki_predict(m, np, cpad)) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, 0, 1, OZAKI_PREDICT_DIGITS, s, 1));
     else GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_ROWK, g, s));
     // var = Kdiag - sum(tmp^2) (+ noise)                            posterior.py:294-295, gaussian.py:109
     GPB_TRY(launch_var_from_vt(m->Vt, np, mcb, n, m->variance + (include_likelihood ? m->noise : 0.0), m->var, s));
@@ -963,7 +1014,7 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
     // Ut = Vt M = (Ky^-1 Kx)^T                                      core/gp.py:450-451 (woodbury_inv product as 2nd triangular product)
     if (!skinny) {
       GemmArgs g{m->Vt, np, m->f.Mi, np, m->Ut, np, cpad, np, np, 1.0, 0.0, 0, 2, 0};
-      if (ozaki_predict(np, cpad)) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, 0, 2, OZAKI_PREDICT_DIGITS, s, 2));
+      if (ozaki_predict(m, np, cpad)) GPB_TRY(ozaki_gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, 0, 2, OZAKI_PREDICT_DIGITS, s, 2));
       else GPB_TRY(gemm_launch(LAYOUT_ROWK, LAYOUT_COLK, g, s));
     }
     // dmu = gradients_X(alpha^T, X*, X); dvar = gradients_X(-2 Kx^T Wi, X*, X)     core/gp.py:431-434,450-453
@@ -1760,6 +1811,13 @@ int gpb_ozaki_dgemm(int ta, int tb, int m, int n, int k, double alpha, const dou
                            reinterpret_cast<cudaStream_t>(stream));
 }
 int gpb_set_ozaki(int min_n, int slices) { return ozaki_configure(min_n, slices); }
+int gpb_model_engine_report(gpb_model *m, int *engine_used, double *residual) {
+  GPB_REQUIRE(m, "engine_report: NULL model");
+  if (engine_used) *engine_used = m->engine_used ? 1 : 0;
+  if (residual) *residual = m->last_residual;
+  return 0;
+}
+long long gpb_ozaki_fallback_count(void) { return g_engine_fallbacks.load(std::memory_order_relaxed); }
 // modular mode of the int8 engine: operand bits, and the host restatement of its integer arithmetic (test hooks, no GPU needed)
 int gpb_ozaki_crt_bits(int nmod, long long k) { return ozaki_crt_bits(nmod, k); }
 int gpb_ozaki_crt_host_residues(const double *A, int rows, int k, int nmod, int beta, signed char *planes, double *scale) {

@@ -71,5 +71,7 @@ int launch_topk_update(const double *f, int n_c, long long index_base, double *v
 int launch_topk_pack(const double *vals, const long long *idx, const double *Xc_dev, int d, int k, long long index_offset, double *out,
                      cudaStream_t s);
 int launch_min(const double *v, int n, double *out, cudaStream_t s);
+// out[0] = max_i |Ky alpha - y|_i / (|Ky| |alpha| + |y|)_i over the n x n leading part of the full symmetric Ky
+int launch_solve_residual(const double *Ky, int ld, int n, const double *alpha, const double *y, double *out, cudaStream_t s);
 
 }  // namespace gpb

@@ -712,7 +712,10 @@ static bool valid_planes(int s) { return (s >= 1 && s <= MAX_S) || (s >= crt::MI
 
 }  // namespace oz
 
+static thread_local int t_suppress = 0;   // > 0: this host thread's calls stay on the fp64 DMMA engine (fallback after a failed residual check)
+void ozaki_suppress(int on) { t_suppress += on ? 1 : -1; }
 int ozaki_min_n() {
+  if (t_suppress > 0) return 0;
   if (oz::g_min_n < 0) {
     const char *e = getenv("GPB_OZAKI_MIN_N");
     oz::g_min_n = e ? atoi(e) : 0;

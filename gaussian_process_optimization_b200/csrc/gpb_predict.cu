@@ -461,6 +461,39 @@ __global__ void min_kernel(const double *__restrict__ v, int n, double *out) {
   }
 }
 
+// Componentwise backward error of the solve (Oettli-Prager): omega = max_i |Ky alpha - y|_i / (|Ky| |alpha| + |y|)_i, one warp per row
+// of the full symmetric Ky (np x np), maximum taken with an integer atomic on the bit pattern (non-negative doubles order like
+// integers; the maximum does not depend on the order of arrival).  *out must be zero before the launch.
+__global__ void solve_residual_kernel(const double *__restrict__ Ky, int ld, int n, const double *__restrict__ alpha,
+                                      const double *__restrict__ y, double *out) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const double *row = Ky + (size_t)i * ld;
+  double r = 0.0, sc = 0.0;
+  for (int j = lane; j < n; j += 32) {
+    const double t = row[j] * alpha[j];
+    r += t;
+    sc += fabs(t);
+  }
+  r = warp_sum(r);
+  sc = warp_sum(sc);
+  if (lane == 0) {
+    const double yi = y[i];
+    const double den = sc + fabs(yi);
+    double om = den > 0.0 ? fabs(r - yi) / den : 0.0;
+    if (!(om == om)) om = INFINITY;                        // NaN anywhere -> the check fails
+    atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(om));
+  }
+}
+
+int launch_solve_residual(const double *Ky, int ld, int n, const double *alpha, const double *y, double *out, cudaStream_t s) {
+  GPB_CUDA(cudaMemsetAsync(out, 0, sizeof(double), s));
+  solve_residual_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(Ky, ld, n, alpha, y, out);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_min(const double *v, int n, double *out, cudaStream_t s) {
   min_kernel<<<1, 1024, 0, s>>>(v, n, out);
   count_launch();

@@ -15,11 +15,13 @@
 //   P3  mu = k*^T alpha, var = base - |Z|^2, d mu / dx* and d var / dx*     (posterior.py:276,294-295; core/gp.py:431-434,450-453;
 //                                                                            stationary.py:354-364)
 // with the 32 KB chunks of the triangle dealt to the CTAs in contiguous, equal runs (+-1 chunk) and streamed through a 4-stage
-// shared-memory ring by the TMA engine (cp.async.bulk row copies completing on mbarriers: the first version, which loaded the
-// chunks into registers, kept too few bytes in flight -- 4.8 of 6.5 TB/s, ncu r2c), every lane owning four columns of a chunk.
+// shared-memory ring by the TMA engine -- ONE cp.async.bulk.tensor.2d per chunk (tensor map over M, box 128 x 32 doubles) completing on
+// an mbarrier -- every lane owning four columns of a chunk.  (History, ncu r2c / r2d: loading the chunks into registers kept too few
+// bytes in flight, 4.8 of 6.5 TB/s; 32 one-row bulk copies of 1 KB per chunk made the TMA engine's per-operation cost the bound, 2.7.)
 // All partial sums are combined in fixed orders that do not depend on the number of candidates sharing the call: candidate c's
 // results are bit-identical whether it is evaluated alone or with seven others, and run to run.
 #include <cooperative_groups.h>
+#include <cuda.h>
 
 #include <algorithm>
 
@@ -55,10 +57,10 @@ __device__ __forceinline__ void sk_mbar_wait(uint32_t bar, uint32_t parity) {
                  : "memory");
   }
 }
-// one contiguous run of bytes (multiple of 16, 16-byte aligned on both sides) global -> shared through the TMA engine
-__device__ __forceinline__ void sk_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-               "r"(bar)
+// one box of a 2-d tensor map (inner coordinate c0 = column, c1 = row) global -> shared through the TMA engine
+__device__ __forceinline__ void sk_tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ void sk_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -107,7 +109,8 @@ __device__ __forceinline__ double sk_usum(const SkinnyParams &a, int c, int j, i
 }
 
 template <int KIND, int C>
-__global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const SkinnyParams a) {
+__global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const __grid_constant__ CUtensorMap mapM,
+                                                                      const __grid_constant__ CUtensorMap mapK, const SkinnyParams a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(128) unsigned char sk_dyn[];   // ring: SK_STAGES x (chunk of M | C x 128 right-hand sides)
   __shared__ double xcs[8 * 64];              // candidates divided by the lengthscales, [c][q]
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const Skinn
   const long long T = 2ll * nb * (nb + 1);
   const bool want_var = a.level == 1 || a.level == 2, want_g = a.level >= 2, want_dvar = a.level == 2;
   constexpr int STAGE_DOUBLES = SK_MTILE + C * TILE;
-  double *ring = reinterpret_cast<double *>(sk_dyn);
+  double *ring = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sk_dyn) + 127) & ~uintptr_t(127));   // TMA destinations: 128-byte aligned
   if (tid == 0) {
     for (int st = 0; st < SK_STAGES; ++st) sk_mbar_init(sk_smem_u32(&full_bar[st]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -178,14 +181,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const Skinn
     int ip = p, icb = cb, issued = 0;
     auto feed1 = [&](int slot_it) {   // warp 0: one chunk of M (32 rows of 1 KB) and the matching 1 KB of every right-hand side
       const int st = slot_it % SK_STAGES;
-      if (warp == 0) {
+      if (tid == 0) {
         const uint32_t bar = sk_smem_u32(&full_bar[st]);
         double *dstM = ring + (size_t)st * STAGE_DOUBLES;
-        if (lane == 0) sk_mbar_expect_tx(bar, (uint32_t)(STAGE_DOUBLES * sizeof(double)));
-        __syncwarp();
-        sk_bulk_load(sk_smem_u32(dstM + lane * TILE), a.M + (size_t)(ip * SK_PH + lane) * np + icb * TILE, TILE * sizeof(double), bar);
-        if (lane < C)
-          sk_bulk_load(sk_smem_u32(dstM + SK_MTILE + lane * TILE), a.Kx + (size_t)lane * np + icb * TILE, TILE * sizeof(double), bar);
+        sk_mbar_expect_tx(bar, (uint32_t)(STAGE_DOUBLES * sizeof(double)));
+        sk_tma_load_2d(sk_smem_u32(dstM), &mapM, icb * TILE, ip * SK_PH, bar);            // 32 rows x 128 columns of M
+        sk_tma_load_2d(sk_smem_u32(dstM + SK_MTILE), &mapK, icb * TILE, 0, bar);          // the same 128 columns of the C right-hand sides
       }
       if (++icb > (ip >> 2)) {
         ++ip;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const Skinn
       }
       ++issued;
     };
-    if (warp == 0) sk_fence_proxy_async();
+    if (tid == 0) sk_fence_proxy_async();
     for (int i = 0; i < SK_STAGES && i < nu; ++i) feed1(it + i);
     double acc[4][C];
 #pragma unroll
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const Skinn
       }
       __syncthreads();                                 // every warp has read stage st: refill it
       if (issued < nu) {
-        if (warp == 0) sk_fence_proxy_async();
+        if (tid == 0) sk_fence_proxy_async();
         feed1(it + SK_STAGES);
       }
     }
@@ -275,12 +276,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const Skinn
     int ip = p, icb = cb, issued = 0;
     auto feed2 = [&](int slot_it) {
       const int st = slot_it % SK_STAGES;
-      if (warp == 0) {
+      if (tid == 0) {
         const uint32_t bar = sk_smem_u32(&full_bar[st]);
-        double *dstM = ring + (size_t)st * STAGE_DOUBLES;
-        if (lane == 0) sk_mbar_expect_tx(bar, (uint32_t)(SK_MTILE * sizeof(double)));
-        __syncwarp();
-        sk_bulk_load(sk_smem_u32(dstM + lane * TILE), a.M + (size_t)(ip * SK_PH + lane) * np + icb * TILE, TILE * sizeof(double), bar);
+        sk_mbar_expect_tx(bar, (uint32_t)(SK_MTILE * sizeof(double)));
+        sk_tma_load_2d(sk_smem_u32(ring + (size_t)st * STAGE_DOUBLES), &mapM, icb * TILE, ip * SK_PH, bar);
       }
       if (++ip == P) {
         ++icb;
@@ -288,7 +287,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const Skinn
       }
       ++issued;
     };
-    if (warp == 0) sk_fence_proxy_async();
+    if (tid == 0) sk_fence_proxy_async();
     for (int i = 0; i < SK_STAGES && i < nu; ++i) feed2(it + i);
     double acc[C][4];
 #pragma unroll
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const Skinn
       const bool col_done = (p + 1 == P);
       __syncthreads();                                  // stage st and zs[i & 1] are free again
       if (issued < nu) {
-        if (warp == 0) sk_fence_proxy_async();
+        if (tid == 0) sk_fence_proxy_async();
         feed2(it + SK_STAGES);
       }
       if (col_done) flush2(cb);
@@ -454,12 +453,40 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const Skinn
 size_t skinny_fused_part12_doubles(int np) { return (size_t)np * (SK_SLOTS1 * 8 + SK_SLOTS2 * 8); }
 size_t skinny_fused_part3_doubles(int d) { return (size_t)(148 * 4) * 8 * (2 + 2 * d) + 8; }
 
+typedef CUresult (*SkEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static SkEncodeTiledFn sk_encode_fn() {
+  static const SkEncodeTiledFn fn = [] {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      return (SkEncodeTiledFn)ptr;
+    return (SkEncodeTiledFn) nullptr;
+  }();
+  return fn;
+}
+// rows x cols fp64 matrix with row pitch ld doubles -> 2-d tensor map with boxes of box_rows x 128 doubles (no swizzle: a warp reads a
+// 1 KB row of the box with consecutive 32-byte pieces per lane, which is conflict free as it stands)
+static int sk_make_map(CUtensorMap *map, const double *base, int rows, int cols, int ld, int box_rows) {
+  SkEncodeTiledFn fn = sk_encode_fn();
+  GPB_REQUIRE(fn != nullptr, "skinny: cuTensorMapEncodeTiled is not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  cuuint32_t box[2] = {(cuuint32_t)TILE, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GPB_REQUIRE(r == CUDA_SUCCESS, "skinny: cuTensorMapEncodeTiled failed (%d) for %d x %d, ld %d", (int)r, rows, cols, ld);
+  return 0;
+}
+
 template <int KIND, int C>
 static int launch_skinny_fused_t(SkinnyParams &a, double *part12, double *part3, cudaStream_t s) {
   static std::atomic<int> per_sm[64];                    // co-resident CTAs per SM of this instantiation, per device (0 = not yet known)
   static std::atomic<int> sms[64];
   static FuncConfigMask configured{0};
-  constexpr size_t smem = (size_t)SK_STAGES * (SK_MTILE + C * TILE) * sizeof(double);
+  constexpr size_t smem = (size_t)SK_STAGES * (SK_MTILE + C * TILE) * sizeof(double) + 128;
   int dev = 0;
   GPB_CUDA(cudaGetDevice(&dev));
   GPB_REQUIRE(dev >= 0 && dev < 64, "skinny: device ordinal %d out of range", dev);
@@ -477,6 +504,9 @@ static int launch_skinny_fused_t(SkinnyParams &a, double *part12, double *part3,
       per_sm[dev].store(std::min(occ, 4), std::memory_order_release);
     }
   }
+  CUtensorMap mapM, mapK;
+  GPB_TRY(sk_make_map(&mapM, a.M, a.np, a.np, a.np, SK_PH));
+  GPB_TRY(sk_make_map(&mapK, a.Kx, C, a.np, a.np, C));
   const int nb = a.np / TILE, P = a.np / SK_PH;
   const long long T = 2ll * nb * (nb + 1);
   // G <= 4 (nb + 1) keeps the chunks of one row panel within SK_SLOTS1 CTAs and those of one column block within SK_SLOTS2;
@@ -487,7 +517,7 @@ static int launch_skinny_fused_t(SkinnyParams &a, double *part12, double *part3,
   a.part2 = a.part1 + (size_t)P * SK_SLOTS1 * 8 * SK_PH;
   a.part3 = part3;
   a.ticket = reinterpret_cast<unsigned int *>(a.part3 + (size_t)(148 * 4) * 8 * (2 + 2 * a.d));
-  void *args[] = {&a};
+  void *args[] = {&mapM, &mapK, &a};
   GPB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(skinny_fused_kernel<KIND, C>), dim3(G), dim3(SK_THREADS), args, smem, s));
   count_launch();
   return 0;

@@ -188,6 +188,11 @@ def set_ozaki(min_n, slices=8):
     check(_lib.load().gpb_set_ozaki(int(min_n), int(slices)), "set_ozaki")
 
 
+def ozaki_fallback_count():
+    """Fits of this process that the int8 engine's residual check sent back to the fp64 DMMA engine."""
+    return int(_lib.load().gpb_ozaki_fallback_count())
+
+
 def ozaki_crt_bits(nmod, k):
     """Bits per operand the modular mode of the int8 engine carries with nmod moduli at inner dimension k."""
     return int(_lib.load().gpb_ozaki_crt_bits(int(nmod), int(k)))
@@ -308,6 +313,12 @@ class NativeModel(object):
         if rc > 0:
             return rc, None, None
         return 0, float(out[0]), (out[1:].copy() if want_grad else None)
+
+    def engine_report(self):
+        """-> (the current posterior came from the int8 engine, componentwise backward error of its solve or -1 if unchecked)."""
+        used, res = ctypes.c_int(0), ctypes.c_double(0.0)
+        check(self._lib.gpb_model_engine_report(self._h, ctypes.byref(used), ctypes.byref(res)), "engine_report")
+        return bool(used.value), res.value
 
     def append(self, Xnew, Yall, want_grad=True):
         """Extend the fitted model by the rows Xnew (targets replaced by Yall) without refactorising: O(N^2 b).

@@ -203,6 +203,13 @@ int gpb_ozaki_dgemm(int ta, int tb, int m, int n, int k, double alpha, const dou
 /* Products of gpb_model_fit's factorisation with at least min_n rows go through the int8 engine (0 = off, the default; also
  * GPB_OZAKI_MIN_N / GPB_OZAKI_SLICES in the environment). */
 int gpb_set_ozaki(int min_n, int slices);
+/* Safety net of the engine inside gpb_model_fit.  Its products are accurate relative to the largest entry of an operand row, not
+ * entry by entry, so every fit that used it measures the componentwise backward error of the solve Ky alpha = y against a Ky rebuilt
+ * from the inputs; above the tolerance (2e-13, GPB_OZAKI_CHECK_TOL; 0 = no check) the evaluation is repeated on the fp64 DMMA engine
+ * and the predictive products of that posterior stay there too.  engine_report: whether the current posterior came from the engine,
+ * and the backward error measured (-1 if no check ran); fallback_count: fits of this process that were repeated. */
+int gpb_model_engine_report(gpb_model *m, int *engine_used, double *residual);
+long long gpb_ozaki_fallback_count(void);
 /* Modular (CRT) mode of the same engine: slices in [10, 18] means "that many pairwise coprime moduli <= 256" instead of digits --
  * ONE int8 product per modulus (16 moduli carry 56 bits per operand at k = 16384, where 7 digits = 28 products carry 55), the
  * integer product rebuilt by the Chinese remainder theorem (csrc/gpb_crt.cuh).  gpb_ozaki_crt_bits: bits per operand for nmod moduli

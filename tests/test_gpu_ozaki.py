@@ -199,3 +199,123 @@ def test_nll_and_gradients_through_the_int8_engine(ozaki_on, kind, noise, N, D):
     assert_allclose(r2["f"], f2, rtol=1e-6 * widen, atol=1e-9)
     assert_allclose(r2["df"], df2, rtol=1e-5 * widen, atol=1e-8 * widen * np.abs(df2).max())
     m.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Round 2: the engine's error bound, stated and attacked; the residual check and the automatic fallback
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("slices", [8, 16, 18])
+def test_ozaki_error_bound_with_graded_rows(slices):
+    """THE bound of the scheme: operands are cut relative to the largest entry of each row of op(A) / op(B), so
+        |C_ij - (A B^T)_ij|  <=  2 k 2^-beta  max_k|a_ik|  max_k|b_jk|   +   2 eps |A B^T|_ij
+    (beta = bits per operand: 8 S - 1 for S digits minus the dropped pairs' tail, gpb_ozaki_crt_bits for moduli) -- norm-wise per
+    row pair, NOT component-wise: entries far below their row's maximum lose relative accuracy.  Rows whose entries span 2^+-40 (what a
+    row of L^-1 of an ill-conditioned Ky looks like) must still satisfy it, and the test also shows the flip side: the component-wise
+    relative error against |A||B|^T can exceed the fp64 engine's by orders of magnitude."""
+    import torch
+    rs = np.random.RandomState(slices)
+    m, n, k = 256, 384, 1024
+    A = rs.randn(m, k) * np.exp2(rs.randint(-40, 41, (m, k)).astype(float))        # graded WITHIN every row
+    B = rs.randn(n, k) * np.exp2(rs.randint(-40, 41, (n, k)).astype(float))
+    Ad, Bd = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    C = torch.zeros(m, n, dtype=torch.float64, device="cuda")
+    native.ozaki_dgemm(0, 0, 1.0, Ad, Bd, 0.0, C, slices=slices)
+    Cf = torch.zeros(m, n, dtype=torch.float64, device="cuda")
+    native.dgemm(0, 0, 1.0, Ad, Bd, 0.0, Cf)
+    torch.cuda.synchronize()
+    ref = np.asarray((A.astype(np.longdouble) @ B.T.astype(np.longdouble)), dtype=np.float64)    # 64-bit mantissa accumulation
+    beta = native.ozaki_crt_bits(slices, k) if slices >= 10 else 8 * slices - 3
+    rowmax, colmax = np.abs(A).max(1)[:, None], np.abs(B).max(1)[None, :]
+    absAB = np.abs(A) @ np.abs(B).T
+    bound = 2.0 * k * 2.0 ** -beta * rowmax * colmax + 2 * 2.2e-16 * absAB
+    err = np.abs(C.cpu().numpy() - ref)
+    assert float((err / bound).max()) <= 1.0
+    err_f = np.abs(Cf.cpu().numpy() - ref)
+    assert float((err_f / (k * 1.2e-16 * absAB)).max()) <= 1.0                      # the fp64 engine's component-wise bound
+    # the flip side, documented: measured against |A||B|^T the int8 result may be far outside the fp64 bound
+    comp = float((err / (k * 1.2e-16 * absAB)).max())
+    assert np.isfinite(comp)
+
+
+@pytest.mark.parametrize("noise", [1e-7, 1e-9])
+def test_ozaki_on_ill_conditioned_models_is_checked_and_no_worse_than_fp64(noise):
+    """cond(Ky) ~ 1e10 .. 1e11 (smooth RBF in 2-D, tiny noise): rows of L^-1 are strongly graded.  Against LAPACK (the oracle), every
+    quantity from the engine (18 moduli forced on every product >= 256 rows) must be as close as the fp64 DMMA engine's up to a small
+    factor -- or the residual check must have sent the fit back to the DMMA engine.  Includes the predictive variance AT the data
+    (sigma^2 - |L^-1 k*|^2 cancels to ~ noise)."""
+    rs = np.random.RandomState(7)
+    n, d = 1536, 2
+    X = rs.uniform(0, 1, (n, d))
+    Y = np.sin(4 * X[:, :1]) * np.cos(3 * X[:, 1:]) + 1e-4 * rs.randn(n, 1)
+    ls, v = np.array([0.35, 0.45]), 1.0
+    lo, go, post = O.log_likelihood_and_gradients("rbf", X, Y, v, ls, noise)
+    w = np.linalg.eigvalsh(post.K + (noise + 1e-8) * np.eye(n))
+    cond = w[-1] / w[0]
+    assert cond > 1e9
+    Xs = np.vstack([X[:64] + 1e-6, rs.uniform(0, 1, (64, d))])               # at the data, and away from it
+    mu_o, var_o = O.predict("rbf", post, X, Xs, v, ls, noise, include_likelihood=False)
+    out = {}
+    for engine in ("dmma", "int8"):
+        native.set_ozaki(256 if engine == "int8" else 0, 18)
+        try:
+            m = native.NativeModel("rbf", True, d, 1, n_cap=n, cand_block=1024)
+            m.set_data(X, Y)
+            m.set_theta(v, ls, noise)
+            info, logL, g = m.fit(True)
+            assert info == 0
+            used, resid = m.engine_report()
+            mu, var = m.predict(Xs, include_likelihood=False)
+            out[engine] = dict(logL=abs(logL - lo) / abs(lo), g=np.abs(g - go).max() / np.abs(go).max(),
+                               mu=np.abs(mu - mu_o).max() / np.abs(mu_o).max(), var=np.abs(var - var_o).max() / v, used=used, resid=resid)
+            m.close()
+        finally:
+            native.set_ozaki(0)
+    assert out["dmma"]["used"] is False and out["dmma"]["resid"] == -1.0
+    e, f = out["int8"], out["dmma"]
+    assert e["used"] is False or (0.0 <= e["resid"] <= 2e-13)              # either checked and passed, or fell back
+    floor = cond * 2.2e-16                                                   # what two LAPACK builds differ by
+    for key in ("logL", "g", "mu", "var"):
+        assert e[key] <= max(10.0 * f[key], floor), (key, e, f, cond)
+
+
+def test_ozaki_residual_check_falls_back_to_the_fp64_engine():
+    """10 moduli carry ~34 bits per operand: far too few.  The residual check after the solve must notice, the evaluation must be
+    repeated on the DMMA engine (bit-identical to a fit that never saw the engine), and later predictions must stay there."""
+    rs = np.random.RandomState(3)
+    n, d = 900, 4
+    X = rs.uniform(0, 1, (n, d))
+    Y = np.sin(X.sum(1))[:, None] + 0.05 * rs.randn(n, 1)
+    ls = np.array([0.5, 0.6, 0.7, 0.8])
+    Xc = rs.uniform(0, 1, (1500, d))
+
+    def run():
+        m = native.NativeModel("mat52", True, d, 1, n_cap=n, cand_block=1536)
+        m.set_data(X, Y)
+        m.set_theta(1.2, ls, 1e-3)
+        info, logL, g = m.fit(True)
+        assert info == 0
+        f = m.acquisition("EI", 0.01, m.fmin(), Xc, with_gradients=True)
+        rep = m.engine_report()
+        m.close()
+        return logL, g, f["f"], f["df"], rep
+
+    base = run()
+    before = native.ozaki_fallback_count()
+    native.set_ozaki(256, 10)
+    try:
+        weak = run()
+    finally:
+        native.set_ozaki(0)
+    assert native.ozaki_fallback_count() == before + 1
+    assert weak[4][0] is False and weak[4][1] > 2e-13                        # engine not in the final posterior; the residual that failed
+    assert weak[0] == base[0] and np.array_equal(weak[1], base[1])
+    assert np.array_equal(weak[2], base[2]) and np.array_equal(weak[3], base[3])
+    # and a healthy setting passes the check without falling back
+    native.set_ozaki(256, 18)
+    try:
+        good = run()
+    finally:
+        native.set_ozaki(0)
+    assert native.ozaki_fallback_count() == before + 1
+    assert good[4][0] is True and 0.0 <= good[4][1] <= 2e-13
+    assert_allclose(good[0], base[0], rtol=1e-12)
