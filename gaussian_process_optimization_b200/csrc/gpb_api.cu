@@ -955,11 +955,11 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   }
   // A handful of candidates (the M = 1 .. 8 calls of the L-BFGS-B refinements, optimizer.py:46-51, coalesced by the host's
   // LockstepEvaluator): everything from the covariance row to the four reductions in ONE persistent cooperative kernel
-  // (gpb_skinny.cu) -- two streaming passes over the triangle of M.  Kx lives in the first 8 rows of KxT, Dk and Z in the first 16 of Vt.
+  // (gpb_skinny.cu) -- two streaming passes over the triangle of M.  Kx and U live in the first 16 rows of KxT, Dk and Z in the first 16 of Vt.
   static const int fused_on = env_int("GPB_SKINNY_FUSED", 1);
   if (mcb <= 8 && p == 1 && !m->gower && fused_on && level >= 1)
     return launch_skinny_fused(m->kind, m->f.Mi, np, n, d, mcb, level, m->XsT, m->Xc, m->ls_dev, m->inv_ls_dev, m->alpha, m->variance,
-                               m->variance + (include_likelihood ? m->noise : 0.0), m->KxT, m->Vt, m->Vt + (size_t)8 * np, m->f.part, m->sk_part3,
+                               m->variance + (include_likelihood ? m->noise : 0.0), m->KxT, m->Vt, m->Vt + (size_t)8 * np, m->KxT + (size_t)8 * np, m->f.part, m->sk_part3,
                                m->mu, m->var, m->dmu, m->dvar, s);
   GPB_TRY(launch_scale_transpose(m->Xc, mcb, d, m->ls_dev, m->XcT, cpad, s));
   // KxT[c][n] = k(x*_c, x_n)                                        posterior.py:275 (stored transposed)

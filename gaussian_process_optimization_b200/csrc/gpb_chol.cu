@@ -937,9 +937,12 @@ static int cholinv(Factor &f, int off, int n, int depth, int split = 0) {
   double *S21 = f.W + (size_t)(off + h) * ld + off;   // r x h: L21
   double *T12 = f.W + (size_t)off * ld + off + h;     // h x r: T21^T
   // n >= ozaki_min_n(): the four products of this level run on the int8 tensor cores (gpb_ozaki.cu; experimental, off by default).
-  // They share one digit workspace per stream, so such a level does not fork its T12 product.
+  // The engine keeps one plane workspace per (device, stream), so the T12 product of such a level can fork to the side stream like
+  // the DMMA one: its residue extraction, MMAs and reconstruction then run underneath A22 -= L21 L21^T and the recursion into A22
+  // (GPB_OZAKI_FORK=0 restores the serial order of round 1).
   const bool oz = split == 0 && ozaki_min_n() > 0 && n >= ozaki_min_n();   // (an append keeps the DMMA engine: r is small)
-  const bool fork = !oz && f.ov != nullptr && depth < FactorOverlap::MAX_DEPTH && n >= f.ov->min_n;
+  static const bool oz_fork = [] { const char *e = getenv("GPB_OZAKI_FORK"); return !e || atoi(e) != 0; }();
+  const bool fork = (!oz || oz_fork) && f.ov != nullptr && depth < FactorOverlap::MAX_DEPTH && n >= f.ov->min_n;
   GemmArgs g;
   // L21 = A21 * M11^T      (M11 lower: k <= column tile)
   g = GemmArgs{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 0, 2};

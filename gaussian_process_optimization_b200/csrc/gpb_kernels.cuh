@@ -55,8 +55,8 @@ size_t skinny_fused_part12_doubles(int np);
 size_t skinny_fused_part3_doubles(int d);
 int launch_skinny_fused(int kind, const double *M, int np, int n, int d, int mc, int level, const double *XT, const double *Xc,
                         const double *ls, const double *inv_ls, const double *alpha, double variance, double var_base, double *Kx,
-                        double *Dk, double *Z, double *part12, double *part3, double *mu, double *var, double *dmu, double *dvar,
-                        cudaStream_t s);
+                        double *Dk, double *Z, double *U, double *part12, double *part3, double *mu, double *var, double *dmu,
+                        double *dvar, cudaStream_t s);
 // GPModel.predict clip + get_quantiles + EI/LCB (+ gradients) + AcquisitionBase sign
 int launch_acq_epilogue(int acq, double par, double fmin, int n_c, int d, const double *mu, const double *var, const double *dmu,
                         const double *dvar, double *f, double *df, double *mean_out, double *sd_out, double *dmdx_out,
