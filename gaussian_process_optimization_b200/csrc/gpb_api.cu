@@ -476,6 +476,12 @@ int gpb_model_destroy(gpb_model *m) {
   cudaStreamSynchronize(m->stream);
   for (auto &g : m->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
+  // the int8 engine keeps a plane workspace per stream it was launched on: this model's streams are about to disappear
+  if (m->own_stream) ozaki_release_stream(m->stream);
+  if (m->ov) {
+    ozaki_release_stream(m->ov->main);
+    for (int d = 0; d < FactorOverlap::MAX_DEPTH; ++d) ozaki_release_stream(m->ov->side[d]);
+  }
   factor_overlap_destroy(m->ov);
   if (m->entry_ev) cudaEventDestroy(m->entry_ev);
   if (m->exit_ev) cudaEventDestroy(m->exit_ev);

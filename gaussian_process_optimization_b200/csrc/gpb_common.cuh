@@ -242,6 +242,7 @@ int ozaki_gemm_launch(int layout_a, int layout_b, const GemmArgs &g, int tri_a, 
 void ozaki_invalidate();                     // a factorisation ran: cached digit planes of L^-1 are stale
 int ozaki_min_n();                           // products of the recursion with n >= this go through the engine (0 = off)
 int ozaki_configure(int min_n, int slices);
+void ozaki_release_stream(cudaStream_t st);   // the stream is about to be destroyed: free the engine's plane workspace keyed by it
 void ozaki_suppress(int on);                 // thread-local: 1 = the calling thread's products stay on the DMMA engine until ozaki_suppress(0)
 int ozaki_predict_planes();                 // planes of the predictive products: 8 digits, or 18 moduli in modular mode
 int ozaki_crt_bits(int nmod, long long k);   // modular mode (gpb_crt.cuh): bits per operand; host restatements for the CPU tests

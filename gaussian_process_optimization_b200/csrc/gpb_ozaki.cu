@@ -696,6 +696,15 @@ static Workspace *workspace_for(int dev, cudaStream_t st) {
   return g_slots.back().ws;
 }
 
+// The stream is being destroyed (its model is): give the planes back.  Without this every model that ever used the engine left
+// several GB behind, keyed by a stream handle that no longer exists (20 models at N = 16384 exhausted the 180 GB, r2f).
+static void release_workspace(Workspace *w) {
+  for (void *q : {(void *)w->dA, (void *)w->dB, (void *)w->ra, (void *)w->rb, (void *)w->amax, w->T, (void *)w->cache[0].dig,
+                  (void *)w->cache[0].scale, (void *)w->cache[1].dig, (void *)w->cache[1].scale})
+    if (q) cudaFree(q);
+  delete w;
+}
+
 static int ensure(void **p, size_t *cap, size_t need) {
   if (*cap >= need) return 0;
   if (*p) GPB_CUDA(cudaFree(*p));
@@ -711,6 +720,19 @@ static int g_min_n = -1;   // -1: read GPB_OZAKI_MIN_N once; 0: off
 static bool valid_planes(int s) { return (s >= 1 && s <= MAX_S) || (s >= crt::MINMOD && s <= crt::MAXMOD); }
 
 }  // namespace oz
+
+void ozaki_release_stream(cudaStream_t st) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lock(oz::g_ws_mutex);
+  for (size_t i = 0; i < oz::g_slots.size(); ++i) {
+    if (oz::g_slots[i].dev == dev && oz::g_slots[i].st == st) {
+      oz::release_workspace(oz::g_slots[i].ws);
+      oz::g_slots.erase(oz::g_slots.begin() + i);
+      return;
+    }
+  }
+}
 
 static thread_local int t_suppress = 0;   // > 0: this host thread's calls stay on the fp64 DMMA engine (fallback after a failed residual check)
 void ozaki_suppress(int on) { t_suppress += on ? 1 : -1; }

@@ -15,6 +15,19 @@ Mirrors (paths relative to /root/reference/GPyOpt/GPyOpt):
   core/evaluators/batch_local_penalization.py:9-70        LocalPenalization, estimate_L
   core/bo.py:20-260, methods/bayesian_optimization.py:76-202   BO, BayesianOptimization
 Host logic only (bookkeeping, RNG order, L-BFGS-B through SciPy like the reference); every GP quantity comes from the device.
+
+ATTRIBUTION.  This file is a host-side mirror of GPyOpt 1.2.5's control plane, kept only so that the BO-trajectory parity tests
+(BASELINE config 1) can run on a GPU box where /root/reference does not exist.  Class / method names, signatures, attribute names
+and -- for the bookkeeping classes (DuplicateManager, RandomDesign, Design_space, normalize, BO.run_optimization,
+BayesianOptimization.__init__ and its choosers) -- the statement order of the bodies follow GPyOpt closely, because the NumPy RNG
+consumption order and the stopping rules are part of the trajectory being compared.  GPyOpt is
+    Copyright (c) 2015, the GPyOpt authors.  All rights reserved.  Licensed under the BSD 3-clause license
+    (GPyOpt/LICENSE.txt in the reference tree: redistribution in source and binary forms, with or without modification, is
+    permitted provided that the copyright notice, the list of conditions and the disclaimer are retained; the names of the authors
+    may not be used to endorse derived products; the software is provided "as is", without warranty of any kind).
+It is NOT part of the B200 hot path and earns no credit as such (SURVEY.md section 2 marks the control plane out of scope); the product
+is the C ABI underneath (include/gpb200.h).  What is original here: LockstepEvaluator / the lock-step anchor refinement, the
+sharded / distributed variants, and the device-backed GPModel / acquisition plumbing.
 """
 import time
 
