@@ -980,7 +980,7 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   // the triangle of M per product instead of a 128-row padded GEMM, and the row reductions (mean, variance, both input
   // gradients) split over the training points in one fused pass (launch_skinny_moments) instead of one warp per candidate.
   const bool skinny = mcb <= 8;
-  if (skinny && p == 1) {
+  if (skinny && p == 1 && d <= 32) {      // (round-1 route: Gower kernel, GPB_SKINNY_FUSED=0; wider inputs take the generic kernels below)
     const double var_base = m->variance + (include_likelihood ? m->noise : 0.0);
     const double *Vt = nullptr, *Ut = nullptr;
     if (level == 1 || level == 2) {

@@ -497,6 +497,78 @@ __global__ void __launch_bounds__(256) gradx_kernel(const double *__restrict__ X
   }
 }
 
+// 32 < d <= 64: the register version above would need 4 x 64 doubles per lane (the DCAP = 64 instantiation spilled 9 KB per thread).
+// Here the candidate's coordinates sit in shared memory (read by broadcast), the squared distance is formed over all dimensions
+// first, and the gradient sums are accumulated for 32 dimensions at a time in two sweeps over the training points.
+template <int KIND, int TWO>
+__global__ void __launch_bounds__(256) gradx_wide_kernel(const double *__restrict__ XcT, int ldc, int n_c, const double *__restrict__ XT,
+                                                         int ldx, int n, int d, double variance, const double *__restrict__ inv_ls,
+                                                         const double *__restrict__ G1, int ldg1, double s1, int add_t,
+                                                         const double *__restrict__ G2, int ldg2, double s2,
+                                                         double *__restrict__ out1, double *__restrict__ out2, int ldo) {
+  __shared__ double xcs[8][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp;
+  if (c < n_c)
+    for (int q = lane; q < 64; q += 32) xcs[warp][q] = (q < d) ? XcT[(size_t)q * ldc + c] : 0.0;
+  __syncwarp();
+  if (c >= n_c) return;
+  const double *xc = xcs[warp];
+  for (int q0 = 0; q0 < d; q0 += 32) {
+    double a1[32], a2[TWO ? 32 : 1];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      a1[q] = 0.0;
+      if (TWO) a2[q] = 0.0;
+    }
+    for (int j = lane; j < n; j += 32) {
+      double r2 = 0.0;
+      for (int q = 0; q < d; ++q) {
+        const double df = xc[q] - XT[(size_t)q * ldx + j];
+        r2 = fma(df, df, r2);
+      }
+      double k, dk;
+      cov_k_dk<KIND>(r2, variance, k, dk);
+      double g1 = G1[(size_t)c * ldg1 + j];
+      if (add_t) g1 += G1[(size_t)j * ldg1 + c];
+      const double w1 = dk * g1;
+      double w2 = 0.0;
+      if (TWO) w2 = dk * G2[(size_t)c * ldg2 + j];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const double df = (q0 + q < d) ? xc[q0 + q] - XT[(size_t)(q0 + q) * ldx + j] : 0.0;
+        a1[q] = fma(w1, df, a1[q]);
+        if (TWO) a2[q] = fma(w2, df, a2[q]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      if (q0 + q < d) {
+        const double v1 = warp_sum(a1[q]);
+        if (lane == 0) out1[(size_t)c * ldo + q0 + q] = s1 * inv_ls[q0 + q] * v1;
+        if (TWO) {
+          const double v2 = warp_sum(a2[q]);
+          if (lane == 0) out2[(size_t)c * ldo + q0 + q] = s2 * inv_ls[q0 + q] * v2;
+        }
+      }
+    }
+  }
+}
+
+template <int KIND>
+static int launch_gradx_wide(const double *XcT, int ldc, int n_c, const double *XT, int ldx, int n, int d, double variance,
+                             const double *inv_ls, const double *G1, int ldg1, double s1, int add_t, const double *G2, int ldg2,
+                             double s2, double *out1, double *out2, int ldo, cudaStream_t s) {
+  const int blocks = (n_c + 7) / 8;
+  if (G2)
+    gradx_wide_kernel<KIND, 1><<<blocks, 256, 0, s>>>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, G2, ldg2, s2, out1, out2, ldo);
+  else
+    gradx_wide_kernel<KIND, 0><<<blocks, 256, 0, s>>>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, nullptr, 0, 0.0, out1, nullptr, ldo);
+  count_launch();
+  GPB_CHECK_LAUNCH();
+  return 0;
+}
+
 template <int KIND, int DCAP>
 static int launch_gradx_t(const double *XcT, int ldc, int n_c, const double *XT, int ldx, int n, int d, double variance,
                           const double *inv_ls, const double *G1, int ldg1, double s1, int add_t, const double *G2, int ldg2,
@@ -522,13 +594,13 @@ int launch_gradx(int kind, const double *XcT, int ldc, int n_c, const double *XT
     if (d <= 8) GPB_GX(GPB_KERN_RBF, 8);
     if (d <= 16) GPB_GX(GPB_KERN_RBF, 16);
     if (d <= 32) GPB_GX(GPB_KERN_RBF, 32);
-    GPB_GX(GPB_KERN_RBF, 64);
+    return launch_gradx_wide<GPB_KERN_RBF>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, G2, ldg2, s2, out1, out2, ldo, s);
   } else {
     if (d <= 4) GPB_GX(GPB_KERN_MATERN52, 4);
     if (d <= 8) GPB_GX(GPB_KERN_MATERN52, 8);
     if (d <= 16) GPB_GX(GPB_KERN_MATERN52, 16);
     if (d <= 32) GPB_GX(GPB_KERN_MATERN52, 32);
-    GPB_GX(GPB_KERN_MATERN52, 64);
+    return launch_gradx_wide<GPB_KERN_MATERN52>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, G2, ldg2, s2, out1, out2, ldo, s);
   }
 #undef GPB_GX
 }

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) skinny_moments_reduce_kernel(const double
 }
 
 size_t skinny_moments_part_doubles(int n_c, int np, int d) {
-  const int dcap = d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : 64;
+  const int dcap = d <= 4 ? 4 : d <= 8 ? 8 : d <= 16 ? 16 : 32;
   return (size_t)n_c * (np / SKM_THREADS) * (2 + 2 * dcap);
 }
 
@@ -177,7 +177,7 @@ int launch_skinny_moments(int kind, const double *KxT, const double *Vt, const d
                           double var_base, int want_g, double *part, double *mu, double *var, double *dmu, double *dvar,
                           cudaStream_t s) {
   if (n_c == 0) return 0;
-  GPB_REQUIRE(d <= 64, "gradients_X: input dimension %d > 64 not supported", d);
+  GPB_REQUIRE(d <= 32, "skinny moments: input dimension %d > 32 takes the generic kernels (predict_block)", d);
 #define GPB_SKM(K_, D_)                                                                                                          \
   return launch_skinny_moments_t<K_, D_>(KxT, Vt, Ut, ld, n_c, n, alpha, XcT, ldc, XT, ldx, d, variance, inv_ls, var_base, want_g, \
                                          part, mu, var, want_g ? dmu : nullptr, (want_g && Ut) ? dvar : nullptr, s)
@@ -185,14 +185,12 @@ int launch_skinny_moments(int kind, const double *KxT, const double *Vt, const d
     if (d <= 4) GPB_SKM(GPB_KERN_RBF, 4);
     if (d <= 8) GPB_SKM(GPB_KERN_RBF, 8);
     if (d <= 16) GPB_SKM(GPB_KERN_RBF, 16);
-    if (d <= 32) GPB_SKM(GPB_KERN_RBF, 32);
-    GPB_SKM(GPB_KERN_RBF, 64);
+    GPB_SKM(GPB_KERN_RBF, 32);
   } else {
     if (d <= 4) GPB_SKM(GPB_KERN_MATERN52, 4);
     if (d <= 8) GPB_SKM(GPB_KERN_MATERN52, 8);
     if (d <= 16) GPB_SKM(GPB_KERN_MATERN52, 16);
-    if (d <= 32) GPB_SKM(GPB_KERN_MATERN52, 32);
-    GPB_SKM(GPB_KERN_MATERN52, 64);
+    GPB_SKM(GPB_KERN_MATERN52, 32);
   }
 #undef GPB_SKM
 }

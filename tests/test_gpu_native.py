@@ -502,3 +502,35 @@ def test_edge_sizes_one_point_empty_candidates_two_outputs():
             assert_allclose(mu, mu_r, rtol=1e-9, atol=1e-11)
             assert_allclose(var, var_r, rtol=1e-9, atol=1e-12)
         m.close()
+
+
+@pytest.mark.parametrize("kind", ["rbf", "mat52"])
+def test_wide_inputs_d48_block_and_skinny_routes_match_the_oracle(kind):
+    """32 < D <= 64: the gradient kernels take their two-sweep form (no register spills); fit, M = 3 and M = 200 acquisition calls."""
+    rs = np.random.RandomState(48)
+    n, d = 300, 48
+    X = rs.uniform(0, 1, (n, d))
+    Y = np.sin(X[:, :5].sum(1))[:, None] + 0.05 * rs.randn(n, 1)
+    Y = (Y - Y.mean()) / Y.std()
+    ls = 1.5 + 0.02 * np.arange(d)
+    m = native.NativeModel(kind, True, d, 1, n_cap=n, cand_block=256)
+    m.set_data(X, Y)
+    m.set_theta(1.2, ls, 1e-2)
+    info, logL, g = m.fit(True)
+    assert info == 0
+    l_ref, g_ref, _ = O.log_likelihood_and_gradients(kind, X, Y, 1.2, ls, 1e-2)
+    assert_allclose(logL, l_ref, rtol=1e-9)
+    assert_allclose(g, g_ref, rtol=1e-7, atol=1e-9 * np.abs(g_ref).max())
+    st = O.GPState(kind, X, Y, 1.2, ls, 1e-2)
+    fmin = m.fmin()
+    for mc in (3, 200):
+        Xc = rs.uniform(0, 1, (mc, d))
+        r = m.acquisition("EI", 0.01, fmin, Xc, with_gradients=True)
+        f_ref, df_ref = st.acquisition("EI", Xc, with_gradients=True)
+        assert_allclose(r["f"], f_ref, rtol=1e-7, atol=1e-12)
+        assert_allclose(r["df"], df_ref, rtol=1e-6, atol=1e-9 * np.abs(df_ref).max())
+    G = rs.randn(40, n)
+    gx = native.kern_gradients_X(kind, G, X[:40] + 0.01, X, 1.2, ls)
+    gx_ref = O.gradients_X(kind, G, X[:40] + 0.01, X, 1.2, ls)
+    assert_allclose(gx, gx_ref, rtol=1e-7, atol=1e-9 * np.abs(gx_ref).max())
+    m.close()
