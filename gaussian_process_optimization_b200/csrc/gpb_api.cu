@@ -243,6 +243,16 @@ struct gpb_model {
   double *topv = nullptr;
   long long *topi = nullptr;
   double *sk_part3 = nullptr;   // per-CTA sums + arrival counter of the fused M <= 8 call (gpb_skinny.cu)
+  // Second lane of candidate-block buffers + stream (allocated on the first multi-block device-resident scoring pass): block b + 1 runs
+  // its covariance rows, residue extraction / small kernels underneath block b's GEMMs instead of behind them
+  struct Lane {
+    double *Xc, *XcT, *XcgT, *KxT, *Vt, *Ut, *mu, *var, *dmu, *dvar, *fbuf, *dfbuf, *sdbuf, *dsbuf;
+    cudaStream_t stream;
+  };
+  void *lane_mem = nullptr;
+  Lane lane1 = {};
+  cudaStream_t lane_stream = nullptr;
+  cudaEvent_t lane_ev[3] = {nullptr, nullptr, nullptr};   // [0] entry hand-over, [1] top-k chain, [2] lane-1 completion
   // int8 engine (experimental): every fit that used it is followed by a residual check of the solve; a failed check refits on the
   // fp64 DMMA engine, and the predictive products of that posterior stay there as well
   bool engine_used = false, engine_ok = true;
@@ -483,6 +493,14 @@ int gpb_model_destroy(gpb_model *m) {
     for (int d = 0; d < FactorOverlap::MAX_DEPTH; ++d) ozaki_release_stream(m->ov->side[d]);
   }
   factor_overlap_destroy(m->ov);
+  if (m->lane_stream) {
+    ozaki_release_stream(m->lane_stream);
+    cudaStreamSynchronize(m->lane_stream);
+    cudaStreamDestroy(m->lane_stream);
+  }
+  for (auto &e : m->lane_ev)
+    if (e) cudaEventDestroy(e);
+  if (m->lane_mem) cudaFree(m->lane_mem);
   if (m->entry_ev) cudaEventDestroy(m->entry_ev);
   if (m->exit_ev) cudaEventDestroy(m->exit_ev);
   if (m->own_stream) cudaStreamDestroy(m->stream);
@@ -1232,25 +1250,83 @@ int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int
   return 0;
 }
 
+// ---- two-lane block pipeline of the scoring pass --------------------------------------------------------------------------------
+static gpb_model::Lane lane_of(const gpb_model *m) {
+  return {m->Xc, m->XcT, m->XcgT, m->KxT, m->Vt, m->Ut, m->mu, m->var, m->dmu, m->dvar, m->fbuf, m->dfbuf, m->sdbuf, m->dsbuf, m->stream};
+}
+static void lane_activate(gpb_model *m, const gpb_model::Lane &l) {
+  m->Xc = l.Xc; m->XcT = l.XcT; m->XcgT = l.XcgT; m->KxT = l.KxT; m->Vt = l.Vt; m->Ut = l.Ut; m->mu = l.mu; m->var = l.var;
+  m->dmu = l.dmu; m->dvar = l.dvar; m->fbuf = l.fbuf; m->dfbuf = l.dfbuf; m->sdbuf = l.sdbuf; m->dsbuf = l.dsbuf; m->stream = l.stream;
+}
+static int lane_ensure(gpb_model *m) {
+  if (m->lane_mem) return 0;
+  const size_t cb = m->cb, d = m->d, np = m->np_cap, p = m->p;
+  const size_t counts[14] = {cb * d, cb * d, cb * d, cb * np, cb * np, cb * np, cb * p, cb, cb * d, cb * d, cb, cb * d, cb, cb * d};
+  size_t total = 0;
+  for (size_t c : counts) total += align256(c * sizeof(double));
+  GPB_CUDA(cudaMalloc(&m->lane_mem, total));
+  char *base = reinterpret_cast<char *>(m->lane_mem);
+  double **dst[14] = {&m->lane1.Xc, &m->lane1.XcT, &m->lane1.XcgT, &m->lane1.KxT, &m->lane1.Vt, &m->lane1.Ut, &m->lane1.mu, &m->lane1.var,
+                      &m->lane1.dmu, &m->lane1.dvar, &m->lane1.fbuf, &m->lane1.dfbuf, &m->lane1.sdbuf, &m->lane1.dsbuf};
+  size_t off = 0;
+  for (int i = 0; i < 14; ++i) {
+    *dst[i] = reinterpret_cast<double *>(base + off);
+    off += align256(counts[i] * sizeof(double));
+  }
+  GPB_CUDA(cudaStreamCreateWithFlags(&m->lane_stream, cudaStreamNonBlocking));
+  for (auto &e : m->lane_ev) GPB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  m->lane1.stream = m->lane_stream;
+  return 0;
+}
+
 // One scoring pass with a running top-k on the device.  The k result rows [value, global index, coordinates] are left in
 // out_rows_dev (device, k x (d + 2); needs device-resident candidates) when it is given.  No synchronisation at the end.
 static int acq_topk_pass(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k, long long index_offset,
                          double *f, double *df, double *out_rows_dev) {
   const int d = m->d;
   const bool grad = df != nullptr;
-  cudaStream_t s = m->stream;
-  GPB_TRY(launch_topk_init(m->topv, m->topi, k, s));
-  for (int c0 = 0; c0 < mc; c0 += m->cb) {
-    const int mcb = std::min(m->cb, mc - c0);
-    GPB_TRY(predict_block(m, Xc + (size_t)c0 * d, mcb, dev, grad ? 2 : 1, 1));
-    GPB_TRY(launch_acq_epilogue(acq, par, fmin, mcb, d, m->mu, m->var, grad ? m->dmu : nullptr, grad ? m->dvar : nullptr, m->fbuf,
-                                grad ? m->dfbuf : nullptr, nullptr, nullptr, nullptr, nullptr, s));
-    GPB_TRY(launch_topk_update(m->fbuf, mcb, index_offset + c0, m->topv, m->topi, k, s));
-    GPB_TRY(copy_out(f ? f + c0 : nullptr, m->fbuf, mcb, dev, s));
-    if (grad) GPB_TRY(copy_out(df + (size_t)c0 * d, m->dfbuf, (size_t)mcb * d, dev, s));
-    if (!dev) GPB_CUDA(cudaStreamSynchronize(s));  // the host block may be reused by the caller's next copy
+  cudaStream_t s0 = m->stream;
+  GPB_TRY(launch_topk_init(m->topv, m->topi, k, s0));
+  // Device-resident candidates in several blocks: the blocks alternate between two lanes (buffer sets + streams).  Within a lane the
+  // stream orders the reuse of its buffers; across lanes only the running top-k is shared, so its updates are chained by an event.
+  static const int two_lanes_on = env_int("GPB_ACQ_LANES", 2) >= 2;
+  const bool two = two_lanes_on && dev && mc > m->cb && !m->gower;
+  const gpb_model::Lane lane0 = lane_of(m);
+  if (two) {
+    GPB_TRY(lane_ensure(m));
+    GPB_CUDA(cudaEventRecord(m->lane_ev[0], s0));                 // lane 1 starts behind everything queued so far (the fit, top-k init)
+    GPB_CUDA(cudaStreamWaitEvent(m->lane_stream, m->lane_ev[0], 0));
   }
-  if (out_rows_dev) GPB_TRY(launch_topk_pack(m->topv, m->topi, Xc, d, k, index_offset, out_rows_dev, s));
+  int rc = 0, blk = 0;
+  bool chain = false;
+  for (int c0 = 0; c0 < mc && rc == 0; c0 += m->cb, ++blk) {
+    const int mcb = std::min(m->cb, mc - c0);
+    if (two) lane_activate(m, (blk & 1) ? m->lane1 : lane0);
+    cudaStream_t s = m->stream;
+    rc = predict_block(m, Xc + (size_t)c0 * d, mcb, dev, grad ? 2 : 1, 1);
+    if (rc == 0)
+      rc = launch_acq_epilogue(acq, par, fmin, mcb, d, m->mu, m->var, grad ? m->dmu : nullptr, grad ? m->dvar : nullptr, m->fbuf,
+                               grad ? m->dfbuf : nullptr, nullptr, nullptr, nullptr, nullptr, s);
+    if (rc == 0 && two && chain && cudaStreamWaitEvent(s, m->lane_ev[1], 0) != cudaSuccess) rc = -1;   // the previous block's top-k update
+    if (rc == 0) rc = launch_topk_update(m->fbuf, mcb, index_offset + c0, m->topv, m->topi, k, s);
+    if (rc == 0 && two) {
+      if (cudaEventRecord(m->lane_ev[1], s) != cudaSuccess) rc = -1;
+      chain = true;
+    }
+    if (rc == 0) rc = copy_out(f ? f + c0 : nullptr, m->fbuf, mcb, dev, s);
+    if (rc == 0 && grad) rc = copy_out(df + (size_t)c0 * d, m->dfbuf, (size_t)mcb * d, dev, s);
+    if (rc == 0 && !dev && cudaStreamSynchronize(s) != cudaSuccess) rc = -1;  // the host block may be reused by the caller's next copy
+  }
+  if (two) {
+    lane_activate(m, lane0);
+    // join: the model's stream continues behind lane 1 (and behind the last top-k update, wherever it ran)
+    if (cudaEventRecord(m->lane_ev[2], m->lane_stream) != cudaSuccess || cudaStreamWaitEvent(s0, m->lane_ev[2], 0) != cudaSuccess) rc = rc ? rc : -1;
+  }
+  if (rc != 0) {
+    if (rc == -1 && gpb_last_error()[0] == 0) set_error("acq_topk: CUDA error in the block pipeline");
+    return rc;
+  }
+  if (out_rows_dev) GPB_TRY(launch_topk_pack(m->topv, m->topi, Xc, d, k, index_offset, out_rows_dev, s0));
   return 0;
 }
 

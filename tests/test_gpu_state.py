@@ -200,3 +200,35 @@ def test_bo_anchor_refinement_in_lockstep_equals_the_sequential_loop():
     assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
     assert out[True][3] is not None and out[True][3]["device_calls"] < out[True][3]["requests"]
     assert out[True][2] < out[False][2]                   # fewer kernels launched for the same answer
+
+
+@pytest.mark.parametrize("engine", [0, 18])
+def test_two_lane_block_pipeline_equals_the_single_lane_pass(engine):
+    """Device-resident candidates in several blocks alternate between two buffer sets / streams (block b + 1's covariance rows and small
+    kernels run underneath block b's GEMMs); values, gradients and anchors must be bit-identical to the host-buffer pass, which walks the
+    blocks one after the other on one stream.  Also with the int8 engine on (its plane workspaces are per stream)."""
+    import torch
+    n, d = 1500, 6
+    X, Y = _data(n, d, seed=21)
+    native.set_ozaki(256 if engine else 0, engine if engine else 8)
+    try:
+        nm = native.NativeModel("mat52", True, d, 1, n_cap=n, cand_block=1024)
+        nm.set_data(X, Y)
+        nm.set_theta(1.2, 0.4 + 0.05 * np.arange(d), 1e-3)
+        assert nm.fit(False)[0] == 0
+        fmin = nm.fmin()
+        Xc = np.random.RandomState(9).uniform(0, 1, (1024 * 4 + 300, d))          # five blocks, the last one ragged
+        v0, i0, p0, f0, df0 = nm.acq_topk_full("EI", 0.01, fmin, Xc, 5)            # host buffers: one lane
+        Xd = torch.from_numpy(Xc).cuda()
+        for rep in range(2):
+            v1, i1, p1, f1, df1 = nm.acq_topk_full("EI", 0.01, fmin, Xd, 5)        # device buffers: two lanes
+            assert np.array_equal(i0, i1) and np.array_equal(v0, v1) and np.array_equal(p0, p1)
+            assert np.array_equal(f0, f1.cpu().numpy()) and np.array_equal(df0, df1.cpu().numpy())
+            rows, f2, df2 = nm.acq_topk_dev("EI", 0.01, fmin, Xd, 5, with_gradients=True)
+            torch.cuda.synchronize()
+            r = rows.cpu().numpy()
+            assert np.array_equal(r[:, 0], v0) and np.array_equal(r[:, 1], i0.astype(float)) and np.array_equal(r[:, 2:], p0)
+            assert np.array_equal(f2.cpu().numpy(), f0) and np.array_equal(df2.cpu().numpy(), df0)
+        nm.close()
+    finally:
+        native.set_ozaki(0)
