@@ -892,7 +892,7 @@ class AcquisitionOptimizer(object):
         run = lambda a: apply_optimizer(self.optimizer, a, f=f, df=None, f_df=f_df, duplicate_manager=duplicate_manager,  # noqa: E731
                                         space=self.space)
         if world > 1:
-            optimized_points = self._optimize_anchors_distributed(anchor_points, run, world, rank)
+            optimized_points = self._optimize_anchors_distributed(anchor_points, run, world, rank, f, f_df, duplicate_manager)
         elif self._lockstep_ok(f_df, anchor_points):
             optimized_points = self._optimize_anchors_lockstep(anchor_points, f, f_df, duplicate_manager)
         else:
@@ -963,14 +963,19 @@ class AcquisitionOptimizer(object):
             return 1, 0
         return dist.get_world_size(), dist.get_rank()
 
-    def _optimize_anchors_distributed(self, anchor_points, run, world, rank):
+    def _optimize_anchors_distributed(self, anchor_points, run, world, rank, f=None, f_df=None, duplicate_manager=None):
         import torch
         import torch.distributed as dist
         anchor_points = np.atleast_2d(anchor_points)
         na, d = anchor_points.shape
         table = np.full((na, 1 + d), np.inf)
-        for i in range(rank, na, world):
-            x, fx = run(anchor_points[i])
+        mine = list(range(rank, na, world))
+        if len(mine) > 1 and self._lockstep_ok(f_df, anchor_points[mine]):
+            # fewer ranks than anchors: this rank's anchors advance in lock step (one coalesced device call per joint step)
+            results = self._optimize_anchors_lockstep(anchor_points[mine], f, f_df, duplicate_manager)
+        else:
+            results = [run(anchor_points[i]) for i in mine]
+        for i, (x, fx) in zip(mine, results):
             table[i, 0], table[i, 1:] = float(np.asarray(fx).ravel()[0]), np.asarray(x).ravel()
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
         t = torch.from_numpy(table).to(dev)
