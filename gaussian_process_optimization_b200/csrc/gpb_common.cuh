@@ -229,6 +229,7 @@ struct GemmArgs {
   int tri_out;   // 1: only tiles with tile_col <= tile_row are computed
   int klo_mode;  // 0: 0       1: row0        2: col0
   int khi_mode;  // 0: K       1: row0 + 128  2: col0 + 128
+  int band = 0;  // tri_out: block rows per band of the tile enumeration (0 = default 12; GPB_TRI_BAND)
 };
 int gemm_launch(int layout_a, int layout_b, const GemmArgs &g, cudaStream_t s);
 int gemm_profile_enable(int on);

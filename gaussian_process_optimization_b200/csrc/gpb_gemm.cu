@@ -111,7 +111,10 @@ __global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MIN_BLOCKS) gemm_dmma_k
     // klo_mode 1 (k >= row block).
     constexpr int R = 128 / BM, CW = 128 / BN;
     constexpr int per = R * CW;   // tiles of one 128x128 block
-    constexpr int G = 12;         // 144 blocks per square ~ one wave of resident CTAs
+    // 6 x 6 squares: the resident CTAs then share 12 operand panels per square and DRAM reads of Ky^-1 = M^T M at N = 16384 are
+    // 16.2 GB (3.2 GB of operands); 12 x 12 squares, one wave of CTAs per square, read 34.0 GB, whole block rows 74 GB
+    // (profiles/r2m_traffic_band.json).  Same duration either way: the kernel is tensor-pipe bound.
+    const int G = p.band > 0 ? p.band : 6;
     const int nb = p.M / 128;
     const int q = t / per, w_in = t - q * per;
     int i = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);   // block row of q in row-major triangular order
@@ -388,7 +391,10 @@ static int launch_cfg(const GemmArgs &g, cudaStream_t s) {
   return launch_t<LA, LB, 32, 32, 2, 2, 4, 16, 3>(g, s);
 }
 
-int gemm_launch(int la, int lb, const GemmArgs &g, cudaStream_t s) {
+int gemm_launch(int la, int lb, const GemmArgs &g_in, cudaStream_t s) {
+  static const int band_env = [] { const char *e = getenv("GPB_TRI_BAND"); return e ? atoi(e) : 0; }();
+  GemmArgs g = g_in;
+  if (g.band == 0) g.band = band_env;
   GPB_REQUIRE(g.M % 128 == 0 && g.N % 128 == 0 && g.K % BK_MIN == 0, "gemm: M,N must be multiples of 128 and K of 16 (got %d %d %d)",
               g.M, g.N, g.K);
   GPB_REQUIRE((g.lda % 2) == 0 && (g.ldb % 2) == 0 && (g.ldc % 2) == 0, "gemm: leading dimensions must be even");
