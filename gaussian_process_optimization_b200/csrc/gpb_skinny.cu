@@ -16,7 +16,7 @@
 //                                                                            stationary.py:354-364)
 // with the 32 KB chunks of the triangle dealt to the CTAs in contiguous, equal runs (+-1 chunk) and streamed through a 3-stage
 // shared-memory ring by the TMA engine -- ONE cp.async.bulk.tensor.2d per chunk (tensor map over M, box 128 x 32 doubles) completing on
-// an mbarrier -- every lane owning four columns of a chunk.  (History, ncu r2c / r2d: loading the chunks into registers kept too few
+// an mbarrier -- every lane owning four columns of a chunk (two 16-byte pieces 512 bytes apart, so that a warp's shared loads are conflict free).  (History, ncu r2c / r2d: loading the chunks into registers kept too few
 // bytes in flight, 4.8 of 6.5 TB/s; 32 one-row bulk copies of 1 KB per chunk made the TMA engine's per-operation cost the bound, 2.7.)
 // All partial sums are combined in fixed orders that do not depend on the number of candidates sharing the call: candidate c's
 // results are bit-identical whether it is evaluated alone or with seven others, and run to run.
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const __gri
   const uint64_t pol_stream = sk_policy_evict_first(), pol_keep = sk_policy_evict_last();
   int it = 0;                  // chunks consumed so far by this CTA, over both passes: stage = it % STAGES, parity = (it / STAGES) & 1
 
-  // ---- P1: Z = M k*  (row panels; warp w owns rows 4 w .. 4 w + 3 of the panel, lane l columns 4 l .. 4 l + 3 of the chunk) ----
+  // ---- P1: Z = M k*  (row panels; warp w owns rows 4 w .. 4 w + 3 of the panel, lane l four columns of the chunk) ----
   if (want_var && nu > 0) {
     // decode u0 -> (panel p, column block cb); a second cursor (ip, icb) runs SK_STAGES chunks ahead and feeds the ring
     int p = 0;
@@ -256,17 +256,19 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const __gri
       const int st = it % SK_STAGES;
       sk_mbar_wait(sk_smem_u32(&full_bar[st]), (uint32_t)((it / SK_STAGES) & 1));
       const double *tile = ring + (size_t)st * STAGE_DOUBLES;
-      const double *mrow = tile + (4 * warp) * TILE + 4 * lane;
+      // a lane's four columns are {2 l, 2 l + 1, 64 + 2 l, 64 + 2 l + 1}: each 16-byte shared load of the warp then covers 512
+      // contiguous bytes (with columns 4 l .. 4 l + 3 the lanes stride 32 bytes and every load is a two-way bank conflict, ncu r2o)
+      const double *mrow = tile + (4 * warp) * TILE + 2 * lane;
       double2 m[4][2];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         m[rr][0] = *reinterpret_cast<const double2 *>(mrow + rr * TILE);
-        m[rr][1] = *(reinterpret_cast<const double2 *>(mrow + rr * TILE) + 1);
+        m[rr][1] = *reinterpret_cast<const double2 *>(mrow + rr * TILE + 64);
       }
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const double2 b0 = *reinterpret_cast<const double2 *>(tile + SK_MTILE + c * TILE + 4 * lane);
-        const double2 b1 = *(reinterpret_cast<const double2 *>(tile + SK_MTILE + c * TILE + 4 * lane) + 1);
+        const double2 b0 = *reinterpret_cast<const double2 *>(tile + SK_MTILE + c * TILE + 2 * lane);
+        const double2 b1 = *reinterpret_cast<const double2 *>(tile + SK_MTILE + c * TILE + 2 * lane + 64);
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
           double sacc = acc[rr][c];
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const __gri
     sk_stamp(a.dbg, 6);
   }
 
-  // ---- P2: U = M^T Z  (column blocks; lane l owns columns 4 l .. 4 l + 3, warp w rows 4 w .. 4 w + 3 of every panel) --------
+  // ---- P2: U = M^T Z  (column blocks; lane l owns four columns, warp w rows 4 w .. 4 w + 3 of every panel) --------
   if (want_dvar && nu > 0) {
     int cb = 0;
     {
@@ -345,9 +347,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const __gri
       const int slot = g - sk_owner(sk_prefix2(cc, P), G, T);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        double *dst = wred + ((size_t)warp * C + c) * TILE + 4 * lane;
+        double *dst = wred + ((size_t)warp * C + c) * TILE + 2 * lane;
         *reinterpret_cast<double2 *>(dst) = make_double2(acc[c][0], acc[c][1]);
-        *reinterpret_cast<double2 *>(dst + 2) = make_double2(acc[c][2], acc[c][3]);
+        *reinterpret_cast<double2 *>(dst + 64) = make_double2(acc[c][2], acc[c][3]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[c][k] = 0.0;
       }
@@ -374,12 +376,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) skinny_fused_kernel(const __gri
       double znext = 0.0;
       if (i + 1 < nu && tid < C * SK_PH) znext = a.Z[(size_t)(tid >> 5) * np + pn * SK_PH + (tid & 31)];
       sk_mbar_wait(sk_smem_u32(&full_bar[st]), (uint32_t)((it / SK_STAGES) & 1));
-      const double *mrow = ring + (size_t)st * STAGE_DOUBLES + (4 * warp) * TILE + 4 * lane;
+      const double *mrow = ring + (size_t)st * STAGE_DOUBLES + (4 * warp) * TILE + 2 * lane;
       const double *zc = zs[i & 1];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
-        const double2 m0 = *reinterpret_cast<const double2 *>(mrow + rr * TILE);
-        const double2 m1 = *(reinterpret_cast<const double2 *>(mrow + rr * TILE) + 1);
+        const double2 m0 = *reinterpret_cast<const double2 *>(mrow + rr * TILE);             // columns 2 l, 2 l + 1
+        const double2 m1 = *reinterpret_cast<const double2 *>(mrow + rr * TILE + 64);        // columns 64 + 2 l, 64 + 2 l + 1
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           const double z = zc[c * SK_PH + 4 * warp + rr];
