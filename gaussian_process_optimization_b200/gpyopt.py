@@ -903,11 +903,22 @@ class AcquisitionOptimizer(object):
     # -- all anchors refined concurrently, their M = 1 requests coalesced into one M <= 8 device call (LockstepEvaluator) ----------
     # Needs an f_df whose rows are bit-identical to single-row calls: the CUDA acquisition path declares it
     # (`batched_rows_bitwise`); the kwarg lockstep_anchors=False forces the sequential loop.
+    LOCKSTEP_MIN_N = 1024      # below this a device call is tens of microseconds and the threads' hand-overs cost more than they save
+
     def _lockstep_ok(self, f_df, anchor_points):
-        if f_df is None or len(anchor_points) < 2 or not self.kwargs.get('lockstep_anchors', True):
+        """kwarg lockstep_anchors: True forces it, False forbids it, absent = automatic (models of at least LOCKSTEP_MIN_N points:
+        BASELINE config 1, N <= 35, ran 10% slower in lock step -- 0.57 s against 0.51 s for the 30 iterations)."""
+        mode = self.kwargs.get('lockstep_anchors', 'auto')
+        if f_df is None or len(anchor_points) < 2 or mode is False:
             return False
         owner = getattr(f_df, '__self__', None)
-        return bool(getattr(owner, 'batched_rows_bitwise', False))
+        if not getattr(owner, 'batched_rows_bitwise', False):
+            return False
+        if mode is True:
+            return True
+        gp = getattr(getattr(owner, 'model', None), 'model', None)
+        n = getattr(getattr(gp, 'X', None), 'shape', (0,))[0]
+        return n >= self.LOCKSTEP_MIN_N
 
     def _optimize_anchors_lockstep(self, anchor_points, f, f_df, duplicate_manager):
         import threading

@@ -226,7 +226,14 @@ def test_lockstep_evaluator_gives_every_run_its_sequential_trajectory():
     assert a_lock.rows == a_seq.rows                      # the same requests were answered ...
     assert a_lock.calls < a_seq.calls                     # ... in fewer calls
     assert opt.lockstep_stats["requests"] == a_seq.rows
+    opt.kwargs['lockstep_anchors'] = True
     assert opt._lockstep_ok(a_lock.f_df, anchors) and not opt._lockstep_ok(a_lock.f_df, anchors[:1])
+    opt.kwargs['lockstep_anchors'] = 'auto'            # automatic mode: only for models of at least LOCKSTEP_MIN_N points
+    assert not opt._lockstep_ok(a_lock.f_df, anchors)
+    a_lock.model = type("M", (), {"model": type("G", (), {"X": np.zeros((opt.LOCKSTEP_MIN_N, 3))})()})()
+    assert opt._lockstep_ok(a_lock.f_df, anchors)
+    opt.kwargs['lockstep_anchors'] = False
+    assert not opt._lockstep_ok(a_lock.f_df, anchors)
 
 
 def test_lockstep_evaluator_propagates_errors_and_does_not_deadlock():
