@@ -283,8 +283,15 @@ static int check_device(const gpb_model *m, const char *what) {
     // captured while any thread touches the legacy stream).  Work the caller queued on the legacy stream before this call (e.g. a
     // torch op producing an input tensor) is ordered in front of ours explicitly; every entry point synchronises its stream before
     // it returns, which orders the other direction.
-    GPB_CUDA(cudaEventRecord(m->entry_ev, cudaStreamLegacy));
-    GPB_CUDA(cudaStreamWaitEvent(m->stream, m->entry_ev, 0));
+    // (an idle legacy stream has nothing to order against: one query instead of an event pair on the hot path of the small-N BO loop,
+    // which makes tens of thousands of these calls)
+    const cudaError_t q = cudaStreamQuery(cudaStreamLegacy);
+    if (q == cudaErrorNotReady) {
+      GPB_CUDA(cudaEventRecord(m->entry_ev, cudaStreamLegacy));
+      GPB_CUDA(cudaStreamWaitEvent(m->stream, m->entry_ev, 0));
+    } else if (q != cudaSuccess) {
+      GPB_CUDA(q);
+    }
   }
   return 0;
 }
