@@ -14,7 +14,10 @@
 // dpotrf + dpotri.  The leaf factors a 128x128 block and inverts its factor in ONE fused rank-1 sweep held in registers.
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "gpb_common.cuh"
+#include "gpb_gemm_tile.cuh"
 
 namespace gpb {
 
@@ -819,6 +822,261 @@ int launch_tiny_fit(int kind, const double *X, const double *ls_host, double *Xs
   return 0;
 }
 
+// =====================================================================================================================
+// Cooperative diagonal-block solver: cholinv of a block of up to COOP_MAX rows as ONE persistent kernel
+// =====================================================================================================================
+// MEASURED AND SWITCHED OFF (GPB_COOP_N=1024 selects it; default 0).  The idea (round-1 review, item 5): below ~1024 rows the
+// recursion is a chain of dependent launches that each last 6 - 15 us (84 of them on the critical path of an N = 4096 evaluation,
+// profiles/r2i_launches_nll4096.md); one grid of co-resident CTAs could walk the same recursion itself -- explicit stack, the same
+// order of operations -- and separate dependent steps by grid-wide barriers instead of kernel boundaries.  Built, bit-identical to
+// the launch chain (tests/test_gpu_native.py), and SLOWER: N = 4096 4.32 ms against 3.70, N = 1024 0.535 against 0.437, N = 256
+// 0.189 against 0.158 (profiles/r2q_coop_solver.json).  A 32 x 32 tile's k-loop is a latency chain (16 dependent DMMA issue slots
+// per 16 k); the stand-alone launches hide it with 16 warps per SM and programmatic dependent launch, a persistent grid that must
+// also hold the leaf's 176 KB of shared memory runs 8 warps per SM, two tiles at a time -- its product steps take about twice as
+// long as the launches they replace, which the cheaper barriers do not buy back.  A leaf is executed by CTA 0 with the code of leaf_blocked_kernel; a product step
+// is cut into the 32 x 32 tiles of the stand-alone engine's small configuration (BK 16, 3 stages, the same fragment order, so every
+// output element is the bit pattern gemm_dmma_kernel<.., 32, 32, ..> produces), dealt to the two 4-warp halves of every CTA;
+// T12 = M11^T L21^T and A22 -= L21 L21^T depend on L21 only and share a step.
+namespace cgc = cooperative_groups;
+
+struct CoopArgs {
+  double *A, *Mi, *W;
+  int ld, off, n;
+  int *info;
+};
+
+__device__ __forceinline__ void half_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// one 32 x 32 tile of C = alpha op(A) op(B)^T + beta C, executed by 128 threads (tid in [0, 128)) with their own staging area
+template <int LA, int LB>
+__device__ __forceinline__ void coop_gemm_tile(const GemmArgs &p, int t, double *smem, int tid, int bar_id) {
+  constexpr int BM = 32, BN = 32, BK = 16, STAGES = 3, THREADS = 128, WARPS_N = 2;
+  constexpr int WTM = 16, WTN = 16, MI = 2, NI = 2;
+  constexpr int A_TILE = tile_doubles<LA, BM, BK>();
+  constexpr int B_TILE = tile_doubles<LB, BN, BK>();
+  double *sA = smem, *sB = smem + STAGES * A_TILE;
+  int tm, tn;
+  if (p.tri_out) {
+    const int q = t >> 4, w_in = t & 15;                           // 16 tiles per 128-block; lower blocks in row-major order
+    int i = (int)((sqrt(8.0 * (double)q + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= q) ++i;
+    while (i * (i + 1) / 2 > q) --i;
+    const int j = q - i * (i + 1) / 2;
+    tm = i * 4 + (w_in >> 2);
+    tn = j * 4 + (w_in & 3);
+  } else {
+    const int tiles_n = p.N / BN;
+    tm = t / tiles_n;
+    tn = t - tm * tiles_n;
+  }
+  const int row0 = tm * BM, col0 = tn * BN;
+  const int rblk = row0 & ~127, cblk = col0 & ~127;
+  const int klo = (p.klo_mode == 1) ? rblk : (p.klo_mode == 2) ? cblk : 0;
+  int khi = (p.khi_mode == 1) ? rblk + 128 : (p.khi_mode == 2) ? cblk + 128 : p.K;
+  if (khi > p.K) khi = p.K;
+  const int ktiles = (khi - klo) / BK;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  const int wm = (warp / WARPS_N) * WTM, wn = (warp % WARPS_N) * WTN;
+  const double *Abase = (LA == LAYOUT_ROWK) ? p.A + (size_t)row0 * p.lda : p.A + row0;
+  const double *Bbase = (LB == LAYOUT_ROWK) ? p.B + (size_t)col0 * p.ldb : p.B + col0;
+  double acc[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < ktiles) {
+      load_tile<LA, BM, THREADS, BK>(sA + s * A_TILE, Abase, p.lda, klo + s * BK, tid);
+      load_tile<LB, BN, THREADS, BK>(sB + s * B_TILE, Bbase, p.ldb, klo + s * BK, tid);
+    }
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    half_bar(bar_id);
+    {
+      const int nt = kt + STAGES - 1;
+      if (nt < ktiles) {
+        const int s = nt % STAGES;
+        load_tile<LA, BM, THREADS, BK>(sA + s * A_TILE, Abase, p.lda, klo + nt * BK, tid);
+        load_tile<LB, BN, THREADS, BK>(sB + s * B_TILE, Bbase, p.ldb, klo + nt * BK, tid);
+      }
+      cp_async_commit();
+    }
+    const double *a_s = sA + (kt % STAGES) * A_TILE;
+    const double *b_s = sB + (kt % STAGES) * B_TILE;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ++ks) {
+      const int k0 = ks * 4 + tq;
+      double a[MI], b[NI];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) a[i] = frag<LA, BM, BK>(a_s, wm + i * 8 + g, k0);
+#pragma unroll
+      for (int j = 0; j < NI; ++j) b[j] = frag<LB, BN, BK>(b_s, wn + j * 8 + g, k0);
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+  const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+  for (int i = 0; i < MI; ++i) {
+    const int row = row0 + wm + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int col = col0 + wn + j * 8 + 2 * tq;
+      double2 *ptr = reinterpret_cast<double2 *>(p.C + (size_t)row * p.ldc + col);
+      double2 o;
+      o.x = alpha * acc[i][j][0];
+      o.y = alpha * acc[i][j][1];
+      if (beta != 0.0) {
+        const double2 c = *ptr;
+        o.x += beta * c.x;
+        o.y += beta * c.y;
+      }
+      *ptr = o;
+    }
+  }
+  half_bar(bar_id);            // the staging area is free for the half's next tile
+}
+
+__device__ __forceinline__ int coop_tiles(const GemmArgs &p) {
+  const int bm = p.M / 128, bn = p.N / 128;
+  return (p.tri_out ? bm * (bm + 1) / 2 : bm * bn) * 16;
+}
+
+// one step: up to two independent products (la / lb: storage orders of the first one; the second is always ROWK x ROWK)
+__device__ __forceinline__ void coop_step(const GemmArgs &g0, int la0, const GemmArgs *g1, double *smem_half, int tid128, int half,
+                                          int G) {
+  const int t0 = coop_tiles(g0), t1 = g1 ? coop_tiles(*g1) : 0;
+  for (int w = blockIdx.x * 2 + half; w < t0 + t1; w += 2 * G) {
+    if (w < t0) {
+      if (la0 == LAYOUT_COLK) coop_gemm_tile<LAYOUT_COLK, LAYOUT_ROWK>(g0, w, smem_half, tid128, 1 + half);
+      else coop_gemm_tile<LAYOUT_ROWK, LAYOUT_ROWK>(g0, w, smem_half, tid128, 1 + half);
+    } else {
+      coop_gemm_tile<LAYOUT_ROWK, LAYOUT_ROWK>(*g1, w - t0, smem_half, tid128, 1 + half);
+    }
+  }
+}
+
+constexpr int COOP_GEMM_SMEM = 3 * (32 * 20 + 32 * 20);   // doubles per half (the larger of the two layouts)
+
+__global__ void __launch_bounds__(LEAF_THREADS, 1) cholinv_coop_kernel(const CoopArgs a) {
+  cgc::grid_group grid = cgc::this_grid();
+  extern __shared__ double sm[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int half = warp >> 2, tid128 = tid & 127;
+  const int G = gridDim.x, ld = a.ld;
+  double *smem_half = sm + half * COOP_GEMM_SMEM;
+  int s_off[8], s_n[8], s_state[8];
+  int sp = 0;
+  s_off[0] = a.off;
+  s_n[0] = a.n;
+  s_state[0] = 0;
+  while (sp >= 0) {
+    const int off = s_off[sp], n = s_n[sp];
+    if (n == TILE) {
+      if (blockIdx.x == 0) {                       // the leaf: exactly the body of leaf_blocked_kernel
+        double *S = sm, *Md = S + TILE * LSD, *Tw = Md + LNB * LB * LMD;
+        double *Ab = a.A + (size_t)off * ld + off, *Mb = a.Mi + (size_t)off * ld + off;
+#pragma unroll
+        for (int it = 0; it < TILE * (TILE / 2) / LEAF_THREADS; ++it) {
+          const int e = tid + it * LEAF_THREADS, r = e >> 6, c = (e & 63) * 2;
+          if (c <= r) leaf_cp_async16(S + r * LSD + c, Ab + (size_t)r * ld + c);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        const int fail = leaf_core(S, Md, Tw, Ab, ld, Mb, ld, tid, lane, warp);
+        if (warp == 0 && lane == 0 && fail != 0) atomicCAS(a.info, 0, off + fail);
+        __syncthreads();
+      }
+      grid.sync();
+      --sp;
+      continue;
+    }
+    const int h = ((n / TILE) / 2) * TILE, r = n - h;
+    double *A21 = a.A + (size_t)(off + h) * ld + off;
+    double *A22 = a.A + (size_t)(off + h) * ld + off + h;
+    double *M11 = a.Mi + (size_t)off * ld + off;
+    double *M21 = a.Mi + (size_t)(off + h) * ld + off;
+    double *M22 = a.Mi + (size_t)(off + h) * ld + off + h;
+    double *S21 = a.W + (size_t)(off + h) * ld + off;
+    double *T12 = a.W + (size_t)off * ld + off + h;
+    if (s_state[sp] == 0) {                        // cholinv(A11)
+      s_state[sp] = 1;
+      ++sp;
+      s_off[sp] = off;
+      s_n[sp] = h;
+      s_state[sp] = 0;
+    } else if (s_state[sp] == 1) {
+      // L21 = A21 M11^T
+      const GemmArgs g1{A21, ld, M11, ld, S21, ld, r, h, h, 1.0, 0.0, 0, 0, 2};
+      coop_step(g1, LAYOUT_ROWK, nullptr, smem_half, tid128, half, G);
+      grid.sync();
+      // T12 = M11^T L21^T   and   A22 -= L21 L21^T
+      const GemmArgs g2{M11, ld, S21, ld, T12, ld, h, r, h, 1.0, 0.0, 0, 1, 0};
+      const GemmArgs g3{S21, ld, S21, ld, A22, ld, r, r, h, -1.0, 1.0, 1, 0, 0};
+      coop_step(g2, LAYOUT_COLK, &g3, smem_half, tid128, half, G);
+      grid.sync();
+      s_state[sp] = 2;                             // cholinv(A22)
+      ++sp;
+      s_off[sp] = off + h;
+      s_n[sp] = r;
+      s_state[sp] = 0;
+    } else {
+      // M21 = -M22 T21
+      const GemmArgs g4{M22, ld, T12, ld, M21, ld, r, h, r, -1.0, 0.0, 0, 0, 1};
+      coop_step(g4, LAYOUT_ROWK, nullptr, smem_half, tid128, half, G);
+      grid.sync();
+      --sp;
+    }
+  }
+}
+
+static int coop_max_n() {
+  static const int v = [] {
+    const char *e = getenv("GPB_COOP_N");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+// cholinv of the diagonal block [off, off + n) in one cooperative launch (n a multiple of 128, 256 <= n <= coop_max_n())
+static int launch_cholinv_coop(Factor &f, int off, int n) {
+  const size_t smem_b = (size_t)(TILE * LSD + 2 * LNB * LB * LMD) * sizeof(double);
+  static std::atomic<int> sms[64];
+  static FuncConfigMask configured{0};
+  int dev = 0;
+  GPB_CUDA(cudaGetDevice(&dev));
+  GPB_REQUIRE(dev >= 0 && dev < 64, "cholinv_coop: device ordinal %d out of range", dev);
+  {
+    FuncConfigOnce once(configured);
+    if (once.needed) {
+      int nsm = 0, occ = 0;
+      GPB_CUDA(cudaFuncSetAttribute(cholinv_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+      GPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cholinv_coop_kernel, LEAF_THREADS, smem_b));
+      GPB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      GPB_REQUIRE(occ >= 1 && nsm >= 1, "cholinv_coop: kernel does not fit an SM");
+      sms[dev].store(nsm, std::memory_order_release);
+    }
+  }
+  // never more CTAs than the largest step has half-tiles for (a step of an n-row block has at most 2 (n / 64)^2 / 4 ... tiles)
+  const int h = ((n / TILE) / 2) * TILE, r = n - h;
+  const int max_tiles = ((h / 128) * (r / 128) + (r / 128) * (r / 128 + 1) / 2) * 16;
+  const int G = std::max(1, std::min(sms[dev].load(), (max_tiles + 1) / 2));
+  CoopArgs a{f.A, f.Mi, f.W, f.np, off, n, f.info};
+  void *args[] = {&a};
+  GPB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(cholinv_coop_kernel), dim3(G), dim3(LEAF_THREADS), args, smem_b, f.stream));
+  count_launch();
+  return 0;
+}
+
 static int g_leaf_variant = -1;  // 1: blocked DMMA leaf (default), 0: register rank-1 sweep (GPB_LEAF=0)
 
 static int launch_leaf(Factor &f, int off, int mode) {
@@ -905,6 +1163,22 @@ int launch_symmetrize_lower(double *A, int ld, int n, cudaStream_t s) {
   return 0;
 }
 
+// cooperative solver usable for this call?  (blocked leaf variant; the stream is not being captured into a CUDA graph)
+static bool coop_usable(const Factor &f) {
+  if (coop_max_n() < 2 * TILE) return false;
+  if (g_leaf_variant < 0) {
+    const char *e = getenv("GPB_LEAF");
+    g_leaf_variant = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (g_leaf_variant != 1) return false;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(f.stream, &st) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return st == cudaStreamCaptureStatusNone;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // potrf + triangular inverse (recursive)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -925,6 +1199,10 @@ int launch_symmetrize_lower(double *A, int ld, int n, cudaStream_t s) {
 // trailing block rows are (re)computed: O(N^2 r) instead of O(N^3).
 static int cholinv(Factor &f, int off, int n, int depth, int split = 0) {
   if (n == TILE) return launch_leaf(f, off, 0);
+  // small diagonal blocks: the whole sub-recursion in one persistent cooperative kernel (not under stream capture: cooperative
+  // launches cannot be captured; not with the register leaf variant or the int8 engine on these rows)
+  if (split == 0 && n <= coop_max_n() && n >= 2 * TILE && coop_usable(f) && !(ozaki_min_n() > 0 && n >= ozaki_min_n()))
+    return launch_cholinv_coop(f, off, n);
   const int ld = f.np;
   const int h = split > 0 ? split : ((n / TILE) / 2) * TILE;  // first part (multiple of 128); default: half, n - h >= h
   const int r = n - h;

@@ -534,3 +534,24 @@ def test_wide_inputs_d48_block_and_skinny_routes_match_the_oracle(kind):
     gx_ref = O.gradients_X(kind, G, X[:40] + 0.01, X, 1.2, ls)
     assert_allclose(gx, gx_ref, rtol=1e-7, atol=1e-9 * np.abs(gx_ref).max())
     m.close()
+
+
+def test_cooperative_block_solver_is_bit_identical_to_the_launch_chain():
+    """GPB_COOP_N selects the persistent cooperative kernel for diagonal blocks of the recursion (measured slower, off by default:
+    profiles/r2q_coop_solver.json).  It is read once per process, so the comparison runs in two child processes."""
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np; sys.path.insert(0, '.');"
+            "from gaussian_process_optimization_b200 import native;"
+            "rs = np.random.RandomState(3); n = 900; B = rs.randn(n, n + 2); A = B @ B.T + 0.5 * n * np.eye(n);"
+            "rc, Ai, L, Li, ld = native.pdinv(A); assert rc == 0;"
+            "import hashlib; print(hashlib.sha256(L.tobytes() + Li.tobytes() + Ai.tobytes()).hexdigest(), repr(ld))")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for coop in ("0", "1024"):
+        env = dict(os.environ, GPB_COOP_N=coop)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
