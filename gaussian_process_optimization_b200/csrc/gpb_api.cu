@@ -644,7 +644,9 @@ static int fit_launch_general(gpb_model *m, int want_grad, double extra_jitter, 
                       m->stream, kc.gflag, append_from, theta));
   // fork threshold: the top three levels of the recursion (more forks only add cross-stream latency, scripts/overlap_sweep.py)
   static const int fork_div = std::max(1, env_int("GPB_FORK_DIV", 8));
-  const int fork_min_n = g_overlap_min_n > 0 ? std::max(g_overlap_min_n, np / fork_div) : 0;
+  // up to 4096 rows every level forks (each T12 taken off the critical path is one 6 - 15 us launch less on it: 3.750 -> 3.726 ms at
+  // N = 4096, 0.441 -> 0.424 at N = 1024); above, only the top three levels (deeper forks cost 0.1 ms at N = 16384), scripts/overlap_min_probe.py
+  const int fork_min_n = g_overlap_min_n > 0 ? (np <= 4096 && g_overlap_min_n == 512 ? 128 : std::max(g_overlap_min_n, np / fork_div)) : 0;
   if (m->ov && fork_min_n > 0 && np >= fork_min_n) {
     // critical path on the model's high-priority stream, T21 products on its low-priority side streams (gpb_chol.cu)
     Factor fo = m->f;
