@@ -8,8 +8,13 @@
 // (row stride ldx >= number of points, zero padded), so that a 64-point tile of one dimension is one coalesced 512 B line
 // and lands in shared memory in the order the register-tiled pair loops read it.  r^2 is the direct sum of squared
 // differences (exactly 0 on the diagonal, never negative) instead of the reference's |x|^2+|y|^2-2xy expansion.
+#include <cooperative_groups.h>
+#include <cuda_pipeline.h>
+
 #include "gpb_common.cuh"
 #include "gpb_kernels.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace gpb {
 
@@ -448,53 +453,235 @@ int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *
 // One warp per output row c; lanes stride over n (coalesced in the dimension-major layout); per-lane accumulators for all
 // dimensions live in registers (DCAP), then a fixed-order warp reduction.
 // ---------------------------------------------------------------------------------------------------------------------
+// GX_WPC warps share one output row: with one warp per row a block of 2048 candidates put 14 warps on an SM, each walking all N
+// training points through a dependent chain (2.8 ms per block at N = 16384, 22% of the int8 engine's EI pass: profiles/
+// r2v_launches_ei_engine.md).  The warps of a row take interleaved 32-point slices; their sums are added in warp order (fixed).
+constexpr int GX_WPC = 4;
+
 template <int KIND, int DCAP, int TWO>
 __global__ void __launch_bounds__(256) gradx_kernel(const double *__restrict__ XcT, int ldc, int n_c, const double *__restrict__ XT, int ldx,
                                                     int n, int d, double variance, const double *__restrict__ inv_ls,
                                                     const double *__restrict__ G1, int ldg1, double s1, int add_t,
                                                     const double *__restrict__ G2, int ldg2, double s2,
                                                     double *__restrict__ out1, double *__restrict__ out2, int ldo) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= n_c) return;
+  constexpr int NV = TWO ? 2 * DCAP : DCAP;
+  __shared__ double part[8][NV];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int c = blockIdx.x * (8 / GX_WPC) + warp / GX_WPC, slice = warp % GX_WPC;
+  const bool live = c < n_c;
   double xc[DCAP], a1[DCAP], a2[TWO ? DCAP : 1];
 #pragma unroll
   for (int q = 0; q < DCAP; ++q) {
-    xc[q] = (q < d) ? XcT[(size_t)q * ldc + c] : 0.0;
+    xc[q] = (live && q < d) ? XcT[(size_t)q * ldc + c] : 0.0;
     a1[q] = 0.0;
     if (TWO) a2[q] = 0.0;
   }
-  for (int j = lane; j < n; j += 32) {
-    double df[DCAP];
-    double r2 = 0.0;
+  if (live) {
+    for (int j = slice * 32 + lane; j < n; j += 32 * GX_WPC) {
+      double df[DCAP];
+      double r2 = 0.0;
 #pragma unroll
-    for (int q = 0; q < DCAP; ++q) {
-      df[q] = (q < d) ? xc[q] - XT[(size_t)q * ldx + j] : 0.0;
-      r2 = fma(df[q], df[q], r2);
-    }
-    double k, dk;
-    cov_k_dk<KIND>(r2, variance, k, dk);
-    double g1 = G1[(size_t)c * ldg1 + j];
-    if (add_t) g1 += G1[(size_t)j * ldg1 + c];
-    const double w1 = dk * g1;
-    double w2 = 0.0;
-    if (TWO) w2 = dk * G2[(size_t)c * ldg2 + j];
+      for (int q = 0; q < DCAP; ++q) {
+        df[q] = (q < d) ? xc[q] - XT[(size_t)q * ldx + j] : 0.0;
+        r2 = fma(df[q], df[q], r2);
+      }
+      double k, dk;
+      cov_k_dk<KIND>(r2, variance, k, dk);
+      double g1 = G1[(size_t)c * ldg1 + j];
+      if (add_t) g1 += G1[(size_t)j * ldg1 + c];
+      const double w1 = dk * g1;
+      double w2 = 0.0;
+      if (TWO) w2 = dk * G2[(size_t)c * ldg2 + j];
 #pragma unroll
-    for (int q = 0; q < DCAP; ++q) {
-      a1[q] = fma(w1, df[q], a1[q]);
-      if (TWO) a2[q] = fma(w2, df[q], a2[q]);
+      for (int q = 0; q < DCAP; ++q) {
+        a1[q] = fma(w1, df[q], a1[q]);
+        if (TWO) a2[q] = fma(w2, df[q], a2[q]);
+      }
     }
   }
 #pragma unroll
   for (int q = 0; q < DCAP; ++q) {
-    if (q < d) {
-      const double v1 = warp_sum(a1[q]);
-      if (lane == 0) out1[(size_t)c * ldo + q] = s1 * inv_ls[q] * v1;
-      if (TWO) {
-        const double v2 = warp_sum(a2[q]);
-        if (lane == 0) out2[(size_t)c * ldo + q] = s2 * inv_ls[q] * v2;
+    const double v1 = warp_sum(a1[q]);
+    if (lane == 0) part[warp][q] = v1;
+    if (TWO) {
+      const double v2 = warp_sum(a2[q]);
+      if (lane == 0) part[warp][DCAP + q] = v2;
+    }
+  }
+  __syncthreads();
+  // one thread per (row of this CTA, value): the GX_WPC slices in order
+  for (int e = threadIdx.x; e < (8 / GX_WPC) * NV; e += 256) {
+    const int rloc = e / NV, i = e - rloc * NV;
+    const int cc = blockIdx.x * (8 / GX_WPC) + rloc;
+    const int q = i < DCAP ? i : i - DCAP;
+    if (cc < n_c && q < d) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < GX_WPC; ++w) v += part[rloc * GX_WPC + w][i];
+      if (i < DCAP) out1[(size_t)cc * ldo + q] = s1 * inv_ls[q] * v;
+      else out2[(size_t)cc * ldo + q] = s2 * inv_ls[q] * v;
+    }
+  }
+}
+
+// Candidate blocks (n_c >= GX_TILE_MIN_ROWS) take the tiled version: the one-warp-per-row kernel above spends its time waiting for
+// global loads (ncu r2w: long-scoreboard 6.2 cycles per issue, 8 warps per SM, FP64 pipe 15% busy; 2.8 ms for 2048 x 16384 pairs).
+// Here a CTA of 8 warps owns 8 rows and walks chunks of 128 training points that a 3-stage cp.async ring brings into shared
+// memory once for all 8 rows (coordinates) plus each row's weights; a cluster of GX_SLICES CTAs shares the 8 rows, every CTA of
+// it taking every GX_SLICES-th chunk, and rank 0 adds the slices' sums in rank order through distributed shared memory -- no
+// scratch buffer, no atomics, the same bits on every run.
+constexpr int GX_SLICES = 4;
+constexpr int GX_CH = 128;
+constexpr int GX_ROWS = 8;
+constexpr int GX_TILE_MIN_ROWS = 64;
+
+template <int DCAP, int TWO>
+struct GxTile {
+  static constexpr int ST = DCAP > 16 ? 2 : 3;
+  static constexpr int NV = TWO ? 2 * DCAP : DCAP;
+  static constexpr int STAGE = DCAP * GX_CH + GX_ROWS * GX_CH * (TWO ? 2 : 1);      // doubles
+  static constexpr size_t SMEM = (size_t)(ST * STAGE + GX_ROWS * NV) * sizeof(double);
+};
+
+template <int KIND, int DCAP, int TWO>
+__global__ void __launch_bounds__(256) gradx_tile_kernel(const double *__restrict__ XcT, int ldc, int n_c, const double *__restrict__ XT, int ldx,
+                                                                      int n, int d, double variance, const double *__restrict__ inv_ls,
+                                                                      const double *__restrict__ G1, int ldg1, double s1, int add_t,
+                                                                      const double *__restrict__ G2, int ldg2, double s2,
+                                                                      double *__restrict__ out1, double *__restrict__ out2, int ldo) {
+  using T = GxTile<DCAP, TWO>;
+  constexpr int NV = T::NV, ST = T::ST;
+  extern __shared__ double gx_sm[];
+  double *part = gx_sm + ST * T::STAGE;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int group = blockIdx.x / GX_SLICES;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int c = group * GX_ROWS + warp;
+  const bool live = c < n_c;
+  const int n_chunks = (n + GX_CH - 1) / GX_CH;
+  const int mine = rank < n_chunks ? (n_chunks - rank + GX_SLICES - 1) / GX_SLICES : 0;
+
+  auto issue = [&](int i) {
+    if (i < mine) {
+      double *sx = gx_sm + (i % ST) * T::STAGE, *sg1 = sx + DCAP * GX_CH, *sg2 = sg1 + GX_ROWS * GX_CH;
+      const int j0 = (rank + GX_SLICES * i) * GX_CH;
+      for (int e = tid; e < DCAP * GX_CH; e += 256) {
+        const int q = e / GX_CH, j = j0 + (e % GX_CH);
+        if (q < d && j < n) __pipeline_memcpy_async(sx + e, XT + (size_t)q * ldx + j, 8);
+        else sx[e] = 0.0;
+      }
+      for (int e = tid; e < GX_ROWS * GX_CH; e += 256) {
+        const int cc = group * GX_ROWS + e / GX_CH, j = j0 + (e % GX_CH);
+        const bool in = cc < n_c && j < n;                    // weight 0 outside: the pair adds nothing
+        if (in && !add_t) __pipeline_memcpy_async(sg1 + e, G1 + (size_t)cc * ldg1 + j, 8);
+        else sg1[e] = in ? G1[(size_t)cc * ldg1 + j] + G1[(size_t)j * ldg1 + cc] : 0.0;
+        if (TWO) {
+          if (in) __pipeline_memcpy_async(sg2 + e, G2 + (size_t)cc * ldg2 + j, 8);
+          else sg2[e] = 0.0;
+        }
+      }
+    }
+    __pipeline_commit();
+  };
+
+  double xc[DCAP], a1[DCAP], a2[TWO ? DCAP : 1];
+#pragma unroll
+  for (int q = 0; q < DCAP; ++q) {
+    xc[q] = (live && q < d) ? XcT[(size_t)q * ldc + c] : 0.0;
+    a1[q] = 0.0;
+    if (TWO) a2[q] = 0.0;
+  }
+  for (int i = 0; i < ST - 1; ++i) issue(i);
+  for (int i = 0; i < mine; ++i) {
+    issue(i + ST - 1);
+    __pipeline_wait_prior(ST - 1);
+    __syncthreads();
+    if (live) {
+      const double *sx = gx_sm + (i % ST) * T::STAGE, *sg1 = sx + DCAP * GX_CH + warp * GX_CH, *sg2 = sg1 + GX_ROWS * GX_CH;
+#pragma unroll 1
+      for (int u = 0; u < GX_CH / 32; ++u) {
+        const int jj = lane + 32 * u;
+        double df[DCAP];
+        double ra = 0.0, rb = 0.0;                      // two chains: half the dependent latency
+#pragma unroll
+        for (int q = 0; q < DCAP; q += 2) {
+          const double da = xc[q] - sx[q * GX_CH + jj];
+          const double db = (q + 1 < DCAP) ? xc[q + 1] - sx[(q + 1) * GX_CH + jj] : 0.0;
+          df[q] = da;
+          if (q + 1 < DCAP) df[q + 1] = db;
+          ra = fma(da, da, ra);
+          rb = fma(db, db, rb);
+        }
+        double k, dk;
+        cov_k_dk<KIND>(ra + rb, variance, k, dk);
+        const double w1 = dk * sg1[jj];
+        const double w2 = TWO ? dk * sg2[jj] : 0.0;
+#pragma unroll
+        for (int q = 0; q < DCAP; ++q) {
+          a1[q] = fma(w1, df[q], a1[q]);
+          if (TWO) a2[q] = fma(w2, df[q], a2[q]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __pipeline_wait_prior(0);
+#pragma unroll
+  for (int q = 0; q < DCAP; ++q) {
+    const double v1 = warp_sum(a1[q]);
+    if (lane == 0) part[warp * NV + q] = v1;
+    if (TWO) {
+      const double v2 = warp_sum(a2[q]);
+      if (lane == 0) part[warp * NV + DCAP + q] = v2;
+    }
+  }
+  cluster.sync();
+  if (rank == 0) {
+    for (int e = tid; e < GX_ROWS * NV; e += 256) {
+      const int w = e / NV, i = e - w * NV;
+      const int cc = group * GX_ROWS + w;
+      const int q = i < DCAP ? i : i - DCAP;
+      if (cc < n_c && q < d) {
+        double v = 0.0;
+#pragma unroll
+        for (int r = 0; r < GX_SLICES; ++r) v += cluster.map_shared_rank(part, r)[e];
+        if (i < DCAP) out1[(size_t)cc * ldo + q] = s1 * inv_ls[q] * v;
+        else out2[(size_t)cc * ldo + q] = s2 * inv_ls[q] * v;
       }
     }
   }
+  cluster.sync();      // the other ranks' shared memory must outlive rank 0's reads
+}
+
+template <int KIND, int DCAP, int TWO>
+static int launch_gradx_tile(const double *XcT, int ldc, int n_c, const double *XT, int ldx, int n, int d, double variance,
+                             const double *inv_ls, const double *G1, int ldg1, double s1, int add_t, const double *G2, int ldg2,
+                             double s2, double *out1, double *out2, int ldo, cudaStream_t s) {
+  using T = GxTile<DCAP, TWO>;
+  auto kernel = gradx_tile_kernel<KIND, DCAP, TWO>;
+  static FuncConfigMask configured;
+  {
+    FuncConfigOnce once(configured);
+    if (once.needed) GPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(GX_SLICES * ((n_c + GX_ROWS - 1) / GX_ROWS)));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = T::SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = GX_SLICES;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GPB_CUDA(cudaLaunchKernelEx(&cfg, kernel, XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, G2, ldg2, s2, out1, out2, ldo));
+  count_launch();
+  return 0;
 }
 
 // 32 < d <= 64: the register version above would need 4 x 64 doubles per lane (the DCAP = 64 instantiation spilled 9 KB per thread).
@@ -573,7 +760,12 @@ template <int KIND, int DCAP>
 static int launch_gradx_t(const double *XcT, int ldc, int n_c, const double *XT, int ldx, int n, int d, double variance,
                           const double *inv_ls, const double *G1, int ldg1, double s1, int add_t, const double *G2, int ldg2,
                           double s2, double *out1, double *out2, int ldo, cudaStream_t s) {
-  const int blocks = (n_c * 32 + 255) / 256;
+  const int blocks = (n_c + 8 / GX_WPC - 1) / (8 / GX_WPC);
+  static const bool tile_on = !getenv("GPB_GRADX_TILE") || atoi(getenv("GPB_GRADX_TILE")) != 0;
+  if (tile_on && n_c >= GX_TILE_MIN_ROWS) {
+    if (G2) return launch_gradx_tile<KIND, DCAP, 1>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, G2, ldg2, s2, out1, out2, ldo, s);
+    return launch_gradx_tile<KIND, DCAP, 0>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, nullptr, 0, 0.0, out1, nullptr, ldo, s);
+  }
   if (G2)
     gradx_kernel<KIND, DCAP, 1><<<blocks, 256, 0, s>>>(XcT, ldc, n_c, XT, ldx, n, d, variance, inv_ls, G1, ldg1, s1, add_t, G2, ldg2, s2, out1, out2, ldo);
   else
