@@ -446,7 +446,10 @@ def run_gpu(args, rank, world, local_rank):
                 "ei_candidates_per_s_per_gpu_18_moduli": mo.get("aux", {}).get("value"),
                 "agreement_logL_rel": mo.get("agreement_with_dmma_engine", {}).get("logL_rel"),
                 "int8_tops_sustained": mo.get("roofline", {}).get("achieved"), "frac_of_nominal_int8_at_measured_clock": mo.get("roofline", {}).get("frac"),
-                "sm_mhz_under_load": mo.get("roofline", {}).get("sm_mhz_under_load")}
+                "sm_mhz_under_load": mo.get("roofline", {}).get("sm_mhz_under_load"),
+                "engine_min_n": mo.get("engine", {}).get("min_n"),
+                "nll_grad_ms_per_eval_fewer_moduli": {k: (w.get("ms_per_eval"), w.get("agreement_with_dmma_engine", {}).get("logL_rel"))
+                                                      for k, w in mo.get("with_fewer_moduli", {}).items()}}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if aux_m1 is not None:
@@ -514,7 +517,7 @@ def bench_int8_engine(args, model, theta, dmma_s_per_eval, dgemm_peak_tflops):
         # modular (CRT) mode of the same engine: 16 moduli = 16 int8 products per fp64 product (56 bits per operand at k = 16384,
         # where 7 digits = 28 products carry 55); the predictive products then use 18 moduli (62 bits) instead of 8 digits
         try:
-            modular = bench_int8_modular(args, model, theta, (v, l, nz), dmma_s_per_eval, MIN_N, logL0, g0, shard, idx0, f0, df0)
+            modular = bench_int8_modular(args, model, theta, (v, l, nz), dmma_s_per_eval, 4096, logL0, g0, shard, idx0, f0, df0)
         except Exception as exc:                       # the experimental block must never take the headline line down with it
             modular = {"error": repr(exc)}
         native.set_ozaki(MIN_N, SLICES)
@@ -607,6 +610,35 @@ def bench_int8_modular(args, model, theta, theta0, dmma_s_per_eval, min_n, logL0
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / args.steps
+    # the accuracy knob: fewer moduli = fewer int8 products.  Every evaluation is still checked (componentwise backward error of
+    # Ky alpha = y, gpb_api.cu) and falls back to the fp64 engine when it fails -- at 12 moduli it does, and costs both evaluations.
+    fewer = {}
+    for nm in (14, 13):
+        try:
+            native.set_ozaki(min_n, nm)
+            fb0 = native.ozaki_fallback_count()
+            model.set_theta(*theta(0))
+            model.fit(True)
+            model.set_theta(v, l, nz)
+            info_k, logL_k, g_k = model.fit(True)
+            torch.cuda.synchronize()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for i in range(args.steps):
+                model.set_theta(*theta(100 + i))
+                model.fit(True)
+            k1.record()
+            torch.cuda.synchronize()
+            tk = k0.elapsed_time(k1) * 1e-3 / args.steps
+            fewer["%d_moduli" % nm] = {"ms_per_eval": tk * 1e3, "value": 1.0 / tk, "speedup_vs_dmma_engine": dmma_s_per_eval / tk,
+                                       "bits_per_operand": native.ozaki_crt_bits(nm, N_TRAIN),
+                                       "fallbacks_to_fp64_engine": native.ozaki_fallback_count() - fb0,
+                                       "agreement_with_dmma_engine": {"logL_rel": abs(logL_k - logL0) / abs(logL0),
+                                                                      "grad_rel_to_max": float(np.max(np.abs(g_k - g0)) / np.max(np.abs(g0))),
+                                                                      "info": int(info_k)}}
+        except Exception as exc:
+            fewer["%d_moduli" % nm] = {"error": repr(exc)}
+    native.set_ozaki(min_n, nmod)
     model.set_theta(v, l, nz)
     model.fit(True)
     fmin = model.fmin()
@@ -661,6 +693,7 @@ def bench_int8_modular(args, model, theta, theta0, dmma_s_per_eval, min_n, logL0
             "algorithmic_tflops_fp64_equivalent": flops / t / 1e12,
             "engine": {"min_n": min_n, "moduli": nmod, "int8_products_per_fp64_product": nmod,
                        "bits_per_operand": native.ozaki_crt_bits(nmod, N_TRAIN)},
+            "with_fewer_moduli": fewer,
             "agreement_with_dmma_engine": {"logL_rel": abs(logL - logL0) / abs(logL0),
                                            "grad_rel_to_max": float(np.max(np.abs(g - g0)) / np.max(np.abs(g0))), "info": int(info)},
             "aux": {"metric": "ei_value_gradient_candidates_per_s", "value": shard.shape[0] / t_acq, "unit": "candidates/s",

@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(256) gradx_kernel(const double *__restrict__ X
   }
 }
 
-// Candidate blocks (n_c >= GX_TILE_MIN_ROWS) take the tiled version: the one-warp-per-row kernel above spends its time waiting for
+// More than 8 rows (n_c >= GX_TILE_MIN_ROWS) take the tiled version: the one-warp-per-row kernel above spends its time waiting for
 // global loads (ncu r2w: long-scoreboard 6.2 cycles per issue, 8 warps per SM, FP64 pipe 15% busy; 2.8 ms for 2048 x 16384 pairs).
 // Here a CTA of 8 warps owns 8 rows and walks chunks of 128 training points that a 3-stage cp.async ring brings into shared
 // memory once for all 8 rows (coordinates) plus each row's weights; a cluster of GX_SLICES CTAs shares the 8 rows, every CTA of
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(256) gradx_kernel(const double *__restrict__ X
 constexpr int GX_SLICES = 4;
 constexpr int GX_CH = 128;
 constexpr int GX_ROWS = 8;
-constexpr int GX_TILE_MIN_ROWS = 64;
+constexpr int GX_TILE_MIN_ROWS = 9;       // every block of more than one 8-row group: a row's bits do not depend on the block it came in
 
 template <int DCAP, int TWO>
 struct GxTile {

@@ -135,9 +135,9 @@ def test_kernel_shapes_like_reference_cython_tests(kind):
 @pytest.mark.parametrize("kind", ["rbf", "mat52"])
 @pytest.mark.parametrize("rows,n,d", [(64, 128, 16), (71, 389, 5), (203, 1031, 16), (130, 517, 27), (96, 130, 1)])
 def test_gradients_X_tiled_kernel_ragged_shapes(kind, rows, n, d):
-    """>= 64 output rows take the shared-memory tiled cluster kernel (gpb_kernels.cu gradx_tile_kernel): rows not a multiple of 8,
+    """More than 8 output rows take the shared-memory tiled cluster kernel (gpb_kernels.cu gradx_tile_kernel): rows not a multiple of 8,
     points not a multiple of the 128-point chunk or of the 4 slices, every register cap; rectangular and symmetric (tmp + tmp.T)
-    forms of stationary.py:354-366 against the oracle, and row-wise against the one-warp-group-per-row kernel (< 64 rows)."""
+    forms of stationary.py:354-366 against the oracle, and row-wise against the one-warp-group-per-row kernel (<= 8 rows)."""
     rs = np.random.RandomState(rows + n + d)
     X, Z = rs.rand(rows, d), rs.rand(n, d)
     ls = 0.3 + rs.rand(d)
@@ -145,7 +145,7 @@ def test_gradients_X_tiled_kernel_ragged_shapes(kind, rows, n, d):
     ref = O.gradients_X(kind, G, X, Z, 1.3, ls)
     got = native.kern_gradients_X(kind, G, X, Z, 1.3, ls)
     assert_allclose(got, ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max())
-    small = np.vstack([native.kern_gradients_X(kind, G[a:a + 40], X[a:a + 40], Z, 1.3, ls) for a in range(0, rows, 40)])
+    small = np.vstack([native.kern_gradients_X(kind, G[a:a + 8], X[a:a + 8], Z, 1.3, ls) for a in range(0, rows, 8)])
     assert_allclose(got, small, rtol=1e-11, atol=1e-13 * np.abs(ref).max())
     Gs = rs.randn(rows, rows)
     ref = O.gradients_X(kind, Gs, X, None, 1.3, ls)
