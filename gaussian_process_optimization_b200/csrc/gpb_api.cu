@@ -6,6 +6,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "gpb_common.cuh"
 #include "gpb_kernels.cuh"
 
@@ -20,6 +22,13 @@ std::mutex &func_config_mutex() {
 }
 
 // environment knob read once (thread-safe: C++11 static initialisation)
+// NVTX range around every C-ABI call (header-only NVTX3: a no-op costing a pointer check unless a tool such as ncu --nvtx is attached)
+struct ApiRange {
+  explicit ApiRange(const char *name) { nvtxRangePushA(name); }
+  ~ApiRange() { nvtxRangePop(); }
+};
+#define GPB_RANGE(name) ApiRange api_range_(name)
+
 static int env_int(const char *name, int fallback) {
   const char *e = getenv(name);
   return e ? atoi(e) : fallback;
@@ -401,6 +410,7 @@ size_t gpb_model_workspace_bytes(int n_cap, int d, int p, int cand_block) {
 
 int gpb_model_create(gpb_model **out, int kind, int ard, int d, int p, int n_cap, int cand_block, void *workspace,
                      size_t workspace_bytes, void *stream) {
+  GPB_RANGE("gpb_model_create");
   GPB_REQUIRE(out != nullptr, "model_create: out is NULL");
   GPB_REQUIRE(kind == GPB_KERN_RBF || kind == GPB_KERN_MATERN52, "model_create: unknown kernel kind %d", kind);
   // 64 = what the predictive kernels (skinny moments, gradients_X) are instantiated for: a model that could be fitted but not queried
@@ -519,6 +529,7 @@ int gpb_model_destroy(gpb_model *m) {
 }
 
 int gpb_model_set_data(gpb_model *m, int n, const double *X, const double *Y, int dev) {
+  GPB_RANGE("gpb_model_set_data");
   GPB_REQUIRE(m && X && Y, "set_data: NULL argument");
   GPB_TRY(check_device(m, "set_data"));
   GPB_REQUIRE(n >= 1 && n <= m->n_cap, "set_data: n = %d exceeds the model capacity %d", n, m->n_cap);
@@ -578,6 +589,7 @@ int gpb_model_set_gower(gpb_model *m, int enable, const int *discrete, const dou
 }
 
 int gpb_model_set_theta(gpb_model *m, double variance, const double *lengthscale, double noise) {
+  GPB_RANGE("gpb_model_set_theta");
   GPB_REQUIRE(m && lengthscale, "set_theta: NULL argument");
   {
     // bit-identical hyper-parameters keep the factorisation (what makes gpb_model_append usable after GP.set_XY)
@@ -855,6 +867,7 @@ static int fit_core(gpb_model *m, int want_grad, double extra_jitter, double *ou
 }
 
 int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out) {
+  GPB_RANGE("gpb_model_fit");
   GPB_REQUIRE(m && out, "fit: NULL argument");
   GPB_TRY(check_device(m, "fit"));
   GPB_REQUIRE(m->have_data, "fit: set_data has not been called");
@@ -863,6 +876,7 @@ int gpb_model_fit(gpb_model *m, int want_grad, double extra_jitter, double *out)
 }
 
 int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall, int dev, int want_grad, double *out) {
+  GPB_RANGE("gpb_model_append");
   GPB_REQUIRE(m && Xnew && Yall && out, "append: NULL argument");
   GPB_TRY(check_device(m, "append"));
   GPB_REQUIRE(m->fitted && m->jitter == 0.0, "append: needs a model fitted (without extra jitter) for the current hyper-parameters");
@@ -928,6 +942,7 @@ int gpb_model_append(gpb_model *m, int b, const double *Xnew, const double *Yall
 }
 
 int gpb_model_get(gpb_model *m, const char *what, double *dst, int ld, int dev) {
+  GPB_RANGE("gpb_model_get");
   GPB_REQUIRE(m && what && dst, "get: NULL argument");
   GPB_TRY(check_device(m, "get"));
   const std::string w(what);
@@ -1101,6 +1116,7 @@ static int finish_staged(gpb_model *m) {
 }
 
 int gpb_model_predict(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *var, int dev) {
+  GPB_RANGE("gpb_model_predict");
   GPB_REQUIRE(m && Xc, "predict: NULL argument");
   GPB_TRY(check_device(m, "predict"));
   GPB_REQUIRE(m->fitted, "predict: model has not been fitted");
@@ -1117,6 +1133,7 @@ int gpb_model_predict(gpb_model *m, int mc, const double *Xc, int include_likeli
 }
 
 int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int include_likelihood, double *mu, double *cov, int dev) {
+  GPB_RANGE("gpb_model_predict_full_cov");
   GPB_REQUIRE(m && Xc && cov, "predict_full_cov: NULL argument");
   GPB_TRY(check_device(m, "predict_full_cov"));
   GPB_REQUIRE(m->fitted, "predict_full_cov: model has not been fitted");
@@ -1142,6 +1159,7 @@ int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int inclu
 }
 
 int gpb_model_predictive_gradients(gpb_model *m, int mc, const double *Xc, double *dmu, double *dvar, int dev) {
+  GPB_RANGE("gpb_model_predictive_gradients");
   GPB_REQUIRE(m && Xc, "predictive_gradients: NULL argument");
   GPB_TRY(check_device(m, "predictive_gradients"));
   GPB_REQUIRE(m->fitted, "predictive_gradients: model has not been fitted");
@@ -1177,6 +1195,7 @@ int gpb_model_fmin(gpb_model *m, double *fmin) {
 
 int gpb_model_acquisition(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df,
                           double *mean, double *sd, double *dmdx, double *dsdx, int dev) {
+  GPB_RANGE("gpb_model_acquisition");
   GPB_REQUIRE(m && Xc, "acquisition: NULL argument");
   GPB_TRY(check_device(m, "acquisition"));
   GPB_REQUIRE(m->fitted, "acquisition: model has not been fitted");
@@ -1242,6 +1261,7 @@ int gpb_model_set_penalizers(gpb_model *m, int transform, int nb, const double *
 }
 
 int gpb_model_acquisition_lp(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, double *f, double *df, int dev) {
+  GPB_RANGE("gpb_model_acquisition_lp");
   GPB_REQUIRE(m && Xc && f, "acquisition_lp: NULL argument");
   GPB_TRY(check_device(m, "acquisition_lp"));
   GPB_REQUIRE(m->fitted, "acquisition_lp: model has not been fitted");
@@ -1367,6 +1387,7 @@ static int acq_topk_check(gpb_model *m, int acq, int mc, int k, const char *what
 
 int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
                             long long index_offset, double *vals, long long *idx, double *pts, double *f, double *df) {
+  GPB_RANGE("gpb_model_acq_topk_full");
   GPB_REQUIRE(m && Xc && vals && idx, "acq_topk: NULL argument");
   GPB_TRY(acq_topk_check(m, acq, mc, k, "acq_topk"));
   const int d = m->d;
@@ -1401,6 +1422,7 @@ int gpb_model_acq_topk_full(gpb_model *m, int acq, double par, double fmin, int 
 
 int gpb_model_acq_topk_dev(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc_dev, int k, long long index_offset,
                            double *rows_dev, double *f_dev, double *df_dev) {
+  GPB_RANGE("gpb_model_acq_topk_dev");
   GPB_REQUIRE(m && Xc_dev && rows_dev, "acq_topk_dev: NULL argument");
   GPB_TRY(acq_topk_check(m, acq, mc, k, "acq_topk_dev"));
   AllocStream alloc_scope(m->stream);
@@ -1442,6 +1464,7 @@ int gpb_model_state_ptr(gpb_model *m, const char *what, void **ptr, size_t *coun
 }
 
 int gpb_model_adopt_state(gpb_model *m, double variance, const double *lengthscale, double noise, double jitter, int have_mask) {
+  GPB_RANGE("gpb_model_adopt_state");
   GPB_REQUIRE(m && lengthscale, "adopt_state: NULL argument");
   GPB_TRY(check_device(m, "adopt_state"));
   GPB_REQUIRE(m->have_data, "adopt_state: set_data has not been called (every rank holds the same X, Y)");
@@ -1464,6 +1487,7 @@ int gpb_model_adopt_state(gpb_model *m, double variance, const double *lengthsca
 
 int gpb_model_acq_topk(gpb_model *m, int acq, double par, double fmin, int mc, const double *Xc, int dev, int k,
                        long long index_offset, double *vals, long long *idx, double *pts) {
+  GPB_RANGE("gpb_model_acq_topk");
   return gpb_model_acq_topk_full(m, acq, par, fmin, mc, Xc, dev, k, index_offset, vals, idx, pts, nullptr, nullptr);
 }
 
@@ -1507,6 +1531,7 @@ static int kern_prepare(KernTmp &t, int d, int n, const double *X, int m, const 
 
 int gpb_kern_K(int kind, int d, int n, const double *X, int m, const double *X2, double variance, const double *lengthscale,
                int nls, double *K, int ldk, int dev, void *stream) {
+  GPB_RANGE("gpb_kern_K");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   AllocStream alloc_scope(s);
   GPB_REQUIRE(K != nullptr, "kern_K: K is NULL");
@@ -1574,6 +1599,7 @@ static int gower_prepare(GowerTmp &t, int d, int n, const double *X, int m, cons
 
 int gpb_kern_K_gower(int kind, int d, int n, const double *X, int m, const double *X2, double variance, const int *discrete,
                      const double *ranges, double *K, int ldk, int dev, void *stream) {
+  GPB_RANGE("gpb_kern_K_gower");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   AllocStream alloc_scope(s);
   GPB_REQUIRE(K != nullptr, "kern_K: K is NULL");
@@ -1604,6 +1630,7 @@ int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int 
 int gpb_kern_update_gradients_full_gower(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
                                          double variance, const double *lengthscale, int nls, const int *discrete,
                                          const double *ranges, double *out, int dev, void *stream) {
+  GPB_RANGE("gpb_kern_update_gradients_full_gower");
   // lengthscale terms: the reference keeps the Euclidean distance under the patch (stationary.py:227-238)
   GPB_TRY(gpb_kern_update_gradients_full(kind, d, n, X, m, X2, dL_dK, ld, variance, lengthscale, nls, out, dev, stream));
   // variance term: sum(K_gower * dL_dK) / variance (stationary.py:224 with the patched K)
@@ -1635,6 +1662,7 @@ int gpb_kern_update_gradients_full_gower(int kind, int d, int n, const double *X
 
 int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
                                    double variance, const double *lengthscale, int nls, double *out, int dev, void *stream) {
+  GPB_RANGE("gpb_kern_update_gradients_full");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   AllocStream alloc_scope(s);
   GPB_REQUIRE(dL_dK && out, "update_gradients_full: NULL argument");
@@ -1672,6 +1700,7 @@ int gpb_kern_update_gradients_full(int kind, int d, int n, const double *X, int 
 
 int gpb_kern_gradients_X(int kind, int d, int n, const double *X, int m, const double *X2, const double *dL_dK, int ld,
                          double variance, const double *lengthscale, int nls, double *out, int dev, void *stream) {
+  GPB_RANGE("gpb_kern_gradients_X");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   AllocStream alloc_scope(s);
   GPB_REQUIRE(dL_dK && out, "gradients_X: NULL argument");
@@ -1706,6 +1735,7 @@ int gpb_kern_gradients_X(int kind, int d, int n, const double *X, int m, const d
 // util.linalg
 // =====================================================================================================================
 int gpb_pdinv(int n, const double *A, int lda, double *L, double *Ai, double *Li, double *logdet, int dev, void *stream) {
+  GPB_RANGE("gpb_pdinv");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   AllocStream alloc_scope(s);
   GPB_REQUIRE(A && n >= 1 && lda >= n, "pdinv: bad arguments");
@@ -1772,6 +1802,7 @@ int gpb_pdinv(int n, const double *A, int lda, double *L, double *Ai, double *Li
 }
 
 int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, void *stream) {
+  GPB_RANGE("gpb_potrs");
   // (L L^T) X = B as X = M^T (M B) with M = L^-1 rebuilt by the triangular-inverse recursion (factor_trtri).
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   AllocStream alloc_scope(s);
@@ -1832,6 +1863,7 @@ int gpb_potrs(int n, const double *L, int ldl, double *B, int nrhs, int dev, voi
 }
 
 int gpb_potri(int n, const double *L, int ldl, double *Ai, int ldai, int dev, void *stream) {
+  GPB_RANGE("gpb_potri");
   // A^-1 = L^-T L^-1 from the Cholesky factor: triangular-inverse recursion (dtrtri) + the lower-tile product M^T M
   // (dlauum), then mirrored like GPy's symmetrify.
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1904,6 +1936,7 @@ int gpb_profile_gemm_last(double *ms, double *flops) { return gemm_profile_last(
 
 int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb, double beta,
               double *C, int ldc, void *stream) {
+  GPB_RANGE("gpb_dgemm");
   GPB_REQUIRE(A && B && C, "dgemm: NULL argument");
   GemmArgs g{A, lda, B, ldb, C, ldc, m, n, k, alpha, beta, 0, 0, 0};
   return gemm_launch(ta ? LAYOUT_COLK : LAYOUT_ROWK, tb ? LAYOUT_COLK : LAYOUT_ROWK, g, reinterpret_cast<cudaStream_t>(stream));
@@ -1913,6 +1946,7 @@ int gpb_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A
 int gpb_ozaki_dgemm(int ta, int tb, int m, int n, int k, double alpha, const double *A, int lda, const double *B, int ldb,
                     double beta, double *C, int ldc, int tri_out, int klo_mode, int khi_mode, int tri_a, int tri_b, int slices,
                     void *stream) {
+  GPB_RANGE("gpb_ozaki_dgemm");
   GPB_REQUIRE(A && B && C, "ozaki_dgemm: NULL argument");
   GemmArgs g{A, lda, B, ldb, C, ldc, m, n, k, alpha, beta, tri_out, klo_mode, khi_mode};
   return ozaki_gemm_launch(ta ? LAYOUT_COLK : LAYOUT_ROWK, tb ? LAYOUT_COLK : LAYOUT_ROWK, g, tri_a, tri_b, slices,
