@@ -1,5 +1,6 @@
 """Short program for ncu: EI value + gradient over a few candidate blocks with the int8 engine in modular mode (18 moduli in the
-predictive products) against the N = 16384 model -- the launch list shows where a block's time goes."""
+predictive products; argv[1] = 0 for the fp64 DMMA path) against the N = 16384 model -- the launch list shows where a block's time goes.
+  ncu --nvtx --nvtx-include "gpb_model_acq_topk_dev/" --metrics gpu__time_duration.sum --clock-control none --csv ... (both passes)"""
 import sys
 
 import numpy as np
@@ -11,7 +12,7 @@ from gaussian_process_optimization_b200 import native  # noqa: E402
 
 N, D = 16384, 16
 X, Y, ls = synth(N, D)
-native.set_ozaki(8192, 16)
+native.set_ozaki(int(sys.argv[1]) if len(sys.argv) > 1 else 8192, 16)      # 0: the fp64 DMMA path
 m = native.NativeModel("mat52", True, D, 1, n_cap=N, cand_block=2048)
 m.set_data(X, Y)
 m.set_theta(1.0, ls, 1e-6)
