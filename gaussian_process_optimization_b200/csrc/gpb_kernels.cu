@@ -450,12 +450,11 @@ int launch_kgrad(int kind, int fused, const double *XaT, int lda, const double *
 // Input gradients:  out1[c][q] = (s1 / l_q) sum_n (k'/r)_cn g1_cn (xs_cq - xs_nq)       [and the same with g2, s2]
 // with g_cn = G[c * ldg + n] (ldg == 0 broadcasts one row: the dL_dK = alpha^T case of core/gp.py:431-434)
 // (+ G[n * ldg + c] when add_t: the `tmp + tmp.T` of stationary.py:359-361 when X2 is None).
-// One warp per output row c; lanes stride over n (coalesced in the dimension-major layout); per-lane accumulators for all
-// dimensions live in registers (DCAP), then a fixed-order warp reduction.
+// gradx_kernel (up to 8 rows): GX_WPC warps per output row c; lanes stride over n (coalesced in the dimension-major layout);
+// per-lane accumulators for all dimensions live in registers (DCAP), then a fixed-order warp + cross-warp reduction.
+// gradx_tile_kernel (more rows) follows below.
 // ---------------------------------------------------------------------------------------------------------------------
-// GX_WPC warps share one output row: with one warp per row a block of 2048 candidates put 14 warps on an SM, each walking all N
-// training points through a dependent chain (2.8 ms per block at N = 16384, 22% of the int8 engine's EI pass: profiles/
-// r2v_launches_ei_engine.md).  The warps of a row take interleaved 32-point slices; their sums are added in warp order (fixed).
+// The warps of a row take interleaved 32-point slices; their sums are added in warp order (fixed).
 constexpr int GX_WPC = 4;
 
 template <int KIND, int DCAP, int TWO>
