@@ -166,7 +166,17 @@ def _worker(rank, world, port, out):
     a, b = sharded.divide_candidates(X.shape[0], rank, world)
     sc = sharded.ShardedAnchorScorer(score_fn=score)
     vals, idx, pts = sc.topk(X[a:b], 5, index_offset=a)
-    np.savez(out % rank, vals=vals, idx=idx, pts=pts)
+    # the same exchange from a (k, d + 2) row buffer [f, global index, coordinates] as acq_topk_dev leaves it (the gloo branch of
+    # all_gather_topk_device; one slot of rank 1 left empty: index -1 rows must not survive the merge)
+    import torch
+    s_loc = score(X[a:b])
+    o = np.lexsort((np.arange(a, b), s_loc))[:5]
+    rows = np.column_stack([s_loc[o], (a + o).astype(np.float64), X[a:b][o]])
+    if rank == 1:
+        rows[-1] = np.nan
+        rows[-1, 1] = -1.0
+    dv, di, dp = sharded.all_gather_topk_device(torch.from_numpy(rows), 5)
+    np.savez(out % rank, vals=vals, idx=idx, pts=pts, dvals=dv, didx=di, dpts=dp)
     dist.destroy_process_group()
 
 
@@ -185,6 +195,9 @@ def test_sharded_topk_gloo_world_size_2(tmp_path):
         assert np.array_equal(z["idx"], order)
         assert_allclose(z["vals"], s[order])
         assert_allclose(z["pts"], X[order])
+        assert np.array_equal(z["didx"], order)
+        assert_allclose(z["dvals"], s[order])
+        assert_allclose(z["dpts"], X[order])
 
 
 # ---------------------------------------------------------------------------------------------------------------------
