@@ -1,0 +1,78 @@
+"""Seeded random sweep of the whole path against the oracle: odd training sizes around the 128-row padding and the 1-row / 1-column
+corners, every input dimension class (register caps 4 / 8 / 16 / 32 and the wide kernels), both kernels, ARD and isotropic, three
+noise levels, candidate counts that fall on every route (fused M <= 8 kernel, the one-group gradient kernel, the tiled cluster
+kernel, more than one candidate block).  Each case: NLL + gradients (exact_gaussian_inference.py:37-74), predict (gp.py:278-330),
+predictive gradients (gp.py:410-455), EI and LCB value + gradient (EI.py:32-51, LCB.py:35-52), top-5 (anchor_points_generator.py:61).
+The bars are north_star's (1e-9 on values, 1e-7 on gradients) scaled by the cond * eps allowance the other parity tests use."""
+import os
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from gaussian_process_optimization_b200 import native
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed):
+    rs = np.random.RandomState(1000 + seed)
+    N = int(rs.choice([1, 2, 3, 17, 64, 127, 128, 129, 200, 255, 256, 257, 300, 383, 385, 500]))
+    D = int(rs.choice([1, 2, 3, 4, 5, 7, 8, 9, 13, 16, 17, 20, 31, 32, 33, 48]))
+    kind = "rbf" if rs.rand() < 0.5 else "mat52"
+    ard = bool(rs.rand() < 0.6)
+    noise = float(rs.choice([1e-6, 1e-2, 0.3]))
+    M = int(rs.choice([1, 2, 5, 8, 9, 16, 63, 64, 65, 100, 129, 260]))
+    X = rs.uniform(0, 1, (N, D))
+    w = rs.randn(D)
+    Y = np.sin(2.0 * X @ w / np.sqrt(D))[:, None] + 0.05 * rs.randn(N, 1)
+    if N > 1:
+        Y = (Y - Y.mean()) / Y.std()
+    ls = (0.4 + rs.rand(D)) * np.sqrt(D) if ard else np.array([(0.4 + rs.rand()) * np.sqrt(D)])
+    var = float(0.5 + 2.0 * rs.rand())
+    Xc = rs.uniform(0, 1, (M, D))
+    return N, D, kind, ard, noise, M, X, Y, ls, var, Xc
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), int(os.environ.get("GPB_FUZZ_LAST", "64"))))
+def test_random_case_matches_the_oracle(seed):
+    N, D, kind, ard, noise, M, X, Y, ls, var, Xc = _case(seed)
+    tag = "seed %d: N=%d D=%d %s ard=%s noise=%g M=%d" % (seed, N, D, kind, ard, noise, M)
+    l_ref, g_ref, _ = O.log_likelihood_and_gradients(kind, X, Y, var, ls, noise, ard=ard, native=True)
+    st = O.GPState(kind, X, Y, var, ls, noise, ard=ard)
+    w = np.linalg.eigvalsh(O.K(kind, X, None, var, ls if ard else np.full(D, ls[0])) + (noise + 1e-8) * np.eye(N))
+    ct = max(1.0, w[-1] / w[0] * 2.2e-16 / 1e-12)          # same allowance as tests/test_gpu_native.py::_cond_tol
+    m = native.NativeModel(kind, ard, D, 1, n_cap=max(N, 128), cand_block=128)
+    try:
+        m.set_data(X, Y)
+        m.set_theta(var, ls, noise)
+        info, logL, g = m.fit(True)
+        assert info == 0, tag
+        assert_allclose(logL, l_ref, rtol=1e-9 * ct, atol=1e-9 * ct, err_msg=tag)
+        assert_allclose(g, g_ref, rtol=1e-7 * ct, atol=1e-9 * ct * max(1.0, np.abs(g_ref).max()), err_msg=tag)
+        mu_ref, v_ref = O.predict(kind, st.post, st.X, Xc, var, ls, noise, ard=ard)
+        mu, v = m.predict(Xc)
+        assert_allclose(mu, mu_ref, rtol=1e-9 * ct, atol=1e-10 * ct, err_msg=tag)
+        assert_allclose(v, v_ref, rtol=1e-9 * ct, atol=1e-11 * ct * var, err_msg=tag)
+        fmin = m.fmin()
+        assert_allclose(fmin, st.get_fmin(), rtol=1e-9 * ct, atol=1e-10 * ct, err_msg=tag)
+        for acq, par in (("EI", 0.01), ("LCB", 2.0)):
+            f_ref, df_ref = st.acquisition(acq, Xc, with_gradients=True, native=True)
+            r = m.acquisition(acq, par, fmin, Xc, with_gradients=True)
+            assert_allclose(r["f"], f_ref, rtol=1e-7 * ct, atol=1e-11 * ct, err_msg=tag + " " + acq)
+            assert_allclose(r["df"], df_ref, rtol=1e-6 * ct, atol=1e-9 * ct * max(1e-3, np.abs(df_ref).max()), err_msg=tag + " " + acq)
+            r0 = m.acquisition(acq, par, fmin, Xc, with_gradients=False)
+            assert_allclose(r0["f"], f_ref, rtol=1e-7 * ct, atol=1e-11 * ct, err_msg=tag + " value-only " + acq)
+        f_ref = st.acquisition("LCB", Xc, with_gradients=False, native=True)
+        k = min(5, M)
+        vals, idx, pts = m.acq_topk("LCB", 2.0, fmin, Xc, k)
+        order = np.argsort(np.asarray(f_ref).ravel(), kind="stable")[:k]
+        # near-ties may swap under the tolerance: compare the selected values, and the indices where the gaps are resolvable
+        assert_allclose(vals, np.asarray(f_ref).ravel()[order], rtol=1e-8 * ct, atol=1e-11 * ct, err_msg=tag)
+        srt = np.sort(np.asarray(f_ref).ravel())
+        if M == 1 or np.min(np.diff(srt[:k + 1])) > 1e-7 * ct * max(1.0, np.abs(srt[:k + 1]).max()):
+            assert np.array_equal(idx, order), tag
+            assert np.array_equal(pts, Xc[order]), tag
+    finally:
+        m.close()
