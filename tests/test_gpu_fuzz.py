@@ -76,3 +76,59 @@ def test_random_case_matches_the_oracle(seed):
             assert np.array_equal(pts, Xc[order]), tag
     finally:
         m.close()
+
+
+def _kern_case(seed):
+    rs = np.random.RandomState(5000 + seed)
+    n = int(rs.choice([1, 2, 7, 8, 9, 31, 64, 100, 127, 128, 129, 257, 300]))
+    m = int(rs.choice([1, 3, 8, 9, 20, 64, 65, 128, 131, 260]))
+    d = int(rs.choice([1, 2, 3, 4, 5, 8, 9, 10, 16, 17, 20, 32, 33, 48, 64]))
+    kind = "rbf" if rs.rand() < 0.5 else "mat52"
+    ard = bool(rs.rand() < 0.6)
+    X, Z = rs.randn(n, d), rs.randn(m, d)
+    ls = (0.6 + rs.rand(d)) * np.sqrt(d) if ard else np.array([(0.6 + rs.rand()) * np.sqrt(d)])
+    var = float(0.3 + 2.0 * rs.rand())
+    return rs, n, m, d, kind, ard, X, Z, ls, var
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), int(os.environ.get("GPB_FUZZ_LAST", "64"))))
+def test_random_kernel_calls_match_the_oracle(seed):
+    """The stateless kernel entry points -- K, update_gradients_full, gradients_X (stationary.py:107-140,218-238,271-278,354-364),
+    square (X2 None: the tmp + tmp.T form) and rectangular -- on random shapes, against the oracle's restatement with the reference's
+    own compiled lengthscale loop."""
+    rs, n, m, d, kind, ard, X, Z, ls, var = _kern_case(seed)
+    tag = "seed %d: n=%d m=%d d=%d %s ard=%s" % (seed, n, m, d, kind, ard)
+    lsf = ls if ard else np.full(d, ls[0])
+    for X2, cols in ((None, n), (Z, m)):
+        G = rs.randn(n, cols)
+        ref = O.K(kind, X, X2, var, ls, ard=ard)
+        assert_allclose(native.kern_K(kind, X, X2, var, ls), ref, rtol=1e-9, atol=1e-300, err_msg=tag)
+        dv, dl = native.kern_update_gradients_full(kind, G, X, X2, var, ls)
+        rv, rl = O.update_gradients_full(kind, G, X, X2, var, ls, ard=ard, native=True)
+        sc = np.abs(G).sum() * var
+        assert_allclose(dv, rv, rtol=1e-7, atol=1e-12 * sc, err_msg=tag)
+        assert_allclose(dl, np.atleast_1d(rl), rtol=1e-7, atol=1e-12 * sc, err_msg=tag)
+        ref = O.gradients_X(kind, G, X, X2, var, ls, ard=ard, native=True)
+        got = native.kern_gradients_X(kind, G, X, X2, var, lsf)      # gradients_X divides by lengthscale**2 per column either way
+        assert_allclose(got, ref, rtol=1e-7, atol=1e-11 * max(1e-30, np.abs(ref).max()), err_msg=tag)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(24, int(os.environ.get("GPB_FUZZ_LAST", "24")))))
+def test_random_pdinv_potrs_potri_match_lapack(seed):
+    """pdinv / dpotrs / dpotri (util/linalg.py:116-145,193-214) on random SPD matrices of random order (leaf, padded, recursion)."""
+    rs = np.random.RandomState(9000 + seed)
+    n = int(rs.choice([1, 2, 5, 64, 127, 128, 129, 255, 256, 257, 383, 500, 640]))
+    B = rs.randn(n, n)
+    A = B @ B.T / n + (0.5 + rs.rand()) * np.eye(n)
+    rc, Ai, L, Li, logdet = native.pdinv(A)
+    assert rc == 0
+    Ai_ref, L_ref, Li_ref, logdet_ref = O.pdinv(A)
+    cond = np.linalg.cond(A)
+    tol = 1e-11 * max(1.0, cond)
+    assert_allclose(np.tril(L), L_ref, rtol=0, atol=tol * np.abs(L_ref).max())
+    assert_allclose(np.tril(Li), Li_ref, rtol=0, atol=tol * np.abs(Li_ref).max())
+    assert_allclose(Ai, Ai_ref, rtol=0, atol=tol * np.abs(Ai_ref).max())
+    assert_allclose(logdet, logdet_ref, rtol=1e-11, atol=1e-11)
+    rhs = rs.randn(n, int(rs.choice([1, 2, 5])))
+    assert_allclose(native.potrs(L_ref, rhs), O.dpotrs(L_ref, rhs)[0], rtol=0, atol=tol * np.abs(rhs).max() * np.abs(Ai_ref).max() * n)
+    assert_allclose(native.potri(L_ref), Ai_ref, rtol=0, atol=tol * np.abs(Ai_ref).max())
