@@ -1005,7 +1005,9 @@ static inline bool ozaki_predict(const gpb_model *m, int np, int cpad) {
   return m->engine_ok && ozaki_min_n() > 0 && np >= ozaki_min_n() && cpad >= 1024;
 }
 
-static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int level, int include_likelihood) {
+// allow_fused = false: the caller reads the block's intermediates afterwards (XcT, and Vt in its row-per-candidate layout -- the fused
+// M <= 8 kernel keeps neither: it never forms XcT and parks k'/r and M k* in rows 0-7 / 8-15 of Vt)
+static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int level, int include_likelihood, bool allow_fused = true) {
   const int n = m->n, np = m->np, d = m->d, p = m->p;
   const int cpad = round_up(mcb, TILE);
   cudaStream_t s = m->stream;
@@ -1022,7 +1024,7 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   // LockstepEvaluator): everything from the covariance row to the four reductions in ONE persistent cooperative kernel
   // (gpb_skinny.cu) -- two streaming passes over the triangle of M.  Kx and U live in the first 16 rows of KxT, Dk and Z in the first 16 of Vt.
   static const int fused_on = env_int("GPB_SKINNY_FUSED", 1);
-  if (mcb <= 8 && p == 1 && !m->gower && fused_on && level >= 1)
+  if (allow_fused && mcb <= 8 && p == 1 && !m->gower && fused_on && level >= 1)
     return launch_skinny_fused(m->kind, m->f.Mi, np, n, d, mcb, level, m->XsT, m->Xc, m->ls_dev, m->inv_ls_dev, m->alpha, m->variance,
                                m->variance + (include_likelihood ? m->noise : 0.0), m->KxT, m->Vt, m->Vt + (size_t)8 * np, m->KxT + (size_t)8 * np, m->f.part, m->sk_part3,
                                m->mu, m->var, m->dmu, m->dvar, s);
@@ -1141,7 +1143,7 @@ int gpb_model_predict_full_cov(gpb_model *m, int mc, const double *Xc, int inclu
   const int cpad = round_up(mc, TILE), np = m->np;
   cudaStream_t s = m->stream;
   AllocStream alloc_scope(s);
-  GPB_TRY(predict_block(m, Xc, mc, dev, 1, include_likelihood));
+  GPB_TRY(predict_block(m, Xc, mc, dev, 1, include_likelihood, false));
   // cov = Kxx - tmp^T tmp (+ noise I)      posterior.py:281-284, gaussian.py:104-107
   DevBuf cbuf;
   GPB_TRY(cbuf.alloc((size_t)cpad * cpad * sizeof(double)));

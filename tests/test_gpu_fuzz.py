@@ -55,6 +55,13 @@ def test_random_case_matches_the_oracle(seed):
         mu, v = m.predict(Xc)
         assert_allclose(mu, mu_ref, rtol=1e-9 * ct, atol=1e-10 * ct, err_msg=tag)
         assert_allclose(v, v_ref, rtol=1e-9 * ct, atol=1e-11 * ct * var, err_msg=tag)
+        # full covariance of one candidate block (posterior.py:281-284): 1 .. 8 rows must not take the fused kernel, whose
+        # intermediates are not laid out for it (found by this sweep)
+        mc = min(M, 128)
+        mu_r, cov_r = O.predict(kind, st.post, st.X, Xc[:mc], var, ls, noise, ard=ard, full_cov=True)
+        mu_f, cov = m.predict_full_cov(Xc[:mc])
+        assert_allclose(mu_f, mu_r, rtol=1e-9 * ct, atol=1e-10 * ct, err_msg=tag)
+        assert_allclose(cov, cov_r, rtol=1e-8 * ct, atol=1e-10 * ct * var, err_msg=tag)
         fmin = m.fmin()
         assert_allclose(fmin, st.get_fmin(), rtol=1e-9 * ct, atol=1e-10 * ct, err_msg=tag)
         for acq, par in (("EI", 0.01), ("LCB", 2.0)):
@@ -132,3 +139,51 @@ def test_random_pdinv_potrs_potri_match_lapack(seed):
     rhs = rs.randn(n, int(rs.choice([1, 2, 5])))
     assert_allclose(native.potrs(L_ref, rhs), O.dpotrs(L_ref, rhs)[0], rtol=0, atol=tol * np.abs(rhs).max() * np.abs(Ai_ref).max() * n)
     assert_allclose(native.potri(L_ref), Ai_ref, rtol=0, atol=tol * np.abs(Ai_ref).max())
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(32, int(os.environ.get("GPB_FUZZ_LAST", "32")))))
+def test_random_growth_by_appends_matches_a_fresh_oracle_fit(seed):
+    """GPModel.updateModel with one or a few more rows per BO step (gpmodel.py:78-93) served by gpb_model_append: random start sizes and
+    increments that cross the 128-row padding, targets re-normalised at every step; after the last step the log-likelihood,
+    gradients, full-covariance prediction (gp.py:278-330, full_cov=True) and predictive gradients (gp.py:410-455) against the
+    oracle's fit of the final data."""
+    rs = np.random.RandomState(7000 + seed)
+    D = int(rs.choice([1, 2, 3, 6, 16, 20]))
+    kind = "rbf" if rs.rand() < 0.5 else "mat52"
+    ard = bool(rs.rand() < 0.5)
+    noise = float(rs.choice([1e-3, 1e-2, 0.1]))
+    n0 = int(rs.choice([1, 5, 100, 120, 127, 128, 250, 255]))
+    steps = [int(b) for b in rs.choice([1, 1, 2, 3, 8, 9, 30], size=int(rs.randint(1, 5)))]
+    N = n0 + sum(steps)
+    X = rs.uniform(0, 1, (N, D))
+    Y = np.sin(3.0 * X.sum(axis=1) / np.sqrt(D))[:, None] + 0.05 * rs.randn(N, 1)
+    ls = (0.4 + rs.rand(D)) * np.sqrt(D) if ard else np.array([(0.4 + rs.rand()) * np.sqrt(D)])
+    var = float(0.5 + rs.rand())
+    tag = "seed %d: D=%d %s ard=%s noise=%g n0=%d steps=%s" % (seed, D, kind, ard, noise, n0, steps)
+    m = native.NativeModel(kind, ard, D, 1, n_cap=512, cand_block=128)
+    try:
+        m.set_data(X[:n0], Y[:n0])
+        m.set_theta(var, ls, noise)
+        assert m.fit(False)[0] == 0, tag
+        n = n0
+        for i, b in enumerate(steps):
+            Yn = Y[:n + b] * (1.0 + 0.01 * i)
+            info, logL, g = m.append(X[n:n + b], Yn, want_grad=(i == len(steps) - 1))
+            n += b
+            assert info == 0 and m.n == n, tag
+        l_ref, g_ref, post = O.log_likelihood_and_gradients(kind, X, Yn, var, ls, noise, ard=ard, native=True)
+        w = np.linalg.eigvalsh(O.K(kind, X, None, var, ls if ard else np.full(D, ls[0])) + (noise + 1e-8) * np.eye(N))
+        ct = max(1.0, w[-1] / w[0] * 2.2e-16 / 1e-12)
+        assert_allclose(logL, l_ref, rtol=1e-9 * ct, atol=1e-9 * ct, err_msg=tag)
+        assert_allclose(g, g_ref, rtol=1e-7 * ct, atol=1e-9 * ct * max(1.0, np.abs(g_ref).max()), err_msg=tag)
+        Xc = rs.uniform(0, 1, (int(rs.choice([1, 4, 9, 40])), D))
+        mu_r, cov_r = O.predict(kind, post, X, Xc, var, ls, noise, ard=ard, full_cov=True)
+        mu, cov = m.predict_full_cov(Xc)
+        assert_allclose(mu, mu_r, rtol=1e-9 * ct, atol=1e-10 * ct, err_msg=tag)
+        assert_allclose(cov, cov_r, rtol=1e-8 * ct, atol=1e-10 * ct * var, err_msg=tag)
+        dm_r, dv_r = O.predictive_gradients(kind, post, X, Xc, var, ls, ard=ard, native=True)
+        dm, dv = m.predictive_gradients(Xc)
+        assert_allclose(dm, dm_r, rtol=1e-7 * ct, atol=1e-9 * ct * max(1e-3, np.abs(dm_r).max()), err_msg=tag)
+        assert_allclose(dv, dv_r, rtol=1e-7 * ct, atol=1e-9 * ct * max(1e-3, np.abs(dv_r).max()), err_msg=tag)
+    finally:
+        m.close()
