@@ -187,3 +187,146 @@ def test_random_growth_by_appends_matches_a_fresh_oracle_fit(seed):
         assert_allclose(dv, dv_r, rtol=1e-7 * ct, atol=1e-9 * ct * max(1e-3, np.abs(dv_r).max()), err_msg=tag)
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(32, int(os.environ.get("GPB_FUZZ_LAST", "32")))))
+def test_random_interleaved_calls_and_buffer_kinds_agree(seed):
+    """One model, a random sequence of entry points with candidate counts on every route, host and device buffers mixed: every
+    answer must equal -- bitwise, value and gradient -- what the same call gives on a freshly fitted twin that has seen nothing
+    else (no entry point may leave state behind that changes another one's result), and the host-buffer and device-buffer forms of
+    acquisition / acq_topk_full / acq_topk_dev must agree bitwise with each other."""
+    import torch
+    rs = np.random.RandomState(11000 + seed)
+    N = int(rs.choice([40, 128, 200, 300]))
+    D = int(rs.choice([2, 5, 16, 20, 40]))
+    kind = "rbf" if rs.rand() < 0.5 else "mat52"
+    X = rs.uniform(0, 1, (N, D))
+    Y = np.sin(3.0 * X.sum(axis=1) / np.sqrt(D))[:, None] + 0.05 * rs.randn(N, 1)
+    ls = (0.4 + rs.rand(D)) * np.sqrt(D)
+    tag = "seed %d: N=%d D=%d %s" % (seed, N, D, kind)
+
+    def fresh():
+        mm = native.NativeModel(kind, True, D, 1, n_cap=384, cand_block=128)
+        mm.set_data(X, Y)
+        mm.set_theta(1.2, ls, 1e-2)
+        assert mm.fit(True)[0] == 0
+        return mm
+
+    m = fresh()
+    try:
+        fmin = m.fmin()
+        for step in range(8):
+            M = int(rs.choice([1, 3, 8, 9, 50, 128, 131, 300]))
+            Xc = rs.uniform(0, 1, (M, D))
+            Xd = torch.from_numpy(Xc).cuda()
+            op = int(rs.randint(0, 6))
+            twin = fresh()
+            try:
+                if op == 0:
+                    a, b = m.predict(Xc), twin.predict(Xc)
+                    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (tag, step, "predict", M)
+                elif op == 1:
+                    a, b = m.predictive_gradients(Xc), twin.predictive_gradients(Xc)
+                    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (tag, step, "predictive_gradients", M)
+                elif op == 2:
+                    mc = min(M, 128)
+                    a, b = m.predict_full_cov(Xc[:mc]), twin.predict_full_cov(Xc[:mc])
+                    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (tag, step, "predict_full_cov", mc)
+                elif op == 3:
+                    acq, par = (("EI", 0.01), ("LCB", 2.0))[int(rs.randint(0, 2))]
+                    a = m.acquisition(acq, par, fmin, Xc, with_gradients=True, want_moments=True)
+                    b = twin.acquisition(acq, par, fmin, Xc, with_gradients=True, want_moments=True)
+                    c = m.acquisition(acq, par, fmin, Xd, with_gradients=True, want_moments=True)
+                    for key in ("f", "df", "m", "s", "dmdx", "dsdx"):
+                        assert np.array_equal(a[key], b[key]), (tag, step, acq, key, M)
+                        assert np.array_equal(a[key], c[key].cpu().numpy()), (tag, step, acq, key, M, "device buffers")
+                elif op == 4:
+                    k = min(5, M)
+                    a = m.acq_topk_full("EI", 0.01, fmin, Xc, k, index_offset=7)
+                    b = twin.acq_topk_full("EI", 0.01, fmin, Xc, k, index_offset=7)
+                    c = m.acq_topk_full("EI", 0.01, fmin, Xd, k, index_offset=7)
+                    rows, f, df = m.acq_topk_dev("EI", 0.01, fmin, Xd, k, index_offset=7, with_gradients=True)
+                    torch.cuda.synchronize()
+                    for i in range(3):
+                        assert np.array_equal(a[i], b[i]) and np.array_equal(a[i], c[i]), (tag, step, "acq_topk_full", i, M)
+                    for i in (3, 4):
+                        assert np.array_equal(a[i], b[i]) and np.array_equal(a[i], c[i].cpu().numpy()), (tag, step, "acq_topk_full", i, M)
+                    rows = rows.cpu().numpy()
+                    assert np.array_equal(rows[:, 0], a[0]) and np.array_equal(rows[:, 1].astype(np.int64), a[1]), (tag, step, "acq_topk_dev", M)
+                    assert np.array_equal(rows[:, 2:], a[2]) and np.array_equal(f.cpu().numpy(), a[3]) and np.array_equal(df.cpu().numpy(), a[4])
+                else:
+                    a, b = m.acq_topk("LCB", 2.0, fmin, Xc, min(5, M)), twin.acq_topk("LCB", 2.0, fmin, Xd, min(5, M))
+                    for i in range(3):
+                        assert np.array_equal(a[i], b[i]), (tag, step, "acq_topk host vs device", i, M)
+            finally:
+                twin.close()
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(24, int(os.environ.get("GPB_FUZZ_LAST", "24")))))
+def test_random_host_mirror_models_agree_with_the_oracle_backend(seed):
+    """The GPy-shaped host classes once on libgpb200.so and once on the CPU oracle (tests/oracle_backend.py), random model and
+    data: objective and gradient vector (core/gp.py:258-271 through the paramz transforms), predict with and without the full
+    covariance and with / without the likelihood (gp.py:278-354), predictive_gradients (gp.py:410-455), after construction, after
+    a parameter write and after set_XY with more rows; then GPyOpt's GPModel.predict_withGradients / get_fmin (gpmodel.py:95-142)."""
+    import oracle_backend as OB
+    from gaussian_process_optimization_b200 import GPy, GPyOpt
+    rs = np.random.RandomState(13000 + seed)
+    N = int(rs.choice([3, 20, 127, 129, 200]))
+    D = int(rs.choice([1, 2, 4, 6, 17]))
+    kname = "RBF" if rs.rand() < 0.5 else "Matern52"
+    ard = bool(rs.rand() < 0.6)
+    X = rs.uniform(-1, 2, (N + 9, D))
+    Y = np.sin(X.sum(axis=1))[:, None] + 0.1 * rs.randn(N + 9, 1)
+    noise0 = float(rs.choice([1e-3, 1e-2, 0.5]))
+    tag = "seed %d: N=%d D=%d %s ard=%s" % (seed, N, D, kname, ard)
+
+    def pair():
+        ls0 = (0.5 + rs.rand(D if ard else 1)) * np.sqrt(D)
+        v0 = 0.5 + rs.rand()
+        ka = getattr(GPy.kern, kname)(D, variance=v0, lengthscale=ls0.copy(), ARD=ard)
+        kb = getattr(GPy.kern, kname)(D, variance=v0, lengthscale=ls0.copy(), ARD=ard)
+        return (GPy.models.GPRegression(X[:N], Y[:N], kernel=ka, noise_var=noise0), OB.oracle_gp_regression(X[:N], Y[:N], kb, noise0))
+
+    def compare(a, b, what):
+        assert_allclose(a.log_likelihood(), b.log_likelihood(), rtol=1e-8, atol=1e-8, err_msg=tag + what)
+        ga, gb = a.objective_function_gradients(), b.objective_function_gradients()
+        assert_allclose(ga, gb, rtol=1e-6, atol=1e-8 * max(1.0, np.abs(gb).max()), err_msg=tag + what)
+        for M in (1, 5, 8, 30):
+            Xn = rs.uniform(-1, 2, (M, D))
+            for full_cov in (False, True):
+                for lik in (True, False):
+                    pa = a.predict(Xn, full_cov=full_cov, include_likelihood=lik)
+                    pb = b.predict(Xn, full_cov=full_cov, include_likelihood=lik)
+                    assert pa[0].shape == pb[0].shape and pa[1].shape == pb[1].shape, tag + what
+                    assert_allclose(pa[0], pb[0], rtol=1e-7, atol=1e-9, err_msg=tag + what)
+                    assert_allclose(pa[1], pb[1], rtol=1e-6, atol=1e-9, err_msg=tag + what + " full_cov=%s lik=%s M=%d" % (full_cov, lik, M))
+            da, db = a.predictive_gradients(Xn), b.predictive_gradients(Xn)
+            assert_allclose(da[0], db[0], rtol=1e-6, atol=1e-8 * max(1e-3, np.abs(db[0]).max()), err_msg=tag + what)
+            assert_allclose(da[1], db[1], rtol=1e-6, atol=1e-8 * max(1e-3, np.abs(db[1]).max()), err_msg=tag + what)
+
+    a, b = pair()
+    compare(a, b, " after construction")
+    x = a.optimizer_array.copy() + 0.3 * rs.randn(a.optimizer_array.size)
+    a.optimizer_array = x
+    b.optimizer_array = x
+    compare(a, b, " after a parameter write")
+    a.set_XY(X, Y)
+    b.set_XY(X, Y)
+    compare(a, b, " after set_XY")
+    # GPyOpt's adaptor
+    ga = GPyOpt.models.GPModel(optimize_restarts=1, verbose=False, exact_feval=bool(rs.rand() < 0.5), ARD=ard, max_iters=0)
+    gb = OB.OracleGPModel(optimize_restarts=1, verbose=False, exact_feval=ga.exact_feval, ARD=ard, max_iters=0)
+    ga.updateModel(X[:N], Y[:N], None, None)
+    gb.updateModel(X[:N], Y[:N], None, None)
+    kb = gb.model.kern
+    Kb = O.K(kb._kind, gb.model.X, None, float(kb.variance.values[0]), kb.lengthscale.values, kb.ARD)
+    wv = np.linalg.eigvalsh(Kb + (float(gb.model.Gaussian_noise.variance.values[0]) + 1e-8) * np.eye(N))
+    ct = max(1.0, wv[-1] / wv[0] * 2.2e-16 / 1e-12)          # exact_feval fixes the noise at 1e-6: cond(Ky) * eps allowance as elsewhere
+    assert_allclose(ga.get_fmin(), gb.get_fmin(), rtol=1e-7 * ct, atol=1e-9 * ct, err_msg=tag)
+    for M in (1, 4, 20):
+        Xn = rs.uniform(-1, 2, (M, D))
+        ra, rb = ga.predict_withGradients(Xn), gb.predict_withGradients(Xn)
+        for u, w in zip(ra, rb):
+            assert_allclose(u, w, rtol=1e-6 * ct, atol=1e-8 * ct * max(1e-3, np.abs(w).max()), err_msg=tag + " GPModel M=%d" % M)
