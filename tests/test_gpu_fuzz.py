@@ -330,3 +330,99 @@ def test_random_host_mirror_models_agree_with_the_oracle_backend(seed):
         ra, rb = ga.predict_withGradients(Xn), gb.predict_withGradients(Xn)
         for u, w in zip(ra, rb):
             assert_allclose(u, w, rtol=1e-6 * ct, atol=1e-8 * ct * max(1e-3, np.abs(w).max()), err_msg=tag + " GPModel M=%d" % M)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(24, int(os.environ.get("GPB_FUZZ_LAST", "24")))))
+def test_random_gower_and_two_output_models_match_the_oracle(seed):
+    """The reference's mixed-variable product kernel (stationary.py:116-135; only the variance gradient sees it, :224) with random
+    splits into continuous and discrete dimensions, and models with two output columns (exact_gaussian_inference.py:62,70),
+    N equal to the model's capacity and candidate counts equal to / one past its candidate block."""
+    rs = np.random.RandomState(17000 + seed)
+    N = int(rs.choice([2, 30, 128, 129, 256]))
+    D = int(rs.choice([2, 3, 5, 8, 12]))
+    kind = "rbf" if rs.rand() < 0.5 else "mat52"
+    ard = bool(rs.rand() < 0.5)
+    use_gower = bool(seed % 2 == 0)
+    P = 1 if use_gower else 2
+    X = rs.uniform(0, 1, (N, D))
+    gower = None
+    if use_gower:
+        nd = int(rs.randint(1, D))
+        disc = sorted(int(i) for i in rs.choice(D, size=nd, replace=False))
+        cont = [i for i in range(D) if i not in disc]
+        for i in disc:
+            X[:, i] = rs.randint(0, 3, N)
+        gower = (cont, disc, [float(0.5 + 2.0 * rs.rand()) for _ in cont])
+    Y = np.stack([np.sin(3.0 * X.sum(axis=1) / D + j) for j in range(P)], 1) + 0.05 * rs.randn(N, P)
+    ls = (0.4 + rs.rand(D)) if ard else np.array([0.4 + rs.rand()])
+    var, noise = float(0.6 + 0.5 * rs.rand()), float(rs.choice([1e-2, 0.2]))
+    tag = "seed %d: N=%d D=%d %s ard=%s gower=%s P=%d" % (seed, N, D, kind, ard, gower, P)
+    cb = 128
+    m = native.NativeModel(kind, ard, D, P, n_cap=N, cand_block=cb)          # N == capacity
+    try:
+        m.set_data(X, Y)
+        if gower is not None:
+            m.set_gower(gower)
+        m.set_theta(var, ls, noise)
+        info, logL, g = m.fit(True)
+        assert info == 0, tag
+        l_ref, g_ref, post = O.log_likelihood_and_gradients(kind, X, Y, var, ls, noise, ard=ard, native=True, gower=gower)
+        assert_allclose(logL, l_ref, rtol=1e-9, atol=1e-9, err_msg=tag)
+        assert_allclose(g, g_ref, rtol=1e-7, atol=1e-9 * max(1.0, np.abs(g_ref).max()), err_msg=tag)
+        for M in (1, 7, cb, cb + 1):
+            Xc = rs.uniform(0, 1, (M, D))
+            if gower is not None:
+                for i in gower[1]:
+                    Xc[:, i] = rs.randint(0, 3, M)
+            mu_r, v_r = O.predict(kind, post, X, Xc, var, ls, noise, ard=ard, gower=gower)
+            mu, v = m.predict(Xc)
+            assert mu.shape == (M, P), tag
+            assert_allclose(mu, mu_r, rtol=1e-9, atol=1e-10, err_msg=tag + " M=%d" % M)
+            assert_allclose(v, v_r, rtol=1e-9, atol=1e-11, err_msg=tag + " M=%d" % M)
+            if P == 1:
+                st_f = O.GPState(kind, X, Y, var, ls, noise, ard=ard, gower=gower)
+                f_ref = st_f.acquisition("LCB", Xc, with_gradients=False)
+                r = m.acquisition("LCB", 2.0, m.fmin(), Xc, with_gradients=False)
+                assert_allclose(r["f"], f_ref, rtol=1e-9, atol=1e-10, err_msg=tag + " M=%d" % M)
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(16, int(os.environ.get("GPB_FUZZ_LAST", "16")))))
+def test_random_models_on_the_int8_engine_match_the_oracle(seed):
+    """Every product of >= 256 rows on the int8 tensor cores (18 moduli; every second seed 8 digits): random sizes that are not
+    multiples of the engine's 256-row tiles, random hyper-parameters, the same bars as the fp64 engine; the residual check must not
+    have sent any of these back (gpb_ozaki_fallback_count)."""
+    rs = np.random.RandomState(19000 + seed)
+    N = int(rs.choice([256, 300, 511, 513, 700, 1000]))
+    D = int(rs.choice([2, 8, 16]))
+    kind = "rbf" if rs.rand() < 0.5 else "mat52"
+    noise = float(rs.choice([1e-2, 0.1]))
+    X = rs.uniform(0, 1, (N, D))
+    Y = np.sin(3.0 * X.sum(axis=1) / np.sqrt(D))[:, None] + 0.05 * rs.randn(N, 1)
+    ls = (0.4 + rs.rand(D)) * np.sqrt(D)
+    tag = "seed %d: N=%d D=%d %s noise=%g" % (seed, N, D, kind, noise)
+    l_ref, g_ref, post = O.log_likelihood_and_gradients(kind, X, Y, 1.1, ls, noise, native=True)
+    w = np.linalg.eigvalsh(O.K(kind, X, None, 1.1, ls) + (noise + 1e-8) * np.eye(N))
+    ct = max(1.0, w[-1] / w[0] * 2.2e-16 / 1e-12)
+    fb0 = native.ozaki_fallback_count()
+    native.set_ozaki(256, 18 if seed % 2 == 0 else 8)
+    m = native.NativeModel(kind, True, D, 1, n_cap=1024, cand_block=1024)
+    try:
+        m.set_data(X, Y)
+        m.set_theta(1.1, ls, noise)
+        info, logL, g = m.fit(True)
+        assert info == 0, tag
+        assert m.engine_report()[0], tag
+        assert_allclose(logL, l_ref, rtol=1e-9 * ct, atol=1e-9 * ct, err_msg=tag)
+        assert_allclose(g, g_ref, rtol=1e-7 * ct, atol=1e-9 * ct * max(1.0, np.abs(g_ref).max()), err_msg=tag)
+        Xc = rs.uniform(0, 1, (int(rs.choice([1024, 1100, 2047])), D))       # >= 1024 rows: the predictive products use the engine too
+        st = O.GPState(kind, X, Y, 1.1, ls, noise)
+        f_ref, df_ref = st.acquisition("EI", Xc, with_gradients=True, native=True)
+        r = m.acquisition("EI", 0.01, m.fmin(), Xc, with_gradients=True)
+        assert_allclose(r["f"], f_ref, rtol=1e-7 * ct, atol=1e-11 * ct, err_msg=tag)
+        assert_allclose(r["df"], df_ref, rtol=1e-6 * ct, atol=1e-9 * ct * max(1e-3, np.abs(df_ref).max()), err_msg=tag)
+        assert native.ozaki_fallback_count() == fb0, tag
+    finally:
+        m.close()
+        native.set_ozaki(0, 8)
