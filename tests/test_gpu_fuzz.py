@@ -426,3 +426,54 @@ def test_random_models_on_the_int8_engine_match_the_oracle(seed):
     finally:
         m.close()
         native.set_ozaki(0, 8)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(24, int(os.environ.get("GPB_FUZZ_LAST", "24")))))
+def test_random_acquisition_classes_and_local_penalisation_across_backends(seed):
+    """GPyOpt's AcquisitionEI / LCB / LP objects (EI.py:32-51, LCB.py:35-52, LP.py:40-140) on the CUDA GPModel against the same
+    objects on the oracle-backed GPModel (NumPy restatement of the hammer functions in gpyopt.py): random model, a random batch of
+    1 .. 6 penalisers, query sets of 1 .. 8 rows (fused kernel) and larger ones, value and gradient."""
+    import oracle_backend as OB
+    from gaussian_process_optimization_b200 import GPy, GPyOpt
+    rs = np.random.RandomState(23000 + seed)
+    N = int(rs.choice([10, 60, 130, 260]))
+    D = int(rs.choice([1, 2, 5, 10, 20]))
+    kname = "RBF" if rs.rand() < 0.5 else "Matern52"
+    X = rs.uniform(0, 1, (N, D))
+    Y = np.sin(4.0 * X.sum(axis=1) / np.sqrt(D))[:, None] + 0.1 * rs.randn(N, 1)
+    Y = (Y - Y.mean()) / Y.std()
+    ls0 = (0.3 + 0.5 * rs.rand(D)) * np.sqrt(D)
+    tag = "seed %d: N=%d D=%d %s" % (seed, N, D, kname)
+    space = GPyOpt.Design_space([{'name': 'x', 'type': 'continuous', 'domain': (0, 1), 'dimensionality': D}])
+    objs = []
+    for backend in ("cuda", "oracle"):
+        k = getattr(GPy.kern, kname)(D, variance=1.3, lengthscale=ls0.copy(), ARD=True)
+        gm = (GPyOpt.models.GPModel if backend == "cuda" else OB.OracleGPModel)(exact_feval=False, verbose=False)
+        gm.model = (GPy.models.GPRegression(X, Y, kernel=k, noise_var=0.02) if backend == "cuda"
+                    else OB.oracle_gp_regression(X, Y, k, 0.02))
+        ei = GPyOpt.acquisitions.AcquisitionEI(gm, space, optimizer=None, jitter=0.01)
+        lcb = GPyOpt.acquisitions.AcquisitionLCB(gm, space, optimizer=None, exploration_weight=2)
+        objs.append((gm, ei, lcb))
+    nb = int(rs.randint(1, 7))
+    Xb = rs.uniform(0, 1, (nb, D))
+    L, Min = float(0.5 + 3.0 * rs.rand()), float(Y.min())
+    for which in (1, 2):
+        lps = [GPyOpt.acquisitions.AcquisitionLP(o[0], space, None, o[which]) for o in objs]
+        for lp in lps:
+            lp.update_batches(Xb, L, Min)
+        assert_allclose(lps[0].r_x0, lps[1].r_x0, rtol=1e-8, atol=1e-10, err_msg=tag)
+        assert_allclose(lps[0].s_x0, lps[1].s_x0, rtol=1e-8, atol=1e-12, err_msg=tag)
+        for M in (1, 3, 8, 9, 70):
+            Xq = rs.uniform(0, 1, (M, D))
+            for a, b in ((objs[0][which], objs[1][which]), (lps[0], lps[1])):
+                fa, fb = a.acquisition_function(Xq), b.acquisition_function(Xq)
+                assert_allclose(fa, fb, rtol=1e-7, atol=1e-9, err_msg=tag + " %s M=%d" % (type(a).__name__, M))
+                if a is lps[0]:      # the NumPy LP gradient is written for one point at a time (LP.py:120-140)
+                    ga = a.acquisition_function_withGradients(Xq)
+                    gb = np.vstack([b.acquisition_function_withGradients(Xq[i:i + 1])[1] for i in range(M)])
+                    assert_allclose(ga[0], fb, rtol=1e-7, atol=1e-9, err_msg=tag + " LP f M=%d" % M)
+                    assert_allclose(ga[1], gb, rtol=1e-6, atol=1e-8 * max(1e-3, np.abs(gb).max()), err_msg=tag + " LP df M=%d" % M)
+                else:
+                    ga, gb = a.acquisition_function_withGradients(Xq), b.acquisition_function_withGradients(Xq)
+                    assert_allclose(ga[0], gb[0], rtol=1e-7, atol=1e-9, err_msg=tag + " %s M=%d" % (type(a).__name__, M))
+                    assert_allclose(ga[1], gb[1], rtol=1e-6, atol=1e-8 * max(1e-3, np.abs(gb[1]).max()), err_msg=tag + " %s M=%d" % (type(a).__name__, M))
