@@ -477,3 +477,125 @@ def test_random_acquisition_classes_and_local_penalisation_across_backends(seed)
                     ga, gb = a.acquisition_function_withGradients(Xq), b.acquisition_function_withGradients(Xq)
                     assert_allclose(ga[0], gb[0], rtol=1e-7, atol=1e-9, err_msg=tag + " %s M=%d" % (type(a).__name__, M))
                     assert_allclose(ga[1], gb[1], rtol=1e-6, atol=1e-8 * max(1e-3, np.abs(gb[1]).max()), err_msg=tag + " %s M=%d" % (type(a).__name__, M))
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(16, int(os.environ.get("GPB_FUZZ_LAST", "16")))))
+def test_device_pointer_forms_of_the_c_abi_equal_the_host_forms(seed):
+    """include/gpb200.h gives most entry points a `dev` flag (buffers already in HBM).  The Python wrappers reach only some of
+    those forms; here the others are called straight through ctypes with CUDA tensors -- set_data, append, predict,
+    predict_full_cov, predictive_gradients, acquisition_lp, get, and the stateless kern_K / update_gradients_full / gradients_X /
+    pdinv / potrs / potri -- and must reproduce the host-buffer forms bit for bit."""
+    import ctypes
+
+    import torch
+    from gaussian_process_optimization_b200 import _lib
+    from gaussian_process_optimization_b200._lib import ptr, dptr
+    lib = _lib.load()
+    rs = np.random.RandomState(29000 + seed)
+    N = int(rs.choice([20, 127, 130, 260]))
+    D = int(rs.choice([1, 3, 8, 20, 40]))
+    b = int(rs.choice([1, 2, 9]))
+    kind = "rbf" if rs.rand() < 0.5 else "mat52"
+    X = rs.uniform(0, 1, (N + b, D))
+    Y = np.sin(3.0 * X.sum(axis=1) / np.sqrt(D))[:, None] + 0.05 * rs.randn(N + b, 1)
+    ls = (0.4 + rs.rand(D)) * np.sqrt(D)
+    tag = "seed %d: N=%d D=%d b=%d %s" % (seed, N, D, b, kind)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    ok = lambda rc, what: _lib.check(rc, what)  # noqa: E731
+
+    h = native.NativeModel(kind, True, D, 1, n_cap=384, cand_block=128)      # host forms
+    g = native.NativeModel(kind, True, D, 1, n_cap=384, cand_block=128)      # device forms
+    try:
+        h.set_data(X[:N], Y[:N])
+        g.set_data(dev(X[:N]), dev(Y[:N]))
+        for mdl in (h, g):
+            mdl.set_theta(1.2, ls, 1e-2)
+        rh, rg = h.fit(True), g.fit(True)
+        assert rh[0] == 0 and rh[1] == rg[1] and np.array_equal(rh[2], rg[2]), tag
+        # append: host pointers vs device pointers
+        rh = h.append(X[N:], Y, want_grad=True)
+        out = np.zeros(3 + D)
+        Xn_d, Y_d = dev(X[N:]), dev(Y)
+        ok(lib.gpb_model_append(g._h, b, ptr(Xn_d), ptr(Y_d), 1, 1, dptr(out)), "append(dev)")
+        g.n += b
+        g.generation += 1
+        assert rh[0] == 0 and rh[1] == out[0] and np.array_equal(rh[2], out[1:]), tag
+        for what in ("L", "Li", "Wi", "alpha"):
+            a = h.get(what)
+            t = torch.empty(a.shape, dtype=torch.float64, device="cuda")
+            g.get(what, out=t)
+            assert np.array_equal(a, t.cpu().numpy()), (tag, what)
+        for M in (1, 6, 9, 128, 200):
+            Xc = rs.uniform(0, 1, (M, D))
+            Xc_d = dev(Xc)
+            mu, var = h.predict(Xc)
+            mu_d, var_d = torch.empty((M, 1), dtype=torch.float64, device="cuda"), torch.empty((M, 1), dtype=torch.float64, device="cuda")
+            ok(lib.gpb_model_predict(g._h, M, ptr(Xc_d), 1, ptr(mu_d), ptr(var_d), 1), "predict(dev)")
+            torch.cuda.synchronize()
+            assert np.array_equal(mu, mu_d.cpu().numpy()) and np.array_equal(var, var_d.cpu().numpy()), (tag, "predict", M)
+            dm, dv = h.predictive_gradients(Xc)
+            dm_d, dv_d = torch.empty((M, D, 1), dtype=torch.float64, device="cuda"), torch.empty((M, D), dtype=torch.float64, device="cuda")
+            ok(lib.gpb_model_predictive_gradients(g._h, M, ptr(Xc_d), ptr(dm_d), ptr(dv_d), 1), "predictive_gradients(dev)")
+            torch.cuda.synchronize()
+            assert np.array_equal(dm, dm_d.cpu().numpy()) and np.array_equal(dv, dv_d.cpu().numpy()), (tag, "predictive_gradients", M)
+            if M <= 128:
+                mu, cov = h.predict_full_cov(Xc)
+                mu_d, cov_d = torch.empty((M, 1), dtype=torch.float64, device="cuda"), torch.empty((M, M), dtype=torch.float64, device="cuda")
+                ok(lib.gpb_model_predict_full_cov(g._h, M, ptr(Xc_d), 1, ptr(mu_d), ptr(cov_d), 1), "predict_full_cov(dev)")
+                torch.cuda.synchronize()
+                assert np.array_equal(mu, mu_d.cpu().numpy()) and np.array_equal(cov, cov_d.cpu().numpy()), (tag, "predict_full_cov", M)
+            for mdl in (h, g):
+                mdl.set_penalizers("softplus", X[:3], np.array([0.2, 0.3, 0.1]), np.array([0.05, 0.02, 0.04]))
+            f, df = h.acquisition_lp("LCB", 2.0, 0.0, Xc, with_gradients=True)
+            f_d, df_d = torch.empty(M, dtype=torch.float64, device="cuda"), torch.empty((M, D), dtype=torch.float64, device="cuda")
+            ok(lib.gpb_model_acquisition_lp(g._h, _lib.ACQ_LCB, 2.0, 0.0, M, ptr(Xc_d), ptr(f_d), ptr(df_d), 1), "acquisition_lp(dev)")
+            torch.cuda.synchronize()
+            assert np.array_equal(f, f_d.cpu().numpy(), equal_nan=True) and np.array_equal(df, df_d.cpu().numpy(), equal_nan=True), (tag, "lp", M)
+    finally:
+        h.close()
+        g.close()
+    # stateless entry points
+    n, m = int(rs.choice([1, 9, 130])), int(rs.choice([1, 8, 70]))
+    A, Z = rs.randn(n, D), rs.randn(m, D)
+    stream = _lib.current_stream()
+    kid = _lib.KIND_IDS[kind]
+    for X2, cols in ((None, n), (Z, m)):
+        G = rs.randn(n, cols)
+        K_h = native.kern_K(kind, A, X2, 1.3, ls)
+        A_d, Z_d, G_d = dev(A), (dev(X2) if X2 is not None else None), dev(G)
+        K_d = torch.empty((n, cols), dtype=torch.float64, device="cuda")
+        ok(lib.gpb_kern_K(kid, D, n, ptr(A_d), 0 if X2 is None else m, ptr(Z_d), 1.3, dptr(ls), D, ptr(K_d), cols, 1, stream), "kern_K(dev)")
+        torch.cuda.synchronize()
+        assert np.array_equal(K_h, K_d.cpu().numpy()), (tag, "kern_K")
+        dv, dl = native.kern_update_gradients_full(kind, G, A, X2, 1.3, ls)
+        out = np.zeros(1 + D)
+        ok(lib.gpb_kern_update_gradients_full(kid, D, n, ptr(A_d), 0 if X2 is None else m, ptr(Z_d), ptr(G_d), cols, 1.3, dptr(ls), D,
+                                              dptr(out), 1, stream), "update_gradients_full(dev)")
+        assert dv == out[0] and np.array_equal(dl, out[1:]), (tag, "update_gradients_full")
+        gx = native.kern_gradients_X(kind, G, A, X2, 1.3, ls)
+        gx_d = torch.empty((n, D), dtype=torch.float64, device="cuda")
+        ok(lib.gpb_kern_gradients_X(kid, D, n, ptr(A_d), 0 if X2 is None else m, ptr(Z_d), ptr(G_d), cols, 1.3, dptr(ls), D, ptr(gx_d), 1,
+                                    stream), "gradients_X(dev)")
+        torch.cuda.synchronize()
+        assert np.array_equal(gx, gx_d.cpu().numpy()), (tag, "gradients_X")
+    q = int(rs.choice([1, 100, 129, 300]))
+    B = rs.randn(q, q)
+    S = B @ B.T / q + np.eye(q)
+    rc, Ai, L, Li, logdet = native.pdinv(S)
+    S_d = dev(S)
+    L_d, Ai_d, Li_d = (torch.empty((q, q), dtype=torch.float64, device="cuda") for _ in range(3))
+    ld = ctypes.c_double(0.0)
+    ok(lib.gpb_pdinv(q, ptr(S_d), q, ptr(L_d), ptr(Ai_d), ptr(Li_d), ctypes.byref(ld), 1, stream), "pdinv(dev)")
+    torch.cuda.synchronize()
+    assert rc == 0 and ld.value == logdet and np.array_equal(L, L_d.cpu().numpy()) and np.array_equal(Ai, Ai_d.cpu().numpy()), tag
+    assert np.array_equal(Li, Li_d.cpu().numpy()), tag
+    rhs = rs.randn(q, 3)
+    rhs_d = dev(rhs)
+    Lc = np.ascontiguousarray(np.tril(L))
+    ok(lib.gpb_potrs(q, ptr(dev(Lc)), q, ptr(rhs_d), 3, 1, stream), "potrs(dev)")
+    torch.cuda.synchronize()
+    assert np.array_equal(native.potrs(Lc, rhs), rhs_d.cpu().numpy()), (tag, "potrs")
+    Ai2_d = torch.empty((q, q), dtype=torch.float64, device="cuda")
+    ok(lib.gpb_potri(q, ptr(dev(Lc)), q, ptr(Ai2_d), q, 1, stream), "potri(dev)")
+    torch.cuda.synchronize()
+    assert np.array_equal(native.potri(Lc), Ai2_d.cpu().numpy()), (tag, "potri")
