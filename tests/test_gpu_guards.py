@@ -163,3 +163,86 @@ def test_engines_write_only_their_output_tiles(slices, m, n, k):
             np.testing.assert_allclose(out, ref, rtol=0, atol=1e-11 * np.abs(ref).max())
             assert prev is None or np.array_equal(prev, out)
             prev = out
+
+
+def test_misuse_returns_error_codes_and_leaves_the_model_usable():
+    """Wrong call order, NULL pointers, sizes beyond the capacity, unknown names: every entry point answers with a negative code and
+    a message (gpb_last_error), never with a crash, and the model gives the same answers afterwards as before.  Non-finite inputs
+    travel like in the reference: a NaN in X makes the factorisation fail with LAPACK's info > 0 (jitchol's LinAlgError,
+    util/linalg.py:56-75), a NaN candidate gives a NaN score and never wins a top-k slot."""
+    import ctypes
+
+    from gaussian_process_optimization_b200 import _lib
+    from gaussian_process_optimization_b200._lib import ptr, dptr
+    lib = _lib.load()
+    rs = np.random.RandomState(77)
+    N, D = 60, 3
+    X, Y = rs.uniform(0, 1, (N, D)), rs.randn(N, 1)
+    ls = np.array([0.5, 0.6, 0.7])
+    m = native.NativeModel("rbf", True, D, 1, n_cap=64, cand_block=128)
+    out = np.zeros(3 + D)
+    Xc = rs.uniform(0, 1, (5, D))
+    mu, var = np.empty((5, 1)), np.empty((5, 1))
+
+    def bad(rc, needle=None):
+        assert rc < 0, rc
+        msg = lib.gpb_last_error().decode()
+        assert msg and (needle is None or needle in msg), msg
+
+    bad(lib.gpb_model_fit(m._h, 1, 0.0, dptr(out)), "set_data")                                  # fit before data
+    bad(lib.gpb_model_predict(m._h, 5, ptr(Xc), 1, ptr(mu), ptr(var), 0), "fitted")              # predict before fit
+    bad(lib.gpb_model_set_data(m._h, 65, ptr(rs.randn(65, D)), ptr(rs.randn(65, 1)), 0))          # beyond n_cap
+    bad(lib.gpb_model_set_data(m._h, N, None, ptr(Y), 0), "NULL")
+    m.set_data(X, Y)
+    m.set_theta(1.0, ls, 1e-2)
+    # hyper-parameters outside their domain: like the reference, where they reach LAPACK and come back as "not positive definite"
+    # (a LinAlgError, which paramz's optimiser loop survives), the fit answers GPB_ERR_DOMAIN -> numpy.linalg.LinAlgError
+    for v_bad, ls_bad in ((-1.0, ls), (1.0, np.array([0.5, 0.0, 0.7])), (float("nan"), ls), (1.0, np.array([0.5, np.nan, 0.7]))):
+        m.set_theta(v_bad, ls_bad, 1e-2)
+        assert lib.gpb_model_fit(m._h, 1, 0.0, dptr(out)) == _lib.ERR_DOMAIN, (v_bad, ls_bad)
+        with pytest.raises(np.linalg.LinAlgError):
+            m.fit(True)
+    m.set_theta(1.0, ls, 1e-2)
+    bad(lib.gpb_model_fit(m._h, 1, 0.0, None), "NULL")
+    info, logL, g = m.fit(True)
+    assert info == 0
+    ref = m.acquisition("EI", 0.01, m.fmin(), Xc, with_gradients=True)
+    bad(lib.gpb_model_predict(m._h, -1, ptr(Xc), 1, ptr(mu), ptr(var), 0), "negative")
+    bad(lib.gpb_model_predict(m._h, 5, None, 1, ptr(mu), ptr(var), 0), "NULL")
+    big = rs.uniform(0, 1, (129, D))
+    cov = np.empty((129, 129))
+    bad(lib.gpb_model_predict_full_cov(m._h, 129, ptr(big), 1, ptr(np.empty((129, 1))), ptr(cov), 0), "candidate block")
+    bad(lib.gpb_model_get(m._h, b"no_such_array", ptr(np.empty((N, N))), N, 0))
+    bad(lib.gpb_model_append(m._h, 5, ptr(rs.randn(5, D)), ptr(rs.randn(N + 5, 1)), 0, 1, dptr(out)))   # 60 + 5 > n_cap = 64
+    bad(lib.gpb_model_acquisition(m._h, 7, 0.01, 0.0, 5, ptr(Xc), ptr(mu), None, None, None, None, None, 0))   # unknown acquisition
+    bad(lib.gpb_kern_K(9, D, 5, ptr(Xc), 0, None, 1.0, dptr(ls), D, ptr(np.empty((5, 5))), 5, 0, None))        # unknown kernel
+    bad(lib.gpb_kern_K(0, 97, 5, ptr(rs.randn(5, 97)), 0, None, 1.0, dptr(np.ones(97)), 97, ptr(np.empty((5, 5))), 5, 0, None))   # d <= 96
+    bad(lib.gpb_kern_gradients_X(0, 65, 5, ptr(rs.randn(5, 65)), 0, None, ptr(rs.randn(5, 5)), 5, 1.0, dptr(np.ones(65)), 65,
+                                 ptr(np.empty((5, 65))), 0, None), "64")                                                        # d <= 64
+    bad(lib.gpb_pdinv(0, ptr(np.eye(1)), 1, None, None, None, ctypes.byref(ctypes.c_double()), 0, None))
+    h = ctypes.c_void_p()
+    bad(lib.gpb_model_create(ctypes.byref(h), 0, 1, 0, 1, 64, 128, None, 0, None))                # zero input dimension
+    bad(lib.gpb_model_create(ctypes.byref(h), 0, 1, 3, 1, 0, 128, None, 0, None))                 # zero capacity
+    # nothing above disturbed the model
+    again = m.acquisition("EI", 0.01, m.fmin(), Xc, with_gradients=True)
+    assert np.array_equal(ref["f"], again["f"]) and np.array_equal(ref["df"], again["df"])
+    info2, logL2, g2 = m.fit(True)
+    assert info2 == 0 and logL2 == logL and np.array_equal(g, g2)
+    # non-finite values
+    Xn = Xc.copy()
+    Xn[2, 1] = np.nan
+    r = m.acquisition("EI", 0.01, m.fmin(), Xn, with_gradients=False)
+    assert np.isnan(r["f"][2, 0]) and np.all(np.isfinite(np.delete(r["f"], 2, axis=0)))
+    vals, idx, pts = m.acq_topk("EI", 0.01, m.fmin(), Xn, 5)
+    assert 2 not in list(idx) and list(idx).count(-1) == 1
+    Xbad = X.copy()
+    Xbad[7, 0] = np.nan
+    m.set_data(Xbad, Y)
+    m.set_theta(1.0, ls, 1e-2)
+    info, _, _ = m.fit(True)
+    assert info > 0                                    # "not positive definite": the reference's jitchol raises here as well
+    m.set_data(X, Y)
+    m.set_theta(1.0, ls, 1e-2)
+    info3, logL3, g3 = m.fit(True)
+    assert info3 == 0 and logL3 == logL and np.array_equal(g, g3)
+    m.close()
