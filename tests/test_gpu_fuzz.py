@@ -599,3 +599,58 @@ def test_device_pointer_forms_of_the_c_abi_equal_the_host_forms(seed):
     ok(lib.gpb_potri(q, ptr(dev(Lc)), q, ptr(Ai2_d), q, 1, stream), "potri(dev)")
     torch.cuda.synchronize()
     assert np.array_equal(native.potri(Lc), Ai2_d.cpu().numpy()), (tag, "potri")
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(12, int(os.environ.get("GPB_FUZZ_LAST", "12")))))
+def test_random_fit_sequences_replay_bitwise(seed):
+    """The evaluation of a model up to 2048 padded rows is replayed as a CUDA graph whose parameters travel through pinned memory
+    (gpb_api.cu fit_launch_graph).  A random sequence on ONE model -- new hyper-parameters, with / without gradients, an extra
+    jitter as the ladder of util/linalg.py:62-72 passes it, new data of another size, an append -- must give, step by step, exactly
+    the bits a freshly created model gives for that step alone."""
+    rs = np.random.RandomState(31000 + seed)
+    D = int(rs.choice([2, 8, 16]))
+    kind = "rbf" if rs.rand() < 0.5 else "mat52"
+    Nmax = 700
+    X = rs.uniform(0, 1, (Nmax, D))
+    Y = np.sin(3.0 * X.sum(axis=1) / np.sqrt(D))[:, None] + 0.05 * rs.randn(Nmax, 1)
+    m = native.NativeModel(kind, True, D, 1, n_cap=Nmax, cand_block=128)
+    n = int(rs.choice([100, 128, 300, 513]))
+    m.set_data(X[:n], Y[:n])
+    try:
+        for step in range(10):
+            op = int(rs.randint(0, 5))
+            ls = (0.4 + rs.rand(D)) * np.sqrt(D)
+            var, noise = float(0.5 + rs.rand()), float(rs.choice([1e-3, 1e-2, 0.1]))
+            want_grad = bool(rs.rand() < 0.6)
+            jitter = float(rs.choice([0.0, 0.0, 1e-6, 1e-4]))
+            if op == 3:
+                n = int(rs.choice([90, 128, 257, 300, 640]))
+                m.set_data(X[:n], Y[:n])
+            fresh = native.NativeModel(kind, True, D, 1, n_cap=Nmax, cand_block=128)
+            try:
+                if op == 4 and n + 7 <= Nmax:
+                    # an append on the long-lived model against a fresh model that grows the same way
+                    m.set_theta(var, ls, noise)
+                    assert m.fit(False)[0] == 0
+                    a = m.append(X[n:n + 7], Y[:n + 7], want_grad=want_grad)
+                    fresh.set_data(X[:n], Y[:n])
+                    fresh.set_theta(var, ls, noise)
+                    assert fresh.fit(False)[0] == 0
+                    b = fresh.append(X[n:n + 7], Y[:n + 7], want_grad=want_grad)
+                    n += 7
+                else:
+                    m.set_theta(var, ls, noise)
+                    a = m.fit(want_grad, extra_jitter=jitter)
+                    fresh.set_data(X[:n], Y[:n])
+                    fresh.set_theta(var, ls, noise)
+                    b = fresh.fit(want_grad, extra_jitter=jitter)
+                assert a[0] == b[0] == 0 and a[1] == b[1], (seed, step, op, n)
+                assert (a[2] is None and b[2] is None) or np.array_equal(a[2], b[2]), (seed, step, op, n)
+                Xc = rs.uniform(0, 1, (int(rs.choice([1, 5, 40])), D))
+                ra = m.acquisition("EI", 0.01, m.fmin(), Xc, with_gradients=True)
+                rb = fresh.acquisition("EI", 0.01, fresh.fmin(), Xc, with_gradients=True)
+                assert np.array_equal(ra["f"], rb["f"]) and np.array_equal(ra["df"], rb["df"]), (seed, step, op, n)
+            finally:
+                fresh.close()
+    finally:
+        m.close()
