@@ -654,3 +654,40 @@ def test_random_fit_sequences_replay_bitwise(seed):
                 fresh.close()
     finally:
         m.close()
+
+
+@pytest.mark.parametrize("N,D,kind", [(2500, 5, "mat52"), (4999, 12, "rbf")])
+def test_large_odd_sizes_match_the_oracle_on_both_engines(N, D, kind):
+    """Training sizes that are neither powers of two nor multiples of 128 / 256, above the CUDA-graph range, where the recursion forks
+    its side-stream products and the engine picks its large tiles: NLL + gradients and an EI pass over several ragged candidate blocks
+    against the oracle, on the fp64 engine and with every product of >= 1024 rows on the int8 engine (16 moduli; 18 in prediction)."""
+    rs = np.random.RandomState(N)
+    X = rs.uniform(0, 1, (N, D))
+    Y = np.sin(3.0 * X.sum(axis=1) / np.sqrt(D))[:, None] + 0.05 * rs.randn(N, 1)
+    Y = (Y - Y.mean()) / Y.std()
+    ls = (0.5 + 0.5 * rs.rand(D)) * np.sqrt(D)
+    l_ref, g_ref, post = O.log_likelihood_and_gradients(kind, X, Y, 1.0, ls, 1e-2, native=True)
+    st = O.GPState(kind, X, Y, 1.0, ls, 1e-2)
+    Xc = rs.uniform(0, 1, (2 * 1024 + 1031, D))
+    f_ref, df_ref = st.acquisition("EI", Xc[:1500], with_gradients=True, native=True)
+    for engine in ("fp64", "int8"):
+        native.set_ozaki(1024 if engine == "int8" else 0, 16)
+        m = native.NativeModel(kind, True, D, 1, n_cap=N, cand_block=1024)
+        try:
+            m.set_data(X, Y)
+            m.set_theta(1.0, ls, 1e-2)
+            info, logL, g = m.fit(True)
+            assert info == 0
+            assert m.engine_report()[0] == (engine == "int8")
+            assert_allclose(logL, l_ref, rtol=1e-9, err_msg=engine)
+            assert_allclose(g, g_ref, rtol=1e-7, atol=1e-9 * np.abs(g_ref).max(), err_msg=engine)
+            fmin = m.fmin()
+            assert_allclose(fmin, st.get_fmin(), rtol=1e-9, err_msg=engine)
+            vals, idx, pts, f, df = m.acq_topk_full("EI", 0.01, fmin, Xc, 5)
+            assert_allclose(f[:1500], f_ref, rtol=1e-7, atol=1e-12, err_msg=engine)
+            assert_allclose(df[:1500], df_ref, rtol=1e-6, atol=1e-9 * np.abs(df_ref).max(), err_msg=engine)
+            order = np.argsort(f.ravel(), kind="stable")[:5]
+            assert np.array_equal(idx, order) and np.array_equal(pts, Xc[order])
+        finally:
+            m.close()
+            native.set_ozaki(0, 8)
