@@ -16,6 +16,13 @@ from oracle import gp_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+def _seeds(default):
+    """Seeds of one sweep: `default` of them in the driver's run; GPB_FUZZ_FIRST / GPB_FUZZ_LAST widen or move the range by hand."""
+    if "GPB_FUZZ_LAST" in os.environ or "GPB_FUZZ_FIRST" in os.environ:
+        return range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), int(os.environ.get("GPB_FUZZ_LAST", str(default))))
+    return range(default)
+
+
 def _case(seed):
     rs = np.random.RandomState(1000 + seed)
     N = int(rs.choice([1, 2, 3, 17, 64, 127, 128, 129, 200, 255, 256, 257, 300, 383, 385, 500]))
@@ -35,7 +42,7 @@ def _case(seed):
     return N, D, kind, ard, noise, M, X, Y, ls, var, Xc
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), int(os.environ.get("GPB_FUZZ_LAST", "64"))))
+@pytest.mark.parametrize("seed", _seeds(64))
 def test_random_case_matches_the_oracle(seed):
     N, D, kind, ard, noise, M, X, Y, ls, var, Xc = _case(seed)
     tag = "seed %d: N=%d D=%d %s ard=%s noise=%g M=%d" % (seed, N, D, kind, ard, noise, M)
@@ -98,7 +105,7 @@ def _kern_case(seed):
     return rs, n, m, d, kind, ard, X, Z, ls, var
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), int(os.environ.get("GPB_FUZZ_LAST", "64"))))
+@pytest.mark.parametrize("seed", _seeds(64))
 def test_random_kernel_calls_match_the_oracle(seed):
     """The stateless kernel entry points -- K, update_gradients_full, gradients_X (stationary.py:107-140,218-238,271-278,354-364),
     square (X2 None: the tmp + tmp.T form) and rectangular -- on random shapes, against the oracle's restatement with the reference's
@@ -120,7 +127,7 @@ def test_random_kernel_calls_match_the_oracle(seed):
         assert_allclose(got, ref, rtol=1e-7, atol=1e-11 * max(1e-30, np.abs(ref).max()), err_msg=tag)
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(24, int(os.environ.get("GPB_FUZZ_LAST", "24")))))
+@pytest.mark.parametrize("seed", _seeds(24))
 def test_random_pdinv_potrs_potri_match_lapack(seed):
     """pdinv / dpotrs / dpotri (util/linalg.py:116-145,193-214) on random SPD matrices of random order (leaf, padded, recursion)."""
     rs = np.random.RandomState(9000 + seed)
@@ -141,7 +148,7 @@ def test_random_pdinv_potrs_potri_match_lapack(seed):
     assert_allclose(native.potri(L_ref), Ai_ref, rtol=0, atol=tol * np.abs(Ai_ref).max())
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(32, int(os.environ.get("GPB_FUZZ_LAST", "32")))))
+@pytest.mark.parametrize("seed", _seeds(32))
 def test_random_growth_by_appends_matches_a_fresh_oracle_fit(seed):
     """GPModel.updateModel with one or a few more rows per BO step (gpmodel.py:78-93) served by gpb_model_append: random start sizes and
     increments that cross the 128-row padding, targets re-normalised at every step; after the last step the log-likelihood,
@@ -189,7 +196,7 @@ def test_random_growth_by_appends_matches_a_fresh_oracle_fit(seed):
         m.close()
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(32, int(os.environ.get("GPB_FUZZ_LAST", "32")))))
+@pytest.mark.parametrize("seed", _seeds(32))
 def test_random_interleaved_calls_and_buffer_kinds_agree(seed):
     """One model, a random sequence of entry points with candidate counts on every route, host and device buffers mixed: every
     answer must equal -- bitwise, value and gradient -- what the same call gives on a freshly fitted twin that has seen nothing
@@ -264,7 +271,7 @@ def test_random_interleaved_calls_and_buffer_kinds_agree(seed):
         m.close()
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(24, int(os.environ.get("GPB_FUZZ_LAST", "24")))))
+@pytest.mark.parametrize("seed", _seeds(24))
 def test_random_host_mirror_models_agree_with_the_oracle_backend(seed):
     """The GPy-shaped host classes once on libgpb200.so and once on the CPU oracle (tests/oracle_backend.py), random model and
     data: objective and gradient vector (core/gp.py:258-271 through the paramz transforms), predict with and without the full
@@ -332,7 +339,7 @@ def test_random_host_mirror_models_agree_with_the_oracle_backend(seed):
             assert_allclose(u, w, rtol=1e-6 * ct, atol=1e-8 * ct * max(1e-3, np.abs(w).max()), err_msg=tag + " GPModel M=%d" % M)
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(24, int(os.environ.get("GPB_FUZZ_LAST", "24")))))
+@pytest.mark.parametrize("seed", _seeds(24))
 def test_random_gower_and_two_output_models_match_the_oracle(seed):
     """The reference's mixed-variable product kernel (stationary.py:116-135; only the variance gradient sees it, :224) with random
     splits into continuous and discrete dimensions, and models with two output columns (exact_gaussian_inference.py:62,70),
@@ -388,7 +395,7 @@ def test_random_gower_and_two_output_models_match_the_oracle(seed):
         m.close()
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(16, int(os.environ.get("GPB_FUZZ_LAST", "16")))))
+@pytest.mark.parametrize("seed", _seeds(16))
 def test_random_models_on_the_int8_engine_match_the_oracle(seed):
     """Every product of >= 256 rows on the int8 tensor cores (18 moduli; every second seed 8 digits): random sizes that are not
     multiples of the engine's 256-row tiles, random hyper-parameters, the same bars as the fp64 engine; the residual check must not
@@ -428,7 +435,7 @@ def test_random_models_on_the_int8_engine_match_the_oracle(seed):
         native.set_ozaki(0, 8)
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(24, int(os.environ.get("GPB_FUZZ_LAST", "24")))))
+@pytest.mark.parametrize("seed", _seeds(24))
 def test_random_acquisition_classes_and_local_penalisation_across_backends(seed):
     """GPyOpt's AcquisitionEI / LCB / LP objects (EI.py:32-51, LCB.py:35-52, LP.py:40-140) on the CUDA GPModel against the same
     objects on the oracle-backed GPModel (NumPy restatement of the hammer functions in gpyopt.py): random model, a random batch of
@@ -479,7 +486,7 @@ def test_random_acquisition_classes_and_local_penalisation_across_backends(seed)
                     assert_allclose(ga[1], gb[1], rtol=1e-6, atol=1e-8 * max(1e-3, np.abs(gb[1]).max()), err_msg=tag + " %s M=%d" % (type(a).__name__, M))
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(16, int(os.environ.get("GPB_FUZZ_LAST", "16")))))
+@pytest.mark.parametrize("seed", _seeds(16))
 def test_device_pointer_forms_of_the_c_abi_equal_the_host_forms(seed):
     """include/gpb200.h gives most entry points a `dev` flag (buffers already in HBM).  The Python wrappers reach only some of
     those forms; here the others are called straight through ctypes with CUDA tensors -- set_data, append, predict,
@@ -601,7 +608,7 @@ def test_device_pointer_forms_of_the_c_abi_equal_the_host_forms(seed):
     assert np.array_equal(native.potri(Lc), Ai2_d.cpu().numpy()), (tag, "potri")
 
 
-@pytest.mark.parametrize("seed", range(int(os.environ.get("GPB_FUZZ_FIRST", "0")), min(12, int(os.environ.get("GPB_FUZZ_LAST", "12")))))
+@pytest.mark.parametrize("seed", _seeds(12))
 def test_random_fit_sequences_replay_bitwise(seed):
     """The evaluation of a model up to 2048 padded rows is replayed as a CUDA graph whose parameters travel through pinned memory
     (gpb_api.cu fit_launch_graph).  A random sequence on ONE model -- new hyper-parameters, with / without gradients, an extra
