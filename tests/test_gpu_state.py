@@ -2,8 +2,9 @@
 multi-rank state distribution (rank 0 fits, theta / alpha / L^-1 are broadcast, the other ranks adopt them instead of refitting;
 SURVEY.md 8e) with the device-side all-gather of the per-shard anchors.
 
-The two-rank test runs both ranks on ONE GPU over the gloo backend (the driver's GPU box has a single B200; NCCL refuses two
-ranks on one device) -- the same code path as `bench.py --gpus N` over NCCL up to the transport underneath torch.distributed.
+The two-rank test gives every rank its own GPU over NCCL when the box has two; on a single-GPU box (the driver's test box) it runs both
+ranks on ONE GPU over the gloo backend (NCCL refuses two ranks on one device) -- the same code path as `bench.py --gpus N` over NCCL up
+to the transport underneath torch.distributed.
 """
 import os
 
@@ -99,8 +100,11 @@ def _rank_worker(rank, world, port, out):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.cuda.set_device(0)
+    # one GPU per rank over NCCL when the box has them (the exchange then runs device to device over NVLink); both ranks on GPU 0 over
+    # gloo on the driver's single-GPU test box (NCCL refuses two ranks on one device)
+    many = torch.cuda.device_count() >= world
+    dist.init_process_group("nccl" if many else "gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank if many else 0)
     n, d = 700, 5
     X, Y = _data(n, d, seed=11)
     ls = 0.4 + 0.1 * np.arange(d)
