@@ -11,12 +11,12 @@ sys.path.insert(0, ".")
 from bench import synth  # noqa: E402
 from gaussian_process_optimization_b200 import native  # noqa: E402
 
-N, D = 16384, 16
+N, D = 16384, int(os.environ.get("GPB_PROBE_D", "16"))
 X, Y, ls = synth(N, D)
-out = {"variant": os.environ.get("GPB_GX_VARIANT", "default")}
+out = {"D": D, "tile": os.environ.get("GPB_GRADX_TILE", "1")}
 Xc = np.random.RandomState(4321).uniform(0, 1, (2048 * 6, D))
 Xd = torch.from_numpy(Xc).cuda()
-for engine in ("dmma", "int8"):
+for engine in os.environ.get("GPB_PROBE_ENGINES", "dmma,int8").split(","):
     native.set_ozaki(8192 if engine == "int8" else 0, 16)
     m = native.NativeModel("mat52", True, D, 1, n_cap=N, cand_block=2048)
     m.set_data(X, Y)
