@@ -1041,12 +1041,18 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   // the triangle of M per product instead of a 128-row padded GEMM, and the row reductions (mean, variance, both input
   // gradients) split over the training points in one fused pass (launch_skinny_moments) instead of one warp per candidate.
   const bool skinny = mcb <= 8;
+  // the skinny products run on THIS block's stream: in the two-lane scoring pass that is not the factor's own stream (they used to be
+  // issued there, unordered against the lane's covariance rows and reductions: found by the random sweep under GPB_SKINNY_FUSED=0;
+  // the same route serves Gower models by default)
+  Factor fl = m->f;
+  fl.stream = s;
+  fl.ov = nullptr;
   if (skinny && p == 1 && d <= 32) {      // (round-1 route: Gower kernel, GPB_SKINNY_FUSED=0; wider inputs take the generic kernels below)
     const double var_base = m->variance + (include_likelihood ? m->noise : 0.0);
     const double *Vt = nullptr, *Ut = nullptr;
     if (level == 1 || level == 2) {
       const int c = mcb <= 1 ? 1 : mcb <= 2 ? 2 : mcb <= 4 ? 4 : 8;   // rows mcb .. c of KxT are zero (mode 2 padding)
-      GPB_TRY(factor_skinny_products(m->f, c, m->KxT, np, m->Vt, np, level >= 2 ? m->Ut : nullptr, np, m->f.part));
+      GPB_TRY(factor_skinny_products(fl, c, m->KxT, np, m->Vt, np, level >= 2 ? m->Ut : nullptr, np, m->f.part));
       Vt = m->Vt;
       if (level == 2) Ut = m->Ut;
     }
@@ -1065,7 +1071,7 @@ static int predict_block(gpb_model *m, const double *Xc, int mcb, int dev, int l
   }
   if (level >= 1 && skinny) {
     const int c = mcb <= 1 ? 1 : mcb <= 2 ? 2 : mcb <= 4 ? 4 : 8;   // rows mcb .. c of KxT are zero (mode 2 padding)
-    GPB_TRY(factor_skinny_products(m->f, c, m->KxT, np, m->Vt, np, level >= 2 ? m->Ut : nullptr, np, m->f.part));
+    GPB_TRY(factor_skinny_products(fl, c, m->KxT, np, m->Vt, np, level >= 2 ? m->Ut : nullptr, np, m->f.part));
     GPB_TRY(launch_var_from_vt(m->Vt, np, mcb, n, m->variance + (include_likelihood ? m->noise : 0.0), m->var, s));
   } else if (level >= 1) {
     // Vt = KxT M^T  (== (L^-1 Kx)^T: dtrtrs of posterior.py:293 as a product with the explicit inverse factor)

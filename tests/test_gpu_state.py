@@ -236,3 +236,31 @@ def test_two_lane_block_pipeline_equals_the_single_lane_pass(engine):
         nm.close()
     finally:
         native.set_ozaki(0)
+
+
+def test_gower_model_two_lane_pass_with_a_short_tail_block_equals_the_host_buffer_pass():
+    """A Gower model takes the multi-kernel route for a tail block of <= 8 candidates.  In the two-lane scoring pass that block runs
+    on the second lane's stream; its triangular products used to be issued on the factor's own stream, unordered against the lane's
+    covariance rows (found by the random sweep with GPB_SKINNY_FUSED=0).  Device-buffer pass (two lanes) == host-buffer pass, bitwise."""
+    import torch
+    rs = np.random.RandomState(21)
+    n, d = 300, 4
+    X = rs.uniform(0, 1, (n, d))
+    X[:, 3] = rs.randint(0, 3, n)
+    Y = np.sin(3 * X.sum(1))[:, None] + 0.05 * rs.randn(n, 1)
+    nm = native.NativeModel("mat52", True, d, 1, n_cap=n, cand_block=128)
+    nm.set_data(X, Y)
+    nm.set_gower(([0, 1, 2], [3], [1.0, 1.5, 0.7]))
+    nm.set_theta(1.2, np.ones(d), 1e-2)
+    assert nm.fit(False)[0] == 0
+    fmin = nm.fmin()
+    for M in (128 * 2 + 3, 128 * 3 + 8, 128 + 1):
+        Xc = rs.uniform(0, 1, (M, d))
+        Xc[:, 3] = rs.randint(0, 3, M)
+        for rep in range(3):
+            a = nm.acq_topk_full("EI", 0.01, fmin, Xc, 5)
+            b = nm.acq_topk_full("EI", 0.01, fmin, torch.from_numpy(Xc).cuda(), 5)
+            for i in range(3):
+                assert np.array_equal(a[i], b[i]), (M, rep, i)
+            assert np.array_equal(a[3], b[3].cpu().numpy()) and np.array_equal(a[4], b[4].cpu().numpy()), (M, rep)
+    nm.close()
